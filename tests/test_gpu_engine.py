@@ -1,0 +1,350 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the oracle on identical
+seeded inputs.  Tolerances: inputs are bf16-representable, so the fp32 paths (K1 dense scan,
+K3 sparse, K4 fusion) must agree with the oracle to fp32 summation error (1e-5); the
+tensor-core path (K2) rounds the unit query to bf16 and is held to the north_star's stated
+1e-3 relative tie tolerance."""
+import math
+
+import numpy as np
+import pytest
+
+import _data
+import _coded
+from _parity import assert_same_ranking, assert_topk_valid
+from oracle import oracle as O
+from oracle import oracle_c
+
+pytestmark = pytest.mark.gpu
+
+FZ = {"weighted": 1, "rrf": 2}
+
+
+def make_index(coded, dim, **opts):
+    from voitta_rag_b200 import engine
+    ix = engine.Index(dim)
+    ix.upsert(coded["dense"], coded["csr"], coded["scope"], coded["created"], coded["modified"])
+    for k, v in opts.items():
+        ix.set_option(k, v)
+    return ix
+
+
+@pytest.fixture(scope="module")
+def world():
+    from voitta_rag_b200 import engine
+    n, dim = 20000, 64
+    corpus = _data.make_corpus(seed=3, n=n, dim=dim, n_index=6, per_index=6, vocab=3000)
+    corpus["dense"][100] = corpus["dense"][99]          # exact tie
+    corpus["sparse"][100] = corpus["sparse"][99]
+    corpus["dense"][5] = 0.0
+    queries = _data.make_queries(seed=9, corpus=corpus, nq=12)
+    coded = _coded.code_corpus(corpus)
+    cc = oracle_c.CorpusC(coded["dense"], coded["csr"], coded["scope"], coded["created"], coded["modified"])
+    ix = make_index(coded, dim)
+    return dict(n=n, dim=dim, corpus=corpus, queries=queries, coded=coded, cc=cc, ix=ix, engine=engine)
+
+
+def filters_for(coded):
+    sl = coded["scope_list"]
+    folders = [f for f, _ in sl]
+    return [
+        None,
+        (_coded.scope_bits(sl, include=folders[:5]), 0, _coded.TS_MIN, _coded.TS_MAX),
+        (_coded.scope_bits(sl, exclude=folders[:2], disabled=["root3"]), 0, _coded.TS_MIN, _coded.TS_MAX),
+        (None, 2, 1500000000, 1650000000),
+        (_coded.scope_bits(sl, include=folders[3:20]), 1, 1450000000, _coded.TS_MAX),
+        (_coded.scope_bits(sl, include=[folders[-1]]), 2, 1766000000, 1767225600),   # ~nothing passes
+    ]
+
+
+def run_both(w, qs, flt, limit, fusion, sparse_weight=0.1, use_sparse=True, **kw):
+    eng = w["engine"]
+    Q = np.stack([q for q, _ in qs])
+    SP = [s for _, s in qs] if use_sparse else None
+    B = len(qs)
+    gf = None if flt is None else [eng.Filter(flt[0], flt[1], flt[2], flt[3])]
+    fo = None if flt is None else np.zeros(B, np.int32)
+    got = w["ix"].search_batch(Q, SP, gf, fo, limit=limit, fusion=fusion if use_sparse else "dense",
+                               sparse_weight=sparse_weight, branches=True, **kw)
+    want = w["cc"].search_batch(Q, SP, None if flt is None else [flt], fo, limit=limit,
+                                kprime=got.dense_rows.shape[1],
+                                fusion=FZ[fusion] if use_sparse else 0, sparse_weight=sparse_weight)
+    return got, want
+
+
+def check(got, want, B, tol, what):
+    for i in range(B):
+        gd = got.branch(i, "dense")
+        wd = [(int(want["dense_rows"][i, j]), float(want["dense_scores"][i, j])) for j in range(want["dense_counts"][i])]
+        assert_same_ranking(gd, wd, rel_tol=tol, abs_tol=tol, what=f"{what} dense q{i}")
+        gs = got.branch(i, "sparse")
+        ws = [(int(want["sparse_rows"][i, j]), float(want["sparse_scores"][i, j])) for j in range(want["sparse_counts"][i])]
+        assert_same_ranking(gs, ws, rel_tol=0.0, what=f"{what} sparse q{i}")      # fp64 ordered sums: bit-equal
+        gf = got.hits(i)
+        wf = [(int(want["rows"][i, j]), float(want["scores"][i, j])) for j in range(want["counts"][i])]
+        assert_same_ranking(gf, wf, rel_tol=10 * tol, abs_tol=10 * tol, what=f"{what} fused q{i}")
+
+
+def fusion_bit_exact(got, i, limit, fusion, w):
+    """K4 against the Python oracle's fusion, fed the GPU's own branch lists: ids, order and
+    fp64 scores must be identical."""
+    d = [O.ScoredPoint(str(r), s, {}, r) for r, s in got.branch(i, "dense")]
+    s = [O.ScoredPoint(str(r), sc, {}, r) for r, sc in got.branch(i, "sparse")]
+    if fusion == "rrf":
+        want = O.reciprocal_rank_fusion([d, s], limit)
+    else:
+        want = O.weighted_fusion(d, s, limit, w)
+    assert [(int(pid), sc) for pid, sc, _ in want] == got.hits(i)
+
+
+@pytest.mark.parametrize("fusion", ["weighted", "rrf"])
+@pytest.mark.parametrize("fi", range(6))
+def test_single_query_hybrid_filtered(world, fusion, fi):
+    flt = filters_for(world["coded"])[fi]
+    for qi in range(6):
+        got, want = run_both(world, world["queries"][qi:qi + 1], flt, 10, fusion, 0.3)
+        check(got, want, 1, 1e-5, f"{fusion} f{fi} q{qi}")
+        fusion_bit_exact(got, 0, 10, fusion, 0.3)
+    assert world["ix"].stats()["last_dense_path"] == 1
+
+
+def test_dense_only_and_limits(world):
+    for limit in (1, 10, 100, 341):
+        got, want = run_both(world, world["queries"][:3], None, limit, "weighted", use_sparse=False)
+        for i in range(3):
+            wf = [(int(want["rows"][i, j]), float(want["scores"][i, j])) for j in range(want["counts"][i])]
+            assert_same_ranking(got.hits(i), wf, rel_tol=1e-5, abs_tol=1e-6, what=f"limit {limit}")
+
+
+def test_weights_and_spread_zero(world):
+    for w_sparse in (0.0, 0.5, 1.0):
+        got, want = run_both(world, world["queries"][:4], None, 5, "weighted", w_sparse)
+        check(got, want, 4, 1e-5, f"w={w_sparse}")
+        for i in range(4):
+            fusion_bit_exact(got, i, 5, "weighted", w_sparse)
+    # a single sparse hit => spread == 0 => normalised score 1.0 (vector_store.py:667)
+    corpus = world["corpus"]
+    df = {}
+    for idx, _ in corpus["sparse"]:
+        for t in idx:
+            df[t] = df.get(t, 0) + 1
+    t1 = next(t for t, c in sorted(df.items()) if c == 1)
+    q = world["queries"][0][0]
+    got, want = run_both(world, [(q, ([t1], [1.0]))], None, 10, "weighted", 0.4)
+    assert got.sparse_counts[0] == 1
+    check(got, want, 1, 1e-5, "single sparse hit")
+    fusion_bit_exact(got, 0, 10, "weighted", 0.4)
+    # absent term => empty sparse list
+    got, want = run_both(world, [(q, ([2**31 - 7], [1.0]))], None, 10, "rrf")
+    assert got.sparse_counts[0] == 0
+    check(got, want, 1, 1e-5, "absent term")
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_batch_paths(world, path):
+    """B = 12 through the GEMV scan (K1, one pass per query) and the tcgen05 GEMM (K2)."""
+    ix = world["ix"]
+    ix.set_option("dense_path", path)
+    try:
+        tol = 1e-5 if path == 1 else 1e-3
+        for fi in (0, 1, 3):
+            flt = filters_for(world["coded"])[fi]
+            got, want = run_both(world, world["queries"], flt, 10, "rrf")
+            assert ix.stats()["last_dense_path"] == path
+            B = len(world["queries"])
+            for i in range(B):
+                gd = got.branch(i, "dense")
+                wd = [(int(want["dense_rows"][i, j]), float(want["dense_scores"][i, j])) for j in range(want["dense_counts"][i])]
+                assert_same_ranking(gd, wd, rel_tol=tol, abs_tol=tol, what=f"path {path} f{fi} dense q{i}")
+                fusion_bit_exact(got, i, 10, "rrf", 0.1)
+    finally:
+        ix.set_option("dense_path", 0)
+
+
+def test_per_query_filters_in_one_batch(world):
+    eng = world["engine"]
+    fl = [f for f in filters_for(world["coded"]) if f is not None]
+    qs = world["queries"][:10]
+    Q = np.stack([q for q, _ in qs])
+    SP = [s for _, s in qs]
+    fo = np.array([i % (len(fl) + 1) - 1 for i in range(len(qs))], np.int32)    # -1 = unfiltered
+    for path in (1, 2):
+        world["ix"].set_option("dense_path", path)
+        got = world["ix"].search_batch(Q, SP, [eng.Filter(*f) for f in fl], fo, limit=10, fusion="weighted", branches=True)
+        want = world["cc"].search_batch(Q, SP, fl, fo, limit=10, kprime=30, fusion=1)
+        tol = 1e-5 if path == 1 else 1e-3
+        for i in range(len(qs)):
+            wd = [(int(want["dense_rows"][i, j]), float(want["dense_scores"][i, j])) for j in range(want["dense_counts"][i])]
+            assert_same_ranking(got.branch(i, "dense"), wd, rel_tol=tol, abs_tol=tol, what=f"path{path} q{i}")
+            ws = [(int(want["sparse_rows"][i, j]), float(want["sparse_scores"][i, j])) for j in range(want["sparse_counts"][i])]
+            assert_same_ranking(got.branch(i, "sparse"), ws, rel_tol=0.0, what=f"path{path} sparse q{i}")
+    world["ix"].set_option("dense_path", 0)
+
+
+def test_segmentation_does_not_change_results(world):
+    """Exactness is independent of the segment schedule (and of the safe mode)."""
+    ix = world["ix"]
+    qs = world["queries"][:6]
+    Q = np.stack([q for q, _ in qs]); SP = [s for _, s in qs]
+    base = ix.search_batch(Q, SP, limit=20, fusion="weighted", branches=True)
+    try:
+        for opts in ({"seg_ratio": 2}, {"seg_first": 16384, "seg_ratio": 2}, {"safe_mode": 1}):
+            for k, v in opts.items():
+                ix.set_option(k, v)
+            r = ix.search_batch(Q, SP, limit=20, fusion="weighted", branches=True)
+            for name in ("rows", "scores", "counts", "dense_rows", "dense_scores", "sparse_rows", "sparse_scores"):
+                assert np.array_equal(getattr(r, name), getattr(base, name)), (opts, name)
+            ix.set_option("safe_mode", 0); ix.set_option("seg_first", 8192); ix.set_option("seg_ratio", 32)
+    finally:
+        ix.set_option("safe_mode", 0); ix.set_option("seg_first", 8192); ix.set_option("seg_ratio", 32)
+
+
+def test_deletes_update_mask_n_and_df(world):
+    coded, dim = world["coded"], world["dim"]
+    ix = make_index(coded, dim)
+    rng = np.random.RandomState(1)
+    dead = rng.choice(world["n"], size=3000, replace=False)
+    ix.delete_rows(dead)
+    alive = np.ones(world["n"], np.uint8); alive[dead] = 0
+    cc = oracle_c.CorpusC(coded["dense"], coded["csr"], coded["scope"], coded["created"], coded["modified"], alive)
+    df, n_live = ix.term_stats(np.array([t for t in world["queries"][0][1][0]], np.uint32))
+    assert n_live == world["n"] - 3000
+    for t, d in zip(world["queries"][0][1][0], df):
+        assert cc.df(t) == int(d)
+    w2 = dict(world, ix=ix, cc=cc)
+    for fi in (0, 1):
+        got, want = run_both(w2, world["queries"][:5], filters_for(coded)[fi], 10, "weighted")
+        check(got, want, 5, 1e-5, f"after delete f{fi}")
+        assert not (set(int(r) for r in got.rows.ravel()) & set(int(x) for x in dead)) or got.counts.sum() == 0
+    # append after delete, search again
+    ix.upsert(coded["dense"][:500], (coded["csr"][0][:501], coded["csr"][1][:coded["csr"][0][500]], coded["csr"][2][:coded["csr"][0][500]]),
+              coded["scope"][:500], coded["created"][:500], coded["modified"][:500])
+    assert ix.stats()["n_rows"] == world["n"] + 500 and ix.stats()["n_live"] == world["n"] - 3000 + 500
+    ix.close()
+
+
+def test_overflow_falls_back_to_safe_mode_and_stays_exact():
+    """Adversarial order (scores strictly increasing with the row id) floods the candidate lists;
+    the library must notice, re-run in safe mode and still return the exact answer."""
+    from voitta_rag_b200 import engine
+    n, dim = 300000, 64
+    theta = np.linspace(1.5, 0.05, n).astype(np.float64)
+    dense = np.zeros((n, dim), np.float32)
+    dense[:, 0] = np.cos(theta); dense[:, 1] = np.sin(theta)
+    dense = _data.bf16_round(dense)
+    ix = engine.Index(dim)
+    ix.upsert(dense)
+    q = np.zeros(dim, np.float32); q[0] = 1.0
+    r = ix.search_batch(q[None, :], limit=10)
+    assert ix.stats()["overflow_reruns"] == 1
+    v = dense.astype(np.float64)
+    scores = (v[:, 0] / np.linalg.norm(v, axis=1)).astype(np.float32)
+    assert_topk_valid(r.hits(0), scores, np.ones(n, bool), 10, rel_tol=1e-6, abs_tol=1e-6, what="ascending corpus")
+    ix.close()
+
+
+@pytest.mark.parametrize("dim", [100, 384, 768, 1024, 1536])
+def test_dimensions_and_padding(dim):
+    from voitta_rag_b200 import engine
+    rng = np.random.RandomState(dim)
+    n = 4000
+    dense = _data.bf16_round(rng.randn(n, dim).astype(np.float32))
+    Q = _data.bf16_round(rng.randn(5, dim).astype(np.float32))
+    ix = engine.Index(dim)
+    ix.upsert(dense)
+    cc = oracle_c.CorpusC(dense)
+    want = cc.search_batch(Q, None, limit=10, fusion=0)
+    for path, tol in ((1, 1e-5), (2, 1e-3)):
+        ix.set_option("dense_path", path)
+        got = ix.search_batch(Q, limit=10)
+        for i in range(5):
+            wf = [(int(want["rows"][i, j]), float(want["scores"][i, j])) for j in range(want["counts"][i])]
+            assert_same_ranking(got.hits(i), wf, rel_tol=tol, abs_tol=tol, what=f"dim {dim} path {path} q{i}")
+    ix.close()
+
+
+def test_two_shards_merge_equals_single_index(world):
+    """Row-sharded search emulated on one GPU: two indexes with row offsets, global
+    IDF from summed df, candidates concatenated as an all-gather would, merged and fused.  Must be
+    bit-identical to the single-index answer."""
+    import torch
+    eng, coded, dim, n = world["engine"], world["coded"], world["dim"], world["n"]
+    half = 8192 + 1000
+    ip, tm, vl = coded["csr"]
+    a = eng.Index(dim, row_base=0)
+    a.upsert(coded["dense"][:half], (ip[:half + 1], tm[:ip[half]], vl[:ip[half]]), coded["scope"][:half],
+             coded["created"][:half], coded["modified"][:half])
+    b = eng.Index(dim, row_base=half)
+    b.upsert(coded["dense"][half:], (ip[half:] - ip[half], tm[ip[half]:], vl[ip[half]:]), coded["scope"][half:],
+             coded["created"][half:], coded["modified"][half:])
+    qs = world["queries"][:8]
+    Q = np.stack([q for q, _ in qs]); SP = [s for _, s in qs]
+    flt = filters_for(coded)[1]
+    gf, fo = [eng.Filter(*flt)], np.zeros(len(qs), np.int32)
+    # global IDF: df summed over shards, N = total live
+    SPW = []
+    for idx, val in SP:
+        t = np.asarray(idx, np.uint32)
+        dfa, na = a.term_stats(t); dfb, nb = b.term_stats(t)
+        N = na + nb
+        wts = [float(v) * math.log((N - float(d) + 0.5) / (float(d) + 0.5) + 1.0) for v, d in zip(val, (dfa + dfb))]
+        SPW.append((idx, wts))
+    limit, k = 10, 30
+    for fusion in ("weighted", "rrf"):
+        single = world["ix"].search_batch(Q, SP, gf, fo, limit=limit, fusion=fusion, branches=True)
+        bufs = [torch.zeros(2 * len(qs) * k, dtype=torch.int64, device="cuda") for _ in range(2)]
+        a.search_local(bufs[0].data_ptr(), Q, SPW, gf, fo, limit=limit, kprime=k, fusion=fusion)
+        b.search_local(bufs[1].data_ptr(), Q, SPW, gf, fo, limit=limit, kprime=k, fusion=fusion)
+        gathered = torch.cat(bufs)
+        torch.cuda.synchronize()
+        merged = a.merge_fuse(gathered.data_ptr(), 2, Q, SPW, limit=limit, kprime=k, fusion=fusion, branches=True)
+        for name in ("rows", "counts", "dense_rows", "dense_scores", "dense_counts", "sparse_rows", "sparse_counts"):
+            assert np.array_equal(getattr(merged, name), getattr(single, name)), (fusion, name)
+        # idf computed by numpy here vs libm in the library may differ in the last bit of a weight
+        np.testing.assert_allclose(merged.sparse_scores, single.sparse_scores, rtol=1e-6)
+        np.testing.assert_allclose(merged.scores, single.scores, rtol=1e-6, atol=1e-9)
+    a.close(); b.close()
+
+
+def test_upsert_dev_matches_host_upsert(world):
+    import torch
+    eng, coded, dim = world["engine"], world["coded"], world["dim"]
+    n = 9000
+    ip, tm, vl = coded["csr"]
+    rows = torch.from_numpy(coded["dense"][:n]).cuda().to(torch.bfloat16).contiguous()
+    t_ip = torch.from_numpy(ip[:n + 1].copy()).cuda(); t_tm = torch.from_numpy(tm[:ip[n]].astype(np.int32)).cuda()
+    t_vl = torch.from_numpy(vl[:ip[n]].copy()).cuda()
+    t_sc = torch.from_numpy(coded["scope"][:n].astype(np.int32)).cuda()
+    t_cr = torch.from_numpy(coded["created"][:n].copy()).cuda(); t_mo = torch.from_numpy(coded["modified"][:n].copy()).cuda()
+    torch.cuda.synchronize()
+    d = eng.Index(dim)
+    d.upsert_dev(n, rows.data_ptr(), t_ip.data_ptr(), t_tm.data_ptr(), t_vl.data_ptr(), t_sc.data_ptr(),
+                 t_cr.data_ptr(), t_mo.data_ptr())
+    h = eng.Index(dim)
+    h.upsert(coded["dense"][:n], (ip[:n + 1], tm[:ip[n]], vl[:ip[n]]), coded["scope"][:n], coded["created"][:n], coded["modified"][:n])
+    qs = world["queries"][:4]
+    Q = np.stack([q for q, _ in qs]); SP = [s for _, s in qs]
+    flt = filters_for(coded)[4]
+    ra = d.search_batch(Q, SP, [eng.Filter(*flt)], np.zeros(4, np.int32), limit=10, fusion="rrf", branches=True)
+    rb = h.search_batch(Q, SP, [eng.Filter(*flt)], np.zeros(4, np.int32), limit=10, fusion="rrf", branches=True)
+    for name in ("rows", "scores", "counts", "dense_rows", "dense_scores", "sparse_rows", "sparse_scores"):
+        assert np.array_equal(getattr(ra, name), getattr(rb, name)), name
+    d.close(); h.close()
+
+
+def test_edge_cases(world):
+    eng = world["engine"]
+    e = eng.Index(16)
+    r = e.search_batch(np.ones((2, 16), np.float32), limit=5)
+    assert r.counts.tolist() == [0, 0]                                  # empty index
+    e.upsert(np.eye(16, dtype=np.float32)[:3])                          # fewer rows than k
+    r = e.search_batch(np.ones((1, 16), np.float32), [([1, 2], [1.0, 1.0])], limit=5, fusion="rrf", branches=True)
+    assert r.counts[0] == 3 and r.sparse_counts[0] == 0
+    with pytest.raises(ValueError):
+        e.search_batch(np.full((1, 16), np.nan, np.float32))
+    with pytest.raises(eng.B200Error):
+        e.search_batch(np.ones((1, 16), np.float32), limit=400, kprime=1200)
+    with pytest.raises(eng.B200Error):
+        e.search_batch(np.ones((1, 16), np.float32), [([3, 3], [1.0, 1.0])], limit=5)   # repeated sparse index
+    with pytest.raises(eng.B200Error):
+        e.delete_rows([99])
+    e.close()

@@ -1,0 +1,95 @@
+"""Host layer of the drop-in (voitta_rag_b200.vector_store) on a CPU box: the reference's
+recorded behaviour (tests/golden) replayed through VectorStoreService over a test-double index.
+Checks the 22-method surface, payload/id bookkeeping, filter folding and error conventions."""
+import inspect
+import json
+from pathlib import Path
+
+import pytest
+
+from golden import make_golden as G
+from _fake_index import FakeIndex
+from _parity import assert_same_ranking
+from voitta_rag_b200 import vector_store as VS
+
+GOLD = json.loads((Path(__file__).parent / "golden" / "voitta_cases.json").read_text())
+
+
+@pytest.fixture()
+def store(monkeypatch):
+    monkeypatch.setenv("QDRANT_COLLECTION", "host_layer_test")
+    monkeypatch.setenv("EMBEDDING_DIMENSION", str(GOLD["dim"]))
+    VS._drop_collection("host_layer_test")
+    s = VS.VectorStoreService(_index_factory=lambda: FakeIndex(GOLD["dim"]))
+    yield s
+    VS._drop_collection("host_layer_test")
+
+
+def check_outputs(outs):
+    assert len(outs) == len(GOLD["outs"])
+    for i, (op, got, want) in enumerate(zip(GOLD["ops"], outs, GOLD["outs"])):
+        what = f"op {i} {op}"
+        if op["op"] == "search":
+            assert_same_ranking(got, want, rel_tol=1e-5, abs_tol=2e-6, what=what)
+            for g, w in zip(got, want):
+                if g[0] == w[0]:
+                    assert g[2:] == w[2:], what
+        else:
+            assert json.loads(json.dumps(got)) == want, what
+
+
+def test_golden_replay_through_host_layer(store):
+    corpus, queries = G.build_inputs()
+    outs = G.replay(store, GOLD["ops"], corpus, queries, VS.ChunkMetadata, {})
+    check_outputs(outs)
+
+
+def test_surface_matches_reference_signatures():
+    """Names, positional order and defaults of SURVEY.md §8(b)."""
+    sig = inspect.signature(VS.VectorStoreService.search)
+    assert list(sig.parameters) == ["self", "query_embedding", "limit", "folder_filter", "include_folders",
+                                    "exclude_folders", "exclude_index_folders", "sparse_query", "sparse_weight",
+                                    "date_start", "date_end", "date_field"]
+    assert sig.parameters["limit"].default == 10 and sig.parameters["sparse_weight"].default == 0.1
+    sig = inspect.signature(VS.VectorStoreService.store_chunks)
+    assert list(sig.parameters) == ["self", "chunks", "sparse_vectors", "batch_size"]
+    assert sig.parameters["batch_size"].default == 100
+    for name in ["find_by_source_url", "set_file_acl", "store_chunks", "delete_by_file", "delete_by_folder",
+                 "delete_by_index_folder", "get_file_paths_by_index_folder", "_build_filter", "search",
+                 "get_collection_info", "count_by_file", "count_chunks_for_files", "count_chunks_for_folder",
+                 "get_folder_stats_batch", "get_stored_page_count", "get_chunks_by_range", "get_file_chunk_counts"]:
+        assert callable(getattr(VS.VectorStoreService, name)), name
+    fields = [f for f in VS.ChunkMetadata.__dataclass_fields__]
+    assert fields == ["file_path", "folder_path", "index_folder", "file_name", "chunk_index", "total_chunks",
+                      "start_char", "end_char", "indexed_at", "start_page", "end_page", "source_page_count",
+                      "source_created_at", "source_modified_at", "allowed_users", "source_url"]
+    assert [f for f in VS.StoredChunk.__dataclass_fields__] == ["id", "text", "metadata", "score"]
+    assert VS.get_vector_store() is VS.get_vector_store()
+
+
+def test_second_instance_sees_same_collection(store):
+    corpus, queries = G.build_inputs()
+    G.replay(store, GOLD["ops"][:1], corpus, queries, VS.ChunkMetadata, {})
+    other = VS.VectorStoreService(_index_factory=lambda: FakeIndex(GOLD["dim"]))   # folders.py:139-141 does this
+    assert other.count_by_file(corpus["metas"][0]["file_path"]) == 3
+    assert other.delete_by_index_folder("root0") > 0
+    assert store.count_by_file(corpus["metas"][0]["file_path"]) in (0, 3)
+
+
+def test_error_conventions(store):
+    assert store.store_chunks([]) == []
+    assert store.search([0.0] * GOLD["dim"]) == []              # empty collection
+    assert store.count_by_file("x") == 0 and store.count_chunks_for_files([]) == {}
+    assert store.get_folder_stats_batch([]) == {} and store.get_stored_page_count("x") is None
+    assert store.delete_by_file("x") == 0 and store.find_by_source_url("x") == []
+    m = VS.ChunkMetadata("a/f", "a", "a", "f", 0, 1, 0, 1, "t")
+    with pytest.raises(ValueError):
+        store.store_chunks([("t", [0.0] * 3, m)])               # wrong dimension propagates
+    with pytest.raises(ValueError):
+        store.store_chunks([("t", [1.0] * GOLD["dim"], m)], [([5, 5], [1.0, 1.0])])   # duplicate sparse index
+    store.store_chunks([("t", [1.0] * GOLD["dim"], m)], [([9, 5], [1.0, 2.0])])
+    with pytest.raises(ValueError):
+        store.search([0.0] * 3)
+    assert store._build_filter() is None and store._build_filter(include_folders=[]) is None
+    f = store._build_filter(include_folders=["a"], date_end=5, date_field="created")
+    assert f.ts_field == 1 and f.ts_hi == 5 and f.scope_bits[0] == 1

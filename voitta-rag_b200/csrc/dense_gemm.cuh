@@ -1,0 +1,352 @@
+// K2 — batched dense scoring on the 5th-gen tensor cores (tcgen05 + TMEM, TMA-fed) with the
+// filter bitmask and the top-k' threshold fused into the epilogue: the B x N score matrix is
+// never written to memory.
+// Replaces qdrant's cosine scoring for a BATCH of query_points(query=vec, limit=k', filter)
+// calls (vector_store.py:640-645).  voitta issues B = 1; batches come from search_batch().
+//
+// Shape: D[128 rows, BN queries] = A[128 x d] (corpus tile, bf16, K-major) * Q[BN x d]^T
+//   - persistent kernel, one CTA per SM, tiles of 128 corpus rows, round-robin over CTAs;
+//   - warp 0: TMA producer — corpus tiles stream through an S-stage ring of 128x64 bf16 boxes
+//     (16 KB, 128B swizzle), the query matrix is loaded once and stays resident in smem;
+//   - warp 1: allocates TMEM (512 columns) and issues tcgen05.mma (M=128, N=BN, K=16) from one
+//     elected lane; accumulators are double buffered in TMEM (2 x 256 columns);
+//   - warps 2-5: epilogue — tcgen05.ld the accumulator (lane = corpus row, column = query),
+//     score = acc * inv_norm[row], test the filter bit and the per-query threshold tau, and
+//     append survivors to the query's candidate list (warp-ballot skips the common no-survivor
+//     case).  vb_compact_kernel then selects the exact top-k'.
+// Roofline: HBM for BN <~ 250 (one pass over the bf16 corpus per sub-batch), tensor pipe above.
+// Algorithmic bytes per launch = rows*(d_pad*2 + 4) + mask words; flops = 2*rows*BN*d_pad.
+#pragma once
+#include "common.cuh"
+#include <cuda.h>
+#include <string>
+
+#define VB_GEMM_THREADS 192
+#define VB_TILE_M 128u
+#define VB_BLOCK_K 64u
+#define VB_STAGE_BYTES (VB_TILE_M * VB_BLOCK_K * 2u)   // 16 KB
+#define VB_GEMM_MAX_FILTERS 256u
+
+static std::string g_gemm_err;
+static const char* vb_gemm_last_error() { return g_gemm_err.c_str(); }
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t vb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void vb_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void vb_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void vb_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void vb_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void vb_tma_load_2d(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void vb_tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void vb_tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void vb_tcgen05_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void vb_tcgen05_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 16 consecutive columns, one fp32 per (lane, column)
+__device__ __forceinline__ void vb_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void vb_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 B apart
+// (bits: [0,14) addr>>4, [16,30) LBO>>4 = 0, [32,46) SBO>>4 = 64, [46,48) version = 1,
+//  [61,64) layout = 2 (SWIZZLE_128B)).
+__device__ __forceinline__ uint64_t vb_umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// UMMA instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major, M = 128, N = bn
+__host__ __device__ __forceinline__ uint32_t vb_umma_idesc(uint32_t bn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((bn >> 3) << 17) | ((VB_TILE_M >> 4) << 24);
+}
+
+struct VbGemmArgs {
+    const float* inv_norm;
+    const uint32_t* mask;      // [n_filters][mask_words] or nullptr
+    const int32_t* mask_of;    // [B_total] or nullptr
+    const float* tau;          // [n_lists]
+    uint64_t* cand;
+    uint32_t* cnt;
+    uint32_t mask_words, n_filters;
+    uint32_t cap;
+    uint32_t tile_begin, tile_end;   // 128-row tiles of this segment
+    uint32_t row_end;                // rows >= row_end are not part of the segment
+    uint32_t row_base;
+    uint32_t k_blocks;               // d_pad / 64
+    uint32_t bn;                     // padded sub-batch (multiple of 16, <= 256)
+    uint32_t n_q;                    // real queries in this sub-batch
+    uint32_t q_begin;                // first query (list index) of the sub-batch
+    uint32_t stages;
+};
+
+__global__ void __launch_bounds__(VB_GEMM_THREADS, 1)
+vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_q,
+                     const VbGemmArgs a)
+{
+    extern __shared__ unsigned char vb_gemm_smem_raw[];
+    // 1024-byte alignment for the 128B-swizzle atoms
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)vb_gemm_smem_raw + 1023u) & ~(uintptr_t)1023u);
+    const uint32_t q_bytes = a.bn * a.k_blocks * 128u;                       // resident query matrix
+    unsigned char* smem_q = smem;
+    unsigned char* smem_a = smem + q_bytes;                                   // stages * 16 KB (q_bytes % 1024 == 0)
+    unsigned char* tail = smem_a + a.stages * VB_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);                       // full[S], empty[S], tfull[2], tempty[2], qfull
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tail + 8u * (2u * 16u + 5u));
+    float* tau_s = reinterpret_cast<float*>(tail + 8u * (2u * 16u + 5u) + 16u);   // [256]
+    int32_t* mof_s = reinterpret_cast<int32_t*>(tau_s + 256);                     // [256]
+    uint32_t* mw_s = reinterpret_cast<uint32_t*>(mof_s + 256);                    // [4 warps][VB_GEMM_MAX_FILTERS]
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t S = a.stages;
+    const uint32_t bar_full = vb_smem_u32(bars), bar_empty = bar_full + 8u * 16u;
+    const uint32_t bar_tfull = bar_full + 8u * 32u, bar_tempty = bar_tfull + 16u, bar_q = bar_tfull + 32u;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            for (uint32_t s = 0; s < S; ++s) { vb_mbar_init(bar_full + 8u * s, 1); vb_mbar_init(bar_empty + 8u * s, 1); }
+            for (uint32_t s = 0; s < 2; ++s) { vb_mbar_init(bar_tfull + 8u * s, 1); vb_mbar_init(bar_tempty + 8u * s, 4); }
+            vb_mbar_init(bar_q, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(vb_smem_u32(tmem_ptr)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (uint32_t c = threadIdx.x; c < 256u; c += blockDim.x) {
+        const bool live = c < a.n_q;
+        tau_s[c] = live ? a.tau[a.q_begin + c] : INFINITY;
+        mof_s[c] = (live && a.mask_of) ? a.mask_of[a.q_begin + c] : -1;
+    }
+    vb_tcgen05_fence_before();
+    __syncthreads();
+    vb_tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const uint32_t n_tiles = a.tile_end - a.tile_begin;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            vb_mbar_expect_tx(bar_q, q_bytes);
+            for (uint32_t kb = 0; kb < a.k_blocks; ++kb)
+                vb_tma_load_2d(vb_smem_u32(smem_q + kb * a.bn * 128u), &tmap_q, (int32_t)(kb * VB_BLOCK_K), 0, bar_q);
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int32_t row0 = (int32_t)((a.tile_begin + t) * VB_TILE_M);
+                for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
+                    vb_mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
+                    vb_mbar_expect_tx(bar_full + 8u * stage, VB_STAGE_BYTES);
+                    vb_tma_load_2d(vb_smem_u32(smem_a + stage * VB_STAGE_BYTES), &tmap_a, (int32_t)(kb * VB_BLOCK_K), row0, bar_full + 8u * stage);
+                    if (++stage == S) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one elected lane) =====
+        if (lane == 0) {
+            const uint32_t idesc = vb_umma_idesc(a.bn);
+            vb_mbar_wait(bar_q, 0);
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+                const uint32_t acc = it & 1u;
+                vb_mbar_wait(bar_tempty + 8u * acc, ((it >> 1) & 1u) ^ 1u);
+                vb_tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * 256u;
+                for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
+                    vb_mbar_wait(bar_full + 8u * stage, phase);
+                    vb_tcgen05_fence_after();
+                    const uint32_t a_addr = vb_smem_u32(smem_a + stage * VB_STAGE_BYTES);
+                    const uint32_t q_addr = vb_smem_u32(smem_q + kb * a.bn * 128u);
+#pragma unroll
+                    for (uint32_t k = 0; k < VB_BLOCK_K / 16u; ++k)
+                        vb_tcgen05_mma_bf16(tmem_d, vb_umma_desc(a_addr + k * 32u), vb_umma_desc(q_addr + k * 32u), idesc, (kb | k) != 0u);
+                    vb_tcgen05_commit(bar_empty + 8u * stage);     // smem stage free once these MMAs retire
+                    if (++stage == S) { stage = 0; phase ^= 1u; }
+                }
+                vb_tcgen05_commit(bar_tfull + 8u * acc);           // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..5; TMEM lane quadrant = warp % 4 =====
+        const uint32_t quad = warp & 3u;
+        uint32_t* mw = mw_s + quad * VB_GEMM_MAX_FILTERS;
+        const bool has_mask = a.mask != nullptr;
+        uint32_t it = 0;
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            const uint32_t acc = it & 1u;
+            const uint32_t tile = a.tile_begin + t;
+            const uint32_t row = tile * VB_TILE_M + quad * 32u + lane;
+            const bool row_ok = row < a.row_end;
+            // issue the global loads before blocking on the accumulator
+            const float invn = row_ok ? a.inv_norm[row] : 0.0f;
+            if (has_mask) {
+                const uint32_t word = tile * 4u + quad;
+                for (uint32_t f = lane; f < a.n_filters; f += 32u)
+                    mw[f] = word < a.mask_words ? a.mask[(size_t)f * a.mask_words + word] : 0u;
+                __syncwarp();
+            }
+            vb_mbar_wait(bar_tfull + 8u * acc, (it >> 1) & 1u);
+            vb_tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * 256u;
+            for (uint32_t c0 = 0; c0 < a.bn; c0 += 16u) {
+                uint32_t v[16];
+                vb_tmem_ld16(taddr + c0, v);
+                vb_tmem_ld_wait();
+#pragma unroll
+                for (uint32_t j = 0; j < 16u; ++j) {
+                    const uint32_t col = c0 + j;
+                    const float s = __uint_as_float(v[j]) * invn;
+                    bool pass = row_ok && s > tau_s[col];          // tau = +inf for padded columns
+                    if (has_mask) {
+                        const int32_t f = mof_s[col];
+                        if (f >= 0) pass = pass && ((mw[f] >> lane) & 1u);
+                    }
+                    if (__ballot_sync(0xffffffffu, pass) != 0u) {
+                        if (pass) vb_push(a.cand, a.cnt, a.cap, a.q_begin + col, s, a.row_base + row);
+                    }
+                }
+            }
+            vb_tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) vb_mbar_arrive(bar_tempty + 8u * acc);
+        }
+    }
+    vb_tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        vb_tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*VbEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static VbEncodeTiledFn g_encode_tiled = nullptr;
+static int g_gemm_smem_max = 0;
+
+static int vb_gemm_configure() {
+    if (g_encode_tiled) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+        g_gemm_err = "cuTensorMapEncodeTiled not available from the driver";
+        return 1;
+    }
+    int dev = 0, smem = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    e = cudaFuncSetAttribute(vb_dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { g_gemm_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
+    g_gemm_smem_max = smem;
+    g_encode_tiled = reinterpret_cast<VbEncodeTiledFn>(fn);
+    return 0;
+}
+
+static const uint32_t VB_GEMM_TAIL_BYTES = 8u * (2u * 16u + 5u) + 16u + 256u * 4u + 256u * 4u + 4u * VB_GEMM_MAX_FILTERS * 4u;
+
+// largest padded sub-batch whose resident query matrix leaves room for >= 4 stages
+static uint32_t vb_gemm_max_bn(uint32_t d_pad) {
+    const uint32_t avail = (uint32_t)g_gemm_smem_max - 1024u - VB_GEMM_TAIL_BYTES - 4u * VB_STAGE_BYTES;
+    uint32_t bn = avail / (d_pad * 2u);
+    bn = bn / 16u * 16u;
+    return bn > 256u ? 256u : bn;
+}
+
+static bool vb_gemm_supported(int d_pad, uint32_t B) {
+    (void)B;
+    return g_encode_tiled != nullptr && d_pad % 64 == 0 && vb_gemm_max_bn((uint32_t)d_pad) >= 16u;
+}
+
+struct VbGemmLaunch {
+    const void* rows;          // [n_rows_total][d_pad] bf16
+    const float* inv_norm;
+    const void* q_bf16;        // [>= round_up(B,16)][d_pad] bf16
+    const uint32_t* mask;
+    const int32_t* mask_of;
+    uint32_t mask_words, n_filters;
+    const float* tau;
+    uint64_t* cand;
+    uint32_t* cnt;
+    uint32_t cap;
+    uint32_t n_rows_total, row_begin, row_end, row_base, d_pad, n_queries;
+    int sm_count;
+    cudaStream_t stream;
+};
+
+static int vb_encode_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {VB_BLOCK_K, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { g_gemm_err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return 1; }
+    return 0;
+}
+
+static int vb_gemm_launch(const VbGemmLaunch& g, int* launches) {
+    if (!g_encode_tiled) { g_gemm_err = "tensor-core path not configured"; return 1; }
+    if (g.mask && g.n_filters > VB_GEMM_MAX_FILTERS) { g_gemm_err = "more than 256 distinct filters in one batch"; return 1; }
+    const uint32_t bn_max = vb_gemm_max_bn(g.d_pad);
+    CUtensorMap tmap_a;
+    if (vb_encode_2d(&tmap_a, g.rows, g.n_rows_total, g.d_pad, VB_TILE_M)) return 1;
+    for (uint32_t q0 = 0; q0 < g.n_queries; q0 += bn_max) {
+        const uint32_t n_q = std::min(bn_max, g.n_queries - q0);
+        const uint32_t bn = (n_q + 15u) / 16u * 16u;
+        CUtensorMap tmap_q;
+        if (vb_encode_2d(&tmap_q, reinterpret_cast<const unsigned char*>(g.q_bf16) + (size_t)q0 * g.d_pad * 2, bn, g.d_pad, bn)) return 1;
+        VbGemmArgs a{};
+        a.inv_norm = g.inv_norm; a.mask = g.mask; a.mask_of = g.mask_of; a.tau = g.tau; a.cand = g.cand; a.cnt = g.cnt;
+        a.mask_words = g.mask_words; a.n_filters = g.n_filters; a.cap = g.cap;
+        a.tile_begin = g.row_begin / VB_TILE_M; a.tile_end = (g.row_end + VB_TILE_M - 1) / VB_TILE_M;
+        a.row_end = g.row_end; a.row_base = g.row_base; a.k_blocks = g.d_pad / VB_BLOCK_K;
+        a.bn = bn; a.n_q = n_q; a.q_begin = q0;
+        const uint32_t q_bytes = bn * g.d_pad * 2u;
+        uint32_t stages = ((uint32_t)g_gemm_smem_max - 1024u - VB_GEMM_TAIL_BYTES - q_bytes) / VB_STAGE_BYTES;
+        a.stages = stages > 12u ? 12u : stages;
+        const size_t smem = 1024u + q_bytes + a.stages * VB_STAGE_BYTES + VB_GEMM_TAIL_BYTES;
+        const uint32_t tiles = a.tile_end - a.tile_begin;
+        const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)g.sm_count);
+        vb_dense_gemm_kernel<<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { g_gemm_err = std::string("launch failed: ") + cudaGetErrorString(e); return 1; }
+        ++*launches;
+    }
+    return 0;
+}

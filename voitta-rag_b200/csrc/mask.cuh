@@ -1,0 +1,117 @@
+// K0 — filter evaluation.  Replaces the payload-filter evaluation qdrant performs for
+// query_filter (vector_store.py:462-530 builds it; :612-617/:640-656 pass it).
+//
+// One pass over the per-row columns (scope id u32, one or two i64 timestamps, alive bits)
+// produces, for every distinct filter of the batch, a packed bitmask (bit r%32 of word r/32).
+// The scoring kernels K1/K2/K3 then apply the filter as a bitmask inside their loops.
+// HBM-bound: algorithmic bytes = n*(4 [+8 per timestamp column used]) + n/8 read,
+// n_filters*n/8 written.
+#pragma once
+#include "common.cuh"
+
+__global__ void __launch_bounds__(256)
+vb_mask_kernel(const uint32_t* __restrict__ scope_id, const int64_t* __restrict__ created,
+               const int64_t* __restrict__ modified, const uint32_t* __restrict__ alive,
+               uint32_t n_rows, const VbFilterDev* __restrict__ filters, uint32_t n_filters,
+               uint32_t words, uint32_t need_created, uint32_t need_modified, uint32_t need_scope,
+               uint32_t* __restrict__ out)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < words; w += warps) {
+        const uint32_t row = w * 32u + lane;
+        const bool valid = row < n_rows;
+        const uint32_t alive_w = alive[w];
+        const bool is_alive = valid && ((alive_w >> lane) & 1u);
+        uint32_t sid = 0;
+        int64_t tc = INT64_MIN, tm = INT64_MIN;
+        if (valid) {
+            if (need_scope) sid = scope_id[row];
+            if (need_created) tc = created[row];
+            if (need_modified) tm = modified[row];
+        }
+        for (uint32_t f = 0; f < n_filters; ++f) {
+            const VbFilterDev flt = filters[f];
+            bool pass = is_alive;
+            if (flt.scope_bits != nullptr) {
+                const uint32_t sw = sid >> 5;
+                pass = pass && sw < flt.scope_words && ((flt.scope_bits[sw] >> (sid & 31u)) & 1u);
+            }
+            if (flt.ts_field != 0) {
+                const int64_t t = (flt.ts_field == 1) ? tc : tm;
+                // a must-range on a missing field fails (payload_filters semantics)
+                pass = pass && t != INT64_MIN && t >= flt.ts_lo && t <= flt.ts_hi;
+            }
+            const uint32_t bits = __ballot_sync(0xffffffffu, pass);
+            if (lane == 0) out[(size_t)f * words + w] = bits;
+        }
+    }
+}
+
+// Ingest (K5): fp32 -> bf16 rows (zero padded to d_pad) + fp32 inverse norm of the ROUNDED row,
+// so that score = dot(bf16 row, q_hat) * inv_norm is the cosine against the stored point.
+// Replaces the normalise-at-upsert step of qdrant's COSINE distance (vector_store.py:93, :313).
+__global__ void __launch_bounds__(256)
+vb_ingest_f32_kernel(const float* __restrict__ src, uint32_t n, uint32_t dim, uint32_t d_pad,
+                     __nv_bfloat16* __restrict__ dst, float* __restrict__ inv_norm)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+        double ss = 0.0;
+        for (uint32_t c = lane; c < d_pad; c += 32u) {
+            __nv_bfloat16 b = __float2bfloat16_rn(c < dim ? src[(size_t)r * dim + c] : 0.0f);
+            dst[(size_t)r * d_pad + c] = b;
+            const double v = (double)__bfloat162float(b);
+            ss += v * v;
+        }
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) inv_norm[r] = ss > 0.0 ? (float)(1.0 / sqrt(ss)) : 0.0f;
+    }
+}
+
+// Same for rows that are already bf16 on the device (bulk loader): copy/pad + inverse norm.
+__global__ void __launch_bounds__(256)
+vb_ingest_bf16_kernel(const __nv_bfloat16* __restrict__ src, uint32_t n, uint32_t dim, uint32_t d_pad,
+                      __nv_bfloat16* __restrict__ dst, float* __restrict__ inv_norm)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+        double ss = 0.0;
+        for (uint32_t c = lane; c < d_pad; c += 32u) {
+            __nv_bfloat16 b = c < dim ? src[(size_t)r * dim + c] : __float2bfloat16_rn(0.0f);
+            dst[(size_t)r * d_pad + c] = b;
+            const double v = (double)__bfloat162float(b);
+            ss += v * v;
+        }
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) inv_norm[r] = ss > 0.0 ? (float)(1.0 / sqrt(ss)) : 0.0f;
+    }
+}
+
+// Query preparation: q_hat = q/||q|| in fp32 (zero vector stays zero), zero padded to d_pad;
+// also written as bf16 for the tensor-core path.  (distances.py cosine_similarity normalises
+// the query the same way.)
+__global__ void __launch_bounds__(128)
+vb_prep_query_kernel(const float* __restrict__ q, uint32_t dim, uint32_t d_pad,
+                     float* __restrict__ q_hat, __nv_bfloat16* __restrict__ q_bf16)
+{
+    __shared__ double red[4];
+    const uint32_t b = blockIdx.x;
+    double ss = 0.0;
+    for (uint32_t c = threadIdx.x; c < dim; c += blockDim.x) {
+        const double v = (double)q[(size_t)b * dim + c];
+        ss += v * v;
+    }
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31u) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    ss = red[0] + red[1] + red[2] + red[3];
+    const float inv = ss > 0.0 ? (float)(1.0 / sqrt(ss)) : 0.0f;
+    for (uint32_t c = threadIdx.x; c < d_pad; c += blockDim.x) {
+        const float v = c < dim ? q[(size_t)b * dim + c] * inv : 0.0f;
+        q_hat[(size_t)b * d_pad + c] = v;
+        q_bf16[(size_t)b * d_pad + c] = __float2bfloat16_rn(v);
+    }
+}

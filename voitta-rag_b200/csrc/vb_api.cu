@@ -1,0 +1,1046 @@
+// libvoitta_b200.so — host side of the C ABI declared in include/voitta_b200.h.
+// Owns device memory, streams and the launch schedule; all arithmetic is in the kernels
+// (mask.cuh K0/K5, dense_scan.cuh K1, dense_gemm.cuh K2, sparse.cuh K3, topk.cuh select + K4).
+#include "../../include/voitta_b200.h"
+#include "common.cuh"
+#include "mask.cuh"
+#include "dense_scan.cuh"
+#include "dense_gemm.cuh"
+#include "sparse.cuh"
+#include "topk.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int vb_fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess)                                                           \
+            return vb_fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define CKK(what)                                                                         \
+    do {                                                                                  \
+        cudaError_t e__ = cudaGetLastError();                                             \
+        if (e__ != cudaSuccess)                                                           \
+            return vb_fail("launch %s failed: %s (%s:%d)", what, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define TRY(expr)                  \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__) return rc__;     \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// buffers
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct vb_index {
+    int32_t dim = 0, d_pad = 0, device = 0;
+    uint64_t row_base = 0;
+    uint64_t n_rows = 0, n_live = 0, cap_rows = 0;
+    uint64_t nnz = 0, cap_nnz = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::mutex mu;
+    int sm_count = 148;
+    uint64_t device_bytes = 0;
+
+    // corpus (device)
+    DevBuf rows, inv_norm, scope_id, created, modified, alive;
+    DevBuf sp_indptr, sp_term, sp_val;     // row-major CSR as appended
+    std::vector<uint32_t> alive_host;      // mirror of the alive bitmap
+    bool any_ts_created = false, any_ts_modified = false;
+
+    // inverted index (device) + host copy of the term directory
+    bool sparse_dirty = true;
+    DevBuf post_row, post_val;
+    uint64_t nnz_live = 0;
+    std::vector<uint32_t> terms_sorted;
+    std::vector<uint64_t> term_ptr;
+
+    // per-search scratch
+    DevBuf args, mask, cand, lists, offs, out, q_hat, q_bf16, tmp;
+    HostBuf h_args, h_out, h_stage;
+    uint32_t cand_cap = 0;
+
+    // options
+    int64_t opt_dense_path = 0, opt_seg_first = 8192, opt_seg_ratio = 32, opt_safe_mode = 0, opt_profile = 0;
+
+    vb_stats stats{};
+    std::vector<cudaEvent_t> prof_events;
+    std::vector<int> prof_phase;
+};
+
+static int dev_reserve(vb_index* h, DevBuf& b, size_t bytes, bool keep, size_t used_bytes = 0) {
+    if (bytes <= b.cap) return 0;
+    size_t ncap = keep ? std::max(bytes, b.cap + b.cap / 2) : bytes;
+    ncap = align_up(ncap, 256);
+    void* np = nullptr;
+    CK(cudaMalloc(&np, ncap));
+    if (keep && b.p && used_bytes) {
+        CK(cudaMemcpyAsync(np, b.p, used_bytes, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (b.p) { CK(cudaFree(b.p)); h->device_bytes -= b.cap; }
+    b.p = np;
+    b.cap = ncap;
+    h->device_bytes += ncap;
+    return 0;
+}
+
+static int host_reserve(HostBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) CK(cudaFreeHost(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t ncap = align_up(bytes + bytes / 4, 4096);
+    CK(cudaMallocHost(&b.p, ncap));
+    b.cap = ncap;
+    return 0;
+}
+
+static void dev_free(vb_index* h, DevBuf& b) {
+    if (b.p) { cudaFree(b.p); h->device_bytes -= b.cap; }
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tiny utility kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void vb_init_lists_kernel(float* tau, uint32_t* cnt, uint32_t* overflow, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { tau[i] = -INFINITY; cnt[i] = 0u; overflow[i] = 0u; }
+}
+__global__ void vb_fill_i64_kernel(int64_t* p, uint64_t n, int64_t v) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void vb_fill_u32_kernel(uint32_t* p, uint64_t n, uint32_t v) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void vb_offset_i64_kernel(const int64_t* src, int64_t* dst, uint64_t n, int64_t add) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[i] + add;
+}
+__global__ void vb_set_alive_kernel(uint32_t* alive, uint64_t first, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = first + i;
+        atomicOr(&alive[r >> 5], 1u << (r & 31u));
+    }
+}
+__global__ void vb_find_tail_kernel(const uint64_t* keys, uint64_t n, uint64_t* out) {
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (keys[mid] != ~0ull) lo = mid + 1; else hi = mid; }
+    *out = lo;
+}
+
+static unsigned grid_for(uint64_t n, unsigned block, unsigned max_blocks = 148u * 16u) {
+    uint64_t g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    return (unsigned)std::min<uint64_t>(g, max_blocks);
+}
+
+// ------------------------------------------------------------------------------------------------
+// lifecycle
+// ------------------------------------------------------------------------------------------------
+extern "C" int vb_abi_version(void) { return VB_ABI_VERSION; }
+extern "C" const char* vb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int vb_create(int32_t dim, int32_t device, uint64_t capacity_hint, uint64_t row_base, vb_index** out) {
+    if (!out) return vb_fail("vb_create: out is NULL");
+    *out = nullptr;
+    if (dim <= 0 || dim > 4096) return vb_fail("vb_create: dim %d out of range (1..4096)", dim);
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return vb_fail("vb_create: no CUDA device (%s); this backend has no CPU fallback",
+                       e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n_dev) return vb_fail("vb_create: device %d not in [0,%d)", device, n_dev);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return vb_fail("vb_create: device %d is sm_%d%d; libvoitta_b200 is built for sm_100a only", device, prop.major, prop.minor);
+    vb_index* h = new vb_index();
+    h->dim = dim;
+    h->d_pad = (int32_t)align_up((size_t)dim, 64);
+    h->device = device;
+    h->row_base = row_base;
+    h->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+        delete h;
+        return vb_fail("vb_create: stream/event creation failed");
+    }
+    cudaFuncSetAttribute(vb_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(VB_ROWS_PER_BLOCK * 8u));
+    if (vb_gemm_configure() != 0) { delete h; return vb_fail("vb_create: tensor-core kernel configuration failed: %s", vb_gemm_last_error()); }
+    (void)capacity_hint;
+    if (const char* env = getenv("VB200_DENSE_PATH")) h->opt_dense_path = atoi(env);   // 0 auto, 1 K1, 2 K2
+    *out = h;
+    return 0;
+}
+
+extern "C" void vb_destroy(vb_index* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (DevBuf* b : {&h->rows, &h->inv_norm, &h->scope_id, &h->created, &h->modified, &h->alive, &h->sp_indptr,
+                      &h->sp_term, &h->sp_val, &h->post_row, &h->post_val, &h->args, &h->mask, &h->cand, &h->lists,
+                      &h->offs, &h->out, &h->q_hat, &h->q_bf16, &h->tmp})
+        dev_free(h, *b);
+    for (HostBuf* b : {&h->h_args, &h->h_out, &h->h_stage}) if (b->p) cudaFreeHost(b->p);
+    for (auto ev : h->prof_events) cudaEventDestroy(ev);
+    cudaEventDestroy(h->ev0);
+    cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
+    if (!h || !key) return vb_fail("vb_set_option: NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    std::string k(key);
+    if (k == "dense_path") h->opt_dense_path = value;
+    else if (k == "seg_first") h->opt_seg_first = std::max<int64_t>(VB_ROWS_PER_BLOCK, (int64_t)align_up((size_t)value, VB_ROWS_PER_BLOCK));
+    else if (k == "seg_ratio") h->opt_seg_ratio = std::max<int64_t>(2, value);
+    else if (k == "safe_mode") h->opt_safe_mode = value;
+    else if (k == "profile") h->opt_profile = value;
+    else return vb_fail("vb_set_option: unknown key '%s'", key);
+    return 0;
+}
+
+extern "C" int vb_get_stats(vb_index* h, vb_stats* out) {
+    if (!h || !out) return vb_fail("vb_get_stats: NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->stats.n_rows = h->n_rows;
+    h->stats.n_live = h->n_live;
+    h->stats.nnz = h->nnz;
+    h->stats.n_terms = h->terms_sorted.size();
+    h->stats.device_bytes = h->device_bytes;
+    *out = h->stats;
+    return 0;
+}
+
+extern "C" int vb_sync(vb_index* h) {
+    if (!h) return vb_fail("vb_sync: NULL index");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ingest
+// ------------------------------------------------------------------------------------------------
+static int reserve_rows(vb_index* h, uint64_t n_total, uint64_t nnz_total) {
+    if (n_total + h->row_base > 0xffffffffull) return vb_fail("row ids exceed 32 bits");
+    if (n_total > h->cap_rows) {
+        uint64_t ncap = std::max<uint64_t>(n_total, h->cap_rows + h->cap_rows / 2);
+        ncap = align_up(ncap, 1024);
+        const uint64_t old = h->n_rows;
+        TRY(dev_reserve(h, h->rows, ncap * h->d_pad * 2, true, old * h->d_pad * 2));
+        TRY(dev_reserve(h, h->inv_norm, ncap * 4, true, old * 4));
+        TRY(dev_reserve(h, h->scope_id, ncap * 4, true, old * 4));
+        TRY(dev_reserve(h, h->created, ncap * 8, true, old * 8));
+        TRY(dev_reserve(h, h->modified, ncap * 8, true, old * 8));
+        const uint64_t old_words = (h->cap_rows + 31) / 32, new_words = (ncap + 31) / 32;
+        TRY(dev_reserve(h, h->alive, new_words * 4, true, old_words * 4));
+        CK(cudaMemsetAsync(h->alive.as<uint32_t>() + old_words, 0, (new_words - old_words) * 4, h->stream));
+        TRY(dev_reserve(h, h->sp_indptr, (ncap + 1) * 8, true, h->sp_indptr.p ? (old + 1) * 8 : 0));
+        if (old == 0) CK(cudaMemsetAsync(h->sp_indptr.p, 0, 8, h->stream));
+        h->alive_host.resize(new_words, 0u);
+        h->cap_rows = ncap;
+    }
+    if (nnz_total > h->cap_nnz) {
+        uint64_t ncap = std::max<uint64_t>(nnz_total, h->cap_nnz + h->cap_nnz / 2);
+        ncap = align_up(ncap, 4096);
+        TRY(dev_reserve(h, h->sp_term, ncap * 4, true, h->nnz * 4));
+        TRY(dev_reserve(h, h->sp_val, ncap * 4, true, h->nnz * 4));
+        h->cap_nnz = ncap;
+    }
+    return 0;
+}
+
+static void mark_alive_host(vb_index* h, uint64_t first, uint64_t n) {
+    for (uint64_t r = first; r < first + n; ++r) h->alive_host[r >> 5] |= 1u << (r & 31u);
+}
+
+extern "C" int vb_upsert(vb_index* h, uint64_t n, const float* dense, const int64_t* sp_indptr,
+                         const uint32_t* sp_term, const float* sp_val, const uint32_t* scope_id,
+                         const int64_t* created, const int64_t* modified, uint64_t* first_row) {
+    if (!h) return vb_fail("vb_upsert: NULL index");
+    if (n == 0) { if (first_row) *first_row = h->row_base + h->n_rows; return 0; }
+    if (!dense) return vb_fail("vb_upsert: dense is NULL");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    const uint64_t add_nnz = sp_indptr ? (uint64_t)(sp_indptr[n] - sp_indptr[0]) : 0;
+    if (sp_indptr) {
+        if (!sp_term || !sp_val) return vb_fail("vb_upsert: sparse arrays missing");
+        for (uint64_t r = 0; r < n; ++r) {
+            if (sp_indptr[r + 1] < sp_indptr[r]) return vb_fail("vb_upsert: sp_indptr not monotone at row %llu", (unsigned long long)r);
+            for (int64_t p = sp_indptr[r] + 1; p < sp_indptr[r + 1]; ++p)
+                if (sp_term[p] <= sp_term[p - 1])
+                    return vb_fail("vb_upsert: sparse indices of row %llu are not strictly ascending", (unsigned long long)r);
+        }
+    }
+    TRY(reserve_rows(h, h->n_rows + n, h->nnz + add_nnz));
+    const uint64_t first = h->n_rows;
+    // dense rows: staged through pinned memory in chunks, converted on the device
+    const uint64_t chunk_rows = std::max<uint64_t>(1, (32ull << 20) / ((uint64_t)h->dim * 4));
+    TRY(host_reserve(h->h_stage, std::min<uint64_t>(n, chunk_rows) * h->dim * 4));
+    TRY(dev_reserve(h, h->tmp, std::min<uint64_t>(n, chunk_rows) * h->dim * 4, false));
+    for (uint64_t r0 = 0; r0 < n; r0 += chunk_rows) {
+        const uint64_t m = std::min<uint64_t>(chunk_rows, n - r0);
+        memcpy(h->h_stage.p, dense + r0 * h->dim, m * h->dim * 4);
+        CK(cudaMemcpyAsync(h->tmp.p, h->h_stage.p, m * h->dim * 4, cudaMemcpyHostToDevice, h->stream));
+        vb_ingest_f32_kernel<<<grid_for(m * 32, 256), 256, 0, h->stream>>>(
+            h->tmp.as<float>(), (uint32_t)m, (uint32_t)h->dim, (uint32_t)h->d_pad,
+            h->rows.as<__nv_bfloat16>() + (first + r0) * h->d_pad, h->inv_norm.as<float>() + first + r0);
+        CKK("vb_ingest_f32_kernel");
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    // columns
+    if (scope_id) CK(cudaMemcpyAsync(h->scope_id.as<uint32_t>() + first, scope_id, n * 4, cudaMemcpyHostToDevice, h->stream));
+    else CK(cudaMemsetAsync(h->scope_id.as<uint32_t>() + first, 0, n * 4, h->stream));
+    if (created) { CK(cudaMemcpyAsync(h->created.as<int64_t>() + first, created, n * 8, cudaMemcpyHostToDevice, h->stream)); h->any_ts_created = true; }
+    else { vb_fill_i64_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(h->created.as<int64_t>() + first, n, INT64_MIN); CKK("fill"); }
+    if (modified) { CK(cudaMemcpyAsync(h->modified.as<int64_t>() + first, modified, n * 8, cudaMemcpyHostToDevice, h->stream)); h->any_ts_modified = true; }
+    else { vb_fill_i64_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(h->modified.as<int64_t>() + first, n, INT64_MIN); CKK("fill"); }
+    // CSR append
+    {
+        std::vector<int64_t> ip(n);
+        for (uint64_t r = 0; r < n; ++r)
+            ip[r] = (int64_t)h->nnz + (sp_indptr ? (sp_indptr[r + 1] - sp_indptr[0]) : 0);
+        CK(cudaMemcpyAsync(h->sp_indptr.as<int64_t>() + first + 1, ip.data(), n * 8, cudaMemcpyHostToDevice, h->stream));
+        if (add_nnz) {
+            CK(cudaMemcpyAsync(h->sp_term.as<uint32_t>() + h->nnz, sp_term + sp_indptr[0], add_nnz * 4, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(h->sp_val.as<float>() + h->nnz, sp_val + sp_indptr[0], add_nnz * 4, cudaMemcpyHostToDevice, h->stream));
+        }
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    mark_alive_host(h, first, n);
+    vb_set_alive_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(h->alive.as<uint32_t>(), first, n);
+    CKK("vb_set_alive_kernel");
+    CK(cudaStreamSynchronize(h->stream));
+    h->n_rows += n;
+    h->n_live += n;
+    h->nnz += add_nnz;
+    h->sparse_dirty = true;
+    if (first_row) *first_row = h->row_base + first;
+    return 0;
+}
+
+extern "C" int vb_upsert_dev(vb_index* h, uint64_t n, const void* rows_bf16, const int64_t* sp_indptr,
+                             const uint32_t* sp_term, const float* sp_val, const uint32_t* scope_id,
+                             const int64_t* created, const int64_t* modified, uint64_t* first_row) {
+    if (!h) return vb_fail("vb_upsert_dev: NULL index");
+    if (n == 0) { if (first_row) *first_row = h->row_base + h->n_rows; return 0; }
+    if (!rows_bf16) return vb_fail("vb_upsert_dev: rows is NULL");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    uint64_t add_nnz = 0;
+    int64_t ip0 = 0;
+    if (sp_indptr) {
+        int64_t ends[2];
+        CK(cudaMemcpy(&ends[0], sp_indptr, 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&ends[1], sp_indptr + n, 8, cudaMemcpyDeviceToHost));
+        ip0 = ends[0];
+        add_nnz = (uint64_t)(ends[1] - ends[0]);
+    }
+    TRY(reserve_rows(h, h->n_rows + n, h->nnz + add_nnz));
+    const uint64_t first = h->n_rows;
+    vb_ingest_bf16_kernel<<<grid_for(n * 32, 256), 256, 0, h->stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(rows_bf16), (uint32_t)n, (uint32_t)h->dim, (uint32_t)h->d_pad,
+        h->rows.as<__nv_bfloat16>() + first * h->d_pad, h->inv_norm.as<float>() + first);
+    CKK("vb_ingest_bf16_kernel");
+    if (scope_id) CK(cudaMemcpyAsync(h->scope_id.as<uint32_t>() + first, scope_id, n * 4, cudaMemcpyDeviceToDevice, h->stream));
+    else CK(cudaMemsetAsync(h->scope_id.as<uint32_t>() + first, 0, n * 4, h->stream));
+    if (created) { CK(cudaMemcpyAsync(h->created.as<int64_t>() + first, created, n * 8, cudaMemcpyDeviceToDevice, h->stream)); h->any_ts_created = true; }
+    else { vb_fill_i64_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(h->created.as<int64_t>() + first, n, INT64_MIN); CKK("fill"); }
+    if (modified) { CK(cudaMemcpyAsync(h->modified.as<int64_t>() + first, modified, n * 8, cudaMemcpyDeviceToDevice, h->stream)); h->any_ts_modified = true; }
+    else { vb_fill_i64_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(h->modified.as<int64_t>() + first, n, INT64_MIN); CKK("fill"); }
+    if (sp_indptr) {
+        vb_offset_i64_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(sp_indptr + 1, h->sp_indptr.as<int64_t>() + first + 1, n, (int64_t)h->nnz - ip0);
+        CKK("vb_offset_i64_kernel");
+        if (add_nnz) {
+            CK(cudaMemcpyAsync(h->sp_term.as<uint32_t>() + h->nnz, sp_term + ip0, add_nnz * 4, cudaMemcpyDeviceToDevice, h->stream));
+            CK(cudaMemcpyAsync(h->sp_val.as<float>() + h->nnz, sp_val + ip0, add_nnz * 4, cudaMemcpyDeviceToDevice, h->stream));
+        }
+    } else {
+        vb_fill_i64_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(h->sp_indptr.as<int64_t>() + first + 1, n, (int64_t)h->nnz);
+        CKK("fill");
+    }
+    mark_alive_host(h, first, n);
+    vb_set_alive_kernel<<<grid_for(n, 256), 256, 0, h->stream>>>(h->alive.as<uint32_t>(), first, n);
+    CKK("vb_set_alive_kernel");
+    CK(cudaStreamSynchronize(h->stream));
+    h->n_rows += n;
+    h->n_live += n;
+    h->nnz += add_nnz;
+    h->sparse_dirty = true;
+    if (first_row) *first_row = h->row_base + first;
+    return 0;
+}
+
+extern "C" int vb_delete_rows(vb_index* h, uint64_t n, const uint64_t* rows) {
+    if (!h) return vb_fail("vb_delete_rows: NULL index");
+    if (n == 0) return 0;
+    if (!rows) return vb_fail("vb_delete_rows: rows is NULL");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    uint64_t killed = 0;
+    std::vector<uint32_t> touched;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (rows[i] < h->row_base || rows[i] - h->row_base >= h->n_rows)
+            return vb_fail("vb_delete_rows: row %llu out of range", (unsigned long long)rows[i]);
+        const uint64_t r = rows[i] - h->row_base;
+        uint32_t& w = h->alive_host[r >> 5];
+        if (w & (1u << (r & 31u))) { w &= ~(1u << (r & 31u)); ++killed; touched.push_back((uint32_t)(r >> 5)); }
+    }
+    std::sort(touched.begin(), touched.end());
+    touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
+    for (uint32_t w : touched)
+        CK(cudaMemcpyAsync(h->alive.as<uint32_t>() + w, &h->alive_host[w], 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->n_live -= killed;
+    if (killed) h->sparse_dirty = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// inverted index build (device; CUB radix sort of (term,row) keys)
+// ------------------------------------------------------------------------------------------------
+static int ensure_sparse_index(vb_index* h) {
+    if (!h->sparse_dirty) return 0;
+    h->terms_sorted.clear();
+    h->term_ptr.assign(1, 0);
+    h->nnz_live = 0;
+    if (h->nnz == 0) { h->sparse_dirty = false; return 0; }
+    const uint64_t nnz = h->nnz;
+    if (nnz >= (1ull << 31)) return vb_fail("sparse index: %llu postings exceed the 2^31 limit of one shard", (unsigned long long)nnz);
+    DevBuf keys_in, keys_out, vals_out, cub_tmp, misc;
+    int rc = 0;
+    auto cleanup = [&]() { dev_free(h, keys_in); dev_free(h, keys_out); dev_free(h, vals_out); dev_free(h, cub_tmp); dev_free(h, misc); };
+#define TRYC(expr) do { rc = (expr); if (rc) { cleanup(); return rc; } } while (0)
+#define CKC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return vb_fail("%s failed: %s", #call, cudaGetErrorString(e__)); } } while (0)
+    TRYC(dev_reserve(h, keys_in, nnz * 8, false));
+    TRYC(dev_reserve(h, keys_out, nnz * 8, false));
+    TRYC(dev_reserve(h, vals_out, nnz * 4, false));
+    TRYC(dev_reserve(h, misc, 64, false));
+    vb_posting_keys_kernel<<<grid_for(h->n_rows * 32, 256), 256, 0, h->stream>>>(
+        h->sp_indptr.as<int64_t>(), h->sp_term.as<uint32_t>(), h->alive.as<uint32_t>(), (uint32_t)h->n_rows, keys_in.as<uint64_t>());
+    CKC(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CKC(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.as<uint64_t>(), keys_out.as<uint64_t>(),
+                                        h->sp_val.as<float>(), vals_out.as<float>(), (int)nnz, 0, 64, h->stream));
+    TRYC(dev_reserve(h, cub_tmp, tmp_bytes, false));
+    CKC(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, keys_in.as<uint64_t>(), keys_out.as<uint64_t>(),
+                                        h->sp_val.as<float>(), vals_out.as<float>(), (int)nnz, 0, 64, h->stream));
+    vb_find_tail_kernel<<<1, 1, 0, h->stream>>>(keys_out.as<uint64_t>(), nnz, misc.as<uint64_t>());
+    CKC(cudaGetLastError());
+    uint64_t live = 0;
+    CKC(cudaMemcpyAsync(&live, misc.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    CKC(cudaStreamSynchronize(h->stream));
+    h->nnz_live = live;
+    if (live == 0) { cleanup(); h->sparse_dirty = false; return 0; }
+    TRYC(dev_reserve(h, h->post_row, live * 4, false));
+    TRYC(dev_reserve(h, h->post_val, live * 4, false));
+    // keys_in is free now: reuse it for post_term (u32), unique terms (u32), run lengths (u32)
+    uint32_t* post_term = keys_in.as<uint32_t>();
+    vb_posting_split_kernel<<<grid_for(live, 256), 256, 0, h->stream>>>(keys_out.as<uint64_t>(), live, h->post_row.as<uint32_t>(), post_term);
+    CKC(cudaGetLastError());
+    CKC(cudaMemcpyAsync(h->post_val.p, vals_out.p, live * 4, cudaMemcpyDeviceToDevice, h->stream));
+    // run-length encode the sorted terms -> distinct terms + df
+    DevBuf uniq, runs, ptrs;
+    auto cleanup2 = [&]() { dev_free(h, uniq); dev_free(h, runs); dev_free(h, ptrs); cleanup(); };
+#define CKC2(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup2(); return vb_fail("%s failed: %s", #call, cudaGetErrorString(e__)); } } while (0)
+    rc = dev_reserve(h, uniq, live * 4, false); if (rc) { cleanup2(); return rc; }
+    rc = dev_reserve(h, runs, live * 8, false); if (rc) { cleanup2(); return rc; }
+    size_t tb = 0;
+    CKC2(cub::DeviceRunLengthEncode::Encode(nullptr, tb, post_term, uniq.as<uint32_t>(), runs.as<uint64_t>(), misc.as<uint32_t>() + 4, (int)live, h->stream));
+    rc = dev_reserve(h, cub_tmp, tb, false); if (rc) { cleanup2(); return rc; }
+    CKC2(cub::DeviceRunLengthEncode::Encode(cub_tmp.p, tb, post_term, uniq.as<uint32_t>(), runs.as<uint64_t>(), misc.as<uint32_t>() + 4, (int)live, h->stream));
+    uint32_t T = 0;
+    CKC2(cudaMemcpyAsync(&T, misc.as<uint32_t>() + 4, 4, cudaMemcpyDeviceToHost, h->stream));
+    CKC2(cudaStreamSynchronize(h->stream));
+    rc = dev_reserve(h, ptrs, ((size_t)T + 1) * 8, false); if (rc) { cleanup2(); return rc; }
+    tb = 0;
+    CKC2(cub::DeviceScan::ExclusiveSum(nullptr, tb, runs.as<uint64_t>(), ptrs.as<uint64_t>(), (int)T, h->stream));
+    rc = dev_reserve(h, cub_tmp, tb, false); if (rc) { cleanup2(); return rc; }
+    CKC2(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tb, runs.as<uint64_t>(), ptrs.as<uint64_t>(), (int)T, h->stream));
+    h->terms_sorted.resize(T);
+    h->term_ptr.resize((size_t)T + 1);
+    CKC2(cudaMemcpyAsync(h->terms_sorted.data(), uniq.p, (size_t)T * 4, cudaMemcpyDeviceToHost, h->stream));
+    CKC2(cudaMemcpyAsync(h->term_ptr.data(), ptrs.p, (size_t)T * 8, cudaMemcpyDeviceToHost, h->stream));
+    CKC2(cudaStreamSynchronize(h->stream));
+    h->term_ptr[T] = live;
+    cleanup2();
+    h->sparse_dirty = false;
+    return 0;
+#undef TRYC
+#undef CKC
+#undef CKC2
+}
+
+// slot of a term in the directory, or -1
+static int64_t term_slot(const vb_index* h, uint32_t term) {
+    auto it = std::lower_bound(h->terms_sorted.begin(), h->terms_sorted.end(), term);
+    if (it == h->terms_sorted.end() || *it != term) return -1;
+    return it - h->terms_sorted.begin();
+}
+
+extern "C" int vb_term_stats(vb_index* h, uint32_t n_terms, const uint32_t* terms, uint64_t* df, uint64_t* n_live) {
+    if (!h) return vb_fail("vb_term_stats: NULL index");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    TRY(ensure_sparse_index(h));
+    for (uint32_t i = 0; i < n_terms; ++i) {
+        const int64_t s = term_slot(h, terms[i]);
+        df[i] = s < 0 ? 0 : h->term_ptr[s + 1] - h->term_ptr[s];
+    }
+    if (n_live) *n_live = h->n_live;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// search
+// ------------------------------------------------------------------------------------------------
+struct Arena {
+    size_t off = 0;
+    size_t take(size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; }
+};
+
+struct Batch {
+    uint32_t B = 0, k = 0, limit = 0, n_lists = 0, n_qterms = 0, n_filters = 0, mask_words = 0, n_blocks = 0;
+    bool any_sparse = false, use_mask = false;
+    std::vector<int32_t> mode;
+    // device pointers into h->args
+    const float* d_q = nullptr;
+    const int64_t* d_qindptr = nullptr;
+    const double* d_qweight = nullptr;
+    const uint64_t* d_qlo = nullptr;
+    const uint64_t* d_qhi = nullptr;
+    const int32_t* d_maskof = nullptr;
+    const int32_t* d_mode = nullptr;
+    const VbFilterDev* d_filters = nullptr;
+    uint32_t need_created = 0, need_modified = 0, need_scope = 0;
+    // lists
+    float* tau = nullptr;
+    uint32_t* cnt = nullptr;
+    uint32_t* overflow = nullptr;
+};
+
+enum { PH_MASK = 0, PH_DENSE = 1, PH_SPARSE = 2, PH_SELECT = 3, PH_FUSE = 4, PH_N = 5 };
+
+static void prof_begin(vb_index* h, int phase) {
+    if (!h->opt_profile) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    h->prof_events.push_back(a); h->prof_events.push_back(b);
+    h->prof_phase.push_back(phase);
+    cudaEventRecord(a, h->stream);
+}
+static void prof_end(vb_index* h) {
+    if (!h->opt_profile) return;
+    cudaEventRecord(h->prof_events.back(), h->stream);
+}
+static void prof_collect(vb_index* h) {
+    double acc[PH_N] = {0, 0, 0, 0, 0};
+    for (size_t i = 0; i < h->prof_phase.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->prof_events[2 * i], h->prof_events[2 * i + 1]);
+        acc[h->prof_phase[i]] += ms;
+    }
+    for (auto ev : h->prof_events) cudaEventDestroy(ev);
+    h->prof_events.clear();
+    h->prof_phase.clear();
+    h->stats.last_mask_ms = acc[PH_MASK];
+    h->stats.last_dense_ms = acc[PH_DENSE];
+    h->stats.last_sparse_ms = acc[PH_SPARSE];
+    h->stats.last_select_ms = acc[PH_SELECT];
+    h->stats.last_fuse_ms = acc[PH_FUSE];
+}
+
+static int validate_batch(const vb_index* h, const vb_query_batch* q) {
+    if (!q) return vb_fail("query batch is NULL");
+    if (q->n_queries == 0) return vb_fail("empty query batch");
+    if (!q->dense) return vb_fail("dense queries are NULL");
+    if (q->limit == 0) return vb_fail("limit must be > 0");
+    if (q->kprime < q->limit) return vb_fail("kprime (%u) < limit (%u)", q->kprime, q->limit);
+    if (q->kprime > VB_MAX_KPRIME) return vb_fail("kprime %u exceeds VB_MAX_KPRIME (%d)", q->kprime, VB_MAX_KPRIME);
+    if (q->fusion < 0 || q->fusion > 2) return vb_fail("unknown fusion mode %d", q->fusion);
+    if (q->n_filters && !q->filters) return vb_fail("filters is NULL");
+    if (q->filter_of)
+        for (uint32_t i = 0; i < q->n_queries; ++i)
+            if (q->filter_of[i] >= (int32_t)q->n_filters) return vb_fail("filter_of[%u] out of range", i);
+    (void)h;
+    return 0;
+}
+
+// Upload the batch, evaluate the filters, initialise the candidate lists.
+static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool need_corpus) {
+    b.B = q->n_queries;
+    b.k = q->kprime;
+    b.limit = q->limit;
+    b.n_lists = 2 * b.B;
+    b.mode.assign(b.B, 0);
+    const bool sparse_enabled = q->fusion != VB_FUSE_DENSE_ONLY && q->sp_indptr != nullptr;
+
+    // ---- sparse queries: sort by term id, resolve posting ranges, apply IDF ----
+    std::vector<int64_t> indptr(b.B + 1, 0);
+    std::vector<double> weight;
+    std::vector<uint64_t> qlo, qhi;
+    if (sparse_enabled) {
+        if (need_corpus) TRY(ensure_sparse_index(h));
+        std::vector<std::pair<uint32_t, double>> tw;
+        for (uint32_t i = 0; i < b.B; ++i) {
+            const int64_t lo = q->sp_indptr[i], hi = q->sp_indptr[i + 1];
+            if (hi < lo) return vb_fail("sp_indptr not monotone at query %u", i);
+            if (hi - lo > VB_MAX_QUERY_TERMS) return vb_fail("query %u has %lld terms (max %d)", i, (long long)(hi - lo), VB_MAX_QUERY_TERMS);
+            tw.clear();
+            for (int64_t p = lo; p < hi; ++p) tw.emplace_back(q->sp_term[p], q->sp_weight[p]);
+            std::sort(tw.begin(), tw.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+            for (size_t t = 1; t < tw.size(); ++t)
+                if (tw[t].first == tw[t - 1].first) return vb_fail("query %u repeats sparse index %u", i, tw[t].first);
+            for (auto& pr : tw) {
+                uint64_t plo = 0, phi = 0;
+                if (need_corpus) {
+                    const int64_t s = term_slot(h, pr.first);
+                    if (s >= 0) { plo = h->term_ptr[s]; phi = h->term_ptr[s + 1]; }
+                }
+                double w = pr.second;
+                if (q->apply_idf) {
+                    const double df = (double)(phi - plo);
+                    // local_collection.py _compute_idf: log((N - df + 0.5) / (df + 0.5) + 1)
+                    w = w * std::log(((double)h->n_live - df + 0.5) / (df + 0.5) + 1.0);
+                }
+                weight.push_back(w);
+                qlo.push_back(plo);
+                qhi.push_back(phi);
+            }
+            indptr[i + 1] = (int64_t)weight.size();
+            if (hi > lo) { b.mode[i] = q->fusion; b.any_sparse = true; }
+        }
+    }
+    b.n_qterms = (uint32_t)weight.size();
+
+    // ---- filters ----
+    const bool tombstones = h->n_live < h->n_rows;
+    std::vector<int32_t> mask_of(b.B, -1);
+    std::vector<vb_filter> flt(q->filters, q->filters + q->n_filters);
+    bool any_filter = false;
+    for (uint32_t i = 0; i < b.B; ++i) {
+        int32_t f = q->filter_of ? q->filter_of[i] : -1;
+        if (f >= 0) {
+            const vb_filter& x = flt[f];
+            if (x.scope_bits == nullptr && x.ts_field == VB_TS_NONE && !tombstones) f = -1;   // filter with no clause
+        }
+        mask_of[i] = f;
+        any_filter |= f >= 0;
+    }
+    if (tombstones) {   // unfiltered queries still need the alive bits
+        int32_t alive_only = -1;
+        for (uint32_t i = 0; i < b.B; ++i)
+            if (mask_of[i] < 0) {
+                if (alive_only < 0) { alive_only = (int32_t)flt.size(); flt.push_back(vb_filter{nullptr, 0, VB_TS_NONE, 0, 0}); }
+                mask_of[i] = alive_only;
+            }
+        any_filter = true;
+    }
+    b.use_mask = any_filter && need_corpus;
+    b.n_filters = b.use_mask ? (uint32_t)flt.size() : 0;
+    b.mask_words = (uint32_t)((h->n_rows + 31) / 32);
+    b.n_blocks = (uint32_t)((h->n_rows + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK);
+
+    // ---- pack everything into one pinned block, one H2D copy ----
+    Arena ar;
+    const size_t o_q = ar.take((size_t)b.B * h->dim * 4);
+    const size_t o_ip = ar.take((b.B + 1) * 8);
+    const size_t o_w = ar.take((size_t)b.n_qterms * 8 + 8);
+    const size_t o_lo = ar.take((size_t)b.n_qterms * 8 + 8);
+    const size_t o_hi = ar.take((size_t)b.n_qterms * 8 + 8);
+    const size_t o_mo = ar.take((size_t)b.B * 4);
+    const size_t o_md = ar.take((size_t)b.B * 4);
+    const size_t o_fl = ar.take((size_t)std::max<uint32_t>(1, b.n_filters) * sizeof(VbFilterDev));
+    std::vector<size_t> o_bits(b.n_filters, 0);
+    for (uint32_t f = 0; f < b.n_filters; ++f)
+        if (flt[f].scope_bits) o_bits[f] = ar.take((size_t)flt[f].scope_words * 4);
+    TRY(host_reserve(h->h_args, ar.off));
+    TRY(dev_reserve(h, h->args, ar.off, false));
+    unsigned char* hp = h->h_args.as<unsigned char>();
+    unsigned char* dp = h->args.as<unsigned char>();
+    memcpy(hp + o_q, q->dense, (size_t)b.B * h->dim * 4);
+    memcpy(hp + o_ip, indptr.data(), (b.B + 1) * 8);
+    if (b.n_qterms) {
+        memcpy(hp + o_w, weight.data(), (size_t)b.n_qterms * 8);
+        memcpy(hp + o_lo, qlo.data(), (size_t)b.n_qterms * 8);
+        memcpy(hp + o_hi, qhi.data(), (size_t)b.n_qterms * 8);
+    }
+    memcpy(hp + o_mo, mask_of.data(), (size_t)b.B * 4);
+    memcpy(hp + o_md, b.mode.data(), (size_t)b.B * 4);
+    VbFilterDev* hf = reinterpret_cast<VbFilterDev*>(hp + o_fl);
+    for (uint32_t f = 0; f < b.n_filters; ++f) {
+        hf[f].scope_bits = flt[f].scope_bits ? reinterpret_cast<const uint32_t*>(dp + o_bits[f]) : nullptr;
+        hf[f].scope_words = flt[f].scope_words;
+        hf[f].ts_field = flt[f].ts_field;
+        hf[f].ts_lo = flt[f].ts_lo;
+        hf[f].ts_hi = flt[f].ts_hi;
+        if (flt[f].scope_bits) { memcpy(hp + o_bits[f], flt[f].scope_bits, (size_t)flt[f].scope_words * 4); b.need_scope = 1; }
+        if (flt[f].ts_field == VB_TS_CREATED) b.need_created = 1;
+        if (flt[f].ts_field == VB_TS_MODIFIED) b.need_modified = 1;
+    }
+    CK(cudaMemcpyAsync(dp, hp, ar.off, cudaMemcpyHostToDevice, h->stream));
+    b.d_q = reinterpret_cast<const float*>(dp + o_q);
+    b.d_qindptr = reinterpret_cast<const int64_t*>(dp + o_ip);
+    b.d_qweight = reinterpret_cast<const double*>(dp + o_w);
+    b.d_qlo = reinterpret_cast<const uint64_t*>(dp + o_lo);
+    b.d_qhi = reinterpret_cast<const uint64_t*>(dp + o_hi);
+    b.d_maskof = reinterpret_cast<const int32_t*>(dp + o_mo);
+    b.d_mode = reinterpret_cast<const int32_t*>(dp + o_md);
+    b.d_filters = reinterpret_cast<const VbFilterDev*>(dp + o_fl);
+
+    // ---- candidate lists ----
+    const uint32_t need_cap = std::max<uint32_t>(16384u, (uint32_t)align_up((size_t)2 * (size_t)h->opt_seg_ratio * b.k, 4096));
+    h->cand_cap = need_cap;
+    TRY(dev_reserve(h, h->cand, (size_t)b.n_lists * need_cap * 8, false));
+    TRY(dev_reserve(h, h->lists, (size_t)b.n_lists * 12, false));
+    b.tau = h->lists.as<float>();
+    b.cnt = h->lists.as<uint32_t>() + b.n_lists;
+    b.overflow = h->lists.as<uint32_t>() + 2 * (size_t)b.n_lists;
+    vb_init_lists_kernel<<<(b.n_lists + 255) / 256, 256, 0, h->stream>>>(b.tau, b.cnt, b.overflow, b.n_lists);
+    CKK("vb_init_lists_kernel");
+    ++h->stats.last_launches;
+    return 0;
+}
+
+static int launch_scan(vb_index* h, const Batch& b, uint32_t row_begin, uint32_t row_end) {
+    VbScanArgs a{};
+    a.rows = h->rows.as<uint4>();
+    a.inv_norm = h->inv_norm.as<float>();
+    a.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr;
+    a.mask_of = b.use_mask ? b.d_maskof : nullptr;
+    a.q_hat = h->q_hat.as<float>();
+    a.tau = b.tau;
+    a.cand = h->cand.as<uint64_t>();
+    a.cnt = b.cnt;
+    a.mask_words = b.mask_words;
+    a.chunks = (uint32_t)h->d_pad / 8;
+    a.row_begin = row_begin;
+    a.row_end = row_end;
+    a.row_base = (uint32_t)h->row_base;
+    a.cap = h->cand_cap;
+    a.q_begin = 0;
+    const uint32_t groups = (row_end - row_begin + 31) / 32;
+    const uint32_t per_q = std::max<uint32_t>(1, (uint32_t)(h->sm_count * 8) / std::min<uint32_t>(b.B, 8));
+    dim3 grid(std::min<uint32_t>((groups + 7) / 8, per_q), b.B);
+    const int nch = (int)((a.chunks + 31) / 32);
+    switch (nch) {
+        case 1: vb_dense_scan_kernel<1><<<grid, 256, 0, h->stream>>>(a); break;
+        case 2: vb_dense_scan_kernel<2><<<grid, 256, 0, h->stream>>>(a); break;
+        case 3: vb_dense_scan_kernel<3><<<grid, 256, 0, h->stream>>>(a); break;
+        case 4: vb_dense_scan_kernel<4><<<grid, 256, 0, h->stream>>>(a); break;
+        default: vb_dense_scan_generic_kernel<<<grid, 256, 0, h->stream>>>(a); break;
+    }
+    CKK("vb_dense_scan_kernel");
+    ++h->stats.last_launches;
+    return 0;
+}
+
+// Score both branches of this shard and leave the exact, sorted top-k' of every list in
+// cand[list][0..cnt).  `safe`: fixed small segments that can never overflow a list.
+static int run_branches(vb_index* h, const Batch& b, bool safe) {
+    const uint32_t n = (uint32_t)h->n_rows;
+    // query prep
+    TRY(dev_reserve(h, h->q_hat, (size_t)b.B * h->d_pad * 4, false));
+    TRY(dev_reserve(h, h->q_bf16, (size_t)align_up(b.B, 256) * h->d_pad * 2, false));
+    vb_prep_query_kernel<<<b.B, 128, 0, h->stream>>>(b.d_q, (uint32_t)h->dim, (uint32_t)h->d_pad, h->q_hat.as<float>(), h->q_bf16.as<__nv_bfloat16>());
+    CKK("vb_prep_query_kernel");
+    ++h->stats.last_launches;
+    // K0 filter masks
+    if (b.use_mask) {
+        prof_begin(h, PH_MASK);
+        TRY(dev_reserve(h, h->mask, (size_t)b.n_filters * b.mask_words * 4, false));
+        vb_mask_kernel<<<grid_for((uint64_t)b.mask_words * 32, 256, h->sm_count * 8), 256, 0, h->stream>>>(
+            h->scope_id.as<uint32_t>(), h->created.as<int64_t>(), h->modified.as<int64_t>(), h->alive.as<uint32_t>(), n,
+            b.d_filters, b.n_filters, b.mask_words, b.need_created, b.need_modified, b.need_scope, h->mask.as<uint32_t>());
+        CKK("vb_mask_kernel");
+        ++h->stats.last_launches;
+        prof_end(h);
+    }
+    // sparse slice table
+    const bool do_sparse = b.any_sparse && h->nnz_live > 0 && b.n_qterms > 0;
+    if (do_sparse) {
+        prof_begin(h, PH_SPARSE);
+        const uint64_t total = (uint64_t)b.n_qterms * (b.n_blocks + 1);
+        TRY(dev_reserve(h, h->offs, total * 8, false));
+        vb_slice_kernel<<<grid_for(total, 256), 256, 0, h->stream>>>(h->post_row.as<uint32_t>(), b.d_qlo, b.d_qhi, b.n_qterms, b.n_blocks, h->offs.as<uint64_t>());
+        CKK("vb_slice_kernel");
+        ++h->stats.last_launches;
+        prof_end(h);
+    }
+    // dense path choice
+    int path = (int)h->opt_dense_path;
+    if (path == 0) path = vb_gemm_supported(h->d_pad, b.B) && b.B >= 2 ? 2 : 1;
+    if (path == 2 && !vb_gemm_supported(h->d_pad, b.B)) return vb_fail("dense_path=2 requested but unsupported for d_pad=%d B=%u", h->d_pad, b.B);
+    h->stats.last_dense_path = (uint32_t)path;
+
+    // segment schedule (boundaries are multiples of VB_ROWS_PER_BLOCK)
+    std::vector<uint32_t> bounds{0};
+    if (safe || h->opt_safe_mode) {
+        const uint32_t step = (uint32_t)std::max<size_t>(VB_ROWS_PER_BLOCK, (h->cand_cap - b.k) / VB_ROWS_PER_BLOCK * VB_ROWS_PER_BLOCK);
+        for (uint64_t r = step; r < n; r += step) bounds.push_back((uint32_t)r);
+    } else {
+        for (uint64_t r = (uint64_t)h->opt_seg_first; r < n; r *= (uint64_t)h->opt_seg_ratio) bounds.push_back((uint32_t)r);
+    }
+    bounds.push_back(n);
+
+    for (size_t s = 0; s + 1 < bounds.size(); ++s) {
+        const uint32_t r0 = bounds[s], r1 = bounds[s + 1];
+        prof_begin(h, PH_DENSE);
+        if (path == 2) {
+            VbGemmLaunch g{};
+            g.rows = h->rows.p; g.inv_norm = h->inv_norm.as<float>(); g.q_bf16 = h->q_bf16.p;
+            g.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; g.mask_of = b.use_mask ? b.d_maskof : nullptr;
+            g.mask_words = b.mask_words; g.n_filters = b.n_filters; g.tau = b.tau; g.cand = h->cand.as<uint64_t>(); g.cnt = b.cnt;
+            g.cap = h->cand_cap; g.n_rows_total = n; g.row_begin = r0; g.row_end = r1; g.row_base = (uint32_t)h->row_base;
+            g.d_pad = (uint32_t)h->d_pad; g.n_queries = b.B; g.sm_count = h->sm_count; g.stream = h->stream;
+            int launches = 0;
+            if (vb_gemm_launch(g, &launches) != 0) return vb_fail("tensor-core dense kernel: %s", vb_gemm_last_error());
+            h->stats.last_launches += (uint32_t)launches;
+        } else {
+            TRY(launch_scan(h, b, r0, r1));
+        }
+        prof_end(h);
+        if (do_sparse) {
+            prof_begin(h, PH_SPARSE);
+            VbSparseArgs a{};
+            a.post_row = h->post_row.as<uint32_t>(); a.post_val = h->post_val.as<float>(); a.off = h->offs.as<uint64_t>();
+            a.q_indptr = b.d_qindptr; a.q_weight = b.d_qweight;
+            a.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; a.mask_of = b.use_mask ? b.d_maskof : nullptr;
+            a.tau = b.tau; a.cand = h->cand.as<uint64_t>(); a.cnt = b.cnt; a.mask_words = b.mask_words;
+            a.n_blocks = b.n_blocks; a.blk_begin = r0 / VB_ROWS_PER_BLOCK; a.n_queries = b.B; a.n_rows = n;
+            a.row_base = (uint32_t)h->row_base; a.cap = h->cand_cap;
+            const uint32_t nblk = (r1 - r0 + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK;
+            vb_sparse_kernel<<<nblk * b.B, 256, VB_ROWS_PER_BLOCK * 8, h->stream>>>(a);
+            CKK("vb_sparse_kernel");
+            ++h->stats.last_launches;
+            prof_end(h);
+        }
+        prof_begin(h, PH_SELECT);
+        vb_compact_kernel<<<b.n_lists, VB_COMPACT_THREADS, 0, h->stream>>>(h->cand.as<uint64_t>(), b.cnt, b.tau, b.overflow, h->cand_cap, b.k);
+        CKK("vb_compact_kernel");
+        ++h->stats.last_launches;
+        prof_end(h);
+    }
+    return 0;
+}
+
+// Fuse the (already exact, sorted) branch lists and bring everything back to the host.
+// Returns *overflowed = 1 if any list overflowed during scoring (caller re-runs in safe mode).
+static int fuse_and_fetch(vb_index* h, const Batch& b, const vb_query_batch* q, vb_result* out, int* overflowed) {
+    Arena ar;
+    const size_t o_rows = ar.take((size_t)b.B * b.limit * 4);
+    const size_t o_sc = ar.take((size_t)b.B * b.limit * 8);
+    const size_t o_cnt = ar.take((size_t)b.B * 4);
+    const size_t o_keys = ar.take((size_t)b.n_lists * b.k * 8);
+    const size_t o_lcnt = ar.take((size_t)b.n_lists * 4);
+    const size_t o_ovf = ar.take((size_t)b.n_lists * 4);
+    TRY(dev_reserve(h, h->out, ar.off, false));
+    TRY(host_reserve(h->h_out, ar.off));
+    unsigned char* dp = h->out.as<unsigned char>();
+    prof_begin(h, PH_FUSE);
+    VbFuseArgs f{};
+    f.cand = h->cand.as<uint64_t>(); f.cnt = b.cnt; f.mode = b.d_mode; f.cap = h->cand_cap; f.n_queries = b.B;
+    f.k = b.k; f.limit = b.limit; f.w_sparse = q->sparse_weight; f.w_dense = 1.0 - q->sparse_weight;
+    f.out_rows = reinterpret_cast<uint32_t*>(dp + o_rows); f.out_scores = reinterpret_cast<double*>(dp + o_sc);
+    f.out_cnt = reinterpret_cast<int32_t*>(dp + o_cnt);
+    vb_fuse_kernel<<<b.B, 128, (size_t)2 * b.k * 13 + 16, h->stream>>>(f);
+    CKK("vb_fuse_kernel");
+    ++h->stats.last_launches;
+    const bool want_branches = out->dense_rows || out->dense_scores || out->dense_counts || out->sparse_rows || out->sparse_scores || out->sparse_counts;
+    if (want_branches) {
+        vb_export_kernel<<<b.n_lists, 128, 0, h->stream>>>(h->cand.as<uint64_t>(), b.cnt, h->cand_cap, b.k, reinterpret_cast<uint64_t*>(dp + o_keys));
+        CKK("vb_export_kernel");
+        ++h->stats.last_launches;
+    }
+    prof_end(h);
+    CK(cudaMemcpyAsync(dp + o_lcnt, b.cnt, (size_t)b.n_lists * 4, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(dp + o_ovf, b.overflow, (size_t)b.n_lists * 4, cudaMemcpyDeviceToDevice, h->stream));
+    unsigned char* hp = h->h_out.as<unsigned char>();
+    if (want_branches) {
+        CK(cudaMemcpyAsync(hp, dp, ar.off, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        CK(cudaMemcpyAsync(hp, dp, o_keys, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(hp + o_lcnt, dp + o_lcnt, ar.off - o_lcnt, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const uint32_t* ovf = reinterpret_cast<const uint32_t*>(hp + o_ovf);
+    *overflowed = 0;
+    for (uint32_t i = 0; i < b.n_lists; ++i) if (ovf[i]) *overflowed = 1;
+    if (*overflowed) return 0;
+    const uint32_t* rows = reinterpret_cast<const uint32_t*>(hp + o_rows);
+    const double* sc = reinterpret_cast<const double*>(hp + o_sc);
+    const int32_t* cn = reinterpret_cast<const int32_t*>(hp + o_cnt);
+    for (uint32_t i = 0; i < b.B; ++i) {
+        if (out->counts) out->counts[i] = cn[i];
+        for (int32_t j = 0; j < cn[i]; ++j) {
+            if (out->rows) out->rows[(size_t)i * b.limit + j] = rows[(size_t)i * b.limit + j];
+            if (out->scores) out->scores[(size_t)i * b.limit + j] = sc[(size_t)i * b.limit + j];
+        }
+    }
+    if (want_branches) {
+        const uint64_t* keys = reinterpret_cast<const uint64_t*>(hp + o_keys);
+        const uint32_t* lc = reinterpret_cast<const uint32_t*>(hp + o_lcnt);
+        for (uint32_t br = 0; br < 2; ++br) {
+            uint64_t* orow = br ? out->sparse_rows : out->dense_rows;
+            float* osc = br ? out->sparse_scores : out->dense_scores;
+            int32_t* ocn = br ? out->sparse_counts : out->dense_counts;
+            for (uint32_t i = 0; i < b.B; ++i) {
+                const uint32_t list = br * b.B + i;
+                const uint32_t c = std::min(lc[list], b.k);
+                if (ocn) ocn[i] = (int32_t)c;
+                for (uint32_t j = 0; j < c; ++j) {
+                    const uint64_t key = keys[(size_t)list * b.k + j];
+                    if (orow) orow[(size_t)i * b.k + j] = vb_key_row(key);
+                    if (osc) {
+                        const uint32_t bits = vb_ordered_f32((uint32_t)(key >> 32));
+                        float s;
+                        memcpy(&s, &bits, 4);
+                        osc[(size_t)i * b.k + j] = s;
+                    }
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+static void finish_stats(vb_index* h, const Batch& b) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->stats.last_search_ms = ms;
+    h->stats.searches += 1;
+    h->stats.queries += b.B;
+    if (h->opt_profile) prof_collect(h);
+}
+
+static void zero_result(const vb_query_batch* q, vb_result* out) {
+    for (uint32_t i = 0; i < q->n_queries; ++i) {
+        if (out->counts) out->counts[i] = 0;
+        if (out->dense_counts) out->dense_counts[i] = 0;
+        if (out->sparse_counts) out->sparse_counts[i] = 0;
+    }
+}
+
+extern "C" int vb_search(vb_index* h, const vb_query_batch* q, vb_result* out) {
+    if (!h || !out) return vb_fail("vb_search: NULL argument");
+    TRY(validate_batch(h, q));
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (h->n_rows == 0) { zero_result(q, out); return 0; }
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        Batch b;
+        h->stats.last_launches = 0;
+        CK(cudaEventRecord(h->ev0, h->stream));
+        TRY(prepare_batch(h, q, b, true));
+        TRY(run_branches(h, b, attempt == 1));
+        int overflowed = 0;
+        TRY(fuse_and_fetch(h, b, q, out, &overflowed));
+        finish_stats(h, b);
+        if (!overflowed) return 0;
+        if (attempt == 1) return vb_fail("vb_search: candidate list overflow even in safe mode (internal error)");
+        ++h->stats.overflow_reruns;
+    }
+    return 0;
+}
+
+extern "C" int vb_search_local(vb_index* h, const vb_query_batch* q, uint64_t* cand_dev) {
+    if (!h || !cand_dev) return vb_fail("vb_search_local: NULL argument");
+    TRY(validate_batch(h, q));
+    if (q->apply_idf) return vb_fail("vb_search_local: weights must carry the global IDF (apply_idf = 0)");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    const uint32_t n_lists = 2 * q->n_queries;
+    if (h->n_rows == 0) {
+        CK(cudaMemsetAsync(cand_dev, 0, (size_t)n_lists * q->kprime * 8, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        Batch b;
+        h->stats.last_launches = 0;
+        CK(cudaEventRecord(h->ev0, h->stream));
+        TRY(prepare_batch(h, q, b, true));
+        TRY(run_branches(h, b, attempt == 1));
+        vb_export_kernel<<<b.n_lists, 128, 0, h->stream>>>(h->cand.as<uint64_t>(), b.cnt, h->cand_cap, b.k, cand_dev);
+        CKK("vb_export_kernel");
+        ++h->stats.last_launches;
+        TRY(host_reserve(h->h_out, (size_t)b.n_lists * 4));
+        CK(cudaMemcpyAsync(h->h_out.p, b.overflow, (size_t)b.n_lists * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(h->ev1, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        finish_stats(h, b);
+        bool ovf = false;
+        for (uint32_t i = 0; i < b.n_lists; ++i) ovf |= h->h_out.as<uint32_t>()[i] != 0;
+        if (!ovf) return 0;
+        if (attempt == 1) return vb_fail("vb_search_local: candidate list overflow even in safe mode (internal error)");
+        ++h->stats.overflow_reruns;
+    }
+    return 0;
+}
+
+extern "C" int vb_merge_fuse(vb_index* h, const vb_query_batch* q, uint32_t n_shards, const uint64_t* gathered_dev, vb_result* out) {
+    if (!h || !gathered_dev || !out) return vb_fail("vb_merge_fuse: NULL argument");
+    TRY(validate_batch(h, q));
+    if (n_shards == 0 || (uint64_t)n_shards * q->kprime > 16384) return vb_fail("vb_merge_fuse: n_shards*kprime out of range");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    Batch b;
+    h->stats.last_launches = 0;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    TRY(prepare_batch(h, q, b, false));
+    vb_import_kernel<<<b.n_lists, 256, 0, h->stream>>>(gathered_dev, n_shards, b.n_lists, b.k, h->cand_cap, h->cand.as<uint64_t>(), b.cnt);
+    CKK("vb_import_kernel");
+    vb_compact_kernel<<<b.n_lists, VB_COMPACT_THREADS, 0, h->stream>>>(h->cand.as<uint64_t>(), b.cnt, b.tau, b.overflow, h->cand_cap, b.k);
+    CKK("vb_compact_kernel");
+    h->stats.last_launches += 2;
+    int overflowed = 0;
+    TRY(fuse_and_fetch(h, b, q, out, &overflowed));
+    finish_stats(h, b);
+    if (overflowed) return vb_fail("vb_merge_fuse: unexpected overflow");
+    return 0;
+}

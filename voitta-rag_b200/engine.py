@@ -1,0 +1,345 @@
+"""ctypes binding of libvoitta_b200.so (include/voitta_b200.h) and the ``Index`` handle.
+
+This is the thin layer the north_star asks for: Python host code calls CUDA through the C ABI;
+numpy arrays (host) or raw device pointers (torch tensors' ``data_ptr()``) cross the boundary.
+There is no CPU fallback: if the library is missing or no sm_100 device is present, every
+compute call raises ``B200Error``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libvoitta_b200.so"
+
+TS_MISSING = -(2 ** 63)
+TS_MIN = -(2 ** 63) + 1
+TS_MAX = 2 ** 63 - 1
+FUSE_DENSE_ONLY, FUSE_WEIGHTED, FUSE_RRF = 0, 1, 2
+FUSION = {"dense": FUSE_DENSE_ONLY, "weighted": FUSE_WEIGHTED, "rrf": FUSE_RRF}
+TS_NONE, TS_CREATED, TS_MODIFIED = 0, 1, 2
+MAX_KPRIME = 1024
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class _Filter(C.Structure):
+    _fields_ = [("scope_bits", C.POINTER(C.c_uint32)), ("scope_words", C.c_uint32),
+                ("ts_field", C.c_int32), ("ts_lo", C.c_int64), ("ts_hi", C.c_int64)]
+
+
+class _QueryBatch(C.Structure):
+    _fields_ = [("n_queries", C.c_uint32), ("dense", C.POINTER(C.c_float)),
+                ("sp_indptr", C.POINTER(C.c_int64)), ("sp_term", C.POINTER(C.c_uint32)),
+                ("sp_weight", C.POINTER(C.c_double)), ("apply_idf", C.c_int32),
+                ("n_filters", C.c_uint32), ("filters", C.POINTER(_Filter)),
+                ("filter_of", C.POINTER(C.c_int32)), ("limit", C.c_uint32), ("kprime", C.c_uint32),
+                ("fusion", C.c_int32), ("sparse_weight", C.c_double)]
+
+
+class _Result(C.Structure):
+    _fields_ = [("rows", C.POINTER(C.c_uint64)), ("scores", C.POINTER(C.c_double)),
+                ("counts", C.POINTER(C.c_int32)),
+                ("dense_rows", C.POINTER(C.c_uint64)), ("dense_scores", C.POINTER(C.c_float)),
+                ("dense_counts", C.POINTER(C.c_int32)),
+                ("sparse_rows", C.POINTER(C.c_uint64)), ("sparse_scores", C.POINTER(C.c_float)),
+                ("sparse_counts", C.POINTER(C.c_int32))]
+
+
+class _Stats(C.Structure):
+    _fields_ = [("n_rows", C.c_uint64), ("n_live", C.c_uint64), ("nnz", C.c_uint64), ("n_terms", C.c_uint64),
+                ("searches", C.c_uint64), ("queries", C.c_uint64), ("overflow_reruns", C.c_uint64),
+                ("last_search_ms", C.c_double), ("last_dense_ms", C.c_double), ("last_sparse_ms", C.c_double),
+                ("last_select_ms", C.c_double), ("last_mask_ms", C.c_double), ("last_fuse_ms", C.c_double),
+                ("last_dense_path", C.c_uint32), ("last_launches", C.c_uint32), ("device_bytes", C.c_uint64)]
+
+
+# every symbol include/voitta_b200.h declares
+EXPORTS = ["vb_abi_version", "vb_last_error", "vb_create", "vb_destroy", "vb_upsert", "vb_upsert_dev",
+           "vb_delete_rows", "vb_term_stats", "vb_search", "vb_search_local", "vb_merge_fuse",
+           "vb_set_option", "vb_get_stats", "vb_sync"]
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree library.  Never builds and never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise B200Error(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    lib = C.CDLL(str(LIB_PATH))
+    vp, u64p, u32p = C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+    lib.vb_abi_version.restype = C.c_int
+    lib.vb_last_error.restype = C.c_char_p
+    lib.vb_create.argtypes = [C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.POINTER(vp)]
+    lib.vb_destroy.argtypes = [vp]
+    lib.vb_destroy.restype = None
+    lib.vb_upsert.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, vp, vp, vp, u64p]
+    lib.vb_upsert_dev.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, vp, vp, vp, u64p]
+    lib.vb_delete_rows.argtypes = [vp, C.c_uint64, vp]
+    lib.vb_term_stats.argtypes = [vp, C.c_uint32, vp, vp, u64p]
+    lib.vb_search.argtypes = [vp, C.POINTER(_QueryBatch), C.POINTER(_Result)]
+    lib.vb_search_local.argtypes = [vp, C.POINTER(_QueryBatch), vp]
+    lib.vb_merge_fuse.argtypes = [vp, C.POINTER(_QueryBatch), C.c_uint32, vp, C.POINTER(_Result)]
+    lib.vb_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    lib.vb_get_stats.argtypes = [vp, C.POINTER(_Stats)]
+    lib.vb_sync.argtypes = [vp]
+    _lib = lib
+    return lib
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype)) if a is not None else None
+
+
+def _vp(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.ctypes.data)
+
+
+@dataclass
+class Filter:
+    """One evaluated filter (see vb_filter).  ``scope_bits``: uint32 words over scope ids or None."""
+    scope_bits: np.ndarray | None = None
+    ts_field: int = TS_NONE
+    ts_lo: int = TS_MIN
+    ts_hi: int = TS_MAX
+
+
+@dataclass
+class SearchResult:
+    rows: np.ndarray            # [B, limit] uint64
+    scores: np.ndarray          # [B, limit] float64
+    counts: np.ndarray          # [B] int32
+    dense_rows: np.ndarray | None = None
+    dense_scores: np.ndarray | None = None
+    dense_counts: np.ndarray | None = None
+    sparse_rows: np.ndarray | None = None
+    sparse_scores: np.ndarray | None = None
+    sparse_counts: np.ndarray | None = None
+
+    def hits(self, q: int):
+        c = int(self.counts[q])
+        return [(int(self.rows[q, i]), float(self.scores[q, i])) for i in range(c)]
+
+    def branch(self, q: int, which: str):
+        rows, sc, cn = ((self.dense_rows, self.dense_scores, self.dense_counts) if which == "dense"
+                        else (self.sparse_rows, self.sparse_scores, self.sparse_counts))
+        c = int(cn[q])
+        return [(int(rows[q, i]), float(sc[q, i])) for i in range(c)]
+
+
+def pack_keys(scores, rows) -> np.ndarray:
+    """Candidate keys as the kernels build them (csrc/common.cuh): hi = monotone map of the fp32
+    score, lo = ~row, so that a larger key means (higher score, then lower row).  0 = empty."""
+    s = np.asarray(scores, dtype=np.float32) + np.float32(0.0)
+    u = s.view(np.uint32).astype(np.uint64)
+    o = np.where(u & 0x80000000, (~u) & 0xFFFFFFFF, u ^ 0x80000000)
+    r = (~np.asarray(rows, dtype=np.uint32)).astype(np.uint64)
+    return ((o << np.uint64(32)) | r).astype(np.uint64)
+
+
+def unpack_keys(keys):
+    """Inverse of pack_keys -> (scores float32, rows uint32)."""
+    k = np.asarray(keys, dtype=np.uint64)
+    o = (k >> np.uint64(32)).astype(np.uint64)
+    u = np.where(o & 0x80000000, o ^ 0x80000000, (~o) & 0xFFFFFFFF).astype(np.uint32)
+    return u.view(np.float32), (~(k & np.uint64(0xFFFFFFFF)).astype(np.uint32))
+
+
+class _Packed:
+    """Keeps the numpy arrays behind a vb_query_batch alive."""
+
+    def __init__(self, dim, queries, sparse, filters, filter_of, limit, kprime, fusion, sparse_weight, apply_idf):
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != dim:
+            raise ValueError(f"queries must have shape [B, {dim}], got {q.shape}")
+        if not np.isfinite(q).all():
+            raise ValueError("Query vector must not contain NaN or inf")
+        B = q.shape[0]
+        self.q = q
+        self.B = B
+        self.indptr = self.terms = self.weights = None
+        if sparse is not None:
+            if len(sparse) != B:
+                raise ValueError("one sparse query (or None) per dense query expected")
+            lens = [0 if s is None else len(s[0]) for s in sparse]
+            self.indptr = np.zeros(B + 1, dtype=np.int64)
+            np.cumsum(lens, out=self.indptr[1:])
+            nnz = int(self.indptr[-1])
+            self.terms = np.zeros(max(nnz, 1), dtype=np.uint32)
+            self.weights = np.zeros(max(nnz, 1), dtype=np.float64)
+            for i, s in enumerate(sparse):
+                if s is None or lens[i] == 0:
+                    continue
+                idx = np.asarray(s[0], dtype=np.int64)
+                if len(s[1]) != len(idx):
+                    raise ValueError("sparse indices/values length mismatch")
+                if (idx < 0).any() or (idx > 0xFFFFFFFF).any():
+                    raise ValueError("sparse index out of uint32 range")
+                self.terms[self.indptr[i]:self.indptr[i + 1]] = idx.astype(np.uint32)
+                self.weights[self.indptr[i]:self.indptr[i + 1]] = np.asarray(s[1], dtype=np.float64)
+        self.filters = list(filters or [])
+        self.bits = [None if f.scope_bits is None else np.ascontiguousarray(f.scope_bits, dtype=np.uint32)
+                     for f in self.filters]
+        self.cfilters = (_Filter * max(1, len(self.filters)))()
+        for i, f in enumerate(self.filters):
+            b = self.bits[i]
+            self.cfilters[i] = _Filter(_ptr(b, C.c_uint32), 0 if b is None else b.size,
+                                       int(f.ts_field), int(f.ts_lo), int(f.ts_hi))
+        self.filter_of = None
+        if filter_of is not None:
+            self.filter_of = np.ascontiguousarray(filter_of, dtype=np.int32)
+            if self.filter_of.shape != (B,):
+                raise ValueError("filter_of must have one entry per query")
+        self.c = _QueryBatch(B, _ptr(self.q, C.c_float), _ptr(self.indptr, C.c_int64), _ptr(self.terms, C.c_uint32),
+                             _ptr(self.weights, C.c_double), int(apply_idf), len(self.filters),
+                             C.cast(self.cfilters, C.POINTER(_Filter)), _ptr(self.filter_of, C.c_int32),
+                             int(limit), int(kprime), int(fusion), float(sparse_weight))
+
+
+class Index:
+    """One shard of the corpus on one GPU (bf16 rows + inverse norms, inverted sparse index,
+    filter columns, tombstones)."""
+
+    def __init__(self, dim: int, device: int = 0, row_base: int = 0, capacity_hint: int = 0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self.dim = int(dim)
+        self.device = int(device)
+        self.row_base = int(row_base)
+        self._check(self._lib.vb_create(self.dim, self.device, int(capacity_hint), self.row_base, C.byref(self._h)))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B200Error(self._lib.vb_last_error().decode("utf-8", "replace"))
+
+    def close(self):
+        if self._h:
+            self._lib.vb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- ingest -----------------------------------------------------------------------------
+    def upsert(self, dense, sparse_csr=None, scope_id=None, created=None, modified=None) -> int:
+        """Append rows (host arrays).  sparse_csr = (indptr int64 [n+1], terms uint32, values float32)
+        with strictly ascending terms inside each row.  Returns the first row id."""
+        d = np.ascontiguousarray(dense, dtype=np.float32)
+        if d.ndim != 2 or d.shape[1] != self.dim:
+            raise ValueError(f"dense must have shape [n, {self.dim}], got {d.shape}")
+        n = d.shape[0]
+        ip = tm = vl = None
+        if sparse_csr is not None:
+            ip = np.ascontiguousarray(sparse_csr[0], dtype=np.int64)
+            tm = np.ascontiguousarray(sparse_csr[1], dtype=np.uint32)
+            vl = np.ascontiguousarray(sparse_csr[2], dtype=np.float32)
+            if ip.shape != (n + 1,):
+                raise ValueError("sparse indptr must have n+1 entries")
+            if tm.size == 0:
+                tm = np.zeros(1, np.uint32)
+                vl = np.zeros(1, np.float32)
+        sc = None if scope_id is None else np.ascontiguousarray(scope_id, dtype=np.uint32)
+        cr = None if created is None else np.ascontiguousarray(created, dtype=np.int64)
+        mo = None if modified is None else np.ascontiguousarray(modified, dtype=np.int64)
+        first = C.c_uint64()
+        self._check(self._lib.vb_upsert(self._h, n, _vp(d), _vp(ip), _vp(tm), _vp(vl), _vp(sc), _vp(cr), _vp(mo),
+                                        C.byref(first)))
+        return int(first.value)
+
+    def upsert_dev(self, n: int, rows_bf16_ptr: int, indptr_ptr=None, terms_ptr=None, vals_ptr=None,
+                   scope_ptr=None, created_ptr=None, modified_ptr=None) -> int:
+        """Bulk append from device pointers (e.g. torch tensors' data_ptr())."""
+        first = C.c_uint64()
+        self._check(self._lib.vb_upsert_dev(self._h, int(n), _vp(rows_bf16_ptr), _vp(indptr_ptr), _vp(terms_ptr),
+                                            _vp(vals_ptr), _vp(scope_ptr), _vp(created_ptr), _vp(modified_ptr),
+                                            C.byref(first)))
+        return int(first.value)
+
+    def delete_rows(self, rows) -> None:
+        r = np.ascontiguousarray(rows, dtype=np.uint64)
+        self._check(self._lib.vb_delete_rows(self._h, r.size, _vp(r)))
+
+    def term_stats(self, terms):
+        t = np.ascontiguousarray(terms, dtype=np.uint32)
+        df = np.zeros(max(1, t.size), dtype=np.uint64)
+        n_live = C.c_uint64()
+        self._check(self._lib.vb_term_stats(self._h, t.size, _vp(t if t.size else np.zeros(1, np.uint32)), _vp(df),
+                                            C.byref(n_live)))
+        return df[:t.size], int(n_live.value)
+
+    # ---- query ------------------------------------------------------------------------------
+    def _alloc_result(self, B, limit, kprime, branches):
+        r = SearchResult(np.zeros((B, limit), np.uint64), np.zeros((B, limit), np.float64), np.zeros(B, np.int32))
+        if branches:
+            r.dense_rows = np.zeros((B, kprime), np.uint64)
+            r.dense_scores = np.zeros((B, kprime), np.float32)
+            r.dense_counts = np.zeros(B, np.int32)
+            r.sparse_rows = np.zeros((B, kprime), np.uint64)
+            r.sparse_scores = np.zeros((B, kprime), np.float32)
+            r.sparse_counts = np.zeros(B, np.int32)
+        c = _Result(_ptr(r.rows, C.c_uint64), _ptr(r.scores, C.c_double), _ptr(r.counts, C.c_int32),
+                    _ptr(r.dense_rows, C.c_uint64), _ptr(r.dense_scores, C.c_float), _ptr(r.dense_counts, C.c_int32),
+                    _ptr(r.sparse_rows, C.c_uint64), _ptr(r.sparse_scores, C.c_float), _ptr(r.sparse_counts, C.c_int32))
+        return r, c
+
+    def search_batch(self, queries, sparse=None, filters=None, filter_of=None, limit: int = 10,
+                     kprime: int | None = None, fusion: str | int = "weighted", sparse_weight: float = 0.1,
+                     apply_idf: bool = True, branches: bool = False) -> SearchResult:
+        """Hybrid filtered top-k for a batch (host buffers in/out; one vb_search call)."""
+        fz = FUSION[fusion] if isinstance(fusion, str) else int(fusion)
+        if kprime is None:
+            kprime = limit * 3 if (sparse is not None and fz != FUSE_DENSE_ONLY) else limit
+        p = _Packed(self.dim, queries, sparse, filters, filter_of, limit, kprime, fz, sparse_weight, apply_idf)
+        res, cres = self._alloc_result(p.B, limit, kprime, branches)
+        self._check(self._lib.vb_search(self._h, C.byref(p.c), C.byref(cres)))
+        return res
+
+    def search_local(self, cand_dev_ptr: int, queries, sparse=None, filters=None, filter_of=None, limit: int = 10,
+                     kprime: int | None = None, fusion: str | int = "weighted", sparse_weight: float = 0.1):
+        """Shard-local branch top-k' left on the device (all-gather payload); weights carry global IDF."""
+        fz = FUSION[fusion] if isinstance(fusion, str) else int(fusion)
+        if kprime is None:
+            kprime = limit * 3
+        p = _Packed(self.dim, queries, sparse, filters, filter_of, limit, kprime, fz, sparse_weight, False)
+        self._check(self._lib.vb_search_local(self._h, C.byref(p.c), _vp(cand_dev_ptr)))
+
+    def merge_fuse(self, gathered_dev_ptr: int, n_shards: int, queries, sparse=None, limit: int = 10,
+                   kprime: int | None = None, fusion: str | int = "weighted", sparse_weight: float = 0.1,
+                   branches: bool = False) -> SearchResult:
+        fz = FUSION[fusion] if isinstance(fusion, str) else int(fusion)
+        if kprime is None:
+            kprime = limit * 3
+        p = _Packed(self.dim, queries, sparse, None, None, limit, kprime, fz, sparse_weight, False)
+        res, cres = self._alloc_result(p.B, limit, kprime, branches)
+        self._check(self._lib.vb_merge_fuse(self._h, C.byref(p.c), int(n_shards), _vp(gathered_dev_ptr), C.byref(cres)))
+        return res
+
+    def set_option(self, key: str, value: int) -> None:
+        self._check(self._lib.vb_set_option(self._h, key.encode(), int(value)))
+
+    def stats(self) -> dict:
+        s = _Stats()
+        self._check(self._lib.vb_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in _Stats._fields_}
+
+    def sync(self) -> None:
+        self._check(self._lib.vb_sync(self._h))

@@ -1,0 +1,124 @@
+"""Row-sharded multi-GPU search: one process per GPU, ``torch.distributed`` for the plumbing.
+
+The corpus is row-partitioned (contiguous blocks; dense rows, postings, filter columns and
+tombstones all follow the same row -> shard map).  Queries, filters and the IDF inputs are
+replicated.  Each rank computes the exact top-k' of both branches over its shard
+(``vb_search_local``); the ONE exchange step of the path is an all-gather of those candidates
+(``[2][B][k']`` packed u64 per rank — NCCL over NVLink on GPUs, gloo in the CPU tests); every rank
+then merges n_shards*k' -> k' per branch and only THEN fuses (min-max and ranks are global
+properties; fusing per shard would be wrong) — ``vb_merge_fuse``.
+
+IDF needs global statistics (N = live points, df per term).  They are host-owned: ``finalize()``
+all-gathers each shard's (term, df) directory once and keeps the summed table, so the per-query
+weights are computed identically on every rank without a per-query collective.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class ShardedIndex:
+    def __init__(self, index, rank: int, world: int, group=None, device=None):
+        """``index``: this rank's engine.Index (created with row_base = first global row of the shard)."""
+        self.index = index
+        self.rank, self.world, self.group = rank, world, group
+        self.device = device if device is not None else torch.device("cuda", index.device)
+        self.terms_g: np.ndarray | None = None
+        self.df_g: np.ndarray | None = None
+        self.n_live_g = 0
+        self._bufs: dict = {}
+
+    # ---- global IDF statistics ----------------------------------------------------------------
+    def _all_gather_var(self, arr: np.ndarray) -> list[np.ndarray]:
+        """all-gather of variable-length int64 arrays (pad to the max length)."""
+        n = torch.tensor([arr.size], dtype=torch.int64, device=self.device)
+        sizes = [torch.zeros_like(n) for _ in range(self.world)]
+        dist.all_gather(sizes, n, group=self.group)
+        m = max(int(s.item()) for s in sizes)
+        buf = torch.zeros(max(m, 1), dtype=torch.int64, device=self.device)
+        buf[:arr.size] = torch.from_numpy(arr.astype(np.int64)).to(self.device)
+        out = [torch.zeros_like(buf) for _ in range(self.world)]
+        dist.all_gather(out, buf, group=self.group)
+        return [o[:int(s.item())].cpu().numpy() for o, s in zip(out, sizes)]
+
+    def finalize(self, local_terms: np.ndarray, local_df: np.ndarray, n_live_local: int) -> None:
+        """Exchange the shard term directories; afterwards ``idf_weights`` needs no collective."""
+        packed = (local_terms.astype(np.int64) << 32) | local_df.astype(np.int64)
+        parts = self._all_gather_var(packed)
+        allp = np.concatenate(parts) if parts else np.zeros(0, np.int64)
+        terms = (allp >> 32).astype(np.uint32)
+        df = (allp & 0xFFFFFFFF).astype(np.int64)
+        order = np.argsort(terms, kind="stable")
+        terms, df = terms[order], df[order]
+        uniq, start = np.unique(terms, return_index=True)
+        self.terms_g = uniq
+        self.df_g = np.add.reduceat(df, start) if len(df) else np.zeros(0, np.int64)
+        n = torch.tensor([n_live_local], dtype=torch.int64, device=self.device)
+        dist.all_reduce(n, group=self.group)
+        self.n_live_g = int(n.item())
+
+    def finalize_from_queries(self, sparse_batches) -> None:
+        """Cheaper variant for static benchmark corpora: only the terms that occur in the given
+        query batches are exchanged (df via vb_term_stats on each shard)."""
+        terms = sorted({int(t) for sp in sparse_batches for s in sp if s is not None for t in s[0]})
+        t = np.asarray(terms, dtype=np.uint32)
+        df, n_live = self.index.term_stats(t)
+        self.finalize(t, np.asarray(df, dtype=np.int64), n_live)
+
+    def idf_weights(self, sparse):
+        """qdrant's IDF modifier with GLOBAL statistics (local_collection.py _rescore_idf)."""
+        if sparse is None:
+            return None
+        out = []
+        N = self.n_live_g
+        for s in sparse:
+            if s is None or len(s[0]) == 0:
+                out.append(None)
+                continue
+            idx = np.asarray(s[0], dtype=np.uint32)
+            pos = np.searchsorted(self.terms_g, idx)
+            pos_c = np.minimum(pos, max(len(self.terms_g) - 1, 0))
+            hit = (pos < len(self.terms_g)) & (self.terms_g[pos_c] == idx) if len(self.terms_g) else np.zeros(len(idx), bool)
+            w = []
+            for j, v in enumerate(s[1]):
+                d = float(self.df_g[pos_c[j]]) if hit[j] else 0.0
+                w.append(float(v) * math.log((N - d + 0.5) / (d + 0.5) + 1.0))
+            out.append((list(s[0]), w))
+        return out
+
+    # ---- query --------------------------------------------------------------------------------
+    def _buf(self, name, numel):
+        b = self._bufs.get(name)
+        if b is None or b.numel() < numel:
+            b = torch.zeros(numel, dtype=torch.int64, device=self.device)
+            self._bufs[name] = b
+        return b[:numel]
+
+    def search_batch(self, queries, sparse=None, filters=None, filter_of=None, limit=10, kprime=None,
+                     fusion="weighted", sparse_weight=0.1, branches=False):
+        """Same call shape and result as engine.Index.search_batch; identical on every rank."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        B = q.shape[0]
+        any_sparse = sparse is not None and any(s is not None and len(s[0]) for s in sparse)
+        if kprime is None:
+            kprime = limit * 3 if (any_sparse and fusion != "dense") else limit
+        weighted = self.idf_weights(sparse) if any_sparse else None
+        n_local = 2 * B * kprime
+        local = self._buf("local", n_local)
+        gathered = self._buf("gathered", n_local * self.world)
+        self.index.search_local(local.data_ptr(), q, weighted, filters, filter_of, limit=limit, kprime=kprime,
+                                fusion=fusion, sparse_weight=sparse_weight)
+        if self.world > 1:
+            dist.all_gather_into_tensor(gathered, local, group=self.group)   # the path's one exchange step
+            if gathered.is_cuda:
+                torch.cuda.current_stream(self.device).synchronize()
+        else:
+            gathered.copy_(local)
+            if gathered.is_cuda:
+                torch.cuda.current_stream(self.device).synchronize()
+        return self.index.merge_fuse(gathered.data_ptr(), self.world, q, weighted, limit=limit, kprime=kprime,
+                                     fusion=fusion, sparse_weight=sparse_weight, branches=branches)

@@ -1,0 +1,612 @@
+"""Drop-in replacement for ``voitta.services.vector_store`` backed by the B200 index.
+
+Same names, argument order, defaults, return types and error behaviour as the reference class
+(/root/reference/src/voitta/services/vector_store.py:18-1028): ``ChunkMetadata``, ``StoredChunk``,
+``VectorStoreService`` (22 methods) and ``get_vector_store()``.  What the reference forwards to
+Qdrant is split in two here:
+
+  * arithmetic (cosine top-k, IDF sparse scoring, filter evaluation, fusion) -> the CUDA library
+    through ``engine.Index`` (C ABI, include/voitta_b200.h);
+  * payloads, point ids and the exact-match lookups behind the scroll / count / delete helpers ->
+    host-side maps in ``_Collection`` (they are dictionary work, not GPU work).
+
+State is process-global per collection name, so a second ``VectorStoreService()`` (as
+api/routes/folders.py:139-141 creates) sees the same index.  Thread-safe (one re-entrant lock per
+collection; callers are MCP worker threads, the indexing worker and the watchdog thread).
+
+Additive API (not in the reference): ``search_batch`` and the ``fusion`` switch
+(``VOITTA_FUSION=weighted|rrf``; default ``weighted`` = the reference's behaviour).
+"""
+from __future__ import annotations
+
+import logging
+import os
+import threading
+import uuid
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import engine
+
+logger = logging.getLogger("voitta.services.vector_store")
+
+SPARSE_VECTOR_NAME = "bm25"  # reference: services/sparse_embedding.py:9
+
+
+@dataclass
+class ChunkMetadata:
+    """Metadata for a stored chunk (reference :18-41)."""
+
+    file_path: str
+    folder_path: str
+    index_folder: str
+    file_name: str
+    chunk_index: int
+    total_chunks: int
+    start_char: int
+    end_char: int
+    indexed_at: str
+    start_page: int | None = None
+    end_page: int | None = None
+    source_page_count: int | None = None
+    source_created_at: int | None = None
+    source_modified_at: int | None = None
+    allowed_users: list[str] | None = None
+    source_url: str | None = None
+
+
+@dataclass
+class StoredChunk:
+    """A chunk stored in the vector database (reference :44-51)."""
+
+    id: str
+    text: str
+    metadata: ChunkMetadata
+    score: float | None = None
+
+
+class _Settings:
+    """The six keys the reference store reads from voitta.config (config.py:28-34,44,72) plus
+    the backend's own."""
+
+    def __init__(self):
+        self.qdrant_host = os.getenv("QDRANT_HOST", "localhost")
+        self.qdrant_port = int(os.getenv("QDRANT_PORT", "6333"))
+        self.qdrant_collection = os.getenv("QDRANT_COLLECTION", "voitta_documents")
+        self.embedding_dimension = int(os.getenv("EMBEDDING_DIMENSION", "768"))
+        self.device = int(os.getenv("VOITTA_B200_DEVICE", "0"))
+        self.fusion = os.getenv("VOITTA_FUSION", "weighted")
+
+
+def get_settings() -> _Settings:
+    return _Settings()
+
+
+_OPTIONAL = ("start_page", "end_page", "source_page_count", "source_created_at",
+             "source_modified_at", "allowed_users", "source_url")
+
+
+def _payload_to_chunk(pid: str, payload: dict, score) -> StoredChunk:
+    """reference :532-558 (_result_to_chunk) and the identical blocks at :186-210, :943-965."""
+    return StoredChunk(
+        id=str(pid),
+        text=payload["text"],
+        metadata=ChunkMetadata(
+            file_path=payload["file_path"],
+            folder_path=payload["folder_path"],
+            index_folder=payload.get("index_folder", payload["folder_path"]),
+            file_name=payload["file_name"],
+            chunk_index=payload["chunk_index"],
+            total_chunks=payload["total_chunks"],
+            start_char=payload["start_char"],
+            end_char=payload["end_char"],
+            indexed_at=payload["indexed_at"],
+            **{k: payload.get(k) for k in _OPTIONAL},
+        ),
+        score=score,
+    )
+
+
+class _Collection:
+    """Host half of one collection: ids, payloads and exact-match maps; owns the device index."""
+
+    def __init__(self, name: str, dim: int, device: int, index_factory=None):
+        self.name = name
+        self.dim = dim
+        self.device = device
+        self.lock = threading.RLock()
+        self._factory = index_factory or (lambda: engine.Index(dim, device=device))
+        self._index = None
+        self.ids: list[str] = []              # row -> point id
+        self.payload: list[dict | None] = []  # row -> payload (None once deleted)
+        self.n_live = 0
+        self.by_file: dict[str, set[int]] = {}
+        self.by_folder: dict[str, set[int]] = {}
+        self.by_index_folder: dict[str, set[int]] = {}
+        self.by_url: dict[str, set[int]] = {}
+        self.scopes: dict[tuple[str, str], int] = {}   # (folder_path, index_folder) -> scope id
+        self.scope_list: list[tuple[str, str]] = []
+
+    @property
+    def index(self):
+        with self.lock:
+            if self._index is None:
+                logger.info(f"Creating B200 index '{self.name}' (dim={self.dim}, device={self.device})")
+                self._index = self._factory()
+            return self._index
+
+    def scope_id(self, folder_path: str, index_folder: str) -> int:
+        key = (folder_path, index_folder)
+        sid = self.scopes.get(key)
+        if sid is None:
+            sid = len(self.scope_list)
+            self.scopes[key] = sid
+            self.scope_list.append(key)
+        return sid
+
+    def _map_add(self, m: dict, key, row: int):
+        if key is not None:
+            m.setdefault(key, set()).add(row)
+
+    def add_rows(self, first_row: int, ids: list[str], payloads: list[dict]):
+        assert first_row == len(self.ids)
+        for i, (pid, p) in enumerate(zip(ids, payloads)):
+            r = first_row + i
+            self.ids.append(pid)
+            self.payload.append(p)
+            self._map_add(self.by_file, p["file_path"], r)
+            self._map_add(self.by_folder, p["folder_path"], r)
+            self._map_add(self.by_index_folder, p["index_folder"], r)
+            self._map_add(self.by_url, p.get("source_url"), r)
+        self.n_live += len(ids)
+
+    def remove_rows(self, rows: list[int]):
+        for r in rows:
+            p = self.payload[r]
+            if p is None:
+                continue
+            for m, k in ((self.by_file, p["file_path"]), (self.by_folder, p["folder_path"]),
+                         (self.by_index_folder, p["index_folder"]), (self.by_url, p.get("source_url"))):
+                if k is not None and k in m:
+                    m[k].discard(r)
+                    if not m[k]:
+                        del m[k]
+            self.payload[r] = None
+            self.n_live -= 1
+
+    def live_rows(self):
+        return (r for r, p in enumerate(self.payload) if p is not None)
+
+
+_collections: dict[str, _Collection] = {}
+_collections_lock = threading.Lock()
+
+
+def _get_collection(name: str, dim: int, device: int, index_factory=None) -> _Collection:
+    with _collections_lock:
+        c = _collections.get(name)
+        if c is None:
+            c = _Collection(name, dim, device, index_factory)
+            _collections[name] = c
+        elif c.dim != dim:
+            raise ValueError(f"collection '{name}' exists with dimension {c.dim}, requested {dim}")
+        return c
+
+
+def _drop_collection(name: str) -> None:
+    """Test helper: forget a collection (frees the device index)."""
+    with _collections_lock:
+        c = _collections.pop(name, None)
+    if c is not None and c._index is not None:
+        c._index.close()
+
+
+class VectorStoreService:
+    """Service for storing and retrieving document chunks on the B200 index (reference :54)."""
+
+    def __init__(self, _index_factory=None):
+        settings = get_settings()
+        self.host = settings.qdrant_host
+        self.port = settings.qdrant_port
+        self.collection_name = settings.qdrant_collection
+        self.dimension = settings.embedding_dimension
+        self.fusion = settings.fusion
+        self._device = settings.device
+        self._client = None
+        self._has_sparse: bool = False
+        self._index_factory = _index_factory
+
+    # ---- lazy "connection" (reference :66-115) --------------------------------------------------
+    @property
+    def _coll(self) -> _Collection:
+        return _get_collection(self.collection_name, self.dimension, self._device, self._index_factory)
+
+    @property
+    def client(self):
+        """Lazy-create the device index (the reference lazily connects to Qdrant here)."""
+        if self._client is None:
+            self._client = self._coll.index
+            self._ensure_collection()
+        return self._client
+
+    def _ensure_collection(self) -> None:
+        # a new collection always carries the sparse vector "bm25" with IDF (reference :95-99,114)
+        self._has_sparse = True
+
+    # ---- helpers --------------------------------------------------------------------------------
+    def _rows_where(self, coll: _Collection, m: dict, key) -> list[int]:
+        return sorted(r for r in m.get(key, ()) if coll.payload[r] is not None)
+
+    def _by_id(self, coll: _Collection, rows) -> list[int]:
+        """scroll() order: ascending point id."""
+        return sorted(rows, key=lambda r: coll.ids[r])
+
+    def find_by_source_url(self, source_url: str) -> list[StoredChunk]:
+        """Find all chunks matching a given source_url, sorted by chunk_index (reference :163)."""
+        coll = self._coll
+        with coll.lock:
+            rows = self._by_id(coll, self._rows_where(coll, coll.by_url, source_url))
+            chunks = [_payload_to_chunk(coll.ids[r], coll.payload[r], None) for r in rows]
+        chunks.sort(key=lambda c: c.metadata.chunk_index)
+        return chunks
+
+    def set_file_acl(self, file_path: str, allowed_users: list[str]) -> None:
+        """Update allowed_users on all chunks for a specific file (reference :216)."""
+        coll = self._coll
+        with coll.lock:
+            for r in self._rows_where(coll, coll.by_file, file_path):
+                coll.payload[r]["allowed_users"] = allowed_users
+
+    def store_chunks(
+        self,
+        chunks: list[tuple[str, list[float], ChunkMetadata]],
+        sparse_vectors: list[tuple[list[int], list[float]]] | None = None,
+        batch_size: int = 100,
+    ) -> list[str]:
+        """Store multiple chunks with their embeddings; returns the generated point ids
+        (reference :233-317)."""
+        if not chunks:
+            return []
+        n = len(chunks)
+        dense = np.empty((n, self.dimension), dtype=np.float32)
+        ids, payloads = [], []
+        indptr = np.zeros(n + 1, dtype=np.int64)
+        terms, vals = [], []
+        created = np.full(n, engine.TS_MISSING, dtype=np.int64)
+        modified = np.full(n, engine.TS_MISSING, dtype=np.int64)
+        coll = self._coll
+        for idx, (text, embedding, metadata) in enumerate(chunks):
+            ids.append(str(uuid.uuid4()))
+            payload = {
+                "text": text,
+                "file_path": metadata.file_path,
+                "folder_path": metadata.folder_path,
+                "index_folder": metadata.index_folder,
+                "file_name": metadata.file_name,
+                "chunk_index": metadata.chunk_index,
+                "total_chunks": metadata.total_chunks,
+                "start_char": metadata.start_char,
+                "end_char": metadata.end_char,
+                "indexed_at": metadata.indexed_at,
+            }
+            for k in _OPTIONAL:
+                v = getattr(metadata, k)
+                if v is not None:
+                    payload[k] = v
+            payloads.append(payload)
+            if len(embedding) != self.dimension:
+                raise ValueError(f"Vector dimension error: expected {self.dimension}, got {len(embedding)}")
+            dense[idx] = embedding
+            if metadata.source_created_at is not None:
+                created[idx] = int(metadata.source_created_at)
+            if metadata.source_modified_at is not None:
+                modified[idx] = int(metadata.source_modified_at)
+            nnz = 0
+            if sparse_vectors and idx < len(sparse_vectors):
+                indices, values = sparse_vectors[idx]
+                if len(indices) != len(values):
+                    raise ValueError("sparse vector indices/values length mismatch")
+                if len(indices):
+                    ix = np.asarray(indices, dtype=np.int64)
+                    order = np.argsort(ix, kind="stable")   # qdrant sorts sparse vectors by index at upsert
+                    ix = ix[order]
+                    if (ix < 0).any() or (ix > 0xFFFFFFFF).any():
+                        raise ValueError("sparse index out of uint32 range")
+                    if (np.diff(ix) == 0).any():
+                        raise ValueError("sparse vector indices must be unique")
+                    terms.append(ix.astype(np.uint32))
+                    vals.append(np.asarray(values, dtype=np.float32)[order])
+                    nnz = len(ix)
+            indptr[idx + 1] = indptr[idx] + nnz
+        with coll.lock:
+            scope = np.fromiter((coll.scope_id(p["folder_path"], p["index_folder"]) for p in payloads),
+                                dtype=np.uint32, count=n)
+            tcat = np.concatenate(terms) if terms else np.zeros(0, np.uint32)
+            vcat = np.concatenate(vals) if vals else np.zeros(0, np.float32)
+            index = self.client
+            first = None
+            for i in range(0, n, max(1, batch_size)):       # reference upserts in batches (:311-313)
+                j = min(n, i + max(1, batch_size))
+                lo, hi = indptr[i], indptr[j]
+                f = index.upsert(dense[i:j], (indptr[i:j + 1] - lo, tcat[lo:hi], vcat[lo:hi]),
+                                 scope[i:j], created[i:j], modified[i:j])
+                if first is None:
+                    first = f
+            coll.add_rows(first - getattr(index, "row_base", 0), ids, payloads)
+        logger.info(f"Stored {n} chunks in B200 index")
+        return ids
+
+    def _delete_where(self, m_name: str, key: str, what: str) -> int:
+        coll = self._coll
+        with coll.lock:
+            rows = self._rows_where(coll, getattr(coll, m_name), key)
+            count = len(rows)
+            if count > 0:
+                index = self.client
+                base = getattr(index, "row_base", 0)
+                index.delete_rows(np.asarray(rows, dtype=np.uint64) + np.uint64(base))
+                coll.remove_rows(rows)
+                logger.info(f"Deleted {count} chunks for {what}: {key}")
+        return count
+
+    def delete_by_file(self, file_path: str) -> int:
+        """Delete all chunks for a specific file; returns the number deleted (reference :319)."""
+        return self._delete_where("by_file", file_path, "file")
+
+    def delete_by_folder(self, folder_path: str) -> int:
+        """Delete all chunks whose folder_path equals folder_path (reference :357)."""
+        return self._delete_where("by_folder", folder_path, "folder")
+
+    def delete_by_index_folder(self, index_folder: str) -> int:
+        """Delete all chunks indexed from a specific index folder (reference :395)."""
+        return self._delete_where("by_index_folder", index_folder, "index_folder")
+
+    def get_file_paths_by_index_folder(self, index_folder: str) -> set[str]:
+        """All unique file_path values for a given index_folder (reference :436)."""
+        coll = self._coll
+        with coll.lock:
+            return {coll.payload[r]["file_path"] for r in self._rows_where(coll, coll.by_index_folder, index_folder)}
+
+    # ---- filter (reference :462-530) ------------------------------------------------------------
+    def _build_filter(
+        self,
+        folder_filter: str | None = None,
+        include_folders: list[str] | None = None,
+        exclude_folders: list[str] | None = None,
+        exclude_index_folders: list[str] | None = None,
+        date_start: int | None = None,
+        date_end: int | None = None,
+        date_field: str | None = None,
+    ) -> engine.Filter | None:
+        """Evaluate the folder clauses over the scope dictionary and return the device filter.
+
+        must folder_path == folder_filter; must folder_path IN include_folders (exact strings, the
+        caller already expanded prefixes); must_not folder_path == e; must_not index_folder == f;
+        must ts in [gte, lte] on source_created_at if date_field == "created" else source_modified_at.
+        Returns None when no clause applies (reference :525-530)."""
+        coll = self._coll
+        bits = None
+        if folder_filter or include_folders or exclude_folders or exclude_index_folders:
+            inc = set(include_folders) if include_folders else None
+            exc = set(exclude_folders) if exclude_folders else ()
+            dis = set(exclude_index_folders) if exclude_index_folders else ()
+            with coll.lock:
+                n_scopes = len(coll.scope_list)
+                bits = np.zeros(max(1, (n_scopes + 31) // 32), dtype=np.uint32)
+                for sid, (fp, ifp) in enumerate(coll.scope_list):
+                    ok = ((not folder_filter or fp == folder_filter) and (inc is None or fp in inc)
+                          and fp not in exc and ifp not in dis)
+                    if ok:
+                        bits[sid >> 5] |= np.uint32(1 << (sid & 31))
+        ts_field, lo, hi = engine.TS_NONE, engine.TS_MIN, engine.TS_MAX
+        if date_start is not None or date_end is not None:
+            field_map = {"created": engine.TS_CREATED, "modified": engine.TS_MODIFIED}
+            ts_field = field_map.get(date_field, engine.TS_MODIFIED) if date_field else engine.TS_MODIFIED
+            if date_start is not None:
+                lo = max(engine.TS_MIN, int(np.ceil(date_start)))
+            if date_end is not None:
+                hi = min(engine.TS_MAX, int(np.floor(date_end)))
+        if bits is None and ts_field == engine.TS_NONE:
+            return None
+        return engine.Filter(scope_bits=bits, ts_field=ts_field, ts_lo=lo, ts_hi=hi)
+
+    def _rows_to_chunks(self, coll: _Collection, hits) -> list[StoredChunk]:
+        base = getattr(coll.index, "row_base", 0)
+        out = []
+        for row, score in hits:
+            r = row - base
+            out.append(_payload_to_chunk(coll.ids[r], coll.payload[r], score))
+        return out
+
+    def search(
+        self,
+        query_embedding: list[float],
+        limit: int = 10,
+        folder_filter: str | None = None,
+        include_folders: list[str] | None = None,
+        exclude_folders: list[str] | None = None,
+        exclude_index_folders: list[str] | None = None,
+        sparse_query: tuple[list[int], list[float]] | None = None,
+        sparse_weight: float = 0.1,
+        date_start: int | None = None,
+        date_end: int | None = None,
+        date_field: str | None = None,
+    ) -> list[StoredChunk]:
+        """Dense or hybrid (dense + sparse) retrieval (reference :560-697).
+
+        Hybrid iff ``sparse_query`` has indices and the collection has the sparse vector: both
+        branches fetch limit*3 candidates under the same filter and are fused (min-max weighted
+        sum by default).  Otherwise dense-only with ``limit``."""
+        return self.search_batch(
+            [query_embedding], limit, folder_filter, include_folders, exclude_folders, exclude_index_folders,
+            [sparse_query], sparse_weight, date_start, date_end, date_field)[0]
+
+    def search_batch(
+        self,
+        query_embeddings,
+        limit: int = 10,
+        folder_filter: str | None = None,
+        include_folders: list[str] | None = None,
+        exclude_folders: list[str] | None = None,
+        exclude_index_folders: list[str] | None = None,
+        sparse_queries=None,
+        sparse_weight: float = 0.1,
+        date_start: int | None = None,
+        date_end: int | None = None,
+        date_field: str | None = None,
+        fusion: str | None = None,
+    ) -> list[list[StoredChunk]]:
+        """Additive: ``search`` for B queries sharing one filter, in one device pass."""
+        index = self.client
+        coll = self._coll
+        search_filter = self._build_filter(
+            folder_filter, include_folders, exclude_folders, exclude_index_folders,
+            date_start=date_start, date_end=date_end, date_field=date_field)
+        B = len(query_embeddings)
+        q = np.asarray(query_embeddings, dtype=np.float32)
+        if q.ndim != 2 or q.shape[1] != self.dimension:
+            raise ValueError(f"Vector dimension error: expected {self.dimension}, got {q.shape[-1] if q.ndim else 0}")
+        sparse = [None] * B
+        any_sparse = False
+        if sparse_queries is not None and self._has_sparse:
+            for i, sq in enumerate(sparse_queries):
+                if sq:
+                    indices, values = sq
+                    if len(indices):
+                        sparse[i] = (indices, values)
+                        any_sparse = True
+        with coll.lock:
+            if coll.n_live == 0:
+                return [[] for _ in range(B)]
+            res = index.search_batch(
+                q, sparse if any_sparse else None,
+                filters=[search_filter] if search_filter is not None else None,
+                filter_of=np.zeros(B, np.int32) if search_filter is not None else None,
+                limit=limit, kprime=limit * 3 if any_sparse else limit,
+                fusion=(fusion or self.fusion) if any_sparse else "dense", sparse_weight=sparse_weight)
+            return [self._rows_to_chunks(coll, res.hits(i)) for i in range(B)]
+
+    # ---- collection / scroll helpers (reference :699-1016) --------------------------------------
+    def get_collection_info(self) -> dict:
+        """Information about the collection (reference :699)."""
+        try:
+            coll = self._coll
+            return {
+                "name": self.collection_name,
+                "vectors_count": coll.n_live,
+                "points_count": coll.n_live,
+                "status": "green",
+            }
+        except Exception as e:
+            return {"error": str(e)}
+
+    def count_by_file(self, file_path: str) -> int:
+        """Count chunks for a specific file (reference :712)."""
+        try:
+            coll = self._coll
+            with coll.lock:
+                return len(self._rows_where(coll, coll.by_file, file_path))
+        except Exception:
+            return 0
+
+    def count_chunks_for_files(self, file_paths: list[str]) -> dict[str, int]:
+        """Chunk counts for several files; only files with chunks appear (reference :730)."""
+        if not file_paths:
+            return {}
+        try:
+            coll = self._coll
+            out: dict[str, int] = {}
+            with coll.lock:
+                for fp in dict.fromkeys(file_paths):
+                    c = len(self._rows_where(coll, coll.by_file, fp))
+                    if c:
+                        out[fp] = c
+            return out
+        except Exception as e:
+            logger.error(f"Error counting chunks for files: {e}")
+            return {}
+
+    def _file_counts(self, coll: _Collection) -> dict[str, int]:
+        return {fp: n for fp, rows in coll.by_file.items() if (n := sum(1 for r in rows if coll.payload[r] is not None))}
+
+    def count_chunks_for_folder(self, folder_path: str) -> tuple[int, int]:
+        """(indexed file count, total chunk count) under a folder, recursively (reference :777)."""
+        try:
+            prefix = folder_path + "/" if folder_path else ""
+            coll = self._coll
+            with coll.lock:
+                fc = {fp: n for fp, n in self._file_counts(coll).items()
+                      if fp.startswith(prefix) or (not prefix and "/" not in fp)}
+            return len(fc), sum(fc.values())
+        except Exception as e:
+            logger.error(f"Error counting chunks for folder {folder_path}: {e}")
+            return 0, 0
+
+    def get_folder_stats_batch(self, folder_paths: list[str]) -> dict[str, tuple[int, int]]:
+        """(file count, chunk count) for several folders in one scan (reference :816)."""
+        if not folder_paths:
+            return {}
+        try:
+            coll = self._coll
+            with coll.lock:
+                counts = self._file_counts(coll)
+            out = {}
+            for folder in folder_paths:
+                prefix = folder + "/" if folder else ""
+                sel = [n for fp, n in counts.items() if fp.startswith(prefix) or (not prefix and "/" not in fp)]
+                out[folder] = (len(sel), sum(sel))
+            return out
+        except Exception as e:
+            logger.error(f"Error getting folder stats batch: {e}")
+            return {fp: (0, 0) for fp in folder_paths}
+
+    def get_stored_page_count(self, file_path: str) -> int | None:
+        """Stored source_page_count of (any chunk of) a PDF file (reference :869)."""
+        try:
+            coll = self._coll
+            with coll.lock:
+                rows = self._by_id(coll, self._rows_where(coll, coll.by_file, file_path))
+                if rows and coll.payload[rows[0]].get("source_page_count"):
+                    return coll.payload[rows[0]]["source_page_count"]
+            return None
+        except Exception as e:
+            logger.error(f"Error getting stored page count for {file_path}: {e}")
+            return None
+
+    def get_chunks_by_range(self, file_path: str, first_chunk: int, last_chunk: int) -> list[StoredChunk]:
+        """Chunks of a file with first_chunk <= chunk_index <= last_chunk, sorted (reference :898)."""
+        try:
+            coll = self._coll
+            with coll.lock:
+                rows = self._by_id(coll, self._rows_where(coll, coll.by_file, file_path))
+                chunks = [_payload_to_chunk(coll.ids[r], coll.payload[r], None) for r in rows
+                          if first_chunk <= coll.payload[r]["chunk_index"] <= last_chunk]
+            chunks.sort(key=lambda c: c.metadata.chunk_index)
+            return chunks
+        except Exception as e:
+            logger.error(f"Error getting chunks by range for {file_path}: {e}")
+            return []
+
+    def get_file_chunk_counts(self, folder_prefix: str = "") -> dict[str, int]:
+        """Chunk counts for all files, optionally restricted to a path prefix (reference :979)."""
+        try:
+            coll = self._coll
+            with coll.lock:
+                return {fp: n for fp, n in self._file_counts(coll).items()
+                        if not folder_prefix or fp.startswith(folder_prefix)}
+        except Exception as e:
+            logger.error(f"Error getting file chunk counts: {e}")
+            return {}
+
+
+# Global singleton instance (reference :1019-1028)
+_vector_store: VectorStoreService | None = None
+
+
+def get_vector_store() -> VectorStoreService:
+    """Get the global vector store service instance."""
+    global _vector_store
+    if _vector_store is None:
+        _vector_store = VectorStoreService()
+    return _vector_store
