@@ -98,6 +98,8 @@ typedef struct vb_stats {
     uint32_t last_dense_path;     /* 1 = GEMV scan (K1), 2 = tcgen05 GEMM (K2)                */
     uint32_t last_launches;       /* kernels launched by the last vb_search                   */
     uint64_t device_bytes;
+    uint64_t last_h2d_bytes, last_d2h_bytes;   /* host<->device copies of the last staged search */
+    uint64_t last_dense_passes;                /* passes over the shard's dense rows (K1: B, K2: sub-batches) */
 } vb_stats;
 
 int         vb_abi_version(void);
@@ -138,17 +140,34 @@ int vb_term_stats(vb_index* h, uint32_t n_terms, const uint32_t* terms, uint64_t
 int vb_search(vb_index* h, const vb_query_batch* q, vb_result* out);
 
 /* Multi-GPU building blocks (one process per GPU).
- * vb_search_local: branch top-k' of this shard, left on the device as packed candidates
- *   cand[2][B][kprime] (u64; 0 = empty slot; branch 0 dense, 1 sparse), ready for an
- *   all-gather.  Query weights must already carry the GLOBAL idf (apply_idf = 0).
- * vb_merge_fuse: merge `n_shards` gathered candidate blocks [n_shards][2][B][kprime] (device)
- *   into the global branch lists, fuse, and write host results like vb_search. */
+ * vb_search_local: branch top-k' of this shard, left on the device as ONE candidate block of
+ *   VB_CAND_BLOCK_WORDS(B, kprime) u64 words: cand[2][B][kprime] (0 = empty slot; branch 0 dense,
+ *   1 sparse) followed by one flag word (shard overflowed), ready for an all-gather.  Query
+ *   weights must already carry the GLOBAL idf (apply_idf = 0).
+ * vb_merge_fuse: merge `n_shards` gathered candidate blocks (device, contiguous) into the
+ *   global branch lists, fuse, and write host results like vb_search. */
+#define VB_CAND_BLOCK_WORDS(B, kprime) (2ull * (B) * (kprime) + 1ull)
 int vb_search_local(vb_index* h, const vb_query_batch* q, uint64_t* cand_dev);
 int vb_merge_fuse(vb_index* h, const vb_query_batch* q, uint32_t n_shards,
                   const uint64_t* gathered_dev, vb_result* out);
 
+/* Staged form of the same work, for callers that overlap or time the phases themselves
+ * (bench.py, the multi-GPU host layer).  vb_search == vb_stage + vb_run_local + vb_run_fuse + vb_fetch.
+ *   vb_stage     validate, resolve terms/IDF, upload the batch (the only H2D copy); need_corpus = 0
+ *                when only a merge of gathered candidates will follow.
+ *   vb_run_local K0 + K1/K2 + K3 + select over this shard, asynchronously on the index's stream;
+ *                cand_dev (optional) receives the packed branch candidates [2][B][kprime].
+ *   vb_run_fuse  gathered_dev != NULL: merge n_shards candidate blocks first; then K4.  Asynchronous.
+ *   vb_fetch     D2H of the results, stream sync, decode; *overflowed = 1 asks for a safe-mode re-run
+ *                (vb_set_option "safe_mode"). */
+int vb_stage(vb_index* h, const vb_query_batch* q, int32_t want_branches, int32_t need_corpus);
+int vb_run_local(vb_index* h, uint64_t* cand_dev);
+int vb_run_fuse(vb_index* h, uint32_t n_shards, const uint64_t* gathered_dev);
+int vb_fetch(vb_index* h, vb_result* out, int32_t* overflowed);
+
 /* Tuning knobs (tests exercise every path with them): key = "dense_path" (0 auto, 1 K1, 2 K2),
- * "seg_first", "seg_ratio", "safe_mode". */
+ * "seg_first", "seg_ratio", "safe_mode", "profile" (per-phase CUDA-event times in vb_stats),
+ * "stream" (a cudaStream_t to run on instead of the index's own stream; 0 restores it). */
 int vb_set_option(vb_index* h, const char* key, int64_t value);
 
 int vb_get_stats(vb_index* h, vb_stats* out);

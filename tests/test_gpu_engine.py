@@ -291,7 +291,7 @@ def test_two_shards_merge_equals_single_index(world):
     limit, k = 10, 30
     for fusion in ("weighted", "rrf"):
         single = world["ix"].search_batch(Q, SP, gf, fo, limit=limit, fusion=fusion, branches=True)
-        bufs = [torch.zeros(2 * len(qs) * k, dtype=torch.int64, device="cuda") for _ in range(2)]
+        bufs = [torch.zeros(eng.Index.cand_block_words(len(qs), k), dtype=torch.int64, device="cuda") for _ in range(2)]
         a.search_local(bufs[0].data_ptr(), Q, SPW, gf, fo, limit=limit, kprime=k, fusion=fusion)
         b.search_local(bufs[1].data_ptr(), Q, SPW, gf, fo, limit=limit, kprime=k, fusion=fusion)
         gathered = torch.cat(bufs)

@@ -34,40 +34,63 @@ class FakeShardIndex:
         t, c = np.unique(self.csr[1], return_counts=True)
         return t.astype(np.uint32), c.astype(np.int64)
 
-    def search_local(self, ptr, queries, sparse, filters, filter_of, limit, kprime, fusion, sparse_weight):
-        fl = None if not filters else [(f.scope_bits, f.ts_field, f.ts_lo, f.ts_hi) for f in filters]
-        out = self.cc.search_batch(queries, sparse, fl, filter_of, limit, kprime, 1 if sparse is not None else 0,
-                                   sparse_weight, apply_idf=False)
-        B = len(queries)
-        keys = np.zeros((2, B, kprime), np.uint64)
+    @staticmethod
+    def cand_block_words(B, k):
+        return 2 * B * k + 1
+
+    def set_option(self, key, value):
+        pass
+
+    def stage(self, queries, sparse=None, filters=None, filter_of=None, limit=10, kprime=None, fusion="weighted",
+              sparse_weight=0.1, apply_idf=True, branches=False, need_corpus=True):
+        assert not apply_idf
+        self.st = dict(q=queries, sp=sparse, fl=filters, fo=filter_of, limit=limit, k=kprime, fusion=fusion, w=sparse_weight)
+        return "staged"
+
+    def run_local(self, ptr):
+        st = self.st
+        fl = None if not st["fl"] else [(f.scope_bits, f.ts_field, f.ts_lo, f.ts_hi) for f in st["fl"]]
+        out = self.cc.search_batch(st["q"], st["sp"], fl, st["fo"], st["limit"], st["k"], 1 if st["sp"] is not None else 0,
+                                   st["w"], apply_idf=False)
+        B, k = len(st["q"]), st["k"]
+        keys = np.zeros(2 * B * k + 1, np.uint64)
+        kv = keys[:-1].reshape(2, B, k)
         for br, name in enumerate(("dense", "sparse")):
             for i in range(B):
                 c = int(out[f"{name}_counts"][i])
-                keys[br, i, :c] = engine.pack_keys(out[f"{name}_scores"][i, :c], out[f"{name}_rows"][i, :c] + self.row_base)
+                kv[br, i, :c] = engine.pack_keys(out[f"{name}_scores"][i, :c], out[f"{name}_rows"][i, :c] + self.row_base)
         ctypes.memmove(ptr, keys.ctypes.data, keys.nbytes)
 
-    def merge_fuse(self, ptr, n_shards, queries, sparse, limit, kprime, fusion, sparse_weight, branches):
-        B = len(queries)
-        g = np.ctypeslib.as_array((ctypes.c_uint64 * (n_shards * 2 * B * kprime)).from_address(ptr)).reshape(n_shards, 2, B, kprime)
+    def run_fuse(self, n_shards, ptr):
+        st = self.st
+        B, k, limit = len(st["q"]), st["k"], st["limit"]
+        words = 2 * B * k + 1
+        g = np.ctypeslib.as_array((ctypes.c_uint64 * (n_shards * words)).from_address(ptr)).reshape(n_shards, words)
+        assert not g[:, -1].any()
+        g = g[:, :-1].reshape(n_shards, 2, B, k)
         res = engine.SearchResult(np.zeros((B, limit), np.uint64), np.zeros((B, limit)), np.zeros(B, np.int32))
         for i in range(B):
             lists = []
             for br in range(2):
-                k = np.sort(g[:, br, i, :].ravel())[::-1]
-                k = k[k != 0][:kprime]
-                sc, rows = engine.unpack_keys(k)
+                kk = np.sort(g[:, br, i, :].ravel())[::-1]
+                kk = kk[kk != 0][:k]
+                sc, rows = engine.unpack_keys(kk)
                 lists.append([O.ScoredPoint(str(int(r)), float(s), {}, int(r)) for s, r in zip(sc, rows)])
-            has_sparse = sparse is not None and sparse[i] is not None and len(sparse[i][0])
+            sp = st["sp"]
+            has_sparse = sp is not None and sp[i] is not None and len(sp[i][0])
             if not has_sparse:
                 fused = [(p.id, p.score, p) for p in lists[0][:limit]]
-            elif fusion == "rrf":
+            elif st["fusion"] == "rrf":
                 fused = O.reciprocal_rank_fusion(lists, limit)
             else:
-                fused = O.weighted_fusion(lists[0], lists[1], limit, sparse_weight)
+                fused = O.weighted_fusion(lists[0], lists[1], limit, st["w"])
             res.counts[i] = len(fused)
-            for j, (pid, s, _) in enumerate(fused):
-                res.rows[i, j], res.scores[i, j] = int(pid), s
-        return res
+            for j, (pid, s_, _) in enumerate(fused):
+                res.rows[i, j], res.scores[i, j] = int(pid), s_
+        self.res = res
+
+    def fetch(self, staged, allow_overflow=False):
+        return self.res
 
 
 def _worker(rank, world, port, ret):

@@ -109,26 +109,42 @@ vb_compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float
 }
 
 // Pack the first k keys of every list into out[list][k] (0-padded): the all-gather payload.
+// If `overflow` is given, one extra word out[n_lists*k] carries "some list of this shard
+// overflowed", so every rank learns it from the same all-gather and re-runs consistently.
 __global__ void vb_export_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt,
-                                 uint32_t cap, uint32_t k, uint64_t* __restrict__ out)
+                                 uint32_t cap, uint32_t k, uint64_t* __restrict__ out,
+                                 const uint32_t* __restrict__ overflow, uint32_t n_lists)
 {
     const uint32_t list = blockIdx.x;
     const uint32_t c = cnt[list] < k ? cnt[list] : k;
     for (uint32_t i = threadIdx.x; i < k; i += blockDim.x)
         out[(size_t)list * k + i] = i < c ? cand[(size_t)list * cap + i] : 0ull;
+    if (overflow != nullptr && blockIdx.x == 0) {
+        int any = 0;
+        for (uint32_t i = threadIdx.x; i < n_lists; i += blockDim.x) any |= overflow[i] != 0u;
+        any = __syncthreads_or(any);
+        if (threadIdx.x == 0) out[(size_t)n_lists * k] = any ? 1ull : 0ull;
+    }
 }
 
-// Scatter gathered[shard][list][k] into cand[list][shard*k + i] and set cnt = n_shards*k
-// (empty slots are 0 keys, which the compaction ignores).
+// Scatter gathered[shard][list][k] (+1 flag word per shard) into cand[list][shard*k + i] and set
+// cnt = n_shards*k (empty slots are 0 keys, which the compaction ignores).
 __global__ void vb_import_kernel(const uint64_t* __restrict__ gathered, uint32_t n_shards, uint32_t n_lists,
-                                 uint32_t k, uint32_t cap, uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt)
+                                 uint32_t k, uint32_t cap, uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt,
+                                 uint32_t* __restrict__ overflow)
 {
     const uint32_t list = blockIdx.x;
+    const size_t stride = (size_t)n_lists * k + 1;
     for (uint32_t i = threadIdx.x; i < n_shards * k; i += blockDim.x) {
         const uint32_t sh = i / k, j = i % k;
-        cand[(size_t)list * cap + i] = gathered[((size_t)sh * n_lists + list) * k + j];
+        cand[(size_t)list * cap + i] = gathered[sh * stride + (size_t)list * k + j];
     }
-    if (threadIdx.x == 0) cnt[list] = n_shards * k;
+    if (threadIdx.x == 0) {
+        cnt[list] = n_shards * k;
+        if (list == 0)
+            for (uint32_t sh = 0; sh < n_shards; ++sh)
+                if (gathered[sh * stride + (size_t)n_lists * k] != 0ull) overflow[0] = 1u;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -69,12 +69,37 @@ struct HostBuf {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+struct Batch {
+    uint32_t B = 0, k = 0, limit = 0, n_lists = 0, n_qterms = 0, n_filters = 0, mask_words = 0, n_blocks = 0;
+    bool any_sparse = false, use_mask = false;
+    std::vector<int32_t> mode;
+    // device pointers into h->args
+    const float* d_q = nullptr;
+    const int64_t* d_qindptr = nullptr;
+    const double* d_qweight = nullptr;
+    const uint64_t* d_qlo = nullptr;
+    const uint64_t* d_qhi = nullptr;
+    const int32_t* d_maskof = nullptr;
+    const int32_t* d_mode = nullptr;
+    const VbFilterDev* d_filters = nullptr;
+    uint32_t need_created = 0, need_modified = 0, need_scope = 0;
+    // lists
+    float* tau = nullptr;
+    uint32_t* cnt = nullptr;
+    uint32_t* overflow = nullptr;
+    // fusion / output
+    double w_sparse = 0.0;
+    bool want_branches = false, valid = false, need_corpus = true;
+    size_t o_rows = 0, o_sc = 0, o_cnt = 0, o_keys = 0, o_lcnt = 0, o_ovf = 0, out_bytes = 0;
+    size_t h2d_bytes = 0;
+};
+
 struct vb_index {
     int32_t dim = 0, d_pad = 0, device = 0;
     uint64_t row_base = 0;
     uint64_t n_rows = 0, n_live = 0, cap_rows = 0;
     uint64_t nnz = 0, cap_nnz = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::mutex mu;
     int sm_count = 148;
@@ -102,6 +127,8 @@ struct vb_index {
     int64_t opt_dense_path = 0, opt_seg_first = 8192, opt_seg_ratio = 32, opt_safe_mode = 0, opt_profile = 0;
 
     vb_stats stats{};
+    Batch staged;
+    bool staged_safe = false;
     std::vector<cudaEvent_t> prof_events;
     std::vector<int> prof_phase;
 };
@@ -201,11 +228,12 @@ extern "C" int vb_create(int32_t dim, int32_t device, uint64_t capacity_hint, ui
     h->device = device;
     h->row_base = row_base;
     h->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
         delete h;
         return vb_fail("vb_create: stream/event creation failed");
     }
+    h->stream = h->own_stream;
     cudaFuncSetAttribute(vb_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(VB_ROWS_PER_BLOCK * 8u));
     if (vb_gemm_configure() != 0) { delete h; return vb_fail("vb_create: tensor-core kernel configuration failed: %s", vb_gemm_last_error()); }
     (void)capacity_hint;
@@ -226,7 +254,7 @@ extern "C" void vb_destroy(vb_index* h) {
     for (auto ev : h->prof_events) cudaEventDestroy(ev);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
-    cudaStreamDestroy(h->stream);
+    cudaStreamDestroy(h->own_stream);
     delete h;
 }
 
@@ -239,6 +267,9 @@ extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
     else if (k == "seg_ratio") h->opt_seg_ratio = std::max<int64_t>(2, value);
     else if (k == "safe_mode") h->opt_safe_mode = value;
     else if (k == "profile") h->opt_profile = value;
+    else if (k == "stream") {   // run on the caller's stream (e.g. torch's current stream); 0 = own stream
+        h->stream = value ? reinterpret_cast<cudaStream_t>(static_cast<uintptr_t>(value)) : h->own_stream;
+    }
     else return vb_fail("vb_set_option: unknown key '%s'", key);
     return 0;
 }
@@ -543,40 +574,25 @@ struct Arena {
     size_t take(size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; }
 };
 
-struct Batch {
-    uint32_t B = 0, k = 0, limit = 0, n_lists = 0, n_qterms = 0, n_filters = 0, mask_words = 0, n_blocks = 0;
-    bool any_sparse = false, use_mask = false;
-    std::vector<int32_t> mode;
-    // device pointers into h->args
-    const float* d_q = nullptr;
-    const int64_t* d_qindptr = nullptr;
-    const double* d_qweight = nullptr;
-    const uint64_t* d_qlo = nullptr;
-    const uint64_t* d_qhi = nullptr;
-    const int32_t* d_maskof = nullptr;
-    const int32_t* d_mode = nullptr;
-    const VbFilterDev* d_filters = nullptr;
-    uint32_t need_created = 0, need_modified = 0, need_scope = 0;
-    // lists
-    float* tau = nullptr;
-    uint32_t* cnt = nullptr;
-    uint32_t* overflow = nullptr;
-};
 
 enum { PH_MASK = 0, PH_DENSE = 1, PH_SPARSE = 2, PH_SELECT = 3, PH_FUSE = 4, PH_N = 5 };
 
 static void prof_begin(vb_index* h, int phase) {
     if (!h->opt_profile) return;
-    cudaEvent_t a, b;
-    cudaEventCreate(&a); cudaEventCreate(&b);
-    h->prof_events.push_back(a); h->prof_events.push_back(b);
+    const size_t i = h->prof_phase.size();
+    while (h->prof_events.size() < 2 * (i + 1)) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->prof_events.push_back(e);
+    }
     h->prof_phase.push_back(phase);
-    cudaEventRecord(a, h->stream);
+    cudaEventRecord(h->prof_events[2 * i], h->stream);
 }
 static void prof_end(vb_index* h) {
     if (!h->opt_profile) return;
-    cudaEventRecord(h->prof_events.back(), h->stream);
+    cudaEventRecord(h->prof_events[2 * h->prof_phase.size() - 1], h->stream);
 }
+// call after the stream has been synchronised
 static void prof_collect(vb_index* h) {
     double acc[PH_N] = {0, 0, 0, 0, 0};
     for (size_t i = 0; i < h->prof_phase.size(); ++i) {
@@ -584,8 +600,6 @@ static void prof_collect(vb_index* h) {
         cudaEventElapsedTime(&ms, h->prof_events[2 * i], h->prof_events[2 * i + 1]);
         acc[h->prof_phase[i]] += ms;
     }
-    for (auto ev : h->prof_events) cudaEventDestroy(ev);
-    h->prof_events.clear();
     h->prof_phase.clear();
     h->stats.last_mask_ms = acc[PH_MASK];
     h->stats.last_dense_ms = acc[PH_DENSE];
@@ -612,6 +626,9 @@ static int validate_batch(const vb_index* h, const vb_query_batch* q) {
 
 // Upload the batch, evaluate the filters, initialise the candidate lists.
 static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool need_corpus) {
+    b = Batch();
+    b.need_corpus = need_corpus;
+    b.w_sparse = q->sparse_weight;
     b.B = q->n_queries;
     b.k = q->kprime;
     b.limit = q->limit;
@@ -740,6 +757,24 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     b.tau = h->lists.as<float>();
     b.cnt = h->lists.as<uint32_t>() + b.n_lists;
     b.overflow = h->lists.as<uint32_t>() + 2 * (size_t)b.n_lists;
+    b.h2d_bytes = ar.off;
+    h->stats.last_h2d_bytes = ar.off;
+    // output block layout
+    Arena ao;
+    b.o_rows = ao.take((size_t)b.B * b.limit * 4);
+    b.o_sc = ao.take((size_t)b.B * b.limit * 8);
+    b.o_cnt = ao.take((size_t)b.B * 4);
+    b.o_lcnt = ao.take((size_t)b.n_lists * 4);
+    b.o_ovf = ao.take((size_t)b.n_lists * 4);
+    b.o_keys = ao.take((size_t)b.n_lists * b.k * 8);
+    b.out_bytes = ao.off;
+    TRY(dev_reserve(h, h->out, b.out_bytes, false));
+    TRY(host_reserve(h->h_out, b.out_bytes));
+    b.valid = true;
+    return 0;
+}
+
+static int init_lists(vb_index* h, const Batch& b) {
     vb_init_lists_kernel<<<(b.n_lists + 255) / 256, 256, 0, h->stream>>>(b.tau, b.cnt, b.overflow, b.n_lists);
     CKK("vb_init_lists_kernel");
     ++h->stats.last_launches;
@@ -783,6 +818,7 @@ static int launch_scan(vb_index* h, const Batch& b, uint32_t row_begin, uint32_t
 // cand[list][0..cnt).  `safe`: fixed small segments that can never overflow a list.
 static int run_branches(vb_index* h, const Batch& b, bool safe) {
     const uint32_t n = (uint32_t)h->n_rows;
+    TRY(init_lists(h, b));
     // query prep
     TRY(dev_reserve(h, h->q_hat, (size_t)b.B * h->d_pad * 4, false));
     TRY(dev_reserve(h, h->q_bf16, (size_t)align_up(b.B, 256) * h->d_pad * 2, false));
@@ -816,6 +852,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
     if (path == 0) path = vb_gemm_supported(h->d_pad, b.B) && b.B >= 2 ? 2 : 1;
     if (path == 2 && !vb_gemm_supported(h->d_pad, b.B)) return vb_fail("dense_path=2 requested but unsupported for d_pad=%d B=%u", h->d_pad, b.B);
     h->stats.last_dense_path = (uint32_t)path;
+    h->stats.last_dense_passes = path == 2 ? (b.B + vb_gemm_max_bn((uint32_t)h->d_pad) - 1) / vb_gemm_max_bn((uint32_t)h->d_pad) : b.B;
 
     // segment schedule (boundaries are multiples of VB_ROWS_PER_BLOCK)
     std::vector<uint32_t> bounds{0};
@@ -868,53 +905,46 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
     return 0;
 }
 
-// Fuse the (already exact, sorted) branch lists and bring everything back to the host.
-// Returns *overflowed = 1 if any list overflowed during scoring (caller re-runs in safe mode).
-static int fuse_and_fetch(vb_index* h, const Batch& b, const vb_query_batch* q, vb_result* out, int* overflowed) {
-    Arena ar;
-    const size_t o_rows = ar.take((size_t)b.B * b.limit * 4);
-    const size_t o_sc = ar.take((size_t)b.B * b.limit * 8);
-    const size_t o_cnt = ar.take((size_t)b.B * 4);
-    const size_t o_keys = ar.take((size_t)b.n_lists * b.k * 8);
-    const size_t o_lcnt = ar.take((size_t)b.n_lists * 4);
-    const size_t o_ovf = ar.take((size_t)b.n_lists * 4);
-    TRY(dev_reserve(h, h->out, ar.off, false));
-    TRY(host_reserve(h->h_out, ar.off));
+// K4 on the (already exact, sorted) branch lists; results stay in h->out on the device.
+static int fuse_stage(vb_index* h, const Batch& b) {
     unsigned char* dp = h->out.as<unsigned char>();
     prof_begin(h, PH_FUSE);
     VbFuseArgs f{};
     f.cand = h->cand.as<uint64_t>(); f.cnt = b.cnt; f.mode = b.d_mode; f.cap = h->cand_cap; f.n_queries = b.B;
-    f.k = b.k; f.limit = b.limit; f.w_sparse = q->sparse_weight; f.w_dense = 1.0 - q->sparse_weight;
-    f.out_rows = reinterpret_cast<uint32_t*>(dp + o_rows); f.out_scores = reinterpret_cast<double*>(dp + o_sc);
-    f.out_cnt = reinterpret_cast<int32_t*>(dp + o_cnt);
+    f.k = b.k; f.limit = b.limit; f.w_sparse = b.w_sparse; f.w_dense = 1.0 - b.w_sparse;
+    f.out_rows = reinterpret_cast<uint32_t*>(dp + b.o_rows); f.out_scores = reinterpret_cast<double*>(dp + b.o_sc);
+    f.out_cnt = reinterpret_cast<int32_t*>(dp + b.o_cnt);
     vb_fuse_kernel<<<b.B, 128, (size_t)2 * b.k * 13 + 16, h->stream>>>(f);
     CKK("vb_fuse_kernel");
     ++h->stats.last_launches;
-    const bool want_branches = out->dense_rows || out->dense_scores || out->dense_counts || out->sparse_rows || out->sparse_scores || out->sparse_counts;
-    if (want_branches) {
-        vb_export_kernel<<<b.n_lists, 128, 0, h->stream>>>(h->cand.as<uint64_t>(), b.cnt, h->cand_cap, b.k, reinterpret_cast<uint64_t*>(dp + o_keys));
+    if (b.want_branches) {
+        vb_export_kernel<<<b.n_lists, 128, 0, h->stream>>>(h->cand.as<uint64_t>(), b.cnt, h->cand_cap, b.k, reinterpret_cast<uint64_t*>(dp + b.o_keys), nullptr, b.n_lists);
         CKK("vb_export_kernel");
         ++h->stats.last_launches;
     }
     prof_end(h);
-    CK(cudaMemcpyAsync(dp + o_lcnt, b.cnt, (size_t)b.n_lists * 4, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(dp + o_ovf, b.overflow, (size_t)b.n_lists * 4, cudaMemcpyDeviceToDevice, h->stream));
-    unsigned char* hp = h->h_out.as<unsigned char>();
-    if (want_branches) {
-        CK(cudaMemcpyAsync(hp, dp, ar.off, cudaMemcpyDeviceToHost, h->stream));
-    } else {
-        CK(cudaMemcpyAsync(hp, dp, o_keys, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(hp + o_lcnt, dp + o_lcnt, ar.off - o_lcnt, cudaMemcpyDeviceToHost, h->stream));
-    }
+    CK(cudaMemcpyAsync(dp + b.o_lcnt, b.cnt, (size_t)b.n_lists * 4, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(dp + b.o_ovf, b.overflow, (size_t)b.n_lists * 4, cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaEventRecord(h->ev1, h->stream));
+    return 0;
+}
+
+// D2H of the result block, sync, decode into the caller's arrays.
+// *overflowed = 1 if any list overflowed during scoring (caller re-runs in safe mode).
+static int fetch_stage(vb_index* h, const Batch& b, vb_result* out, int* overflowed) {
+    unsigned char* dp = h->out.as<unsigned char>();
+    unsigned char* hp = h->h_out.as<unsigned char>();
+    const size_t bytes = b.want_branches ? b.out_bytes : b.o_keys;
+    h->stats.last_d2h_bytes = bytes;
+    CK(cudaMemcpyAsync(hp, dp, bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    const uint32_t* ovf = reinterpret_cast<const uint32_t*>(hp + o_ovf);
+    const uint32_t* ovf = reinterpret_cast<const uint32_t*>(hp + b.o_ovf);
     *overflowed = 0;
     for (uint32_t i = 0; i < b.n_lists; ++i) if (ovf[i]) *overflowed = 1;
-    if (*overflowed) return 0;
-    const uint32_t* rows = reinterpret_cast<const uint32_t*>(hp + o_rows);
-    const double* sc = reinterpret_cast<const double*>(hp + o_sc);
-    const int32_t* cn = reinterpret_cast<const int32_t*>(hp + o_cnt);
+    if (*overflowed || !out) return 0;
+    const uint32_t* rows = reinterpret_cast<const uint32_t*>(hp + b.o_rows);
+    const double* sc = reinterpret_cast<const double*>(hp + b.o_sc);
+    const int32_t* cn = reinterpret_cast<const int32_t*>(hp + b.o_cnt);
     for (uint32_t i = 0; i < b.B; ++i) {
         if (out->counts) out->counts[i] = cn[i];
         for (int32_t j = 0; j < cn[i]; ++j) {
@@ -922,9 +952,9 @@ static int fuse_and_fetch(vb_index* h, const Batch& b, const vb_query_batch* q, 
             if (out->scores) out->scores[(size_t)i * b.limit + j] = sc[(size_t)i * b.limit + j];
         }
     }
-    if (want_branches) {
-        const uint64_t* keys = reinterpret_cast<const uint64_t*>(hp + o_keys);
-        const uint32_t* lc = reinterpret_cast<const uint32_t*>(hp + o_lcnt);
+    if (b.want_branches) {
+        const uint64_t* keys = reinterpret_cast<const uint64_t*>(hp + b.o_keys);
+        const uint32_t* lc = reinterpret_cast<const uint32_t*>(hp + b.o_lcnt);
         for (uint32_t br = 0; br < 2; ++br) {
             uint64_t* orow = br ? out->sparse_rows : out->dense_rows;
             float* osc = br ? out->sparse_scores : out->dense_scores;
@@ -938,9 +968,9 @@ static int fuse_and_fetch(vb_index* h, const Batch& b, const vb_query_batch* q, 
                     if (orow) orow[(size_t)i * b.k + j] = vb_key_row(key);
                     if (osc) {
                         const uint32_t bits = vb_ordered_f32((uint32_t)(key >> 32));
-                        float s;
-                        memcpy(&s, &bits, 4);
-                        osc[(size_t)i * b.k + j] = s;
+                        float sv;
+                        memcpy(&sv, &bits, 4);
+                        osc[(size_t)i * b.k + j] = sv;
                     }
                 }
             }
@@ -966,21 +996,88 @@ static void zero_result(const vb_query_batch* q, vb_result* out) {
     }
 }
 
-extern "C" int vb_search(vb_index* h, const vb_query_batch* q, vb_result* out) {
-    if (!h || !out) return vb_fail("vb_search: NULL argument");
+static bool wants_branches(const vb_result* out) {
+    return out && (out->dense_rows || out->dense_scores || out->dense_counts || out->sparse_rows || out->sparse_scores || out->sparse_counts);
+}
+
+// ---- staged API: upload once, run the device work asynchronously, fetch ---------------------------
+extern "C" int vb_stage(vb_index* h, const vb_query_batch* q, int32_t want_branches, int32_t need_corpus) {
+    if (!h) return vb_fail("vb_stage: NULL index");
     TRY(validate_batch(h, q));
     std::lock_guard<std::mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
+    h->staged.valid = false;
+    TRY(prepare_batch(h, q, h->staged, need_corpus != 0));
+    h->staged.want_branches = want_branches != 0;
+    return 0;
+}
+
+extern "C" int vb_run_local(vb_index* h, uint64_t* cand_dev) {
+    if (!h) return vb_fail("vb_run_local: NULL index");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->staged.valid) return vb_fail("vb_run_local: no staged batch");
+    CK(cudaSetDevice(h->device));
+    h->stats.last_launches = 0;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    if (h->n_rows == 0) {
+        TRY(init_lists(h, h->staged));
+    } else {
+        TRY(run_branches(h, h->staged, h->staged_safe));
+    }
+    if (cand_dev) {
+        vb_export_kernel<<<h->staged.n_lists, 128, 0, h->stream>>>(h->cand.as<uint64_t>(), h->staged.cnt, h->cand_cap, h->staged.k, cand_dev, h->staged.overflow, h->staged.n_lists);
+        CKK("vb_export_kernel");
+        ++h->stats.last_launches;
+    }
+    return 0;
+}
+
+extern "C" int vb_run_fuse(vb_index* h, uint32_t n_shards, const uint64_t* gathered_dev) {
+    if (!h) return vb_fail("vb_run_fuse: NULL index");
+    std::lock_guard<std::mutex> lk(h->mu);
+    Batch& b = h->staged;
+    if (!b.valid) return vb_fail("vb_run_fuse: no staged batch");
+    CK(cudaSetDevice(h->device));
+    if (gathered_dev) {
+        if (n_shards == 0 || (uint64_t)n_shards * b.k > h->cand_cap) return vb_fail("vb_run_fuse: n_shards*kprime out of range");
+        prof_begin(h, PH_SELECT);
+        vb_import_kernel<<<b.n_lists, 256, 0, h->stream>>>(gathered_dev, n_shards, b.n_lists, b.k, h->cand_cap, h->cand.as<uint64_t>(), b.cnt, b.overflow);
+        CKK("vb_import_kernel");
+        vb_compact_kernel<<<b.n_lists, VB_COMPACT_THREADS, 0, h->stream>>>(h->cand.as<uint64_t>(), b.cnt, b.tau, b.overflow, h->cand_cap, b.k);
+        CKK("vb_compact_kernel");
+        h->stats.last_launches += 2;
+        prof_end(h);
+    }
+    TRY(fuse_stage(h, b));
+    return 0;
+}
+
+extern "C" int vb_fetch(vb_index* h, vb_result* out, int32_t* overflowed) {
+    if (!h) return vb_fail("vb_fetch: NULL index");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->staged.valid) return vb_fail("vb_fetch: no staged batch");
+    CK(cudaSetDevice(h->device));
+    int ovf = 0;
+    TRY(fetch_stage(h, h->staged, out, &ovf));
+    finish_stats(h, h->staged);
+    if (overflowed) *overflowed = ovf;
+    return 0;
+}
+
+// ---- one-call API ------------------------------------------------------------------------------------
+extern "C" int vb_search(vb_index* h, const vb_query_batch* q, vb_result* out) {
+    if (!h || !out) return vb_fail("vb_search: NULL argument");
+    TRY(validate_batch(h, q));
     if (h->n_rows == 0) { zero_result(q, out); return 0; }
     for (int attempt = 0; attempt < 2; ++attempt) {
-        Batch b;
-        h->stats.last_launches = 0;
-        CK(cudaEventRecord(h->ev0, h->stream));
-        TRY(prepare_batch(h, q, b, true));
-        TRY(run_branches(h, b, attempt == 1));
-        int overflowed = 0;
-        TRY(fuse_and_fetch(h, b, q, out, &overflowed));
-        finish_stats(h, b);
+        TRY(vb_stage(h, q, wants_branches(out), 1));
+        h->staged_safe = attempt == 1;
+        int rc = vb_run_local(h, nullptr);
+        h->staged_safe = false;
+        TRY(rc);
+        TRY(vb_run_fuse(h, 0, nullptr));
+        int32_t overflowed = 0;
+        TRY(vb_fetch(h, out, &overflowed));
         if (!overflowed) return 0;
         if (attempt == 1) return vb_fail("vb_search: candidate list overflow even in safe mode (internal error)");
         ++h->stats.overflow_reruns;
@@ -992,30 +1089,20 @@ extern "C" int vb_search_local(vb_index* h, const vb_query_batch* q, uint64_t* c
     if (!h || !cand_dev) return vb_fail("vb_search_local: NULL argument");
     TRY(validate_batch(h, q));
     if (q->apply_idf) return vb_fail("vb_search_local: weights must carry the global IDF (apply_idf = 0)");
-    std::lock_guard<std::mutex> lk(h->mu);
-    CK(cudaSetDevice(h->device));
-    const uint32_t n_lists = 2 * q->n_queries;
-    if (h->n_rows == 0) {
-        CK(cudaMemsetAsync(cand_dev, 0, (size_t)n_lists * q->kprime * 8, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        return 0;
-    }
     for (int attempt = 0; attempt < 2; ++attempt) {
-        Batch b;
-        h->stats.last_launches = 0;
-        CK(cudaEventRecord(h->ev0, h->stream));
-        TRY(prepare_batch(h, q, b, true));
-        TRY(run_branches(h, b, attempt == 1));
-        vb_export_kernel<<<b.n_lists, 128, 0, h->stream>>>(h->cand.as<uint64_t>(), b.cnt, h->cand_cap, b.k, cand_dev);
-        CKK("vb_export_kernel");
-        ++h->stats.last_launches;
-        TRY(host_reserve(h->h_out, (size_t)b.n_lists * 4));
-        CK(cudaMemcpyAsync(h->h_out.p, b.overflow, (size_t)b.n_lists * 4, cudaMemcpyDeviceToHost, h->stream));
+        TRY(vb_stage(h, q, 0, 1));
+        h->staged_safe = attempt == 1;
+        int rc = vb_run_local(h, cand_dev);
+        h->staged_safe = false;
+        TRY(rc);
+        // overflow flags
+        TRY(host_reserve(h->h_stage, (size_t)h->staged.n_lists * 4));
+        CK(cudaMemcpyAsync(h->h_stage.p, h->staged.overflow, (size_t)h->staged.n_lists * 4, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaEventRecord(h->ev1, h->stream));
         CK(cudaStreamSynchronize(h->stream));
-        finish_stats(h, b);
+        finish_stats(h, h->staged);
         bool ovf = false;
-        for (uint32_t i = 0; i < b.n_lists; ++i) ovf |= h->h_out.as<uint32_t>()[i] != 0;
+        for (uint32_t i = 0; i < h->staged.n_lists; ++i) ovf |= h->h_stage.as<uint32_t>()[i] != 0;
         if (!ovf) return 0;
         if (attempt == 1) return vb_fail("vb_search_local: candidate list overflow even in safe mode (internal error)");
         ++h->stats.overflow_reruns;
@@ -1026,21 +1113,13 @@ extern "C" int vb_search_local(vb_index* h, const vb_query_batch* q, uint64_t* c
 extern "C" int vb_merge_fuse(vb_index* h, const vb_query_batch* q, uint32_t n_shards, const uint64_t* gathered_dev, vb_result* out) {
     if (!h || !gathered_dev || !out) return vb_fail("vb_merge_fuse: NULL argument");
     TRY(validate_batch(h, q));
-    if (n_shards == 0 || (uint64_t)n_shards * q->kprime > 16384) return vb_fail("vb_merge_fuse: n_shards*kprime out of range");
-    std::lock_guard<std::mutex> lk(h->mu);
-    CK(cudaSetDevice(h->device));
-    Batch b;
-    h->stats.last_launches = 0;
+    TRY(vb_stage(h, q, wants_branches(out), 0));
     CK(cudaEventRecord(h->ev0, h->stream));
-    TRY(prepare_batch(h, q, b, false));
-    vb_import_kernel<<<b.n_lists, 256, 0, h->stream>>>(gathered_dev, n_shards, b.n_lists, b.k, h->cand_cap, h->cand.as<uint64_t>(), b.cnt);
-    CKK("vb_import_kernel");
-    vb_compact_kernel<<<b.n_lists, VB_COMPACT_THREADS, 0, h->stream>>>(h->cand.as<uint64_t>(), b.cnt, b.tau, b.overflow, h->cand_cap, b.k);
-    CKK("vb_compact_kernel");
-    h->stats.last_launches += 2;
-    int overflowed = 0;
-    TRY(fuse_and_fetch(h, b, q, out, &overflowed));
-    finish_stats(h, b);
+    h->stats.last_launches = 0;
+    TRY(init_lists(h, h->staged));
+    TRY(vb_run_fuse(h, n_shards, gathered_dev));
+    int32_t overflowed = 0;
+    TRY(vb_fetch(h, out, &overflowed));
     if (overflowed) return vb_fail("vb_merge_fuse: unexpected overflow");
     return 0;
 }

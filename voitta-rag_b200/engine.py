@@ -57,12 +57,14 @@ class _Stats(C.Structure):
                 ("searches", C.c_uint64), ("queries", C.c_uint64), ("overflow_reruns", C.c_uint64),
                 ("last_search_ms", C.c_double), ("last_dense_ms", C.c_double), ("last_sparse_ms", C.c_double),
                 ("last_select_ms", C.c_double), ("last_mask_ms", C.c_double), ("last_fuse_ms", C.c_double),
-                ("last_dense_path", C.c_uint32), ("last_launches", C.c_uint32), ("device_bytes", C.c_uint64)]
+                ("last_dense_path", C.c_uint32), ("last_launches", C.c_uint32), ("device_bytes", C.c_uint64),
+                ("last_h2d_bytes", C.c_uint64), ("last_d2h_bytes", C.c_uint64), ("last_dense_passes", C.c_uint64)]
 
 
 # every symbol include/voitta_b200.h declares
 EXPORTS = ["vb_abi_version", "vb_last_error", "vb_create", "vb_destroy", "vb_upsert", "vb_upsert_dev",
            "vb_delete_rows", "vb_term_stats", "vb_search", "vb_search_local", "vb_merge_fuse",
+           "vb_stage", "vb_run_local", "vb_run_fuse", "vb_fetch",
            "vb_set_option", "vb_get_stats", "vb_sync"]
 
 _lib = None
@@ -90,6 +92,10 @@ def load_library():
     lib.vb_search.argtypes = [vp, C.POINTER(_QueryBatch), C.POINTER(_Result)]
     lib.vb_search_local.argtypes = [vp, C.POINTER(_QueryBatch), vp]
     lib.vb_merge_fuse.argtypes = [vp, C.POINTER(_QueryBatch), C.c_uint32, vp, C.POINTER(_Result)]
+    lib.vb_stage.argtypes = [vp, C.POINTER(_QueryBatch), C.c_int32, C.c_int32]
+    lib.vb_run_local.argtypes = [vp, vp]
+    lib.vb_run_fuse.argtypes = [vp, C.c_uint32, vp]
+    lib.vb_fetch.argtypes = [vp, C.POINTER(_Result), C.POINTER(C.c_int32)]
     lib.vb_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.vb_get_stats.argtypes = [vp, C.POINTER(_Stats)]
     lib.vb_sync.argtypes = [vp]
@@ -313,6 +319,11 @@ class Index:
         self._check(self._lib.vb_search(self._h, C.byref(p.c), C.byref(cres)))
         return res
 
+    @staticmethod
+    def cand_block_words(n_queries: int, kprime: int) -> int:
+        """u64 words of one shard's candidate block (VB_CAND_BLOCK_WORDS)."""
+        return 2 * n_queries * kprime + 1
+
     def search_local(self, cand_dev_ptr: int, queries, sparse=None, filters=None, filter_of=None, limit: int = 10,
                      kprime: int | None = None, fusion: str | int = "weighted", sparse_weight: float = 0.1):
         """Shard-local branch top-k' left on the device (all-gather payload); weights carry global IDF."""
@@ -331,6 +342,37 @@ class Index:
         p = _Packed(self.dim, queries, sparse, None, None, limit, kprime, fz, sparse_weight, False)
         res, cres = self._alloc_result(p.B, limit, kprime, branches)
         self._check(self._lib.vb_merge_fuse(self._h, C.byref(p.c), int(n_shards), _vp(gathered_dev_ptr), C.byref(cres)))
+        return res
+
+    # ---- staged form (vb_stage / vb_run_local / vb_run_fuse / vb_fetch) -------------------------
+    def stage(self, queries, sparse=None, filters=None, filter_of=None, limit: int = 10, kprime: int | None = None,
+              fusion: str | int = "weighted", sparse_weight: float = 0.1, apply_idf: bool = True,
+              branches: bool = False, need_corpus: bool = True):
+        """Upload a batch; returns the (result, handle) pair that ``fetch`` fills."""
+        fz = FUSION[fusion] if isinstance(fusion, str) else int(fusion)
+        if kprime is None:
+            kprime = limit * 3 if (sparse is not None and fz != FUSE_DENSE_ONLY) else limit
+        p = _Packed(self.dim, queries, sparse, filters, filter_of, limit, kprime, fz, sparse_weight, apply_idf)
+        self._check(self._lib.vb_stage(self._h, C.byref(p.c), int(branches), int(need_corpus)))
+        res, cres = self._alloc_result(p.B, limit, kprime, branches)
+        return res, cres
+
+    def run_local(self, cand_dev_ptr: int | None = None) -> None:
+        self._check(self._lib.vb_run_local(self._h, _vp(cand_dev_ptr)))
+
+    def run_fuse(self, n_shards: int = 0, gathered_dev_ptr: int | None = None) -> None:
+        self._check(self._lib.vb_run_fuse(self._h, int(n_shards), _vp(gathered_dev_ptr)))
+
+    def fetch(self, staged, allow_overflow: bool = False) -> SearchResult | None:
+        """D2H + sync + decode.  Returns None (if allowed) when a candidate list overflowed and the
+        staged batch must be re-run with set_option('safe_mode', 1)."""
+        res, cres = staged
+        ovf = C.c_int32()
+        self._check(self._lib.vb_fetch(self._h, C.byref(cres), C.byref(ovf)))
+        if ovf.value:
+            if allow_overflow:
+                return None
+            raise B200Error("candidate list overflow: re-run with set_option('safe_mode', 1) or use search_batch")
         return res
 
     def set_option(self, key: str, value: int) -> None:

@@ -31,10 +31,22 @@ class ShardedIndex:
         self.df_g: np.ndarray | None = None
         self.n_live_g = 0
         self._bufs: dict = {}
+        # one CUDA stream carries the library's kernels AND the collective, so they are ordered
+        # without host synchronisation
+        self.stream = None
+        if self.device.type == "cuda":
+            self.stream = torch.cuda.Stream(self.device)
+            self.index.set_option("stream", self.stream.cuda_stream)
+
+    def _stream_ctx(self):
+        import contextlib
+        return torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
 
     # ---- global IDF statistics ----------------------------------------------------------------
     def _all_gather_var(self, arr: np.ndarray) -> list[np.ndarray]:
         """all-gather of variable-length int64 arrays (pad to the max length)."""
+        if self.world == 1:
+            return [arr.astype(np.int64)]
         n = torch.tensor([arr.size], dtype=torch.int64, device=self.device)
         sizes = [torch.zeros_like(n) for _ in range(self.world)]
         dist.all_gather(sizes, n, group=self.group)
@@ -58,7 +70,8 @@ class ShardedIndex:
         self.terms_g = uniq
         self.df_g = np.add.reduceat(df, start) if len(df) else np.zeros(0, np.int64)
         n = torch.tensor([n_live_local], dtype=torch.int64, device=self.device)
-        dist.all_reduce(n, group=self.group)
+        if self.world > 1:
+            dist.all_reduce(n, group=self.group)
         self.n_live_g = int(n.item())
 
     def finalize_from_queries(self, sparse_batches) -> None:
@@ -95,6 +108,8 @@ class ShardedIndex:
         b = self._bufs.get(name)
         if b is None or b.numel() < numel:
             b = torch.zeros(numel, dtype=torch.int64, device=self.device)
+            if b.is_cuda:
+                torch.cuda.synchronize(self.device)
             self._bufs[name] = b
         return b[:numel]
 
@@ -107,18 +122,30 @@ class ShardedIndex:
         if kprime is None:
             kprime = limit * 3 if (any_sparse and fusion != "dense") else limit
         weighted = self.idf_weights(sparse) if any_sparse else None
-        n_local = 2 * B * kprime
-        local = self._buf("local", n_local)
-        gathered = self._buf("gathered", n_local * self.world)
-        self.index.search_local(local.data_ptr(), q, weighted, filters, filter_of, limit=limit, kprime=kprime,
-                                fusion=fusion, sparse_weight=sparse_weight)
-        if self.world > 1:
-            dist.all_gather_into_tensor(gathered, local, group=self.group)   # the path's one exchange step
-            if gathered.is_cuda:
-                torch.cuda.current_stream(self.device).synchronize()
-        else:
-            gathered.copy_(local)
-            if gathered.is_cuda:
-                torch.cuda.current_stream(self.device).synchronize()
-        return self.index.merge_fuse(gathered.data_ptr(), self.world, q, weighted, limit=limit, kprime=kprime,
-                                     fusion=fusion, sparse_weight=sparse_weight, branches=branches)
+        staged = self.index.stage(q, weighted, filters, filter_of, limit=limit, kprime=kprime, fusion=fusion,
+                                  sparse_weight=sparse_weight, apply_idf=False, branches=branches)
+        try:
+            for attempt in range(2):
+                if attempt:
+                    self.index.set_option("safe_mode", 1)     # some shard overflowed: every rank re-runs
+                res = self.run_staged(staged, B, kprime)
+                if res is not None:
+                    return res
+        finally:
+            self.index.set_option("safe_mode", 0)
+        raise RuntimeError("candidate list overflow even in safe mode")
+
+    def run_staged(self, staged, B: int, kprime: int):
+        """Device part of one sharded search on an already staged batch: local branches ->
+        all-gather of the candidate blocks (the path's ONE exchange step) -> merge -> fuse -> fetch."""
+        words = self.index.cand_block_words(B, kprime)
+        local = self._buf("local", words)
+        gathered = self._buf("gathered", words * self.world)
+        with self._stream_ctx():
+            self.index.run_local(local.data_ptr())
+            if self.world > 1:
+                dist.all_gather_into_tensor(gathered, local, group=self.group)
+            else:
+                gathered.copy_(local)
+            self.index.run_fuse(self.world, gathered.data_ptr())
+        return self.index.fetch(staged, allow_overflow=True)
