@@ -1,8 +1,9 @@
 """GPU parity tests proper: the CUDA path (through the C ABI) against the oracle on identical
 seeded inputs.  Tolerances: inputs are bf16-representable, so the fp32 paths (K1 dense scan,
 K3 sparse, K4 fusion) must agree with the oracle to fp32 summation error (1e-5); the
-tensor-core path (K2) rounds the unit query to bf16 and is held to the north_star's stated
-1e-3 relative tie tolerance."""
+tensor-core path (K2) feeds the unit query as bf16 hi+lo halves (bf16x2) when the batch fits one
+pass and must then agree to 2e-5; with a plain bf16 query (k2_precision=1, throughput mode for
+large batches) it is held to the north_star's stated 1e-3 relative tie tolerance."""
 import math
 
 import numpy as np
@@ -109,13 +110,17 @@ def test_single_query_hybrid_filtered(world, fusion, fi):
 
 def test_dense_only_and_limits(world):
     for limit in (1, 10, 100, 341):
-        got, want = run_both(world, world["queries"][:3], None, limit, "weighted", use_sparse=False)
-        for i in range(3):
-            wf = [(int(want["rows"][i, j]), float(want["scores"][i, j])) for j in range(want["counts"][i])]
-            assert_same_ranking(got.hits(i), wf, rel_tol=1e-5, abs_tol=1e-6, what=f"limit {limit}")
+        for path, tol in ((1, 1e-5), (2, 2e-5)):
+            world["ix"].set_option("dense_path", path)
+            got, want = run_both(world, world["queries"][:3], None, limit, "weighted", use_sparse=False)
+            for i in range(3):
+                wf = [(int(want["rows"][i, j]), float(want["scores"][i, j])) for j in range(want["counts"][i])]
+                assert_same_ranking(got.hits(i), wf, rel_tol=tol, abs_tol=tol, what=f"limit {limit} path {path}")
+    world["ix"].set_option("dense_path", 0)
 
 
 def test_weights_and_spread_zero(world):
+    world["ix"].set_option("dense_path", 1)      # strict fp32 comparison below
     for w_sparse in (0.0, 0.5, 1.0):
         got, want = run_both(world, world["queries"][:4], None, 5, "weighted", w_sparse)
         check(got, want, 4, 1e-5, f"w={w_sparse}")
@@ -137,15 +142,18 @@ def test_weights_and_spread_zero(world):
     got, want = run_both(world, [(q, ([2**31 - 7], [1.0]))], None, 10, "rrf")
     assert got.sparse_counts[0] == 0
     check(got, want, 1, 1e-5, "absent term")
+    world["ix"].set_option("dense_path", 0)
 
 
-@pytest.mark.parametrize("path", [1, 2])
-def test_batch_paths(world, path):
-    """B = 12 through the GEMV scan (K1, one pass per query) and the tcgen05 GEMM (K2)."""
+@pytest.mark.parametrize("path,prec", [(1, 0), (2, 0), (2, 1), (2, 2)])
+def test_batch_paths(world, path, prec):
+    """B = 12 through the GEMV scan (K1, one pass per query) and the tcgen05 GEMM (K2) with a
+    bf16x2 (auto / forced) or plain bf16 query."""
     ix = world["ix"]
     ix.set_option("dense_path", path)
+    ix.set_option("k2_precision", prec)
     try:
-        tol = 1e-5 if path == 1 else 1e-3
+        tol = 1e-5 if path == 1 else (1e-3 if prec == 1 else 2e-5)
         for fi in (0, 1, 3):
             flt = filters_for(world["coded"])[fi]
             got, want = run_both(world, world["queries"], flt, 10, "rrf")
@@ -158,6 +166,7 @@ def test_batch_paths(world, path):
                 fusion_bit_exact(got, i, 10, "rrf", 0.1)
     finally:
         ix.set_option("dense_path", 0)
+        ix.set_option("k2_precision", 0)
 
 
 def test_per_query_filters_in_one_batch(world):
@@ -171,7 +180,7 @@ def test_per_query_filters_in_one_batch(world):
         world["ix"].set_option("dense_path", path)
         got = world["ix"].search_batch(Q, SP, [eng.Filter(*f) for f in fl], fo, limit=10, fusion="weighted", branches=True)
         want = world["cc"].search_batch(Q, SP, fl, fo, limit=10, kprime=30, fusion=1)
-        tol = 1e-5 if path == 1 else 1e-3
+        tol = 1e-5 if path == 1 else 2e-5
         for i in range(len(qs)):
             wd = [(int(want["dense_rows"][i, j]), float(want["dense_scores"][i, j])) for j in range(want["dense_counts"][i])]
             assert_same_ranking(got.branch(i, "dense"), wd, rel_tol=tol, abs_tol=tol, what=f"path{path} q{i}")
@@ -200,7 +209,7 @@ def test_segmentation_does_not_change_results(world):
 
 def test_deletes_update_mask_n_and_df(world):
     coded, dim = world["coded"], world["dim"]
-    ix = make_index(coded, dim)
+    ix = make_index(coded, dim, dense_path=1)
     rng = np.random.RandomState(1)
     dead = rng.choice(world["n"], size=3000, replace=False)
     ix.delete_rows(dead)
@@ -253,7 +262,7 @@ def test_dimensions_and_padding(dim):
     ix.upsert(dense)
     cc = oracle_c.CorpusC(dense)
     want = cc.search_batch(Q, None, limit=10, fusion=0)
-    for path, tol in ((1, 1e-5), (2, 1e-3)):
+    for path, tol in ((1, 1e-5), (2, 2e-5)):
         ix.set_option("dense_path", path)
         got = ix.search_batch(Q, limit=10)
         for i in range(5):

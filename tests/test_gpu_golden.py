@@ -24,17 +24,18 @@ def test_reference_scenario_on_b200(monkeypatch, dense_path):
     store.client.set_option("dense_path", dense_path)
     corpus, queries = G.build_inputs()
     outs = G.replay(store, GOLD["ops"], corpus, queries, VS.ChunkMetadata, {})
-    # K1 (fp32 query) agrees to summation error; K2 rounds the query to bf16 (1e-3, north_star)
-    tol = 1e-5 if dense_path == 0 else 1e-3
+    # K1 (fp32 query) agrees to summation error; K2 feeds the query as bf16 hi+lo halves (B = 1 fits
+    # one pass), so it agrees to ~2e-5 as well
+    tol = 1e-5 if dense_path == 0 else 2e-5
     assert len(outs) == len(GOLD["outs"])
     for i, (op, got, want) in enumerate(zip(GOLD["ops"], outs, GOLD["outs"])):
         what = f"op {i} {op}"
         if op["op"] == "search":
             if dense_path == 2 and op["kw"].get("sparse") not in (False, "empty"):
-                # fused scores are min-max normalised: a 1e-3 wobble of the k'-th dense score moves
-                # every normalised score; check membership/order loosely and scores to 2e-2
+                # fused scores are min-max normalised: an error e of the k'-th dense score moves every
+                # normalised score by ~e/spread
                 assert len(got) == len(want), what
-                assert_same_ranking(got, want, rel_tol=2e-2, abs_tol=2e-2, what=what)
+                assert_same_ranking(got, want, rel_tol=5e-4, abs_tol=5e-4, what=what)
             else:
                 assert_same_ranking(got, want, rel_tol=tol, abs_tol=tol, what=what)
                 for g, w in zip(got, want):

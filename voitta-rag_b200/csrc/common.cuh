@@ -5,7 +5,7 @@
 #include <stdint.h>
 #include <stddef.h>
 
-#define VB_ROWS_PER_BLOCK 8192u   // sparse row block (smem accumulators) and segment alignment
+#define VB_ROWS_PER_BLOCK 2048u   // sparse row block (smem accumulators) and segment alignment
 
 // ---------------------------------------------------------------------------------------------
 // Candidate key: one u64 orders candidates by (score desc, row asc).  0 is never a valid key

@@ -81,6 +81,22 @@ __device__ __forceinline__ void vb_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) 
 }
 __device__ __forceinline__ void vb_tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ float4 vb_lds_f4(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ int4 vb_lds_i4(uint32_t addr) {
+    int4 r;
+    asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ uint32_t vb_lds_u32(uint32_t addr) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+
 // UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 B apart
 // (bits: [0,14) addr>>4, [16,30) LBO>>4 = 0, [32,46) SBO>>4 = 64, [46,48) version = 1,
 //  [61,64) layout = 2 (SWIZZLE_128B)).
@@ -109,6 +125,10 @@ struct VbGemmArgs {
     uint32_t n_q;                    // real queries in this sub-batch
     uint32_t q_begin;                // first query (list index) of the sub-batch
     uint32_t stages;
+    uint32_t direct;                 // 1: first segment — write every key to slot (row - row_begin), no atomics
+    uint32_t mask_mode;              // 0 none, 1 one filter for the whole sub-batch, 2 <= 31 filters, 3 general
+    int32_t  uniform_filter;         // mask_mode 1: the filter index
+    uint32_t split;                  // 1: columns [0,bn/2) hold q_hi, [bn/2,bn) hold q_lo (bf16x2 query precision)
 };
 
 __global__ void __launch_bounds__(VB_GEMM_THREADS, 1)
@@ -124,7 +144,7 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     unsigned char* tail = smem_a + a.stages * VB_STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail);                       // full[S], empty[S], tfull[2], tempty[2], qfull
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tail + 8u * (2u * 16u + 5u));
-    float* tau_s = reinterpret_cast<float*>(tail + 8u * (2u * 16u + 5u) + 16u);   // [256]
+    float* tau_s = reinterpret_cast<float*>(tail + 320u);                         // [256], 16-byte aligned
     int32_t* mof_s = reinterpret_cast<int32_t*>(tau_s + 256);                     // [256]
     uint32_t* mw_s = reinterpret_cast<uint32_t*>(mof_s + 256);                    // [4 warps][VB_GEMM_MAX_FILTERS]
 
@@ -200,19 +220,35 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         }
     } else {
         // ===== epilogue warps 2..5; TMEM lane quadrant = warp % 4 =====
+        // Branch-free per column: 16 columns are compared against their thresholds into a bit
+        // mask, ONE warp vote per 16-column chunk decides whether the (rare) append path runs.
         const uint32_t quad = warp & 3u;
+        const uint32_t tau_addr = vb_smem_u32(tau_s), mof_addr = vb_smem_u32(mof_s);
+        const uint32_t mw_addr = vb_smem_u32(mw_s + quad * VB_GEMM_MAX_FILTERS);
         uint32_t* mw = mw_s + quad * VB_GEMM_MAX_FILTERS;
-        const bool has_mask = a.mask != nullptr;
+        const uint32_t mode = a.mask_mode;
+        const bool split = a.split != 0u;
+        const uint32_t ncol = split ? a.bn >> 1 : a.bn;       // query columns handled by the epilogue
+        const float qnan = __int_as_float(0x7fc00000);
         uint32_t it = 0;
         for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const uint32_t acc = it & 1u;
             const uint32_t tile = a.tile_begin + t;
             const uint32_t row = tile * VB_TILE_M + quad * 32u + lane;
             const bool row_ok = row < a.row_end;
-            // issue the global loads before blocking on the accumulator
-            const float invn = row_ok ? a.inv_norm[row] : 0.0f;
-            if (has_mask) {
-                const uint32_t word = tile * 4u + quad;
+            // global loads are issued before blocking on the accumulator.
+            // A row that is out of range or (modes 0/1) masked gets a NaN scale: every compare fails.
+            float invn = row_ok ? a.inv_norm[row] : qnan;
+            const uint32_t word = tile * 4u + quad;
+            uint32_t fbits = 0x80000000u;                 // mode 2: bit f = row passes filter f; bit 31 = unfiltered
+            if (mode == 1u) {
+                const uint32_t w = word < a.mask_words ? a.mask[(size_t)a.uniform_filter * a.mask_words + word] : 0u;
+                if (!((w >> lane) & 1u)) invn = qnan;
+            } else if (mode == 2u) {
+                const uint32_t w = (lane < a.n_filters && word < a.mask_words) ? a.mask[(size_t)lane * a.mask_words + word] : 0u;
+                for (uint32_t f = 0; f < a.n_filters; ++f)
+                    fbits |= ((__shfl_sync(0xffffffffu, w, f) >> lane) & 1u) << f;
+            } else if (mode == 3u) {
                 for (uint32_t f = lane; f < a.n_filters; f += 32u)
                     mw[f] = word < a.mask_words ? a.mask[(size_t)f * a.mask_words + word] : 0u;
                 __syncwarp();
@@ -220,22 +256,61 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             vb_mbar_wait(bar_tfull + 8u * acc, (it >> 1) & 1u);
             vb_tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * 256u;
-            for (uint32_t c0 = 0; c0 < a.bn; c0 += 16u) {
-                uint32_t v[16];
-                vb_tmem_ld16(taddr + c0, v);
-                vb_tmem_ld_wait();
+            const uint32_t slot = row - a.tile_begin * VB_TILE_M;      // direct mode: position inside the segment
+            // one 16-column chunk: compare, then (rarely) append — or, in direct mode, store all
+            auto process = [&](const uint32_t (&v)[16], const uint32_t (&w)[16], uint32_t c0) {
+                uint32_t m = 0;
 #pragma unroll
-                for (uint32_t j = 0; j < 16u; ++j) {
-                    const uint32_t col = c0 + j;
-                    const float s = __uint_as_float(v[j]) * invn;
-                    bool pass = row_ok && s > tau_s[col];          // tau = +inf for padded columns
-                    if (has_mask) {
-                        const int32_t f = mof_s[col];
-                        if (f >= 0) pass = pass && ((mw[f] >> lane) & 1u);
+                for (uint32_t j4 = 0; j4 < 4u; ++j4) {
+                    const float4 tq = vb_lds_f4(tau_addr + (c0 + 4u * j4) * 4u);
+                    const float tv[4] = {tq.x, tq.y, tq.z, tq.w};
+                    int fv[4] = {-1, -1, -1, -1};
+                    if (mode >= 2u) {
+                        const int4 fq = vb_lds_i4(mof_addr + (c0 + 4u * j4) * 4u);
+                        fv[0] = fq.x; fv[1] = fq.y; fv[2] = fq.z; fv[3] = fq.w;
                     }
-                    if (__ballot_sync(0xffffffffu, pass) != 0u) {
-                        if (pass) vb_push(a.cand, a.cnt, a.cap, a.q_begin + col, s, a.row_base + row);
+#pragma unroll
+                    for (uint32_t e = 0; e < 4u; ++e) {
+                        const uint32_t j = 4u * j4 + e;
+                        const float sc = (split ? __uint_as_float(v[j]) + __uint_as_float(w[j]) : __uint_as_float(v[j])) * invn;
+                        uint32_t p = sc > tv[e] ? 1u : 0u;                    // tau = +inf for padded columns
+                        if (mode == 2u) p &= fbits >> ((uint32_t)fv[e] & 31u);
+                        else if (mode == 3u) p &= fv[e] < 0 ? 1u : (vb_lds_u32(mw_addr + (uint32_t)fv[e] * 4u) >> lane);
+                        m |= (p & 1u) << j;
                     }
+                }
+                if (a.direct) {
+                    if (row_ok) {
+#pragma unroll
+                        for (uint32_t j = 0; j < 16u; ++j) {
+                            const uint32_t col = c0 + j;
+                            if (col < a.n_q)
+                                a.cand[(size_t)(a.q_begin + col) * a.cap + slot] =
+                                    ((m >> j) & 1u) ? vb_pack_key((split ? __uint_as_float(v[j]) + __uint_as_float(w[j]) : __uint_as_float(v[j])) * invn, a.row_base + row) : 0ull;
+                        }
+                    }
+                } else if (__any_sync(0xffffffffu, m != 0u)) {
+#pragma unroll
+                    for (uint32_t j = 0; j < 16u; ++j)
+                        if ((m >> j) & 1u)
+                            vb_push(a.cand, a.cnt, a.cap, a.q_begin + c0 + j, (split ? __uint_as_float(v[j]) + __uint_as_float(w[j]) : __uint_as_float(v[j])) * invn, a.row_base + row);
+                }
+            };
+            uint32_t va[16], vb[16], wa[16], wb[16];
+            auto load = [&](uint32_t (&v)[16], uint32_t (&w)[16], uint32_t c0) {
+                vb_tmem_ld16(taddr + c0, v);
+                if (split) vb_tmem_ld16(taddr + ncol + c0, w);
+            };
+            load(va, wa, 0);
+            for (uint32_t c0 = 0; c0 < ncol; c0 += 32u) {
+                vb_tmem_ld_wait();
+                const bool second = c0 + 16u < ncol;
+                if (second) load(vb, wb, c0 + 16u);                        // next chunk in flight
+                process(va, wa, c0);
+                if (second) {
+                    vb_tmem_ld_wait();
+                    if (c0 + 32u < ncol) load(va, wa, c0 + 32u);
+                    process(vb, wb, c0 + 16u);
                 }
             }
             vb_tcgen05_fence_before();
@@ -277,7 +352,7 @@ static int vb_gemm_configure() {
     return 0;
 }
 
-static const uint32_t VB_GEMM_TAIL_BYTES = 8u * (2u * 16u + 5u) + 16u + 256u * 4u + 256u * 4u + 4u * VB_GEMM_MAX_FILTERS * 4u;
+static const uint32_t VB_GEMM_TAIL_BYTES = 320u + 256u * 4u + 256u * 4u + 4u * VB_GEMM_MAX_FILTERS * 4u;
 
 // largest padded sub-batch whose resident query matrix leaves room for >= 4 stages
 static uint32_t vb_gemm_max_bn(uint32_t d_pad) {
@@ -285,6 +360,20 @@ static uint32_t vb_gemm_max_bn(uint32_t d_pad) {
     uint32_t bn = avail / (d_pad * 2u);
     bn = bn / 16u * 16u;
     return bn > 256u ? 256u : bn;
+}
+
+// Sub-batch geometry shared by the query-packing kernel and the launcher: queries are cut into
+// sub-batches of `sub` queries; sub-batch s occupies rows [s*sub*mult, ...) of the packed bf16
+// operand: bn_q rows of q_hi followed (split) by bn_q rows of q_lo, bn_q = round_up(n_q, 16).
+struct VbGemmPlan { uint32_t sub; uint32_t split; };
+static VbGemmPlan vb_gemm_plan(uint32_t d_pad, uint32_t B, int precision /*0 auto, 1 bf16, 2 bf16x2*/) {
+    const uint32_t bn_max = vb_gemm_max_bn(d_pad);
+    const uint32_t half = (bn_max / 2u) / 16u * 16u;
+    VbGemmPlan p;
+    p.split = precision == 2 ? 1u : (precision == 1 ? 0u : (B <= half ? 1u : 0u));
+    if (p.split && half < 16u) p.split = 0u;
+    p.sub = p.split ? half : bn_max;
+    return p;
 }
 
 static bool vb_gemm_supported(int d_pad, uint32_t B) {
@@ -306,6 +395,9 @@ struct VbGemmLaunch {
     uint32_t n_rows_total, row_begin, row_end, row_base, d_pad, n_queries;
     int sm_count;
     cudaStream_t stream;
+    uint32_t direct;
+    VbGemmPlan plan;
+    const int32_t* mask_of_host;   // host copy of mask_of (to pick the epilogue's mask mode)
 };
 
 static int vb_encode_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
@@ -323,20 +415,30 @@ static int vb_encode_2d(CUtensorMap* map, const void* base, uint64_t rows, uint6
 static int vb_gemm_launch(const VbGemmLaunch& g, int* launches) {
     if (!g_encode_tiled) { g_gemm_err = "tensor-core path not configured"; return 1; }
     if (g.mask && g.n_filters > VB_GEMM_MAX_FILTERS) { g_gemm_err = "more than 256 distinct filters in one batch"; return 1; }
-    const uint32_t bn_max = vb_gemm_max_bn(g.d_pad);
+    const uint32_t sub = g.plan.sub, mult = g.plan.split ? 2u : 1u;
     CUtensorMap tmap_a;
     if (vb_encode_2d(&tmap_a, g.rows, g.n_rows_total, g.d_pad, VB_TILE_M)) return 1;
-    for (uint32_t q0 = 0; q0 < g.n_queries; q0 += bn_max) {
-        const uint32_t n_q = std::min(bn_max, g.n_queries - q0);
-        const uint32_t bn = (n_q + 15u) / 16u * 16u;
+    for (uint32_t q0 = 0; q0 < g.n_queries; q0 += sub) {
+        const uint32_t n_q = std::min(sub, g.n_queries - q0);
+        const uint32_t bn = (n_q + 15u) / 16u * 16u * mult;
         CUtensorMap tmap_q;
-        if (vb_encode_2d(&tmap_q, reinterpret_cast<const unsigned char*>(g.q_bf16) + (size_t)q0 * g.d_pad * 2, bn, g.d_pad, bn)) return 1;
+        if (vb_encode_2d(&tmap_q, reinterpret_cast<const unsigned char*>(g.q_bf16) + (size_t)q0 * mult * g.d_pad * 2, bn, g.d_pad, bn)) return 1;
         VbGemmArgs a{};
         a.inv_norm = g.inv_norm; a.mask = g.mask; a.mask_of = g.mask_of; a.tau = g.tau; a.cand = g.cand; a.cnt = g.cnt;
         a.mask_words = g.mask_words; a.n_filters = g.n_filters; a.cap = g.cap;
         a.tile_begin = g.row_begin / VB_TILE_M; a.tile_end = (g.row_end + VB_TILE_M - 1) / VB_TILE_M;
         a.row_end = g.row_end; a.row_base = g.row_base; a.k_blocks = g.d_pad / VB_BLOCK_K;
         a.bn = bn; a.n_q = n_q; a.q_begin = q0;
+        a.direct = g.direct;
+        a.split = g.plan.split;
+        a.mask_mode = 0; a.uniform_filter = -1;
+        if (g.mask != nullptr) {
+            bool uniform = true;
+            for (uint32_t i = 1; i < n_q; ++i) uniform = uniform && g.mask_of_host[q0 + i] == g.mask_of_host[q0];
+            if (uniform && g.mask_of_host[q0] < 0) { a.mask = nullptr; a.mask_of = nullptr; }
+            else if (uniform) { a.mask_mode = 1; a.uniform_filter = g.mask_of_host[q0]; }
+            else a.mask_mode = g.n_filters <= 31u ? 2 : 3;
+        }
         const uint32_t q_bytes = bn * g.d_pad * 2u;
         uint32_t stages = ((uint32_t)g_gemm_smem_max - 1024u - VB_GEMM_TAIL_BYTES - q_bytes) / VB_STAGE_BYTES;
         a.stages = stages > 12u ? 12u : stages;

@@ -30,6 +30,7 @@ struct VbScanArgs {
     uint32_t row_base;          // added to the row in the candidate key (shard offset)
     uint32_t cap;
     uint32_t q_begin;           // first query handled by blockIdx.y == 0
+    uint32_t direct;            // 1: first segment — store the key at slot (row - row_begin), no atomics
 };
 
 __device__ __forceinline__ float vb_dot8(const uint4 v, const float* q, float acc) {
@@ -122,7 +123,9 @@ vb_dense_scan_kernel(const VbScanArgs a)
             const float inv_r = __shfl_sync(0xffffffffu, invn, myr < 0 ? 0 : myr);
             if (lane < (uint32_t)ROWS && myr >= 0) {
                 const float s = mine * inv_r;
-                if (s > tau) vb_push(a.cand, a.cnt, a.cap, list, s, a.row_base + row0 + (uint32_t)myr);
+                const uint32_t row = row0 + (uint32_t)myr;
+                if (a.direct) a.cand[(size_t)list * a.cap + (row - a.row_begin)] = s > tau ? vb_pack_key(s, a.row_base + row) : 0ull;
+                else if (s > tau) vb_push(a.cand, a.cnt, a.cap, list, s, a.row_base + row);
             }
         }
     }
@@ -163,7 +166,9 @@ vb_dense_scan_generic_kernel(const VbScanArgs a)
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == 0) {
                 const float s = acc * a.inv_norm[row0 + r];
-                if (s > tau) vb_push(a.cand, a.cnt, a.cap, list, s, a.row_base + row0 + r);
+                const uint32_t row = row0 + r;
+                if (a.direct) a.cand[(size_t)list * a.cap + (row - a.row_begin)] = s > tau ? vb_pack_key(s, a.row_base + row) : 0ull;
+                else if (s > tau) vb_push(a.cand, a.cnt, a.cap, list, s, a.row_base + row);
             }
         }
     }

@@ -90,12 +90,14 @@ vb_ingest_bf16_kernel(const __nv_bfloat16* __restrict__ src, uint32_t n, uint32_
     }
 }
 
-// Query preparation: q_hat = q/||q|| in fp32 (zero vector stays zero), zero padded to d_pad;
-// also written as bf16 for the tensor-core path.  (distances.py cosine_similarity normalises
-// the query the same way.)
+// Query preparation: q_hat = q/||q|| in fp32 (zero vector stays zero), zero padded to d_pad
+// (distances.py cosine_similarity normalises the query the same way); also packed as the bf16
+// B-operand of the tensor-core path: sub-batches of `sub` queries, each bn_q = round_up(n_q,16)
+// rows of q_hi = bf16(q_hat) followed, if `split`, by bn_q rows of q_lo = bf16(q_hat - q_hi), so
+// that q_hi + q_lo carries ~16 mantissa bits and the MMA result matches the fp32 dot to ~1e-5.
 __global__ void __launch_bounds__(128)
-vb_prep_query_kernel(const float* __restrict__ q, uint32_t dim, uint32_t d_pad,
-                     float* __restrict__ q_hat, __nv_bfloat16* __restrict__ q_bf16)
+vb_prep_query_kernel(const float* __restrict__ q, uint32_t dim, uint32_t d_pad, uint32_t n_queries,
+                     uint32_t sub, uint32_t split, float* __restrict__ q_hat, __nv_bfloat16* __restrict__ q_bf16)
 {
     __shared__ double red[4];
     const uint32_t b = blockIdx.x;
@@ -109,9 +111,15 @@ vb_prep_query_kernel(const float* __restrict__ q, uint32_t dim, uint32_t d_pad,
     __syncthreads();
     ss = red[0] + red[1] + red[2] + red[3];
     const float inv = ss > 0.0 ? (float)(1.0 / sqrt(ss)) : 0.0f;
+    const uint32_t s_idx = b / sub, j = b % sub;
+    const uint32_t n_q = min(sub, n_queries - s_idx * sub);
+    const uint32_t bn_q = (n_q + 15u) / 16u * 16u;
+    const size_t base = (size_t)s_idx * sub * (split ? 2u : 1u);
     for (uint32_t c = threadIdx.x; c < d_pad; c += blockDim.x) {
         const float v = c < dim ? q[(size_t)b * dim + c] * inv : 0.0f;
         q_hat[(size_t)b * d_pad + c] = v;
-        q_bf16[(size_t)b * d_pad + c] = __float2bfloat16_rn(v);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        q_bf16[(base + j) * d_pad + c] = hi;
+        if (split) q_bf16[(base + bn_q + j) * d_pad + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
     }
 }

@@ -91,15 +91,20 @@ struct VbSparseArgs {
     uint32_t n_rows;
     uint32_t row_base;
     uint32_t cap;
+    uint32_t direct;            // 1: first segment — store keys at slot (row - segment begin), no atomics
 };
 
+#define VB_SPARSE_THREADS 128
+#define VB_SPARSE_UNROLL 4
+
 // grid.x = (#blocks in segment) * B ; CTA (blk, q) with q fastest so that concurrently running
-// CTAs share a row block (and the posting slices of common terms hit L2).
-__global__ void __launch_bounds__(256)
+// CTAs share a row block (and the posting slices of common terms hit L2).  16 KB of shared
+// memory per CTA keeps ~14 CTAs resident per SM: the kernel is latency-bound (dependent global
+// loads per term), so residency, not bandwidth, sets its speed.
+__global__ void __launch_bounds__(VB_SPARSE_THREADS)
 vb_sparse_kernel(const VbSparseArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* acc = reinterpret_cast<unsigned long long*>(smem_raw);   // [VB_ROWS_PER_BLOCK] fp64 bits
+    __shared__ unsigned long long acc[VB_ROWS_PER_BLOCK];       // fp64 bits; sentinel = untouched
 
     const uint32_t q = blockIdx.x % a.n_queries;
     const uint32_t blk = a.blk_begin + blockIdx.x / a.n_queries;
@@ -123,13 +128,26 @@ vb_sparse_kernel(const VbSparseArgs a)
         const uint64_t lo = o[0], hi = o[1];
         if (lo == hi) continue;                                 // uniform across the CTA
         const double w = a.q_weight[j];
-        for (uint64_t p = lo + threadIdx.x; p < hi; p += blockDim.x) {
-            const uint32_t r = a.post_row[p] - row0;
-            const double prod = __dmul_rn(w, (double)a.post_val[p]);
-            const unsigned long long cur = acc[r];
-            acc[r] = (cur == VB_ACC_SENTINEL)
-                         ? (unsigned long long)__double_as_longlong(__dadd_rn(0.0, prod))
-                         : (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)cur), prod));
+        for (uint64_t p0 = lo; p0 < hi; p0 += VB_SPARSE_THREADS * VB_SPARSE_UNROLL) {
+            uint32_t r[VB_SPARSE_UNROLL];
+            float v[VB_SPARSE_UNROLL];
+#pragma unroll
+            for (int u = 0; u < VB_SPARSE_UNROLL; ++u) {        // all loads first (memory-level parallelism)
+                const uint64_t p = p0 + (uint64_t)u * VB_SPARSE_THREADS + threadIdx.x;
+                const bool ok = p < hi;
+                r[u] = ok ? __ldg(a.post_row + p) : 0xffffffffu;
+                v[u] = ok ? __ldg(a.post_val + p) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < VB_SPARSE_UNROLL; ++u) {        // inside one term every row occurs once
+                if (r[u] == 0xffffffffu) continue;
+                const uint32_t lr = r[u] - row0;
+                const double prod = __dmul_rn(w, (double)v[u]);
+                const unsigned long long cur = acc[lr];
+                acc[lr] = (cur == VB_ACC_SENTINEL)
+                              ? (unsigned long long)__double_as_longlong(__dadd_rn(0.0, prod))
+                              : (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)cur), prod));
+            }
         }
         __syncthreads();
     }
@@ -141,13 +159,18 @@ vb_sparse_kernel(const VbSparseArgs a)
         const int32_t f = a.mask_of[q];
         if (f >= 0) mask = a.mask + (size_t)f * a.mask_words;
     }
+    const uint32_t seg_row0 = a.blk_begin * VB_ROWS_PER_BLOCK;
     for (uint32_t r = threadIdx.x; r < VB_ROWS_PER_BLOCK; r += blockDim.x) {
         const unsigned long long cur = acc[r];
-        if (cur == VB_ACC_SENTINEL) continue;
         const uint32_t row = row0 + r;
-        if (row >= a.n_rows) continue;
-        if (mask && !((mask[row >> 5] >> (row & 31u)) & 1u)) continue;
-        const float s = __double2float_rn(__longlong_as_double((long long)cur));
-        if (s > tau) vb_push(a.cand, a.cnt, a.cap, list, s, a.row_base + row);
+        bool pass = cur != VB_ACC_SENTINEL && row < a.n_rows;
+        if (pass && mask) pass = (mask[row >> 5] >> (row & 31u)) & 1u;
+        float s = 0.0f;
+        if (pass) { s = __double2float_rn(__longlong_as_double((long long)cur)); pass = s > tau; }
+        if (a.direct) {
+            if (row < a.n_rows) a.cand[(size_t)list * a.cap + (row - seg_row0)] = pass ? vb_pack_key(s, a.row_base + row) : 0ull;
+        } else if (pass) {
+            vb_push(a.cand, a.cnt, a.cap, list, s, a.row_base + row);
+        }
     }
 }

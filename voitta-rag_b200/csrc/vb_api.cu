@@ -72,7 +72,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct Batch {
     uint32_t B = 0, k = 0, limit = 0, n_lists = 0, n_qterms = 0, n_filters = 0, mask_words = 0, n_blocks = 0;
     bool any_sparse = false, use_mask = false;
-    std::vector<int32_t> mode;
+    std::vector<int32_t> mode, mask_of_host;
     // device pointers into h->args
     const float* d_q = nullptr;
     const int64_t* d_qindptr = nullptr;
@@ -124,7 +124,7 @@ struct vb_index {
     uint32_t cand_cap = 0;
 
     // options
-    int64_t opt_dense_path = 0, opt_seg_first = 8192, opt_seg_ratio = 32, opt_safe_mode = 0, opt_profile = 0;
+    int64_t opt_dense_path = 0, opt_seg_first = 2048, opt_seg_ratio = 32, opt_safe_mode = 0, opt_profile = 0, opt_k2_precision = 0;
 
     vb_stats stats{};
     Batch staged;
@@ -170,9 +170,9 @@ static void dev_free(vb_index* h, DevBuf& b) {
 // ------------------------------------------------------------------------------------------------
 // tiny utility kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void vb_init_lists_kernel(float* tau, uint32_t* cnt, uint32_t* overflow, uint32_t n) {
+__global__ void vb_init_lists_kernel(float* tau, uint32_t* cnt, uint32_t* overflow, uint32_t n, uint32_t cnt0) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { tau[i] = -INFINITY; cnt[i] = 0u; overflow[i] = 0u; }
+    if (i < n) { tau[i] = -INFINITY; cnt[i] = cnt0; overflow[i] = 0u; }
 }
 __global__ void vb_fill_i64_kernel(int64_t* p, uint64_t n, int64_t v) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
@@ -234,7 +234,6 @@ extern "C" int vb_create(int32_t dim, int32_t device, uint64_t capacity_hint, ui
         return vb_fail("vb_create: stream/event creation failed");
     }
     h->stream = h->own_stream;
-    cudaFuncSetAttribute(vb_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(VB_ROWS_PER_BLOCK * 8u));
     if (vb_gemm_configure() != 0) { delete h; return vb_fail("vb_create: tensor-core kernel configuration failed: %s", vb_gemm_last_error()); }
     (void)capacity_hint;
     if (const char* env = getenv("VB200_DENSE_PATH")) h->opt_dense_path = atoi(env);   // 0 auto, 1 K1, 2 K2
@@ -267,6 +266,7 @@ extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
     else if (k == "seg_ratio") h->opt_seg_ratio = std::max<int64_t>(2, value);
     else if (k == "safe_mode") h->opt_safe_mode = value;
     else if (k == "profile") h->opt_profile = value;
+    else if (k == "k2_precision") h->opt_k2_precision = value;   // 0 auto, 1 bf16 query, 2 bf16x2 (hi+lo) query
     else if (k == "stream") {   // run on the caller's stream (e.g. torch's current stream); 0 = own stream
         h->stream = value ? reinterpret_cast<cudaStream_t>(static_cast<uintptr_t>(value)) : h->own_stream;
     }
@@ -698,6 +698,7 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
         any_filter = true;
     }
     b.use_mask = any_filter && need_corpus;
+    b.mask_of_host = mask_of;
     b.n_filters = b.use_mask ? (uint32_t)flt.size() : 0;
     b.mask_words = (uint32_t)((h->n_rows + 31) / 32);
     b.n_blocks = (uint32_t)((h->n_rows + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK);
@@ -774,14 +775,18 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     return 0;
 }
 
-static int init_lists(vb_index* h, const Batch& b) {
-    vb_init_lists_kernel<<<(b.n_lists + 255) / 256, 256, 0, h->stream>>>(b.tau, b.cnt, b.overflow, b.n_lists);
+// direct_rows > 0: the first segment stores its keys at fixed slots [0, direct_rows) of every
+// list (no atomics); slots nobody writes (masked rows, rows without postings) must read as empty.
+static int init_lists(vb_index* h, const Batch& b, uint32_t direct_rows) {
+    vb_init_lists_kernel<<<(b.n_lists + 255) / 256, 256, 0, h->stream>>>(b.tau, b.cnt, b.overflow, b.n_lists, direct_rows);
     CKK("vb_init_lists_kernel");
     ++h->stats.last_launches;
+    if (direct_rows)
+        CK(cudaMemset2DAsync(h->cand.p, (size_t)h->cand_cap * 8, 0, (size_t)direct_rows * 8, b.n_lists, h->stream));
     return 0;
 }
 
-static int launch_scan(vb_index* h, const Batch& b, uint32_t row_begin, uint32_t row_end) {
+static int launch_scan(vb_index* h, const Batch& b, uint32_t row_begin, uint32_t row_end, uint32_t direct) {
     VbScanArgs a{};
     a.rows = h->rows.as<uint4>();
     a.inv_norm = h->inv_norm.as<float>();
@@ -798,6 +803,7 @@ static int launch_scan(vb_index* h, const Batch& b, uint32_t row_begin, uint32_t
     a.row_base = (uint32_t)h->row_base;
     a.cap = h->cand_cap;
     a.q_begin = 0;
+    a.direct = direct;
     const uint32_t groups = (row_end - row_begin + 31) / 32;
     const uint32_t per_q = std::max<uint32_t>(1, (uint32_t)(h->sm_count * 8) / std::min<uint32_t>(b.B, 8));
     dim3 grid(std::min<uint32_t>((groups + 7) / 8, per_q), b.B);
@@ -818,11 +824,30 @@ static int launch_scan(vb_index* h, const Batch& b, uint32_t row_begin, uint32_t
 // cand[list][0..cnt).  `safe`: fixed small segments that can never overflow a list.
 static int run_branches(vb_index* h, const Batch& b, bool safe) {
     const uint32_t n = (uint32_t)h->n_rows;
-    TRY(init_lists(h, b));
-    // query prep
+    // segment schedule (boundaries are multiples of VB_ROWS_PER_BLOCK)
+    std::vector<uint32_t> bounds{0};
+    if (safe || h->opt_safe_mode) {
+        const uint32_t step = (uint32_t)std::max<size_t>(VB_ROWS_PER_BLOCK, (h->cand_cap - b.k) / VB_ROWS_PER_BLOCK * VB_ROWS_PER_BLOCK);
+        for (uint64_t r = step; r < n; r += step) bounds.push_back((uint32_t)r);
+    } else {
+        for (uint64_t r = (uint64_t)h->opt_seg_first; r < n; r *= (uint64_t)h->opt_seg_ratio) bounds.push_back((uint32_t)r);
+    }
+    bounds.push_back(n);
+    const uint32_t direct_rows = bounds[1] <= h->cand_cap ? bounds[1] : 0u;   // first segment writes slots directly
+    TRY(init_lists(h, b, direct_rows));
+    // dense path choice
+    int path = (int)h->opt_dense_path;
+    if (path == 0) path = vb_gemm_supported(h->d_pad, b.B) && b.B >= 2 ? 2 : 1;
+    if (path == 2 && !vb_gemm_supported(h->d_pad, b.B)) return vb_fail("dense_path=2 requested but unsupported for d_pad=%d B=%u", h->d_pad, b.B);
+    h->stats.last_dense_path = (uint32_t)path;
+    VbGemmPlan plan{1u, 0u};
+    if (path == 2) plan = vb_gemm_plan((uint32_t)h->d_pad, b.B, (int)h->opt_k2_precision);
+    h->stats.last_dense_passes = path == 2 ? (b.B + plan.sub - 1) / plan.sub : b.B;
+    // query prep (fp32 unit queries for K1, packed bf16 operand for K2)
     TRY(dev_reserve(h, h->q_hat, (size_t)b.B * h->d_pad * 4, false));
-    TRY(dev_reserve(h, h->q_bf16, (size_t)align_up(b.B, 256) * h->d_pad * 2, false));
-    vb_prep_query_kernel<<<b.B, 128, 0, h->stream>>>(b.d_q, (uint32_t)h->dim, (uint32_t)h->d_pad, h->q_hat.as<float>(), h->q_bf16.as<__nv_bfloat16>());
+    TRY(dev_reserve(h, h->q_bf16, (size_t)(2 * ((size_t)b.B + 256)) * h->d_pad * 2, false));
+    vb_prep_query_kernel<<<b.B, 128, 0, h->stream>>>(b.d_q, (uint32_t)h->dim, (uint32_t)h->d_pad, b.B, plan.sub, plan.split,
+                                                     h->q_hat.as<float>(), h->q_bf16.as<__nv_bfloat16>());
     CKK("vb_prep_query_kernel");
     ++h->stats.last_launches;
     // K0 filter masks
@@ -847,25 +872,9 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
         ++h->stats.last_launches;
         prof_end(h);
     }
-    // dense path choice
-    int path = (int)h->opt_dense_path;
-    if (path == 0) path = vb_gemm_supported(h->d_pad, b.B) && b.B >= 2 ? 2 : 1;
-    if (path == 2 && !vb_gemm_supported(h->d_pad, b.B)) return vb_fail("dense_path=2 requested but unsupported for d_pad=%d B=%u", h->d_pad, b.B);
-    h->stats.last_dense_path = (uint32_t)path;
-    h->stats.last_dense_passes = path == 2 ? (b.B + vb_gemm_max_bn((uint32_t)h->d_pad) - 1) / vb_gemm_max_bn((uint32_t)h->d_pad) : b.B;
-
-    // segment schedule (boundaries are multiples of VB_ROWS_PER_BLOCK)
-    std::vector<uint32_t> bounds{0};
-    if (safe || h->opt_safe_mode) {
-        const uint32_t step = (uint32_t)std::max<size_t>(VB_ROWS_PER_BLOCK, (h->cand_cap - b.k) / VB_ROWS_PER_BLOCK * VB_ROWS_PER_BLOCK);
-        for (uint64_t r = step; r < n; r += step) bounds.push_back((uint32_t)r);
-    } else {
-        for (uint64_t r = (uint64_t)h->opt_seg_first; r < n; r *= (uint64_t)h->opt_seg_ratio) bounds.push_back((uint32_t)r);
-    }
-    bounds.push_back(n);
-
     for (size_t s = 0; s + 1 < bounds.size(); ++s) {
         const uint32_t r0 = bounds[s], r1 = bounds[s + 1];
+        const uint32_t direct = (s == 0 && direct_rows) ? 1u : 0u;
         prof_begin(h, PH_DENSE);
         if (path == 2) {
             VbGemmLaunch g{};
@@ -874,11 +883,12 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
             g.mask_words = b.mask_words; g.n_filters = b.n_filters; g.tau = b.tau; g.cand = h->cand.as<uint64_t>(); g.cnt = b.cnt;
             g.cap = h->cand_cap; g.n_rows_total = n; g.row_begin = r0; g.row_end = r1; g.row_base = (uint32_t)h->row_base;
             g.d_pad = (uint32_t)h->d_pad; g.n_queries = b.B; g.sm_count = h->sm_count; g.stream = h->stream;
+            g.direct = direct; g.plan = plan; g.mask_of_host = b.mask_of_host.data();
             int launches = 0;
             if (vb_gemm_launch(g, &launches) != 0) return vb_fail("tensor-core dense kernel: %s", vb_gemm_last_error());
             h->stats.last_launches += (uint32_t)launches;
         } else {
-            TRY(launch_scan(h, b, r0, r1));
+            TRY(launch_scan(h, b, r0, r1, direct));
         }
         prof_end(h);
         if (do_sparse) {
@@ -889,9 +899,9 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
             a.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; a.mask_of = b.use_mask ? b.d_maskof : nullptr;
             a.tau = b.tau; a.cand = h->cand.as<uint64_t>(); a.cnt = b.cnt; a.mask_words = b.mask_words;
             a.n_blocks = b.n_blocks; a.blk_begin = r0 / VB_ROWS_PER_BLOCK; a.n_queries = b.B; a.n_rows = n;
-            a.row_base = (uint32_t)h->row_base; a.cap = h->cand_cap;
+            a.row_base = (uint32_t)h->row_base; a.cap = h->cand_cap; a.direct = direct;
             const uint32_t nblk = (r1 - r0 + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK;
-            vb_sparse_kernel<<<nblk * b.B, 256, VB_ROWS_PER_BLOCK * 8, h->stream>>>(a);
+            vb_sparse_kernel<<<nblk * b.B, VB_SPARSE_THREADS, 0, h->stream>>>(a);
             CKK("vb_sparse_kernel");
             ++h->stats.last_launches;
             prof_end(h);
@@ -1020,7 +1030,7 @@ extern "C" int vb_run_local(vb_index* h, uint64_t* cand_dev) {
     h->stats.last_launches = 0;
     CK(cudaEventRecord(h->ev0, h->stream));
     if (h->n_rows == 0) {
-        TRY(init_lists(h, h->staged));
+        TRY(init_lists(h, h->staged, 0));
     } else {
         TRY(run_branches(h, h->staged, h->staged_safe));
     }
@@ -1116,7 +1126,7 @@ extern "C" int vb_merge_fuse(vb_index* h, const vb_query_batch* q, uint32_t n_sh
     TRY(vb_stage(h, q, wants_branches(out), 0));
     CK(cudaEventRecord(h->ev0, h->stream));
     h->stats.last_launches = 0;
-    TRY(init_lists(h, h->staged));
+    TRY(init_lists(h, h->staged, 0));
     TRY(vb_run_fuse(h, n_shards, gathered_dev));
     int32_t overflowed = 0;
     TRY(vb_fetch(h, out, &overflowed));
