@@ -20,6 +20,8 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <string>
+#include <cstdlib>
+#include <algorithm>
 
 #define VB_GEMM_THREADS 192
 #define VB_TILE_M 128u
@@ -57,6 +59,11 @@ __device__ __forceinline__ void vb_tma_load_2d(uint32_t dst, const CUtensorMap* 
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void vb_tma_load_3d(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, int32_t c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void vb_tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void vb_tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -129,8 +136,14 @@ struct VbGemmArgs {
     uint32_t mask_mode;              // 0 none, 1 one filter for the whole sub-batch, 2 <= 31 filters, 3 general
     int32_t  uniform_filter;         // mask_mode 1: the filter index
     uint32_t split;                  // 1: columns [0,bn/2) hold q_hi, [bn/2,bn) hold q_lo (bf16x2 query precision)
+    uint32_t kbox;                   // K-blocks (of 64) per TMA box / pipeline stage
+    uint32_t debug;                  // perf triage only (VB200_K2_DEBUG): 1 skip epilogue math, 2 skip MMA, 4 skip TMA
 };
 
+// MODE: per-column mask handling (0 = none / one filter folded into the row scale, 2 = <= 31
+// filters via a per-row bit set, 3 = general); SPLIT: bf16x2 query; DIRECT: first-segment stores.
+// They are template parameters so that the per-column epilogue code is branch-free.
+template <int MODE, bool SPLIT, bool DIRECT>
 __global__ void __launch_bounds__(VB_GEMM_THREADS, 1)
 vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_q,
                      const VbGemmArgs a)
@@ -141,7 +154,8 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     const uint32_t q_bytes = a.bn * a.k_blocks * 128u;                       // resident query matrix
     unsigned char* smem_q = smem;
     unsigned char* smem_a = smem + q_bytes;                                   // stages * 16 KB (q_bytes % 1024 == 0)
-    unsigned char* tail = smem_a + a.stages * VB_STAGE_BYTES;
+    const uint32_t stage_bytes = a.kbox * VB_STAGE_BYTES;
+    unsigned char* tail = smem_a + a.stages * stage_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail);                       // full[S], empty[S], tfull[2], tempty[2], qfull
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tail + 8u * (2u * 16u + 5u));
     float* tau_s = reinterpret_cast<float*>(tail + 320u);                         // [256], 16-byte aligned
@@ -185,10 +199,14 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
                 const int32_t row0 = (int32_t)((a.tile_begin + t) * VB_TILE_M);
-                for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
+                for (uint32_t kb = 0; kb < a.k_blocks; kb += a.kbox) {
                     vb_mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
-                    vb_mbar_expect_tx(bar_full + 8u * stage, VB_STAGE_BYTES);
-                    vb_tma_load_2d(vb_smem_u32(smem_a + stage * VB_STAGE_BYTES), &tmap_a, (int32_t)(kb * VB_BLOCK_K), row0, bar_full + 8u * stage);
+                    if (a.debug & 4u) { vb_mbar_arrive(bar_full + 8u * stage); }
+                    else {
+                    vb_mbar_expect_tx(bar_full + 8u * stage, stage_bytes);
+                    // one box = 128 rows x kbox K-blocks: [kb][row][64] in smem, i.e. kbox UMMA slabs
+                    vb_tma_load_3d(vb_smem_u32(smem_a + stage * stage_bytes), &tmap_a, 0, row0, (int32_t)kb, bar_full + 8u * stage);
+                    }
                     if (++stage == S) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -204,14 +222,18 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 vb_mbar_wait(bar_tempty + 8u * acc, ((it >> 1) & 1u) ^ 1u);
                 vb_tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * 256u;
-                for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
+                for (uint32_t kb0 = 0; kb0 < a.k_blocks; kb0 += a.kbox) {
                     vb_mbar_wait(bar_full + 8u * stage, phase);
                     vb_tcgen05_fence_after();
-                    const uint32_t a_addr = vb_smem_u32(smem_a + stage * VB_STAGE_BYTES);
-                    const uint32_t q_addr = vb_smem_u32(smem_q + kb * a.bn * 128u);
+                    const uint32_t nkb = min(a.kbox, a.k_blocks - kb0);
+                    for (uint32_t kk = 0; kk < nkb && !(a.debug & 2u); ++kk) {
+                        const uint32_t kb = kb0 + kk;
+                        const uint32_t a_addr = vb_smem_u32(smem_a + stage * stage_bytes + kk * VB_STAGE_BYTES);
+                        const uint32_t q_addr = vb_smem_u32(smem_q + kb * a.bn * 128u);
 #pragma unroll
-                    for (uint32_t k = 0; k < VB_BLOCK_K / 16u; ++k)
-                        vb_tcgen05_mma_bf16(tmem_d, vb_umma_desc(a_addr + k * 32u), vb_umma_desc(q_addr + k * 32u), idesc, (kb | k) != 0u);
+                        for (uint32_t k = 0; k < VB_BLOCK_K / 16u; ++k)
+                            vb_tcgen05_mma_bf16(tmem_d, vb_umma_desc(a_addr + k * 32u), vb_umma_desc(q_addr + k * 32u), idesc, (kb | k) != 0u);
+                    }
                     vb_tcgen05_commit(bar_empty + 8u * stage);     // smem stage free once these MMAs retire
                     if (++stage == S) { stage = 0; phase ^= 1u; }
                 }
@@ -226,8 +248,8 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const uint32_t tau_addr = vb_smem_u32(tau_s), mof_addr = vb_smem_u32(mof_s);
         const uint32_t mw_addr = vb_smem_u32(mw_s + quad * VB_GEMM_MAX_FILTERS);
         uint32_t* mw = mw_s + quad * VB_GEMM_MAX_FILTERS;
-        const uint32_t mode = a.mask_mode;
-        const bool split = a.split != 0u;
+        constexpr uint32_t mode = (uint32_t)MODE;
+        constexpr bool split = SPLIT;
         const uint32_t ncol = split ? a.bn >> 1 : a.bn;       // query columns handled by the epilogue
         const float qnan = __int_as_float(0x7fc00000);
         uint32_t it = 0;
@@ -241,7 +263,7 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             float invn = row_ok ? a.inv_norm[row] : qnan;
             const uint32_t word = tile * 4u + quad;
             uint32_t fbits = 0x80000000u;                 // mode 2: bit f = row passes filter f; bit 31 = unfiltered
-            if (mode == 1u) {
+            if (MODE == 0 && a.mask_mode == 1u) {
                 const uint32_t w = word < a.mask_words ? a.mask[(size_t)a.uniform_filter * a.mask_words + word] : 0u;
                 if (!((w >> lane) & 1u)) invn = qnan;
             } else if (mode == 2u) {
@@ -279,7 +301,7 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                         m |= (p & 1u) << j;
                     }
                 }
-                if (a.direct) {
+                if (DIRECT) {
                     if (row_ok) {
 #pragma unroll
                         for (uint32_t j = 0; j < 16u; ++j) {
@@ -290,10 +312,21 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                         }
                     }
                 } else if (__any_sync(0xffffffffu, m != 0u)) {
+                    // rare path: reserve slots for all survivors of the chunk first (predicated atomics
+                    // issued back to back, so their L2 round trips overlap), then store the keys
+                    uint32_t slot[16];
 #pragma unroll
-                    for (uint32_t j = 0; j < 16u; ++j)
-                        if ((m >> j) & 1u)
-                            vb_push(a.cand, a.cnt, a.cap, a.q_begin + c0 + j, (split ? __uint_as_float(v[j]) + __uint_as_float(w[j]) : __uint_as_float(v[j])) * invn, a.row_base + row);
+                    for (uint32_t j = 0; j < 16u; ++j) {
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p atom.global.add.u32 %0, [%1], 1;\n\t}"
+                            : "=r"(slot[j]) : "l"(a.cnt + a.q_begin + c0 + j), "r"((m >> j) & 1u) : "memory");
+                    }
+#pragma unroll
+                    for (uint32_t j = 0; j < 16u; ++j) {
+                        if (((m >> j) & 1u) && slot[j] < a.cap)
+                            a.cand[(size_t)(a.q_begin + c0 + j) * a.cap + slot[j]] =
+                                vb_pack_key((split ? __uint_as_float(v[j]) + __uint_as_float(w[j]) : __uint_as_float(v[j])) * invn, a.row_base + row);
+                    }
                 }
             };
             uint32_t va[16], vb[16], wa[16], wb[16];
@@ -301,8 +334,8 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 vb_tmem_ld16(taddr + c0, v);
                 if (split) vb_tmem_ld16(taddr + ncol + c0, w);
             };
-            load(va, wa, 0);
-            for (uint32_t c0 = 0; c0 < ncol; c0 += 32u) {
+            if (!(a.debug & 1u)) load(va, wa, 0);
+            for (uint32_t c0 = 0; c0 < ncol && !(a.debug & 1u); c0 += 32u) {
                 vb_tmem_ld_wait();
                 const bool second = c0 + 16u < ncol;
                 if (second) load(vb, wb, c0 + 16u);                        // next chunk in flight
@@ -333,6 +366,20 @@ typedef CUresult (*VbEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 static VbEncodeTiledFn g_encode_tiled = nullptr;
 static int g_gemm_smem_max = 0;
 
+typedef void (*VbGemmKernel)(const CUtensorMap, const CUtensorMap, const VbGemmArgs);
+// variant index = modeIdx*4 + split*2 + direct, modeIdx: 0 -> MODE 0, 1 -> MODE 2, 2 -> MODE 3
+static VbGemmKernel vb_gemm_variant(int i) {
+    static const VbGemmKernel table[12] = {
+        vb_dense_gemm_kernel<0, false, false>, vb_dense_gemm_kernel<0, false, true>,
+        vb_dense_gemm_kernel<0, true, false>,  vb_dense_gemm_kernel<0, true, true>,
+        vb_dense_gemm_kernel<2, false, false>, vb_dense_gemm_kernel<2, false, true>,
+        vb_dense_gemm_kernel<2, true, false>,  vb_dense_gemm_kernel<2, true, true>,
+        vb_dense_gemm_kernel<3, false, false>, vb_dense_gemm_kernel<3, false, true>,
+        vb_dense_gemm_kernel<3, true, false>,  vb_dense_gemm_kernel<3, true, true>,
+    };
+    return table[i];
+}
+
 static int vb_gemm_configure() {
     if (g_encode_tiled) return 0;
     void* fn = nullptr;
@@ -345,8 +392,10 @@ static int vb_gemm_configure() {
     int dev = 0, smem = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    e = cudaFuncSetAttribute(vb_dense_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) { g_gemm_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
+    for (int i = 0; i < 12; ++i) {
+        e = cudaFuncSetAttribute(vb_gemm_variant(i), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { g_gemm_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
+    }
     g_gemm_smem_max = smem;
     g_encode_tiled = reinterpret_cast<VbEncodeTiledFn>(fn);
     return 0;
@@ -355,8 +404,20 @@ static int vb_gemm_configure() {
 static const uint32_t VB_GEMM_TAIL_BYTES = 320u + 256u * 4u + 256u * 4u + 4u * VB_GEMM_MAX_FILTERS * 4u;
 
 // largest padded sub-batch whose resident query matrix leaves room for >= 4 stages
+static int vb_env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+// K-blocks per TMA box (pipeline stage granularity)
+static uint32_t vb_gemm_kbox(uint32_t d_pad) {
+    const uint32_t k_blocks = d_pad / VB_BLOCK_K;
+    uint32_t kbox = (uint32_t)vb_env_int("VB200_K2_KBOX", 3);
+    if (kbox < 1u) kbox = 1u;
+    return kbox > k_blocks ? k_blocks : kbox;
+}
 static uint32_t vb_gemm_max_bn(uint32_t d_pad) {
-    const uint32_t avail = (uint32_t)g_gemm_smem_max - 1024u - VB_GEMM_TAIL_BYTES - 4u * VB_STAGE_BYTES;
+    const uint32_t reserve = std::max(4u, 2u * vb_gemm_kbox(d_pad)) * VB_STAGE_BYTES;   // room for the A ring
+    const uint32_t avail = (uint32_t)g_gemm_smem_max - 1024u - VB_GEMM_TAIL_BYTES - reserve;
     uint32_t bn = avail / (d_pad * 2u);
     bn = bn / 16u * 16u;
     return bn > 256u ? 256u : bn;
@@ -412,12 +473,30 @@ static int vb_encode_2d(CUtensorMap* map, const void* base, uint64_t rows, uint6
     return 0;
 }
 
+// A operand as a 3-D tensor [k_block][row][64]: one TMA box brings `kbox` K-blocks of 128 rows,
+// landing as kbox consecutive [128 rows x 128 B] swizzled slabs (what the UMMA descriptors expect).
+static int vb_encode_a3d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t d_pad, uint32_t kbox, int promo) {
+    cuuint64_t dims[3] = {VB_BLOCK_K, rows, d_pad / VB_BLOCK_K};
+    cuuint64_t strides[2] = {d_pad * 2, VB_BLOCK_K * 2};
+    cuuint32_t box[3] = {VB_BLOCK_K, VB_TILE_M, kbox};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : (promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B),
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { g_gemm_err = "cuTensorMapEncodeTiled(3d) failed (" + std::to_string((int)r) + ")"; return 1; }
+    return 0;
+}
+
 static int vb_gemm_launch(const VbGemmLaunch& g, int* launches) {
     if (!g_encode_tiled) { g_gemm_err = "tensor-core path not configured"; return 1; }
     if (g.mask && g.n_filters > VB_GEMM_MAX_FILTERS) { g_gemm_err = "more than 256 distinct filters in one batch"; return 1; }
     const uint32_t sub = g.plan.sub, mult = g.plan.split ? 2u : 1u;
+    const uint32_t k_blocks = g.d_pad / VB_BLOCK_K;
+    const uint32_t kbox = vb_gemm_kbox(g.d_pad);
+    (void)k_blocks;
     CUtensorMap tmap_a;
-    if (vb_encode_2d(&tmap_a, g.rows, g.n_rows_total, g.d_pad, VB_TILE_M)) return 1;
+    if (vb_encode_a3d(&tmap_a, g.rows, g.n_rows_total, g.d_pad, kbox, vb_env_int("VB200_K2_L2PROMO", 1))) return 1;
     for (uint32_t q0 = 0; q0 < g.n_queries; q0 += sub) {
         const uint32_t n_q = std::min(sub, g.n_queries - q0);
         const uint32_t bn = (n_q + 15u) / 16u * 16u * mult;
@@ -440,12 +519,17 @@ static int vb_gemm_launch(const VbGemmLaunch& g, int* launches) {
             else a.mask_mode = g.n_filters <= 31u ? 2 : 3;
         }
         const uint32_t q_bytes = bn * g.d_pad * 2u;
-        uint32_t stages = ((uint32_t)g_gemm_smem_max - 1024u - VB_GEMM_TAIL_BYTES - q_bytes) / VB_STAGE_BYTES;
-        a.stages = stages > 12u ? 12u : stages;
-        const size_t smem = 1024u + q_bytes + a.stages * VB_STAGE_BYTES + VB_GEMM_TAIL_BYTES;
+        a.kbox = kbox;
+        a.debug = (uint32_t)vb_env_int("VB200_K2_DEBUG", 0);
+        uint32_t stages = ((uint32_t)g_gemm_smem_max - 1024u - VB_GEMM_TAIL_BYTES - q_bytes) / (kbox * VB_STAGE_BYTES);
+        const uint32_t cap_stages = (uint32_t)vb_env_int("VB200_K2_STAGES", 12);
+        a.stages = stages > cap_stages ? cap_stages : stages;
+        if (a.stages < 2u) { g_gemm_err = "not enough shared memory for a 2-stage pipeline"; return 1; }
+        const size_t smem = 1024u + q_bytes + a.stages * kbox * VB_STAGE_BYTES + VB_GEMM_TAIL_BYTES;
         const uint32_t tiles = a.tile_end - a.tile_begin;
         const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)g.sm_count);
-        vb_dense_gemm_kernel<<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
+        const int variant = (a.mask_mode >= 2u ? (int)a.mask_mode - 1 : 0) * 4 + (a.split ? 2 : 0) + (a.direct ? 1 : 0);
+        vb_gemm_variant(variant)<<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { g_gemm_err = std::string("launch failed: ") + cudaGetErrorString(e); return 1; }
         ++*launches;
