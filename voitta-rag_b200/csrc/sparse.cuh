@@ -22,7 +22,7 @@
 #include "common.cuh"
 #include <cub/cub.cuh>
 
-#define VB_ACC_SENTINEL 0x7ff8dead00000000ull   // a NaN payload no sum can produce
+#define VB_ACC_SENTINEL 0x8000000000000000ull   // -0.0: no sum can produce it (see vb_sparse_kernel)
 
 // ---- index build ------------------------------------------------------------------------------
 // key = term << 32 | row for live rows, ~0 for tombstoned rows (sorted to the tail, then cut).
@@ -53,20 +53,21 @@ vb_posting_split_kernel(const uint64_t* __restrict__ keys, uint64_t nnz, uint32_
 }
 
 // ---- per-batch slice table ----------------------------------------------------------------------
-// off[j][b] = first posting of query-term j whose row >= b*VB_ROWS_PER_BLOCK  (b = 0..n_blocks)
+// off[j][b] = first posting of query-term j whose row >= b*VB_ROWS_PER_BLOCK  (b = 0..n_blocks).
+// Posting offsets fit 32 bits (a shard holds < 2^31 postings).
 __global__ void __launch_bounds__(256)
-vb_slice_kernel(const uint32_t* __restrict__ post_row, const uint64_t* __restrict__ qt_lo,
-                const uint64_t* __restrict__ qt_hi, uint32_t n_qterms, uint32_t n_blocks,
-                uint64_t* __restrict__ off)
+vb_slice_kernel(const uint32_t* __restrict__ post_row, const uint32_t* __restrict__ qt_lo,
+                const uint32_t* __restrict__ qt_hi, uint32_t n_qterms, uint32_t n_blocks,
+                uint32_t* __restrict__ off)
 {
     const uint64_t total = (uint64_t)n_qterms * (n_blocks + 1u);
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t j = (uint32_t)(i / (n_blocks + 1u));
         const uint32_t b = (uint32_t)(i % (n_blocks + 1u));
-        uint64_t lo = qt_lo[j], hi = qt_hi[j];
+        uint32_t lo = qt_lo[j], hi = qt_hi[j];
         const uint64_t target = (uint64_t)b * VB_ROWS_PER_BLOCK;
         while (lo < hi) {
-            const uint64_t mid = (lo + hi) >> 1;
+            const uint32_t mid = lo + ((hi - lo) >> 1);
             if ((uint64_t)post_row[mid] < target) lo = mid + 1; else hi = mid;
         }
         off[i] = lo;
@@ -76,7 +77,7 @@ vb_slice_kernel(const uint32_t* __restrict__ post_row, const uint64_t* __restric
 struct VbSparseArgs {
     const uint32_t* post_row;
     const float* post_val;
-    const uint64_t* off;        // [n_qterms][n_blocks+1]
+    const uint32_t* off;        // [n_qterms][n_blocks+1]
     const int64_t* q_indptr;    // [B+1] into the sorted query-term arrays
     const double* q_weight;     // [n_qterms] idf-scaled query values, ascending term id per query
     const uint32_t* mask;       // [n_filters][mask_words] or nullptr
@@ -95,61 +96,99 @@ struct VbSparseArgs {
 };
 
 #define VB_SPARSE_THREADS 128
-#define VB_SPARSE_UNROLL 4
+#define VB_SPARSE_UNROLL 2
 
 // grid.x = (#blocks in segment) * B ; CTA (blk, q) with q fastest so that concurrently running
-// CTAs share a row block (and the posting slices of common terms hit L2).  16 KB of shared
-// memory per CTA keeps ~14 CTAs resident per SM: the kernel is latency-bound (dependent global
-// loads per term), so residency, not bandwidth, sets its speed.
+// CTAs share a row block (and the posting slices of common terms hit L2).  The kernel is
+// instruction/latency-bound, not bandwidth-bound, so it (1) fetches all slice bounds of the query
+// for this block in one parallel step, (2) keeps only the non-empty terms, (3) software-pipelines
+// the posting loads one step ahead of the shared-memory accumulation and (4) keeps the per-posting
+// instruction count minimal:
+//   accumulators start at -0.0 and every product is canonicalised with "+ 0.0", so
+//   acc = acc + (w*v + 0.0) reproduces Python's `result = 0.0; result += w*v` bit for bit (the only
+//   differences would involve -0.0, which both sides turn into +0.0) while an untouched row is
+//   still recognisable (-0.0 can never be a sum); padding lanes accumulate 0 into a dummy slot.
 __global__ void __launch_bounds__(VB_SPARSE_THREADS)
 vb_sparse_kernel(const VbSparseArgs a)
 {
-    __shared__ unsigned long long acc[VB_ROWS_PER_BLOCK];       // fp64 bits; sentinel = untouched
+    __shared__ double acc[VB_ROWS_PER_BLOCK + 1];               // [VB_ROWS_PER_BLOCK] = dummy slot for padding lanes
+    __shared__ uint32_t s_lo[256], s_hi[256];                   // VB_MAX_QUERY_TERMS slices of this block
+    __shared__ double s_w[256];
+    __shared__ uint16_t s_nz[256];                              // non-empty terms, ascending term id
+    __shared__ uint32_t s_nnz;
 
     const uint32_t q = blockIdx.x % a.n_queries;
     const uint32_t blk = a.blk_begin + blockIdx.x / a.n_queries;
-    const int64_t t_lo = a.q_indptr[q], t_hi = a.q_indptr[q + 1];
-    if (t_lo == t_hi) return;                                   // dense-only query
+    const int64_t t_lo = a.q_indptr[q];
+    const uint32_t nt = (uint32_t)(a.q_indptr[q + 1] - t_lo);
+    if (nt == 0) return;                                        // dense-only query
 
-    // any posting of this query in this block?
-    int any = 0;
-    for (int64_t j = t_lo + threadIdx.x; j < t_hi; j += blockDim.x) {
-        const uint64_t* o = a.off + (size_t)j * (a.n_blocks + 1u) + blk;
-        any |= (o[1] > o[0]);
+    for (uint32_t j = threadIdx.x; j < nt; j += blockDim.x) {
+        const uint32_t* o = a.off + (size_t)(t_lo + j) * (a.n_blocks + 1u) + blk;
+        s_lo[j] = o[0];
+        s_hi[j] = o[1];
+        s_w[j] = a.q_weight[t_lo + j];
     }
-    if (!__syncthreads_or(any)) return;
-
-    for (uint32_t r = threadIdx.x; r < VB_ROWS_PER_BLOCK; r += blockDim.x) acc[r] = VB_ACC_SENTINEL;
     __syncthreads();
+    if (threadIdx.x < 32) {                                     // ordered compaction of the non-empty terms
+        uint32_t base = 0;
+        for (uint32_t j0 = 0; j0 < nt; j0 += 32) {
+            const uint32_t j = j0 + threadIdx.x;
+            const bool ne = j < nt && s_hi[j] > s_lo[j];
+            const uint32_t bal = __ballot_sync(0xffffffffu, ne);
+            if (ne) s_nz[base + __popc(bal & ((1u << threadIdx.x) - 1u))] = (uint16_t)j;
+            base += __popc(bal);
+        }
+        if (threadIdx.x == 0) s_nnz = base;
+    }
+    const double neg_zero = __longlong_as_double((long long)VB_ACC_SENTINEL);
+    for (uint32_t r = threadIdx.x; r <= VB_ROWS_PER_BLOCK; r += blockDim.x) acc[r] = neg_zero;
+    __syncthreads();
+    const uint32_t nnz = s_nnz;
+    if (nnz == 0) return;                                       // (direct-mode slots were zeroed by the host)
 
     const uint32_t row0 = blk * VB_ROWS_PER_BLOCK;
-    for (int64_t j = t_lo; j < t_hi; ++j) {
-        const uint64_t* o = a.off + (size_t)j * (a.n_blocks + 1u) + blk;
-        const uint64_t lo = o[0], hi = o[1];
-        if (lo == hi) continue;                                 // uniform across the CTA
-        const double w = a.q_weight[j];
-        for (uint64_t p0 = lo; p0 < hi; p0 += VB_SPARSE_THREADS * VB_SPARSE_UNROLL) {
-            uint32_t r[VB_SPARSE_UNROLL];
-            float v[VB_SPARSE_UNROLL];
+    // posting stream: for each non-empty term, steps of U*blockDim.x postings (U per thread, all
+    // independent); the loads of step i+1 are in flight while step i is accumulated.
+    constexpr int U = VB_SPARSE_UNROLL;
+    constexpr uint32_t STEP = VB_SPARSE_THREADS * U;
+    uint32_t ti = 0, p0 = s_lo[s_nz[0]], hi = s_hi[s_nz[0]];
+    uint32_t r_cur[U], r_nxt[U];
+    float v_cur[U], v_nxt[U];
 #pragma unroll
-            for (int u = 0; u < VB_SPARSE_UNROLL; ++u) {        // all loads first (memory-level parallelism)
-                const uint64_t p = p0 + (uint64_t)u * VB_SPARSE_THREADS + threadIdx.x;
-                const bool ok = p < hi;
-                r[u] = ok ? __ldg(a.post_row + p) : 0xffffffffu;
-                v[u] = ok ? __ldg(a.post_val + p) : 0.0f;
-            }
+    for (int u = 0; u < U; ++u) {
+        const uint32_t p = p0 + u * VB_SPARSE_THREADS + threadIdx.x;
+        const bool ok = p < hi;
+        r_cur[u] = ok ? __ldg(a.post_row + p) - row0 : VB_ROWS_PER_BLOCK;
+        v_cur[u] = ok ? __ldg(a.post_val + p) : 0.0f;
+        r_nxt[u] = VB_ROWS_PER_BLOCK; v_nxt[u] = 0.0f;
+    }
+    while (ti < nnz) {
+        const double w = s_w[s_nz[ti]];
+        uint32_t nti = ti, np0 = p0 + STEP, nhi = hi;
+        if (np0 >= hi) {
+            nti = ti + 1;
+            if (nti < nnz) { np0 = s_lo[s_nz[nti]]; nhi = s_hi[s_nz[nti]]; }
+        }
+        if (nti < nnz) {
 #pragma unroll
-            for (int u = 0; u < VB_SPARSE_UNROLL; ++u) {        // inside one term every row occurs once
-                if (r[u] == 0xffffffffu) continue;
-                const uint32_t lr = r[u] - row0;
-                const double prod = __dmul_rn(w, (double)v[u]);
-                const unsigned long long cur = acc[lr];
-                acc[lr] = (cur == VB_ACC_SENTINEL)
-                              ? (unsigned long long)__double_as_longlong(__dadd_rn(0.0, prod))
-                              : (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)cur), prod));
+            for (int u = 0; u < U; ++u) {
+                const uint32_t p = np0 + u * VB_SPARSE_THREADS + threadIdx.x;
+                const bool ok = p < nhi;
+                r_nxt[u] = ok ? __ldg(a.post_row + p) - row0 : VB_ROWS_PER_BLOCK;
+                v_nxt[u] = ok ? __ldg(a.post_val + p) : 0.0f;
             }
         }
-        __syncthreads();
+        // inside one term every row occurs once: plain read-modify-write, no atomics
+        double cur[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) cur[u] = acc[r_cur[u]];
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc[r_cur[u]] = __dadd_rn(cur[u], __dadd_rn(__dmul_rn(w, (double)v_cur[u]), 0.0));
+        if (nti != ti) __syncthreads();                         // term boundary: the next term may hit the same rows
+#pragma unroll
+        for (int u = 0; u < U; ++u) { r_cur[u] = r_nxt[u]; v_cur[u] = v_nxt[u]; }
+        ti = nti; p0 = np0; hi = nhi;
     }
 
     const uint32_t list = a.n_queries + q;                      // sparse lists follow the dense ones
@@ -161,12 +200,12 @@ vb_sparse_kernel(const VbSparseArgs a)
     }
     const uint32_t seg_row0 = a.blk_begin * VB_ROWS_PER_BLOCK;
     for (uint32_t r = threadIdx.x; r < VB_ROWS_PER_BLOCK; r += blockDim.x) {
-        const unsigned long long cur = acc[r];
+        const double cur = acc[r];
         const uint32_t row = row0 + r;
-        bool pass = cur != VB_ACC_SENTINEL && row < a.n_rows;
+        bool pass = (unsigned long long)__double_as_longlong(cur) != VB_ACC_SENTINEL && row < a.n_rows;
         if (pass && mask) pass = (mask[row >> 5] >> (row & 31u)) & 1u;
         float s = 0.0f;
-        if (pass) { s = __double2float_rn(__longlong_as_double((long long)cur)); pass = s > tau; }
+        if (pass) { s = __double2float_rn(cur); pass = s > tau; }
         if (a.direct) {
             if (row < a.n_rows) a.cand[(size_t)list * a.cap + (row - seg_row0)] = pass ? vb_pack_key(s, a.row_base + row) : 0ull;
         } else if (pass) {

@@ -77,8 +77,8 @@ struct Batch {
     const float* d_q = nullptr;
     const int64_t* d_qindptr = nullptr;
     const double* d_qweight = nullptr;
-    const uint64_t* d_qlo = nullptr;
-    const uint64_t* d_qhi = nullptr;
+    const uint32_t* d_qlo = nullptr;
+    const uint32_t* d_qhi = nullptr;
     const int32_t* d_maskof = nullptr;
     const int32_t* d_mode = nullptr;
     const VbFilterDev* d_filters = nullptr;
@@ -639,7 +639,7 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     // ---- sparse queries: sort by term id, resolve posting ranges, apply IDF ----
     std::vector<int64_t> indptr(b.B + 1, 0);
     std::vector<double> weight;
-    std::vector<uint64_t> qlo, qhi;
+    std::vector<uint32_t> qlo, qhi;
     if (sparse_enabled) {
         if (need_corpus) TRY(ensure_sparse_index(h));
         std::vector<std::pair<uint32_t, double>> tw;
@@ -665,8 +665,8 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
                     w = w * std::log(((double)h->n_live - df + 0.5) / (df + 0.5) + 1.0);
                 }
                 weight.push_back(w);
-                qlo.push_back(plo);
-                qhi.push_back(phi);
+                qlo.push_back((uint32_t)plo);
+                qhi.push_back((uint32_t)phi);
             }
             indptr[i + 1] = (int64_t)weight.size();
             if (hi > lo) { b.mode[i] = q->fusion; b.any_sparse = true; }
@@ -708,8 +708,8 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     const size_t o_q = ar.take((size_t)b.B * h->dim * 4);
     const size_t o_ip = ar.take((b.B + 1) * 8);
     const size_t o_w = ar.take((size_t)b.n_qterms * 8 + 8);
-    const size_t o_lo = ar.take((size_t)b.n_qterms * 8 + 8);
-    const size_t o_hi = ar.take((size_t)b.n_qterms * 8 + 8);
+    const size_t o_lo = ar.take((size_t)b.n_qterms * 4 + 8);
+    const size_t o_hi = ar.take((size_t)b.n_qterms * 4 + 8);
     const size_t o_mo = ar.take((size_t)b.B * 4);
     const size_t o_md = ar.take((size_t)b.B * 4);
     const size_t o_fl = ar.take((size_t)std::max<uint32_t>(1, b.n_filters) * sizeof(VbFilterDev));
@@ -724,8 +724,8 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     memcpy(hp + o_ip, indptr.data(), (b.B + 1) * 8);
     if (b.n_qterms) {
         memcpy(hp + o_w, weight.data(), (size_t)b.n_qterms * 8);
-        memcpy(hp + o_lo, qlo.data(), (size_t)b.n_qterms * 8);
-        memcpy(hp + o_hi, qhi.data(), (size_t)b.n_qterms * 8);
+        memcpy(hp + o_lo, qlo.data(), (size_t)b.n_qterms * 4);
+        memcpy(hp + o_hi, qhi.data(), (size_t)b.n_qterms * 4);
     }
     memcpy(hp + o_mo, mask_of.data(), (size_t)b.B * 4);
     memcpy(hp + o_md, b.mode.data(), (size_t)b.B * 4);
@@ -744,8 +744,8 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     b.d_q = reinterpret_cast<const float*>(dp + o_q);
     b.d_qindptr = reinterpret_cast<const int64_t*>(dp + o_ip);
     b.d_qweight = reinterpret_cast<const double*>(dp + o_w);
-    b.d_qlo = reinterpret_cast<const uint64_t*>(dp + o_lo);
-    b.d_qhi = reinterpret_cast<const uint64_t*>(dp + o_hi);
+    b.d_qlo = reinterpret_cast<const uint32_t*>(dp + o_lo);
+    b.d_qhi = reinterpret_cast<const uint32_t*>(dp + o_hi);
     b.d_maskof = reinterpret_cast<const int32_t*>(dp + o_mo);
     b.d_mode = reinterpret_cast<const int32_t*>(dp + o_md);
     b.d_filters = reinterpret_cast<const VbFilterDev*>(dp + o_fl);
@@ -866,8 +866,8 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
     if (do_sparse) {
         prof_begin(h, PH_SPARSE);
         const uint64_t total = (uint64_t)b.n_qterms * (b.n_blocks + 1);
-        TRY(dev_reserve(h, h->offs, total * 8, false));
-        vb_slice_kernel<<<grid_for(total, 256), 256, 0, h->stream>>>(h->post_row.as<uint32_t>(), b.d_qlo, b.d_qhi, b.n_qterms, b.n_blocks, h->offs.as<uint64_t>());
+        TRY(dev_reserve(h, h->offs, total * 4, false));
+        vb_slice_kernel<<<grid_for(total, 256), 256, 0, h->stream>>>(h->post_row.as<uint32_t>(), b.d_qlo, b.d_qhi, b.n_qterms, b.n_blocks, h->offs.as<uint32_t>());
         CKK("vb_slice_kernel");
         ++h->stats.last_launches;
         prof_end(h);
@@ -894,7 +894,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
         if (do_sparse) {
             prof_begin(h, PH_SPARSE);
             VbSparseArgs a{};
-            a.post_row = h->post_row.as<uint32_t>(); a.post_val = h->post_val.as<float>(); a.off = h->offs.as<uint64_t>();
+            a.post_row = h->post_row.as<uint32_t>(); a.post_val = h->post_val.as<float>(); a.off = h->offs.as<uint32_t>();
             a.q_indptr = b.d_qindptr; a.q_weight = b.d_qweight;
             a.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; a.mask_of = b.use_mask ? b.d_maskof : nullptr;
             a.tau = b.tau; a.cand = h->cand.as<uint64_t>(); a.cnt = b.cnt; a.mask_words = b.mask_words;
