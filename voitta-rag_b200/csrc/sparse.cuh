@@ -111,7 +111,7 @@ struct VbSparseArgs {
 __global__ void __launch_bounds__(VB_SPARSE_THREADS)
 vb_sparse_kernel(const VbSparseArgs a)
 {
-    __shared__ double acc[VB_ROWS_PER_BLOCK + 1];               // [VB_ROWS_PER_BLOCK] = dummy slot for padding lanes
+    __shared__ __align__(16) double acc[VB_ROWS_PER_BLOCK + 2]; // (+2: 16-byte aligned pairs for the scan)
     __shared__ uint32_t s_lo[256], s_hi[256];                   // VB_MAX_QUERY_TERMS slices of this block
     __shared__ double s_w[256];
     __shared__ uint16_t s_nz[256];                              // non-empty terms, ascending term id
@@ -142,53 +142,27 @@ vb_sparse_kernel(const VbSparseArgs a)
         if (threadIdx.x == 0) s_nnz = base;
     }
     const double neg_zero = __longlong_as_double((long long)VB_ACC_SENTINEL);
-    for (uint32_t r = threadIdx.x; r <= VB_ROWS_PER_BLOCK; r += blockDim.x) acc[r] = neg_zero;
+    for (uint32_t r = 2u * threadIdx.x; r < VB_ROWS_PER_BLOCK; r += 2u * blockDim.x)
+        *reinterpret_cast<double2*>(&acc[r]) = make_double2(neg_zero, neg_zero);
     __syncthreads();
     const uint32_t nnz = s_nnz;
     if (nnz == 0) return;                                       // (direct-mode slots were zeroed by the host)
 
     const uint32_t row0 = blk * VB_ROWS_PER_BLOCK;
-    // posting stream: for each non-empty term, steps of U*blockDim.x postings (U per thread, all
-    // independent); the loads of step i+1 are in flight while step i is accumulated.
-    constexpr int U = VB_SPARSE_UNROLL;
-    constexpr uint32_t STEP = VB_SPARSE_THREADS * U;
-    uint32_t ti = 0, p0 = s_lo[s_nz[0]], hi = s_hi[s_nz[0]];
-    uint32_t r_cur[U], r_nxt[U];
-    float v_cur[U], v_nxt[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const uint32_t p = p0 + u * VB_SPARSE_THREADS + threadIdx.x;
-        const bool ok = p < hi;
-        r_cur[u] = ok ? __ldg(a.post_row + p) - row0 : VB_ROWS_PER_BLOCK;
-        v_cur[u] = ok ? __ldg(a.post_val + p) : 0.0f;
-        r_nxt[u] = VB_ROWS_PER_BLOCK; v_nxt[u] = 0.0f;
-    }
-    while (ti < nnz) {
-        const double w = s_w[s_nz[ti]];
-        uint32_t nti = ti, np0 = p0 + STEP, nhi = hi;
-        if (np0 >= hi) {
-            nti = ti + 1;
-            if (nti < nnz) { np0 = s_lo[s_nz[nti]]; nhi = s_hi[s_nz[nti]]; }
+    // Non-empty terms in ascending term id; inside one term every row occurs once, so the
+    // read-modify-write needs no atomics.  The kernel is issue-bound: the loop is kept minimal and
+    // the (many) resident CTAs hide the load latency at each term start.
+    for (uint32_t ti = 0; ti < nnz; ++ti) {
+        const uint32_t term = s_nz[ti];
+        const double w = s_w[term];
+        const uint32_t lo = s_lo[term], hi = s_hi[term];
+#pragma unroll 2
+        for (uint32_t p = lo + threadIdx.x; p < hi; p += VB_SPARSE_THREADS) {
+            const uint32_t r = __ldg(a.post_row + p) - row0;
+            const float v = __ldg(a.post_val + p);
+            acc[r] = __dadd_rn(acc[r], __dadd_rn(__dmul_rn(w, (double)v), 0.0));
         }
-        if (nti < nnz) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t p = np0 + u * VB_SPARSE_THREADS + threadIdx.x;
-                const bool ok = p < nhi;
-                r_nxt[u] = ok ? __ldg(a.post_row + p) - row0 : VB_ROWS_PER_BLOCK;
-                v_nxt[u] = ok ? __ldg(a.post_val + p) : 0.0f;
-            }
-        }
-        // inside one term every row occurs once: plain read-modify-write, no atomics
-        double cur[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) cur[u] = acc[r_cur[u]];
-#pragma unroll
-        for (int u = 0; u < U; ++u) acc[r_cur[u]] = __dadd_rn(cur[u], __dadd_rn(__dmul_rn(w, (double)v_cur[u]), 0.0));
-        if (nti != ti) __syncthreads();                         // term boundary: the next term may hit the same rows
-#pragma unroll
-        for (int u = 0; u < U; ++u) { r_cur[u] = r_nxt[u]; v_cur[u] = v_nxt[u]; }
-        ti = nti; p0 = np0; hi = nhi;
+        __syncthreads();                                        // the next term may hit the same rows
     }
 
     const uint32_t list = a.n_queries + q;                      // sparse lists follow the dense ones
@@ -199,17 +173,27 @@ vb_sparse_kernel(const VbSparseArgs a)
         if (f >= 0) mask = a.mask + (size_t)f * a.mask_words;
     }
     const uint32_t seg_row0 = a.blk_begin * VB_ROWS_PER_BLOCK;
-    for (uint32_t r = threadIdx.x; r < VB_ROWS_PER_BLOCK; r += blockDim.x) {
-        const double cur = acc[r];
-        const uint32_t row = row0 + r;
-        bool pass = (unsigned long long)__double_as_longlong(cur) != VB_ACC_SENTINEL && row < a.n_rows;
-        if (pass && mask) pass = (mask[row >> 5] >> (row & 31u)) & 1u;
-        float s = 0.0f;
-        if (pass) { s = __double2float_rn(cur); pass = s > tau; }
-        if (a.direct) {
-            if (row < a.n_rows) a.cand[(size_t)list * a.cap + (row - seg_row0)] = pass ? vb_pack_key(s, a.row_base + row) : 0ull;
-        } else if (pass) {
-            vb_push(a.cand, a.cnt, a.cap, list, s, a.row_base + row);
+    // Scan two accumulators per thread per step.  Cheap exact prefilter in fp64: rounding to fp32 is
+    // monotone, so cur < (double)tau implies float(cur) <= tau — such rows (the vast majority once
+    // tau is established, and every untouched -0.0 row when tau >= 0) are dropped with one compare.
+    const double tau_d = (double)tau;
+    for (uint32_t r = 2u * threadIdx.x; r < VB_ROWS_PER_BLOCK; r += 2u * blockDim.x) {
+        const double2 c2 = *reinterpret_cast<const double2*>(&acc[r]);
+        const double cv[2] = {c2.x, c2.y};
+        if (!a.direct && c2.x < tau_d && c2.y < tau_d) continue;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const double cur = cv[e];
+            const uint32_t row = row0 + r + e;
+            bool pass = (unsigned long long)__double_as_longlong(cur) != VB_ACC_SENTINEL && row < a.n_rows;
+            if (pass && mask) pass = (mask[row >> 5] >> (row & 31u)) & 1u;
+            float s = 0.0f;
+            if (pass) { s = __double2float_rn(cur); pass = s > tau; }
+            if (a.direct) {
+                if (row < a.n_rows) a.cand[(size_t)list * a.cap + (row - seg_row0)] = pass ? vb_pack_key(s, a.row_base + row) : 0ull;
+            } else if (pass) {
+                vb_push(a.cand, a.cnt, a.cap, list, s, a.row_base + row);
+            }
         }
     }
 }

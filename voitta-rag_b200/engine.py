@@ -324,6 +324,23 @@ class Index:
         """u64 words of one shard's candidate block (VB_CAND_BLOCK_WORDS)."""
         return 2 * n_queries * kprime + 1
 
+    def pack(self, queries, sparse=None, filters=None, filter_of=None, limit: int = 10, kprime: int | None = None,
+             fusion: str | int = "weighted", sparse_weight: float = 0.1, apply_idf: bool = True, branches: bool = False):
+        """Build the host buffers of a vb_query_batch once (numpy arrays + the C struct); pass the
+        result to ``search_packed`` any number of times."""
+        fz = FUSION[fusion] if isinstance(fusion, str) else int(fusion)
+        if kprime is None:
+            kprime = limit * 3 if (sparse is not None and fz != FUSE_DENSE_ONLY) else limit
+        p = _Packed(self.dim, queries, sparse, filters, filter_of, limit, kprime, fz, sparse_weight, apply_idf)
+        p.result = self._alloc_result(p.B, limit, kprime, branches)
+        return p
+
+    def search_packed(self, packed) -> SearchResult:
+        """vb_search on prepared host buffers: staging, H2D, kernels, D2H and decode, nothing else."""
+        res, cres = packed.result
+        self._check(self._lib.vb_search(self._h, C.byref(packed.c), C.byref(cres)))
+        return res
+
     def search_local(self, cand_dev_ptr: int, queries, sparse=None, filters=None, filter_of=None, limit: int = 10,
                      kprime: int | None = None, fusion: str | int = "weighted", sparse_weight: float = 0.1):
         """Shard-local branch top-k' left on the device (all-gather payload); weights carry global IDF."""
