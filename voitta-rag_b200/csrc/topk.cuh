@@ -37,7 +37,7 @@ __device__ __forceinline__ void vb_bitonic_desc(uint64_t* s, uint32_t P) {
 // cnt[list] = that count, tau[list] = score of the k-th (or -inf if fewer than k).
 __global__ void __launch_bounds__(VB_COMPACT_THREADS)
 vb_compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* __restrict__ tau,
-                  uint32_t* __restrict__ overflow, uint32_t cap, uint32_t k)
+                  uint32_t* __restrict__ overflow, uint32_t cap, uint32_t k, uint32_t list_begin)
 {
     __shared__ uint64_t s_keys[VB_SORT_MAX];
     __shared__ uint32_t s_hist[256];
@@ -45,7 +45,7 @@ vb_compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float
     __shared__ uint64_t s_prefix;
     __shared__ uint32_t s_need;
 
-    const uint32_t list = blockIdx.x;
+    const uint32_t list = list_begin + blockIdx.x;
     uint64_t* keys = cand + (size_t)list * cap;
     const uint32_t raw = cnt[list];
     if (raw > cap && threadIdx.x == 0) overflow[list] = 1u;

@@ -99,8 +99,8 @@ struct vb_index {
     uint64_t row_base = 0;
     uint64_t n_rows = 0, n_live = 0, cap_rows = 0;
     uint64_t nnz = 0, cap_nnz = 0;
-    cudaStream_t stream = nullptr, own_stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr, aux_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
     std::mutex mu;
     int sm_count = 148;
     uint64_t device_bytes = 0;
@@ -124,7 +124,7 @@ struct vb_index {
     uint32_t cand_cap = 0;
 
     // options
-    int64_t opt_dense_path = 0, opt_seg_first = 2048, opt_seg_ratio = 32, opt_safe_mode = 0, opt_profile = 0, opt_k2_precision = 0;
+    int64_t opt_dense_path = 0, opt_seg_first = 2048, opt_seg_ratio = 32, opt_safe_mode = 0, opt_profile = 0, opt_k2_precision = 0, opt_overlap = 1;
 
     vb_stats stats{};
     Batch staged;
@@ -229,6 +229,9 @@ extern "C" int vb_create(int32_t dim, int32_t device, uint64_t capacity_hint, ui
     h->row_base = row_base;
     h->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
         delete h;
         return vb_fail("vb_create: stream/event creation failed");
@@ -253,6 +256,9 @@ extern "C" void vb_destroy(vb_index* h) {
     for (auto ev : h->prof_events) cudaEventDestroy(ev);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
+    cudaEventDestroy(h->ev_fork);
+    cudaEventDestroy(h->ev_join);
+    cudaStreamDestroy(h->aux_stream);
     cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -266,6 +272,7 @@ extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
     else if (k == "seg_ratio") h->opt_seg_ratio = std::max<int64_t>(2, value);
     else if (k == "safe_mode") h->opt_safe_mode = value;
     else if (k == "profile") h->opt_profile = value;
+    else if (k == "overlap") h->opt_overlap = value;               // 1: dense and sparse chains on two streams
     else if (k == "k2_precision") h->opt_k2_precision = value;   // 0 auto, 1 bf16 query, 2 bf16x2 (hi+lo) query
     else if (k == "stream") {   // run on the caller's stream (e.g. torch's current stream); 0 = own stream
         h->stream = value ? reinterpret_cast<cudaStream_t>(static_cast<uintptr_t>(value)) : h->own_stream;
@@ -577,8 +584,8 @@ struct Arena {
 
 enum { PH_MASK = 0, PH_DENSE = 1, PH_SPARSE = 2, PH_SELECT = 3, PH_FUSE = 4, PH_N = 5 };
 
-static void prof_begin(vb_index* h, int phase) {
-    if (!h->opt_profile) return;
+static int prof_begin(vb_index* h, int phase, cudaStream_t st = nullptr) {
+    if (!h->opt_profile) return -1;
     const size_t i = h->prof_phase.size();
     while (h->prof_events.size() < 2 * (i + 1)) {
         cudaEvent_t e;
@@ -586,11 +593,14 @@ static void prof_begin(vb_index* h, int phase) {
         h->prof_events.push_back(e);
     }
     h->prof_phase.push_back(phase);
-    cudaEventRecord(h->prof_events[2 * i], h->stream);
+    cudaEventRecord(h->prof_events[2 * i], st ? st : h->stream);
+    return (int)i;
 }
-static void prof_end(vb_index* h) {
+static void prof_end(vb_index* h, int idx = -2, cudaStream_t st = nullptr) {
     if (!h->opt_profile) return;
-    cudaEventRecord(h->prof_events[2 * h->prof_phase.size() - 1], h->stream);
+    if (idx == -2) idx = (int)h->prof_phase.size() - 1;
+    if (idx < 0) return;
+    cudaEventRecord(h->prof_events[2 * (size_t)idx + 1], st ? st : h->stream);
 }
 // call after the stream has been synchronised
 static void prof_collect(vb_index* h) {
@@ -786,7 +796,7 @@ static int init_lists(vb_index* h, const Batch& b, uint32_t direct_rows) {
     return 0;
 }
 
-static int launch_scan(vb_index* h, const Batch& b, uint32_t row_begin, uint32_t row_end, uint32_t direct) {
+static int launch_scan(vb_index* h, const Batch& b, uint32_t row_begin, uint32_t row_end, uint32_t direct, cudaStream_t st) {
     VbScanArgs a{};
     a.rows = h->rows.as<uint4>();
     a.inv_norm = h->inv_norm.as<float>();
@@ -809,11 +819,11 @@ static int launch_scan(vb_index* h, const Batch& b, uint32_t row_begin, uint32_t
     dim3 grid(std::min<uint32_t>((groups + 7) / 8, per_q), b.B);
     const int nch = (int)((a.chunks + 31) / 32);
     switch (nch) {
-        case 1: vb_dense_scan_kernel<1><<<grid, 256, 0, h->stream>>>(a); break;
-        case 2: vb_dense_scan_kernel<2><<<grid, 256, 0, h->stream>>>(a); break;
-        case 3: vb_dense_scan_kernel<3><<<grid, 256, 0, h->stream>>>(a); break;
-        case 4: vb_dense_scan_kernel<4><<<grid, 256, 0, h->stream>>>(a); break;
-        default: vb_dense_scan_generic_kernel<<<grid, 256, 0, h->stream>>>(a); break;
+        case 1: vb_dense_scan_kernel<1><<<grid, 256, 0, st>>>(a); break;
+        case 2: vb_dense_scan_kernel<2><<<grid, 256, 0, st>>>(a); break;
+        case 3: vb_dense_scan_kernel<3><<<grid, 256, 0, st>>>(a); break;
+        case 4: vb_dense_scan_kernel<4><<<grid, 256, 0, st>>>(a); break;
+        default: vb_dense_scan_generic_kernel<<<grid, 256, 0, st>>>(a); break;
     }
     CKK("vb_dense_scan_kernel");
     ++h->stats.last_launches;
@@ -861,38 +871,44 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
         ++h->stats.last_launches;
         prof_end(h);
     }
-    // sparse slice table
+    // The dense chain (K1/K2 + select of the dense lists) and the sparse chain (slice table, K3 +
+    // select of the sparse lists) are independent until the fusion, so they run on two streams:
+    // the small kernels of one chain (selects, first segments, slice table) hide behind the big
+    // kernels of the other.
     const bool do_sparse = b.any_sparse && h->nnz_live > 0 && b.n_qterms > 0;
-    if (do_sparse) {
-        prof_begin(h, PH_SPARSE);
-        const uint64_t total = (uint64_t)b.n_qterms * (b.n_blocks + 1);
-        TRY(dev_reserve(h, h->offs, total * 4, false));
-        vb_slice_kernel<<<grid_for(total, 256), 256, 0, h->stream>>>(h->post_row.as<uint32_t>(), b.d_qlo, b.d_qhi, b.n_qterms, b.n_blocks, h->offs.as<uint32_t>());
-        CKK("vb_slice_kernel");
-        ++h->stats.last_launches;
-        prof_end(h);
+    const bool two_streams = do_sparse && h->opt_overlap;
+    cudaStream_t sd = h->stream, ss = two_streams ? h->aux_stream : h->stream;
+    if (two_streams) {
+        CK(cudaEventRecord(h->ev_fork, sd));
+        CK(cudaStreamWaitEvent(ss, h->ev_fork, 0));
     }
-    for (size_t s = 0; s + 1 < bounds.size(); ++s) {
-        const uint32_t r0 = bounds[s], r1 = bounds[s + 1];
-        const uint32_t direct = (s == 0 && direct_rows) ? 1u : 0u;
-        prof_begin(h, PH_DENSE);
+    auto dense_segment = [&](uint32_t r0, uint32_t r1, uint32_t direct) -> int {
+        const int pi = prof_begin(h, PH_DENSE, sd);
         if (path == 2) {
             VbGemmLaunch g{};
             g.rows = h->rows.p; g.inv_norm = h->inv_norm.as<float>(); g.q_bf16 = h->q_bf16.p;
             g.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; g.mask_of = b.use_mask ? b.d_maskof : nullptr;
             g.mask_words = b.mask_words; g.n_filters = b.n_filters; g.tau = b.tau; g.cand = h->cand.as<uint64_t>(); g.cnt = b.cnt;
             g.cap = h->cand_cap; g.n_rows_total = n; g.row_begin = r0; g.row_end = r1; g.row_base = (uint32_t)h->row_base;
-            g.d_pad = (uint32_t)h->d_pad; g.n_queries = b.B; g.sm_count = h->sm_count; g.stream = h->stream;
+            g.d_pad = (uint32_t)h->d_pad; g.n_queries = b.B; g.sm_count = h->sm_count; g.stream = sd;
             g.direct = direct; g.plan = plan; g.mask_of_host = b.mask_of_host.data();
             int launches = 0;
             if (vb_gemm_launch(g, &launches) != 0) return vb_fail("tensor-core dense kernel: %s", vb_gemm_last_error());
             h->stats.last_launches += (uint32_t)launches;
         } else {
-            TRY(launch_scan(h, b, r0, r1, direct));
+            TRY(launch_scan(h, b, r0, r1, direct, sd));
         }
-        prof_end(h);
+        prof_end(h, pi, sd);
+        const int ps = prof_begin(h, PH_SELECT, sd);
+        vb_compact_kernel<<<b.B, VB_COMPACT_THREADS, 0, sd>>>(h->cand.as<uint64_t>(), b.cnt, b.tau, b.overflow, h->cand_cap, b.k, 0u);
+        CKK("vb_compact_kernel");
+        ++h->stats.last_launches;
+        prof_end(h, ps, sd);
+        return 0;
+    };
+    auto sparse_segment = [&](uint32_t r0, uint32_t r1, uint32_t direct) -> int {
         if (do_sparse) {
-            prof_begin(h, PH_SPARSE);
+            const int pi = prof_begin(h, PH_SPARSE, ss);
             VbSparseArgs a{};
             a.post_row = h->post_row.as<uint32_t>(); a.post_val = h->post_val.as<float>(); a.off = h->offs.as<uint32_t>();
             a.q_indptr = b.d_qindptr; a.q_weight = b.d_qweight;
@@ -901,16 +917,38 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
             a.n_blocks = b.n_blocks; a.blk_begin = r0 / VB_ROWS_PER_BLOCK; a.n_queries = b.B; a.n_rows = n;
             a.row_base = (uint32_t)h->row_base; a.cap = h->cand_cap; a.direct = direct;
             const uint32_t nblk = (r1 - r0 + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK;
-            vb_sparse_kernel<<<nblk * b.B, VB_SPARSE_THREADS, 0, h->stream>>>(a);
+            vb_sparse_kernel<<<nblk * b.B, VB_SPARSE_THREADS, 0, ss>>>(a);
             CKK("vb_sparse_kernel");
             ++h->stats.last_launches;
-            prof_end(h);
+            prof_end(h, pi, ss);
         }
-        prof_begin(h, PH_SELECT);
-        vb_compact_kernel<<<b.n_lists, VB_COMPACT_THREADS, 0, h->stream>>>(h->cand.as<uint64_t>(), b.cnt, b.tau, b.overflow, h->cand_cap, b.k);
+        // the sparse lists are compacted even without postings (first-segment slots -> empty lists)
+        const int ps = prof_begin(h, PH_SELECT, ss);
+        vb_compact_kernel<<<b.B, VB_COMPACT_THREADS, 0, ss>>>(h->cand.as<uint64_t>(), b.cnt, b.tau, b.overflow, h->cand_cap, b.k, b.B);
         CKK("vb_compact_kernel");
         ++h->stats.last_launches;
-        prof_end(h);
+        prof_end(h, ps, ss);
+        return 0;
+    };
+    if (do_sparse) {                                            // sparse slice table (sparse chain)
+        const int pi = prof_begin(h, PH_SPARSE, ss);
+        const uint64_t total = (uint64_t)b.n_qterms * (b.n_blocks + 1);
+        TRY(dev_reserve(h, h->offs, total * 4, false));
+        vb_slice_kernel<<<grid_for(total, 256), 256, 0, ss>>>(h->post_row.as<uint32_t>(), b.d_qlo, b.d_qhi, b.n_qterms, b.n_blocks, h->offs.as<uint32_t>());
+        CKK("vb_slice_kernel");
+        ++h->stats.last_launches;
+        prof_end(h, pi, ss);
+    }
+    // enqueue the two chains interleaved so that neither stream starves on the host side
+    const size_t n_seg = bounds.size() - 1;
+    for (size_t s = 0; s < n_seg; ++s) {
+        const uint32_t direct = (s == 0 && direct_rows) ? 1u : 0u;
+        TRY(dense_segment(bounds[s], bounds[s + 1], direct));
+        if (do_sparse || s == 0) TRY(sparse_segment(bounds[s], bounds[s + 1], direct));
+    }
+    if (two_streams) {
+        CK(cudaEventRecord(h->ev_join, ss));
+        CK(cudaStreamWaitEvent(sd, h->ev_join, 0));
     }
     return 0;
 }
@@ -1053,7 +1091,7 @@ extern "C" int vb_run_fuse(vb_index* h, uint32_t n_shards, const uint64_t* gathe
         prof_begin(h, PH_SELECT);
         vb_import_kernel<<<b.n_lists, 256, 0, h->stream>>>(gathered_dev, n_shards, b.n_lists, b.k, h->cand_cap, h->cand.as<uint64_t>(), b.cnt, b.overflow);
         CKK("vb_import_kernel");
-        vb_compact_kernel<<<b.n_lists, VB_COMPACT_THREADS, 0, h->stream>>>(h->cand.as<uint64_t>(), b.cnt, b.tau, b.overflow, h->cand_cap, b.k);
+        vb_compact_kernel<<<b.n_lists, VB_COMPACT_THREADS, 0, h->stream>>>(h->cand.as<uint64_t>(), b.cnt, b.tau, b.overflow, h->cand_cap, b.k, 0u);
         CKK("vb_compact_kernel");
         h->stats.last_launches += 2;
         prof_end(h);
