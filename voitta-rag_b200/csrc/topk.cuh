@@ -14,7 +14,7 @@
 #include "common.cuh"
 
 #define VB_SORT_MAX 2048u
-#define VB_COMPACT_THREADS 512
+#define VB_COMPACT_THREADS 256
 
 // descending bitonic sort of P (power of two <= VB_SORT_MAX) keys in shared memory
 __device__ __forceinline__ void vb_bitonic_desc(uint64_t* s, uint32_t P) {
@@ -35,77 +35,170 @@ __device__ __forceinline__ void vb_bitonic_desc(uint64_t* s, uint32_t P) {
 
 // One CTA per list.  Afterwards: cand[list][0..cnt) = top-min(k, #valid) keys sorted descending,
 // cnt[list] = that count, tau[list] = score of the k-th (or -inf if fewer than k).
+//
+// Selection, not sorting: a list holds a few thousand unsorted keys of which only k' (tens)
+// survive, and this kernel sits on the critical path between two scoring segments.
+//   1. the list is read once into registers (<= 16 keys per thread; longer lists are re-read
+//      from global memory in every pass);
+//   2. block min/max of the active keys give their common bit prefix; ONE 2048-bin histogram
+//      over the 11 bits below the highest differing bit and a block suffix scan find the pivot
+//      bin (the bin holding the k'-th largest key);
+//   3. every key >= the pivot bin's lower bound is gathered (k' + a few) and only those are
+//      sorted.  If that would exceed VB_SORT_MAX keys, step 2 repeats inside the pivot bin.
+#define VB_REG_KEYS 16u
+#define VB_BINS 2048u
+
+template <bool IS_MAX>
+__device__ __forceinline__ uint64_t vb_block_reduce_u64(uint64_t v, uint64_t* s_red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint64_t t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = IS_MAX ? (t > v ? t : v) : (t < v ? t : v);
+    }
+    __syncthreads();                                   // s_red may still be read from a previous call
+    if ((threadIdx.x & 31u) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint64_t r = s_red[0];
+#pragma unroll
+    for (uint32_t w = 1; w < VB_COMPACT_THREADS / 32; ++w) {
+        const uint64_t t = s_red[w];
+        r = IS_MAX ? (t > r ? t : r) : (t < r ? t : r);
+    }
+    return r;
+}
+
+template <bool IN_REGS>
+__device__ __forceinline__ void vb_compact_body(uint64_t* __restrict__ gkeys, uint32_t E, uint32_t k,
+                                                uint32_t* __restrict__ cnt_out, float* __restrict__ tau_out,
+                                                uint64_t* s_sel, uint32_t* s_hist, uint64_t* s_red,
+                                                uint32_t* s_scan, uint32_t* s_misc)
+{
+    uint64_t r[VB_REG_KEYS];
+    if (IN_REGS) {
+#pragma unroll
+        for (uint32_t j = 0; j < VB_REG_KEYS; ++j) {
+            const uint32_t i = threadIdx.x + j * VB_COMPACT_THREADS;
+            r[j] = i < E ? gkeys[i] : 0ull;
+        }
+    }
+    // visit every key of the list (registers, or global memory for long lists)
+    auto for_each = [&](auto&& f) {
+        if (IN_REGS) {
+#pragma unroll
+            for (uint32_t j = 0; j < VB_REG_KEYS; ++j) f(r[j]);
+        } else {
+            for (uint32_t i = threadIdx.x; i < E; i += VB_COMPACT_THREADS) f(gkeys[i]);
+        }
+    };
+
+    uint32_t need = k;                                 // rank of the k-th largest among the active keys
+    uint64_t pmask = 0ull, pval = 0ull;                // active: key != 0 && (key & pmask) == pval
+    uint64_t bound = 1ull;                             // gather every key >= bound
+    for (;;) {
+        uint64_t kmax = 0ull, kmin = ~0ull;
+        uint32_t n_act = 0;
+        for_each([&](uint64_t key) {
+            if (key != 0ull && (key & pmask) == pval) { ++n_act; kmax = key > kmax ? key : kmax; kmin = key < kmin ? key : kmin; }
+        });
+        kmax = vb_block_reduce_u64<true>(kmax, s_red);
+        kmin = vb_block_reduce_u64<false>(kmin, s_red);
+        __syncthreads();
+        if (threadIdx.x == 0) s_misc[0] = 0u;
+        __syncthreads();
+        if (n_act) atomicAdd(&s_misc[0], n_act);
+        __syncthreads();
+        const uint32_t total_act = s_misc[0];
+        if (total_act <= need || kmax == kmin) {       // everything active is kept
+            bound = total_act ? kmin : 1ull;
+            if (pmask != 0ull && total_act == 0) bound = pval ? pval : 1ull;
+            break;
+        }
+        const int top = 63 - __clzll((long long)(kmax ^ kmin));   // highest differing bit
+        const int shift = top >= 10 ? top - 10 : 0;                // digit = bits [shift, shift+11)
+        for (uint32_t i = threadIdx.x; i < VB_BINS; i += VB_COMPACT_THREADS) s_hist[i] = 0u;
+        __syncthreads();
+        for_each([&](uint64_t key) {
+            if (key != 0ull && (key & pmask) == pval) atomicAdd(&s_hist[(uint32_t)(key >> shift) & (VB_BINS - 1u)], 1u);
+        });
+        __syncthreads();
+        // suffix scan over the bins: thread t owns bins [hi_bin - PER + 1, hi_bin], thread 0 the top ones
+        constexpr uint32_t PER = VB_BINS / VB_COMPACT_THREADS;
+        const uint32_t hi_bin = VB_BINS - 1u - threadIdx.x * PER;
+        uint32_t mine = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < PER; ++j) mine += s_hist[hi_bin - j];
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31u) >= (uint32_t)o) incl += t;
+        }
+        if ((threadIdx.x & 31u) == 31u) s_scan[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint32_t before = 0;
+        for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) before += s_scan[w];
+        const uint32_t above_me = before + incl - mine;           // active keys in bins above mine
+        if (above_me < need && above_me + mine >= need) {         // the pivot bin is one of mine
+            uint32_t above = above_me;
+#pragma unroll
+            for (uint32_t j = 0; j < PER; ++j) {
+                const uint32_t c = s_hist[hi_bin - j];
+                if (above < need && above + c >= need) { s_misc[1] = hi_bin - j; s_misc[2] = above; }
+                above += c;
+            }
+        }
+        __syncthreads();
+        const uint32_t pivot = s_misc[1], above = s_misc[2], in_pivot = s_hist[pivot];
+        const uint64_t low_mask = (1ull << shift) - 1ull;         // bits below the digit
+        const uint64_t high_bits = (shift + 11 >= 64) ? 0ull : (kmax >> (shift + 11)) << (shift + 11);
+        const uint64_t pivot_lo = high_bits | ((uint64_t)pivot << shift);     // smallest key value of the pivot bin
+        if ((k - need) + above + in_pivot <= VB_SORT_MAX || shift == 0) { bound = pivot_lo; break; }
+        need -= above;                                            // crowded pivot bin: refine inside it
+        pmask = ~low_mask;
+        pval = pivot_lo;
+        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_misc[0] = 0u;
+    __syncthreads();
+    for_each([&](uint64_t key) {
+        if (key != 0ull && key >= bound) {
+            const uint32_t slot = atomicAdd(&s_misc[0], 1u);
+            if (slot < VB_SORT_MAX) s_sel[slot] = key;
+        }
+    });
+    __syncthreads();
+    const uint32_t nsel = s_misc[0] < VB_SORT_MAX ? s_misc[0] : VB_SORT_MAX;
+    uint32_t P = 2;
+    while (P < nsel) P <<= 1;
+    for (uint32_t i = nsel + threadIdx.x; i < P; i += VB_COMPACT_THREADS) s_sel[i] = 0ull;
+    vb_bitonic_desc(s_sel, P);
+    const uint32_t keep = nsel < k ? nsel : k;
+    for (uint32_t i = threadIdx.x; i < keep; i += VB_COMPACT_THREADS) gkeys[i] = s_sel[i];
+    if (threadIdx.x == 0) {
+        *cnt_out = keep;
+        *tau_out = (keep >= k) ? vb_key_score(s_sel[k - 1]) : -INFINITY;
+    }
+}
+
 __global__ void __launch_bounds__(VB_COMPACT_THREADS)
 vb_compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* __restrict__ tau,
                   uint32_t* __restrict__ overflow, uint32_t cap, uint32_t k, uint32_t list_begin)
 {
-    __shared__ uint64_t s_keys[VB_SORT_MAX];
-    __shared__ uint32_t s_hist[256];
-    __shared__ uint32_t s_nsel;
-    __shared__ uint64_t s_prefix;
-    __shared__ uint32_t s_need;
-
+    __shared__ uint64_t s_sel[VB_SORT_MAX];
+    __shared__ uint32_t s_hist[VB_BINS];
+    __shared__ uint64_t s_red[VB_COMPACT_THREADS / 32];
+    __shared__ uint32_t s_scan[VB_COMPACT_THREADS / 32];
+    __shared__ uint32_t s_misc[4];
     const uint32_t list = list_begin + blockIdx.x;
-    uint64_t* keys = cand + (size_t)list * cap;
+    uint64_t* gkeys = cand + (size_t)list * cap;
     const uint32_t raw = cnt[list];
     if (raw > cap && threadIdx.x == 0) overflow[list] = 1u;
     const uint32_t E = raw < cap ? raw : cap;
-
-    uint32_t nsel;
-    if (E <= VB_SORT_MAX) {
-        for (uint32_t i = threadIdx.x; i < E; i += blockDim.x) s_keys[i] = keys[i];
-        nsel = E;
-    } else {
-        // MSB-first radix select of the k-th largest key (8 bits per pass over 64-bit keys)
-        if (threadIdx.x == 0) { s_prefix = 0ull; s_need = k; s_nsel = 0u; }
-        uint64_t pmask = 0ull;
-        for (int shift = 56; shift >= 0; shift -= 8) {
-            if (threadIdx.x < 256) s_hist[threadIdx.x] = 0u;
-            __syncthreads();
-            const uint64_t prefix = s_prefix;
-            for (uint32_t i = threadIdx.x; i < E; i += blockDim.x) {
-                const uint64_t key = keys[i];
-                if ((key & pmask) == prefix) atomicAdd(&s_hist[(uint32_t)(key >> shift) & 255u], 1u);
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                uint32_t need = s_need, above = 0u;
-                int d = 255;
-                for (; d > 0; --d) {
-                    if (above + s_hist[d] >= need) break;
-                    above += s_hist[d];
-                }
-                s_need = need - above;           // rank inside bucket d
-                s_prefix = prefix | ((uint64_t)d << shift);
-            }
-            pmask |= 0xffull << shift;
-            __syncthreads();
-        }
-        const uint64_t pivot = s_prefix;         // the k-th largest key (0 if fewer than k valid)
-        for (uint32_t i = threadIdx.x; i < E; i += blockDim.x) {
-            const uint64_t key = keys[i];
-            if (key != 0ull && key >= pivot) {
-                const uint32_t slot = atomicAdd(&s_nsel, 1u);
-                if (slot < VB_SORT_MAX) s_keys[slot] = key;
-            }
-        }
-        __syncthreads();
-        nsel = s_nsel < VB_SORT_MAX ? s_nsel : VB_SORT_MAX;
-    }
-    uint32_t P = 1;
-    while (P < nsel) P <<= 1;
-    if (P < 2) P = 2;
-    for (uint32_t i = nsel + threadIdx.x; i < P; i += blockDim.x) s_keys[i] = 0ull;
-    vb_bitonic_desc(s_keys, P);
-
-    const uint32_t keep = nsel < k ? nsel : k;
-    for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x) keys[i] = s_keys[i];
-    if (threadIdx.x == 0) {
-        uint32_t valid = keep;                   // zero keys (padding) sort last
-        while (valid > 0 && s_keys[valid - 1] == 0ull) --valid;
-        cnt[list] = valid;
-        tau[list] = (valid >= k) ? vb_key_score(s_keys[k - 1]) : -INFINITY;
-    }
+    if (E <= VB_REG_KEYS * VB_COMPACT_THREADS)
+        vb_compact_body<true>(gkeys, E, k, cnt + list, tau + list, s_sel, s_hist, s_red, s_scan, s_misc);
+    else
+        vb_compact_body<false>(gkeys, E, k, cnt + list, tau + list, s_sel, s_hist, s_red, s_scan, s_misc);
 }
 
 // Pack the first k keys of every list into out[list][k] (0-padded): the all-gather payload.

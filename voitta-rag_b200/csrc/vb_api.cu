@@ -240,6 +240,9 @@ extern "C" int vb_create(int32_t dim, int32_t device, uint64_t capacity_hint, ui
     if (vb_gemm_configure() != 0) { delete h; return vb_fail("vb_create: tensor-core kernel configuration failed: %s", vb_gemm_last_error()); }
     (void)capacity_hint;
     if (const char* env = getenv("VB200_DENSE_PATH")) h->opt_dense_path = atoi(env);   // 0 auto, 1 K1, 2 K2
+    if (const char* env = getenv("VB200_SEG_FIRST")) h->opt_seg_first = std::max<int64_t>(VB_ROWS_PER_BLOCK, (int64_t)align_up((size_t)atoll(env), VB_ROWS_PER_BLOCK));
+    if (const char* env = getenv("VB200_SEG_RATIO")) h->opt_seg_ratio = std::max<int64_t>(2, atoll(env));
+    if (const char* env = getenv("VB200_OVERLAP")) h->opt_overlap = atoi(env);
     *out = h;
     return 0;
 }
