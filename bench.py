@@ -247,7 +247,6 @@ def main():
     ix, keep, (lo, hi) = build_shard(cfg, rank, world, device, torch, synth, engine)
     if args.dense_path:
         ix.set_option("dense_path", args.dense_path)
-    ix.set_option("profile", 1)
     sh = ShardedIndex(ix, rank, world, device=device)
     obj = [None]
     if rank == 0:
@@ -303,14 +302,11 @@ def main():
     barrier()
     t_begin = time.perf_counter()
     ms = np.zeros(args.steps)
-    phase = np.zeros(5)
     launches = 0
     for i in range(args.steps):
         st = stage(args.warmup + i)                 # host staging + H2D: outside the timed events
         ms[i], _ = device_step(st)
-        s = ix.stats()
-        phase += [s["last_mask_ms"], s["last_dense_ms"], s["last_sparse_ms"], s["last_select_ms"], s["last_fuse_ms"]]
-        launches += s["last_launches"]
+        launches += ix.stats()["last_launches"]
     barrier()
     t_end = time.perf_counter()
     if world > 1:
@@ -324,15 +320,17 @@ def main():
 
     # ---- end to end through the C ABI with host buffers -------------------------------------------
     # host buffers (numpy arrays + C structs) are the call's inputs; they are built once per batch
-    packed = [ix.pack(q, sp, filters, filter_of, limit=limit, kprime=kprime, fusion=cfg["fusion"], sparse_weight=0.1)
-              for q, sp in batches] if world == 1 else None
+    if world == 1:
+        packed = [ix.pack(q, sp, filters, filter_of, limit=limit, kprime=kprime, fusion=cfg["fusion"], sparse_weight=0.1)
+                  for q, sp in batches]
+    else:
+        packed = [sh.pack(q, sp, filters, filter_of, limit=limit, kprime=kprime, fusion=cfg["fusion"], sparse_weight=0.1)
+                  for q, sp in batches]
 
     def e2e_step(i):
-        q, sp = batches[i % len(batches)]
         if world == 1:
             return ix.search_packed(packed[i % len(batches)])
-        return sh.search_batch(q, sp, filters, filter_of, limit=limit, kprime=kprime, fusion=cfg["fusion"],
-                               sparse_weight=0.1)
+        return sh.search_packed(packed[i % len(batches)])
 
     for i in range(args.warmup):
         e2e_step(i)
@@ -350,11 +348,24 @@ def main():
     e2e = {"value": B * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(st["last_h2d_bytes"]),
            "d2h_bytes_per_step": int(st["last_d2h_bytes"]), "ms_per_step": 1e3 * e2e_s / args.steps}
 
+    # ---- per-kernel durations: a short pass with the two chains serialised on one stream and CUDA
+    # events around every phase (the timed regions above run with overlap on and no phase events) ----
+    ix.set_option("profile", 1)
+    ix.set_option("overlap", 0)
+    phase = np.zeros(5)
+    n_prof = max(3, min(args.steps, 50))
+    for i in range(n_prof):
+        device_step(stage(i))
+        s_ = ix.stats()
+        phase += [s_["last_mask_ms"], s_["last_dense_ms"], s_["last_sparse_ms"], s_["last_select_ms"], s_["last_fuse_ms"]]
+    ix.set_option("profile", 0)
+    ix.set_option("overlap", 1)
+
     # ---- roofline of the dominant kernel ------------------------------------------------------------
     hbm_peak, tf_peak, peak_kind = peaks()
     rows_local = hi - lo
     names = ["mask", "dense", "sparse", "select", "fuse"]
-    per_step = phase / args.steps
+    per_step = phase / n_prof
     dom = int(np.argmax(per_step))
     d_pad = (cfg["dim"] + 63) // 64 * 64
     passes = max(1, int(ix.stats()["last_dense_passes"]))     # corpus passes of the dense kernel per step
@@ -380,6 +391,7 @@ def main():
                 "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind}, burst copy)", "traffic": None,
                 "algorithmic_bytes_per_step": alg[dom_name], "kernel_ms_per_step": dom_ms,
                 "dense_tflops": dense_flops / (per_step[1] / 1e3) / 1e12 if per_step[1] > 0 else None,
+                "how": "CUDA events around each phase, chains serialised on one stream, %d steps after the timed region" % n_prof,
                 "phase_ms_per_step": {n_: float(v) for n_, v in zip(names, per_step)},
                 "phase_gbs": {n_: (alg[n_] / (per_step[j] / 1e3) / 1e9 if per_step[j] > 0 else None) for j, n_ in enumerate(names)}}
 

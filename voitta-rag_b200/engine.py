@@ -374,6 +374,13 @@ class Index:
         res, cres = self._alloc_result(p.B, limit, kprime, branches)
         return res, cres
 
+    def stage_packed(self, packed, need_corpus: bool = True):
+        """vb_stage on host buffers built earlier by ``pack`` (branches as chosen there)."""
+        res, cres = packed.result
+        want = res.dense_rows is not None
+        self._check(self._lib.vb_stage(self._h, C.byref(packed.c), int(want), int(need_corpus)))
+        return packed.result
+
     def run_local(self, cand_dev_ptr: int | None = None) -> None:
         self._check(self._lib.vb_run_local(self._h, _vp(cand_dev_ptr)))
 

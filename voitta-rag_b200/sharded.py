@@ -135,6 +135,33 @@ class ShardedIndex:
             self.index.set_option("safe_mode", 0)
         raise RuntimeError("candidate list overflow even in safe mode")
 
+    def pack(self, queries, sparse=None, filters=None, filter_of=None, limit=10, kprime=None,
+             fusion="weighted", sparse_weight=0.1, branches=False):
+        """Host buffers of one batch with the GLOBAL idf already applied (reusable across calls)."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        any_sparse = sparse is not None and any(s is not None and len(s[0]) for s in sparse)
+        if kprime is None:
+            kprime = limit * 3 if (any_sparse and fusion != "dense") else limit
+        weighted = self.idf_weights(sparse) if any_sparse else None
+        p = self.index.pack(q, weighted, filters, filter_of, limit=limit, kprime=kprime, fusion=fusion,
+                            sparse_weight=sparse_weight, apply_idf=False, branches=branches)
+        p.kprime = kprime
+        return p
+
+    def search_packed(self, packed):
+        """stage (H2D) -> local branches -> all-gather -> merge + fuse -> fetch (D2H) on prepared buffers."""
+        try:
+            for attempt in range(2):
+                if attempt:
+                    self.index.set_option("safe_mode", 1)
+                staged = self.index.stage_packed(packed)
+                res = self.run_staged(staged, packed.B, packed.kprime)
+                if res is not None:
+                    return res
+        finally:
+            self.index.set_option("safe_mode", 0)
+        raise RuntimeError("candidate list overflow even in safe mode")
+
     def run_staged(self, staged, B: int, kprime: int):
         """Device part of one sharded search on an already staged batch: local branches ->
         all-gather of the candidate blocks (the path's ONE exchange step) -> merge -> fuse -> fetch."""
