@@ -27,12 +27,26 @@ __device__ __forceinline__ float vb_key_score(uint64_t key) {
     return __uint_as_float(vb_ordered_f32((uint32_t)(key >> 32)));
 }
 
-// Append a surviving candidate to list `list`.  cnt may run past cap: the compaction kernel
-// turns that into the overflow flag and the host re-runs the batch in safe mode.
-__device__ __forceinline__ void vb_push(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt,
-                                        uint32_t cap, uint32_t list, float score, uint32_t row) {
-    uint32_t slot = atomicAdd(&cnt[list], 1u);
-    if (slot < cap) cand[(size_t)list * cap + slot] = vb_pack_key(score, row);
+// A candidate list of `cap` slots is cut into up to VB_SUB sub-ranges of `sub_cap` slots, each with
+// its own append counter (cnt[list*VB_SUB + sub]): a CTA appends to sub-range blockIdx.x % nsub, so
+// the atomics of one list are spread over nsub addresses instead of serialising on one.
+// After a compaction the list lives at the front of sub-range 0.
+#define VB_SUB 8u
+
+struct VbLists {
+    uint64_t* cand;       // [n_lists][cap]
+    uint32_t* cnt;        // [n_lists][VB_SUB]
+    uint32_t cap;         // slots per list
+    uint32_t sub_cap;     // slots per sub-range = cap / nsub
+    uint32_t sub_mask;    // nsub - 1 (nsub is a power of two <= VB_SUB; 1 in safe mode)
+};
+
+// Append a surviving candidate to list `list`.  A counter may run past sub_cap: the compaction
+// kernel turns that into the overflow flag and the host re-runs the batch in safe mode.
+__device__ __forceinline__ void vb_push(const VbLists& L, uint32_t list, float score, uint32_t row) {
+    const uint32_t sub = blockIdx.x & L.sub_mask;
+    const uint32_t slot = atomicAdd(&L.cnt[list * VB_SUB + sub], 1u);
+    if (slot < L.sub_cap) L.cand[(size_t)list * L.cap + (size_t)sub * L.sub_cap + slot] = vb_pack_key(score, row);
 }
 
 __device__ __forceinline__ uint4 vb_ldg_stream(const uint4* p) {

@@ -23,7 +23,7 @@
 #include <cstdlib>
 #include <algorithm>
 
-#define VB_GEMM_THREADS 192
+#define VB_GEMM_THREADS 320          // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quadrant)
 #define VB_TILE_M 128u
 #define VB_BLOCK_K 64u
 #define VB_STAGE_BYTES (VB_TILE_M * VB_BLOCK_K * 2u)   // 16 KB
@@ -120,10 +120,8 @@ struct VbGemmArgs {
     const uint32_t* mask;      // [n_filters][mask_words] or nullptr
     const int32_t* mask_of;    // [B_total] or nullptr
     const float* tau;          // [n_lists]
-    uint64_t* cand;
-    uint32_t* cnt;
+    VbLists lists;
     uint32_t mask_words, n_filters;
-    uint32_t cap;
     uint32_t tile_begin, tile_end;   // 128-row tiles of this segment
     uint32_t row_end;                // rows >= row_end are not part of the segment
     uint32_t row_base;
@@ -170,7 +168,7 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     if (warp == 1) {
         if (lane == 0) {
             for (uint32_t s = 0; s < S; ++s) { vb_mbar_init(bar_full + 8u * s, 1); vb_mbar_init(bar_empty + 8u * s, 1); }
-            for (uint32_t s = 0; s < 2; ++s) { vb_mbar_init(bar_tfull + 8u * s, 1); vb_mbar_init(bar_tempty + 8u * s, 4); }
+            for (uint32_t s = 0; s < 2; ++s) { vb_mbar_init(bar_tfull + 8u * s, 1); vb_mbar_init(bar_tempty + 8u * s, 8); }
             vb_mbar_init(bar_q, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -241,10 +239,12 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             }
         }
     } else {
-        // ===== epilogue warps 2..5; TMEM lane quadrant = warp % 4 =====
+        // ===== epilogue warps 2..9; TMEM lane quadrant = warp % 4, two warps per quadrant that
+        //       split the 16-column chunks between them (even / odd) =====
         // Branch-free per column: 16 columns are compared against their thresholds into a bit
         // mask, ONE warp vote per 16-column chunk decides whether the (rare) append path runs.
         const uint32_t quad = warp & 3u;
+        const uint32_t half = (warp - 2u) >> 2;            // 0: even chunks, 1: odd chunks
         const uint32_t tau_addr = vb_smem_u32(tau_s), mof_addr = vb_smem_u32(mof_s);
         const uint32_t mw_addr = vb_smem_u32(mw_s + quad * VB_GEMM_MAX_FILTERS);
         uint32_t* mw = mw_s + quad * VB_GEMM_MAX_FILTERS;
@@ -281,6 +281,7 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             const uint32_t slot = row - a.tile_begin * VB_TILE_M;      // direct mode: position inside the segment
             // one 16-column chunk: compare, then (rarely) append — or, in direct mode, store all
             auto process = [&](const uint32_t (&v)[16], const uint32_t (&w)[16], uint32_t c0) {
+                if (a.debug & 8u) return;
                 uint32_t m = 0;
 #pragma unroll
                 for (uint32_t j4 = 0; j4 < 4u; ++j4) {
@@ -307,7 +308,7 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                         for (uint32_t j = 0; j < 16u; ++j) {
                             const uint32_t col = c0 + j;
                             if (col < a.n_q)
-                                a.cand[(size_t)(a.q_begin + col) * a.cap + slot] =
+                                a.lists.cand[(size_t)(a.q_begin + col) * a.lists.cap + slot] =
                                     ((m >> j) & 1u) ? vb_pack_key((split ? __uint_as_float(v[j]) + __uint_as_float(w[j]) : __uint_as_float(v[j])) * invn, a.row_base + row) : 0ull;
                         }
                     }
@@ -315,35 +316,39 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     // rare path: reserve slots for all survivors of the chunk first (predicated atomics
                     // issued back to back, so their L2 round trips overlap), then store the keys
                     uint32_t slot[16];
+                    const uint32_t sub = blockIdx.x & a.lists.sub_mask;
 #pragma unroll
                     for (uint32_t j = 0; j < 16u; ++j) {
                         asm volatile(
                             "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p atom.global.add.u32 %0, [%1], 1;\n\t}"
-                            : "=r"(slot[j]) : "l"(a.cnt + a.q_begin + c0 + j), "r"((m >> j) & 1u) : "memory");
+                            : "=r"(slot[j]) : "l"(a.lists.cnt + (size_t)(a.q_begin + c0 + j) * VB_SUB + sub), "r"((m >> j) & 1u) : "memory");
                     }
 #pragma unroll
                     for (uint32_t j = 0; j < 16u; ++j) {
-                        if (((m >> j) & 1u) && slot[j] < a.cap)
-                            a.cand[(size_t)(a.q_begin + c0 + j) * a.cap + slot[j]] =
+                        if (((m >> j) & 1u) && slot[j] < a.lists.sub_cap)
+                            a.lists.cand[(size_t)(a.q_begin + c0 + j) * a.lists.cap + (size_t)sub * a.lists.sub_cap + slot[j]] =
                                 vb_pack_key((split ? __uint_as_float(v[j]) + __uint_as_float(w[j]) : __uint_as_float(v[j])) * invn, a.row_base + row);
                     }
                 }
             };
             uint32_t va[16], vb[16], wa[16], wb[16];
             auto load = [&](uint32_t (&v)[16], uint32_t (&w)[16], uint32_t c0) {
+                if (a.debug & 16u) return;
                 vb_tmem_ld16(taddr + c0, v);
                 if (split) vb_tmem_ld16(taddr + ncol + c0, w);
             };
-            if (!(a.debug & 1u)) load(va, wa, 0);
-            for (uint32_t c0 = 0; c0 < ncol && !(a.debug & 1u); c0 += 32u) {
+            // this warp's chunks: 16*(2i + half); the next one is in flight while one is processed
+            const uint32_t first = 16u * half;
+            if (first < ncol && !(a.debug & 1u)) load(va, wa, first);
+            for (uint32_t c0 = first; c0 < ncol && !(a.debug & 1u); c0 += 64u) {
                 vb_tmem_ld_wait();
-                const bool second = c0 + 16u < ncol;
-                if (second) load(vb, wb, c0 + 16u);                        // next chunk in flight
+                const bool second = c0 + 32u < ncol;
+                if (second) load(vb, wb, c0 + 32u);
                 process(va, wa, c0);
                 if (second) {
                     vb_tmem_ld_wait();
-                    if (c0 + 32u < ncol) load(va, wa, c0 + 32u);
-                    process(vb, wb, c0 + 16u);
+                    if (c0 + 64u < ncol) load(va, wa, c0 + 64u);
+                    process(vb, wb, c0 + 32u);
                 }
             }
             vb_tcgen05_fence_before();
@@ -450,9 +455,7 @@ struct VbGemmLaunch {
     const int32_t* mask_of;
     uint32_t mask_words, n_filters;
     const float* tau;
-    uint64_t* cand;
-    uint32_t* cnt;
-    uint32_t cap;
+    VbLists lists;
     uint32_t n_rows_total, row_begin, row_end, row_base, d_pad, n_queries;
     int sm_count;
     cudaStream_t stream;
@@ -503,8 +506,8 @@ static int vb_gemm_launch(const VbGemmLaunch& g, int* launches) {
         CUtensorMap tmap_q;
         if (vb_encode_2d(&tmap_q, reinterpret_cast<const unsigned char*>(g.q_bf16) + (size_t)q0 * mult * g.d_pad * 2, bn, g.d_pad, bn)) return 1;
         VbGemmArgs a{};
-        a.inv_norm = g.inv_norm; a.mask = g.mask; a.mask_of = g.mask_of; a.tau = g.tau; a.cand = g.cand; a.cnt = g.cnt;
-        a.mask_words = g.mask_words; a.n_filters = g.n_filters; a.cap = g.cap;
+        a.inv_norm = g.inv_norm; a.mask = g.mask; a.mask_of = g.mask_of; a.tau = g.tau; a.lists = g.lists;
+        a.mask_words = g.mask_words; a.n_filters = g.n_filters;
         a.tile_begin = g.row_begin / VB_TILE_M; a.tile_end = (g.row_end + VB_TILE_M - 1) / VB_TILE_M;
         a.row_end = g.row_end; a.row_base = g.row_base; a.k_blocks = g.d_pad / VB_BLOCK_K;
         a.bn = bn; a.n_q = n_q; a.q_begin = q0;

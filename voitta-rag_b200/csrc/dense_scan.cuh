@@ -22,13 +22,11 @@ struct VbScanArgs {
     const int32_t* mask_of;     // [B] filter index per query, -1 = no mask; nullptr = none
     const float* q_hat;         // [B][d_pad] fp32 unit-norm queries
     const float* tau;           // [n_lists]
-    uint64_t* cand;
-    uint32_t* cnt;
+    VbLists lists;
     uint32_t mask_words;
     uint32_t chunks;            // d_pad / 8
     uint32_t row_begin, row_end;// segment (row_begin % 32 == 0)
     uint32_t row_base;          // added to the row in the candidate key (shard offset)
-    uint32_t cap;
     uint32_t q_begin;           // first query handled by blockIdx.y == 0
     uint32_t direct;            // 1: first segment — store the key at slot (row - row_begin), no atomics
 };
@@ -124,8 +122,8 @@ vb_dense_scan_kernel(const VbScanArgs a)
             if (lane < (uint32_t)ROWS && myr >= 0) {
                 const float s = mine * inv_r;
                 const uint32_t row = row0 + (uint32_t)myr;
-                if (a.direct) a.cand[(size_t)list * a.cap + (row - a.row_begin)] = s > tau ? vb_pack_key(s, a.row_base + row) : 0ull;
-                else if (s > tau) vb_push(a.cand, a.cnt, a.cap, list, s, a.row_base + row);
+                if (a.direct) a.lists.cand[(size_t)list * a.lists.cap + (row - a.row_begin)] = s > tau ? vb_pack_key(s, a.row_base + row) : 0ull;
+                else if (s > tau) vb_push(a.lists, list, s, a.row_base + row);
             }
         }
     }
@@ -167,8 +165,8 @@ vb_dense_scan_generic_kernel(const VbScanArgs a)
             if (lane == 0) {
                 const float s = acc * a.inv_norm[row0 + r];
                 const uint32_t row = row0 + r;
-                if (a.direct) a.cand[(size_t)list * a.cap + (row - a.row_begin)] = s > tau ? vb_pack_key(s, a.row_base + row) : 0ull;
-                else if (s > tau) vb_push(a.cand, a.cnt, a.cap, list, s, a.row_base + row);
+                if (a.direct) a.lists.cand[(size_t)list * a.lists.cap + (row - a.row_begin)] = s > tau ? vb_pack_key(s, a.row_base + row) : 0ull;
+                else if (s > tau) vb_push(a.lists, list, s, a.row_base + row);
             }
         }
     }

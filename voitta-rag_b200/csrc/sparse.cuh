@@ -83,15 +83,13 @@ struct VbSparseArgs {
     const uint32_t* mask;       // [n_filters][mask_words] or nullptr
     const int32_t* mask_of;     // [B] or nullptr
     const float* tau;
-    uint64_t* cand;
-    uint32_t* cnt;
+    VbLists lists;
     uint32_t mask_words;
     uint32_t n_blocks;          // row blocks in the whole index
     uint32_t blk_begin;         // first row block of this segment
     uint32_t n_queries;
     uint32_t n_rows;
     uint32_t row_base;
-    uint32_t cap;
     uint32_t direct;            // 1: first segment — store keys at slot (row - segment begin), no atomics
 };
 
@@ -190,9 +188,9 @@ vb_sparse_kernel(const VbSparseArgs a)
             float s = 0.0f;
             if (pass) { s = __double2float_rn(cur); pass = s > tau; }
             if (a.direct) {
-                if (row < a.n_rows) a.cand[(size_t)list * a.cap + (row - seg_row0)] = pass ? vb_pack_key(s, a.row_base + row) : 0ull;
+                if (row < a.n_rows) a.lists.cand[(size_t)list * a.lists.cap + (row - seg_row0)] = pass ? vb_pack_key(s, a.row_base + row) : 0ull;
             } else if (pass) {
-                vb_push(a.cand, a.cnt, a.cap, list, s, a.row_base + row);
+                vb_push(a.lists, list, s, a.row_base + row);
             }
         }
     }

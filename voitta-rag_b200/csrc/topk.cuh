@@ -38,14 +38,12 @@ __device__ __forceinline__ void vb_bitonic_desc(uint64_t* s, uint32_t P) {
 //
 // Selection, not sorting: a list holds a few thousand unsorted keys of which only k' (tens)
 // survive, and this kernel sits on the critical path between two scoring segments.
-//   1. the list is read once into registers (<= 16 keys per thread; longer lists are re-read
-//      from global memory in every pass);
+//   1. the list (the used prefixes of its sub-ranges) is L2-resident and re-read in each pass;
 //   2. block min/max of the active keys give their common bit prefix; ONE 2048-bin histogram
 //      over the 11 bits below the highest differing bit and a block suffix scan find the pivot
 //      bin (the bin holding the k'-th largest key);
 //   3. every key >= the pivot bin's lower bound is gathered (k' + a few) and only those are
 //      sorted.  If that would exceed VB_SORT_MAX keys, step 2 repeats inside the pivot bin.
-#define VB_REG_KEYS 16u
 #define VB_BINS 2048u
 
 template <bool IS_MAX>
@@ -67,27 +65,35 @@ __device__ __forceinline__ uint64_t vb_block_reduce_u64(uint64_t v, uint64_t* s_
     return r;
 }
 
+// IN_REGS: the whole list fits the per-thread register image (sub-range 0: <= 8 keys per thread,
+// sub-ranges 1..7: <= 1 key per thread each) and is read from memory exactly once.
+#define VB_REG0 8u
 template <bool IN_REGS>
-__device__ __forceinline__ void vb_compact_body(uint64_t* __restrict__ gkeys, uint32_t E, uint32_t k,
-                                                uint32_t* __restrict__ cnt_out, float* __restrict__ tau_out,
+__device__ __forceinline__ void vb_compact_body(uint64_t* __restrict__ gkeys, const uint32_t (&E)[VB_SUB], uint32_t sub_cap,
+                                                uint32_t k, uint32_t* __restrict__ cnt_out, float* __restrict__ tau_out,
                                                 uint64_t* s_sel, uint32_t* s_hist, uint64_t* s_red,
                                                 uint32_t* s_scan, uint32_t* s_misc)
 {
-    uint64_t r[VB_REG_KEYS];
+    uint64_t r[VB_REG0 + VB_SUB - 1];
     if (IN_REGS) {
 #pragma unroll
-        for (uint32_t j = 0; j < VB_REG_KEYS; ++j) {
+        for (uint32_t j = 0; j < VB_REG0; ++j) {
             const uint32_t i = threadIdx.x + j * VB_COMPACT_THREADS;
-            r[j] = i < E ? gkeys[i] : 0ull;
+            r[j] = i < E[0] ? gkeys[i] : 0ull;
         }
+#pragma unroll
+        for (uint32_t sub = 1; sub < VB_SUB; ++sub)
+            r[VB_REG0 + sub - 1] = threadIdx.x < E[sub] ? gkeys[(size_t)sub * sub_cap + threadIdx.x] : 0ull;
     }
-    // visit every key of the list (registers, or global memory for long lists)
+    // visit every key of the list (register image, or the used prefix of each sub-range in L2)
     auto for_each = [&](auto&& f) {
         if (IN_REGS) {
 #pragma unroll
-            for (uint32_t j = 0; j < VB_REG_KEYS; ++j) f(r[j]);
+            for (uint32_t j = 0; j < VB_REG0 + VB_SUB - 1; ++j) f(r[j]);
         } else {
-            for (uint32_t i = threadIdx.x; i < E; i += VB_COMPACT_THREADS) f(gkeys[i]);
+#pragma unroll
+            for (uint32_t sub = 0; sub < VB_SUB; ++sub)
+                for (uint32_t i = threadIdx.x; i < E[sub]; i += VB_COMPACT_THREADS) f(gkeys[(size_t)sub * sub_cap + i]);
         }
     };
 
@@ -175,15 +181,15 @@ __device__ __forceinline__ void vb_compact_body(uint64_t* __restrict__ gkeys, ui
     vb_bitonic_desc(s_sel, P);
     const uint32_t keep = nsel < k ? nsel : k;
     for (uint32_t i = threadIdx.x; i < keep; i += VB_COMPACT_THREADS) gkeys[i] = s_sel[i];
+    if (threadIdx.x < VB_SUB) cnt_out[threadIdx.x] = threadIdx.x == 0 ? keep : 0u;   // the list now lives in sub-range 0
     if (threadIdx.x == 0) {
-        *cnt_out = keep;
         *tau_out = (keep >= k) ? vb_key_score(s_sel[k - 1]) : -INFINITY;
     }
 }
 
 __global__ void __launch_bounds__(VB_COMPACT_THREADS)
-vb_compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float* __restrict__ tau,
-                  uint32_t* __restrict__ overflow, uint32_t cap, uint32_t k, uint32_t list_begin)
+vb_compact_kernel(VbLists L, float* __restrict__ tau, uint32_t* __restrict__ overflow, uint32_t k, uint32_t list_begin,
+                  uint32_t lim0 /* slots sub-range 0 may hold: sub_cap, or the first segment's direct block */)
 {
     __shared__ uint64_t s_sel[VB_SORT_MAX];
     __shared__ uint32_t s_hist[VB_BINS];
@@ -191,14 +197,25 @@ vb_compact_kernel(uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, float
     __shared__ uint32_t s_scan[VB_COMPACT_THREADS / 32];
     __shared__ uint32_t s_misc[4];
     const uint32_t list = list_begin + blockIdx.x;
-    uint64_t* gkeys = cand + (size_t)list * cap;
-    const uint32_t raw = cnt[list];
-    if (raw > cap && threadIdx.x == 0) overflow[list] = 1u;
-    const uint32_t E = raw < cap ? raw : cap;
-    if (E <= VB_REG_KEYS * VB_COMPACT_THREADS)
-        vb_compact_body<true>(gkeys, E, k, cnt + list, tau + list, s_sel, s_hist, s_red, s_scan, s_misc);
+    uint64_t* gkeys = L.cand + (size_t)list * L.cap;
+    uint32_t E[VB_SUB];
+    bool over = false;
+#pragma unroll
+    for (uint32_t sub = 0; sub < VB_SUB; ++sub) {
+        const uint32_t raw = L.cnt[list * VB_SUB + sub];
+        const uint32_t lim = sub == 0 ? lim0 : L.sub_cap;
+        over = over || raw > lim || (sub > L.sub_mask && raw != 0u);
+        E[sub] = raw < lim ? raw : lim;
+    }
+    if (over && threadIdx.x == 0) overflow[list] = 1u;
+    __syncthreads();                                   // everyone has read the counters before they are rewritten
+    bool fits = E[0] <= VB_REG0 * VB_COMPACT_THREADS;
+#pragma unroll
+    for (uint32_t sub = 1; sub < VB_SUB; ++sub) fits = fits && E[sub] <= VB_COMPACT_THREADS;
+    if (fits)
+        vb_compact_body<true>(gkeys, E, L.sub_cap, k, L.cnt + (size_t)list * VB_SUB, tau + list, s_sel, s_hist, s_red, s_scan, s_misc);
     else
-        vb_compact_body<false>(gkeys, E, k, cnt + list, tau + list, s_sel, s_hist, s_red, s_scan, s_misc);
+        vb_compact_body<false>(gkeys, E, L.sub_cap, k, L.cnt + (size_t)list * VB_SUB, tau + list, s_sel, s_hist, s_red, s_scan, s_misc);
 }
 
 // Pack the first k keys of every list into out[list][k] (0-padded): the all-gather payload.
@@ -209,7 +226,7 @@ __global__ void vb_export_kernel(const uint64_t* __restrict__ cand, const uint32
                                  const uint32_t* __restrict__ overflow, uint32_t n_lists)
 {
     const uint32_t list = blockIdx.x;
-    const uint32_t c = cnt[list] < k ? cnt[list] : k;
+    const uint32_t c = cnt[list * VB_SUB] < k ? cnt[list * VB_SUB] : k;
     for (uint32_t i = threadIdx.x; i < k; i += blockDim.x)
         out[(size_t)list * k + i] = i < c ? cand[(size_t)list * cap + i] : 0ull;
     if (overflow != nullptr && blockIdx.x == 0) {
@@ -232,8 +249,8 @@ __global__ void vb_import_kernel(const uint64_t* __restrict__ gathered, uint32_t
         const uint32_t sh = i / k, j = i % k;
         cand[(size_t)list * cap + i] = gathered[sh * stride + (size_t)list * k + j];
     }
+    if (threadIdx.x < VB_SUB) cnt[list * VB_SUB + threadIdx.x] = threadIdx.x == 0 ? n_shards * k : 0u;
     if (threadIdx.x == 0) {
-        cnt[list] = n_shards * k;
         if (list == 0)
             for (uint32_t sh = 0; sh < n_shards; ++sh)
                 if (gathered[sh * stride + (size_t)n_lists * k] != 0ull) overflow[0] = 1u;
@@ -271,7 +288,7 @@ vb_fuse_kernel(const VbFuseArgs a)
     const uint32_t q = blockIdx.x, B = a.n_queries;
     const uint64_t* dk = a.cand + (size_t)q * a.cap;
     const uint64_t* sk = a.cand + (size_t)(B + q) * a.cap;
-    const uint32_t nd = a.cnt[q] < k ? a.cnt[q] : k;
+    const uint32_t nd = a.cnt[q * VB_SUB] < k ? a.cnt[q * VB_SUB] : k;
     const int32_t mode = a.mode[q];
 
     if (mode == 0) {
@@ -283,7 +300,7 @@ vb_fuse_kernel(const VbFuseArgs a)
         if (threadIdx.x == 0) a.out_cnt[q] = (int32_t)n;
         return;
     }
-    const uint32_t ns = a.cnt[B + q] < k ? a.cnt[B + q] : k;
+    const uint32_t ns = a.cnt[(B + q) * VB_SUB] < k ? a.cnt[(B + q) * VB_SUB] : k;
 
     double dmin = 0.0, dspread = 0.0, smin = 0.0, sspread = 0.0;
     if (nd) { dmin = (double)vb_key_score(dk[nd - 1]); dspread = __dsub_rn((double)vb_key_score(dk[0]), dmin); }

@@ -172,7 +172,10 @@ static void dev_free(vb_index* h, DevBuf& b) {
 // ------------------------------------------------------------------------------------------------
 __global__ void vb_init_lists_kernel(float* tau, uint32_t* cnt, uint32_t* overflow, uint32_t n, uint32_t cnt0) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { tau[i] = -INFINITY; cnt[i] = cnt0; overflow[i] = 0u; }
+    if (i < n) {
+        tau[i] = -INFINITY; overflow[i] = 0u;
+        for (uint32_t s = 0; s < VB_SUB; ++s) cnt[i * VB_SUB + s] = s == 0 ? cnt0 : 0u;
+    }
 }
 __global__ void vb_fill_i64_kernel(int64_t* p, uint64_t n, int64_t v) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
@@ -767,10 +770,10 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     const uint32_t need_cap = std::max<uint32_t>(16384u, (uint32_t)align_up((size_t)2 * (size_t)h->opt_seg_ratio * b.k, 4096));
     h->cand_cap = need_cap;
     TRY(dev_reserve(h, h->cand, (size_t)b.n_lists * need_cap * 8, false));
-    TRY(dev_reserve(h, h->lists, (size_t)b.n_lists * 12, false));
+    TRY(dev_reserve(h, h->lists, (size_t)b.n_lists * (8 + 4 * VB_SUB), false));
     b.tau = h->lists.as<float>();
-    b.cnt = h->lists.as<uint32_t>() + b.n_lists;
-    b.overflow = h->lists.as<uint32_t>() + 2 * (size_t)b.n_lists;
+    b.overflow = h->lists.as<uint32_t>() + b.n_lists;
+    b.cnt = h->lists.as<uint32_t>() + 2 * (size_t)b.n_lists;      // [n_lists][VB_SUB]
     b.h2d_bytes = ar.off;
     h->stats.last_h2d_bytes = ar.off;
     // output block layout
@@ -799,7 +802,18 @@ static int init_lists(vb_index* h, const Batch& b, uint32_t direct_rows) {
     return 0;
 }
 
-static int launch_scan(vb_index* h, const Batch& b, uint32_t row_begin, uint32_t row_end, uint32_t direct, cudaStream_t st) {
+static VbLists make_lists(const vb_index* h, const Batch& b, bool safe) {
+    VbLists L;
+    L.cand = h->cand.as<uint64_t>();
+    L.cnt = b.cnt;
+    L.cap = h->cand_cap;
+    const uint32_t nsub = safe ? 1u : VB_SUB;          // safe mode: one range, segments that cannot overflow it
+    L.sub_cap = h->cand_cap / nsub;
+    L.sub_mask = nsub - 1u;
+    return L;
+}
+
+static int launch_scan(vb_index* h, const Batch& b, const VbLists& L, uint32_t row_begin, uint32_t row_end, uint32_t direct, cudaStream_t st) {
     VbScanArgs a{};
     a.rows = h->rows.as<uint4>();
     a.inv_norm = h->inv_norm.as<float>();
@@ -807,14 +821,12 @@ static int launch_scan(vb_index* h, const Batch& b, uint32_t row_begin, uint32_t
     a.mask_of = b.use_mask ? b.d_maskof : nullptr;
     a.q_hat = h->q_hat.as<float>();
     a.tau = b.tau;
-    a.cand = h->cand.as<uint64_t>();
-    a.cnt = b.cnt;
+    a.lists = L;
     a.mask_words = b.mask_words;
     a.chunks = (uint32_t)h->d_pad / 8;
     a.row_begin = row_begin;
     a.row_end = row_end;
     a.row_base = (uint32_t)h->row_base;
-    a.cap = h->cand_cap;
     a.q_begin = 0;
     a.direct = direct;
     const uint32_t groups = (row_end - row_begin + 31) / 32;
@@ -846,7 +858,10 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
         for (uint64_t r = (uint64_t)h->opt_seg_first; r < n; r *= (uint64_t)h->opt_seg_ratio) bounds.push_back((uint32_t)r);
     }
     bounds.push_back(n);
-    const uint32_t direct_rows = bounds[1] <= h->cand_cap ? bounds[1] : 0u;   // first segment writes slots directly
+    const bool safe_mode = safe || h->opt_safe_mode;
+    const VbLists L = make_lists(h, b, safe_mode);
+    // the first segment writes its keys to fixed slots at the front of the list (no atomics)
+    const uint32_t direct_rows = bounds[1] <= h->cand_cap ? bounds[1] : 0u;
     TRY(init_lists(h, b, direct_rows));
     // dense path choice
     int path = (int)h->opt_dense_path;
@@ -891,19 +906,19 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
             VbGemmLaunch g{};
             g.rows = h->rows.p; g.inv_norm = h->inv_norm.as<float>(); g.q_bf16 = h->q_bf16.p;
             g.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; g.mask_of = b.use_mask ? b.d_maskof : nullptr;
-            g.mask_words = b.mask_words; g.n_filters = b.n_filters; g.tau = b.tau; g.cand = h->cand.as<uint64_t>(); g.cnt = b.cnt;
-            g.cap = h->cand_cap; g.n_rows_total = n; g.row_begin = r0; g.row_end = r1; g.row_base = (uint32_t)h->row_base;
+            g.mask_words = b.mask_words; g.n_filters = b.n_filters; g.tau = b.tau; g.lists = L;
+            g.n_rows_total = n; g.row_begin = r0; g.row_end = r1; g.row_base = (uint32_t)h->row_base;
             g.d_pad = (uint32_t)h->d_pad; g.n_queries = b.B; g.sm_count = h->sm_count; g.stream = sd;
             g.direct = direct; g.plan = plan; g.mask_of_host = b.mask_of_host.data();
             int launches = 0;
             if (vb_gemm_launch(g, &launches) != 0) return vb_fail("tensor-core dense kernel: %s", vb_gemm_last_error());
             h->stats.last_launches += (uint32_t)launches;
         } else {
-            TRY(launch_scan(h, b, r0, r1, direct, sd));
+            TRY(launch_scan(h, b, L, r0, r1, direct, sd));
         }
         prof_end(h, pi, sd);
         const int ps = prof_begin(h, PH_SELECT, sd);
-        vb_compact_kernel<<<b.B, VB_COMPACT_THREADS, 0, sd>>>(h->cand.as<uint64_t>(), b.cnt, b.tau, b.overflow, h->cand_cap, b.k, 0u);
+        vb_compact_kernel<<<b.B, VB_COMPACT_THREADS, 0, sd>>>(L, b.tau, b.overflow, b.k, 0u, direct ? std::max(direct_rows, L.sub_cap) : L.sub_cap);
         CKK("vb_compact_kernel");
         ++h->stats.last_launches;
         prof_end(h, ps, sd);
@@ -916,9 +931,9 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
             a.post_row = h->post_row.as<uint32_t>(); a.post_val = h->post_val.as<float>(); a.off = h->offs.as<uint32_t>();
             a.q_indptr = b.d_qindptr; a.q_weight = b.d_qweight;
             a.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; a.mask_of = b.use_mask ? b.d_maskof : nullptr;
-            a.tau = b.tau; a.cand = h->cand.as<uint64_t>(); a.cnt = b.cnt; a.mask_words = b.mask_words;
+            a.tau = b.tau; a.lists = L; a.mask_words = b.mask_words;
             a.n_blocks = b.n_blocks; a.blk_begin = r0 / VB_ROWS_PER_BLOCK; a.n_queries = b.B; a.n_rows = n;
-            a.row_base = (uint32_t)h->row_base; a.cap = h->cand_cap; a.direct = direct;
+            a.row_base = (uint32_t)h->row_base; a.direct = direct;
             const uint32_t nblk = (r1 - r0 + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK;
             vb_sparse_kernel<<<nblk * b.B, VB_SPARSE_THREADS, 0, ss>>>(a);
             CKK("vb_sparse_kernel");
@@ -927,7 +942,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
         }
         // the sparse lists are compacted even without postings (first-segment slots -> empty lists)
         const int ps = prof_begin(h, PH_SELECT, ss);
-        vb_compact_kernel<<<b.B, VB_COMPACT_THREADS, 0, ss>>>(h->cand.as<uint64_t>(), b.cnt, b.tau, b.overflow, h->cand_cap, b.k, b.B);
+        vb_compact_kernel<<<b.B, VB_COMPACT_THREADS, 0, ss>>>(L, b.tau, b.overflow, b.k, b.B, direct ? std::max(direct_rows, L.sub_cap) : L.sub_cap);
         CKK("vb_compact_kernel");
         ++h->stats.last_launches;
         prof_end(h, ps, ss);
@@ -974,7 +989,7 @@ static int fuse_stage(vb_index* h, const Batch& b) {
         ++h->stats.last_launches;
     }
     prof_end(h);
-    CK(cudaMemcpyAsync(dp + b.o_lcnt, b.cnt, (size_t)b.n_lists * 4, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpy2DAsync(dp + b.o_lcnt, 4, b.cnt, VB_SUB * 4, 4, b.n_lists, cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaMemcpyAsync(dp + b.o_ovf, b.overflow, (size_t)b.n_lists * 4, cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaEventRecord(h->ev1, h->stream));
     return 0;
@@ -1094,7 +1109,7 @@ extern "C" int vb_run_fuse(vb_index* h, uint32_t n_shards, const uint64_t* gathe
         prof_begin(h, PH_SELECT);
         vb_import_kernel<<<b.n_lists, 256, 0, h->stream>>>(gathered_dev, n_shards, b.n_lists, b.k, h->cand_cap, h->cand.as<uint64_t>(), b.cnt, b.overflow);
         CKK("vb_import_kernel");
-        vb_compact_kernel<<<b.n_lists, VB_COMPACT_THREADS, 0, h->stream>>>(h->cand.as<uint64_t>(), b.cnt, b.tau, b.overflow, h->cand_cap, b.k, 0u);
+        vb_compact_kernel<<<b.n_lists, VB_COMPACT_THREADS, 0, h->stream>>>(make_lists(h, b, true), b.tau, b.overflow, b.k, 0u, h->cand_cap);
         CKK("vb_compact_kernel");
         h->stats.last_launches += 2;
         prof_end(h);
