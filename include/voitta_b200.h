@@ -100,6 +100,8 @@ typedef struct vb_stats {
     uint64_t device_bytes;
     uint64_t last_h2d_bytes, last_d2h_bytes;   /* host<->device copies of the last staged search */
     uint64_t last_dense_passes;                /* passes over the shard's dense rows (K1: B, K2: sub-batches) */
+    uint64_t last_big_rows;                    /* rows of the largest (last) segment of the last search */
+    double   last_dense_big_ms, last_sparse_big_ms;  /* profile: dense / sparse kernel time of that segment */
 } vb_stats;
 
 int         vb_abi_version(void);

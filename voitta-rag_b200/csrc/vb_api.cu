@@ -588,7 +588,7 @@ struct Arena {
 };
 
 
-enum { PH_MASK = 0, PH_DENSE = 1, PH_SPARSE = 2, PH_SELECT = 3, PH_FUSE = 4, PH_N = 5 };
+enum { PH_MASK = 0, PH_DENSE = 1, PH_SPARSE = 2, PH_SELECT = 3, PH_FUSE = 4, PH_N = 5, PH_BIG = 8 /* flag: largest segment */ };
 
 static int prof_begin(vb_index* h, int phase, cudaStream_t st = nullptr) {
     if (!h->opt_profile) return -1;
@@ -611,10 +611,13 @@ static void prof_end(vb_index* h, int idx = -2, cudaStream_t st = nullptr) {
 // call after the stream has been synchronised
 static void prof_collect(vb_index* h) {
     double acc[PH_N] = {0, 0, 0, 0, 0};
+    h->stats.last_dense_big_ms = h->stats.last_sparse_big_ms = 0.0;
     for (size_t i = 0; i < h->prof_phase.size(); ++i) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, h->prof_events[2 * i], h->prof_events[2 * i + 1]);
-        acc[h->prof_phase[i]] += ms;
+        const int ph = h->prof_phase[i] & 7;
+        acc[ph] += ms;
+        if (h->prof_phase[i] & PH_BIG) (ph == PH_DENSE ? h->stats.last_dense_big_ms : h->stats.last_sparse_big_ms) = ms;
     }
     h->prof_phase.clear();
     h->stats.last_mask_ms = acc[PH_MASK];
@@ -900,8 +903,8 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
         CK(cudaEventRecord(h->ev_fork, sd));
         CK(cudaStreamWaitEvent(ss, h->ev_fork, 0));
     }
-    auto dense_segment = [&](uint32_t r0, uint32_t r1, uint32_t direct) -> int {
-        const int pi = prof_begin(h, PH_DENSE, sd);
+    auto dense_segment = [&](uint32_t r0, uint32_t r1, uint32_t direct, bool big) -> int {
+        const int pi = prof_begin(h, PH_DENSE | (big ? PH_BIG : 0), sd);
         if (path == 2) {
             VbGemmLaunch g{};
             g.rows = h->rows.p; g.inv_norm = h->inv_norm.as<float>(); g.q_bf16 = h->q_bf16.p;
@@ -924,9 +927,9 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
         prof_end(h, ps, sd);
         return 0;
     };
-    auto sparse_segment = [&](uint32_t r0, uint32_t r1, uint32_t direct) -> int {
+    auto sparse_segment = [&](uint32_t r0, uint32_t r1, uint32_t direct, bool big) -> int {
         if (do_sparse) {
-            const int pi = prof_begin(h, PH_SPARSE, ss);
+            const int pi = prof_begin(h, PH_SPARSE | (big ? PH_BIG : 0), ss);
             VbSparseArgs a{};
             a.post_row = h->post_row.as<uint32_t>(); a.post_val = h->post_val.as<float>(); a.off = h->offs.as<uint32_t>();
             a.q_indptr = b.d_qindptr; a.q_weight = b.d_qweight;
@@ -961,8 +964,10 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
     const size_t n_seg = bounds.size() - 1;
     for (size_t s = 0; s < n_seg; ++s) {
         const uint32_t direct = (s == 0 && direct_rows) ? 1u : 0u;
-        TRY(dense_segment(bounds[s], bounds[s + 1], direct));
-        if (do_sparse || s == 0) TRY(sparse_segment(bounds[s], bounds[s + 1], direct));
+        const bool big = s + 1 == n_seg;
+        if (big) h->stats.last_big_rows = bounds[s + 1] - bounds[s];
+        TRY(dense_segment(bounds[s], bounds[s + 1], direct, big));
+        if (do_sparse || s == 0) TRY(sparse_segment(bounds[s], bounds[s + 1], direct, big));
     }
     if (two_streams) {
         CK(cudaEventRecord(h->ev_join, ss));

@@ -58,7 +58,8 @@ class _Stats(C.Structure):
                 ("last_search_ms", C.c_double), ("last_dense_ms", C.c_double), ("last_sparse_ms", C.c_double),
                 ("last_select_ms", C.c_double), ("last_mask_ms", C.c_double), ("last_fuse_ms", C.c_double),
                 ("last_dense_path", C.c_uint32), ("last_launches", C.c_uint32), ("device_bytes", C.c_uint64),
-                ("last_h2d_bytes", C.c_uint64), ("last_d2h_bytes", C.c_uint64), ("last_dense_passes", C.c_uint64)]
+                ("last_h2d_bytes", C.c_uint64), ("last_d2h_bytes", C.c_uint64), ("last_dense_passes", C.c_uint64),
+                ("last_big_rows", C.c_uint64), ("last_dense_big_ms", C.c_double), ("last_sparse_big_ms", C.c_double)]
 
 
 # every symbol include/voitta_b200.h declares
