@@ -336,8 +336,18 @@ def main():
         e2e_step(i)
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        last = e2e_step(args.warmup + i)
+    if world == 1:
+        # a stream of batches, two in flight: batch i+1 is staged (host prep + H2D) while batch i runs;
+        # every batch has its own H2D copy from pinned memory and its own D2H read of the results
+        n_done = 0
+        for last in ix.search_stream(packed[(args.warmup + i) % len(batches)] for i in range(args.steps)):
+            n_done += 1
+        assert n_done == args.steps
+    else:
+        n_done = 0
+        for last in sh.search_stream(packed[(args.warmup + i) % len(batches)] for i in range(args.steps)):
+            n_done += 1
+        assert n_done == args.steps
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:

@@ -100,7 +100,9 @@ struct vb_index {
     uint64_t n_rows = 0, n_live = 0, cap_rows = 0;
     uint64_t nnz = 0, cap_nnz = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr, aux_stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev0s[2] = {nullptr, nullptr}, ev1s[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int cur = 0;                               // current slot: two batches can be in flight (pipelined callers)
     std::mutex mu;
     int sm_count = 148;
     uint64_t device_bytes = 0;
@@ -120,14 +122,14 @@ struct vb_index {
 
     // per-search scratch
     DevBuf args, mask, cand, lists, offs, out, q_hat, q_bf16, tmp;
-    HostBuf h_args, h_out, h_stage;
+    HostBuf h_args_s[2], h_out_s[2], h_stage;
     uint32_t cand_cap = 0;
 
     // options
     int64_t opt_dense_path = 0, opt_seg_first = 2048, opt_seg_ratio = 32, opt_safe_mode = 0, opt_profile = 0, opt_k2_precision = 0, opt_overlap = 1;
 
     vb_stats stats{};
-    Batch staged;
+    Batch staged_s[2];
     bool staged_safe = false;
     std::vector<cudaEvent_t> prof_events;
     std::vector<int> prof_phase;
@@ -235,7 +237,10 @@ extern "C" int vb_create(int32_t dim, int32_t device, uint64_t capacity_hint, ui
         cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+        cudaEventCreate(&h->ev0s[0]) != cudaSuccess || cudaEventCreate(&h->ev1s[0]) != cudaSuccess ||
+        cudaEventCreate(&h->ev0s[1]) != cudaSuccess || cudaEventCreate(&h->ev1s[1]) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_done[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_done[1], cudaEventDisableTiming) != cudaSuccess) {
         delete h;
         return vb_fail("vb_create: stream/event creation failed");
     }
@@ -258,10 +263,9 @@ extern "C" void vb_destroy(vb_index* h) {
                       &h->sp_term, &h->sp_val, &h->post_row, &h->post_val, &h->args, &h->mask, &h->cand, &h->lists,
                       &h->offs, &h->out, &h->q_hat, &h->q_bf16, &h->tmp})
         dev_free(h, *b);
-    for (HostBuf* b : {&h->h_args, &h->h_out, &h->h_stage}) if (b->p) cudaFreeHost(b->p);
+    for (HostBuf* b : {&h->h_args_s[0], &h->h_args_s[1], &h->h_out_s[0], &h->h_out_s[1], &h->h_stage}) if (b->p) cudaFreeHost(b->p);
     for (auto ev : h->prof_events) cudaEventDestroy(ev);
-    cudaEventDestroy(h->ev0);
-    cudaEventDestroy(h->ev1);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev0s[i]); cudaEventDestroy(h->ev1s[i]); cudaEventDestroy(h->ev_done[i]); }
     cudaEventDestroy(h->ev_fork);
     cudaEventDestroy(h->ev_join);
     cudaStreamDestroy(h->aux_stream);
@@ -278,6 +282,7 @@ extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
     else if (k == "seg_ratio") h->opt_seg_ratio = std::max<int64_t>(2, value);
     else if (k == "safe_mode") h->opt_safe_mode = value;
     else if (k == "profile") h->opt_profile = value;
+    else if (k == "slot") h->cur = value ? 1 : 0;                   // which of the two in-flight batches the staged calls address
     else if (k == "overlap") h->opt_overlap = value;               // 1: dense and sparse chains on two streams
     else if (k == "k2_precision") h->opt_k2_precision = value;   // 0 auto, 1 bf16 query, 2 bf16x2 (hi+lo) query
     else if (k == "stream") {   // run on the caller's stream (e.g. torch's current stream); 0 = own stream
@@ -735,9 +740,9 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     std::vector<size_t> o_bits(b.n_filters, 0);
     for (uint32_t f = 0; f < b.n_filters; ++f)
         if (flt[f].scope_bits) o_bits[f] = ar.take((size_t)flt[f].scope_words * 4);
-    TRY(host_reserve(h->h_args, ar.off));
+    TRY(host_reserve(h->h_args_s[h->cur], ar.off));
     TRY(dev_reserve(h, h->args, ar.off, false));
-    unsigned char* hp = h->h_args.as<unsigned char>();
+    unsigned char* hp = h->h_args_s[h->cur].as<unsigned char>();
     unsigned char* dp = h->args.as<unsigned char>();
     memcpy(hp + o_q, q->dense, (size_t)b.B * h->dim * 4);
     memcpy(hp + o_ip, indptr.data(), (b.B + 1) * 8);
@@ -789,7 +794,7 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     b.o_keys = ao.take((size_t)b.n_lists * b.k * 8);
     b.out_bytes = ao.off;
     TRY(dev_reserve(h, h->out, b.out_bytes, false));
-    TRY(host_reserve(h->h_out, b.out_bytes));
+    TRY(host_reserve(h->h_out_s[h->cur], b.out_bytes));
     b.valid = true;
     return 0;
 }
@@ -996,19 +1001,21 @@ static int fuse_stage(vb_index* h, const Batch& b) {
     prof_end(h);
     CK(cudaMemcpy2DAsync(dp + b.o_lcnt, 4, b.cnt, VB_SUB * 4, 4, b.n_lists, cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaMemcpyAsync(dp + b.o_ovf, b.overflow, (size_t)b.n_lists * 4, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaEventRecord(h->ev1s[h->cur], h->stream));
+    // results go to this slot's pinned buffer right away, so a pipelined caller's fetch does not
+    // queue behind the next batch's kernels
+    const size_t bytes = b.want_branches ? b.out_bytes : b.o_keys;
+    h->stats.last_d2h_bytes = bytes;
+    CK(cudaMemcpyAsync(h->h_out_s[h->cur].p, dp, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(h->ev_done[h->cur], h->stream));
     return 0;
 }
 
 // D2H of the result block, sync, decode into the caller's arrays.
 // *overflowed = 1 if any list overflowed during scoring (caller re-runs in safe mode).
 static int fetch_stage(vb_index* h, const Batch& b, vb_result* out, int* overflowed) {
-    unsigned char* dp = h->out.as<unsigned char>();
-    unsigned char* hp = h->h_out.as<unsigned char>();
-    const size_t bytes = b.want_branches ? b.out_bytes : b.o_keys;
-    h->stats.last_d2h_bytes = bytes;
-    CK(cudaMemcpyAsync(hp, dp, bytes, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    unsigned char* hp = h->h_out_s[h->cur].as<unsigned char>();
+    CK(cudaEventSynchronize(h->ev_done[h->cur]));
     const uint32_t* ovf = reinterpret_cast<const uint32_t*>(hp + b.o_ovf);
     *overflowed = 0;
     for (uint32_t i = 0; i < b.n_lists; ++i) if (ovf[i]) *overflowed = 1;
@@ -1052,7 +1059,7 @@ static int fetch_stage(vb_index* h, const Batch& b, vb_result* out, int* overflo
 
 static void finish_stats(vb_index* h, const Batch& b) {
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    cudaEventElapsedTime(&ms, h->ev0s[h->cur], h->ev1s[h->cur]);
     h->stats.last_search_ms = ms;
     h->stats.searches += 1;
     h->stats.queries += b.B;
@@ -1077,26 +1084,26 @@ extern "C" int vb_stage(vb_index* h, const vb_query_batch* q, int32_t want_branc
     TRY(validate_batch(h, q));
     std::lock_guard<std::mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
-    h->staged.valid = false;
-    TRY(prepare_batch(h, q, h->staged, need_corpus != 0));
-    h->staged.want_branches = want_branches != 0;
+    h->staged_s[h->cur].valid = false;
+    TRY(prepare_batch(h, q, h->staged_s[h->cur], need_corpus != 0));
+    h->staged_s[h->cur].want_branches = want_branches != 0;
     return 0;
 }
 
 extern "C" int vb_run_local(vb_index* h, uint64_t* cand_dev) {
     if (!h) return vb_fail("vb_run_local: NULL index");
     std::lock_guard<std::mutex> lk(h->mu);
-    if (!h->staged.valid) return vb_fail("vb_run_local: no staged batch");
+    if (!h->staged_s[h->cur].valid) return vb_fail("vb_run_local: no staged batch");
     CK(cudaSetDevice(h->device));
     h->stats.last_launches = 0;
-    CK(cudaEventRecord(h->ev0, h->stream));
+    CK(cudaEventRecord(h->ev0s[h->cur], h->stream));
     if (h->n_rows == 0) {
-        TRY(init_lists(h, h->staged, 0));
+        TRY(init_lists(h, h->staged_s[h->cur], 0));
     } else {
-        TRY(run_branches(h, h->staged, h->staged_safe));
+        TRY(run_branches(h, h->staged_s[h->cur], h->staged_safe));
     }
     if (cand_dev) {
-        vb_export_kernel<<<h->staged.n_lists, 128, 0, h->stream>>>(h->cand.as<uint64_t>(), h->staged.cnt, h->cand_cap, h->staged.k, cand_dev, h->staged.overflow, h->staged.n_lists);
+        vb_export_kernel<<<h->staged_s[h->cur].n_lists, 128, 0, h->stream>>>(h->cand.as<uint64_t>(), h->staged_s[h->cur].cnt, h->cand_cap, h->staged_s[h->cur].k, cand_dev, h->staged_s[h->cur].overflow, h->staged_s[h->cur].n_lists);
         CKK("vb_export_kernel");
         ++h->stats.last_launches;
     }
@@ -1106,7 +1113,7 @@ extern "C" int vb_run_local(vb_index* h, uint64_t* cand_dev) {
 extern "C" int vb_run_fuse(vb_index* h, uint32_t n_shards, const uint64_t* gathered_dev) {
     if (!h) return vb_fail("vb_run_fuse: NULL index");
     std::lock_guard<std::mutex> lk(h->mu);
-    Batch& b = h->staged;
+    Batch& b = h->staged_s[h->cur];
     if (!b.valid) return vb_fail("vb_run_fuse: no staged batch");
     CK(cudaSetDevice(h->device));
     if (gathered_dev) {
@@ -1126,11 +1133,11 @@ extern "C" int vb_run_fuse(vb_index* h, uint32_t n_shards, const uint64_t* gathe
 extern "C" int vb_fetch(vb_index* h, vb_result* out, int32_t* overflowed) {
     if (!h) return vb_fail("vb_fetch: NULL index");
     std::lock_guard<std::mutex> lk(h->mu);
-    if (!h->staged.valid) return vb_fail("vb_fetch: no staged batch");
+    if (!h->staged_s[h->cur].valid) return vb_fail("vb_fetch: no staged batch");
     CK(cudaSetDevice(h->device));
     int ovf = 0;
-    TRY(fetch_stage(h, h->staged, out, &ovf));
-    finish_stats(h, h->staged);
+    TRY(fetch_stage(h, h->staged_s[h->cur], out, &ovf));
+    finish_stats(h, h->staged_s[h->cur]);
     if (overflowed) *overflowed = ovf;
     return 0;
 }
@@ -1167,13 +1174,13 @@ extern "C" int vb_search_local(vb_index* h, const vb_query_batch* q, uint64_t* c
         h->staged_safe = false;
         TRY(rc);
         // overflow flags
-        TRY(host_reserve(h->h_stage, (size_t)h->staged.n_lists * 4));
-        CK(cudaMemcpyAsync(h->h_stage.p, h->staged.overflow, (size_t)h->staged.n_lists * 4, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaEventRecord(h->ev1, h->stream));
+        TRY(host_reserve(h->h_stage, (size_t)h->staged_s[h->cur].n_lists * 4));
+        CK(cudaMemcpyAsync(h->h_stage.p, h->staged_s[h->cur].overflow, (size_t)h->staged_s[h->cur].n_lists * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(h->ev1s[h->cur], h->stream));
         CK(cudaStreamSynchronize(h->stream));
-        finish_stats(h, h->staged);
+        finish_stats(h, h->staged_s[h->cur]);
         bool ovf = false;
-        for (uint32_t i = 0; i < h->staged.n_lists; ++i) ovf |= h->h_stage.as<uint32_t>()[i] != 0;
+        for (uint32_t i = 0; i < h->staged_s[h->cur].n_lists; ++i) ovf |= h->h_stage.as<uint32_t>()[i] != 0;
         if (!ovf) return 0;
         if (attempt == 1) return vb_fail("vb_search_local: candidate list overflow even in safe mode (internal error)");
         ++h->stats.overflow_reruns;
@@ -1185,9 +1192,9 @@ extern "C" int vb_merge_fuse(vb_index* h, const vb_query_batch* q, uint32_t n_sh
     if (!h || !gathered_dev || !out) return vb_fail("vb_merge_fuse: NULL argument");
     TRY(validate_batch(h, q));
     TRY(vb_stage(h, q, wants_branches(out), 0));
-    CK(cudaEventRecord(h->ev0, h->stream));
+    CK(cudaEventRecord(h->ev0s[h->cur], h->stream));
     h->stats.last_launches = 0;
-    TRY(init_lists(h, h->staged, 0));
+    TRY(init_lists(h, h->staged_s[h->cur], 0));
     TRY(vb_run_fuse(h, n_shards, gathered_dev));
     int32_t overflowed = 0;
     TRY(vb_fetch(h, out, &overflowed));

@@ -342,6 +342,35 @@ class Index:
         self._check(self._lib.vb_search(self._h, C.byref(packed.c), C.byref(cres)))
         return res
 
+    def search_stream(self, packed_iter):
+        """Pipelined vb_stage/run/fetch over a stream of prepared batches (two in flight): the host
+        work and H2D copy of batch i+1 overlap the kernels of batch i.  Yields results in order.
+        Every batch still pays its own H2D and D2H copy."""
+        prev = None
+        slot = 0
+        try:
+            for packed in packed_iter:
+                self.set_option("slot", slot)
+                staged = self.stage_packed(packed)
+                self.run_local(None)
+                self.run_fuse(0, None)
+                if prev is not None:
+                    self.set_option("slot", slot ^ 1)
+                    res = self.fetch(prev, allow_overflow=True)
+                    if res is None:
+                        raise B200Error("candidate overflow in a pipelined search; use search_packed for this batch")
+                    yield res
+                prev = staged
+                slot ^= 1
+            if prev is not None:
+                self.set_option("slot", slot ^ 1)
+                res = self.fetch(prev, allow_overflow=True)
+                if res is None:
+                    raise B200Error("candidate overflow in a pipelined search; use search_packed for this batch")
+                yield res
+        finally:
+            self.set_option("slot", 0)
+
     def search_local(self, cand_dev_ptr: int, queries, sparse=None, filters=None, filter_of=None, limit: int = 10,
                      kprime: int | None = None, fusion: str | int = "weighted", sparse_weight: float = 0.1):
         """Shard-local branch top-k' left on the device (all-gather payload); weights carry global IDF."""

@@ -162,9 +162,35 @@ class ShardedIndex:
             self.index.set_option("safe_mode", 0)
         raise RuntimeError("candidate list overflow even in safe mode")
 
-    def run_staged(self, staged, B: int, kprime: int):
-        """Device part of one sharded search on an already staged batch: local branches ->
-        all-gather of the candidate blocks (the path's ONE exchange step) -> merge -> fuse -> fetch."""
+    def search_stream(self, packed_iter):
+        """Pipelined ``search_packed`` over a stream of prepared batches (two in flight per rank):
+        staging + H2D of batch i+1 overlap the kernels / all-gather of batch i.  Yields in order."""
+        prev = None
+        slot = 0
+        try:
+            for packed in packed_iter:
+                self.index.set_option("slot", slot)
+                staged = self.index.stage_packed(packed)
+                self._enqueue(packed.B, packed.kprime)
+                if prev is not None:
+                    self.index.set_option("slot", slot ^ 1)
+                    res = self.index.fetch(prev, allow_overflow=True)
+                    if res is None:
+                        raise RuntimeError("candidate overflow in a pipelined search; use search_packed")
+                    yield res
+                prev = staged
+                slot ^= 1
+            if prev is not None:
+                self.index.set_option("slot", slot ^ 1)
+                res = self.index.fetch(prev, allow_overflow=True)
+                if res is None:
+                    raise RuntimeError("candidate overflow in a pipelined search; use search_packed")
+                yield res
+        finally:
+            self.index.set_option("slot", 0)
+
+    def _enqueue(self, B: int, kprime: int):
+        """local branches -> all-gather -> merge + fuse, all asynchronous on this rank's stream."""
         words = self.index.cand_block_words(B, kprime)
         local = self._buf("local", words)
         gathered = self._buf("gathered", words * self.world)
@@ -175,4 +201,9 @@ class ShardedIndex:
             else:
                 gathered.copy_(local)
             self.index.run_fuse(self.world, gathered.data_ptr())
+
+    def run_staged(self, staged, B: int, kprime: int):
+        """Device part of one sharded search on an already staged batch: local branches ->
+        all-gather of the candidate blocks (the path's ONE exchange step) -> merge -> fuse -> fetch."""
+        self._enqueue(B, kprime)
         return self.index.fetch(staged, allow_overflow=True)
