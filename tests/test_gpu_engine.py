@@ -357,3 +357,59 @@ def test_edge_cases(world):
     with pytest.raises(eng.B200Error):
         e.delete_rows([99])
     e.close()
+
+
+def test_large_batch_hybrid_against_oracle():
+    """BASELINE cfg2 shape scaled down (300k x 128, B = 64, hybrid RRF + weighted): exercises the
+    tcgen05 path with several segments, the sub-range append counters, the two-stream schedule and
+    the pipelined stream API; checked row by row against the C oracle."""
+    from voitta_rag_b200 import engine
+    rng = np.random.RandomState(5)
+    n, dim, B = 300_000, 128, 64
+    cents = rng.randn(512, dim).astype(np.float32)
+    dense = cents[rng.randint(0, 512, size=n)] + 0.5 * rng.randn(n, dim).astype(np.float32)
+    dense = _data.bf16_round(dense)
+    # sparse rows: 12 terms from a Zipf vocabulary of 20k hashed ids
+    vocab = np.unique(rng.randint(1, 2**31 - 1, size=40000).astype(np.int64))[:20000]
+    p = 1.0 / np.arange(1, len(vocab) + 1) ** 1.07
+    p /= p.sum()
+    L = 12
+    picks = rng.choice(len(vocab), size=(n, L), p=p)
+    picks.sort(axis=1)
+    keep = np.ones((n, L), bool); keep[:, 1:] = picks[:, 1:] != picks[:, :-1]
+    terms_sorted_ids = np.argsort(np.argsort(vocab))            # rank of each vocab entry by hashed id
+    hashed = np.sort(vocab)
+    rows_terms = [np.unique(hashed[terms_sorted_ids[picks[r][keep[r]]]]) for r in range(n)]
+    indptr = np.zeros(n + 1, np.int64); np.cumsum([len(t) for t in rows_terms], out=indptr[1:])
+    terms = np.concatenate(rows_terms).astype(np.uint32)
+    vals = (1.0 + rng.rand(len(terms))).astype(np.float32)
+    scope = rng.randint(0, 64, size=n).astype(np.uint32)
+    modified = rng.randint(1420070400, 1767225600, size=n).astype(np.int64)
+    ix = engine.Index(dim)
+    ix.upsert(dense, (indptr, terms, vals), scope, None, modified)
+    cc = oracle_c.CorpusC(dense, (indptr, terms, vals), scope, None, modified)
+    qrows = rng.randint(0, n, size=B)
+    Q = _data.bf16_round(dense[qrows] + 0.3 * rng.randn(B, dim).astype(np.float32))
+    SP = [(rows_terms[r][:6].tolist() + [int(hashed[rng.randint(0, len(hashed))])], [1.0] * 7) for r in qrows]
+    SP = [(list(dict.fromkeys(t)), [1.0] * len(dict.fromkeys(t))) for t, _ in SP]
+    bits = np.zeros(2, np.uint32); bits[0] = 0x0F0F0F0F; bits[1] = 0xFFFF0000
+    flt = (bits, 2, 1500000000, 1767225600)
+    fo = np.zeros(B, np.int32)
+    for fusion, fz in (("rrf", 2), ("weighted", 1)):
+        got = ix.search_batch(Q, SP, [engine.Filter(*flt)], fo, limit=10, fusion=fusion, branches=True)
+        assert ix.stats()["last_dense_path"] == 2
+        want = cc.search_batch(Q, SP, [flt], fo, limit=10, fusion=fz)
+        for i in range(B):
+            wd = [(int(want["dense_rows"][i, j]), float(want["dense_scores"][i, j])) for j in range(want["dense_counts"][i])]
+            assert_same_ranking(got.branch(i, "dense"), wd, rel_tol=2e-5, abs_tol=2e-5, what=f"dense q{i}")
+            ws = [(int(want["sparse_rows"][i, j]), float(want["sparse_scores"][i, j])) for j in range(want["sparse_counts"][i])]
+            assert_same_ranking(got.branch(i, "sparse"), ws, rel_tol=0.0, what=f"sparse q{i}")
+            fusion_bit_exact(got, i, 10, fusion, 0.1)
+    # the pipelined stream API returns the same answers as the one-call API
+    packed = [ix.pack(Q[j:j + 16], SP[j:j + 16], [engine.Filter(*flt)], np.zeros(16, np.int32), limit=10, fusion="rrf")
+              for j in range(0, B, 16)]
+    one = [ix.search_batch(Q[j:j + 16], SP[j:j + 16], [engine.Filter(*flt)], np.zeros(16, np.int32), limit=10, fusion="rrf")
+           for j in range(0, B, 16)]
+    for a, b in zip(ix.search_stream(iter(packed)), one):
+        assert np.array_equal(a.rows, b.rows) and np.array_equal(a.scores, b.scores) and np.array_equal(a.counts, b.counts)
+    ix.close()

@@ -49,6 +49,11 @@ __device__ __forceinline__ void vb_push(const VbLists& L, uint32_t list, float s
     if (slot < L.sub_cap) L.cand[(size_t)list * L.cap + (size_t)sub * L.sub_cap + slot] = vb_pack_key(score, row);
 }
 
+__device__ __forceinline__ void vb_push_sub(const VbLists& L, uint32_t list, uint32_t sub, float score, uint32_t row) {
+    const uint32_t slot = atomicAdd(&L.cnt[list * VB_SUB + sub], 1u);
+    if (slot < L.sub_cap) L.cand[(size_t)list * L.cap + (size_t)sub * L.sub_cap + slot] = vb_pack_key(score, row);
+}
+
 __device__ __forceinline__ uint4 vb_ldg_stream(const uint4* p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"

@@ -53,7 +53,8 @@ vb_posting_split_kernel(const uint64_t* __restrict__ keys, uint64_t nnz, uint32_
 }
 
 // ---- per-batch slice table ----------------------------------------------------------------------
-// off[j][b] = first posting of query-term j whose row >= b*VB_ROWS_PER_BLOCK  (b = 0..n_blocks).
+// off[b][j] = first posting of query-term j whose row >= b*VB_ROWS_PER_BLOCK  (b = 0..n_blocks),
+// block-major so that the CTA of (row block, query) reads its terms' bounds as two contiguous runs.
 // Posting offsets fit 32 bits (a shard holds < 2^31 postings).
 __global__ void __launch_bounds__(256)
 vb_slice_kernel(const uint32_t* __restrict__ post_row, const uint32_t* __restrict__ qt_lo,
@@ -62,8 +63,8 @@ vb_slice_kernel(const uint32_t* __restrict__ post_row, const uint32_t* __restric
 {
     const uint64_t total = (uint64_t)n_qterms * (n_blocks + 1u);
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t j = (uint32_t)(i / (n_blocks + 1u));
-        const uint32_t b = (uint32_t)(i % (n_blocks + 1u));
+        const uint32_t b = (uint32_t)(i / n_qterms);
+        const uint32_t j = (uint32_t)(i % n_qterms);
         uint32_t lo = qt_lo[j], hi = qt_hi[j];
         const uint64_t target = (uint64_t)b * VB_ROWS_PER_BLOCK;
         while (lo < hi) {
@@ -77,7 +78,7 @@ vb_slice_kernel(const uint32_t* __restrict__ post_row, const uint32_t* __restric
 struct VbSparseArgs {
     const uint32_t* post_row;
     const float* post_val;
-    const uint32_t* off;        // [n_qterms][n_blocks+1]
+    const uint32_t* off;        // [n_blocks+1][n_qterms]
     const int64_t* q_indptr;    // [B+1] into the sorted query-term arrays
     const double* q_weight;     // [n_qterms] idf-scaled query values, ascending term id per query
     const uint32_t* mask;       // [n_filters][mask_words] or nullptr
@@ -85,7 +86,8 @@ struct VbSparseArgs {
     const float* tau;
     VbLists lists;
     uint32_t mask_words;
-    uint32_t n_blocks;          // row blocks in the whole index
+    uint32_t n_qterms;          // query terms of the whole batch (row length of `off`)
+    uint32_t nt_max;            // most terms of any query of the batch (sizes the shared term table)
     uint32_t blk_begin;         // first row block of this segment
     uint32_t n_queries;
     uint32_t n_rows;
@@ -94,88 +96,146 @@ struct VbSparseArgs {
 };
 
 #define VB_SPARSE_THREADS 128
-#define VB_SPARSE_UNROLL 2
+#define VB_SPARSE_U 4u                                          // postings per thread per batch
+#define VB_SPARSE_BATCH (VB_SPARSE_U * VB_SPARSE_THREADS)       // 512 postings per batch
+#define VB_SPARSE_PAD 32u                                       // dummy accumulators for padding lanes
+
+static size_t vb_sparse_smem_bytes(uint32_t nt_max) {
+    return (size_t)(VB_ROWS_PER_BLOCK + VB_SPARSE_PAD) * 8u + (size_t)nt_max * 18u + 32u;
+}
 
 // grid.x = (#blocks in segment) * B ; CTA (blk, q) with q fastest so that concurrently running
-// CTAs share a row block (and the posting slices of common terms hit L2).  The kernel is
-// instruction/latency-bound, not bandwidth-bound, so it (1) fetches all slice bounds of the query
-// for this block in one parallel step, (2) keeps only the non-empty terms, (3) software-pipelines
-// the posting loads one step ahead of the shared-memory accumulation and (4) keeps the per-posting
-// instruction count minimal:
+// CTAs share a row block (and the posting slices of common terms hit L2).
+//
+// One CTA's work is small (a few thousand postings in ~6 non-empty slices, 2048 fp64
+// accumulators); the kernel is bound by memory latency and instruction issue, not bandwidth:
+//   * the slice bounds of all the query's terms for this block arrive in one parallel step
+//     (block-major slice table) and only the non-empty terms are kept, in ascending term id;
+//   * postings are fetched in batches of 512 (4 per thread, all loads issued back to back), and the
+//     batch after the current one — the rest of the slice or the head of the NEXT term's slice —
+//     is already in flight while the current one is accumulated, so the L2/HBM latency is paid
+//     about once per CTA instead of once per term;
+//   * padding lanes accumulate into private dummy slots, so the accumulate code is branch-free;
+//   * terms are applied in ascending term id with one barrier between terms (within a term a row
+//     occurs once: no atomics).  That is the summation order of the reference's two-pointer
+//     merge, and the arithmetic is explicit fp64 mul, add.
 //   accumulators start at -0.0 and every product is canonicalised with "+ 0.0", so
 //   acc = acc + (w*v + 0.0) reproduces Python's `result = 0.0; result += w*v` bit for bit (the only
 //   differences would involve -0.0, which both sides turn into +0.0) while an untouched row is
-//   still recognisable (-0.0 can never be a sum); padding lanes accumulate 0 into a dummy slot.
-__global__ void __launch_bounds__(VB_SPARSE_THREADS)
+//   still recognisable (-0.0 can never be a sum).
+__global__ void __launch_bounds__(VB_SPARSE_THREADS, 10)
 vb_sparse_kernel(const VbSparseArgs a)
 {
-    __shared__ __align__(16) double acc[VB_ROWS_PER_BLOCK + 2]; // (+2: 16-byte aligned pairs for the scan)
-    __shared__ uint32_t s_lo[256], s_hi[256];                   // VB_MAX_QUERY_TERMS slices of this block
-    __shared__ double s_w[256];
-    __shared__ uint16_t s_nz[256];                              // non-empty terms, ascending term id
+    extern __shared__ __align__(16) unsigned char vb_sp_smem[];
+    double* acc = reinterpret_cast<double*>(vb_sp_smem);                    // [VB_ROWS_PER_BLOCK + VB_SPARSE_PAD]
+    double* s_w = acc + VB_ROWS_PER_BLOCK + VB_SPARSE_PAD;                  // [nt_max]
+    uint32_t* s_lo = reinterpret_cast<uint32_t*>(s_w + a.nt_max);           // [nt_max]
+    uint32_t* s_hi = s_lo + a.nt_max;                                       // [nt_max]
+    uint16_t* s_nz = reinterpret_cast<uint16_t*>(s_hi + a.nt_max);          // [nt_max] non-empty terms, ascending
     __shared__ uint32_t s_nnz;
 
+    const uint32_t tid = threadIdx.x;
     const uint32_t q = blockIdx.x % a.n_queries;
-    const uint32_t blk = a.blk_begin + blockIdx.x / a.n_queries;
-    const int64_t t_lo = a.q_indptr[q];
-    const uint32_t nt = (uint32_t)(a.q_indptr[q + 1] - t_lo);
+    const uint32_t blk_rel = blockIdx.x / a.n_queries;
+    const uint32_t blk = a.blk_begin + blk_rel;
+    const uint32_t t_lo = (uint32_t)__ldg(a.q_indptr + q);
+    const uint32_t nt = (uint32_t)__ldg(a.q_indptr + q + 1) - t_lo;
     if (nt == 0) return;                                        // dense-only query
 
-    for (uint32_t j = threadIdx.x; j < nt; j += blockDim.x) {
-        const uint32_t* o = a.off + (size_t)(t_lo + j) * (a.n_blocks + 1u) + blk;
-        s_lo[j] = o[0];
-        s_hi[j] = o[1];
-        s_w[j] = a.q_weight[t_lo + j];
+    for (uint32_t j = tid; j < nt; j += VB_SPARSE_THREADS) {
+        s_lo[j] = __ldg(a.off + (size_t)blk * a.n_qterms + t_lo + j);
+        s_hi[j] = __ldg(a.off + (size_t)(blk + 1u) * a.n_qterms + t_lo + j);
+        s_w[j] = __ldg(a.q_weight + t_lo + j);
     }
-    __syncthreads();
-    if (threadIdx.x < 32) {                                     // ordered compaction of the non-empty terms
-        uint32_t base = 0;
-        for (uint32_t j0 = 0; j0 < nt; j0 += 32) {
-            const uint32_t j = j0 + threadIdx.x;
-            const bool ne = j < nt && s_hi[j] > s_lo[j];
-            const uint32_t bal = __ballot_sync(0xffffffffu, ne);
-            if (ne) s_nz[base + __popc(bal & ((1u << threadIdx.x) - 1u))] = (uint16_t)j;
-            base += __popc(bal);
-        }
-        if (threadIdx.x == 0) s_nnz = base;
+    const uint32_t list = a.n_queries + q;                      // sparse lists follow the dense ones
+    const float tau = a.tau[list];
+    const uint32_t* mask = nullptr;
+    if (a.mask != nullptr && a.mask_of != nullptr) {
+        const int32_t f = __ldg(a.mask_of + q);
+        if (f >= 0) mask = a.mask + (size_t)f * a.mask_words;
     }
     const double neg_zero = __longlong_as_double((long long)VB_ACC_SENTINEL);
-    for (uint32_t r = 2u * threadIdx.x; r < VB_ROWS_PER_BLOCK; r += 2u * blockDim.x)
+#pragma unroll
+    for (uint32_t r = 2u * tid; r < VB_ROWS_PER_BLOCK + VB_SPARSE_PAD; r += 2u * VB_SPARSE_THREADS)
         *reinterpret_cast<double2*>(&acc[r]) = make_double2(neg_zero, neg_zero);
+    __syncthreads();
+    if (tid < 32u) {                                            // ordered compaction of the non-empty terms
+        uint32_t base = 0;
+        for (uint32_t j0 = 0; j0 < nt; j0 += 32u) {
+            const uint32_t j = j0 + tid;
+            const bool ne = j < nt && s_hi[j] > s_lo[j];
+            const uint32_t bal = __ballot_sync(0xffffffffu, ne);
+            if (ne) s_nz[base + __popc(bal & ((1u << tid) - 1u))] = (uint16_t)j;
+            base += __popc(bal);
+        }
+        if (tid == 0) s_nnz = base;
+    }
     __syncthreads();
     const uint32_t nnz = s_nnz;
     if (nnz == 0) return;                                       // (direct-mode slots were zeroed by the host)
 
     const uint32_t row0 = blk * VB_ROWS_PER_BLOCK;
-    // Non-empty terms in ascending term id; inside one term every row occurs once, so the
-    // read-modify-write needs no atomics.  The kernel is issue-bound: the loop is kept minimal and
-    // the (many) resident CTAs hide the load latency at each term start.
-    for (uint32_t ti = 0; ti < nnz; ++ti) {
-        const uint32_t term = s_nz[ti];
-        const double w = s_w[term];
-        const uint32_t lo = s_lo[term], hi = s_hi[term];
-#pragma unroll 2
-        for (uint32_t p = lo + threadIdx.x; p < hi; p += VB_SPARSE_THREADS) {
-            const uint32_t r = __ldg(a.post_row + p) - row0;
-            const float v = __ldg(a.post_val + p);
-            acc[r] = __dadd_rn(acc[r], __dadd_rn(__dmul_rn(w, (double)v), 0.0));
+    const uint32_t dummy = VB_ROWS_PER_BLOCK + (tid & 31u);     // this lane's private padding slot
+    const uint32_t* __restrict__ prow = a.post_row;
+    const float* __restrict__ pval = a.post_val;
+
+    // fetch: postings p0 + tid + 128*u (u < 4) of a slice ending at hi; padding lanes get the dummy slot
+    auto fetch = [&](uint32_t p0, uint32_t hi, uint32_t (&fr)[VB_SPARSE_U], float (&fv)[VB_SPARSE_U]) {
+#pragma unroll
+        for (uint32_t u = 0; u < VB_SPARSE_U; ++u) {
+            const uint32_t p = p0 + tid + u * VB_SPARSE_THREADS;
+            const bool ok = p < hi;
+            fr[u] = ok ? __ldg(prow + p) : row0 + dummy;
+            fv[u] = ok ? __ldg(pval + p) : 0.0f;
         }
-        __syncthreads();                                        // the next term may hit the same rows
+    };
+    // accumulate one batch; u-groups past the end of the slice are skipped (uniform per warp)
+    auto rmw = [&](uint32_t p0, uint32_t hi, double w, const uint32_t (&fr)[VB_SPARSE_U], const float (&fv)[VB_SPARSE_U]) {
+        const uint32_t wbase = p0 + (tid & ~31u);
+#pragma unroll
+        for (uint32_t u = 0; u < VB_SPARSE_U; ++u) {
+            if (wbase + u * VB_SPARSE_THREADS < hi) {
+                const uint32_t r = fr[u] - row0;
+                acc[r] = __dadd_rn(acc[r], __dadd_rn(__dmul_rn(w, (double)fv[u]), 0.0));
+            }
+        }
+    };
+
+    {
+        uint32_t rA[VB_SPARSE_U], rB[VB_SPARSE_U];
+        float vA[VB_SPARSE_U], vB[VB_SPARSE_U];
+        uint32_t ti = 0, term = s_nz[0], p0 = s_lo[term], hi = s_hi[term];
+        fetch(p0, hi, rA, vA);
+        for (;;) {
+            // ---- A holds (term ti, p0); find the batch after it and put it in flight into B ----
+            uint32_t n_ti = ti, n_p0 = p0 + VB_SPARSE_BATCH, n_hi = hi;
+            if (n_p0 >= hi) { n_ti = ti + 1u; if (n_ti < nnz) { const uint32_t t2 = s_nz[n_ti]; n_p0 = s_lo[t2]; n_hi = s_hi[t2]; } }
+            const bool more = n_ti < nnz;
+            if (more) fetch(n_p0, n_hi, rB, vB);
+            rmw(p0, hi, s_w[term], rA, vA);
+            if (n_ti != ti) __syncthreads();                    // the next term may hit the same rows
+            if (!more) break;
+            ti = n_ti; p0 = n_p0; hi = n_hi; term = s_nz[ti];
+            // ---- B holds (term ti, p0); same step with the roles swapped ----
+            n_ti = ti; n_p0 = p0 + VB_SPARSE_BATCH; n_hi = hi;
+            if (n_p0 >= hi) { n_ti = ti + 1u; if (n_ti < nnz) { const uint32_t t2 = s_nz[n_ti]; n_p0 = s_lo[t2]; n_hi = s_hi[t2]; } }
+            const bool more2 = n_ti < nnz;
+            if (more2) fetch(n_p0, n_hi, rA, vA);
+            rmw(p0, hi, s_w[term], rB, vB);
+            if (n_ti != ti) __syncthreads();
+            if (!more2) break;
+            ti = n_ti; p0 = n_p0; hi = n_hi; term = s_nz[ti];
+        }
     }
 
-    const uint32_t list = a.n_queries + q;                      // sparse lists follow the dense ones
-    const float tau = a.tau[list];
-    const uint32_t* mask = nullptr;
-    if (a.mask != nullptr && a.mask_of != nullptr) {
-        const int32_t f = a.mask_of[q];
-        if (f >= 0) mask = a.mask + (size_t)f * a.mask_words;
-    }
     const uint32_t seg_row0 = a.blk_begin * VB_ROWS_PER_BLOCK;
+    const uint32_t sub = blk_rel & a.lists.sub_mask;            // append counter of this row block
     // Scan two accumulators per thread per step.  Cheap exact prefilter in fp64: rounding to fp32 is
     // monotone, so cur < (double)tau implies float(cur) <= tau — such rows (the vast majority once
     // tau is established, and every untouched -0.0 row when tau >= 0) are dropped with one compare.
     const double tau_d = (double)tau;
-    for (uint32_t r = 2u * threadIdx.x; r < VB_ROWS_PER_BLOCK; r += 2u * blockDim.x) {
+#pragma unroll 4
+    for (uint32_t r = 2u * tid; r < VB_ROWS_PER_BLOCK; r += 2u * VB_SPARSE_THREADS) {
         const double2 c2 = *reinterpret_cast<const double2*>(&acc[r]);
         const double cv[2] = {c2.x, c2.y};
         if (!a.direct && c2.x < tau_d && c2.y < tau_d) continue;
@@ -190,7 +250,7 @@ vb_sparse_kernel(const VbSparseArgs a)
             if (a.direct) {
                 if (row < a.n_rows) a.lists.cand[(size_t)list * a.lists.cap + (row - seg_row0)] = pass ? vb_pack_key(s, a.row_base + row) : 0ull;
             } else if (pass) {
-                vb_push(a.lists, list, s, a.row_base + row);
+                vb_push_sub(a.lists, list, sub, s, a.row_base + row);
             }
         }
     }

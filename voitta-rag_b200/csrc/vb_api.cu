@@ -70,7 +70,7 @@ struct HostBuf {
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Batch {
-    uint32_t B = 0, k = 0, limit = 0, n_lists = 0, n_qterms = 0, n_filters = 0, mask_words = 0, n_blocks = 0;
+    uint32_t B = 0, k = 0, limit = 0, n_lists = 0, n_qterms = 0, nt_max = 1, n_filters = 0, mask_words = 0, n_blocks = 0;
     bool any_sparse = false, use_mask = false;
     std::vector<int32_t> mode, mask_of_host;
     // device pointers into h->args
@@ -693,6 +693,7 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
                 qhi.push_back((uint32_t)phi);
             }
             indptr[i + 1] = (int64_t)weight.size();
+            b.nt_max = std::max<uint32_t>(b.nt_max, (uint32_t)(indptr[i + 1] - indptr[i]));
             if (hi > lo) { b.mode[i] = q->fusion; b.any_sparse = true; }
         }
     }
@@ -940,10 +941,10 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
             a.q_indptr = b.d_qindptr; a.q_weight = b.d_qweight;
             a.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; a.mask_of = b.use_mask ? b.d_maskof : nullptr;
             a.tau = b.tau; a.lists = L; a.mask_words = b.mask_words;
-            a.n_blocks = b.n_blocks; a.blk_begin = r0 / VB_ROWS_PER_BLOCK; a.n_queries = b.B; a.n_rows = n;
+            a.n_qterms = b.n_qterms; a.nt_max = b.nt_max; a.blk_begin = r0 / VB_ROWS_PER_BLOCK; a.n_queries = b.B; a.n_rows = n;
             a.row_base = (uint32_t)h->row_base; a.direct = direct;
             const uint32_t nblk = (r1 - r0 + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK;
-            vb_sparse_kernel<<<nblk * b.B, VB_SPARSE_THREADS, 0, ss>>>(a);
+            vb_sparse_kernel<<<nblk * b.B, VB_SPARSE_THREADS, vb_sparse_smem_bytes(b.nt_max), ss>>>(a);
             CKK("vb_sparse_kernel");
             ++h->stats.last_launches;
             prof_end(h, pi, ss);
