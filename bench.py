@@ -46,6 +46,10 @@ WORKLOADS = {
                        desc="10M x 768-d hybrid, scope+time filter 1%, batch 1"),
     "cfg3-b256-s50": dict(n=10_000_000, dim=768, batch=256, limit=10, fusion="rrf", sel=0.5, dist="C",
                           desc="10M x 768-d hybrid, scope+time filter 50%, batch 256"),
+    # BASELINE.json configs[3] as ONE of its 8 row shards (100M / 8 rows per GPU, the full batch): the per-GPU
+    # work of the 8-GPU run; needs --no-cpu-baseline (the fp32 host copy would not fit next to it)
+    "cfg4-shard": dict(n=12_500_000, dim=768, batch=1024, limit=100, fusion="rrf", sel=0.5, dist="C",
+                       desc="one 12.5M-row shard of 100M x 768-d hybrid, filter 50%, batch 1024, top-100"),
     # small shape for quick checks
     "tiny": dict(n=65_536, dim=128, batch=16, limit=10, fusion="rrf", sel=None, dist="C", desc="tiny smoke shape"),
 }
@@ -411,7 +415,10 @@ def main():
     if tfile.exists():
         t = json.loads(tfile.read_text()).get(args.workload, {}).get(kname[dom_name])
         traffic = t["dram_bytes_per_launch"] if t else None
-    roofline = {"kernel": kname[dom_name], "launch": "largest segment: %d of %d rows%s" % (
+    tf_launch = (dense_flops * frac_rows / (big[0] / n_prof / 1e3) / 1e12) if big[0] > 0 else None
+    tensor_bound = dom_name == "dense" and dense_path == 2 and B / passes > 250      # past the ridge (252 flop/B)
+    roofline = {"kernel": kname[dom_name] if not tensor_bound else "vb_dense_gemm_tiled_kernel",
+                "launch": "largest segment: %d of %d rows%s" % (
                     big_rows, rows_local, "" if dom_name != "dense" else ", one of %d pass(es)" % passes),
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind}, burst copy)", "traffic": traffic,
@@ -422,7 +429,13 @@ def main():
                 "phase_gbs_per_step": {n_: (alg[n_] / (per_step[j] / 1e3) / 1e9 if per_step[j] > 0 else None) for j, n_ in enumerate(names)},
                 "big_launch": {"dense_ms": float(big[0] / n_prof), "sparse_ms": float(big[1] / n_prof),
                                "dense_gbs": (alg["dense"] / passes * frac_rows) / (big[0] / n_prof / 1e3) / 1e9 if big[0] > 0 else None,
+                               "dense_tflops": tf_launch,
                                "sparse_gbs": (alg["sparse"] * frac_rows) / (big[1] / n_prof / 1e3) / 1e9 if big[1] > 0 else None}}
+    if tensor_bound and tf_launch:
+        # batched scoring past the ridge point: the tensor pipe is the roofline (flops = 2 * rows * B * d_pad)
+        roofline.update({"bound": "tensor", "achieved": tf_launch, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf_launch / tf_peak,
+                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({peak_kind}, cuBLAS burst)",
+                         "algorithmic_flops_per_launch": dense_flops * frac_rows, "hbm_gbs_same_launch": achieved})
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on one batch, plus a parity spot check ----
     cpu = None

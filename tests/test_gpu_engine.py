@@ -413,3 +413,50 @@ def test_large_batch_hybrid_against_oracle():
     for a, b in zip(ix.search_stream(iter(packed)), one):
         assert np.array_equal(a.rows, b.rows) and np.array_equal(a.scores, b.scores) and np.array_equal(a.counts, b.counts)
     ix.close()
+
+
+def test_query_tiled_gemm_large_batch():
+    """B = 600 > the resident sub-batch: the query-tiled tcgen05 kernel (256-query tiles, the last one
+    partial) against the C oracle at the north_star's 1e-3 relative tie tolerance (plain bf16 query),
+    and bit-identical to the multi-pass resident kernel, for every mask mode of the epilogue:
+    no filter, one filter for the whole batch, a few filters, and more than 31 filters."""
+    from voitta_rag_b200 import engine
+    rng = np.random.RandomState(11)
+    n, dim, B = 80_000, 128, 600
+    cents = rng.randn(256, dim).astype(np.float32)
+    dense = _data.bf16_round(cents[rng.randint(0, 256, size=n)] + 0.6 * rng.randn(n, dim).astype(np.float32))
+    scope = rng.randint(0, 64, size=n).astype(np.uint32)
+    modified = rng.randint(1420070400, 1767225600, size=n).astype(np.int64)
+    ix = engine.Index(dim)
+    ix.upsert(dense, None, scope, None, modified)
+    cc = oracle_c.CorpusC(dense, None, scope, None, modified)
+    Q = _data.bf16_round(dense[rng.randint(0, n, size=B)] + 0.4 * rng.randn(B, dim).astype(np.float32))
+    bits = np.zeros(2, np.uint32); bits[0] = 0x00FFFF00; bits[1] = 0x0F0F0F0F
+    span = 1767225600 - 1420070400
+    few = [(bits, 0, 0, 0), (None, 2, 1500000000, 1700000000), (bits, 2, 1450000000, 1767225600)]
+    many = [(None, 2, 1420070400 + i * span // 80, 1420070400 + (i + 40) * span // 80) for i in range(40)]
+    cases = [
+        ("none", None, None),
+        ("uniform", few[:1], np.zeros(B, np.int32)),
+        ("few", few, (np.arange(B) % 4 - 1).astype(np.int32)),
+        ("many", many, (np.arange(B) % 41 - 1).astype(np.int32)),
+    ]
+    try:
+        for name, fl, fo in cases:
+            filters = None if fl is None else [engine.Filter(*f) for f in fl]
+            ix.set_option("k2_tiled", 1)
+            got = ix.search_batch(Q, None, filters, fo, limit=10, fusion="dense")
+            st = ix.stats()
+            assert st["last_dense_path"] == 2 and st["last_dense_passes"] == 1, st
+            ix.set_option("k2_tiled", 0)
+            ref = ix.search_batch(Q, None, filters, fo, limit=10, fusion="dense")
+            assert ix.stats()["last_dense_passes"] > 1
+            assert np.array_equal(got.counts, ref.counts), name
+            for i in range(B):
+                assert got.hits(i) == ref.hits(i), f"tiled vs resident kernel, {name} q{i}"
+            want = cc.search_batch(Q, None, fl, fo, limit=10, fusion=0)
+            for i in range(B):
+                wf = [(int(want["rows"][i, j]), float(want["scores"][i, j])) for j in range(want["counts"][i])]
+                assert_same_ranking(got.hits(i), wf, rel_tol=1e-3, abs_tol=1e-3, what=f"tiled {name} q{i}")
+    finally:
+        ix.close()

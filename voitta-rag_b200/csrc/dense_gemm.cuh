@@ -115,11 +115,22 @@ __host__ __device__ __forceinline__ uint32_t vb_umma_idesc(uint32_t bn) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((bn >> 3) << 17) | ((VB_TILE_M >> 4) << 24);
 }
 
+// Plain-bf16 query precision: rounding the unit query to bf16 changes its length by up to ~2e-3, which
+// would scale every score of that query.  The epilogue therefore multiplies by q_scale = 1/|bf16(q)|
+// (exact cosine against the rounded query; only the direction error, ~2e-4, remains).  The hot loop
+// compares the unscaled value against a pre-threshold tau/q_scale lowered by a safety margin; the
+// rare survivor path applies the scale and repeats the comparison exactly.
+__device__ __forceinline__ float vb_pre_threshold(float tau, float qs) {
+    const float t = tau / qs;
+    return t > 0.0f ? t * (1.0f - 1e-6f) : t * (1.0f + 1e-6f);
+}
+
 struct VbGemmArgs {
     const float* inv_norm;
     const uint32_t* mask;      // [n_filters][mask_words] or nullptr
     const int32_t* mask_of;    // [B_total] or nullptr
     const float* tau;          // [n_lists]
+    const float* q_scale;      // [B_total] 1/|bf16(q)| (1 for the bf16x2 query)
     VbLists lists;
     uint32_t mask_words, n_filters;
     uint32_t tile_begin, tile_end;   // 128-row tiles of this segment
@@ -158,7 +169,9 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tail + 8u * (2u * 16u + 5u));
     float* tau_s = reinterpret_cast<float*>(tail + 320u);                         // [256], 16-byte aligned
     int32_t* mof_s = reinterpret_cast<int32_t*>(tau_s + 256);                     // [256]
-    uint32_t* mw_s = reinterpret_cast<uint32_t*>(mof_s + 256);                    // [4 warps][VB_GEMM_MAX_FILTERS]
+    float* tex_s = reinterpret_cast<float*>(mof_s + 256);                         // [256] exact thresholds
+    float* qs_s = tex_s + 256;                                                    // [256] query scales
+    uint32_t* mw_s = reinterpret_cast<uint32_t*>(qs_s + 256);                     // [8 epilogue warps][VB_GEMM_MAX_FILTERS]
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t S = a.stages;
@@ -178,7 +191,11 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     }
     for (uint32_t c = threadIdx.x; c < 256u; c += blockDim.x) {
         const bool live = c < a.n_q;
-        tau_s[c] = live ? a.tau[a.q_begin + c] : INFINITY;
+        const float t = live ? a.tau[a.q_begin + c] : INFINITY;
+        const float qs = live ? a.q_scale[a.q_begin + c] : 1.0f;
+        tex_s[c] = t;
+        qs_s[c] = qs;
+        tau_s[c] = SPLIT ? t : vb_pre_threshold(t, qs);        // bf16x2 query: no scale, the hot compare is exact
         mof_s[c] = (live && a.mask_of) ? a.mask_of[a.q_begin + c] : -1;
     }
     vb_tcgen05_fence_before();
@@ -246,8 +263,8 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const uint32_t quad = warp & 3u;
         const uint32_t half = (warp - 2u) >> 2;            // 0: even chunks, 1: odd chunks
         const uint32_t tau_addr = vb_smem_u32(tau_s), mof_addr = vb_smem_u32(mof_s);
-        const uint32_t mw_addr = vb_smem_u32(mw_s + quad * VB_GEMM_MAX_FILTERS);
-        uint32_t* mw = mw_s + quad * VB_GEMM_MAX_FILTERS;
+        const uint32_t mw_addr = vb_smem_u32(mw_s + (warp - 2u) * VB_GEMM_MAX_FILTERS);
+        uint32_t* mw = mw_s + (warp - 2u) * VB_GEMM_MAX_FILTERS;   // private: the two warps of a quadrant may be one tile apart
         constexpr uint32_t mode = (uint32_t)MODE;
         constexpr bool split = SPLIT;
         const uint32_t ncol = split ? a.bn >> 1 : a.bn;       // query columns handled by the epilogue
@@ -271,6 +288,7 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 for (uint32_t f = 0; f < a.n_filters; ++f)
                     fbits |= ((__shfl_sync(0xffffffffu, w, f) >> lane) & 1u) << f;
             } else if (mode == 3u) {
+                __syncwarp();
                 for (uint32_t f = lane; f < a.n_filters; f += 32u)
                     mw[f] = word < a.mask_words ? a.mask[(size_t)f * a.mask_words + word] : 0u;
                 __syncwarp();
@@ -302,19 +320,32 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                         m |= (p & 1u) << j;
                     }
                 }
+                // final score of column c0 + j (query scale applied) and the exact comparison
+                auto final_score = [&](uint32_t j) -> float {
+                    if (split) return (__uint_as_float(v[j]) + __uint_as_float(w[j])) * invn;
+                    return __uint_as_float(v[j]) * invn * qs_s[c0 + j];
+                };
                 if (DIRECT) {
                     if (row_ok) {
 #pragma unroll
                         for (uint32_t j = 0; j < 16u; ++j) {
                             const uint32_t col = c0 + j;
-                            if (col < a.n_q)
+                            if (col < a.n_q) {
+                                const float fs = final_score(j);
                                 a.lists.cand[(size_t)(a.q_begin + col) * a.lists.cap + slot] =
-                                    ((m >> j) & 1u) ? vb_pack_key((split ? __uint_as_float(v[j]) + __uint_as_float(w[j]) : __uint_as_float(v[j])) * invn, a.row_base + row) : 0ull;
+                                    (((m >> j) & 1u) && (split || fs > tex_s[col])) ? vb_pack_key(fs, a.row_base + row) : 0ull;
+                            }
                         }
                     }
                 } else if (__any_sync(0xffffffffu, m != 0u)) {
-                    // rare path: reserve slots for all survivors of the chunk first (predicated atomics
-                    // issued back to back, so their L2 round trips overlap), then store the keys
+                    // rare path: exact comparison on the scaled score, then reserve slots for all
+                    // survivors of the chunk first (predicated atomics issued back to back, so their L2
+                    // round trips overlap), then store the keys
+                    if (!split) {
+#pragma unroll
+                        for (uint32_t j = 0; j < 16u; ++j)
+                            if (((m >> j) & 1u) && !(final_score(j) > tex_s[c0 + j])) m &= ~(1u << j);
+                    }
                     uint32_t slot[16];
                     const uint32_t sub = blockIdx.x & a.lists.sub_mask;
 #pragma unroll
@@ -327,7 +358,7 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     for (uint32_t j = 0; j < 16u; ++j) {
                         if (((m >> j) & 1u) && slot[j] < a.lists.sub_cap)
                             a.lists.cand[(size_t)(a.q_begin + c0 + j) * a.lists.cap + (size_t)sub * a.lists.sub_cap + slot[j]] =
-                                vb_pack_key((split ? __uint_as_float(v[j]) + __uint_as_float(w[j]) : __uint_as_float(v[j])) * invn, a.row_base + row);
+                                vb_pack_key(final_score(j), a.row_base + row);
                     }
                 }
             };
@@ -354,6 +385,241 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             vb_tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) vb_mbar_arrive(bar_tempty + 8u * acc);
+        }
+    }
+    vb_tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        vb_tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// ---- K2T: tensor-bound variant for large batches ------------------------------------------------------
+// For B above what fits resident in shared memory the kernel above needs one pass over the corpus
+// per sub-batch (HBM-bound: ~96 queries per pass at d = 768).  This variant tiles the QUERY dimension
+// instead: D[128 rows x 256 queries] tiles, both operands streamed through the TMA ring (16 KB corpus
+// box + 32 KB query box per 64-wide K block), accumulators double-buffered in TMEM (2 x 256
+// columns).  A CTA walks all query tiles of a corpus tile back to back, so the corpus tile comes from
+// HBM once and from L2 afterwards, and the query tiles (shared by all CTAs) stay L2-resident:
+// HBM traffic is ONE pass over the corpus per <= 1024 queries and the tensor pipe is the roofline
+// (flops = 2 * rows * B * d_pad).  Epilogue as above (threshold + mask + append, no score matrix).
+#define VB_TILE_N 256u
+#define VB_TILED_MAX_Q 1024u
+#define VB_TILED_STAGE_BYTES (VB_STAGE_BYTES + VB_TILE_N * VB_BLOCK_K * 2u)     // 48 KB
+
+struct VbGemmTiledArgs {
+    const float* inv_norm;
+    const uint32_t* mask;      // [n_filters][mask_words] or nullptr
+    const int32_t* mask_of;    // [B_total] or nullptr
+    const float* tau;          // [n_lists]
+    const float* q_scale;      // [B_total] 1/|bf16(q)|
+    VbLists lists;
+    uint32_t mask_words, n_filters;
+    uint32_t tile_begin, tile_end;   // 128-row tiles of this segment
+    uint32_t row_end;                // rows >= row_end are not part of the segment
+    uint32_t row_base;
+    uint32_t k_blocks;               // d_pad / 64
+    uint32_t n_q;                    // queries of this launch (<= VB_TILED_MAX_Q)
+    uint32_t q_begin;                // first query (list index) of this launch
+    uint32_t stages;
+    uint32_t mask_mode;              // 0 none, 1 one filter for all queries, 2 <= 31 filters, 3 general
+    int32_t  uniform_filter;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(VB_GEMM_THREADS, 1)
+vb_dense_gemm_tiled_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_q,
+                           const VbGemmTiledArgs a)
+{
+    extern __shared__ unsigned char vb_gemm_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)vb_gemm_smem_raw + 1023u) & ~(uintptr_t)1023u);
+    unsigned char* tail = smem + a.stages * VB_TILED_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);                       // full[16], empty[16], tfull[2], tempty[2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tail + 8u * (2u * 16u + 4u));
+    float* tau_s = reinterpret_cast<float*>(tail + 320u);                     // [VB_TILED_MAX_Q]
+    int32_t* mof_s = reinterpret_cast<int32_t*>(tau_s + VB_TILED_MAX_Q);      // [VB_TILED_MAX_Q]
+    float* tex_s = reinterpret_cast<float*>(mof_s + VB_TILED_MAX_Q);          // [VB_TILED_MAX_Q] exact thresholds
+    float* qs_s = tex_s + VB_TILED_MAX_Q;                                     // [VB_TILED_MAX_Q] query scales
+    uint32_t* mw_s = reinterpret_cast<uint32_t*>(qs_s + VB_TILED_MAX_Q);      // [8 epilogue warps][VB_GEMM_MAX_FILTERS]
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t S = a.stages;
+    const uint32_t bar_full = vb_smem_u32(bars), bar_empty = bar_full + 8u * 16u;
+    const uint32_t bar_tfull = bar_full + 8u * 32u, bar_tempty = bar_tfull + 16u;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            for (uint32_t s = 0; s < S; ++s) { vb_mbar_init(bar_full + 8u * s, 1); vb_mbar_init(bar_empty + 8u * s, 1); }
+            for (uint32_t s = 0; s < 2; ++s) { vb_mbar_init(bar_tfull + 8u * s, 1); vb_mbar_init(bar_tempty + 8u * s, 8); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(vb_smem_u32(tmem_ptr)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (uint32_t c = threadIdx.x; c < VB_TILED_MAX_Q; c += blockDim.x) {
+        const bool live = c < a.n_q;
+        const float t = live ? a.tau[a.q_begin + c] : INFINITY;
+        const float qs = live ? a.q_scale[a.q_begin + c] : 1.0f;
+        tex_s[c] = t;
+        qs_s[c] = qs;
+        tau_s[c] = vb_pre_threshold(t, qs);
+        mof_s[c] = (live && a.mask_of) ? a.mask_of[a.q_begin + c] : -1;
+    }
+    vb_tcgen05_fence_before();
+    __syncthreads();
+    vb_tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const uint32_t n_tiles = a.tile_end - a.tile_begin;
+    const uint32_t n_ntiles = (a.n_q + VB_TILE_N - 1u) / VB_TILE_N;
+
+    if (warp == 0) {
+        // ===== TMA producer: per (corpus tile, query tile, K block) one corpus box + one query box =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int32_t row0 = (int32_t)((a.tile_begin + t) * VB_TILE_M);
+                for (uint32_t j = 0; j < n_ntiles; ++j) {
+                    for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
+                        vb_mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
+                        vb_mbar_expect_tx(bar_full + 8u * stage, VB_TILED_STAGE_BYTES);
+                        const uint32_t dst = vb_smem_u32(smem + stage * VB_TILED_STAGE_BYTES);
+                        vb_tma_load_2d(dst, &tmap_a, (int32_t)(kb * VB_BLOCK_K), row0, bar_full + 8u * stage);
+                        vb_tma_load_2d(dst + VB_STAGE_BYTES, &tmap_q, (int32_t)(kb * VB_BLOCK_K), (int32_t)(j * VB_TILE_N), bar_full + 8u * stage);
+                        if (++stage == S) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one elected lane) =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                for (uint32_t j = 0; j < n_ntiles; ++j, ++it) {
+                    const uint32_t ncol = min(VB_TILE_N, (a.n_q - j * VB_TILE_N + 15u) & ~15u);
+                    const uint32_t idesc = vb_umma_idesc(ncol);
+                    const uint32_t acc = it & 1u;
+                    vb_mbar_wait(bar_tempty + 8u * acc, ((it >> 1) & 1u) ^ 1u);
+                    vb_tcgen05_fence_after();
+                    const uint32_t tmem_d = tmem_base + acc * VB_TILE_N;
+                    for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
+                        vb_mbar_wait(bar_full + 8u * stage, phase);
+                        vb_tcgen05_fence_after();
+                        const uint32_t a_addr = vb_smem_u32(smem + stage * VB_TILED_STAGE_BYTES);
+                        const uint32_t q_addr = a_addr + VB_STAGE_BYTES;
+#pragma unroll
+                        for (uint32_t k = 0; k < VB_BLOCK_K / 16u; ++k)
+                            vb_tcgen05_mma_bf16(tmem_d, vb_umma_desc(a_addr + k * 32u), vb_umma_desc(q_addr + k * 32u), idesc, (kb | k) != 0u);
+                        vb_tcgen05_commit(bar_empty + 8u * stage);     // smem stage free once these MMAs retire
+                        if (++stage == S) { stage = 0; phase ^= 1u; }
+                    }
+                    vb_tcgen05_commit(bar_tfull + 8u * acc);           // accumulator ready for the epilogue
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..9: TMEM lane quadrant = warp % 4, two warps per quadrant split the
+        //       16-column chunks (even / odd); branch-free compare, one vote per chunk =====
+        const uint32_t quad = warp & 3u;
+        const uint32_t half = (warp - 2u) >> 2;
+        const uint32_t tau_addr = vb_smem_u32(tau_s), mof_addr = vb_smem_u32(mof_s);
+        const uint32_t mw_addr = vb_smem_u32(mw_s + (warp - 2u) * VB_GEMM_MAX_FILTERS);
+        uint32_t* mw = mw_s + (warp - 2u) * VB_GEMM_MAX_FILTERS;   // private: the two warps of a quadrant may be one tile apart
+        constexpr uint32_t mode = (uint32_t)MODE;
+        const float qnan = __int_as_float(0x7fc00000);
+        const uint32_t sub = blockIdx.x & a.lists.sub_mask;
+        uint32_t it = 0;
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const uint32_t tile = a.tile_begin + t;
+            const uint32_t row = tile * VB_TILE_M + quad * 32u + lane;
+            const bool row_ok = row < a.row_end;
+            // a row that is out of range or (modes 0/1) masked gets a NaN scale: every compare fails
+            float invn = row_ok ? a.inv_norm[row] : qnan;
+            const uint32_t word = tile * 4u + quad;
+            uint32_t fbits = 0x80000000u;                 // mode 2: bit f = row passes filter f; bit 31 = unfiltered
+            if (MODE == 0 && a.mask_mode == 1u) {
+                const uint32_t w = word < a.mask_words ? a.mask[(size_t)a.uniform_filter * a.mask_words + word] : 0u;
+                if (!((w >> lane) & 1u)) invn = qnan;
+            } else if (mode == 2u) {
+                const uint32_t w = (lane < a.n_filters && word < a.mask_words) ? a.mask[(size_t)lane * a.mask_words + word] : 0u;
+                for (uint32_t f = 0; f < a.n_filters; ++f)
+                    fbits |= ((__shfl_sync(0xffffffffu, w, f) >> lane) & 1u) << f;
+            } else if (mode == 3u) {
+                __syncwarp();
+                for (uint32_t f = lane; f < a.n_filters; f += 32u)
+                    mw[f] = word < a.mask_words ? a.mask[(size_t)f * a.mask_words + word] : 0u;
+                __syncwarp();
+            }
+            for (uint32_t j = 0; j < n_ntiles; ++j, ++it) {
+                const uint32_t acc = it & 1u;
+                const uint32_t qoff = j * VB_TILE_N;
+                const uint32_t ncol = min(VB_TILE_N, (a.n_q - qoff + 15u) & ~15u);
+                vb_mbar_wait(bar_tfull + 8u * acc, (it >> 1) & 1u);
+                vb_tcgen05_fence_after();
+                const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * VB_TILE_N;
+                auto process = [&](const uint32_t (&v)[16], uint32_t c0) {
+                    uint32_t m = 0;
+#pragma unroll
+                    for (uint32_t j4 = 0; j4 < 4u; ++j4) {
+                        const float4 tq = vb_lds_f4(tau_addr + (qoff + c0 + 4u * j4) * 4u);
+                        const float tv[4] = {tq.x, tq.y, tq.z, tq.w};
+                        int fv[4] = {-1, -1, -1, -1};
+                        if (mode >= 2u) {
+                            const int4 fq = vb_lds_i4(mof_addr + (qoff + c0 + 4u * j4) * 4u);
+                            fv[0] = fq.x; fv[1] = fq.y; fv[2] = fq.z; fv[3] = fq.w;
+                        }
+#pragma unroll
+                        for (uint32_t e = 0; e < 4u; ++e) {
+                            const uint32_t jj = 4u * j4 + e;
+                            const float sc = __uint_as_float(v[jj]) * invn;
+                            uint32_t p = sc > tv[e] ? 1u : 0u;                    // tau = +inf for padded columns
+                            if (mode == 2u) p &= fbits >> ((uint32_t)fv[e] & 31u);
+                            else if (mode == 3u) p &= fv[e] < 0 ? 1u : (vb_lds_u32(mw_addr + (uint32_t)fv[e] * 4u) >> lane);
+                            m |= (p & 1u) << jj;
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, m != 0u)) {
+                        // rare path: exact comparison on the scaled score, reserve slots for all survivors
+                        // of the chunk, then store the keys
+#pragma unroll
+                        for (uint32_t jj = 0; jj < 16u; ++jj)
+                            if (((m >> jj) & 1u) && !(__uint_as_float(v[jj]) * invn * qs_s[qoff + c0 + jj] > tex_s[qoff + c0 + jj])) m &= ~(1u << jj);
+                        uint32_t slot[16];
+#pragma unroll
+                        for (uint32_t jj = 0; jj < 16u; ++jj) {
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p atom.global.add.u32 %0, [%1], 1;\n\t}"
+                                : "=r"(slot[jj]) : "l"(a.lists.cnt + (size_t)(a.q_begin + qoff + c0 + jj) * VB_SUB + sub), "r"((m >> jj) & 1u) : "memory");
+                        }
+#pragma unroll
+                        for (uint32_t jj = 0; jj < 16u; ++jj) {
+                            if (((m >> jj) & 1u) && slot[jj] < a.lists.sub_cap)
+                                a.lists.cand[(size_t)(a.q_begin + qoff + c0 + jj) * a.lists.cap + (size_t)sub * a.lists.sub_cap + slot[jj]] =
+                                    vb_pack_key(__uint_as_float(v[jj]) * invn * qs_s[qoff + c0 + jj], a.row_base + row);
+                        }
+                    }
+                };
+                uint32_t va[16], vb[16];
+                const uint32_t first = 16u * half;
+                if (first < ncol) vb_tmem_ld16(taddr + first, va);
+                for (uint32_t c0 = first; c0 < ncol; c0 += 64u) {
+                    vb_tmem_ld_wait();
+                    const bool second = c0 + 32u < ncol;
+                    if (second) vb_tmem_ld16(taddr + c0 + 32u, vb);
+                    process(va, c0);
+                    if (second) {
+                        vb_tmem_ld_wait();
+                        if (c0 + 64u < ncol) vb_tmem_ld16(taddr + c0 + 64u, va);
+                        process(vb, c0 + 32u);
+                    }
+                }
+                vb_tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) vb_mbar_arrive(bar_tempty + 8u * acc);
+            }
         }
     }
     vb_tcgen05_fence_before();
@@ -401,12 +667,16 @@ static int vb_gemm_configure() {
         e = cudaFuncSetAttribute(vb_gemm_variant(i), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { g_gemm_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
     }
+    e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { g_gemm_err = std::string("cudaFuncSetAttribute(tiled): ") + cudaGetErrorString(e); return 1; }
     g_gemm_smem_max = smem;
     g_encode_tiled = reinterpret_cast<VbEncodeTiledFn>(fn);
     return 0;
 }
 
-static const uint32_t VB_GEMM_TAIL_BYTES = 320u + 256u * 4u + 256u * 4u + 4u * VB_GEMM_MAX_FILTERS * 4u;
+static const uint32_t VB_GEMM_TAIL_BYTES = 320u + 4u * 256u * 4u + 8u * VB_GEMM_MAX_FILTERS * 4u;
 
 // largest padded sub-batch whose resident query matrix leaves room for >= 4 stages
 static int vb_env_int(const char* name, int dflt) {
@@ -455,6 +725,7 @@ struct VbGemmLaunch {
     const int32_t* mask_of;
     uint32_t mask_words, n_filters;
     const float* tau;
+    const float* q_scale;      // [B]
     VbLists lists;
     uint32_t n_rows_total, row_begin, row_end, row_base, d_pad, n_queries;
     int sm_count;
@@ -506,7 +777,7 @@ static int vb_gemm_launch(const VbGemmLaunch& g, int* launches) {
         CUtensorMap tmap_q;
         if (vb_encode_2d(&tmap_q, reinterpret_cast<const unsigned char*>(g.q_bf16) + (size_t)q0 * mult * g.d_pad * 2, bn, g.d_pad, bn)) return 1;
         VbGemmArgs a{};
-        a.inv_norm = g.inv_norm; a.mask = g.mask; a.mask_of = g.mask_of; a.tau = g.tau; a.lists = g.lists;
+        a.inv_norm = g.inv_norm; a.mask = g.mask; a.mask_of = g.mask_of; a.tau = g.tau; a.q_scale = g.q_scale; a.lists = g.lists;
         a.mask_words = g.mask_words; a.n_filters = g.n_filters;
         a.tile_begin = g.row_begin / VB_TILE_M; a.tile_end = (g.row_end + VB_TILE_M - 1) / VB_TILE_M;
         a.row_end = g.row_end; a.row_base = g.row_base; a.k_blocks = g.d_pad / VB_BLOCK_K;
@@ -535,6 +806,59 @@ static int vb_gemm_launch(const VbGemmLaunch& g, int* launches) {
         vb_gemm_variant(variant)<<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { g_gemm_err = std::string("launch failed: ") + cudaGetErrorString(e); return 1; }
+        ++*launches;
+    }
+    return 0;
+}
+
+// ---- K2T launcher -------------------------------------------------------------------------------------
+static const uint32_t VB_TILED_TAIL_BYTES = 320u + VB_TILED_MAX_Q * 16u + 8u * VB_GEMM_MAX_FILTERS * 4u;
+
+static uint32_t vb_gemm_tiled_stages() {
+    const uint32_t avail = (uint32_t)g_gemm_smem_max - 1024u - VB_TILED_TAIL_BYTES;
+    uint32_t st = avail / VB_TILED_STAGE_BYTES;
+    const uint32_t cap = (uint32_t)vb_env_int("VB200_K2T_STAGES", 4);
+    return st > cap ? cap : st;
+}
+static bool vb_gemm_tiled_supported(int d_pad) {
+    return g_encode_tiled != nullptr && d_pad % 64 == 0 && vb_gemm_tiled_stages() >= 2u;
+}
+
+// g.q_bf16 must hold the queries unsplit, row i = query i (vb_gemm_plan with split = 0).
+static int vb_gemm_tiled_launch(const VbGemmLaunch& g, int* launches) {
+    if (!g_encode_tiled) { g_gemm_err = "tensor-core path not configured"; return 1; }
+    if (g.mask && g.n_filters > VB_GEMM_MAX_FILTERS) { g_gemm_err = "more than 256 distinct filters in one batch"; return 1; }
+    if (g.plan.split) { g_gemm_err = "tiled kernel needs the unsplit query layout"; return 1; }
+    CUtensorMap tmap_a;
+    if (vb_encode_2d(&tmap_a, g.rows, g.n_rows_total, g.d_pad, VB_TILE_M)) return 1;
+    const uint32_t stages = vb_gemm_tiled_stages();
+    for (uint32_t q0 = 0; q0 < g.n_queries; q0 += VB_TILED_MAX_Q) {
+        const uint32_t n_q = std::min(VB_TILED_MAX_Q, g.n_queries - q0);
+        CUtensorMap tmap_q;
+        if (vb_encode_2d(&tmap_q, reinterpret_cast<const unsigned char*>(g.q_bf16) + (size_t)q0 * g.d_pad * 2,
+                         (n_q + 15u) / 16u * 16u, g.d_pad, VB_TILE_N)) return 1;
+        VbGemmTiledArgs a{};
+        a.inv_norm = g.inv_norm; a.mask = g.mask; a.mask_of = g.mask_of; a.tau = g.tau; a.q_scale = g.q_scale; a.lists = g.lists;
+        a.mask_words = g.mask_words; a.n_filters = g.n_filters;
+        a.tile_begin = g.row_begin / VB_TILE_M; a.tile_end = (g.row_end + VB_TILE_M - 1) / VB_TILE_M;
+        a.row_end = g.row_end; a.row_base = g.row_base; a.k_blocks = g.d_pad / VB_BLOCK_K;
+        a.n_q = n_q; a.q_begin = q0; a.stages = stages;
+        a.mask_mode = 0; a.uniform_filter = -1;
+        if (g.mask != nullptr) {
+            bool uniform = true;
+            for (uint32_t i = 1; i < n_q; ++i) uniform = uniform && g.mask_of_host[q0 + i] == g.mask_of_host[q0];
+            if (uniform && g.mask_of_host[q0] < 0) { a.mask = nullptr; a.mask_of = nullptr; }
+            else if (uniform) { a.mask_mode = 1; a.uniform_filter = g.mask_of_host[q0]; }
+            else a.mask_mode = g.n_filters <= 31u ? 2 : 3;
+        }
+        const size_t smem = 1024u + (size_t)stages * VB_TILED_STAGE_BYTES + VB_TILED_TAIL_BYTES;
+        const uint32_t tiles = a.tile_end - a.tile_begin;
+        const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)g.sm_count);
+        if (a.mask_mode == 2u) vb_dense_gemm_tiled_kernel<2><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
+        else if (a.mask_mode == 3u) vb_dense_gemm_tiled_kernel<3><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
+        else vb_dense_gemm_tiled_kernel<0><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { g_gemm_err = std::string("tiled launch failed: ") + cudaGetErrorString(e); return 1; }
         ++*launches;
     }
     return 0;

@@ -97,7 +97,8 @@ vb_ingest_bf16_kernel(const __nv_bfloat16* __restrict__ src, uint32_t n, uint32_
 // that q_hi + q_lo carries ~16 mantissa bits and the MMA result matches the fp32 dot to ~1e-5.
 __global__ void __launch_bounds__(128)
 vb_prep_query_kernel(const float* __restrict__ q, uint32_t dim, uint32_t d_pad, uint32_t n_queries,
-                     uint32_t sub, uint32_t split, float* __restrict__ q_hat, __nv_bfloat16* __restrict__ q_bf16)
+                     uint32_t sub, uint32_t split, float* __restrict__ q_hat, __nv_bfloat16* __restrict__ q_bf16,
+                     float* __restrict__ q_scale)
 {
     __shared__ double red[4];
     const uint32_t b = blockIdx.x;
@@ -110,16 +111,26 @@ vb_prep_query_kernel(const float* __restrict__ q, uint32_t dim, uint32_t d_pad, 
     if ((threadIdx.x & 31u) == 0) red[threadIdx.x >> 5] = ss;
     __syncthreads();
     ss = red[0] + red[1] + red[2] + red[3];
+    __syncthreads();
     const float inv = ss > 0.0 ? (float)(1.0 / sqrt(ss)) : 0.0f;
     const uint32_t s_idx = b / sub, j = b % sub;
     const uint32_t n_q = min(sub, n_queries - s_idx * sub);
     const uint32_t bn_q = (n_q + 15u) / 16u * 16u;
     const size_t base = (size_t)s_idx * sub * (split ? 2u : 1u);
+    double rr = 0.0;                                            // squared length of the rounded unit query
     for (uint32_t c = threadIdx.x; c < d_pad; c += blockDim.x) {
         const float v = c < dim ? q[(size_t)b * dim + c] * inv : 0.0f;
         q_hat[(size_t)b * d_pad + c] = v;
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         q_bf16[(base + j) * d_pad + c] = hi;
         if (split) q_bf16[(base + bn_q + j) * d_pad + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        const double hv = (double)__bfloat162float(hi);
+        rr += hv * hv;
     }
+    for (int o = 16; o > 0; o >>= 1) rr += __shfl_xor_sync(0xffffffffu, rr, o);
+    if ((threadIdx.x & 31u) == 0) red[threadIdx.x >> 5] = rr;
+    __syncthreads();
+    rr = red[0] + red[1] + red[2] + red[3];
+    // plain bf16 query: rescale scores by 1/|bf16(q)| (see vb_pre_threshold); the bf16x2 query keeps ~16 bits
+    if (threadIdx.x == 0) q_scale[b] = (!split && rr > 0.0) ? (float)(1.0 / sqrt(rr)) : 1.0f;
 }

@@ -121,12 +121,12 @@ struct vb_index {
     std::vector<uint64_t> term_ptr;
 
     // per-search scratch
-    DevBuf args, mask, cand, lists, offs, out, q_hat, q_bf16, tmp;
+    DevBuf args, mask, cand, lists, offs, out, q_hat, q_bf16, q_scale, tmp;
     HostBuf h_args_s[2], h_out_s[2], h_stage;
     uint32_t cand_cap = 0;
 
     // options
-    int64_t opt_dense_path = 0, opt_seg_first = 2048, opt_seg_ratio = 32, opt_safe_mode = 0, opt_profile = 0, opt_k2_precision = 0, opt_overlap = 1;
+    int64_t opt_dense_path = 0, opt_seg_first = 2048, opt_seg_ratio = 32, opt_safe_mode = 0, opt_profile = 0, opt_k2_precision = 0, opt_overlap = 1, opt_k2_tiled = 1;
 
     vb_stats stats{};
     Batch staged_s[2];
@@ -261,7 +261,7 @@ extern "C" void vb_destroy(vb_index* h) {
     cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->rows, &h->inv_norm, &h->scope_id, &h->created, &h->modified, &h->alive, &h->sp_indptr,
                       &h->sp_term, &h->sp_val, &h->post_row, &h->post_val, &h->args, &h->mask, &h->cand, &h->lists,
-                      &h->offs, &h->out, &h->q_hat, &h->q_bf16, &h->tmp})
+                      &h->offs, &h->out, &h->q_hat, &h->q_bf16, &h->q_scale, &h->tmp})
         dev_free(h, *b);
     for (HostBuf* b : {&h->h_args_s[0], &h->h_args_s[1], &h->h_out_s[0], &h->h_out_s[1], &h->h_stage}) if (b->p) cudaFreeHost(b->p);
     for (auto ev : h->prof_events) cudaEventDestroy(ev);
@@ -284,6 +284,7 @@ extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
     else if (k == "profile") h->opt_profile = value;
     else if (k == "slot") h->cur = value ? 1 : 0;                   // which of the two in-flight batches the staged calls address
     else if (k == "overlap") h->opt_overlap = value;               // 1: dense and sparse chains on two streams
+    else if (k == "k2_tiled") h->opt_k2_tiled = value;             // 0: never use the query-tiled kernel (multi-pass resident kernel instead)
     else if (k == "k2_precision") h->opt_k2_precision = value;   // 0 auto, 1 bf16 query, 2 bf16x2 (hi+lo) query
     else if (k == "stream") {   // run on the caller's stream (e.g. torch's current stream); 0 = own stream
         h->stream = value ? reinterpret_cast<cudaStream_t>(static_cast<uintptr_t>(value)) : h->own_stream;
@@ -879,12 +880,16 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
     h->stats.last_dense_path = (uint32_t)path;
     VbGemmPlan plan{1u, 0u};
     if (path == 2) plan = vb_gemm_plan((uint32_t)h->d_pad, b.B, (int)h->opt_k2_precision);
-    h->stats.last_dense_passes = path == 2 ? (b.B + plan.sub - 1) / plan.sub : b.B;
+    // batches too large to sit resident in shared memory go to the query-tiled, tensor-bound kernel
+    // (one corpus pass per 1024 queries); the first (direct) segment always uses the resident kernel
+    const bool tiled = path == 2 && b.B > plan.sub && !plan.split && h->opt_k2_tiled && vb_gemm_tiled_supported(h->d_pad);
+    h->stats.last_dense_passes = path == 2 ? (tiled ? (b.B + VB_TILED_MAX_Q - 1) / VB_TILED_MAX_Q : (b.B + plan.sub - 1) / plan.sub) : b.B;
     // query prep (fp32 unit queries for K1, packed bf16 operand for K2)
     TRY(dev_reserve(h, h->q_hat, (size_t)b.B * h->d_pad * 4, false));
     TRY(dev_reserve(h, h->q_bf16, (size_t)(2 * ((size_t)b.B + 256)) * h->d_pad * 2, false));
+    TRY(dev_reserve(h, h->q_scale, (size_t)b.B * 4, false));
     vb_prep_query_kernel<<<b.B, 128, 0, h->stream>>>(b.d_q, (uint32_t)h->dim, (uint32_t)h->d_pad, b.B, plan.sub, plan.split,
-                                                     h->q_hat.as<float>(), h->q_bf16.as<__nv_bfloat16>());
+                                                     h->q_hat.as<float>(), h->q_bf16.as<__nv_bfloat16>(), h->q_scale.as<float>());
     CKK("vb_prep_query_kernel");
     ++h->stats.last_launches;
     // K0 filter masks
@@ -915,12 +920,13 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
             VbGemmLaunch g{};
             g.rows = h->rows.p; g.inv_norm = h->inv_norm.as<float>(); g.q_bf16 = h->q_bf16.p;
             g.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; g.mask_of = b.use_mask ? b.d_maskof : nullptr;
-            g.mask_words = b.mask_words; g.n_filters = b.n_filters; g.tau = b.tau; g.lists = L;
+            g.mask_words = b.mask_words; g.n_filters = b.n_filters; g.tau = b.tau; g.q_scale = h->q_scale.as<float>(); g.lists = L;
             g.n_rows_total = n; g.row_begin = r0; g.row_end = r1; g.row_base = (uint32_t)h->row_base;
             g.d_pad = (uint32_t)h->d_pad; g.n_queries = b.B; g.sm_count = h->sm_count; g.stream = sd;
             g.direct = direct; g.plan = plan; g.mask_of_host = b.mask_of_host.data();
             int launches = 0;
-            if (vb_gemm_launch(g, &launches) != 0) return vb_fail("tensor-core dense kernel: %s", vb_gemm_last_error());
+            if ((tiled && !direct ? vb_gemm_tiled_launch(g, &launches) : vb_gemm_launch(g, &launches)) != 0)
+                return vb_fail("tensor-core dense kernel: %s", vb_gemm_last_error());
             h->stats.last_launches += (uint32_t)launches;
         } else {
             TRY(launch_scan(h, b, L, r0, r1, direct, sd));
