@@ -405,6 +405,14 @@ def test_large_batch_hybrid_against_oracle():
             ws = [(int(want["sparse_rows"][i, j]), float(want["sparse_scores"][i, j])) for j in range(want["sparse_counts"][i])]
             assert_same_ranking(got.branch(i, "sparse"), ws, rel_tol=0.0, what=f"sparse q{i}")
             fusion_bit_exact(got, i, 10, fusion, 0.1)
+    # MaxScore pruning forced on: identical sparse lists (bit for bit) and fused results
+    base = ix.search_batch(Q, SP, [engine.Filter(*flt)], fo, limit=10, fusion="rrf", branches=True)
+    ix.set_option("sparse_prune_force", 1)
+    pruned = ix.search_batch(Q, SP, [engine.Filter(*flt)], fo, limit=10, fusion="rrf", branches=True)
+    ix.set_option("sparse_prune_force", 0)
+    for i in range(B):
+        assert pruned.branch(i, "sparse") == base.branch(i, "sparse"), f"pruned sparse list q{i}"
+        assert pruned.hits(i) == base.hits(i)
     # the pipelined stream API returns the same answers as the one-call API
     packed = [ix.pack(Q[j:j + 16], SP[j:j + 16], [engine.Filter(*flt)], np.zeros(16, np.int32), limit=10, fusion="rrf")
               for j in range(0, B, 16)]
@@ -413,6 +421,27 @@ def test_large_batch_hybrid_against_oracle():
     for a, b in zip(ix.search_stream(iter(packed)), one):
         assert np.array_equal(a.rows, b.rows) and np.array_equal(a.scores, b.scores) and np.array_equal(a.counts, b.counts)
     ix.close()
+
+
+@pytest.mark.parametrize("budget", [20, 100])
+def test_maxscore_pruning_is_exact(world, budget):
+    """MaxScore pruning of the sparse branch (non-essential terms skipped, survivors re-scored from the
+    forward index) forced on for every segment: the sparse lists stay bit-identical to the oracle's
+    ordered fp64 sums, with and without filters, and with a tighter (20 %) or the full (100 %) budget."""
+    ix = world["ix"]
+    ix.set_option("sparse_prune_force", 1)
+    ix.set_option("sparse_prune", budget)
+    ix.set_option("seg_ratio", 4)                       # more segments => thresholds (and plans) change more often
+    try:
+        for fi in (0, 1, 3, 5):
+            flt = filters_for(world["coded"])[fi]
+            for limit in (10, 40):
+                got, want = run_both(world, world["queries"], flt, limit, "weighted")
+                check(got, want, len(world["queries"]), 1e-5, f"prune {budget}% f{fi} limit {limit}")
+    finally:
+        ix.set_option("sparse_prune_force", 0)
+        ix.set_option("sparse_prune", 20)
+        ix.set_option("seg_ratio", 32)
 
 
 def test_query_tiled_gemm_large_batch():

@@ -81,6 +81,12 @@ struct VbSparseArgs {
     const uint32_t* off;        // [n_blocks+1][n_qterms]
     const int64_t* q_indptr;    // [B+1] into the sorted query-term arrays
     const double* q_weight;     // [n_qterms] idf-scaled query values, ascending term id per query
+    const uint32_t* q_term;     // [n_qterms] term ids (ascending per query)
+    const uint8_t* ess;         // [n_qterms] 1 = essential term for the current thresholds; nullptr = all
+    const double* ubne;         // [B] sum of the upper bounds of the query's non-essential terms
+    const int64_t* sp_indptr;   // forward index (row-major CSR as appended), for exact re-scoring
+    const uint32_t* sp_term;
+    const float* sp_val;
     const uint32_t* mask;       // [n_filters][mask_words] or nullptr
     const int32_t* mask_of;     // [B] or nullptr
     const float* tau;
@@ -95,13 +101,56 @@ struct VbSparseArgs {
     uint32_t direct;            // 1: first segment — store keys at slot (row - segment begin), no atomics
 };
 
+// ---- MaxScore plan: which query terms are essential under the current thresholds --------------------
+// ub[j] >= the largest contribution term j can make to any row of this shard (weight x the term's
+// largest posting value; +inf = "always essential").  Sorting a query's terms by ub, the longest
+// prefix whose ub sum stays below a fixed share of tau is NON-essential: a row that contains only such terms cannot
+// beat tau, so the scoring kernel scatters only the essential terms' postings, drops every row
+// whose partial score + (sum of non-essential ubs) is still below tau, and re-scores the few
+// survivors exactly.  One CTA per query, launched before every sparse segment (tau moves).
+// The 1e-9 relative margins dwarf the fp64 rounding of the sums involved (<= 256 terms, ~3e-14).
+__global__ void __launch_bounds__(256)
+vb_sparse_plan_kernel(const int64_t* __restrict__ q_indptr, const double* __restrict__ q_ub, const float* __restrict__ tau,
+                      uint32_t n_queries, uint32_t budget_pct, uint8_t* __restrict__ ess, double* __restrict__ ubne)
+{
+    __shared__ double s_ub[256];
+    __shared__ double s_red[8];
+    const uint32_t q = blockIdx.x, j = threadIdx.x;
+    const uint32_t t_lo = (uint32_t)q_indptr[q];
+    const uint32_t nt = (uint32_t)q_indptr[q + 1] - t_lo;
+    const double tau_d = (double)tau[n_queries + q];
+    const double ub = j < nt ? q_ub[t_lo + j] : INFINITY;
+    s_ub[j] = ub;
+    __syncthreads();
+    double cum = 0.0;                                           // ub sum of the sorted prefix that ends with term j
+    for (uint32_t i = 0; i < nt; ++i) {
+        const double u = s_ub[i];
+        if (u < ub || (u == ub && i <= j)) cum += u;
+    }
+    // budget: the non-essential ubs may sum to at most budget_pct % of tau.  A small budget already
+    // covers the most frequent (lowest-idf, longest) posting lists while keeping the survivor test
+    // partial >= tau - sum(ub) selective, so that few rows need exact re-scoring.
+    const bool ok = budget_pct != 0u && tau_d > 0.0 && tau_d < INFINITY;
+    const bool ne = ok && j < nt && ub < INFINITY && cum < tau_d * (0.01 * (double)min(budget_pct, 100u)) * (1.0 - 2e-9);
+    if (j < nt) ess[t_lo + j] = ne ? 0 : 1;
+    double m = ne ? cum : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((j & 31u) == 0) s_red[j >> 5] = m;
+    __syncthreads();
+    if (j == 0) {
+        for (uint32_t w = 1; w < 8; ++w) m = fmax(m, s_red[w]);
+        ubne[q] = m;
+    }
+}
+
 #define VB_SPARSE_THREADS 128
 #define VB_SPARSE_U 4u                                          // postings per thread per batch
 #define VB_SPARSE_BATCH (VB_SPARSE_U * VB_SPARSE_THREADS)       // 512 postings per batch
 #define VB_SPARSE_PAD 32u                                       // dummy accumulators for padding lanes
 
 static size_t vb_sparse_smem_bytes(uint32_t nt_max) {
-    return (size_t)(VB_ROWS_PER_BLOCK + VB_SPARSE_PAD) * 8u + (size_t)nt_max * 18u + 32u;
+    return (size_t)(VB_ROWS_PER_BLOCK + VB_SPARSE_PAD) * 8u + (size_t)VB_ROWS_PER_BLOCK * 2u + (size_t)nt_max * 20u + 32u;
 }
 
 // grid.x = (#blocks in segment) * B ; CTA (blk, q) with q fastest so that concurrently running
@@ -131,8 +180,10 @@ vb_sparse_kernel(const VbSparseArgs a)
     double* s_w = acc + VB_ROWS_PER_BLOCK + VB_SPARSE_PAD;                  // [nt_max]
     uint32_t* s_lo = reinterpret_cast<uint32_t*>(s_w + a.nt_max);           // [nt_max]
     uint32_t* s_hi = s_lo + a.nt_max;                                       // [nt_max]
-    uint16_t* s_nz = reinterpret_cast<uint16_t*>(s_hi + a.nt_max);          // [nt_max] non-empty terms, ascending
-    __shared__ uint32_t s_nnz;
+    uint16_t* s_surv = reinterpret_cast<uint16_t*>(s_hi + a.nt_max);        // [VB_ROWS_PER_BLOCK] rows to re-score
+    uint16_t* s_nz = s_surv + VB_ROWS_PER_BLOCK;                            // [nt_max] non-empty ESSENTIAL terms, ascending
+    uint16_t* s_all = s_nz + a.nt_max;                                      // [nt_max] all non-empty terms, ascending
+    __shared__ uint32_t s_nnz, s_nall, s_nsurv;
 
     const uint32_t tid = threadIdx.x;
     const uint32_t q = blockIdx.x % a.n_queries;
@@ -160,19 +211,24 @@ vb_sparse_kernel(const VbSparseArgs a)
         *reinterpret_cast<double2*>(&acc[r]) = make_double2(neg_zero, neg_zero);
     __syncthreads();
     if (tid < 32u) {                                            // ordered compaction of the non-empty terms
-        uint32_t base = 0;
+        uint32_t base = 0, base_all = 0;
         for (uint32_t j0 = 0; j0 < nt; j0 += 32u) {
             const uint32_t j = j0 + tid;
             const bool ne = j < nt && s_hi[j] > s_lo[j];
-            const uint32_t bal = __ballot_sync(0xffffffffu, ne);
-            if (ne) s_nz[base + __popc(bal & ((1u << tid) - 1u))] = (uint16_t)j;
+            const bool es = ne && (a.ess == nullptr || a.ess[t_lo + j] != 0);
+            const uint32_t bal_all = __ballot_sync(0xffffffffu, ne);
+            const uint32_t bal = __ballot_sync(0xffffffffu, es);
+            if (ne) s_all[base_all + __popc(bal_all & ((1u << tid) - 1u))] = (uint16_t)j;
+            if (es) s_nz[base + __popc(bal & ((1u << tid) - 1u))] = (uint16_t)j;
             base += __popc(bal);
+            base_all += __popc(bal_all);
         }
-        if (tid == 0) s_nnz = base;
+        if (tid == 0) { s_nnz = base; s_nall = base_all; s_nsurv = 0u; }
     }
     __syncthreads();
-    const uint32_t nnz = s_nnz;
-    if (nnz == 0) return;                                       // (direct-mode slots were zeroed by the host)
+    const uint32_t nnz = s_nnz;                                 // essential terms with postings in this block
+    const uint32_t n_all = s_nall;
+    if (nnz == 0) return;                                       // no row of this block can beat tau (direct-mode slots were zeroed by the host)
 
     const uint32_t row0 = blk * VB_ROWS_PER_BLOCK;
     const uint32_t dummy = VB_ROWS_PER_BLOCK + (tid & 31u);     // this lane's private padding slot
@@ -230,28 +286,73 @@ vb_sparse_kernel(const VbSparseArgs a)
 
     const uint32_t seg_row0 = a.blk_begin * VB_ROWS_PER_BLOCK;
     const uint32_t sub = blk_rel & a.lists.sub_mask;            // append counter of this row block
-    // Scan two accumulators per thread per step.  Cheap exact prefilter in fp64: rounding to fp32 is
-    // monotone, so cur < (double)tau implies float(cur) <= tau — such rows (the vast majority once
-    // tau is established, and every untouched -0.0 row when tau >= 0) are dropped with one compare.
     const double tau_d = (double)tau;
+    if (n_all == nnz) {
+        // Every term with postings here was accumulated: the accumulators hold the exact scores.
+        // Scan two per thread per step.  Cheap exact prefilter in fp64: rounding to fp32 is monotone, so
+        // cur < (double)tau implies float(cur) <= tau — such rows (the vast majority once tau is
+        // established, and every untouched -0.0 row when tau >= 0) are dropped with one compare.
+#pragma unroll 4
+        for (uint32_t r = 2u * tid; r < VB_ROWS_PER_BLOCK; r += 2u * VB_SPARSE_THREADS) {
+            const double2 c2 = *reinterpret_cast<const double2*>(&acc[r]);
+            const double cv[2] = {c2.x, c2.y};
+            if (!a.direct && c2.x < tau_d && c2.y < tau_d) continue;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double cur = cv[e];
+                const uint32_t row = row0 + r + e;
+                bool pass = (unsigned long long)__double_as_longlong(cur) != VB_ACC_SENTINEL && row < a.n_rows;
+                if (pass && mask) pass = (mask[row >> 5] >> (row & 31u)) & 1u;
+                float s = 0.0f;
+                if (pass) { s = __double2float_rn(cur); pass = s > tau; }
+                if (a.direct) {
+                    if (row < a.n_rows) a.lists.cand[(size_t)list * a.lists.cap + (row - seg_row0)] = pass ? vb_pack_key(s, a.row_base + row) : 0ull;
+                } else if (pass) {
+                    vb_push_sub(a.lists, list, sub, s, a.row_base + row);
+                }
+            }
+        }
+        return;
+    }
+    // Some non-essential terms were skipped: the accumulators hold partial scores.  A row survives only
+    // if partial + (sum of the non-essential upper bounds) can still reach tau; survivors are re-scored
+    // exactly from the forward index (all shared terms in ascending term id, as the reference does).
+    // (tau > 0 here, so untouched -0.0 rows never survive; direct mode never gets here: tau = -inf.)
+    const double bound = tau_d * (1.0 - 1e-9) - a.ubne[q];
 #pragma unroll 4
     for (uint32_t r = 2u * tid; r < VB_ROWS_PER_BLOCK; r += 2u * VB_SPARSE_THREADS) {
         const double2 c2 = *reinterpret_cast<const double2*>(&acc[r]);
-        const double cv[2] = {c2.x, c2.y};
-        if (!a.direct && c2.x < tau_d && c2.y < tau_d) continue;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const double cur = cv[e];
-            const uint32_t row = row0 + r + e;
-            bool pass = (unsigned long long)__double_as_longlong(cur) != VB_ACC_SENTINEL && row < a.n_rows;
-            if (pass && mask) pass = (mask[row >> 5] >> (row & 31u)) & 1u;
-            float s = 0.0f;
-            if (pass) { s = __double2float_rn(cur); pass = s > tau; }
-            if (a.direct) {
-                if (row < a.n_rows) a.lists.cand[(size_t)list * a.lists.cap + (row - seg_row0)] = pass ? vb_pack_key(s, a.row_base + row) : 0ull;
-            } else if (pass) {
-                vb_push_sub(a.lists, list, sub, s, a.row_base + row);
+        if (c2.x < bound && c2.y < bound) continue;
+        if (!(c2.x < bound)) s_surv[atomicAdd(&s_nsurv, 1u)] = (uint16_t)r;
+        if (!(c2.y < bound)) s_surv[atomicAdd(&s_nsurv, 1u)] = (uint16_t)(r + 1u);
+    }
+    __syncthreads();
+    const uint32_t nsurv = s_nsurv;
+    const uint32_t lane = tid & 31u;
+    for (uint32_t i = tid >> 5; i < nsurv; i += VB_SPARSE_THREADS / 32u) {      // one warp per survivor
+        const uint32_t row = row0 + s_surv[i];
+        if (row >= a.n_rows) continue;
+        if (mask && !((mask[row >> 5] >> (row & 31u)) & 1u)) continue;
+        const int64_t ip0 = __ldg(a.sp_indptr + row), ip1 = __ldg(a.sp_indptr + row + 1);
+        double sc = 0.0;
+        for (uint32_t ti = 0; ti < n_all; ++ti) {
+            const uint32_t j = s_all[ti];
+            const uint32_t term = __ldg(a.q_term + t_lo + j);
+            for (int64_t c0 = ip0; c0 < ip1; c0 += 32) {
+                const int64_t p = c0 + lane;
+                const bool hit = p < ip1 && __ldg(a.sp_term + p) == term;
+                const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+                if (bal) {
+                    float v = hit ? __ldg(a.sp_val + p) : 0.0f;
+                    v = __shfl_sync(0xffffffffu, v, __ffs(bal) - 1);
+                    sc = __dadd_rn(sc, __dmul_rn(s_w[j], (double)v));
+                    break;
+                }
             }
+        }
+        if (lane == 0) {
+            const float sf = __double2float_rn(sc);
+            if (sf > tau) vb_push_sub(a.lists, list, sub, sf, a.row_base + row);
         }
     }
 }

@@ -77,6 +77,8 @@ struct Batch {
     const float* d_q = nullptr;
     const int64_t* d_qindptr = nullptr;
     const double* d_qweight = nullptr;
+    const double* d_qub = nullptr;
+    const uint32_t* d_qterm = nullptr;
     const uint32_t* d_qlo = nullptr;
     const uint32_t* d_qhi = nullptr;
     const int32_t* d_maskof = nullptr;
@@ -119,14 +121,15 @@ struct vb_index {
     uint64_t nnz_live = 0;
     std::vector<uint32_t> terms_sorted;
     std::vector<uint64_t> term_ptr;
+    std::vector<float> term_maxval;        // largest posting value per term (MaxScore upper bounds)
 
     // per-search scratch
-    DevBuf args, mask, cand, lists, offs, out, q_hat, q_bf16, q_scale, tmp;
+    DevBuf args, mask, cand, lists, offs, plan, out, q_hat, q_bf16, q_scale, tmp;
     HostBuf h_args_s[2], h_out_s[2], h_stage;
     uint32_t cand_cap = 0;
 
     // options
-    int64_t opt_dense_path = 0, opt_seg_first = 2048, opt_seg_ratio = 32, opt_safe_mode = 0, opt_profile = 0, opt_k2_precision = 0, opt_overlap = 1, opt_k2_tiled = 1;
+    int64_t opt_dense_path = 0, opt_seg_first = 2048, opt_seg_ratio = 32, opt_safe_mode = 0, opt_profile = 0, opt_k2_precision = 0, opt_overlap = 1, opt_k2_tiled = 1, opt_sparse_prune = 20, opt_sparse_prune_force = 0;
 
     vb_stats stats{};
     Batch staged_s[2];
@@ -251,6 +254,7 @@ extern "C" int vb_create(int32_t dim, int32_t device, uint64_t capacity_hint, ui
     if (const char* env = getenv("VB200_SEG_FIRST")) h->opt_seg_first = std::max<int64_t>(VB_ROWS_PER_BLOCK, (int64_t)align_up((size_t)atoll(env), VB_ROWS_PER_BLOCK));
     if (const char* env = getenv("VB200_SEG_RATIO")) h->opt_seg_ratio = std::max<int64_t>(2, atoll(env));
     if (const char* env = getenv("VB200_OVERLAP")) h->opt_overlap = atoi(env);
+    if (const char* env = getenv("VB200_SPARSE_PRUNE")) h->opt_sparse_prune = atoi(env);
     *out = h;
     return 0;
 }
@@ -261,7 +265,7 @@ extern "C" void vb_destroy(vb_index* h) {
     cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->rows, &h->inv_norm, &h->scope_id, &h->created, &h->modified, &h->alive, &h->sp_indptr,
                       &h->sp_term, &h->sp_val, &h->post_row, &h->post_val, &h->args, &h->mask, &h->cand, &h->lists,
-                      &h->offs, &h->out, &h->q_hat, &h->q_bf16, &h->q_scale, &h->tmp})
+                      &h->offs, &h->plan, &h->out, &h->q_hat, &h->q_bf16, &h->q_scale, &h->tmp})
         dev_free(h, *b);
     for (HostBuf* b : {&h->h_args_s[0], &h->h_args_s[1], &h->h_out_s[0], &h->h_out_s[1], &h->h_stage}) if (b->p) cudaFreeHost(b->p);
     for (auto ev : h->prof_events) cudaEventDestroy(ev);
@@ -284,6 +288,8 @@ extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
     else if (k == "profile") h->opt_profile = value;
     else if (k == "slot") h->cur = value ? 1 : 0;                   // which of the two in-flight batches the staged calls address
     else if (k == "overlap") h->opt_overlap = value;               // 1: dense and sparse chains on two streams
+    else if (k == "sparse_prune_force") h->opt_sparse_prune_force = value;   // 1: prune in every non-direct segment (tests)
+    else if (k == "sparse_prune") h->opt_sparse_prune = value;     // MaxScore budget in % of tau (0: score every term's postings)
     else if (k == "k2_tiled") h->opt_k2_tiled = value;             // 0: never use the query-tiled kernel (multi-pass resident kernel instead)
     else if (k == "k2_precision") h->opt_k2_precision = value;   // 0 auto, 1 bf16 query, 2 bf16x2 (hi+lo) query
     else if (k == "stream") {   // run on the caller's stream (e.g. torch's current stream); 0 = own stream
@@ -497,6 +503,7 @@ static int ensure_sparse_index(vb_index* h) {
     if (!h->sparse_dirty) return 0;
     h->terms_sorted.clear();
     h->term_ptr.assign(1, 0);
+    h->term_maxval.clear();
     h->nnz_live = 0;
     if (h->nnz == 0) { h->sparse_dirty = false; return 0; }
     const uint64_t nnz = h->nnz;
@@ -553,6 +560,16 @@ static int ensure_sparse_index(vb_index* h) {
     CKC2(cub::DeviceScan::ExclusiveSum(cub_tmp.p, tb, runs.as<uint64_t>(), ptrs.as<uint64_t>(), (int)T, h->stream));
     h->terms_sorted.resize(T);
     h->term_ptr.resize((size_t)T + 1);
+    h->term_maxval.resize(T);
+    // per-term largest posting value (segmented max over the sorted postings); `runs` is free now
+    CKC2(cudaMemcpyAsync(ptrs.as<uint64_t>() + T, &live, 8, cudaMemcpyHostToDevice, h->stream));
+    tb = 0;
+    CKC2(cub::DeviceSegmentedReduce::Max(nullptr, tb, h->post_val.as<float>(), runs.as<float>(), (int)T,
+                                         ptrs.as<uint64_t>(), ptrs.as<uint64_t>() + 1, h->stream));
+    rc = dev_reserve(h, cub_tmp, tb, false); if (rc) { cleanup2(); return rc; }
+    CKC2(cub::DeviceSegmentedReduce::Max(cub_tmp.p, tb, h->post_val.as<float>(), runs.as<float>(), (int)T,
+                                         ptrs.as<uint64_t>(), ptrs.as<uint64_t>() + 1, h->stream));
+    CKC2(cudaMemcpyAsync(h->term_maxval.data(), runs.p, (size_t)T * 4, cudaMemcpyDeviceToHost, h->stream));
     CKC2(cudaMemcpyAsync(h->terms_sorted.data(), uniq.p, (size_t)T * 4, cudaMemcpyDeviceToHost, h->stream));
     CKC2(cudaMemcpyAsync(h->term_ptr.data(), ptrs.p, (size_t)T * 8, cudaMemcpyDeviceToHost, h->stream));
     CKC2(cudaStreamSynchronize(h->stream));
@@ -663,8 +680,8 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
 
     // ---- sparse queries: sort by term id, resolve posting ranges, apply IDF ----
     std::vector<int64_t> indptr(b.B + 1, 0);
-    std::vector<double> weight;
-    std::vector<uint32_t> qlo, qhi;
+    std::vector<double> weight, qub;
+    std::vector<uint32_t> qlo, qhi, qterm;
     if (sparse_enabled) {
         if (need_corpus) TRY(ensure_sparse_index(h));
         std::vector<std::pair<uint32_t, double>> tw;
@@ -679,9 +696,10 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
                 if (tw[t].first == tw[t - 1].first) return vb_fail("query %u repeats sparse index %u", i, tw[t].first);
             for (auto& pr : tw) {
                 uint64_t plo = 0, phi = 0;
+                int64_t slot = -1;
                 if (need_corpus) {
-                    const int64_t s = term_slot(h, pr.first);
-                    if (s >= 0) { plo = h->term_ptr[s]; phi = h->term_ptr[s + 1]; }
+                    slot = term_slot(h, pr.first);
+                    if (slot >= 0) { plo = h->term_ptr[slot]; phi = h->term_ptr[slot + 1]; }
                 }
                 double w = pr.second;
                 if (q->apply_idf) {
@@ -689,7 +707,13 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
                     // local_collection.py _compute_idf: log((N - df + 0.5) / (df + 0.5) + 1)
                     w = w * std::log(((double)h->n_live - df + 0.5) / (df + 0.5) + 1.0);
                 }
+                // MaxScore upper bound of this term's contribution to any row of the shard; +inf = "always
+                // essential" (non-positive or non-finite weights are never pruned)
+                double ub = INFINITY;
+                if (w > 0.0 && w < INFINITY) ub = (slot >= 0 && h->term_maxval[slot] > 0.0f) ? w * (double)h->term_maxval[slot] : 0.0;
                 weight.push_back(w);
+                qub.push_back(ub);
+                qterm.push_back(pr.first);
                 qlo.push_back((uint32_t)plo);
                 qhi.push_back((uint32_t)phi);
             }
@@ -734,6 +758,8 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     const size_t o_q = ar.take((size_t)b.B * h->dim * 4);
     const size_t o_ip = ar.take((b.B + 1) * 8);
     const size_t o_w = ar.take((size_t)b.n_qterms * 8 + 8);
+    const size_t o_ub = ar.take((size_t)b.n_qterms * 8 + 8);
+    const size_t o_tid = ar.take((size_t)b.n_qterms * 4 + 8);
     const size_t o_lo = ar.take((size_t)b.n_qterms * 4 + 8);
     const size_t o_hi = ar.take((size_t)b.n_qterms * 4 + 8);
     const size_t o_mo = ar.take((size_t)b.B * 4);
@@ -750,6 +776,8 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     memcpy(hp + o_ip, indptr.data(), (b.B + 1) * 8);
     if (b.n_qterms) {
         memcpy(hp + o_w, weight.data(), (size_t)b.n_qterms * 8);
+        memcpy(hp + o_ub, qub.data(), (size_t)b.n_qterms * 8);
+        memcpy(hp + o_tid, qterm.data(), (size_t)b.n_qterms * 4);
         memcpy(hp + o_lo, qlo.data(), (size_t)b.n_qterms * 4);
         memcpy(hp + o_hi, qhi.data(), (size_t)b.n_qterms * 4);
     }
@@ -770,6 +798,8 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     b.d_q = reinterpret_cast<const float*>(dp + o_q);
     b.d_qindptr = reinterpret_cast<const int64_t*>(dp + o_ip);
     b.d_qweight = reinterpret_cast<const double*>(dp + o_w);
+    b.d_qub = reinterpret_cast<const double*>(dp + o_ub);
+    b.d_qterm = reinterpret_cast<const uint32_t*>(dp + o_tid);
     b.d_qlo = reinterpret_cast<const uint32_t*>(dp + o_lo);
     b.d_qhi = reinterpret_cast<const uint32_t*>(dp + o_hi);
     b.d_maskof = reinterpret_cast<const int32_t*>(dp + o_mo);
@@ -942,9 +972,20 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
     auto sparse_segment = [&](uint32_t r0, uint32_t r1, uint32_t direct, bool big) -> int {
         if (do_sparse) {
             const int pi = prof_begin(h, PH_SPARSE | (big ? PH_BIG : 0), ss);
+            // which terms are essential under the thresholds this segment starts with
+            double* d_ubne = h->plan.as<double>();
+            uint8_t* d_ess = reinterpret_cast<uint8_t*>(d_ubne + b.B);
+            // Pruning pays when exact re-scoring is rare: a segment feeds ~seg_ratio * k' survivors per
+            // list, so it is switched on only where that is well below one survivor per row block.
+            const uint32_t nblk_seg = (r1 - r0 + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK;
+            const uint32_t budget = (!direct && (h->opt_sparse_prune_force || nblk_seg >= 40u * b.k)) ? (uint32_t)h->opt_sparse_prune : 0u;
+            vb_sparse_plan_kernel<<<b.B, 256, 0, ss>>>(b.d_qindptr, b.d_qub, b.tau, b.B, budget, d_ess, d_ubne);
+            CKK("vb_sparse_plan_kernel");
+            ++h->stats.last_launches;
             VbSparseArgs a{};
             a.post_row = h->post_row.as<uint32_t>(); a.post_val = h->post_val.as<float>(); a.off = h->offs.as<uint32_t>();
-            a.q_indptr = b.d_qindptr; a.q_weight = b.d_qweight;
+            a.q_indptr = b.d_qindptr; a.q_weight = b.d_qweight; a.q_term = b.d_qterm; a.ess = d_ess; a.ubne = d_ubne;
+            a.sp_indptr = h->sp_indptr.as<int64_t>(); a.sp_term = h->sp_term.as<uint32_t>(); a.sp_val = h->sp_val.as<float>();
             a.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; a.mask_of = b.use_mask ? b.d_maskof : nullptr;
             a.tau = b.tau; a.lists = L; a.mask_words = b.mask_words;
             a.n_qterms = b.n_qterms; a.nt_max = b.nt_max; a.blk_begin = r0 / VB_ROWS_PER_BLOCK; a.n_queries = b.B; a.n_rows = n;
@@ -967,6 +1008,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
         const int pi = prof_begin(h, PH_SPARSE, ss);
         const uint64_t total = (uint64_t)b.n_qterms * (b.n_blocks + 1);
         TRY(dev_reserve(h, h->offs, total * 4, false));
+        TRY(dev_reserve(h, h->plan, (size_t)b.B * 8 + b.n_qterms + 64, false));
         vb_slice_kernel<<<grid_for(total, 256), 256, 0, ss>>>(h->post_row.as<uint32_t>(), b.d_qlo, b.d_qhi, b.n_qterms, b.n_blocks, h->offs.as<uint32_t>());
         CKK("vb_slice_kernel");
         ++h->stats.last_launches;
