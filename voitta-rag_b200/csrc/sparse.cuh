@@ -145,7 +145,7 @@ vb_sparse_plan_kernel(const int64_t* __restrict__ q_indptr, const double* __rest
 }
 
 #define VB_SPARSE_THREADS 128
-#define VB_SPARSE_U 4u                                          // postings per thread per batch
+#define VB_SPARSE_U 2u                                          // postings per thread per batch
 #define VB_SPARSE_BATCH (VB_SPARSE_U * VB_SPARSE_THREADS)       // 512 postings per batch
 #define VB_SPARSE_PAD 32u                                       // dummy accumulators for padding lanes
 
