@@ -50,6 +50,10 @@ WORKLOADS = {
     # work of the 8-GPU run; needs --no-cpu-baseline (the fp32 host copy would not fit next to it)
     "cfg4-shard": dict(n=12_500_000, dim=768, batch=1024, limit=100, fusion="rrf", sel=0.5, dist="C",
                        desc="one 12.5M-row shard of 100M x 768-d hybrid, filter 50%, batch 1024, top-100"),
+    # BASELINE.json configs[3] itself when run with --gpus 8 (12.5M rows per GPU = 100M rows, batch 1024 for the whole
+    # job, top-100); at --gpus 2/4 the same per-GPU shard size with 25M/50M rows in total
+    "cfg4": dict(rows_per_gpu=12_500_000, n=12_500_000, dim=768, batch=1024, fixed_batch=True, limit=100, fusion="rrf", sel=0.5, dist="C",
+                 desc="100M x 768-d hybrid at 8 GPUs (12.5M rows per GPU), filter 50%, batch 1024, top-100"),
     # small shape for quick checks
     "tiny": dict(n=65_536, dim=128, batch=16, limit=10, fusion="rrf", sel=None, dist="C", desc="tiny smoke shape"),
 }
@@ -136,7 +140,7 @@ def build_shard(cfg, rank, world, device, torch, synth, engine):
 
 def make_batches(cfg, keep, world, synth, engine, torch):
     """Rank-0 query batches (dense fp32 + sparse terms) and, if the workload filters, one filter."""
-    B = cfg["batch"] * world
+    B = cfg["batch"] * (1 if cfg.get("fixed_batch") else world)
     batches = []
     for i in range(N_QUERY_BATCHES):
         q, sp = synth.queries(B, i, keep["rows"], keep["ip"], keep["tm"])
@@ -223,7 +227,9 @@ def main():
     ap.add_argument("--dense-path", type=int, default=0, help="0 auto, 1 GEMV scan, 2 tcgen05 GEMM")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    cfg = WORKLOADS[args.workload]
+    cfg = dict(WORKLOADS[args.workload])
+    if "rows_per_gpu" in cfg:
+        cfg["n"] = cfg["rows_per_gpu"] * max(1, args.gpus)
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
@@ -258,7 +264,7 @@ def main():
     if world > 1:
         dist.broadcast_object_list(obj, src=0)
     batches, flt = obj[0]
-    B = cfg["batch"] * world
+    B = cfg["batch"] * (1 if cfg.get("fixed_batch") else world)
     limit = cfg["limit"]
     hybrid = cfg["fusion"] != "dense"
     kprime = limit * 3 if hybrid else limit
@@ -309,6 +315,9 @@ def main():
     launches = 0
     for i in range(args.steps):
         st = stage(args.warmup + i)                 # host staging + H2D: outside the timed events
+        if world > 1:                               # ranks enter the step together: otherwise the all-gather of the
+            torch.cuda.synchronize(device)          # faster rank waits for the other's host staging inside the events
+            dist.barrier()
         ms[i], _ = device_step(st)
         launches += ix.stats()["last_launches"]
     barrier()
@@ -468,7 +477,7 @@ def main():
             "config": {"workload": f"{args.workload}: {cfg['desc']}", "rows_total": cfg["n"], "rows_per_gpu": rows_local,
                        "dim": cfg["dim"], "queries_per_step": B, "limit": limit, "kprime": kprime, "fusion": cfg["fusion"],
                        "selectivity": cfg["sel"], "dense_path": {1: "K1 GEMV scan", 2: "K2 tcgen05 GEMM"}.get(dense_path),
-                       "parallelism": f"row-sharded x{world}, batch {cfg['batch']}/GPU, NCCL all-gather of candidates" if world > 1 else "1 GPU",
+                       "parallelism": (f"row-sharded x{world}, batch {B} for the whole job, NCCL all-gather of candidates" if cfg.get("fixed_batch") else f"row-sharded x{world}, batch {cfg['batch']}/GPU, NCCL all-gather of candidates") if world > 1 else "1 GPU",
                        "l2": "corpus per GPU (%.0f MB bf16 + postings) exceeds the 126 MB L2; %d distinct query batches rotate" % (rows_local * d_pad * 2 / 1e6, len(batches))},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "parity_spot_check": parity,

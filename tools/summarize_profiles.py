@@ -30,7 +30,7 @@ def raw(rep):
 def main():
     PROF.mkdir(exist_ok=True)
     lines = []
-    for name in ("gemm", "sparse"):
+    for name in ("gemm", "sparse", "tiled"):
         rep = OUT / f"{R}_prof_{name}.ncu-rep"
         if not rep.exists():
             continue
@@ -66,9 +66,27 @@ def main():
             out.append("# one search step, launch by launch (us, grid):")
             out += [f"  {n:44s} {t:9.2f} {g}" for n, t, g in seq[starts[-2]:starts[-1]]]
         (PROF / f"{R}_launches_cfg2.txt").write_text("\n".join(out) + "\n")
-    for f in (f"{R}_bench_cfg2.json", f"{R}_bench_reference.json", f"{R}_pytest_gpu.log", f"{R}_smoke.log"):
-        if (OUT / f).exists():
-            shutil.copy(OUT / f, PROF / f)
+    for f in sorted(OUT.glob(f"{R}_bench_*.json")) + [OUT / f"{R}_pytest_gpu.log", OUT / f"{R}_smoke.log"]:
+        if f.exists() and f.stat().st_size:
+            shutil.copy(f, PROF / f.name)
+    # dram bytes per launch of the captured kernels -> traffic.json (bench.py's roofline.traffic)
+    traffic = {}
+    for name, wl, kern in (("gemm", "cfg2", "vb_dense_gemm_kernel"), ("sparse", "cfg2", "vb_sparse_kernel"),
+                           ("tiled", "cfg3-b256-s50", "vb_dense_gemm_tiled_kernel")):
+        rep = OUT / f"{R}_prof_{name}.ncu-rep"
+        if not rep.exists():
+            continue
+        hdr, units, data = raw(rep)
+        idx = {h: i for i, h in enumerate(hdr)}
+        def val(k):
+            v = float(data[0][idx[k]].replace(",", ""))
+            u = units[idx[k]].lower()
+            return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+        traffic.setdefault(wl, {})[kern] = {"dram_bytes_per_launch": int(val("dram__bytes_read.sum") + val("dram__bytes_write.sum")),
+                                            "capture": rep.name}
+    if traffic:
+        traffic["_comment"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, from the ncu --set full captures summarised in %s_ncu_summary.txt (largest segment launch of a step)" % R
+        (PROF / "traffic.json").write_text(json.dumps(traffic, indent=1) + "\n")
     print("\n".join(lines[:60]))
 
 
