@@ -54,6 +54,10 @@ WORKLOADS = {
     # job, top-100); at --gpus 2/4 the same per-GPU shard size with 25M/50M rows in total
     "cfg4": dict(rows_per_gpu=12_500_000, n=12_500_000, dim=768, batch=1024, fixed_batch=True, limit=100, fusion="rrf", sel=0.5, dist="C",
                  desc="100M x 768-d hybrid at 8 GPUs (12.5M rows per GPU), filter 50%, batch 1024, top-100"),
+    # BASELINE.json configs[4] as one of its 8 row shards: MCP replay, 4096 mixed-length queries (2..64 sparse terms),
+    # 50M x 1024-d / 8 = 6.25M rows per GPU, filtered top-20
+    "cfg5-shard": dict(n=6_250_000, dim=1024, batch=4096, limit=20, fusion="rrf", sel=0.5, dist="C", qnnz=(2, 64),
+                       desc="one 6.25M-row shard of 50M x 1024-d MCP replay, 4096 mixed-length queries, filter 50%, top-20"),
     # small shape for quick checks
     "tiny": dict(n=65_536, dim=128, batch=16, limit=10, fusion="rrf", sel=None, dist="C", desc="tiny smoke shape"),
 }
@@ -143,7 +147,7 @@ def make_batches(cfg, keep, world, synth, engine, torch):
     B = cfg["batch"] * (1 if cfg.get("fixed_batch") else world)
     batches = []
     for i in range(N_QUERY_BATCHES):
-        q, sp = synth.queries(B, i, keep["rows"], keep["ip"], keep["tm"])
+        q, sp = synth.queries(B, i, keep["rows"], keep["ip"], keep["tm"], nnz=cfg.get("qnnz", (3, 12)))
         batches.append((q, sp if cfg["fusion"] != "dense" else None))
     flt = None
     if cfg["sel"] is not None:

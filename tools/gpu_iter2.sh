@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/it_pytest.log 2>&1; echo "gpu tests rc=$?"; tail -5 gpurun_out/it_pytest.log
 for W in ${@:-cfg2}; do
-  ST=300; [ "$W" = "cfg3-b256-s50" ] && ST=20; [ "$W" = "cfg4-shard" ] && ST=5; [ "$W" = "cfg3-b1-s50" ] && ST=100
+  ST=300; [ "$W" = "cfg3-b256-s50" ] && ST=20; [ "$W" = "cfg4-shard" ] && ST=5; [ "$W" = "cfg5-shard" ] && ST=3; [ "$W" = "cfg3-b1-s50" ] && ST=100
   timeout 900 python bench.py --workload $W --steps $ST --warmup 5 --no-cpu-baseline > gpurun_out/it_$W.json 2> gpurun_out/it_$W.err; echo "$W rc=$?"
   python - $W <<'PY'
 import json, sys
