@@ -102,6 +102,7 @@ typedef struct vb_stats {
     uint64_t last_dense_passes;                /* passes over the shard's dense rows (K1: B, K2: sub-batches) */
     uint64_t last_big_rows;                    /* rows of the largest (last) segment of the last search */
     double   last_dense_big_ms, last_sparse_big_ms;  /* profile: dense / sparse kernel time of that segment */
+    uint64_t dim, row_base;                    /* geometry of the index (what vb_load restored)            */
 } vb_stats;
 
 int         vb_abi_version(void);
@@ -174,6 +175,14 @@ int vb_set_option(vb_index* h, const char* key, int64_t value);
 
 int vb_get_stats(vb_index* h, vb_stats* out);
 int vb_sync(vb_index* h);
+
+/* Snapshot of everything the shard holds on the device: bf16 rows, inverse norms, filter columns,
+ * tombstones and the forward sparse CSR (the inverted index is derived data and is rebuilt on the
+ * first search after vb_load).  Stands in for Qdrant's on-disk storage (/qdrant/storage,
+ * docker-compose.yml:8-9): the host side (ids, payloads) is saved next to it by the Python layer.
+ * vb_load creates a new index on `device` with the snapshot's dimension and row_base. */
+int vb_save(vb_index* h, const char* path);
+int vb_load(const char* path, int32_t device, vb_index** out);
 
 #ifdef __cplusplus
 }

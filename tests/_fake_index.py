@@ -27,6 +27,19 @@ class FakeIndex:
     def close(self):
         self._cc = None
 
+    def save(self, path):
+        with open(path, "wb") as f:
+            np.savez(f, dim=self.dim, dense=self.dense, indptr=self.indptr, terms=self.terms, vals=self.vals,
+                     scope=self.scope, created=self.created, modified=self.modified, alive=self.alive)
+
+    @classmethod
+    def load(cls, path):
+        z = np.load(path)
+        self = cls(int(z["dim"]))
+        for k in ("dense", "indptr", "terms", "vals", "scope", "created", "modified", "alive"):
+            setattr(self, k, z[k])
+        return self
+
     def upsert(self, dense, sparse_csr=None, scope_id=None, created=None, modified=None):
         n = len(dense)
         first = len(self.dense)

@@ -93,3 +93,32 @@ def test_error_conventions(store):
     assert store._build_filter() is None and store._build_filter(include_folders=[]) is None
     f = store._build_filter(include_folders=["a"], date_end=5, date_field="created")
     assert f.ts_field == 1 and f.ts_hi == 5 and f.scope_bits[0] == 1
+
+
+def test_snapshot_roundtrip_restores_ids_payloads_and_results(store, tmp_path):
+    """save_snapshot / load_snapshot (stand-in for Qdrant's storage volume): after ingest + deletes the
+    restored collection answers every helper and every search exactly as the original."""
+    corpus, queries = G.build_inputs()
+    split = next(i for i, op in enumerate(GOLD["ops"]) if op["op"] == "search")
+    while GOLD["ops"][split]["op"] == "search":
+        split += 1
+    ops = GOLD["ops"]
+    ctx = {}
+    head = G.replay(store, ops[:split], corpus, queries, VS.ChunkMetadata, ctx)
+    info = store.save_snapshot(str(tmp_path))
+    assert info["live"] == store.get_collection_info()["points_count"] and Path(info["device_file"]).exists()
+    before = {fp: store.count_by_file(fp) for fp in {m["file_path"] for m in corpus["metas"]}}
+    searches = [op for op in ops[:split] if op["op"] == "search"]
+    want = G.replay(store, searches, corpus, queries, VS.ChunkMetadata, dict(ctx))
+    # a different process: forget the collection, restore it from the snapshot
+    VS._drop_collection("host_layer_test")
+    fresh = VS.VectorStoreService(_index_factory=lambda: FakeIndex(GOLD["dim"]))
+    assert fresh.get_collection_info()["points_count"] == 0
+    assert fresh.load_snapshot(str(tmp_path), _index_loader=FakeIndex.load) == info["live"]
+    assert {fp: fresh.count_by_file(fp) for fp in before} == before
+    got = G.replay(fresh, searches, corpus, queries, VS.ChunkMetadata, dict(ctx))
+    assert json.loads(json.dumps(got)) == json.loads(json.dumps(want))
+    # and it keeps working as a live collection: ingest and delete after the restore
+    m = VS.ChunkMetadata("z/new.txt", "z", "z", "new.txt", 0, 1, 0, 1, "t")
+    ids = fresh.store_chunks([("t", [1.0] * GOLD["dim"], m)], [([3, 9], [1.0, 2.0])])
+    assert len(ids) == 1 and fresh.count_by_file("z/new.txt") == 1 and fresh.delete_by_file("z/new.txt") == 1

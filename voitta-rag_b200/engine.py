@@ -59,14 +59,15 @@ class _Stats(C.Structure):
                 ("last_select_ms", C.c_double), ("last_mask_ms", C.c_double), ("last_fuse_ms", C.c_double),
                 ("last_dense_path", C.c_uint32), ("last_launches", C.c_uint32), ("device_bytes", C.c_uint64),
                 ("last_h2d_bytes", C.c_uint64), ("last_d2h_bytes", C.c_uint64), ("last_dense_passes", C.c_uint64),
-                ("last_big_rows", C.c_uint64), ("last_dense_big_ms", C.c_double), ("last_sparse_big_ms", C.c_double)]
+                ("last_big_rows", C.c_uint64), ("last_dense_big_ms", C.c_double), ("last_sparse_big_ms", C.c_double),
+                ("dim", C.c_uint64), ("row_base", C.c_uint64)]
 
 
 # every symbol include/voitta_b200.h declares
 EXPORTS = ["vb_abi_version", "vb_last_error", "vb_create", "vb_destroy", "vb_upsert", "vb_upsert_dev",
            "vb_delete_rows", "vb_term_stats", "vb_search", "vb_search_local", "vb_merge_fuse",
            "vb_stage", "vb_run_local", "vb_run_fuse", "vb_fetch",
-           "vb_set_option", "vb_get_stats", "vb_sync"]
+           "vb_set_option", "vb_get_stats", "vb_sync", "vb_save", "vb_load"]
 
 _lib = None
 
@@ -100,6 +101,8 @@ def load_library():
     lib.vb_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.vb_get_stats.argtypes = [vp, C.POINTER(_Stats)]
     lib.vb_sync.argtypes = [vp]
+    lib.vb_save.argtypes = [vp, C.c_char_p]
+    lib.vb_load.argtypes = [C.c_char_p, C.c_int32, C.POINTER(vp)]
     _lib = lib
     return lib
 
@@ -234,6 +237,26 @@ class Index:
     def _check(self, rc):
         if rc != 0:
             raise B200Error(self._lib.vb_last_error().decode("utf-8", "replace"))
+
+    # ---- snapshot ---------------------------------------------------------------------------
+    def save(self, path) -> None:
+        """Write the shard's device data (rows, columns, tombstones, forward sparse CSR) to ``path``."""
+        self._check(self._lib.vb_save(self._h, str(path).encode()))
+
+    @classmethod
+    def load(cls, path, device: int = 0) -> "Index":
+        """A new Index on ``device`` from a snapshot written by ``save``."""
+        self = cls.__new__(cls)
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self.device = int(device)
+        rc = self._lib.vb_load(str(path).encode(), self.device, C.byref(self._h))
+        if rc != 0:
+            raise B200Error(self._lib.vb_last_error().decode("utf-8", "replace"))
+        st = self.stats()
+        self.dim = int(st["dim"])
+        self.row_base = int(st["row_base"])
+        return self
 
     def close(self):
         if self._h:

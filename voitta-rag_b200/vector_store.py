@@ -21,6 +21,8 @@ from __future__ import annotations
 
 import logging
 import os
+import pickle
+from pathlib import Path
 import threading
 import uuid
 from dataclasses import dataclass
@@ -77,6 +79,8 @@ class _Settings:
         self.embedding_dimension = int(os.getenv("EMBEDDING_DIMENSION", "768"))
         self.device = int(os.getenv("VOITTA_B200_DEVICE", "0"))
         self.fusion = os.getenv("VOITTA_FUSION", "weighted")
+        # directory of a snapshot to restore on first use (stands in for Qdrant's storage volume)
+        self.snapshot_dir = os.getenv("VOITTA_B200_SNAPSHOT_DIR") or None
 
 
 def get_settings() -> _Settings:
@@ -178,6 +182,53 @@ class _Collection:
     def live_rows(self):
         return (r for r, p in enumerate(self.payload) if p is not None)
 
+    # ---- snapshot: <dir>/<name>.vb200 (device data, vb_save) + <dir>/<name>.host.pkl (ids, payloads) ----
+    def snapshot_paths(self, directory):
+        d = Path(directory)
+        return d / f"{self.name}.vb200", d / f"{self.name}.host.pkl"
+
+    def save(self, directory) -> dict:
+        dev_path, host_path = self.snapshot_paths(directory)
+        Path(directory).mkdir(parents=True, exist_ok=True)
+        with self.lock:
+            self.index.save(dev_path)
+            with open(host_path, "wb") as f:
+                pickle.dump({"version": 1, "name": self.name, "dim": self.dim, "ids": self.ids,
+                             "payload": self.payload, "scope_list": self.scope_list}, f, protocol=pickle.HIGHEST_PROTOCOL)
+        return {"rows": len(self.ids), "live": self.n_live, "device_file": str(dev_path), "host_file": str(host_path)}
+
+    def load(self, directory, index_loader=None) -> int:
+        """Replace this collection's contents with a snapshot.  Returns the number of live points."""
+        dev_path, host_path = self.snapshot_paths(directory)
+        with open(host_path, "rb") as f:
+            st = pickle.load(f)
+        if st.get("version") != 1 or st["dim"] != self.dim:
+            raise ValueError(f"snapshot {host_path} does not match collection '{self.name}' (dim {self.dim})")
+        loader = index_loader or (lambda path: engine.Index.load(path, device=self.device))
+        with self.lock:
+            new_index = loader(dev_path)
+            if self._index is not None:
+                self._index.close()
+            self._index = new_index
+            self.ids, self.payload = [], []
+            self.n_live = 0
+            self.by_file, self.by_folder, self.by_index_folder, self.by_url = {}, {}, {}, {}
+            self.scope_list = [tuple(k) for k in st["scope_list"]]
+            self.scopes = {k: i for i, k in enumerate(self.scope_list)}
+            live = [(r, p) for r, p in enumerate(st["payload"])]
+            self.ids = list(st["ids"])
+            self.payload = [None] * len(self.ids)
+            for r, pl in live:
+                if pl is None:
+                    continue
+                self.payload[r] = pl
+                self._map_add(self.by_file, pl["file_path"], r)
+                self._map_add(self.by_folder, pl["folder_path"], r)
+                self._map_add(self.by_index_folder, pl["index_folder"], r)
+                self._map_add(self.by_url, pl.get("source_url"), r)
+                self.n_live += 1
+            return self.n_live
+
 
 _collections: dict[str, _Collection] = {}
 _collections_lock = threading.Lock()
@@ -188,6 +239,10 @@ def _get_collection(name: str, dim: int, device: int, index_factory=None) -> _Co
         c = _collections.get(name)
         if c is None:
             c = _Collection(name, dim, device, index_factory)
+            snap = get_settings().snapshot_dir
+            if snap and index_factory is None and all(p.exists() for p in c.snapshot_paths(snap)):
+                logger.info(f"Restoring collection '{name}' from {snap}")
+                c.load(snap)
             _collections[name] = c
         elif c.dim != dim:
             raise ValueError(f"collection '{name}' exists with dimension {c.dim}, requested {dim}")
@@ -488,6 +543,26 @@ class VectorStoreService:
             return [self._rows_to_chunks(coll, res.hits(i)) for i in range(B)]
 
     # ---- collection / scroll helpers (reference :699-1016) --------------------------------------
+    # ---- persistence (additive: the reference relies on Qdrant's storage volume) --------------------
+    def save_snapshot(self, directory: str | None = None) -> dict:
+        """Write the collection (device index + ids/payloads) under ``directory``
+        (default: $VOITTA_B200_SNAPSHOT_DIR).  A process started with that variable set restores it
+        on first use."""
+        directory = directory or get_settings().snapshot_dir
+        if not directory:
+            raise ValueError("no snapshot directory given and VOITTA_B200_SNAPSHOT_DIR is not set")
+        return self._coll.save(directory)
+
+    def load_snapshot(self, directory: str | None = None, _index_loader=None) -> int:
+        """Replace the collection's contents with the snapshot under ``directory``; returns live points."""
+        directory = directory or get_settings().snapshot_dir
+        if not directory:
+            raise ValueError("no snapshot directory given and VOITTA_B200_SNAPSHOT_DIR is not set")
+        n = self._coll.load(directory, _index_loader)
+        self._client = self._coll.index
+        self._ensure_collection()
+        return n
+
     def get_collection_info(self) -> dict:
         """Information about the collection (reference :699)."""
         try:
