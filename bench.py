@@ -58,6 +58,9 @@ WORKLOADS = {
     # 50M x 1024-d / 8 = 6.25M rows per GPU, filtered top-20
     "cfg5-shard": dict(n=6_250_000, dim=1024, batch=4096, limit=20, fusion="rrf", sel=0.5, dist="C", qnnz=(2, 64),
                        desc="one 6.25M-row shard of 50M x 1024-d MCP replay, 4096 mixed-length queries, filter 50%, top-20"),
+    # the per-GPU work of cfg2 at 8 GPUs (125k rows, batch 512): for profiling the weak-scaling overheads on one GPU
+    "cfg2-g8shard": dict(n=125_000, dim=384, batch=512, limit=10, fusion="rrf", sel=None, dist="C",
+                         desc="one 125k-row shard of cfg2 at 8 GPUs, batch 512, top-10"),
     # small shape for quick checks
     "tiny": dict(n=65_536, dim=128, batch=16, limit=10, fusion="rrf", sel=None, dist="C", desc="tiny smoke shape"),
 }

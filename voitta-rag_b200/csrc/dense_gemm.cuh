@@ -427,7 +427,7 @@ struct VbGemmTiledArgs {
     int32_t  uniform_filter;
 };
 
-template <int MODE>
+template <int MODE, bool DIRECT>
 __global__ void __launch_bounds__(VB_GEMM_THREADS, 1)
 vb_dense_gemm_tiled_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_q,
                            const VbGemmTiledArgs a)
@@ -581,7 +581,21 @@ vb_dense_gemm_tiled_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
                             m |= (p & 1u) << jj;
                         }
                     }
-                    if (__any_sync(0xffffffffu, m != 0u)) {
+                    if (DIRECT) {
+                        // first segment: every key goes to its fixed slot (row - segment begin), no atomics
+                        if (row_ok) {
+                            const uint32_t dslot = row - a.tile_begin * VB_TILE_M;
+#pragma unroll
+                            for (uint32_t jj = 0; jj < 16u; ++jj) {
+                                const uint32_t col = qoff + c0 + jj;
+                                if (col < a.n_q) {
+                                    const float fs = __uint_as_float(v[jj]) * invn * qs_s[col];
+                                    a.lists.cand[(size_t)(a.q_begin + col) * a.lists.cap + dslot] =
+                                        (((m >> jj) & 1u) && fs > tex_s[col]) ? vb_pack_key(fs, a.row_base + row) : 0ull;
+                                }
+                            }
+                        }
+                    } else if (__any_sync(0xffffffffu, m != 0u)) {
                         // rare path: exact comparison on the scaled score, reserve slots for all survivors
                         // of the chunk, then store the keys
 #pragma unroll
@@ -667,9 +681,12 @@ static int vb_gemm_configure() {
         e = cudaFuncSetAttribute(vb_gemm_variant(i), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { g_gemm_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
     }
-    e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { g_gemm_err = std::string("cudaFuncSetAttribute(tiled): ") + cudaGetErrorString(e); return 1; }
     g_gemm_smem_max = smem;
     g_encode_tiled = reinterpret_cast<VbEncodeTiledFn>(fn);
@@ -854,9 +871,15 @@ static int vb_gemm_tiled_launch(const VbGemmLaunch& g, int* launches) {
         const size_t smem = 1024u + (size_t)stages * VB_TILED_STAGE_BYTES + VB_TILED_TAIL_BYTES;
         const uint32_t tiles = a.tile_end - a.tile_begin;
         const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)g.sm_count);
-        if (a.mask_mode == 2u) vb_dense_gemm_tiled_kernel<2><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
-        else if (a.mask_mode == 3u) vb_dense_gemm_tiled_kernel<3><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
-        else vb_dense_gemm_tiled_kernel<0><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
+        if (g.direct) {
+            if (a.mask_mode == 2u) vb_dense_gemm_tiled_kernel<2, true><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
+            else if (a.mask_mode == 3u) vb_dense_gemm_tiled_kernel<3, true><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
+            else vb_dense_gemm_tiled_kernel<0, true><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
+        } else {
+            if (a.mask_mode == 2u) vb_dense_gemm_tiled_kernel<2, false><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
+            else if (a.mask_mode == 3u) vb_dense_gemm_tiled_kernel<3, false><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
+            else vb_dense_gemm_tiled_kernel<0, false><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
+        }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { g_gemm_err = std::string("tiled launch failed: ") + cudaGetErrorString(e); return 1; }
         ++*launches;

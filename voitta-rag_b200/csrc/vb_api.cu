@@ -919,7 +919,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
     VbGemmPlan plan{1u, 0u};
     if (path == 2) plan = vb_gemm_plan((uint32_t)h->d_pad, b.B, (int)h->opt_k2_precision);
     // batches too large to sit resident in shared memory go to the query-tiled, tensor-bound kernel
-    // (one corpus pass per 1024 queries); the first (direct) segment always uses the resident kernel
+    // (one corpus pass per 1024 queries)
     const bool tiled = path == 2 && b.B > plan.sub && !plan.split && h->opt_k2_tiled && vb_gemm_tiled_supported(h->d_pad);
     h->stats.last_dense_passes = path == 2 ? (tiled ? (b.B + VB_TILED_MAX_Q - 1) / VB_TILED_MAX_Q : (b.B + plan.sub - 1) / plan.sub) : b.B;
     // query prep (fp32 unit queries for K1, packed bf16 operand for K2)
@@ -963,7 +963,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
             g.d_pad = (uint32_t)h->d_pad; g.n_queries = b.B; g.sm_count = h->sm_count; g.stream = sd;
             g.direct = direct; g.plan = plan; g.mask_of_host = b.mask_of_host.data();
             int launches = 0;
-            if ((tiled && !direct ? vb_gemm_tiled_launch(g, &launches) : vb_gemm_launch(g, &launches)) != 0)
+            if ((tiled ? vb_gemm_tiled_launch(g, &launches) : vb_gemm_launch(g, &launches)) != 0)
                 return vb_fail("tensor-core dense kernel: %s", vb_gemm_last_error());
             h->stats.last_launches += (uint32_t)launches;
         } else {
