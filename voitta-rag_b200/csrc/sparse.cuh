@@ -52,6 +52,15 @@ vb_posting_split_kernel(const uint64_t* __restrict__ keys, uint64_t nnz, uint32_
     }
 }
 
+// Dense column of a frequent term: out[row] = the term's value in that row (out is pre-filled with NaN).
+__global__ void __launch_bounds__(256)
+vb_heavy_fill_kernel(const uint32_t* __restrict__ post_row, const float* __restrict__ post_val, uint64_t lo, uint64_t hi,
+                     float* __restrict__ out)
+{
+    for (uint64_t p = lo + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < hi; p += (uint64_t)gridDim.x * blockDim.x)
+        out[post_row[p]] = post_val[p];
+}
+
 // ---- per-batch slice table ----------------------------------------------------------------------
 // off[b][j] = first posting of query-term j whose row >= b*VB_ROWS_PER_BLOCK  (b = 0..n_blocks),
 // block-major so that the CTA of (row block, query) reads its terms' bounds as two contiguous runs.
@@ -84,6 +93,10 @@ struct VbSparseArgs {
     const uint32_t* q_term;     // [n_qterms] term ids (ascending per query)
     const uint8_t* ess;         // [n_qterms] 1 = essential term for the current thresholds; nullptr = all
     const double* ubne;         // [B] sum of the upper bounds of the query's non-essential terms
+    const int32_t* q_hidx;      // [n_qterms] dense-column index of the term for this query, -1 = scored from postings
+    const uint8_t* q_relaxed;   // [B] 1 = all products of this query are >= 0: order-free accumulation + verification allowed
+    const float* heavy_vals;    // [n_heavy][heavy_stride] value of the term in each row, NaN = absent
+    uint32_t heavy_stride;
     const int64_t* sp_indptr;   // forward index (row-major CSR as appended), for exact re-scoring
     const uint32_t* sp_term;
     const float* sp_val;
@@ -150,7 +163,7 @@ vb_sparse_plan_kernel(const int64_t* __restrict__ q_indptr, const double* __rest
 #define VB_SPARSE_PAD 32u                                       // dummy accumulators for padding lanes
 
 static size_t vb_sparse_smem_bytes(uint32_t nt_max) {
-    return (size_t)(VB_ROWS_PER_BLOCK + VB_SPARSE_PAD) * 8u + (size_t)VB_ROWS_PER_BLOCK * 2u + (size_t)nt_max * 20u + 32u;
+    return (size_t)(VB_ROWS_PER_BLOCK + VB_SPARSE_PAD) * 8u + (size_t)VB_ROWS_PER_BLOCK * 2u + (size_t)nt_max * 27u + 48u;
 }
 
 // grid.x = (#blocks in segment) * B ; CTA (blk, q) with q fastest so that concurrently running
@@ -172,7 +185,7 @@ static size_t vb_sparse_smem_bytes(uint32_t nt_max) {
 //   acc = acc + (w*v + 0.0) reproduces Python's `result = 0.0; result += w*v` bit for bit (the only
 //   differences would involve -0.0, which both sides turn into +0.0) while an untouched row is
 //   still recognisable (-0.0 can never be a sum).
-__global__ void __launch_bounds__(VB_SPARSE_THREADS, 10)
+__global__ void __launch_bounds__(VB_SPARSE_THREADS, 8)
 vb_sparse_kernel(const VbSparseArgs a)
 {
     extern __shared__ __align__(16) unsigned char vb_sp_smem[];
@@ -183,7 +196,10 @@ vb_sparse_kernel(const VbSparseArgs a)
     uint16_t* s_surv = reinterpret_cast<uint16_t*>(s_hi + a.nt_max);        // [VB_ROWS_PER_BLOCK] rows to re-score
     uint16_t* s_nz = s_surv + VB_ROWS_PER_BLOCK;                            // [nt_max] non-empty ESSENTIAL terms, ascending
     uint16_t* s_all = s_nz + a.nt_max;                                      // [nt_max] all non-empty terms, ascending
-    __shared__ uint32_t s_nnz, s_nall, s_nsurv;
+    uint16_t* s_hv = s_all + a.nt_max;                                      // [nt_max] terms scored from their dense column
+    uint32_t* s_cum = reinterpret_cast<uint32_t*>(s_hv + a.nt_max + (a.nt_max & 1u));   // [nt_max + 1] posting prefix sums over s_nz
+    uint8_t* s_flag = reinterpret_cast<uint8_t*>(s_cum + a.nt_max + 1u);                // [nt_max] bit0 postings here, bit1 essential, bit2 dense column
+    __shared__ uint32_t s_nnz, s_nall, s_nsurv, s_nheavy;
 
     const uint32_t tid = threadIdx.x;
     const uint32_t q = blockIdx.x % a.n_queries;
@@ -194,9 +210,14 @@ vb_sparse_kernel(const VbSparseArgs a)
     if (nt == 0) return;                                        // dense-only query
 
     for (uint32_t j = tid; j < nt; j += VB_SPARSE_THREADS) {
-        s_lo[j] = __ldg(a.off + (size_t)blk * a.n_qterms + t_lo + j);
-        s_hi[j] = __ldg(a.off + (size_t)(blk + 1u) * a.n_qterms + t_lo + j);
+        const uint32_t lo = __ldg(a.off + (size_t)blk * a.n_qterms + t_lo + j);
+        const uint32_t hi = __ldg(a.off + (size_t)(blk + 1u) * a.n_qterms + t_lo + j);
+        const bool es = a.ess == nullptr || __ldg(a.ess + t_lo + j) != 0;
+        const bool hv = a.q_hidx != nullptr && __ldg(a.q_hidx + t_lo + j) >= 0;
         s_w[j] = __ldg(a.q_weight + t_lo + j);
+        s_lo[j] = lo;
+        s_hi[j] = hi;
+        s_flag[j] = (uint8_t)((hi > lo ? 1u : 0u) | (es ? 2u : 0u) | (hv ? 4u : 0u));
     }
     const uint32_t list = a.n_queries + q;                      // sparse lists follow the dense ones
     const float tau = a.tau[list];
@@ -211,24 +232,43 @@ vb_sparse_kernel(const VbSparseArgs a)
         *reinterpret_cast<double2*>(&acc[r]) = make_double2(neg_zero, neg_zero);
     __syncthreads();
     if (tid < 32u) {                                            // ordered compaction of the non-empty terms
-        uint32_t base = 0, base_all = 0;
+        uint32_t base = 0, base_all = 0, base_hv = 0, cum_base = 0, n_skip = 0;
+        if (tid == 0) s_cum[0] = 0u;
         for (uint32_t j0 = 0; j0 < nt; j0 += 32u) {
             const uint32_t j = j0 + tid;
-            const bool ne = j < nt && s_hi[j] > s_lo[j];
-            const bool es = ne && (a.ess == nullptr || a.ess[t_lo + j] != 0);
+            const uint32_t fl = j < nt ? s_flag[j] : 0u;
+            const bool ne = (fl & 1u) != 0u;                                         // postings in this block
+            const bool es = (fl & 3u) == 3u;                                         // ... of an essential term
+            const bool hv = (fl & 6u) == 6u;                                         // essential term with a dense column
+            n_skip += __popc(__ballot_sync(0xffffffffu, (fl & 6u) == 4u));           // dense-column terms skipped as non-essential
             const uint32_t bal_all = __ballot_sync(0xffffffffu, ne);
             const uint32_t bal = __ballot_sync(0xffffffffu, es);
+            const uint32_t bal_hv = __ballot_sync(0xffffffffu, hv);
             if (ne) s_all[base_all + __popc(bal_all & ((1u << tid) - 1u))] = (uint16_t)j;
-            if (es) s_nz[base + __popc(bal & ((1u << tid) - 1u))] = (uint16_t)j;
+            uint32_t incl = es ? s_hi[j] - s_lo[j] : 0u;                             // running posting count over s_nz
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= (uint32_t)o) incl += t;
+            }
+            if (es) {
+                const uint32_t k = base + __popc(bal & ((1u << tid) - 1u));
+                s_nz[k] = (uint16_t)j;
+                s_cum[k + 1u] = cum_base + incl;
+            }
+            cum_base += __shfl_sync(0xffffffffu, incl, 31);
+            if (hv) s_hv[base_hv + __popc(bal_hv & ((1u << tid) - 1u))] = (uint16_t)j;
             base += __popc(bal);
             base_all += __popc(bal_all);
+            base_hv += __popc(bal_hv);
         }
-        if (tid == 0) { s_nnz = base; s_nall = base_all; s_nsurv = 0u; }
+        if (tid == 0) { s_nnz = base; s_nall = base_all + n_skip; s_nheavy = base_hv; s_nsurv = 0u; }
     }
     __syncthreads();
     const uint32_t nnz = s_nnz;                                 // essential terms with postings in this block
-    const uint32_t n_all = s_nall;
-    if (nnz == 0) return;                                       // no row of this block can beat tau (direct-mode slots were zeroed by the host)
+    const uint32_t n_all = s_nall;                              // terms that can touch this block (postings here, or a skipped dense column)
+    const uint32_t nh = s_nheavy;                               // terms read from their dense column (every block)
+    if (nnz == 0 && nh == 0) return;                            // no row of this block can beat tau (direct-mode slots were zeroed by the host)
 
     const uint32_t row0 = blk * VB_ROWS_PER_BLOCK;
     const uint32_t dummy = VB_ROWS_PER_BLOCK + (tid & 31u);     // this lane's private padding slot
@@ -257,7 +297,23 @@ vb_sparse_kernel(const VbSparseArgs a)
         }
     };
 
-    {
+    const bool relaxed = a.q_relaxed != nullptr && __ldg(a.q_relaxed + q) != 0;
+    if (nnz != 0u && relaxed) {
+        // Order-free accumulation (verified afterwards, see below): all essential slices of this block form one
+        // index space walked 128 postings at a time; a row may be hit by several terms at once, so the adds are
+        // shared-memory atomics (a CAS loop for fp64 — affordable: frequent terms never come this way).
+        const uint32_t P = s_cum[nnz];
+        uint32_t k = 0;
+        for (uint32_t pos = tid; pos < P; pos += VB_SPARSE_THREADS) {
+            while (s_cum[k + 1u] <= pos) ++k;
+            const uint32_t j = s_nz[k];
+            const uint32_t pp = s_lo[j] + (pos - s_cum[k]);
+            const uint32_t r = __ldg(prow + pp) - row0;
+            const float v = __ldg(pval + pp);
+            atomicAdd(&acc[r], __dadd_rn(__dmul_rn(s_w[j], (double)v), 0.0));
+        }
+        __syncthreads();
+    } else if (nnz != 0u) {
         uint32_t rA[VB_SPARSE_U], rB[VB_SPARSE_U];
         float vA[VB_SPARSE_U], vB[VB_SPARSE_U];
         uint32_t ti = 0, term = s_nz[0], p0 = s_lo[term], hi = s_hi[term];
@@ -287,8 +343,8 @@ vb_sparse_kernel(const VbSparseArgs a)
     const uint32_t seg_row0 = a.blk_begin * VB_ROWS_PER_BLOCK;
     const uint32_t sub = blk_rel & a.lists.sub_mask;            // append counter of this row block
     const double tau_d = (double)tau;
-    if (n_all == nnz) {
-        // Every term with postings here was accumulated: the accumulators hold the exact scores.
+    if (n_all == nnz && nh == 0u && !relaxed) {
+        // Every term with postings here was accumulated in term order: the accumulators hold the exact scores.
         // Scan two per thread per step.  Cheap exact prefilter in fp64: rounding to fp32 is monotone, so
         // cur < (double)tau implies float(cur) <= tau — such rows (the vast majority once tau is
         // established, and every untouched -0.0 row when tau >= 0) are dropped with one compare.
@@ -314,29 +370,151 @@ vb_sparse_kernel(const VbSparseArgs a)
         }
         return;
     }
-    // Some non-essential terms were skipped: the accumulators hold partial scores.  A row survives only
-    // if partial + (sum of the non-essential upper bounds) can still reach tau; survivors are re-scored
-    // exactly from the forward index (all shared terms in ascending term id, as the reference does).
-    // (tau > 0 here, so untouched -0.0 rows never survive; direct mode never gets here: tau = -inf.)
-    const double bound = tau_d * (1.0 - 1e-9) - a.ubne[q];
-#pragma unroll 4
-    for (uint32_t r = 2u * tid; r < VB_ROWS_PER_BLOCK; r += 2u * VB_SPARSE_THREADS) {
-        const double2 c2 = *reinterpret_cast<const double2*>(&acc[r]);
-        if (c2.x < bound && c2.y < bound) continue;
-        if (!(c2.x < bound)) s_surv[atomicAdd(&s_nsurv, 1u)] = (uint16_t)r;
-        if (!(c2.y < bound)) s_surv[atomicAdd(&s_nsurv, 1u)] = (uint16_t)(r + 1u);
+    // Otherwise the accumulators hold PARTIAL sums (essential terms scattered from postings, in term order):
+    //  * terms with a dense column (frequent terms) are added here, row by row, straight from the column
+    //    (coalesced loads, no shared-memory traffic);
+    //  * non-essential terms were skipped: partial + sum(ub) bounds the score from above.
+    // The sum S computed this way adds the same fp64 products as the reference but in another order, so
+    // |S - S_ref| <= delta * S with delta = 4 * nt * 2^-53 (all products >= 0 on this path).  If
+    // float(S (1-delta)) == float(S (1+delta)) the fp32 score is PROVABLY the reference's and is used as is;
+    // otherwise (~1e-7 of the rows) — and for every row that survives a bound test with skipped terms — the
+    // row is re-scored exactly from the forward index (all shared terms in ascending term id).
+    const bool pruned = n_all != nnz;
+    const bool verify_only = relaxed && !pruned;                // fp32 score provable from the order-free sum
+    const double ubne = pruned ? a.ubne[q] : 0.0;
+    const double delta = (double)(4u * nt) * 1.1102230246251565e-16;
+    const double tau_lo = a.direct ? -INFINITY : (tau_d > 0.0 ? tau_d * (1.0 - 1e-9) : tau_d * (1.0 + 1e-9));
+    const bool has_acc = nnz != 0u;
+    const float fnan = __int_as_float(0x7fc00000);
+    // Fast variant (the large segments): with tau > 0 an untouched row (sum 0) can never pass, so presence
+    // needs no tracking — per row and dense column one max(v, 0) (NaN = absent -> 0), one convert, one fma —
+    // and a single compare against thr = tau (1 - 1e-9) - sum(ub of skipped terms) drops almost every row.
+    const double thr = tau_lo - ubne;
+    if (!a.direct && tau_d > 0.0 && thr > 0.0) {
+        for (uint32_t g0 = 0; g0 < 4u; g0 += 2u) {
+            double sv[2][4];
+#pragma unroll
+            for (uint32_t g = 0; g < 2u; ++g) {
+                const uint32_t r = 4u * tid + (g0 + g) * 4u * VB_SPARSE_THREADS;
+                double2 c01 = make_double2(0.0, 0.0), c23 = c01;
+                if (has_acc) { c01 = *reinterpret_cast<const double2*>(&acc[r]); c23 = *reinterpret_cast<const double2*>(&acc[r + 2u]); }
+                sv[g][0] = c01.x; sv[g][1] = c01.y; sv[g][2] = c23.x; sv[g][3] = c23.y;
+            }
+            for (uint32_t k0 = 0; k0 < nh; k0 += 2u) {
+                const bool two = k0 + 1u < nh;
+                const uint32_t j0 = s_hv[k0], j1 = two ? s_hv[k0 + 1u] : j0;
+                const float* col0 = a.heavy_vals + (size_t)__ldg(a.q_hidx + t_lo + j0) * a.heavy_stride + row0;
+                const float* col1 = a.heavy_vals + (size_t)__ldg(a.q_hidx + t_lo + j1) * a.heavy_stride + row0;
+                const double w0 = s_w[j0], w1 = two ? s_w[j1] : 0.0;
+                float4 h[2][2];
+#pragma unroll
+                for (uint32_t g = 0; g < 2u; ++g) {
+                    const uint32_t r = 4u * tid + (g0 + g) * 4u * VB_SPARSE_THREADS;
+                    const bool in = row0 + r < a.n_rows;
+                    h[g][0] = in ? __ldg(reinterpret_cast<const float4*>(col0 + r)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    h[g][1] = (in && two) ? __ldg(reinterpret_cast<const float4*>(col1 + r)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (uint32_t g = 0; g < 2u; ++g) {
+                    sv[g][0] = fma(w0, (double)fmaxf(h[g][0].x, 0.0f), sv[g][0]);
+                    sv[g][1] = fma(w0, (double)fmaxf(h[g][0].y, 0.0f), sv[g][1]);
+                    sv[g][2] = fma(w0, (double)fmaxf(h[g][0].z, 0.0f), sv[g][2]);
+                    sv[g][3] = fma(w0, (double)fmaxf(h[g][0].w, 0.0f), sv[g][3]);
+                    sv[g][0] = fma(w1, (double)fmaxf(h[g][1].x, 0.0f), sv[g][0]);
+                    sv[g][1] = fma(w1, (double)fmaxf(h[g][1].y, 0.0f), sv[g][1]);
+                    sv[g][2] = fma(w1, (double)fmaxf(h[g][1].z, 0.0f), sv[g][2]);
+                    sv[g][3] = fma(w1, (double)fmaxf(h[g][1].w, 0.0f), sv[g][3]);
+                }
+            }
+#pragma unroll
+            for (uint32_t g = 0; g < 2u; ++g) {
+                const uint32_t r = 4u * tid + (g0 + g) * 4u * VB_SPARSE_THREADS;
+                if (sv[g][0] < thr && sv[g][1] < thr && sv[g][2] < thr && sv[g][3] < thr) continue;
+#pragma unroll
+                for (uint32_t e = 0; e < 4u; ++e) {
+                    const uint32_t row = row0 + r + e;
+                    const double S = sv[g][e];
+                    if (S < thr || row >= a.n_rows) continue;
+                    if (mask && !((mask[row >> 5] >> (row & 31u)) & 1u)) continue;
+                    const float f_lo = __double2float_rn(S * (1.0 - delta)), f_hi = __double2float_rn(S * (1.0 + delta));
+                    if (!verify_only || f_lo != f_hi) { s_surv[atomicAdd(&s_nsurv, 1u)] = (uint16_t)(r + e); continue; }
+                    if (f_lo > tau) vb_push_sub(a.lists, list, sub, f_lo, a.row_base + row);
+                }
+            }
+        }
+    } else
+    // General variant (first segments, thresholds <= 0): tracks which rows have a shared term at all.
+    // each thread owns 4 groups of 4 consecutive rows; the column loads of two groups x two terms (four
+    // 128-bit loads) are issued together before any of them is used
+    for (uint32_t g0 = 0; g0 < 4u; g0 += 2u) {
+        double sv[2][4];
+        uint32_t tch[2] = {0u, 0u};                             // bit e: row e of the group has a shared term
+#pragma unroll
+        for (uint32_t g = 0; g < 2u; ++g) {
+            const uint32_t r = 4u * tid + (g0 + g) * 4u * VB_SPARSE_THREADS;
+            double2 c01 = make_double2(neg_zero, neg_zero), c23 = c01;
+            if (has_acc) { c01 = *reinterpret_cast<const double2*>(&acc[r]); c23 = *reinterpret_cast<const double2*>(&acc[r + 2u]); }
+            sv[g][0] = c01.x; sv[g][1] = c01.y; sv[g][2] = c23.x; sv[g][3] = c23.y;
+#pragma unroll
+            for (uint32_t e = 0; e < 4u; ++e)
+                tch[g] |= ((unsigned long long)__double_as_longlong(sv[g][e]) != VB_ACC_SENTINEL ? 1u : 0u) << e;
+        }
+        for (uint32_t k0 = 0; k0 < nh; k0 += 2u) {
+            const bool two = k0 + 1u < nh;
+            const uint32_t j0 = s_hv[k0], j1 = two ? s_hv[k0 + 1u] : j0;
+            const float* col0 = a.heavy_vals + (size_t)__ldg(a.q_hidx + t_lo + j0) * a.heavy_stride + row0;
+            const float* col1 = a.heavy_vals + (size_t)__ldg(a.q_hidx + t_lo + j1) * a.heavy_stride + row0;
+            const double w0 = s_w[j0], w1 = s_w[j1];
+            float4 h[2][2];
+#pragma unroll
+            for (uint32_t g = 0; g < 2u; ++g) {
+                const uint32_t r = 4u * tid + (g0 + g) * 4u * VB_SPARSE_THREADS;
+                const bool in = row0 + r < a.n_rows;            // (columns are padded to a multiple of 64 rows with NaN)
+                h[g][0] = in ? __ldg(reinterpret_cast<const float4*>(col0 + r)) : make_float4(fnan, fnan, fnan, fnan);
+                h[g][1] = (in && two) ? __ldg(reinterpret_cast<const float4*>(col1 + r)) : make_float4(fnan, fnan, fnan, fnan);
+            }
+#pragma unroll
+            for (uint32_t g = 0; g < 2u; ++g) {
+#pragma unroll
+                for (uint32_t t = 0; t < 2u; ++t) {
+                    const float hv[4] = {h[g][t].x, h[g][t].y, h[g][t].z, h[g][t].w};
+                    const double w = t ? w1 : w0;
+#pragma unroll
+                    for (uint32_t e = 0; e < 4u; ++e) {
+                        if (hv[e] == hv[e]) {
+                            const double pr = __dmul_rn(w, (double)hv[e]);
+                            sv[g][e] = ((tch[g] >> e) & 1u) ? __dadd_rn(sv[g][e], pr) : __dadd_rn(pr, 0.0);
+                            tch[g] |= 1u << e;
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (uint32_t g = 0; g < 2u; ++g) {
+            const uint32_t r = 4u * tid + (g0 + g) * 4u * VB_SPARSE_THREADS;
+#pragma unroll
+            for (uint32_t e = 0; e < 4u; ++e) {
+                const uint32_t row = row0 + r + e;
+                if (!((tch[g] >> e) & 1u) || row >= a.n_rows) continue;
+                const double S = sv[g][e];
+                if ((S + ubne) * (1.0 + delta) < tau_lo) continue;                   // cannot beat tau
+                if (mask && !((mask[row >> 5] >> (row & 31u)) & 1u)) continue;
+                const float f_lo = __double2float_rn(S * (1.0 - delta)), f_hi = __double2float_rn(S * (1.0 + delta));
+                if (!verify_only || f_lo != f_hi) { s_surv[atomicAdd(&s_nsurv, 1u)] = (uint16_t)(r + e); continue; }
+                if (a.direct) a.lists.cand[(size_t)list * a.lists.cap + (row - seg_row0)] = vb_pack_key(f_lo, a.row_base + row);
+                else if (f_lo > tau) vb_push_sub(a.lists, list, sub, f_lo, a.row_base + row);
+            }
+        }
     }
     __syncthreads();
     const uint32_t nsurv = s_nsurv;
     const uint32_t lane = tid & 31u;
     for (uint32_t i = tid >> 5; i < nsurv; i += VB_SPARSE_THREADS / 32u) {      // one warp per survivor
-        const uint32_t row = row0 + s_surv[i];
-        if (row >= a.n_rows) continue;
-        if (mask && !((mask[row >> 5] >> (row & 31u)) & 1u)) continue;
+        const uint32_t row = row0 + s_surv[i];                                   // (in range, passes the mask)
         const int64_t ip0 = __ldg(a.sp_indptr + row), ip1 = __ldg(a.sp_indptr + row + 1);
         double sc = 0.0;
-        for (uint32_t ti = 0; ti < n_all; ++ti) {
-            const uint32_t j = s_all[ti];
+        for (uint32_t j = 0; j < nt; ++j) {                                      // every query term, ascending id
             const uint32_t term = __ldg(a.q_term + t_lo + j);
             for (int64_t c0 = ip0; c0 < ip1; c0 += 32) {
                 const int64_t p = c0 + lane;
@@ -352,7 +530,8 @@ vb_sparse_kernel(const VbSparseArgs a)
         }
         if (lane == 0) {
             const float sf = __double2float_rn(sc);
-            if (sf > tau) vb_push_sub(a.lists, list, sub, sf, a.row_base + row);
+            if (a.direct) a.lists.cand[(size_t)list * a.lists.cap + (row - seg_row0)] = vb_pack_key(sf, a.row_base + row);
+            else if (sf > tau) vb_push_sub(a.lists, list, sub, sf, a.row_base + row);
         }
     }
 }

@@ -71,7 +71,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Batch {
     uint32_t B = 0, k = 0, limit = 0, n_lists = 0, n_qterms = 0, nt_max = 1, n_filters = 0, mask_words = 0, n_blocks = 0;
-    bool any_sparse = false, use_mask = false;
+    bool any_sparse = false, use_mask = false, any_heavy = false;
     uint32_t seg_ratio = 32;                   // growth factor of the segment schedule for this batch
     std::vector<int32_t> mode, mask_of_host;
     // device pointers into h->args
@@ -80,6 +80,8 @@ struct Batch {
     const double* d_qweight = nullptr;
     const double* d_qub = nullptr;
     const uint32_t* d_qterm = nullptr;
+    const int32_t* d_qhidx = nullptr;
+    const uint8_t* d_qrelaxed = nullptr;
     const uint32_t* d_qlo = nullptr;
     const uint32_t* d_qhi = nullptr;
     const int32_t* d_maskof = nullptr;
@@ -123,6 +125,10 @@ struct vb_index {
     std::vector<uint32_t> terms_sorted;
     std::vector<uint64_t> term_ptr;
     std::vector<float> term_maxval;        // largest posting value per term (MaxScore upper bounds)
+    std::vector<int32_t> heavy_of_slot;    // term slot -> dense column, -1 = none
+    DevBuf heavy_vals;                     // [n_heavy][heavy_stride] fp32, NaN = term absent from the row
+    uint32_t n_heavy = 0, heavy_stride = 0;
+    bool sparse_nonneg = false;            // no negative posting value in the shard
 
     // per-search scratch
     DevBuf args, mask, cand, lists, offs, plan, out, q_hat, q_bf16, q_scale, tmp;
@@ -130,7 +136,7 @@ struct vb_index {
     uint32_t cand_cap = 0;
 
     // options
-    int64_t opt_dense_path = 0, opt_seg_first = 2048, opt_seg_ratio = 0 /* 0 = auto */, opt_safe_mode = 0, opt_profile = 0, opt_k2_precision = 0, opt_overlap = 1, opt_k2_tiled = 1, opt_sparse_prune = 20, opt_sparse_prune_force = 0;
+    int64_t opt_dense_path = 0, opt_seg_first = 2048, opt_seg_ratio = 0 /* 0 = auto */, opt_safe_mode = 0, opt_profile = 0, opt_k2_precision = 0, opt_overlap = 1, opt_k2_tiled = 1, opt_sparse_prune = 20, opt_sparse_prune_force = 0, opt_sparse_dense = 1;
 
     vb_stats stats{};
     Batch staged_s[2];
@@ -257,6 +263,7 @@ extern "C" int vb_create(int32_t dim, int32_t device, uint64_t capacity_hint, ui
     if (const char* env = getenv("VB200_OVERLAP")) h->opt_overlap = atoi(env);
     if (const char* env = getenv("VB200_SPARSE_PRUNE")) h->opt_sparse_prune = atoi(env);
     if (const char* env = getenv("VB200_SPARSE_PRUNE_FORCE")) h->opt_sparse_prune_force = atoi(env);
+    if (const char* env = getenv("VB200_SPARSE_DENSE")) h->opt_sparse_dense = atoi(env);
     *out = h;
     return 0;
 }
@@ -266,7 +273,7 @@ extern "C" void vb_destroy(vb_index* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->rows, &h->inv_norm, &h->scope_id, &h->created, &h->modified, &h->alive, &h->sp_indptr,
-                      &h->sp_term, &h->sp_val, &h->post_row, &h->post_val, &h->args, &h->mask, &h->cand, &h->lists,
+                      &h->sp_term, &h->sp_val, &h->post_row, &h->post_val, &h->heavy_vals, &h->args, &h->mask, &h->cand, &h->lists,
                       &h->offs, &h->plan, &h->out, &h->q_hat, &h->q_bf16, &h->q_scale, &h->tmp})
         dev_free(h, *b);
     for (HostBuf* b : {&h->h_args_s[0], &h->h_args_s[1], &h->h_out_s[0], &h->h_out_s[1], &h->h_stage}) if (b->p) cudaFreeHost(b->p);
@@ -290,6 +297,7 @@ extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
     else if (k == "profile") h->opt_profile = value;
     else if (k == "slot") h->cur = value ? 1 : 0;                   // which of the two in-flight batches the staged calls address
     else if (k == "overlap") h->opt_overlap = value;               // 1: dense and sparse chains on two streams
+    else if (k == "sparse_dense") { h->opt_sparse_dense = value; h->sparse_dirty = true; }   // 0: no dense columns for frequent terms
     else if (k == "sparse_prune_force") h->opt_sparse_prune_force = value;   // 1: prune in every non-direct segment (tests)
     else if (k == "sparse_prune") h->opt_sparse_prune = value;     // MaxScore budget in % of tau (0: score every term's postings)
     else if (k == "k2_tiled") h->opt_k2_tiled = value;             // 0: never use the query-tiled kernel (multi-pass resident kernel instead)
@@ -508,6 +516,9 @@ static int ensure_sparse_index(vb_index* h) {
     h->terms_sorted.clear();
     h->term_ptr.assign(1, 0);
     h->term_maxval.clear();
+    h->heavy_of_slot.clear();
+    h->n_heavy = 0;
+    h->sparse_nonneg = false;
     h->nnz_live = 0;
     if (h->nnz == 0) { h->sparse_dirty = false; return 0; }
     const uint64_t nnz = h->nnz;
@@ -578,6 +589,45 @@ static int ensure_sparse_index(vb_index* h) {
     CKC2(cudaMemcpyAsync(h->term_ptr.data(), ptrs.p, (size_t)T * 8, cudaMemcpyDeviceToHost, h->stream));
     CKC2(cudaStreamSynchronize(h->stream));
     h->term_ptr[T] = live;
+    // smallest posting value: the dense-column path below and its error bound need products >= 0
+    {
+        tb = 0;
+        CKC2(cub::DeviceReduce::Min(nullptr, tb, h->post_val.as<float>(), runs.as<float>(), (int)live, h->stream));
+        rc = dev_reserve(h, cub_tmp, tb, false); if (rc) { cleanup2(); return rc; }
+        CKC2(cub::DeviceReduce::Min(cub_tmp.p, tb, h->post_val.as<float>(), runs.as<float>(), (int)live, h->stream));
+        float mn = -1.0f;
+        CKC2(cudaMemcpyAsync(&mn, runs.p, 4, cudaMemcpyDeviceToHost, h->stream));
+        CKC2(cudaStreamSynchronize(h->stream));
+        h->sparse_nonneg = mn >= 0.0f;
+    }
+    // Dense columns for the most frequent terms (df >= 1/8 of the live rows, at most 64 of them): such a
+    // term's postings touch most rows of every block, so the scoring kernel reads its value per row from a
+    // column (coalesced, no shared-memory scatter) instead of walking its posting list once per query.
+    h->heavy_of_slot.assign(T, -1);
+    if (h->opt_sparse_dense && h->sparse_nonneg && h->n_live >= 4096) {
+        std::vector<std::pair<uint64_t, uint32_t>> cand;
+        for (uint32_t sl = 0; sl < T; ++sl) {
+            const uint64_t df = h->term_ptr[sl + 1] - h->term_ptr[sl];
+            if (df * 8 >= h->n_live) cand.emplace_back(df, sl);
+        }
+        std::sort(cand.begin(), cand.end(), [](const auto& x, const auto& y) { return x.first > y.first; });
+        if (cand.size() > 64) cand.resize(64);
+        h->n_heavy = (uint32_t)cand.size();
+        h->heavy_stride = (uint32_t)align_up((size_t)h->n_rows + 2, 64);
+        if (h->n_heavy) {
+            rc = dev_reserve(h, h->heavy_vals, (size_t)h->n_heavy * h->heavy_stride * 4, false); if (rc) { cleanup2(); return rc; }
+            CKC2(cudaMemsetAsync(h->heavy_vals.p, 0xff, (size_t)h->n_heavy * h->heavy_stride * 4, h->stream));   // all NaN
+            for (uint32_t k = 0; k < h->n_heavy; ++k) {
+                const uint32_t sl = cand[k].second;
+                h->heavy_of_slot[sl] = (int32_t)k;
+                vb_heavy_fill_kernel<<<grid_for(cand[k].first, 256), 256, 0, h->stream>>>(
+                    h->post_row.as<uint32_t>(), h->post_val.as<float>(), h->term_ptr[sl], h->term_ptr[sl + 1],
+                    h->heavy_vals.as<float>() + (size_t)k * h->heavy_stride);
+                CKC2(cudaGetLastError());
+            }
+            CKC2(cudaStreamSynchronize(h->stream));
+        }
+    }
     cleanup2();
     h->sparse_dirty = false;
     return 0;
@@ -686,6 +736,8 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     std::vector<int64_t> indptr(b.B + 1, 0);
     std::vector<double> weight, qub;
     std::vector<uint32_t> qlo, qhi, qterm;
+    std::vector<int32_t> qhidx;
+    std::vector<uint8_t> qrelaxed(b.B, 0);
     if (sparse_enabled) {
         if (need_corpus) TRY(ensure_sparse_index(h));
         std::vector<std::pair<uint32_t, double>> tw;
@@ -698,6 +750,8 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
             std::sort(tw.begin(), tw.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
             for (size_t t = 1; t < tw.size(); ++t)
                 if (tw[t].first == tw[t - 1].first) return vb_fail("query %u repeats sparse index %u", i, tw[t].first);
+            const size_t q_first = weight.size();
+            bool all_pos = true;                                // dense columns need every product >= 0 (error bound)
             for (auto& pr : tw) {
                 uint64_t plo = 0, phi = 0;
                 int64_t slot = -1;
@@ -711,6 +765,8 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
                     // local_collection.py _compute_idf: log((N - df + 0.5) / (df + 0.5) + 1)
                     w = w * std::log(((double)h->n_live - df + 0.5) / (df + 0.5) + 1.0);
                 }
+                all_pos = all_pos && w > 0.0 && w < INFINITY;
+                qhidx.push_back((need_corpus && slot >= 0 && h->n_heavy) ? h->heavy_of_slot[slot] : -1);
                 // MaxScore upper bound of this term's contribution to any row of the shard; +inf = "always
                 // essential" (non-positive or non-finite weights are never pruned)
                 double ub = INFINITY;
@@ -720,6 +776,14 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
                 qterm.push_back(pr.first);
                 qlo.push_back((uint32_t)plo);
                 qhi.push_back((uint32_t)phi);
+            }
+            // terms routed to their dense column are not walked as postings (empty slice)
+            // relaxed mode (order-free sums, dense columns) needs every product >= 0 for its error bound
+            const bool relax = all_pos && need_corpus && h->sparse_nonneg && h->opt_sparse_dense;
+            qrelaxed[i] = relax ? 1 : 0;
+            for (size_t t = q_first; t < weight.size(); ++t) {
+                if (!relax) qhidx[t] = -1;
+                if (qhidx[t] >= 0) { qlo[t] = qhi[t] = 0; b.any_heavy = true; }
             }
             indptr[i + 1] = (int64_t)weight.size();
             b.nt_max = std::max<uint32_t>(b.nt_max, (uint32_t)(indptr[i + 1] - indptr[i]));
@@ -764,6 +828,8 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     const size_t o_w = ar.take((size_t)b.n_qterms * 8 + 8);
     const size_t o_ub = ar.take((size_t)b.n_qterms * 8 + 8);
     const size_t o_tid = ar.take((size_t)b.n_qterms * 4 + 8);
+    const size_t o_hx = ar.take((size_t)b.n_qterms * 4 + 8);
+    const size_t o_rx = ar.take((size_t)b.B + 8);
     const size_t o_lo = ar.take((size_t)b.n_qterms * 4 + 8);
     const size_t o_hi = ar.take((size_t)b.n_qterms * 4 + 8);
     const size_t o_mo = ar.take((size_t)b.B * 4);
@@ -782,6 +848,8 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
         memcpy(hp + o_w, weight.data(), (size_t)b.n_qterms * 8);
         memcpy(hp + o_ub, qub.data(), (size_t)b.n_qterms * 8);
         memcpy(hp + o_tid, qterm.data(), (size_t)b.n_qterms * 4);
+        memcpy(hp + o_hx, qhidx.data(), (size_t)b.n_qterms * 4);
+        memcpy(hp + o_rx, qrelaxed.data(), (size_t)b.B);
         memcpy(hp + o_lo, qlo.data(), (size_t)b.n_qterms * 4);
         memcpy(hp + o_hi, qhi.data(), (size_t)b.n_qterms * 4);
     }
@@ -804,6 +872,8 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     b.d_qweight = reinterpret_cast<const double*>(dp + o_w);
     b.d_qub = reinterpret_cast<const double*>(dp + o_ub);
     b.d_qterm = reinterpret_cast<const uint32_t*>(dp + o_tid);
+    b.d_qhidx = reinterpret_cast<const int32_t*>(dp + o_hx);
+    b.d_qrelaxed = reinterpret_cast<const uint8_t*>(dp + o_rx);
     b.d_qlo = reinterpret_cast<const uint32_t*>(dp + o_lo);
     b.d_qhi = reinterpret_cast<const uint32_t*>(dp + o_hi);
     b.d_maskof = reinterpret_cast<const int32_t*>(dp + o_mo);
@@ -994,6 +1064,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
             a.post_row = h->post_row.as<uint32_t>(); a.post_val = h->post_val.as<float>(); a.off = h->offs.as<uint32_t>();
             a.q_indptr = b.d_qindptr; a.q_weight = b.d_qweight; a.q_term = b.d_qterm; a.ess = d_ess; a.ubne = d_ubne;
             a.sp_indptr = h->sp_indptr.as<int64_t>(); a.sp_term = h->sp_term.as<uint32_t>(); a.sp_val = h->sp_val.as<float>();
+            a.q_hidx = b.any_heavy ? b.d_qhidx : nullptr; a.q_relaxed = b.d_qrelaxed; a.heavy_vals = h->heavy_vals.as<float>(); a.heavy_stride = h->heavy_stride;
             a.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; a.mask_of = b.use_mask ? b.d_maskof : nullptr;
             a.tau = b.tau; a.lists = L; a.mask_words = b.mask_words;
             a.n_qterms = b.n_qterms; a.nt_max = b.nt_max; a.blk_begin = r0 / VB_ROWS_PER_BLOCK; a.n_queries = b.B; a.n_rows = n;
