@@ -199,7 +199,7 @@ vb_sparse_kernel(const VbSparseArgs a)
     uint16_t* s_hv = s_all + a.nt_max;                                      // [nt_max] terms scored from their dense column
     uint32_t* s_cum = reinterpret_cast<uint32_t*>(s_hv + a.nt_max + (a.nt_max & 1u));   // [nt_max + 1] posting prefix sums over s_nz
     uint8_t* s_flag = reinterpret_cast<uint8_t*>(s_cum + a.nt_max + 1u);                // [nt_max] bit0 postings here, bit1 essential, bit2 dense column
-    __shared__ uint32_t s_nnz, s_nall, s_nsurv, s_nheavy;
+    __shared__ uint32_t s_nsurv;
 
     const uint32_t tid = threadIdx.x;
     const uint32_t q = blockIdx.x % a.n_queries;
@@ -209,16 +209,24 @@ vb_sparse_kernel(const VbSparseArgs a)
     const uint32_t nt = (uint32_t)__ldg(a.q_indptr + q + 1) - t_lo;
     if (nt == 0) return;                                        // dense-only query
 
-    for (uint32_t j = tid; j < nt; j += VB_SPARSE_THREADS) {
-        const uint32_t lo = __ldg(a.off + (size_t)blk * a.n_qterms + t_lo + j);
-        const uint32_t hi = __ldg(a.off + (size_t)(blk + 1u) * a.n_qterms + t_lo + j);
-        const bool es = a.ess == nullptr || __ldg(a.ess + t_lo + j) != 0;
-        const bool hv = a.q_hidx != nullptr && __ldg(a.q_hidx + t_lo + j) >= 0;
-        s_w[j] = __ldg(a.q_weight + t_lo + j);
-        s_lo[j] = lo;
-        s_hi[j] = hi;
-        s_flag[j] = (uint8_t)((hi > lo ? 1u : 0u) | (es ? 2u : 0u) | (hv ? 4u : 0u));
-    }
+    // Term table: every warp builds it by itself (lane = term, 32 terms per step) and all warps store the
+    // same values, so the four warps never wait for one of them and a single barrier (after the accumulator
+    // initialisation below) publishes everything.
+    const uint32_t lane = tid & 31u;
+    auto load_term = [&](uint32_t j, uint32_t& lo, uint32_t& hi, uint32_t& fl, double& w) {
+        lo = hi = fl = 0u; w = 0.0;
+        if (j < nt) {
+            lo = __ldg(a.off + (size_t)blk * a.n_qterms + t_lo + j);
+            hi = __ldg(a.off + (size_t)(blk + 1u) * a.n_qterms + t_lo + j);
+            w = __ldg(a.q_weight + t_lo + j);
+            const bool es = a.ess == nullptr || __ldg(a.ess + t_lo + j) != 0;
+            const bool hv = a.q_hidx != nullptr && __ldg(a.q_hidx + t_lo + j) >= 0;
+            fl = (es ? 2u : 0u) | (hv ? 4u : 0u);
+        }
+    };
+    uint32_t lo_c, hi_c, fl_c;
+    double w_c;
+    load_term(lane, lo_c, hi_c, fl_c, w_c);                     // first 32 terms: in flight during the initialisation
     const uint32_t list = a.n_queries + q;                      // sparse lists follow the dense ones
     const float tau = a.tau[list];
     const uint32_t* mask = nullptr;
@@ -230,44 +238,38 @@ vb_sparse_kernel(const VbSparseArgs a)
 #pragma unroll
     for (uint32_t r = 2u * tid; r < VB_ROWS_PER_BLOCK + VB_SPARSE_PAD; r += 2u * VB_SPARSE_THREADS)
         *reinterpret_cast<double2*>(&acc[r]) = make_double2(neg_zero, neg_zero);
-    __syncthreads();
-    if (tid < 32u) {                                            // ordered compaction of the non-empty terms
-        uint32_t base = 0, base_all = 0, base_hv = 0, cum_base = 0, n_skip = 0;
-        if (tid == 0) s_cum[0] = 0u;
+    uint32_t nnz = 0, n_all = 0, nh = 0;                        // essential terms with postings here / terms that can touch
+    {                                                           // this block / essential terms read from a dense column
+        uint32_t cum_base = 0;
+        if (lane == 0) { s_cum[0] = 0u; if (tid == 0) s_nsurv = 0u; }
         for (uint32_t j0 = 0; j0 < nt; j0 += 32u) {
-            const uint32_t j = j0 + tid;
-            const uint32_t fl = j < nt ? s_flag[j] : 0u;
-            const bool ne = (fl & 1u) != 0u;                                         // postings in this block
-            const bool es = (fl & 3u) == 3u;                                         // ... of an essential term
-            const bool hv = (fl & 6u) == 6u;                                         // essential term with a dense column
-            n_skip += __popc(__ballot_sync(0xffffffffu, (fl & 6u) == 4u));           // dense-column terms skipped as non-essential
-            const uint32_t bal_all = __ballot_sync(0xffffffffu, ne);
+            const uint32_t j = j0 + lane;
+            if (j0 != 0u) load_term(j, lo_c, hi_c, fl_c, w_c);
+            if (j < nt) { s_lo[j] = lo_c; s_hi[j] = hi_c; s_w[j] = w_c; }
+            const bool ne = hi_c > lo_c;                                             // postings in this block
+            const bool es = ne && (fl_c & 2u);                                       // ... of an essential term
+            const bool hv = (fl_c & 6u) == 6u;                                       // essential term with a dense column
+            n_all += __popc(__ballot_sync(0xffffffffu, ne)) + __popc(__ballot_sync(0xffffffffu, (fl_c & 6u) == 4u));
             const uint32_t bal = __ballot_sync(0xffffffffu, es);
             const uint32_t bal_hv = __ballot_sync(0xffffffffu, hv);
-            if (ne) s_all[base_all + __popc(bal_all & ((1u << tid) - 1u))] = (uint16_t)j;
-            uint32_t incl = es ? s_hi[j] - s_lo[j] : 0u;                             // running posting count over s_nz
+            uint32_t incl = es ? hi_c - lo_c : 0u;                                   // running posting count over s_nz
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (tid >= (uint32_t)o) incl += t;
+                if (lane >= (uint32_t)o) incl += t;
             }
             if (es) {
-                const uint32_t k = base + __popc(bal & ((1u << tid) - 1u));
+                const uint32_t k = nnz + __popc(bal & ((1u << lane) - 1u));
                 s_nz[k] = (uint16_t)j;
                 s_cum[k + 1u] = cum_base + incl;
             }
             cum_base += __shfl_sync(0xffffffffu, incl, 31);
-            if (hv) s_hv[base_hv + __popc(bal_hv & ((1u << tid) - 1u))] = (uint16_t)j;
-            base += __popc(bal);
-            base_all += __popc(bal_all);
-            base_hv += __popc(bal_hv);
+            if (hv) s_hv[nh + __popc(bal_hv & ((1u << lane) - 1u))] = (uint16_t)j;
+            nnz += __popc(bal);
+            nh += __popc(bal_hv);
         }
-        if (tid == 0) { s_nnz = base; s_nall = base_all + n_skip; s_nheavy = base_hv; s_nsurv = 0u; }
     }
     __syncthreads();
-    const uint32_t nnz = s_nnz;                                 // essential terms with postings in this block
-    const uint32_t n_all = s_nall;                              // terms that can touch this block (postings here, or a skipped dense column)
-    const uint32_t nh = s_nheavy;                               // terms read from their dense column (every block)
     if (nnz == 0 && nh == 0) return;                            // no row of this block can beat tau (direct-mode slots were zeroed by the host)
 
     const uint32_t row0 = blk * VB_ROWS_PER_BLOCK;
@@ -509,7 +511,6 @@ vb_sparse_kernel(const VbSparseArgs a)
     }
     __syncthreads();
     const uint32_t nsurv = s_nsurv;
-    const uint32_t lane = tid & 31u;
     for (uint32_t i = tid >> 5; i < nsurv; i += VB_SPARSE_THREADS / 32u) {      // one warp per survivor
         const uint32_t row = row0 + s_surv[i];                                   // (in range, passes the mask)
         const int64_t ip0 = __ldg(a.sp_indptr + row), ip1 = __ldg(a.sp_indptr + row + 1);
