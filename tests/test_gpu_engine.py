@@ -413,6 +413,21 @@ def test_large_batch_hybrid_against_oracle():
     for i in range(B):
         assert pruned.branch(i, "sparse") == base.branch(i, "sparse"), f"pruned sparse list q{i}"
         assert pruned.hits(i) == base.hits(i)
+    # relaxed mode (dense columns for frequent terms, order-free sums + verification) against exact mode
+    # (sparse_dense = 0: every term walked in term order): identical lists, bit for bit
+    assert ix.stats()["n_terms"] > 0
+    ix.set_option("sparse_dense", 0)
+    exact = ix.search_batch(Q, SP, [engine.Filter(*flt)], fo, limit=10, fusion="rrf", branches=True)
+    ix.set_option("sparse_dense", 1)
+    for i in range(B):
+        assert exact.branch(i, "sparse") == base.branch(i, "sparse"), f"exact vs relaxed sparse list q{i}"
+    # query values of either sign and zero: such queries always take the exact mode; still bit-equal to the oracle
+    SPm = [(t, [float(v) for v in rng.choice([-1.0, 0.0, 0.5, 1.0, 2.0], size=len(t))]) for t, _ in SP]
+    gotm = ix.search_batch(Q, SPm, [engine.Filter(*flt)], fo, limit=10, fusion="rrf", branches=True)
+    wantm = cc.search_batch(Q, SPm, [flt], fo, limit=10, fusion=2)
+    for i in range(B):
+        ws = [(int(wantm["sparse_rows"][i, j]), float(wantm["sparse_scores"][i, j])) for j in range(wantm["sparse_counts"][i])]
+        assert_same_ranking(gotm.branch(i, "sparse"), ws, rel_tol=0.0, what=f"mixed-sign sparse q{i}")
     # the pipelined stream API returns the same answers as the one-call API
     packed = [ix.pack(Q[j:j + 16], SP[j:j + 16], [engine.Filter(*flt)], np.zeros(16, np.int32), limit=10, fusion="rrf")
               for j in range(0, B, 16)]
