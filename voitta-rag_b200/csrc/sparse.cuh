@@ -185,7 +185,7 @@ static size_t vb_sparse_smem_bytes(uint32_t nt_max) {
 //   acc = acc + (w*v + 0.0) reproduces Python's `result = 0.0; result += w*v` bit for bit (the only
 //   differences would involve -0.0, which both sides turn into +0.0) while an untouched row is
 //   still recognisable (-0.0 can never be a sum).
-__global__ void __launch_bounds__(VB_SPARSE_THREADS, 8)
+__global__ void __launch_bounds__(VB_SPARSE_THREADS, 10)
 vb_sparse_kernel(const VbSparseArgs a)
 {
     extern __shared__ __align__(16) unsigned char vb_sp_smem[];
