@@ -707,6 +707,13 @@ static uint32_t vb_gemm_kbox(uint32_t d_pad) {
     if (kbox < 1u) kbox = 1u;
     return kbox > k_blocks ? k_blocks : kbox;
 }
+// shared-memory budget of the resident kernel: the device maximum, or VB200_K2_SMEM_KB (leaves room for CTAs of
+// the sparse chain to be co-resident with the persistent GEMM CTA)
+static uint32_t vb_gemm_smem_budget() {
+    const int kb = vb_env_int("VB200_K2_SMEM_KB", 0);
+    const uint32_t mx = (uint32_t)g_gemm_smem_max;
+    return kb > 0 ? std::min<uint32_t>(mx, (uint32_t)kb * 1024u) : mx;
+}
 static uint32_t vb_gemm_max_bn(uint32_t d_pad) {
     const uint32_t reserve = std::max(4u, 2u * vb_gemm_kbox(d_pad)) * VB_STAGE_BYTES;   // room for the A ring
     const uint32_t avail = (uint32_t)g_gemm_smem_max - 1024u - VB_GEMM_TAIL_BYTES - reserve;
@@ -723,7 +730,8 @@ static VbGemmPlan vb_gemm_plan(uint32_t d_pad, uint32_t B, int precision /*0 aut
     const uint32_t bn_max = vb_gemm_max_bn(d_pad);
     const uint32_t half = (bn_max / 2u) / 16u * 16u;
     VbGemmPlan p;
-    p.split = precision == 2 ? 1u : (precision == 1 ? 0u : (B <= half ? 1u : 0u));
+    const uint32_t split_max = (uint32_t)vb_env_int("VB200_K2_SPLIT_MAX_B", 1 << 20);
+    p.split = precision == 2 ? 1u : (precision == 1 ? 0u : ((B <= half && B <= split_max) ? 1u : 0u));
     if (p.split && half < 16u) p.split = 0u;
     p.sub = p.split ? half : bn_max;
     return p;
@@ -812,7 +820,8 @@ static int vb_gemm_launch(const VbGemmLaunch& g, int* launches) {
         const uint32_t q_bytes = bn * g.d_pad * 2u;
         a.kbox = kbox;
         a.debug = (uint32_t)vb_env_int("VB200_K2_DEBUG", 0);
-        uint32_t stages = ((uint32_t)g_gemm_smem_max - 1024u - VB_GEMM_TAIL_BYTES - q_bytes) / (kbox * VB_STAGE_BYTES);
+        const uint32_t budget = std::max<uint32_t>(vb_gemm_smem_budget(), 1024u + VB_GEMM_TAIL_BYTES + q_bytes + 2u * kbox * VB_STAGE_BYTES);
+        uint32_t stages = (std::min<uint32_t>(budget, (uint32_t)g_gemm_smem_max) - 1024u - VB_GEMM_TAIL_BYTES - q_bytes) / (kbox * VB_STAGE_BYTES);
         const uint32_t cap_stages = (uint32_t)vb_env_int("VB200_K2_STAGES", 12);
         a.stages = stages > cap_stages ? cap_stages : stages;
         if (a.stages < 2u) { g_gemm_err = "not enough shared memory for a 2-stage pipeline"; return 1; }

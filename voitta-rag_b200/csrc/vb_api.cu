@@ -1057,12 +1057,14 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
             // on cfg2's 1M-row corpus where the per-survivor re-scoring outweighs the skipped postings).
             const uint32_t nblk_seg = (r1 - r0 + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK;
             const uint32_t budget = (!direct && (h->opt_sparse_prune_force || nblk_seg >= 1000u)) ? (uint32_t)h->opt_sparse_prune : 0u;
-            vb_sparse_plan_kernel<<<b.B, 256, 0, ss>>>(b.d_qindptr, b.d_qub, b.tau, b.B, budget, d_ess, d_ubne);
-            CKK("vb_sparse_plan_kernel");
-            ++h->stats.last_launches;
+            if (budget) {                                       // no budget: every term is essential, no plan needed
+                vb_sparse_plan_kernel<<<b.B, 256, 0, ss>>>(b.d_qindptr, b.d_qub, b.tau, b.B, budget, d_ess, d_ubne);
+                CKK("vb_sparse_plan_kernel");
+                ++h->stats.last_launches;
+            }
             VbSparseArgs a{};
             a.post_row = h->post_row.as<uint32_t>(); a.post_val = h->post_val.as<float>(); a.off = h->offs.as<uint32_t>();
-            a.q_indptr = b.d_qindptr; a.q_weight = b.d_qweight; a.q_term = b.d_qterm; a.ess = d_ess; a.ubne = d_ubne;
+            a.q_indptr = b.d_qindptr; a.q_weight = b.d_qweight; a.q_term = b.d_qterm; a.ess = budget ? d_ess : nullptr; a.ubne = d_ubne;
             a.sp_indptr = h->sp_indptr.as<int64_t>(); a.sp_term = h->sp_term.as<uint32_t>(); a.sp_val = h->sp_val.as<float>();
             a.q_hidx = b.any_heavy ? b.d_qhidx : nullptr; a.q_relaxed = b.d_qrelaxed; a.heavy_vals = h->heavy_vals.as<float>(); a.heavy_stride = h->heavy_stride;
             a.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; a.mask_of = b.use_mask ? b.d_maskof : nullptr;
