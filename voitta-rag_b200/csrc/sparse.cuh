@@ -112,6 +112,7 @@ struct VbSparseArgs {
     uint32_t n_rows;
     uint32_t row_base;
     uint32_t direct;            // 1: first segment — store keys at slot (row - segment begin), no atomics
+    uint32_t debug;             // perf triage only (VB200_SPARSE_DEBUG): 1 stop after the term table, 2 skip the posting scatter, 4 skip the scan, 8 skip the accumulator init
 };
 
 // ---- MaxScore plan: which query terms are essential under the current thresholds --------------------
@@ -185,7 +186,7 @@ static size_t vb_sparse_smem_bytes(uint32_t nt_max) {
 //   acc = acc + (w*v + 0.0) reproduces Python's `result = 0.0; result += w*v` bit for bit (the only
 //   differences would involve -0.0, which both sides turn into +0.0) while an untouched row is
 //   still recognisable (-0.0 can never be a sum).
-__global__ void __launch_bounds__(VB_SPARSE_THREADS, 10)
+__global__ void __launch_bounds__(VB_SPARSE_THREADS, 9)
 vb_sparse_kernel(const VbSparseArgs a)
 {
     extern __shared__ __align__(16) unsigned char vb_sp_smem[];
@@ -235,9 +236,11 @@ vb_sparse_kernel(const VbSparseArgs a)
         if (f >= 0) mask = a.mask + (size_t)f * a.mask_words;
     }
     const double neg_zero = __longlong_as_double((long long)VB_ACC_SENTINEL);
+    if (!(a.debug & 8u)) {
 #pragma unroll
-    for (uint32_t r = 2u * tid; r < VB_ROWS_PER_BLOCK + VB_SPARSE_PAD; r += 2u * VB_SPARSE_THREADS)
-        *reinterpret_cast<double2*>(&acc[r]) = make_double2(neg_zero, neg_zero);
+        for (uint32_t r = 2u * tid; r < VB_ROWS_PER_BLOCK + VB_SPARSE_PAD; r += 2u * VB_SPARSE_THREADS)
+            *reinterpret_cast<double2*>(&acc[r]) = make_double2(neg_zero, neg_zero);
+    }
     uint32_t nnz = 0, n_all = 0, nh = 0;                        // essential terms with postings here / terms that can touch
     {                                                           // this block / essential terms read from a dense column
         uint32_t cum_base = 0;
@@ -270,7 +273,8 @@ vb_sparse_kernel(const VbSparseArgs a)
         }
     }
     __syncthreads();
-    if (nnz == 0 && nh == 0) return;                            // no row of this block can beat tau (direct-mode slots were zeroed by the host)
+    if ((nnz == 0 && nh == 0) || (a.debug & 1u)) return;
+    if (a.debug & 2u) nnz = 0;                            // no row of this block can beat tau (direct-mode slots were zeroed by the host)
 
     const uint32_t row0 = blk * VB_ROWS_PER_BLOCK;
     const uint32_t dummy = VB_ROWS_PER_BLOCK + (tid & 31u);     // this lane's private padding slot
@@ -342,6 +346,7 @@ vb_sparse_kernel(const VbSparseArgs a)
         }
     }
 
+    if (a.debug & 4u) return;
     const uint32_t seg_row0 = a.blk_begin * VB_ROWS_PER_BLOCK;
     const uint32_t sub = blk_rel & a.lists.sub_mask;            // append counter of this row block
     const double tau_d = (double)tau;
@@ -393,55 +398,72 @@ vb_sparse_kernel(const VbSparseArgs a)
     // and a single compare against thr = tau (1 - 1e-9) - sum(ub of skipped terms) drops almost every row.
     const double thr = tau_lo - ubne;
     if (!a.direct && tau_d > 0.0 && thr > 0.0) {
-        for (uint32_t g0 = 0; g0 < 4u; g0 += 2u) {
-            double sv[2][4];
+        // Pass 1, fp32: the same sums in single precision with every input rounded UP (accumulators, weights;
+        // column values are exact floats), against a threshold lowered by more than the fp32 summation error
+        // (~nt * 6e-8 relative, all terms >= 0) — so a row with S >= thr always has s32 >= thr32.  Each thread
+        // owns 16 rows (4 groups of 4 consecutive rows); per dense column: four 128-bit loads, then one max and
+        // one fma per row on the full-rate fp32 pipe.  Pass 2 redoes only the groups that may hold a candidate
+        // in fp64 and runs the candidate logic.
+        const float thr32 = __double2float_rd(thr * (1.0 - 1e-6 - (double)nt * 2e-7));
+        float s32[4][4];
+        bool in[4];
 #pragma unroll
-            for (uint32_t g = 0; g < 2u; ++g) {
-                const uint32_t r = 4u * tid + (g0 + g) * 4u * VB_SPARSE_THREADS;
-                double2 c01 = make_double2(0.0, 0.0), c23 = c01;
-                if (has_acc) { c01 = *reinterpret_cast<const double2*>(&acc[r]); c23 = *reinterpret_cast<const double2*>(&acc[r + 2u]); }
-                sv[g][0] = c01.x; sv[g][1] = c01.y; sv[g][2] = c23.x; sv[g][3] = c23.y;
+        for (uint32_t g = 0; g < 4u; ++g) {
+            const uint32_t r = 4u * tid + g * 4u * VB_SPARSE_THREADS;
+            in[g] = row0 + r < a.n_rows && !(a.debug & 32u);
+            s32[g][0] = s32[g][1] = s32[g][2] = s32[g][3] = 0.0f;
+            if (has_acc) {
+                const double2 c01 = *reinterpret_cast<const double2*>(&acc[r]), c23 = *reinterpret_cast<const double2*>(&acc[r + 2u]);
+                s32[g][0] = __double2float_ru(c01.x); s32[g][1] = __double2float_ru(c01.y);
+                s32[g][2] = __double2float_ru(c23.x); s32[g][3] = __double2float_ru(c23.y);
             }
-            for (uint32_t k0 = 0; k0 < nh; k0 += 2u) {
-                const bool two = k0 + 1u < nh;
-                const uint32_t j0 = s_hv[k0], j1 = two ? s_hv[k0 + 1u] : j0;
-                const float* col0 = a.heavy_vals + (size_t)__ldg(a.q_hidx + t_lo + j0) * a.heavy_stride + row0;
-                const float* col1 = a.heavy_vals + (size_t)__ldg(a.q_hidx + t_lo + j1) * a.heavy_stride + row0;
-                const double w0 = s_w[j0], w1 = two ? s_w[j1] : 0.0;
-                float4 h[2][2];
+        }
+        for (uint32_t k = 0; k < nh; ++k) {
+            const uint32_t j = s_hv[k];
+            const float* col = a.heavy_vals + (size_t)__ldg(a.q_hidx + t_lo + j) * a.heavy_stride + row0 + 4u * tid;
+            const float w = __double2float_ru(s_w[j]);
+            float4 h[4];
 #pragma unroll
-                for (uint32_t g = 0; g < 2u; ++g) {
-                    const uint32_t r = 4u * tid + (g0 + g) * 4u * VB_SPARSE_THREADS;
-                    const bool in = row0 + r < a.n_rows;
-                    h[g][0] = in ? __ldg(reinterpret_cast<const float4*>(col0 + r)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    h[g][1] = (in && two) ? __ldg(reinterpret_cast<const float4*>(col1 + r)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+            for (uint32_t g = 0; g < 4u; ++g)
+                h[g] = in[g] ? __ldg(reinterpret_cast<const float4*>(col + g * 4u * VB_SPARSE_THREADS)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (uint32_t g = 0; g < 2u; ++g) {
-                    sv[g][0] = fma(w0, (double)fmaxf(h[g][0].x, 0.0f), sv[g][0]);
-                    sv[g][1] = fma(w0, (double)fmaxf(h[g][0].y, 0.0f), sv[g][1]);
-                    sv[g][2] = fma(w0, (double)fmaxf(h[g][0].z, 0.0f), sv[g][2]);
-                    sv[g][3] = fma(w0, (double)fmaxf(h[g][0].w, 0.0f), sv[g][3]);
-                    sv[g][0] = fma(w1, (double)fmaxf(h[g][1].x, 0.0f), sv[g][0]);
-                    sv[g][1] = fma(w1, (double)fmaxf(h[g][1].y, 0.0f), sv[g][1]);
-                    sv[g][2] = fma(w1, (double)fmaxf(h[g][1].z, 0.0f), sv[g][2]);
-                    sv[g][3] = fma(w1, (double)fmaxf(h[g][1].w, 0.0f), sv[g][3]);
+            for (uint32_t g = 0; g < 4u; ++g) {
+                s32[g][0] = fmaf(w, fmaxf(h[g].x, 0.0f), s32[g][0]);
+                s32[g][1] = fmaf(w, fmaxf(h[g].y, 0.0f), s32[g][1]);
+                s32[g][2] = fmaf(w, fmaxf(h[g].z, 0.0f), s32[g][2]);
+                s32[g][3] = fmaf(w, fmaxf(h[g].w, 0.0f), s32[g][3]);
+            }
+        }
+#pragma unroll
+        for (uint32_t g = 0; g < 4u; ++g) {
+            if (s32[g][0] < thr32 && s32[g][1] < thr32 && s32[g][2] < thr32 && s32[g][3] < thr32) continue;
+            // ---- pass 2 for this group: exact-order-free fp64 sums, verification, candidates ----
+            const uint32_t r = 4u * tid + g * 4u * VB_SPARSE_THREADS;
+            double sv[4] = {0.0, 0.0, 0.0, 0.0};
+            if (has_acc) {
+                const double2 c01 = *reinterpret_cast<const double2*>(&acc[r]), c23 = *reinterpret_cast<const double2*>(&acc[r + 2u]);
+                sv[0] = c01.x; sv[1] = c01.y; sv[2] = c23.x; sv[3] = c23.y;
+            }
+            if (in[g]) {
+                for (uint32_t k = 0; k < nh; ++k) {
+                    const uint32_t j = s_hv[k];
+                    const float4 hq = __ldg(reinterpret_cast<const float4*>(a.heavy_vals + (size_t)__ldg(a.q_hidx + t_lo + j) * a.heavy_stride + row0 + r));
+                    const double w = s_w[j];
+                    sv[0] = fma(w, (double)fmaxf(hq.x, 0.0f), sv[0]);
+                    sv[1] = fma(w, (double)fmaxf(hq.y, 0.0f), sv[1]);
+                    sv[2] = fma(w, (double)fmaxf(hq.z, 0.0f), sv[2]);
+                    sv[3] = fma(w, (double)fmaxf(hq.w, 0.0f), sv[3]);
                 }
             }
 #pragma unroll
-            for (uint32_t g = 0; g < 2u; ++g) {
-                const uint32_t r = 4u * tid + (g0 + g) * 4u * VB_SPARSE_THREADS;
-                if (sv[g][0] < thr && sv[g][1] < thr && sv[g][2] < thr && sv[g][3] < thr) continue;
-#pragma unroll
-                for (uint32_t e = 0; e < 4u; ++e) {
-                    const uint32_t row = row0 + r + e;
-                    const double S = sv[g][e];
-                    if (S < thr || row >= a.n_rows) continue;
-                    if (mask && !((mask[row >> 5] >> (row & 31u)) & 1u)) continue;
-                    const float f_lo = __double2float_rn(S * (1.0 - delta)), f_hi = __double2float_rn(S * (1.0 + delta));
-                    if (!verify_only || f_lo != f_hi) { s_surv[atomicAdd(&s_nsurv, 1u)] = (uint16_t)(r + e); continue; }
-                    if (f_lo > tau) vb_push_sub(a.lists, list, sub, f_lo, a.row_base + row);
-                }
+            for (uint32_t e = 0; e < 4u; ++e) {
+                const uint32_t row = row0 + r + e;
+                const double S = sv[e];
+                if (S < thr || row >= a.n_rows) continue;
+                if (mask && !((mask[row >> 5] >> (row & 31u)) & 1u)) continue;
+                const float f_lo = __double2float_rn(S * (1.0 - delta)), f_hi = __double2float_rn(S * (1.0 + delta));
+                if (!verify_only || f_lo != f_hi) { s_surv[atomicAdd(&s_nsurv, 1u)] = (uint16_t)(r + e); continue; }
+                if (f_lo > tau) vb_push_sub(a.lists, list, sub, f_lo, a.row_base + row);
             }
         }
     } else

@@ -1071,6 +1071,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
             a.tau = b.tau; a.lists = L; a.mask_words = b.mask_words;
             a.n_qterms = b.n_qterms; a.nt_max = b.nt_max; a.blk_begin = r0 / VB_ROWS_PER_BLOCK; a.n_queries = b.B; a.n_rows = n;
             a.row_base = (uint32_t)h->row_base; a.direct = direct;
+            { static const char* dbg = getenv("VB200_SPARSE_DEBUG"); a.debug = dbg ? (uint32_t)atoi(dbg) : 0u; }
             const uint32_t nblk = (r1 - r0 + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK;
             vb_sparse_kernel<<<nblk * b.B, VB_SPARSE_THREADS, vb_sparse_smem_bytes(b.nt_max), ss>>>(a);
             CKK("vb_sparse_kernel");
