@@ -538,3 +538,69 @@ def test_snapshot_save_load_roundtrip(world, tmp_path):
         jx.close()
     with pytest.raises(eng.B200Error):
         eng.Index.load(tmp_path / "missing.vb200")
+
+
+def test_full_size_cfg2_properties():
+    """BASELINE configs[1] at FULL size (1M x 384, batch 64, top-10 hybrid RRF) through size-independent
+    properties (the oracle comparison at this size is bench.py's parity_spot_check):
+      * the sparse branch of a query does not depend on the batch it travels in (B = 64 vs B = 1), bit for bit;
+      * the dense branch agrees between the tensor-core batch path and the single-query scan within the stated
+        1e-3 tie tolerance;
+      * top-10 is a prefix of top-20 for both branches;
+      * splitting the corpus into two shards and merging (the multi-GPU flow, emulated on one GPU) gives the
+        single-index answer; deleting a query's best row removes exactly that row from its lists."""
+    import torch
+    from voitta_rag_b200 import engine, synth
+    dev = torch.device("cuda", 0)
+    n, dim, B = 1_000_000, 384, 64
+    ix = engine.Index(dim)
+    halves = [engine.Index(dim, row_base=0), engine.Index(dim, row_base=n // 2)]
+    keep = None
+    for blk in range(n // 125_000):
+        rows = synth.dense_rows(125_000, dim, blk, dev, "C")
+        ip, tm, vl = synth.sparse_rows(125_000, blk, dev)
+        sc, cr, mo = synth.columns(125_000, blk, dev)
+        torch.cuda.synchronize()
+        for target in (ix, halves[0] if blk < 4 else halves[1]):
+            target.upsert_dev(125_000, rows.data_ptr(), ip.data_ptr(), tm.data_ptr(), vl.data_ptr(), sc.data_ptr(),
+                              cr.data_ptr(), mo.data_ptr())
+        if keep is None:
+            keep = (rows, ip, tm)
+    Q, SP = synth.queries(B, 0, keep[0], keep[1], keep[2])
+    try:
+        full = ix.search_batch(Q, SP, limit=10, fusion="rrf", branches=True)
+        assert ix.stats()["last_dense_path"] == 2
+        wide = ix.search_batch(Q, SP, limit=20, kprime=60, fusion="rrf", branches=True)
+        for i in range(B):
+            assert len(full.branch(i, "dense")) == 30 and len(full.hits(i)) == 10
+            assert wide.branch(i, "sparse")[:30] == full.branch(i, "sparse"), f"sparse prefix q{i}"
+            assert_same_ranking(wide.branch(i, "dense")[:30], full.branch(i, "dense"), rel_tol=1e-6, abs_tol=1e-6, what=f"dense prefix q{i}")
+        for i in (0, 17, 63):
+            one = ix.search_batch(Q[i:i + 1], SP[i:i + 1], limit=10, fusion="rrf", branches=True)
+            assert ix.stats()["last_dense_path"] == 1
+            assert one.branch(0, "sparse") == full.branch(i, "sparse"), f"sparse batch independence q{i}"
+            assert_same_ranking(full.branch(i, "dense"), one.branch(0, "dense"), rel_tol=1e-3, abs_tol=1e-3, what=f"K2 vs K1 q{i}")
+        # two shards + merge == one index (global idf: weights computed once from the full index)
+        terms = np.asarray(sorted({int(t) for s in SP for t in s[0]}), np.uint32)
+        df, n_live = ix.term_stats(terms)
+        dfm = dict(zip(terms.tolist(), df.tolist()))
+        W = [(s[0], [v * math.log((n_live - dfm[t] + 0.5) / (dfm[t] + 0.5) + 1.0) for t, v in zip(s[0], s[1])]) for s in SP]
+        words = engine.Index.cand_block_words(B, 30)
+        gathered = torch.zeros(2 * words, dtype=torch.int64, device=dev)
+        for r, hx in enumerate(halves):
+            hx.search_local(gathered[r * words:].data_ptr(), Q, W, None, None, limit=10, kprime=30, fusion="rrf")
+        torch.cuda.synchronize()
+        merged = halves[0].merge_fuse(gathered.data_ptr(), 2, Q, W, limit=10, kprime=30, fusion="rrf", branches=True)
+        for i in range(B):
+            assert merged.branch(i, "sparse") == full.branch(i, "sparse"), f"sharded sparse q{i}"
+            assert merged.branch(i, "dense") == full.branch(i, "dense"), f"sharded dense q{i}"
+            assert merged.hits(i) == full.hits(i)
+        # delete the best dense row of query 0: it disappears, everything else keeps its order
+        best = full.branch(0, "dense")[0][0]
+        ix.delete_rows([best])
+        after = ix.search_batch(Q[:1], SP[:1], limit=10, fusion="rrf", branches=True)
+        assert best not in [r for r, _ in after.branch(0, "dense")] and best not in [r for r, _ in after.branch(0, "sparse")]
+    finally:
+        ix.close()
+        for hx in halves:
+            hx.close()
