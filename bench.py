@@ -295,11 +295,7 @@ def main():
                 ix.run_local(None)
                 ix.run_fuse(0, None)
             else:
-                words = ix.cand_block_words(B, kprime)
-                local, gathered = sh._buf("local", words), sh._buf("gathered", words * world)
-                ix.run_local(local.data_ptr())
-                dist.all_gather_into_tensor(gathered, local)
-                ix.run_fuse(world, gathered.data_ptr())
+                sh._enqueue(B, kprime)      # threshold all-reduce, local branches, candidate all-gather, merge + fuse
             ev1.record(sh.stream)
         res = ix.fetch(staged, allow_overflow=True)
         if res is None:

@@ -310,6 +310,29 @@ def test_two_shards_merge_equals_single_index(world):
             assert np.array_equal(getattr(merged, name), getattr(single, name)), (fusion, name)
         # idf computed by numpy here vs libm in the library may differ in the last bit of a weight
         np.testing.assert_allclose(merged.sparse_scores, single.sparse_scores, rtol=1e-6)
+        # the same with the threshold exchange of the sharded flow (all-reduce MAX emulated with torch.maximum):
+        # shards keep fewer candidates, the merged answer is identical
+        taus = []
+        staged = []
+        for sh_ix in (a, b):
+            staged.append(sh_ix.stage(Q, SPW, gf, fo, limit=limit, kprime=k, fusion=fusion, apply_idf=False, branches=True))
+            sh_ix.run_local_begin()
+            t = torch.zeros(2 * len(qs), dtype=torch.float32, device="cuda")
+            sh_ix.tau_export(t.data_ptr())
+            taus.append(t)
+        torch.cuda.synchronize()
+        tmax = torch.maximum(taus[0], taus[1])
+        torch.cuda.synchronize()
+        for sh_ix, buf in zip((a, b), bufs):
+            sh_ix.tau_import(tmax.data_ptr())
+            sh_ix.run_local(buf.data_ptr())
+        torch.cuda.synchronize()
+        gathered2 = torch.cat(bufs)
+        a.run_fuse(2, gathered2.data_ptr())
+        shared = a.fetch(staged[0])
+        for name in ("rows", "counts", "dense_rows", "dense_scores", "dense_counts", "sparse_rows", "sparse_counts"):
+            assert np.array_equal(getattr(shared, name), getattr(merged, name)), ("threshold exchange", fusion, name)
+        assert np.array_equal(shared.sparse_scores, merged.sparse_scores)
         np.testing.assert_allclose(merged.scores, single.scores, rtol=1e-6, atol=1e-9)
     a.close(); b.close()
 

@@ -47,7 +47,24 @@ class FakeShardIndex:
         self.st = dict(q=queries, sp=sparse, fl=filters, fo=filter_of, limit=limit, k=kprime, fusion=fusion, w=sparse_weight)
         return "staged"
 
+    # threshold exchange hooks (the double has no thresholds: it exports -inf and ignores the import, which
+    # exercises the collective of ShardedIndex._enqueue on CPU)
+    def run_local_begin(self):
+        self.began = True
+
+    def tau_export(self, ptr):
+        n = 2 * len(self.st["q"])
+        a = np.full(n, -np.inf, np.float32)
+        ctypes.memmove(ptr, a.ctypes.data, a.nbytes)
+
+    def tau_import(self, ptr):
+        n = 2 * len(self.st["q"])
+        got = np.ctypeslib.as_array((ctypes.c_float * n).from_address(ptr))
+        assert np.all(np.isneginf(got))
+        self.imported = True
+
     def run_local(self, ptr):
+        assert getattr(self, "began", False) and getattr(self, "imported", False)
         st = self.st
         fl = None if not st["fl"] else [(f.scope_bits, f.ts_field, f.ts_lo, f.ts_hi) for f in st["fl"]]
         out = self.cc.search_batch(st["q"], st["sp"], fl, st["fo"], st["limit"], st["k"], 1 if st["sp"] is not None else 0,
@@ -103,6 +120,7 @@ def _worker(rank, world, port, ret):
         cuts = [0, 1100, n]
         shard = FakeShardIndex(coded, cuts[rank], cuts[rank + 1])
         sh = ShardedIndex(shard, rank, world, device=torch.device("cpu"))
+        sh.share_thresholds = True                              # exercise the optional threshold all-reduce too
         t, df = shard.directory()
         sh.finalize(t, df, shard.n)
         assert sh.n_live_g == n

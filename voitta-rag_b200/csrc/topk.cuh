@@ -183,7 +183,9 @@ __device__ __forceinline__ void vb_compact_body(uint64_t* __restrict__ gkeys, co
     for (uint32_t i = threadIdx.x; i < keep; i += VB_COMPACT_THREADS) gkeys[i] = s_sel[i];
     if (threadIdx.x < VB_SUB) cnt_out[threadIdx.x] = threadIdx.x == 0 ? keep : 0u;   // the list now lives in sub-range 0
     if (threadIdx.x == 0) {
-        *tau_out = (keep >= k) ? vb_key_score(s_sel[k - 1]) : -INFINITY;
+        // never below the threshold the segment ran with: another shard's k'-th best may have been imported
+        // (vb_tau_import), and then this list can legitimately hold fewer than k' entries
+        *tau_out = fmaxf(*tau_out, (keep >= k) ? vb_key_score(s_sel[k - 1]) : -INFINITY);
     }
 }
 

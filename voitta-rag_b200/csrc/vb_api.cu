@@ -71,7 +71,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Batch {
     uint32_t B = 0, k = 0, limit = 0, n_lists = 0, n_qterms = 0, nt_max = 1, n_filters = 0, mask_words = 0, n_blocks = 0;
-    bool any_sparse = false, use_mask = false, any_heavy = false;
+    bool any_sparse = false, use_mask = false, any_heavy = false, begun = false;
     uint32_t seg_ratio = 32;                   // growth factor of the segment schedule for this batch
     std::vector<int32_t> mode, mask_of_host;
     // device pointers into h->args
@@ -965,7 +965,9 @@ static int launch_scan(vb_index* h, const Batch& b, const VbLists& L, uint32_t r
 
 // Score both branches of this shard and leave the exact, sorted top-k' of every list in
 // cand[list][0..cnt).  `safe`: fixed small segments that can never overflow a list.
-static int run_branches(vb_index* h, const Batch& b, bool safe) {
+// phase 0: everything; 1: set-up + first segment only; 2: the remaining segments (after phase 1, with the
+// thresholds possibly raised in between by vb_tau_import — the multi-GPU layer's threshold exchange)
+static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     const uint32_t n = (uint32_t)h->n_rows;
     // segment schedule (boundaries are multiples of VB_ROWS_PER_BLOCK)
     std::vector<uint32_t> bounds{0};
@@ -980,7 +982,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
     const VbLists L = make_lists(h, b, safe_mode);
     // the first segment writes its keys to fixed slots at the front of the list (no atomics)
     const uint32_t direct_rows = bounds[1] <= h->cand_cap ? bounds[1] : 0u;
-    TRY(init_lists(h, b, direct_rows));
+    if (phase != 2) TRY(init_lists(h, b, direct_rows));
     // dense path choice
     int path = (int)h->opt_dense_path;
     if (path == 0) path = vb_gemm_supported(h->d_pad, b.B) && b.B >= 2 ? 2 : 1;
@@ -996,12 +998,14 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
     TRY(dev_reserve(h, h->q_hat, (size_t)b.B * h->d_pad * 4, false));
     TRY(dev_reserve(h, h->q_bf16, (size_t)(2 * ((size_t)b.B + 256)) * h->d_pad * 2, false));
     TRY(dev_reserve(h, h->q_scale, (size_t)b.B * 4, false));
-    vb_prep_query_kernel<<<b.B, 128, 0, h->stream>>>(b.d_q, (uint32_t)h->dim, (uint32_t)h->d_pad, b.B, plan.sub, plan.split,
-                                                     h->q_hat.as<float>(), h->q_bf16.as<__nv_bfloat16>(), h->q_scale.as<float>());
-    CKK("vb_prep_query_kernel");
-    ++h->stats.last_launches;
+    if (phase != 2) {
+        vb_prep_query_kernel<<<b.B, 128, 0, h->stream>>>(b.d_q, (uint32_t)h->dim, (uint32_t)h->d_pad, b.B, plan.sub, plan.split,
+                                                         h->q_hat.as<float>(), h->q_bf16.as<__nv_bfloat16>(), h->q_scale.as<float>());
+        CKK("vb_prep_query_kernel");
+        ++h->stats.last_launches;
+    }
     // K0 filter masks
-    if (b.use_mask) {
+    if (b.use_mask && phase != 2) {
         prof_begin(h, PH_MASK);
         TRY(dev_reserve(h, h->mask, (size_t)b.n_filters * b.mask_words * 4, false));
         vb_mask_kernel<<<grid_for((uint64_t)b.mask_words * 32, 256, h->sm_count * 8), 256, 0, h->stream>>>(
@@ -1086,7 +1090,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
         prof_end(h, ps, ss);
         return 0;
     };
-    if (do_sparse) {                                            // sparse slice table (sparse chain)
+    if (do_sparse && phase != 2) {                              // sparse slice table (sparse chain)
         const int pi = prof_begin(h, PH_SPARSE, ss);
         const uint64_t total = (uint64_t)b.n_qterms * (b.n_blocks + 1);
         TRY(dev_reserve(h, h->offs, total * 4, false));
@@ -1098,7 +1102,8 @@ static int run_branches(vb_index* h, const Batch& b, bool safe) {
     }
     // enqueue the two chains interleaved so that neither stream starves on the host side
     const size_t n_seg = bounds.size() - 1;
-    for (size_t s = 0; s < n_seg; ++s) {
+    const size_t s_begin = phase == 2 ? 1 : 0, s_end = phase == 1 ? 1 : n_seg;
+    for (size_t s = s_begin; s < s_end; ++s) {
         const uint32_t direct = (s == 0 && direct_rows) ? 1u : 0u;
         const bool big = s + 1 == n_seg;
         if (big) h->stats.last_big_rows = bounds[s + 1] - bounds[s];
@@ -1221,17 +1226,69 @@ extern "C" int vb_stage(vb_index* h, const vb_query_batch* q, int32_t want_branc
     return 0;
 }
 
+__global__ void vb_tau_import_kernel(float* __restrict__ tau, const float* __restrict__ shared, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        // a row that merely EQUALS another shard's k'-th best can still win its tie at the merge (the order is
+        // score desc, global row asc), so the imported threshold is the next float below it
+        const float g = shared[i];
+        const float lowered = (g > -INFINITY && g < INFINITY) ? nextafterf(g, -INFINITY) : -INFINITY;
+        tau[i] = fmaxf(tau[i], lowered);
+    }
+}
+
+extern "C" int vb_run_local_begin(vb_index* h) {
+    if (!h) return vb_fail("vb_run_local_begin: NULL index");
+    std::lock_guard<std::mutex> lk(h->mu);
+    Batch& b = h->staged_s[h->cur];
+    if (!b.valid) return vb_fail("vb_run_local_begin: no staged batch");
+    CK(cudaSetDevice(h->device));
+    h->stats.last_launches = 0;
+    CK(cudaEventRecord(h->ev0s[h->cur], h->stream));
+    if (h->n_rows == 0) TRY(init_lists(h, b, 0));
+    else TRY(run_branches(h, b, h->staged_safe, 1));
+    b.begun = true;
+    return 0;
+}
+
+extern "C" int vb_tau_export(vb_index* h, float* tau_dev) {
+    if (!h || !tau_dev) return vb_fail("vb_tau_export: NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    const Batch& b = h->staged_s[h->cur];
+    if (!b.valid || !b.begun) return vb_fail("vb_tau_export: call vb_run_local_begin first");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(tau_dev, b.tau, (size_t)b.n_lists * 4, cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
+
+extern "C" int vb_tau_import(vb_index* h, const float* tau_dev) {
+    if (!h || !tau_dev) return vb_fail("vb_tau_import: NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    const Batch& b = h->staged_s[h->cur];
+    if (!b.valid || !b.begun) return vb_fail("vb_tau_import: call vb_run_local_begin first");
+    CK(cudaSetDevice(h->device));
+    vb_tau_import_kernel<<<(b.n_lists + 255) / 256, 256, 0, h->stream>>>(b.tau, tau_dev, b.n_lists);
+    CKK("vb_tau_import_kernel");
+    ++h->stats.last_launches;
+    return 0;
+}
+
 extern "C" int vb_run_local(vb_index* h, uint64_t* cand_dev) {
     if (!h) return vb_fail("vb_run_local: NULL index");
     std::lock_guard<std::mutex> lk(h->mu);
     if (!h->staged_s[h->cur].valid) return vb_fail("vb_run_local: no staged batch");
     CK(cudaSetDevice(h->device));
-    h->stats.last_launches = 0;
-    CK(cudaEventRecord(h->ev0s[h->cur], h->stream));
-    if (h->n_rows == 0) {
-        TRY(init_lists(h, h->staged_s[h->cur], 0));
+    if (h->staged_s[h->cur].begun) {                            // first segment done by vb_run_local_begin
+        h->staged_s[h->cur].begun = false;
+        if (h->n_rows != 0) TRY(run_branches(h, h->staged_s[h->cur], h->staged_safe, 2));
     } else {
-        TRY(run_branches(h, h->staged_s[h->cur], h->staged_safe));
+        h->stats.last_launches = 0;
+        CK(cudaEventRecord(h->ev0s[h->cur], h->stream));
+        if (h->n_rows == 0) {
+            TRY(init_lists(h, h->staged_s[h->cur], 0));
+        } else {
+            TRY(run_branches(h, h->staged_s[h->cur], h->staged_safe));
+        }
     }
     if (cand_dev) {
         vb_export_kernel<<<h->staged_s[h->cur].n_lists, 128, 0, h->stream>>>(h->cand.as<uint64_t>(), h->staged_s[h->cur].cnt, h->cand_cap, h->staged_s[h->cur].k, cand_dev, h->staged_s[h->cur].overflow, h->staged_s[h->cur].n_lists);
