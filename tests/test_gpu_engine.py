@@ -627,3 +627,62 @@ def test_full_size_cfg2_properties():
         ix.close()
         for hx in halves:
             hx.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_sparse_relaxed_mode_stress(seed):
+    """Relaxed sparse mode under stress: a small vocabulary (dozens of dense columns, queries that hold many of
+    them), queries of 1 .. 256 terms (the term table spans several 32-term chunks), posting values that are zero,
+    denormal, tiny and huge in the same corpus, weights over 30 orders of magnitude — sparse lists must equal the
+    oracle's ordered fp64 sums bit for bit, through several segments, with and without a filter."""
+    from voitta_rag_b200 import engine
+    rng = np.random.RandomState(100 + seed)
+    n, dim, V = 20_000, 32, 400
+    dense = _data.bf16_round(rng.randn(n, dim).astype(np.float32))
+    vocab = np.unique(rng.randint(1, 2**31 - 1, size=4 * V).astype(np.int64))[:V]      # sorted, distinct
+    assert len(vocab) == V
+    p = 1.0 / np.arange(1, V + 1) ** 0.9
+    p /= p.sum()
+    lens = rng.randint(20, 121, size=n)
+    picks = rng.choice(V, size=(n, 120), p=p)
+    picks[np.arange(120)[None, :] >= lens[:, None]] = V          # beyond the row's length: sentinel, sorted last
+    picks.sort(axis=1)
+    keep = np.ones_like(picks, bool)
+    keep[:, 1:] = picks[:, 1:] != picks[:, :-1]
+    keep &= picks < V
+    counts = keep.sum(axis=1)
+    indptr = np.zeros(n + 1, np.int64); np.cumsum(counts, out=indptr[1:])
+    terms = vocab[picks[keep]].astype(np.uint32)                  # row-major, ascending (vocab is sorted)
+    nnz = len(terms)
+    kind = rng.randint(0, 10, size=nnz)
+    vals = (0.2 + 2.0 * rng.rand(nnz)).astype(np.float32)
+    vals[kind == 0] = 0.0
+    vals[kind == 1] = np.float32(1e-42)          # denormal
+    vals[kind == 2] = np.float32(3e-30)
+    vals[kind == 3] = np.float32(7e18)
+    scope = rng.randint(0, 8, size=n).astype(np.uint32)
+    ix = engine.Index(dim)
+    ix.upsert(dense, (indptr, terms, vals), scope, None, None)
+    cc = oracle_c.CorpusC(dense, (indptr, terms, vals), scope, None, None)
+    nts = [1, 2, 5, 31, 32, 33, 64, 100, 200, 256, 7, 12]
+    SP = []
+    for nt in nts:
+        t = np.sort(rng.choice(V, size=min(nt, V), replace=False))
+        w = (10.0 ** rng.uniform(-15, 15, size=len(t))) if nt % 2 else (0.5 + rng.rand(len(t)))
+        SP.append((vocab[t].tolist(), [float(x) for x in w]))
+    B = len(SP)
+    Q = _data.bf16_round(rng.randn(B, dim).astype(np.float32))
+    bits = np.zeros(1, np.uint32); bits[0] = 0b10110101
+    try:
+        ix.set_option("seg_ratio", 4)
+        for apply_idf in (True, False):
+            for fl, fo in ((None, None), ([(bits, 0, 0, 0)], np.zeros(B, np.int32))):
+                filters = None if fl is None else [engine.Filter(*f) for f in fl]
+                got = ix.search_batch(Q, SP, filters, fo, limit=20, fusion="rrf", branches=True, apply_idf=apply_idf)
+                want = cc.search_batch(Q, SP, fl, fo, limit=20, fusion=2, apply_idf=apply_idf)
+                for i in range(B):
+                    ws = [(int(want["sparse_rows"][i, j]), float(want["sparse_scores"][i, j])) for j in range(want["sparse_counts"][i])]
+                    assert_same_ranking(got.branch(i, "sparse"), ws, rel_tol=0.0, what=f"stress nt={nts[i]} idf={apply_idf} filter={fl is not None}")
+        assert ix.stats()["overflow_reruns"] <= 8
+    finally:
+        ix.close()
