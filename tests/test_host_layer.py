@@ -122,3 +122,45 @@ def test_snapshot_roundtrip_restores_ids_payloads_and_results(store, tmp_path):
     m = VS.ChunkMetadata("z/new.txt", "z", "z", "new.txt", 0, 1, 0, 1, "t")
     ids = fresh.store_chunks([("t", [1.0] * GOLD["dim"], m)], [([3, 9], [1.0, 2.0])])
     assert len(ids) == 1 and fresh.count_by_file("z/new.txt") == 1 and fresh.delete_by_file("z/new.txt") == 1
+
+
+def test_concurrent_readers_and_writer(store):
+    """The reference's singleton is hit from several threads (MCP tool calls, the indexing worker, the file
+    watcher): concurrent store / search / delete / count through the host layer neither raise nor
+    corrupt the id / payload bookkeeping."""
+    import threading
+    dim = GOLD["dim"]
+    errors = []
+
+    def meta(i, f):
+        return VS.ChunkMetadata(f"root/{f}", "root", "root", f, i, 4, 0, 1, "t")
+
+    def writer(k):
+        try:
+            for it in range(12):
+                f = f"w{k}_{it}.txt"
+                ids = store.store_chunks([(f"text {i}", [float((i + k + it) % 7 + 1)] * dim, meta(i, f)) for i in range(4)],
+                                         [([3 + i, 11 + k], [1.0, 2.0]) for i in range(4)])
+                assert len(ids) == 4 and store.count_by_file(f"root/{f}") == 4
+                if it % 3 == 2:
+                    assert store.delete_by_file(f"root/{f}") == 4
+        except Exception as e:                                  # pragma: no cover - reported below
+            errors.append(repr(e))
+
+    def reader():
+        try:
+            for _ in range(40):
+                res = store.search([1.0] * dim, limit=5, sparse_query=([3, 11], [1.0, 1.0]))
+                assert len(res) <= 5 and all(r.metadata.folder_path == "root" for r in res)
+                store.get_collection_info(); store.get_file_chunk_counts("root")
+        except Exception as e:                                  # pragma: no cover
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=writer, args=(k,)) for k in range(3)] + [threading.Thread(target=reader) for _ in range(3)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not errors, errors
+    # 3 writers x 12 files x 4 chunks, every third file deleted again
+    assert store.get_collection_info()["points_count"] == 3 * (12 - 4) * 4
