@@ -24,5 +24,5 @@ ncu --set full --clock-control none --import-source on -k regex:vb_sparse_kernel
 echo "sparse full rc=$?"
 CMD2="python bench.py --workload cfg3-b256-s50 --steps 3 --warmup 3 --no-cpu-baseline"
 $CMD2 > gpurun_out/plain4.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:vb_dense_gemm_tiled -s 8 -c 1 -f -o gpurun_out/${R}_prof_tiled $CMD2 > gpurun_out/ncu4.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:vb_dense_gemm_tiled -s 11 -c 1 -f -o gpurun_out/${R}_prof_tiled $CMD2 > gpurun_out/ncu4.log 2>&1
 echo "tiled full rc=$?"
