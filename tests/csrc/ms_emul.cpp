@@ -1,0 +1,90 @@
+// CPU emulation of K3M (voitta-rag_b200/csrc/sparse_ms.cuh) — TEST INFRASTRUCTURE ONLY.
+// The development container has no GPU, so the host/device functions that carry the MaxScore logic
+// (plan phases, per-posting scoring, lookups, re-score) are compiled here with g++ and driven the way
+// the two kernels drive them: plan phases as loops over the terms, then every work unit, every posting.
+// tests/test_ms_emul.py checks the candidates against the oracle.  Nothing in the product links this.
+#include "../../voitta-rag_b200/csrc/sparse_ms.cuh"
+#include <vector>
+#include <algorithm>
+
+extern "C" int ms_emul_segment(
+    const uint32_t* post_row, const float* post_val, const float* heavy_vals, uint32_t heavy_stride,
+    const int64_t* sp_indptr, const uint32_t* sp_term, const float* sp_val,
+    uint32_t nt, const uint32_t* q_term, const double* q_weight, const double* q_ub, const int32_t* q_hidx,
+    const uint32_t* q_plo, const uint32_t* q_phi, const uint32_t* mask, float tau,
+    uint32_t seg_row0, uint32_t seg_row1, uint32_t n_rows, uint32_t chunk, uint32_t budget_pct, uint32_t cshift,
+    uint32_t* out_rows, float* out_scores, uint32_t max_out, uint64_t* stats /* [4]: essential postings, units, n_ess, lookups-unused */)
+{
+    if (nt == 0 || nt > VB_MS_MAX_TERMS) return -1;
+    // ---- plan (vb_ms_plan_kernel) ----
+    VbMsPlanShared s;
+    for (uint32_t j = 0; j < nt; ++j) vb_ms_plan_load(s, j, post_row, q_plo[j], q_phi[j], seg_row0, seg_row1, q_ub[j]);
+    for (uint32_t j = 0; j < nt; ++j) vb_ms_plan_partition(s, j, nt, (double)tau, budget_pct);
+    std::vector<uint32_t> pos(nt);
+    uint32_t n_ess = 0;
+    for (uint32_t j = 0; j < nt; ++j) { pos[j] = vb_ms_plan_position(s, j, nt, n_ess); s.ub_pos[pos[j]] = s.ub[j]; }
+    std::vector<VbMsRec> rec(nt);
+    std::vector<uint32_t> units(nt + 1, 0);
+    for (uint32_t j = 0; j < nt; ++j) {
+        VbMsRec r;
+        r.slo = s.slo[j]; r.shi = s.shi[j]; r.w = q_weight[j]; r.suf = vb_ms_plan_suffix(s, pos[j], nt);
+        r.hidx = q_hidx ? q_hidx[j] : -1; r.j = j;
+        rec[pos[j]] = r;
+        units[pos[j]] = s.ne[j] ? 0u : (s.len[j] + chunk - 1u) / chunk;
+    }
+    { uint32_t run = 0; for (uint32_t i = 0; i <= nt; ++i) { const uint32_t c = i < nt ? units[i] : 0u; units[i] = run; run += c; } }
+    const uint32_t total = units[nt];
+    // sanity: positions are a permutation
+    { std::vector<uint32_t> p(pos); std::sort(p.begin(), p.end()); for (uint32_t i = 0; i < nt; ++i) if (p[i] != i) return -2; }
+    // ---- coarse slice table (vb_ms_coarse_kernel) ----
+    const uint32_t n_cb = (uint32_t)(((uint64_t)(n_rows - 1u) >> cshift) + 2u);
+    std::vector<uint32_t> offc((size_t)n_cb * nt);
+    for (uint32_t cb = 0; cb < n_cb; ++cb)
+        for (uint32_t t = 0; t < nt; ++t) {
+            const uint64_t target = (uint64_t)cb << cshift;
+            offc[(size_t)cb * nt + t] = target > 0xffffffffull ? q_phi[t] : vb_ms_lower_bound(post_row, q_plo[t], q_phi[t], (uint32_t)target);
+        }
+    // ---- score (vb_ms_score_kernel) ----
+    std::vector<double> w(nt), suf(nt);
+    std::vector<int32_t> hidx(nt);
+    std::vector<uint32_t> nlo(nt), nhi(nt);
+    uint32_t n_out = 0;
+    uint64_t ess_post = 0;
+    for (uint32_t u = 0; u < total; ++u) {
+        uint32_t lo = 0, hi = nt;
+        while (hi - lo > 1u) { const uint32_t mid = lo + ((hi - lo) >> 1); if (units[mid] <= u) lo = mid; else hi = mid; }
+        const uint32_t pe = lo;
+        const VbMsRec e = rec[pe];
+        const uint32_t p0 = e.slo + (u - units[pe]) * chunk;
+        const uint32_t p1 = std::min(e.shi, p0 + chunk);
+        if (p0 >= p1) return -3;
+        const uint32_t r_first = post_row[p0], r_last = post_row[p1 - 1u];
+        const uint32_t cb0 = r_first >> cshift, cb1 = std::min((r_last >> cshift) + 1u, n_cb - 1u);
+        for (uint32_t i = 0; i < nt; ++i) {
+            const VbMsRec r = rec[i];
+            w[i] = r.w; suf[i] = r.suf; hidx[i] = r.hidx;
+            uint32_t a = r.slo, b = r.shi;
+            if (r.hidx < 0 && i != pe && b > a) {
+                a = std::max(a, offc[(size_t)cb0 * nt + r.j]);
+                b = std::min(b, offc[(size_t)cb1 * nt + r.j]);
+                if (b < a) b = a;
+            }
+            nlo[i] = a; nhi[i] = b;
+        }
+        VbMsCtx c;
+        c.post_row = post_row; c.post_val = post_val; c.heavy_vals = heavy_vals; c.heavy_stride = heavy_stride;
+        c.sp_indptr = sp_indptr; c.sp_term = sp_term; c.sp_val = sp_val; c.q_term = q_term; c.q_weight = q_weight;
+        c.mask = mask; c.w = w.data(); c.suf = suf.data(); c.hidx = hidx.data(); c.nlo = nlo.data(); c.nhi = nhi.data();
+        c.nt = nt; c.n_ess = n_ess; c.tau_lo = vb_ms_tau_lo((double)tau); c.delta = (double)(4u * nt) * 1.1102230246251565e-16; c.tau = tau;
+        for (uint32_t p = p0; p < p1; ++p) {
+            ++ess_post;
+            float score;
+            if (vb_ms_score_posting(c, pe, post_row[p], post_val[p], score)) {
+                if (n_out < max_out) { out_rows[n_out] = post_row[p]; out_scores[n_out] = score; }
+                ++n_out;
+            }
+        }
+    }
+    if (stats) { stats[0] = ess_post; stats[1] = total; stats[2] = n_ess; stats[3] = 0; }
+    return (int)n_out;
+}

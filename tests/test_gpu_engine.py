@@ -686,3 +686,38 @@ def test_sparse_relaxed_mode_stress(seed):
         assert ix.stats()["overflow_reruns"] <= 8
     finally:
         ix.close()
+
+
+def test_k3m_equals_k3_and_oracle(world):
+    """The posting-driven MaxScore kernel (K3M, sparse_ms.cuh) and the block x query kernel (K3) must return
+    the same sparse lists bit for bit — under every filter, budget, work-unit size and segment schedule —
+    and both equal the oracle's ordered fp64 sums."""
+    ix, coded = world["ix"], world["coded"]
+    qs = world["queries"]
+    Q = np.stack([q for q, _ in qs]); SP = [s for _, s in qs]
+    B = len(qs)
+    eng = world["engine"]
+    try:
+        for fi, flt in enumerate(filters_for(coded)):
+            gf = None if flt is None else [eng.Filter(*flt)]
+            fo = None if flt is None else np.zeros(B, np.int32)
+            ix.set_option("sparse_ms", 0)
+            base = ix.search_batch(Q, SP, gf, fo, limit=20, fusion="rrf", branches=True)
+            ix.set_option("sparse_ms", 1)
+            for opts in ({}, {"ms_chunk": 512}, {"ms_chunk": 8192, "ms_budget": 20}, {"ms_budget": 0},
+                         {"seg_ratio": 2}, {"seg_first": 16384, "seg_ratio": 2, "ms_chunk": 512}, {"safe_mode": 1},
+                         {"sparse_dense": 0}):
+                for k, v in opts.items():
+                    ix.set_option(k, v)
+                r = ix.search_batch(Q, SP, gf, fo, limit=20, fusion="rrf", branches=True)
+                for name in ("rows", "scores", "counts", "sparse_rows", "sparse_scores", "sparse_counts"):
+                    assert np.array_equal(getattr(r, name), getattr(base, name)), (fi, opts, name)
+                for k in opts:
+                    ix.set_option(k, {"ms_chunk": 0, "ms_budget": 100, "seg_ratio": 0, "seg_first": 2048, "safe_mode": 0, "sparse_dense": 1}[k])
+            want = world["cc"].search_batch(Q, SP, None if flt is None else [flt], fo, limit=20, kprime=60, fusion=2)
+            for i in range(B):
+                ws = [(int(want["sparse_rows"][i, j]), float(want["sparse_scores"][i, j])) for j in range(want["sparse_counts"][i])]
+                assert_same_ranking(base.branch(i, "sparse"), ws, rel_tol=0.0, what=f"k3m f{fi} q{i}")
+    finally:
+        for k, v in {"sparse_ms": 1, "ms_chunk": 0, "ms_budget": 100, "seg_ratio": 0, "seg_first": 2048, "safe_mode": 0, "sparse_dense": 1}.items():
+            ix.set_option(k, v)

@@ -112,6 +112,8 @@ struct VbSparseArgs {
     uint32_t n_rows;
     uint32_t row_base;
     uint32_t direct;            // 1: first segment — store keys at slot (row - segment begin), no atomics
+    const uint32_t* q_sel;      // [n_sel] queries this launch scores (the rest go to K3M, sparse_ms.cuh); nullptr = all
+    uint32_t n_sel;
     uint32_t debug;             // perf triage only (VB200_SPARSE_DEBUG): 1 stop after the term table, 2 skip the posting scatter, 4 skip the scan, 8 skip the accumulator init
 };
 
@@ -203,8 +205,9 @@ vb_sparse_kernel(const VbSparseArgs a)
     __shared__ uint32_t s_nsurv;
 
     const uint32_t tid = threadIdx.x;
-    const uint32_t q = blockIdx.x % a.n_queries;
-    const uint32_t blk_rel = blockIdx.x / a.n_queries;
+    const uint32_t n_q = a.q_sel != nullptr ? a.n_sel : a.n_queries;
+    const uint32_t q = a.q_sel != nullptr ? __ldg(a.q_sel + blockIdx.x % n_q) : blockIdx.x % n_q;
+    const uint32_t blk_rel = blockIdx.x / n_q;
     const uint32_t blk = a.blk_begin + blk_rel;
     const uint32_t t_lo = (uint32_t)__ldg(a.q_indptr + q);
     const uint32_t nt = (uint32_t)__ldg(a.q_indptr + q + 1) - t_lo;

@@ -1,0 +1,440 @@
+// K3M — posting-driven MaxScore sparse scoring (the batched / large-segment form of K3).
+// Replaces, like sparse.cuh, qdrant's sparse dot product with the IDF modifier for
+// query_points(query=SparseVector, using="bm25", limit=k', query_filter)
+// (vector_store.py:647-656; sparse_distances.py sparse_dot_product in local mode) — same results,
+// bit for bit, but the work is proportional to the postings that can still matter.
+//
+// Why: K3 (sparse.cuh) gives one CTA a (2048-row block, query) pair, initialises 2048 fp64
+// accumulators and scans every row of the block against the query's frequent-term columns.  Once a
+// list has a threshold tau (the score of its current k'-th best), almost all of that work is
+// provably useless: with ub_t = weight_t * (largest posting value of term t), a row that contains
+// only terms whose ub sum stays below tau cannot enter the list (MaxScore).  Measured on the
+// benchmark corpora (tools/proto_maxscore.py) the ESSENTIAL postings are 2-4 % of the posting mass.
+//
+// Per segment, per query (vb_ms_plan_kernel, one CTA per query):
+//   * terms sorted by ub; the longest prefix with sum(ub) < tau is NON-essential (NE);
+//   * essential terms ordered by ascending posting count (rarest first) = "ownership" order, then
+//     the NE terms by descending ub; suf[i] = sum of ub over positions > i;
+//   * every essential term's postings of the segment are cut into work units of `chunk` postings.
+// vb_ms_score_kernel (persistent, dynamic unit counter): one thread per essential posting (e, row):
+//   1. filter bit of the row;
+//   2. w_e*v + suf[e] < tau  =>  drop (even with every later term present at its maximum the row
+//      cannot reach tau; a frequent essential term's postings almost all end here: 8 bytes, one
+//      fma, one compare);
+//   3. ownership: if an EARLIER essential term also occurs in the row, that posting owns the row;
+//   4. the remaining terms are looked up in position order (frequent terms: one load from the
+//      term's dense column; others: binary search in a range narrowed by a coarse slice table),
+//      stopping as soon as partial + suf[i] < tau;
+//   5. the surviving sum S adds the reference's fp64 products in another order:
+//      |S - S_ref| <= delta*S, delta = 4*nt*2^-53 (all products >= 0).  If float(S(1-delta)) ==
+//      float(S(1+delta)) the fp32 score is provably the reference's; otherwise the row is re-scored
+//      from the forward index in ascending term id (the reference's two-pointer merge order).
+// Only queries whose products are all >= 0 ("relaxed", always true for BM25 vectors) come this way;
+// the others, and the first (direct) segment, stay on K3.
+// Roofline: HBM/L2 gathers.  Algorithmic bytes per launch: 8 B per essential posting + 4..32 B per
+// lookup; bench.py still quotes SURVEY §8(d)'s sum(df)*8 for comparability.
+//
+// The per-posting logic lives in host/device functions so that tests/csrc/ms_emul.cpp can run the
+// very same code on the CPU against the oracle (no GPU in the development container).
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#ifdef __CUDACC__
+#define VB_HD __host__ __device__ __forceinline__
+#else
+#define VB_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define VB_LD(p) __ldg(p)
+#define VB_DMUL(a, b) __dmul_rn((a), (b))
+#define VB_DADD(a, b) __dadd_rn((a), (b))
+#define VB_D2F(a) __double2float_rn(a)
+#else
+#define VB_LD(p) (*(p))
+#define VB_DMUL(a, b) ((a) * (b))      // host build uses -ffp-contract=off
+#define VB_DADD(a, b) ((a) + (b))
+#define VB_D2F(a) ((float)(a))
+#endif
+
+#define VB_MS_MAX_TERMS 256u
+
+// One query term in POSITION order (essential terms by ascending posting count, then NE by descending ub).
+struct VbMsRec {
+    uint32_t slo, shi;      // the term's postings inside the segment: [slo, shi) of post_row / post_val
+    double w;               // idf-scaled query weight
+    double suf;             // sum of ub over the positions after this one
+    int32_t hidx;           // dense column of a frequent term, -1 = none
+    uint32_t j;             // index of the term inside the query (term-id order): row of the coarse slice table
+};
+
+struct VbMsQuery {          // per query, written by the plan kernel
+    double tau_lo;          // tau lowered by 1e-9 relative (raised towards 0 for tau <= 0)
+    uint32_t n_ess;         // essential terms (positions [0, n_ess))
+    uint32_t active;        // 1 = scored by the MaxScore kernel in this segment
+};
+
+// ---- term presence lookups -------------------------------------------------------------------------
+// lower bound of `row` in post_row[lo, hi)
+VB_HD uint32_t vb_ms_lower_bound(const uint32_t* post_row, uint32_t lo, uint32_t hi, uint32_t row) {
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (VB_LD(post_row + mid) < row) lo = mid + 1u; else hi = mid;
+    }
+    return lo;
+}
+
+// value of a term in `row`: dense column (NaN = absent) or binary search in the narrowed range
+VB_HD bool vb_ms_lookup(const uint32_t* post_row, const float* post_val, const float* heavy_vals, uint32_t heavy_stride,
+                        int32_t hidx, uint32_t nlo, uint32_t nhi, uint32_t row, float& val) {
+    if (hidx >= 0) {
+        const float v = VB_LD(heavy_vals + (size_t)hidx * heavy_stride + row);
+        val = v;
+        return v == v;
+    }
+    const uint32_t p = vb_ms_lower_bound(post_row, nlo, nhi, row);
+    if (p < nhi && VB_LD(post_row + p) == row) { val = VB_LD(post_val + p); return true; }
+    return false;
+}
+
+// exact score of a row: the reference's two-pointer merge (ascending term id, fp64 mul then add, one
+// rounding to fp32) over the forward index
+VB_HD float vb_ms_rescore(const int64_t* sp_indptr, const uint32_t* sp_term, const float* sp_val, uint32_t row,
+                          const uint32_t* q_term, const double* q_weight, uint32_t nt) {
+    int64_t p = VB_LD(sp_indptr + row);
+    const int64_t pe = VB_LD(sp_indptr + row + 1);
+    double sc = 0.0;
+    uint32_t j = 0;
+    while (p < pe && j < nt) {
+        const uint32_t t = VB_LD(sp_term + p), qt = VB_LD(q_term + j);
+        if (t == qt) { sc = VB_DADD(sc, VB_DMUL(VB_LD(q_weight + j), (double)VB_LD(sp_val + p))); ++p; ++j; }
+        else if (t < qt) ++p;
+        else ++j;
+    }
+    return VB_D2F(sc);
+}
+
+// Everything one posting needs (pointers into the index + the query's position-ordered tables).
+struct VbMsCtx {
+    const uint32_t* post_row;
+    const float* post_val;
+    const float* heavy_vals;
+    uint32_t heavy_stride;
+    const int64_t* sp_indptr;       // forward index, for the exact re-score
+    const uint32_t* sp_term;
+    const float* sp_val;
+    const uint32_t* q_term;         // this query's terms, ascending id  [nt]
+    const double* q_weight;         // weights in the same order          [nt]
+    const uint32_t* mask;           // filter bitmask of this query or nullptr
+    // position-ordered tables of this query (shared memory on the device)
+    const double* w;                // [nt]
+    const double* suf;              // [nt]
+    const int32_t* hidx;            // [nt]
+    const uint32_t* nlo;            // [nt] lookup range per position, narrowed to the unit's row span
+    const uint32_t* nhi;
+    uint32_t nt, n_ess;
+    double tau_lo;                  // conservative threshold for the bound tests
+    double delta;                   // 4 * nt * 2^-53
+    float tau;                      // the list's threshold (exact compare)
+};
+
+// Score the posting (position pe, row, v).  Returns true and sets `score` iff the row is a candidate
+// owned by this posting (its fp32 score, identical to the reference's, beats tau).
+VB_HD bool vb_ms_score_posting(const VbMsCtx& c, uint32_t pe, uint32_t row, float v, float& score) {
+    if (c.mask != nullptr && !((VB_LD(c.mask + (row >> 5)) >> (row & 31u)) & 1u)) return false;
+    double partial = VB_DMUL(c.w[pe], (double)v);
+    if (partial + c.suf[pe] < c.tau_lo) return false;          // cannot reach tau even with every later term at its maximum
+    float lv;
+    for (uint32_t i = 0; i < pe; ++i)                            // ownership: an earlier essential term in the row owns it
+        if (vb_ms_lookup(c.post_row, c.post_val, c.heavy_vals, c.heavy_stride, c.hidx[i], c.nlo[i], c.nhi[i], row, lv)) return false;
+    for (uint32_t i = pe + 1u; i < c.nt; ++i) {
+        if (partial + c.suf[i - 1u] < c.tau_lo) return false;
+        if (vb_ms_lookup(c.post_row, c.post_val, c.heavy_vals, c.heavy_stride, c.hidx[i], c.nlo[i], c.nhi[i], row, lv))
+            partial = VB_DADD(partial, VB_DMUL(c.w[i], (double)lv));
+    }
+    if (partial < c.tau_lo) return false;
+    const float f_lo = VB_D2F(partial * (1.0 - c.delta)), f_hi = VB_D2F(partial * (1.0 + c.delta));
+    score = f_lo == f_hi ? f_lo : vb_ms_rescore(c.sp_indptr, c.sp_term, c.sp_val, row, c.q_term, c.q_weight, c.nt);
+    return score > c.tau;
+}
+
+// ---- plan: one query, `nt` terms; thread j owns term j.  Phases are separated by barriers on the device
+// and by loops in the CPU emulation. --------------------------------------------------------------------
+struct VbMsPlanShared {
+    double ub[VB_MS_MAX_TERMS];         // term order
+    double ub_pos[VB_MS_MAX_TERMS];     // position order
+    uint32_t len[VB_MS_MAX_TERMS];      // postings inside the segment, term order
+    uint32_t slo[VB_MS_MAX_TERMS], shi[VB_MS_MAX_TERMS];
+    uint8_t ne[VB_MS_MAX_TERMS];
+    uint32_t n_ess;
+};
+
+// phase 1: segment range and upper bound of term j
+VB_HD void vb_ms_plan_load(VbMsPlanShared& s, uint32_t j, const uint32_t* post_row, uint32_t plo, uint32_t phi,
+                           uint32_t seg_row0, uint32_t seg_row1, double ub) {
+    const uint32_t lo = vb_ms_lower_bound(post_row, plo, phi, seg_row0);
+    const uint32_t hi = vb_ms_lower_bound(post_row, lo, phi, seg_row1);
+    s.slo[j] = lo; s.shi[j] = hi; s.len[j] = hi - lo; s.ub[j] = ub;
+}
+
+// phase 2: MaxScore partition.  Sorting by ub, the longest prefix whose ub sum stays below
+// budget_pct % of tau is non-essential.  The 2e-9 margin dwarfs the rounding of the sums (<= 256 terms).
+VB_HD void vb_ms_plan_partition(VbMsPlanShared& s, uint32_t j, uint32_t nt, double tau_d, uint32_t budget_pct) {
+    const double ub = s.ub[j];
+    double cum = 0.0;
+    for (uint32_t i = 0; i < nt; ++i) {
+        const double u = s.ub[i];
+        if (u < ub || (u == ub && i <= j)) cum += u;
+    }
+    const bool ok = budget_pct != 0u && tau_d > 0.0 && tau_d < INFINITY;
+    const uint32_t pct = budget_pct < 100u ? budget_pct : 100u;
+    s.ne[j] = (ok && ub < INFINITY && cum < tau_d * (0.01 * (double)pct) * (1.0 - 2e-9)) ? 1 : 0;
+}
+
+// phase 3: position of term j — essential terms by (posting count, index) ascending, then NE by ub descending
+VB_HD uint32_t vb_ms_plan_position(const VbMsPlanShared& s, uint32_t j, uint32_t nt, uint32_t& n_ess_out) {
+    uint32_t n_ess = 0, before = 0;
+    for (uint32_t i = 0; i < nt; ++i) {
+        if (!s.ne[i]) ++n_ess;
+        if (s.ne[i] != s.ne[j] || i == j) continue;
+        if (!s.ne[j]) before += (s.len[i] < s.len[j] || (s.len[i] == s.len[j] && i < j)) ? 1u : 0u;
+        else before += (s.ub[i] > s.ub[j] || (s.ub[i] == s.ub[j] && i < j)) ? 1u : 0u;
+    }
+    n_ess_out = n_ess;
+    return s.ne[j] ? n_ess + before : before;
+}
+
+// phase 5: suffix sum of ub after position i (summed from the tail: small values first)
+VB_HD double vb_ms_plan_suffix(const VbMsPlanShared& s, uint32_t i, uint32_t nt) {
+    double acc = 0.0;
+    for (uint32_t k = nt; k-- > i + 1u;) acc += s.ub_pos[k];
+    return acc;
+}
+
+VB_HD double vb_ms_tau_lo(double tau_d) { return tau_d > 0.0 ? tau_d * (1.0 - 1e-9) : tau_d * (1.0 + 1e-9); }
+
+#ifdef __CUDACC__
+#include "common.cuh"
+
+// ---- coarse slice table: offc[cb][t] = first posting of query-term t whose row >= cb << shift --------
+__global__ void __launch_bounds__(256)
+vb_ms_coarse_kernel(const uint32_t* __restrict__ post_row, const uint32_t* __restrict__ q_plo, const uint32_t* __restrict__ q_phi,
+                    uint32_t n_qterms, uint32_t n_cb /* rows of the table */, uint32_t shift, uint32_t* __restrict__ offc)
+{
+    const uint64_t total = (uint64_t)n_qterms * n_cb;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t cb = (uint32_t)(i / n_qterms), t = (uint32_t)(i % n_qterms);
+        const uint64_t target = (uint64_t)cb << shift;
+        const uint32_t lo = q_plo[t], hi = q_phi[t];
+        offc[i] = target > 0xffffffffull ? hi : vb_ms_lower_bound(post_row, lo, hi, (uint32_t)target);
+    }
+}
+
+struct VbMsPlanArgs {
+    const uint32_t* post_row;
+    const int64_t* q_indptr;     // [B+1]
+    const double* q_weight;      // [n_qterms] term order
+    const double* q_ub;          // [n_qterms]
+    const int32_t* q_hidx;       // [n_qterms] or nullptr
+    const uint32_t* q_plo;       // [n_qterms] full posting range of the term (frequent terms included)
+    const uint32_t* q_phi;
+    const uint8_t* q_ms;         // [B] 1 = query eligible for the MaxScore kernel
+    const float* tau;            // [n_lists]
+    VbMsRec* rec;                // [n_qterms] out, position order
+    VbMsQuery* qinfo;            // [B] out
+    uint32_t* unit_prefix;       // [n_qterms + 1] out: exclusive prefix of the work units per (query, position)
+    uint32_t* counters;          // [0] blocks done (self-resetting), [1] next work unit (reset here), [2] total units
+    uint32_t n_queries, n_qterms;
+    uint32_t seg_row0, seg_row1;
+    uint32_t chunk;              // postings per work unit
+    uint32_t budget_pct;         // MaxScore budget in % of tau (100 = the full MaxScore partition)
+};
+
+__global__ void __launch_bounds__(256)
+vb_ms_plan_kernel(const VbMsPlanArgs a)
+{
+    __shared__ VbMsPlanShared s;
+    __shared__ uint32_t s_pos[VB_MS_MAX_TERMS];
+    __shared__ uint32_t s_last;
+    const uint32_t q = blockIdx.x, j = threadIdx.x;
+    const uint32_t t_lo = (uint32_t)a.q_indptr[q];
+    const uint32_t nt = (uint32_t)a.q_indptr[q + 1] - t_lo;
+    const bool active = nt != 0u && a.q_ms[q] != 0;
+    const double tau_d = (double)a.tau[a.n_queries + q];
+    if (active) {
+        if (j < nt) vb_ms_plan_load(s, j, a.post_row, a.q_plo[t_lo + j], a.q_phi[t_lo + j], a.seg_row0, a.seg_row1, a.q_ub[t_lo + j]);
+        __syncthreads();
+        if (j < nt) vb_ms_plan_partition(s, j, nt, tau_d, a.budget_pct);
+        __syncthreads();
+        uint32_t n_ess = 0, pos = 0;
+        if (j < nt) {
+            pos = vb_ms_plan_position(s, j, nt, n_ess);
+            s_pos[j] = pos;
+            s.ub_pos[pos] = s.ub[j];
+            if (j == 0) s.n_ess = n_ess;
+        }
+        __syncthreads();
+        if (j < nt) {
+            // thread j now finishes POSITION pos (it knows term j's data); the suffix needs every ub_pos
+            VbMsRec r;
+            r.slo = s.slo[j]; r.shi = s.shi[j]; r.w = a.q_weight[t_lo + j];
+            r.suf = vb_ms_plan_suffix(s, pos, nt);
+            r.hidx = a.q_hidx ? a.q_hidx[t_lo + j] : -1;
+            r.j = j;
+            a.rec[t_lo + pos] = r;
+            a.unit_prefix[t_lo + pos] = s.ne[j] ? 0u : (s.len[j] + a.chunk - 1u) / a.chunk;   // counts; scanned below
+        }
+        if (j == 0) { VbMsQuery qi; qi.tau_lo = vb_ms_tau_lo(tau_d); qi.n_ess = s.n_ess; qi.active = 1u; a.qinfo[q] = qi; }
+    } else {
+        for (uint32_t i = j; i < nt; i += blockDim.x) a.unit_prefix[t_lo + i] = 0u;
+        if (j == 0) { VbMsQuery qi; qi.tau_lo = 0.0; qi.n_ess = 0u; qi.active = 0u; a.qinfo[q] = qi; }
+    }
+    // the last CTA to finish turns the per-position unit counts into an exclusive prefix sum
+    __threadfence();
+    __syncthreads();
+    if (j == 0) s_last = atomicAdd(&a.counters[0], 1u) == gridDim.x - 1u ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    __shared__ uint32_t s_scan[256];
+    const uint32_t n = a.n_qterms;
+    const uint32_t per = (n + 255u) / 256u;
+    const uint32_t b0 = j * per, b1 = min(n, b0 + per);
+    uint32_t sum = 0;
+    volatile uint32_t* up = a.unit_prefix;
+    for (uint32_t i = b0; i < b1; ++i) sum += up[i];
+    s_scan[j] = sum;
+    __syncthreads();
+    for (uint32_t o = 1; o < 256u; o <<= 1) {               // inclusive scan of the 256 partial sums
+        const uint32_t v = j >= o ? s_scan[j - o] : 0u;
+        __syncthreads();
+        s_scan[j] += v;
+        __syncthreads();
+    }
+    uint32_t run = j ? s_scan[j - 1u] : 0u;
+    for (uint32_t i = b0; i < b1; ++i) { const uint32_t c = up[i]; up[i] = run; run += c; }
+    if (j == 255u) { up[n] = s_scan[255]; a.counters[2] = s_scan[255]; a.counters[1] = 0u; a.counters[0] = 0u; }
+}
+
+struct VbMsArgs {
+    const uint32_t* post_row;
+    const float* post_val;
+    const float* heavy_vals;
+    uint32_t heavy_stride;
+    const int64_t* sp_indptr;
+    const uint32_t* sp_term;
+    const float* sp_val;
+    const int64_t* q_indptr;
+    const uint32_t* q_term;      // term order
+    const double* q_weight;      // term order
+    const uint32_t* slot_q;      // [n_qterms] query of every term slot
+    const VbMsRec* rec;
+    const VbMsQuery* qinfo;
+    const uint32_t* unit_prefix; // [n_qterms + 1]
+    uint32_t* counters;
+    const uint32_t* offc;        // coarse slice table [n_cb][n_qterms]
+    uint32_t cshift, n_cb;
+    const uint32_t* mask;        // [n_filters][mask_words] or nullptr
+    const int32_t* mask_of;      // [B] or nullptr
+    const float* tau;
+    VbLists lists;
+    uint32_t mask_words, n_qterms, n_queries, row_base, chunk, nt_max;
+};
+
+#define VB_MS_THREADS 128
+#define VB_MS_U 4u               // postings per thread in flight
+
+static size_t vb_ms_smem_bytes(uint32_t nt_max) { return (size_t)nt_max * (8u + 8u + 4u + 4u + 4u) + 16u; }
+
+__global__ void __launch_bounds__(VB_MS_THREADS)
+vb_ms_score_kernel(const VbMsArgs a)
+{
+    extern __shared__ __align__(16) unsigned char vb_ms_smem[];
+    double* s_w = reinterpret_cast<double*>(vb_ms_smem);                 // [nt_max]
+    double* s_suf = s_w + a.nt_max;                                      // [nt_max]
+    int32_t* s_hidx = reinterpret_cast<int32_t*>(s_suf + a.nt_max);      // [nt_max]
+    uint32_t* s_nlo = reinterpret_cast<uint32_t*>(s_hidx + a.nt_max);    // [nt_max]
+    uint32_t* s_nhi = s_nlo + a.nt_max;                                  // [nt_max]
+    __shared__ uint32_t s_unit;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t total = a.unit_prefix[a.n_qterms];
+    const uint32_t sub = blockIdx.x & a.lists.sub_mask;
+    for (;;) {
+        __syncthreads();                                                 // the previous unit's tables are no longer read
+        if (tid == 0) s_unit = atomicAdd(&a.counters[1], 1u);
+        __syncthreads();
+        const uint32_t u = s_unit;
+        if (u >= total) break;
+        // slot = last index with unit_prefix[slot] <= u  (empty slots share their successor's prefix)
+        uint32_t lo = 0, hi = a.n_qterms;
+        while (hi - lo > 1u) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (__ldg(a.unit_prefix + mid) <= u) lo = mid; else hi = mid;
+        }
+        const uint32_t slot = lo;
+        const uint32_t q = __ldg(a.slot_q + slot);
+        const uint32_t t_lo = (uint32_t)__ldg(a.q_indptr + q);
+        const uint32_t nt = (uint32_t)__ldg(a.q_indptr + q + 1) - t_lo;
+        const uint32_t pe = slot - t_lo;
+        const VbMsRec e = a.rec[slot];
+        const uint32_t p0 = e.slo + (u - __ldg(a.unit_prefix + slot)) * a.chunk;
+        const uint32_t p1 = min(e.shi, p0 + a.chunk);
+        const uint32_t r_first = __ldg(a.post_row + p0), r_last = __ldg(a.post_row + p1 - 1u);
+        const uint32_t cb0 = r_first >> a.cshift, cb1 = min((r_last >> a.cshift) + 1u, a.n_cb - 1u);
+        for (uint32_t i = tid; i < nt; i += VB_MS_THREADS) {
+            const VbMsRec r = a.rec[t_lo + i];
+            s_w[i] = r.w; s_suf[i] = r.suf; s_hidx[i] = r.hidx;
+            uint32_t nlo = r.slo, nhi = r.shi;
+            if (r.hidx < 0 && i != pe && nhi > nlo) {
+                nlo = max(nlo, __ldg(a.offc + (size_t)cb0 * a.n_qterms + t_lo + r.j));
+                nhi = min(nhi, __ldg(a.offc + (size_t)cb1 * a.n_qterms + t_lo + r.j));
+                if (nhi < nlo) nhi = nlo;
+            }
+            s_nlo[i] = nlo; s_nhi[i] = nhi;
+        }
+        const VbMsQuery qi = a.qinfo[q];
+        const uint32_t list = a.n_queries + q;
+        VbMsCtx c;
+        c.post_row = a.post_row; c.post_val = a.post_val; c.heavy_vals = a.heavy_vals; c.heavy_stride = a.heavy_stride;
+        c.sp_indptr = a.sp_indptr; c.sp_term = a.sp_term; c.sp_val = a.sp_val;
+        c.q_term = a.q_term + t_lo; c.q_weight = a.q_weight + t_lo;
+        c.mask = nullptr;
+        if (a.mask != nullptr && a.mask_of != nullptr) {
+            const int32_t f = __ldg(a.mask_of + q);
+            if (f >= 0) c.mask = a.mask + (size_t)f * a.mask_words;
+        }
+        c.w = s_w; c.suf = s_suf; c.hidx = s_hidx; c.nlo = s_nlo; c.nhi = s_nhi;
+        c.nt = nt; c.n_ess = qi.n_ess; c.tau_lo = qi.tau_lo;
+        c.delta = (double)(4u * nt) * 1.1102230246251565e-16;
+        c.tau = a.tau[list];
+        __syncthreads();
+        // U postings per thread per step: their (row, value) loads and filter words are issued together
+        for (uint32_t pb = p0 + tid; pb < p1; pb += VB_MS_U * VB_MS_THREADS) {
+            uint32_t row[VB_MS_U];
+            float val[VB_MS_U];
+            uint32_t mw[VB_MS_U];
+#pragma unroll
+            for (uint32_t k = 0; k < VB_MS_U; ++k) {
+                const uint32_t p = pb + k * VB_MS_THREADS;
+                const bool ok = p < p1;
+                row[k] = ok ? __ldg(a.post_row + p) : 0xffffffffu;
+                val[k] = ok ? __ldg(a.post_val + p) : 0.0f;
+            }
+#pragma unroll
+            for (uint32_t k = 0; k < VB_MS_U; ++k)
+                mw[k] = (c.mask != nullptr && row[k] != 0xffffffffu) ? __ldg(c.mask + (row[k] >> 5)) : 0xffffffffu;
+            const uint32_t* keep_mask = c.mask;
+            c.mask = nullptr;                                            // the filter bit is tested here, on the prefetched word
+#pragma unroll
+            for (uint32_t k = 0; k < VB_MS_U; ++k) {
+                if (row[k] == 0xffffffffu || !((mw[k] >> (row[k] & 31u)) & 1u)) continue;
+                float score;
+                if (vb_ms_score_posting(c, pe, row[k], val[k], score))
+                    vb_push_sub(a.lists, list, sub, score, a.row_base + row[k]);
+            }
+            c.mask = keep_mask;
+        }
+    }
+}
+#endif  // __CUDACC__

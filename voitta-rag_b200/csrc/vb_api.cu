@@ -7,6 +7,7 @@
 #include "dense_scan.cuh"
 #include "dense_gemm.cuh"
 #include "sparse.cuh"
+#include "sparse_ms.cuh"
 #include "topk.cuh"
 
 #include <algorithm>
@@ -72,6 +73,9 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct Batch {
     uint32_t B = 0, k = 0, limit = 0, n_lists = 0, n_qterms = 0, nt_max = 1, n_filters = 0, mask_words = 0, n_blocks = 0;
     bool any_sparse = false, use_mask = false, any_heavy = false, begun = false;
+    bool any_ms = false, any_old = false;      // some sparse query goes to the MaxScore kernel / stays on K3
+    uint32_t n_old = 0;                        // sparse queries that stay on K3 in every segment
+    uint32_t n_rows = 0;                       // rows of the index when the batch was staged
     uint32_t seg_ratio = 32;                   // growth factor of the segment schedule for this batch
     std::vector<int32_t> mode, mask_of_host;
     // device pointers into h->args
@@ -84,6 +88,11 @@ struct Batch {
     const uint8_t* d_qrelaxed = nullptr;
     const uint32_t* d_qlo = nullptr;
     const uint32_t* d_qhi = nullptr;
+    const uint32_t* d_qplo = nullptr;          // full posting ranges (frequent terms included): MaxScore kernel
+    const uint32_t* d_qphi = nullptr;
+    const uint32_t* d_slotq = nullptr;         // query of every term slot
+    const uint8_t* d_qms = nullptr;            // [B] 1 = scored by the MaxScore kernel outside the direct segment
+    const uint32_t* d_oldq = nullptr;          // [n_old] the other sparse queries
     const int32_t* d_maskof = nullptr;
     const int32_t* d_mode = nullptr;
     const VbFilterDev* d_filters = nullptr;
@@ -132,11 +141,15 @@ struct vb_index {
 
     // per-search scratch
     DevBuf args, mask, cand, lists, offs, plan, out, q_hat, q_bf16, q_scale, tmp;
+    DevBuf ms_rec, ms_q, ms_units, ms_counters, ms_offc;   // K3M: plan output, work-unit prefix, counters, coarse slice table
     HostBuf h_args_s[2], h_out_s[2], h_stage;
     uint32_t cand_cap = 0;
 
     // options
     int64_t opt_dense_path = 0, opt_seg_first = 2048, opt_seg_ratio = 0 /* 0 = auto */, opt_safe_mode = 0, opt_profile = 0, opt_k2_precision = 0, opt_overlap = 1, opt_k2_tiled = 1, opt_sparse_prune = 20, opt_sparse_prune_force = 0, opt_sparse_dense = 1;
+    int64_t opt_sparse_ms = 1;             // 1: posting-driven MaxScore kernel (K3M) outside the direct segment; 0: K3 everywhere
+    int64_t opt_ms_budget = 100;           // K3M: non-essential ub budget in % of tau (100 = full MaxScore partition)
+    int64_t opt_ms_chunk = 0;              // K3M: postings per work unit (0 = auto)
 
     vb_stats stats{};
     Batch staged_s[2];
@@ -264,6 +277,9 @@ extern "C" int vb_create(int32_t dim, int32_t device, uint64_t capacity_hint, ui
     if (const char* env = getenv("VB200_SPARSE_PRUNE")) h->opt_sparse_prune = atoi(env);
     if (const char* env = getenv("VB200_SPARSE_PRUNE_FORCE")) h->opt_sparse_prune_force = atoi(env);
     if (const char* env = getenv("VB200_SPARSE_DENSE")) h->opt_sparse_dense = atoi(env);
+    if (const char* env = getenv("VB200_SPARSE_MS")) h->opt_sparse_ms = atoi(env);
+    if (const char* env = getenv("VB200_MS_BUDGET")) h->opt_ms_budget = atoi(env);
+    if (const char* env = getenv("VB200_MS_CHUNK")) h->opt_ms_chunk = atoi(env);
     *out = h;
     return 0;
 }
@@ -274,7 +290,8 @@ extern "C" void vb_destroy(vb_index* h) {
     cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->rows, &h->inv_norm, &h->scope_id, &h->created, &h->modified, &h->alive, &h->sp_indptr,
                       &h->sp_term, &h->sp_val, &h->post_row, &h->post_val, &h->heavy_vals, &h->args, &h->mask, &h->cand, &h->lists,
-                      &h->offs, &h->plan, &h->out, &h->q_hat, &h->q_bf16, &h->q_scale, &h->tmp})
+                      &h->offs, &h->plan, &h->out, &h->q_hat, &h->q_bf16, &h->q_scale, &h->tmp,
+                      &h->ms_rec, &h->ms_q, &h->ms_units, &h->ms_counters, &h->ms_offc})
         dev_free(h, *b);
     for (HostBuf* b : {&h->h_args_s[0], &h->h_args_s[1], &h->h_out_s[0], &h->h_out_s[1], &h->h_stage}) if (b->p) cudaFreeHost(b->p);
     for (auto ev : h->prof_events) cudaEventDestroy(ev);
@@ -298,6 +315,9 @@ extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
     else if (k == "slot") h->cur = value ? 1 : 0;                   // which of the two in-flight batches the staged calls address
     else if (k == "overlap") h->opt_overlap = value;               // 1: dense and sparse chains on two streams
     else if (k == "sparse_dense") { h->opt_sparse_dense = value; h->sparse_dirty = true; }   // 0: no dense columns for frequent terms
+    else if (k == "sparse_ms") h->opt_sparse_ms = value;           // 0: K3 in every segment (no MaxScore kernel)
+    else if (k == "ms_budget") h->opt_ms_budget = value;           // K3M non-essential budget in % of tau
+    else if (k == "ms_chunk") h->opt_ms_chunk = value;             // K3M postings per work unit (0 auto)
     else if (k == "sparse_prune_force") h->opt_sparse_prune_force = value;   // 1: prune in every non-direct segment (tests)
     else if (k == "sparse_prune") h->opt_sparse_prune = value;     // MaxScore budget in % of tau (0: score every term's postings)
     else if (k == "k2_tiled") h->opt_k2_tiled = value;             // 0: never use the query-tiled kernel (multi-pass resident kernel instead)
@@ -735,9 +755,9 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     // ---- sparse queries: sort by term id, resolve posting ranges, apply IDF ----
     std::vector<int64_t> indptr(b.B + 1, 0);
     std::vector<double> weight, qub;
-    std::vector<uint32_t> qlo, qhi, qterm;
+    std::vector<uint32_t> qlo, qhi, qterm, qplo, qphi, slotq, oldq;
     std::vector<int32_t> qhidx;
-    std::vector<uint8_t> qrelaxed(b.B, 0);
+    std::vector<uint8_t> qrelaxed(b.B, 0), qms(b.B, 0);
     if (sparse_enabled) {
         if (need_corpus) TRY(ensure_sparse_index(h));
         std::vector<std::pair<uint32_t, double>> tw;
@@ -776,11 +796,19 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
                 qterm.push_back(pr.first);
                 qlo.push_back((uint32_t)plo);
                 qhi.push_back((uint32_t)phi);
+                qplo.push_back((uint32_t)plo);
+                qphi.push_back((uint32_t)phi);
+                slotq.push_back(i);
             }
             // terms routed to their dense column are not walked as postings (empty slice)
             // relaxed mode (order-free sums, dense columns) needs every product >= 0 for its error bound
             const bool relax = all_pos && need_corpus && h->sparse_nonneg && h->opt_sparse_dense;
             qrelaxed[i] = relax ? 1 : 0;
+            // MaxScore kernel: bounds and the order-free sum need every product >= 0 as well
+            const bool ms = all_pos && need_corpus && h->sparse_nonneg && h->opt_sparse_ms && hi > lo;
+            qms[i] = ms ? 1 : 0;
+            if (ms) b.any_ms = true;
+            else if (hi > lo) { b.any_old = true; oldq.push_back(i); }
             for (size_t t = q_first; t < weight.size(); ++t) {
                 if (!relax) qhidx[t] = -1;
                 if (qhidx[t] >= 0) { qlo[t] = qhi[t] = 0; b.any_heavy = true; }
@@ -832,6 +860,11 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     const size_t o_rx = ar.take((size_t)b.B + 8);
     const size_t o_lo = ar.take((size_t)b.n_qterms * 4 + 8);
     const size_t o_hi = ar.take((size_t)b.n_qterms * 4 + 8);
+    const size_t o_plo = ar.take((size_t)b.n_qterms * 4 + 8);
+    const size_t o_phi = ar.take((size_t)b.n_qterms * 4 + 8);
+    const size_t o_sq = ar.take((size_t)b.n_qterms * 4 + 8);
+    const size_t o_ms = ar.take((size_t)b.B + 8);
+    const size_t o_oq = ar.take((size_t)oldq.size() * 4 + 8);
     const size_t o_mo = ar.take((size_t)b.B * 4);
     const size_t o_md = ar.take((size_t)b.B * 4);
     const size_t o_fl = ar.take((size_t)std::max<uint32_t>(1, b.n_filters) * sizeof(VbFilterDev));
@@ -852,7 +885,14 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
         memcpy(hp + o_rx, qrelaxed.data(), (size_t)b.B);
         memcpy(hp + o_lo, qlo.data(), (size_t)b.n_qterms * 4);
         memcpy(hp + o_hi, qhi.data(), (size_t)b.n_qterms * 4);
+        memcpy(hp + o_plo, qplo.data(), (size_t)b.n_qterms * 4);
+        memcpy(hp + o_phi, qphi.data(), (size_t)b.n_qterms * 4);
+        memcpy(hp + o_sq, slotq.data(), (size_t)b.n_qterms * 4);
+        memcpy(hp + o_ms, qms.data(), (size_t)b.B);
+        if (!oldq.empty()) memcpy(hp + o_oq, oldq.data(), oldq.size() * 4);
     }
+    b.n_old = (uint32_t)oldq.size();
+    b.n_rows = (uint32_t)h->n_rows;
     memcpy(hp + o_mo, mask_of.data(), (size_t)b.B * 4);
     memcpy(hp + o_md, b.mode.data(), (size_t)b.B * 4);
     VbFilterDev* hf = reinterpret_cast<VbFilterDev*>(hp + o_fl);
@@ -876,6 +916,11 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     b.d_qrelaxed = reinterpret_cast<const uint8_t*>(dp + o_rx);
     b.d_qlo = reinterpret_cast<const uint32_t*>(dp + o_lo);
     b.d_qhi = reinterpret_cast<const uint32_t*>(dp + o_hi);
+    b.d_qplo = reinterpret_cast<const uint32_t*>(dp + o_plo);
+    b.d_qphi = reinterpret_cast<const uint32_t*>(dp + o_phi);
+    b.d_slotq = reinterpret_cast<const uint32_t*>(dp + o_sq);
+    b.d_qms = reinterpret_cast<const uint8_t*>(dp + o_ms);
+    b.d_oldq = reinterpret_cast<const uint32_t*>(dp + o_oq);
     b.d_maskof = reinterpret_cast<const int32_t*>(dp + o_mo);
     b.d_mode = reinterpret_cast<const int32_t*>(dp + o_md);
     b.d_filters = reinterpret_cast<const VbFilterDev*>(dp + o_fl);
@@ -1051,35 +1096,75 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         prof_end(h, ps, sd);
         return 0;
     };
+    // Which sparse kernel scores which query: the direct segment and the queries whose products may be negative
+    // stay on K3 (block x query CTAs); everything else goes to K3M, the posting-driven MaxScore kernel.
+    const bool ms_on = do_sparse && b.any_ms && h->opt_sparse_ms;
+    const uint32_t ms_chunk = h->opt_ms_chunk > 0 ? (uint32_t)align_up((size_t)h->opt_ms_chunk, VB_MS_U * VB_MS_THREADS)
+                                                   : (b.B <= 4 ? 512u : 2048u);
+    uint32_t ms_shift = 15;                                     // coarse slice table: 2^shift rows per entry, <= 32 MB
+    while ((((uint64_t)(n - 1u) >> ms_shift) + 2u) * (uint64_t)b.n_qterms * 4u > (32ull << 20) && ms_shift < 31u) ++ms_shift;
+    const uint32_t ms_ncb = (uint32_t)(((uint64_t)(n - 1u) >> ms_shift) + 2u);
     auto sparse_segment = [&](uint32_t r0, uint32_t r1, uint32_t direct, bool big) -> int {
         if (do_sparse) {
             const int pi = prof_begin(h, PH_SPARSE | (big ? PH_BIG : 0), ss);
-            // which terms are essential under the thresholds this segment starts with
-            double* d_ubne = h->plan.as<double>();
-            uint8_t* d_ess = reinterpret_cast<uint8_t*>(d_ubne + b.B);
-            // Pruning pays on long segments (measured: -10..-22 % sparse time from 2M rows per segment up, a loss
-            // on cfg2's 1M-row corpus where the per-survivor re-scoring outweighs the skipped postings).
-            const uint32_t nblk_seg = (r1 - r0 + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK;
-            const uint32_t budget = (!direct && (h->opt_sparse_prune_force || nblk_seg >= 1000u)) ? (uint32_t)h->opt_sparse_prune : 0u;
-            if (budget) {                                       // no budget: every term is essential, no plan needed
-                vb_sparse_plan_kernel<<<b.B, 256, 0, ss>>>(b.d_qindptr, b.d_qub, b.tau, b.B, budget, d_ess, d_ubne);
-                CKK("vb_sparse_plan_kernel");
+            const bool use_ms = ms_on && !direct;
+            if (use_ms) {
+                VbMsPlanArgs pa{};
+                pa.post_row = h->post_row.as<uint32_t>(); pa.q_indptr = b.d_qindptr; pa.q_weight = b.d_qweight; pa.q_ub = b.d_qub;
+                pa.q_hidx = b.any_heavy ? b.d_qhidx : nullptr; pa.q_plo = b.d_qplo; pa.q_phi = b.d_qphi; pa.q_ms = b.d_qms; pa.tau = b.tau;
+                pa.rec = h->ms_rec.as<VbMsRec>(); pa.qinfo = h->ms_q.as<VbMsQuery>(); pa.unit_prefix = h->ms_units.as<uint32_t>();
+                pa.counters = h->ms_counters.as<uint32_t>(); pa.n_queries = b.B; pa.n_qterms = b.n_qterms;
+                pa.seg_row0 = r0; pa.seg_row1 = r1; pa.chunk = ms_chunk; pa.budget_pct = (uint32_t)std::max<int64_t>(0, h->opt_ms_budget);
+                vb_ms_plan_kernel<<<b.B, 256, 0, ss>>>(pa);
+                CKK("vb_ms_plan_kernel");
+                VbMsArgs a{};
+                a.post_row = h->post_row.as<uint32_t>(); a.post_val = h->post_val.as<float>();
+                a.heavy_vals = h->heavy_vals.as<float>(); a.heavy_stride = h->heavy_stride;
+                a.sp_indptr = h->sp_indptr.as<int64_t>(); a.sp_term = h->sp_term.as<uint32_t>(); a.sp_val = h->sp_val.as<float>();
+                a.q_indptr = b.d_qindptr; a.q_term = b.d_qterm; a.q_weight = b.d_qweight; a.slot_q = b.d_slotq;
+                a.rec = h->ms_rec.as<VbMsRec>(); a.qinfo = h->ms_q.as<VbMsQuery>(); a.unit_prefix = h->ms_units.as<uint32_t>();
+                a.counters = h->ms_counters.as<uint32_t>(); a.offc = h->ms_offc.as<uint32_t>(); a.cshift = ms_shift; a.n_cb = ms_ncb;
+                a.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; a.mask_of = b.use_mask ? b.d_maskof : nullptr;
+                a.tau = b.tau; a.lists = L; a.mask_words = b.mask_words; a.n_qterms = b.n_qterms; a.n_queries = b.B;
+                a.row_base = (uint32_t)h->row_base; a.chunk = ms_chunk; a.nt_max = b.nt_max;
+                // persistent grid: enough CTAs to fill the machine, never more than the largest possible unit count
+                const uint64_t rows_seg = r1 - r0;
+                const uint64_t max_units = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)h->nnz_live / ms_chunk + b.n_qterms, (uint64_t)b.n_qterms * (rows_seg / ms_chunk + 1)));
+                const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)h->sm_count * 12u, max_units);
+                vb_ms_score_kernel<<<grid, VB_MS_THREADS, vb_ms_smem_bytes(b.nt_max), ss>>>(a);
+                CKK("vb_ms_score_kernel");
+                h->stats.last_launches += 2;
+            }
+            if (!use_ms || b.any_old) {
+                // which terms are essential under the thresholds this segment starts with
+                double* d_ubne = h->plan.as<double>();
+                uint8_t* d_ess = reinterpret_cast<uint8_t*>(d_ubne + b.B);
+                // Pruning pays on long segments (measured: -10..-22 % sparse time from 2M rows per segment up, a loss
+                // on cfg2's 1M-row corpus where the per-survivor re-scoring outweighs the skipped postings).
+                const uint32_t nblk_seg = (r1 - r0 + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK;
+                const uint32_t budget = (!direct && (h->opt_sparse_prune_force || nblk_seg >= 1000u)) ? (uint32_t)h->opt_sparse_prune : 0u;
+                if (budget) {                                       // no budget: every term is essential, no plan needed
+                    vb_sparse_plan_kernel<<<b.B, 256, 0, ss>>>(b.d_qindptr, b.d_qub, b.tau, b.B, budget, d_ess, d_ubne);
+                    CKK("vb_sparse_plan_kernel");
+                    ++h->stats.last_launches;
+                }
+                VbSparseArgs a{};
+                a.post_row = h->post_row.as<uint32_t>(); a.post_val = h->post_val.as<float>(); a.off = h->offs.as<uint32_t>();
+                a.q_indptr = b.d_qindptr; a.q_weight = b.d_qweight; a.q_term = b.d_qterm; a.ess = budget ? d_ess : nullptr; a.ubne = d_ubne;
+                a.sp_indptr = h->sp_indptr.as<int64_t>(); a.sp_term = h->sp_term.as<uint32_t>(); a.sp_val = h->sp_val.as<float>();
+                a.q_hidx = b.any_heavy ? b.d_qhidx : nullptr; a.q_relaxed = b.d_qrelaxed; a.heavy_vals = h->heavy_vals.as<float>(); a.heavy_stride = h->heavy_stride;
+                a.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; a.mask_of = b.use_mask ? b.d_maskof : nullptr;
+                a.tau = b.tau; a.lists = L; a.mask_words = b.mask_words;
+                a.n_qterms = b.n_qterms; a.nt_max = b.nt_max; a.blk_begin = r0 / VB_ROWS_PER_BLOCK; a.n_queries = b.B; a.n_rows = n;
+                a.row_base = (uint32_t)h->row_base; a.direct = direct;
+                uint32_t n_q = b.B;
+                if (use_ms) { a.q_sel = b.d_oldq; a.n_sel = b.n_old; n_q = b.n_old; }   // the MaxScore kernel has the rest
+                { static const char* dbg = getenv("VB200_SPARSE_DEBUG"); a.debug = dbg ? (uint32_t)atoi(dbg) : 0u; }
+                const uint32_t nblk = (r1 - r0 + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK;
+                vb_sparse_kernel<<<nblk * n_q, VB_SPARSE_THREADS, vb_sparse_smem_bytes(b.nt_max), ss>>>(a);
+                CKK("vb_sparse_kernel");
                 ++h->stats.last_launches;
             }
-            VbSparseArgs a{};
-            a.post_row = h->post_row.as<uint32_t>(); a.post_val = h->post_val.as<float>(); a.off = h->offs.as<uint32_t>();
-            a.q_indptr = b.d_qindptr; a.q_weight = b.d_qweight; a.q_term = b.d_qterm; a.ess = budget ? d_ess : nullptr; a.ubne = d_ubne;
-            a.sp_indptr = h->sp_indptr.as<int64_t>(); a.sp_term = h->sp_term.as<uint32_t>(); a.sp_val = h->sp_val.as<float>();
-            a.q_hidx = b.any_heavy ? b.d_qhidx : nullptr; a.q_relaxed = b.d_qrelaxed; a.heavy_vals = h->heavy_vals.as<float>(); a.heavy_stride = h->heavy_stride;
-            a.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; a.mask_of = b.use_mask ? b.d_maskof : nullptr;
-            a.tau = b.tau; a.lists = L; a.mask_words = b.mask_words;
-            a.n_qterms = b.n_qterms; a.nt_max = b.nt_max; a.blk_begin = r0 / VB_ROWS_PER_BLOCK; a.n_queries = b.B; a.n_rows = n;
-            a.row_base = (uint32_t)h->row_base; a.direct = direct;
-            { static const char* dbg = getenv("VB200_SPARSE_DEBUG"); a.debug = dbg ? (uint32_t)atoi(dbg) : 0u; }
-            const uint32_t nblk = (r1 - r0 + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK;
-            vb_sparse_kernel<<<nblk * b.B, VB_SPARSE_THREADS, vb_sparse_smem_bytes(b.nt_max), ss>>>(a);
-            CKK("vb_sparse_kernel");
-            ++h->stats.last_launches;
             prof_end(h, pi, ss);
         }
         // the sparse lists are compacted even without postings (first-segment slots -> empty lists)
@@ -1090,14 +1175,37 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         prof_end(h, ps, ss);
         return 0;
     };
-    if (do_sparse && phase != 2) {                              // sparse slice table (sparse chain)
-        const int pi = prof_begin(h, PH_SPARSE, ss);
-        const uint64_t total = (uint64_t)b.n_qterms * (b.n_blocks + 1);
-        TRY(dev_reserve(h, h->offs, total * 4, false));
+    // fine (2048-row) slice table rows K3 will read: the direct segment only when K3M takes every other segment
+    const bool old_everywhere = do_sparse && (!ms_on || b.any_old);
+    const uint32_t fine_blocks = old_everywhere ? b.n_blocks
+                                                : std::min<uint32_t>(b.n_blocks, (direct_rows + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK);
+    if (do_sparse) {
+        const uint64_t total = (uint64_t)b.n_qterms * (fine_blocks + 1);
+        TRY(dev_reserve(h, h->offs, std::max<uint64_t>(total, 1) * 4, false));
         TRY(dev_reserve(h, h->plan, (size_t)b.B * 8 + b.n_qterms + 64, false));
-        vb_slice_kernel<<<grid_for(total, 256), 256, 0, ss>>>(h->post_row.as<uint32_t>(), b.d_qlo, b.d_qhi, b.n_qterms, b.n_blocks, h->offs.as<uint32_t>());
-        CKK("vb_slice_kernel");
-        ++h->stats.last_launches;
+        if (ms_on) {
+            TRY(dev_reserve(h, h->ms_rec, (size_t)b.n_qterms * sizeof(VbMsRec), false));
+            TRY(dev_reserve(h, h->ms_q, (size_t)b.B * sizeof(VbMsQuery), false));
+            TRY(dev_reserve(h, h->ms_units, ((size_t)b.n_qterms + 1) * 4, false));
+            TRY(dev_reserve(h, h->ms_counters, 64, false));
+            TRY(dev_reserve(h, h->ms_offc, (size_t)ms_ncb * b.n_qterms * 4, false));
+        }
+    }
+    if (do_sparse && phase != 2) {                              // sparse slice tables (sparse chain)
+        const int pi = prof_begin(h, PH_SPARSE, ss);
+        const uint64_t total = (uint64_t)b.n_qterms * (fine_blocks + 1);
+        if (fine_blocks) {
+            vb_slice_kernel<<<grid_for(total, 256), 256, 0, ss>>>(h->post_row.as<uint32_t>(), b.d_qlo, b.d_qhi, b.n_qterms, fine_blocks, h->offs.as<uint32_t>());
+            CKK("vb_slice_kernel");
+            ++h->stats.last_launches;
+        }
+        if (ms_on) {
+            CK(cudaMemsetAsync(h->ms_counters.p, 0, 64, ss));
+            vb_ms_coarse_kernel<<<grid_for((uint64_t)ms_ncb * b.n_qterms, 256), 256, 0, ss>>>(
+                h->post_row.as<uint32_t>(), b.d_qplo, b.d_qphi, b.n_qterms, ms_ncb, ms_shift, h->ms_offc.as<uint32_t>());
+            CKK("vb_ms_coarse_kernel");
+            ++h->stats.last_launches;
+        }
         prof_end(h, pi, ss);
     }
     // enqueue the two chains interleaved so that neither stream starves on the host side
