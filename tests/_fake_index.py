@@ -27,6 +27,9 @@ class FakeIndex:
     def close(self):
         self._cc = None
 
+    def stats(self):
+        return {"n_rows": len(self.dense), "n_live": int(self.alive.sum()), "dim": self.dim, "row_base": 0}
+
     def save(self, path):
         with open(path, "wb") as f:
             np.savez(f, dim=self.dim, dense=self.dense, indptr=self.indptr, terms=self.terms, vals=self.vals,

@@ -9,16 +9,24 @@
 
 extern "C" int ms_emul_segment(
     const uint32_t* post_row, const float* post_val, const float* heavy_vals, uint32_t heavy_stride,
+    const uint32_t* term_tab, const uint32_t* q_tab, const uint8_t* q_shift,
     const int64_t* sp_indptr, const uint32_t* sp_term, const float* sp_val,
     uint32_t nt, const uint32_t* q_term, const double* q_weight, const double* q_ub, const int32_t* q_hidx,
     const uint32_t* q_plo, const uint32_t* q_phi, const uint32_t* mask, float tau,
-    uint32_t seg_row0, uint32_t seg_row1, uint32_t n_rows, uint32_t chunk, uint32_t budget_pct, uint32_t cshift,
+    uint32_t seg_row0, uint32_t seg_row1, uint32_t n_rows, uint32_t chunk, uint32_t budget_pct,
     uint32_t* out_rows, float* out_scores, uint32_t max_out, uint64_t* stats /* [4]: essential postings, units, n_ess, lookups-unused */)
 {
     if (nt == 0 || nt > VB_MS_MAX_TERMS) return -1;
     // ---- plan (vb_ms_plan_kernel) ----
     VbMsPlanShared s;
-    for (uint32_t j = 0; j < nt; ++j) vb_ms_plan_load(s, j, post_row, q_plo[j], q_phi[j], seg_row0, seg_row1, q_ub[j]);
+    for (uint32_t j = 0; j < nt; ++j)
+        vb_ms_plan_load(s, j, post_row, term_tab, q_plo[j], q_phi[j], q_tab[j], q_shift[j], n_rows, seg_row0, seg_row1, q_ub[j]);
+    // the table-assisted segment bounds must equal plain lower bounds
+    for (uint32_t j = 0; j < nt; ++j) {
+        const uint32_t lo = vb_ms_lower_bound(post_row, q_plo[j], q_phi[j], seg_row0);
+        const uint32_t hi = seg_row1 >= n_rows ? q_phi[j] : vb_ms_lower_bound(post_row, q_plo[j], q_phi[j], seg_row1);
+        if (s.slo[j] != lo || s.shi[j] != hi) return -4;
+    }
     for (uint32_t j = 0; j < nt; ++j) vb_ms_plan_partition(s, j, nt, (double)tau, budget_pct);
     std::vector<uint32_t> pos(nt);
     uint32_t n_ess = 0;
@@ -28,7 +36,7 @@ extern "C" int ms_emul_segment(
     for (uint32_t j = 0; j < nt; ++j) {
         VbMsRec r;
         r.slo = s.slo[j]; r.shi = s.shi[j]; r.w = q_weight[j]; r.suf = vb_ms_plan_suffix(s, pos[j], nt);
-        r.hidx = q_hidx ? q_hidx[j] : -1; r.j = j;
+        r.hidx = q_hidx ? q_hidx[j] : -1; r.tab = q_tab[j]; r.shift = q_shift[j]; r.plo = q_plo[j]; r.phi = q_phi[j]; r.pad = 0;
         rec[pos[j]] = r;
         units[pos[j]] = s.ne[j] ? 0u : (s.len[j] + chunk - 1u) / chunk;
     }
@@ -36,18 +44,10 @@ extern "C" int ms_emul_segment(
     const uint32_t total = units[nt];
     // sanity: positions are a permutation
     { std::vector<uint32_t> p(pos); std::sort(p.begin(), p.end()); for (uint32_t i = 0; i < nt; ++i) if (p[i] != i) return -2; }
-    // ---- coarse slice table (vb_ms_coarse_kernel) ----
-    const uint32_t n_cb = (uint32_t)(((uint64_t)(n_rows - 1u) >> cshift) + 2u);
-    std::vector<uint32_t> offc((size_t)n_cb * nt);
-    for (uint32_t cb = 0; cb < n_cb; ++cb)
-        for (uint32_t t = 0; t < nt; ++t) {
-            const uint64_t target = (uint64_t)cb << cshift;
-            offc[(size_t)cb * nt + t] = target > 0xffffffffull ? q_phi[t] : vb_ms_lower_bound(post_row, q_plo[t], q_phi[t], (uint32_t)target);
-        }
     // ---- score (vb_ms_score_kernel) ----
     std::vector<double> w(nt), suf(nt);
     std::vector<int32_t> hidx(nt);
-    std::vector<uint32_t> nlo(nt), nhi(nt);
+    std::vector<uint32_t> tab(nt), shift(nt), plo(nt), phi(nt);
     uint32_t n_out = 0;
     uint64_t ess_post = 0;
     for (uint32_t u = 0; u < total; ++u) {
@@ -58,23 +58,14 @@ extern "C" int ms_emul_segment(
         const uint32_t p0 = e.slo + (u - units[pe]) * chunk;
         const uint32_t p1 = std::min(e.shi, p0 + chunk);
         if (p0 >= p1) return -3;
-        const uint32_t r_first = post_row[p0], r_last = post_row[p1 - 1u];
-        const uint32_t cb0 = r_first >> cshift, cb1 = std::min((r_last >> cshift) + 1u, n_cb - 1u);
         for (uint32_t i = 0; i < nt; ++i) {
             const VbMsRec r = rec[i];
-            w[i] = r.w; suf[i] = r.suf; hidx[i] = r.hidx;
-            uint32_t a = r.slo, b = r.shi;
-            if (r.hidx < 0 && i != pe && b > a) {
-                a = std::max(a, offc[(size_t)cb0 * nt + r.j]);
-                b = std::min(b, offc[(size_t)cb1 * nt + r.j]);
-                if (b < a) b = a;
-            }
-            nlo[i] = a; nhi[i] = b;
+            w[i] = r.w; suf[i] = r.suf; hidx[i] = r.hidx; tab[i] = r.tab; shift[i] = r.shift; plo[i] = r.plo; phi[i] = r.phi;
         }
         VbMsCtx c;
-        c.post_row = post_row; c.post_val = post_val; c.heavy_vals = heavy_vals; c.heavy_stride = heavy_stride;
+        c.post_row = post_row; c.post_val = post_val; c.heavy_vals = heavy_vals; c.heavy_stride = heavy_stride; c.term_tab = term_tab;
         c.sp_indptr = sp_indptr; c.sp_term = sp_term; c.sp_val = sp_val; c.q_term = q_term; c.q_weight = q_weight;
-        c.mask = mask; c.w = w.data(); c.suf = suf.data(); c.hidx = hidx.data(); c.nlo = nlo.data(); c.nhi = nhi.data();
+        c.mask = mask; c.w = w.data(); c.suf = suf.data(); c.hidx = hidx.data(); c.tab = tab.data(); c.shift = shift.data(); c.plo = plo.data(); c.phi = phi.data();
         c.nt = nt; c.n_ess = n_ess; c.tau_lo = vb_ms_tau_lo((double)tau); c.delta = (double)(4u * nt) * 1.1102230246251565e-16; c.tau = tau;
         for (uint32_t p = p0; p < p1; ++p) {
             ++ess_post;

@@ -28,8 +28,8 @@ def emul(tmp_path_factory):
     lib = C.CDLL(str(so))
     vp = C.c_void_p
     lib.ms_emul_segment.restype = C.c_int
-    lib.ms_emul_segment.argtypes = ([vp, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, C.c_float]
-                                    + [C.c_uint32] * 6 + [vp, vp, C.c_uint32, vp])
+    lib.ms_emul_segment.argtypes = ([vp, vp, vp, C.c_uint32, vp, vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, C.c_float]
+                                    + [C.c_uint32] * 5 + [vp, vp, C.c_uint32, vp])
     return lib
 
 
@@ -54,7 +54,23 @@ def index():
     for k, i in enumerate(heavy):
         hv[k, post_row[ptr[i]:ptr[i + 1]]] = post_val[ptr[i]:ptr[i + 1]]
         hof[int(uniq[i])] = k
-    return dict(corpus=corpus, n=n, indptr=indptr, terms=terms, vals=vals, post_row=np.ascontiguousarray(post_row),
+    tab_off, tab_shift, tabs, total = {}, {}, [], 0
+    for i in range(len(uniq)):                       # bucket tables, as ensure_sparse_index builds them
+        d = int(df[i])
+        if d < 32:
+            continue
+        shift = 0
+        while shift < 31 and (d << (shift + 1)) <= n * 4:
+            shift += 1
+        if i in heavy:
+            shift = max(shift, 12)
+        nb = (n >> shift) + 2
+        targets = np.arange(nb, dtype=np.int64) << shift
+        tabs.append((np.searchsorted(post_row[ptr[i]:ptr[i + 1]], targets, side="left") + ptr[i]).astype(np.uint32))
+        tab_off[int(uniq[i])], tab_shift[int(uniq[i])] = total, shift
+        total += nb
+    term_tab = np.concatenate(tabs) if tabs else np.zeros(1, np.uint32)
+    return dict(term_tab=term_tab, tab_off=tab_off, tab_shift=tab_shift, corpus=corpus, n=n, indptr=indptr, terms=terms, vals=vals, post_row=np.ascontiguousarray(post_row),
                 post_val=np.ascontiguousarray(post_val), uniq=uniq, ptr=ptr, df=df, maxval=maxval, hv=hv, stride=stride, hof=hof)
 
 
@@ -70,7 +86,7 @@ def _reference(ix, q_idx, q_w, r0, r1, mask_bits, tau):
     return out
 
 
-def _run(emul, ix, q_idx, q_w, r0, r1, mask_bits, tau, chunk, budget, cshift, use_heavy=True):
+def _run(emul, ix, q_idx, q_w, r0, r1, mask_bits, tau, chunk, budget, use_tabs=True, use_heavy=True):
     nt = len(q_idx)
     qt = np.asarray(q_idx, np.uint32)
     qw = np.asarray(q_w, np.float64)
@@ -80,14 +96,17 @@ def _run(emul, ix, q_idx, q_w, r0, r1, mask_bits, tau, chunk, budget, cshift, us
     phi = np.where(ok, ix["ptr"][np.minimum(slot, len(ix["uniq"]) - 1) + 1], 0).astype(np.uint32)
     ub = np.where(ok, qw * ix["maxval"][np.minimum(slot, len(ix["uniq"]) - 1)].astype(np.float64), 0.0)
     hidx = np.asarray([ix["hof"].get(int(t), -1) if use_heavy else -1 for t in qt], np.int32)
+    qtab = np.asarray([ix["tab_off"].get(int(t), 0xFFFFFFFF) if use_tabs else 0xFFFFFFFF for t in qt], np.uint32)
+    qshift = np.asarray([ix["tab_shift"].get(int(t), 0) for t in qt], np.uint8)
     cap = ix["n"] + 8
     out_rows = np.zeros(cap, np.uint32)
     out_scores = np.zeros(cap, np.float32)
     stats = np.zeros(4, np.uint64)
     p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
-    rc = emul.ms_emul_segment(p(ix["post_row"]), p(ix["post_val"]), p(ix["hv"]), ix["stride"], p(ix["indptr"]), p(ix["terms"]),
+    rc = emul.ms_emul_segment(p(ix["post_row"]), p(ix["post_val"]), p(ix["hv"]), ix["stride"], p(ix["term_tab"]), p(qtab), p(qshift),
+                              p(ix["indptr"]), p(ix["terms"]),
                               p(ix["vals"]), nt, p(qt), p(qw), p(ub), p(hidx), p(plo), p(phi), p(mask_bits), C.c_float(tau),
-                              r0, r1, ix["n"], chunk, budget, cshift, p(out_rows), p(out_scores), cap, p(stats))
+                              r0, r1, ix["n"], chunk, budget, p(out_rows), p(out_scores), cap, p(stats))
     assert rc >= 0, f"emulation failed rc={rc}"
     got = {}
     for r, s in zip(out_rows[:rc], out_scores[:rc]):
@@ -120,8 +139,8 @@ def test_candidates_match_oracle(emul, index, seed, masked):
     for tau in taus:
         for (r0, r1) in ((0, n), (2048, n), (2048, 6144)):
             want = {r: s for r, s in full.items() if r0 <= r < r1 and s > np.float32(tau)}
-            for chunk, budget, cshift, heavy in ((512, 100, 9, True), (2048, 20, 12, True), (512, 100, 15, False)):
-                got, stats = _run(emul, ix, q_idx, w, r0, r1, mask_bits, np.float32(tau), chunk, budget, cshift, heavy)
+            for chunk, budget, tabs, heavy in ((512, 100, True, True), (2048, 20, False, True), (512, 100, True, False)):
+                got, stats = _run(emul, ix, q_idx, w, r0, r1, mask_bits, np.float32(tau), chunk, budget, tabs, heavy)
                 assert got.keys() == want.keys(), (tau, r0, r1, chunk, sorted(set(got) ^ set(want))[:10])
                 bad = [r for r in want if got[r].tobytes() != want[r].tobytes()]
                 assert not bad, f"score bits differ for rows {bad[:5]}"
@@ -137,7 +156,7 @@ def test_pruning_skips_most_postings(emul, index):
         full = _reference(ix, q_idx, w, 0, 2048, None, -np.inf)
         ranked = sorted(full.values(), reverse=True)
         tau = float(ranked[min(len(ranked) - 1, 29)])
-        _, stats = _run(emul, ix, q_idx, w, 2048, n, None, np.float32(tau), 512, 100, 12)
+        _, stats = _run(emul, ix, q_idx, w, 2048, n, None, np.float32(tau), 512, 100)
         dfm = {int(t): int(d) for t, d in zip(ix["uniq"], ix["df"])}
         tot_all += sum(dfm.get(t, 0) for t in q_idx) * (n - 2048) / n
         tot_ess += int(stats[0])
@@ -175,6 +194,6 @@ def test_stress_values(emul, index):
         ranked = sorted(full.values(), reverse=True)
         for tau in (-np.inf, float(ranked[min(len(ranked) - 1, 50)])):
             want = {r: s for r, s in full.items() if s > np.float32(tau)}
-            got, _ = _run(emul, ix, q_idx, w, 0, n, None, np.float32(tau), 512, 100, 10)
+            got, _ = _run(emul, ix, q_idx, w, 0, n, None, np.float32(tau), 512, 100)
             assert got.keys() == want.keys()
             assert all(got[r].tobytes() == want[r].tobytes() for r in want)

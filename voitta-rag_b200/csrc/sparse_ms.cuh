@@ -22,9 +22,12 @@
 //      cannot reach tau; a frequent essential term's postings almost all end here: 8 bytes, one
 //      fma, one compare);
 //   3. ownership: if an EARLIER essential term also occurs in the row, that posting owns the row;
-//   4. the remaining terms are looked up in position order (frequent terms: one load from the
-//      term's dense column; others: binary search in a range narrowed by a coarse slice table),
-//      stopping as soon as partial + suf[i] < tau;
+//   4. the remaining terms are looked up in position order, stopping as soon as partial + suf[i] < tau.
+//      A lookup is one load from the term's dense column (frequent terms) or one 8-byte load from the
+//      term's BUCKET TABLE — built with the index: tab[b] = first posting with row >= b << shift, buckets
+//      sized for ~4 postings — which settles the common "absent" case at once and leaves <= 3 binary
+//      search steps otherwise (the first version searched whole posting ranges: ncu showed the kernel
+//      stalled on those dependent load chains, long_scoreboard 10 of 12 stall cycles per issue);
 //   5. the surviving sum S adds the reference's fp64 products in another order:
 //      |S - S_ref| <= delta*S, delta = 4*nt*2^-53 (all products >= 0).  If float(S(1-delta)) ==
 //      float(S(1+delta)) the fp32 score is provably the reference's; otherwise the row is re-scored
@@ -61,12 +64,16 @@
 #define VB_MS_MAX_TERMS 256u
 
 // One query term in POSITION order (essential terms by ascending posting count, then NE by descending ub).
+#define VB_MS_NO_TAB 0xffffffffu
 struct VbMsRec {
     uint32_t slo, shi;      // the term's postings inside the segment: [slo, shi) of post_row / post_val
     double w;               // idf-scaled query weight
     double suf;             // sum of ub over the positions after this one
     int32_t hidx;           // dense column of a frequent term, -1 = none
-    uint32_t j;             // index of the term inside the query (term-id order): row of the coarse slice table
+    uint32_t tab;           // offset of the term's bucket table in term_tab, VB_MS_NO_TAB = none (short list)
+    uint32_t shift;         // rows per bucket = 1 << shift
+    uint32_t plo, phi;      // the term's whole posting range (lookups of short lists search it directly)
+    uint32_t pad;
 };
 
 struct VbMsQuery {          // per query, written by the plan kernel
@@ -85,16 +92,30 @@ VB_HD uint32_t vb_ms_lower_bound(const uint32_t* post_row, uint32_t lo, uint32_t
     return lo;
 }
 
-// value of a term in `row`: dense column (NaN = absent) or binary search in the narrowed range
+// the postings of a term whose row falls in the bucket of `row`: [lo, hi) from the term's bucket table
+VB_HD void vb_ms_bucket(const uint32_t* term_tab, uint32_t tab, uint32_t shift, uint32_t row, uint32_t& lo, uint32_t& hi) {
+    const uint32_t* t = term_tab + (size_t)tab + (row >> shift);
+    lo = VB_LD(t);
+    hi = VB_LD(t + 1);
+}
+
+// value of a term in `row`: dense column (NaN = absent), bucket table + short search, or (short lists) a
+// search of the whole list [lo0, hi0)
 VB_HD bool vb_ms_lookup(const uint32_t* post_row, const float* post_val, const float* heavy_vals, uint32_t heavy_stride,
-                        int32_t hidx, uint32_t nlo, uint32_t nhi, uint32_t row, float& val) {
+                        const uint32_t* term_tab, int32_t hidx, uint32_t tab, uint32_t shift, uint32_t lo0, uint32_t hi0,
+                        uint32_t row, float& val) {
     if (hidx >= 0) {
         const float v = VB_LD(heavy_vals + (size_t)hidx * heavy_stride + row);
         val = v;
         return v == v;
     }
-    const uint32_t p = vb_ms_lower_bound(post_row, nlo, nhi, row);
-    if (p < nhi && VB_LD(post_row + p) == row) { val = VB_LD(post_val + p); return true; }
+    uint32_t lo = lo0, hi = hi0;
+    if (tab != VB_MS_NO_TAB) {
+        vb_ms_bucket(term_tab, tab, shift, row, lo, hi);
+        if (lo == hi) return false;
+    }
+    const uint32_t p = vb_ms_lower_bound(post_row, lo, hi, row);
+    if (p < hi && VB_LD(post_row + p) == row) { val = VB_LD(post_val + p); return true; }
     return false;
 }
 
@@ -121,6 +142,7 @@ struct VbMsCtx {
     const float* post_val;
     const float* heavy_vals;
     uint32_t heavy_stride;
+    const uint32_t* term_tab;       // bucket tables of the index
     const int64_t* sp_indptr;       // forward index, for the exact re-score
     const uint32_t* sp_term;
     const float* sp_val;
@@ -131,8 +153,10 @@ struct VbMsCtx {
     const double* w;                // [nt]
     const double* suf;              // [nt]
     const int32_t* hidx;            // [nt]
-    const uint32_t* nlo;            // [nt] lookup range per position, narrowed to the unit's row span
-    const uint32_t* nhi;
+    const uint32_t* tab;            // [nt] bucket table offset or VB_MS_NO_TAB
+    const uint32_t* shift;          // [nt]
+    const uint32_t* plo;            // [nt] whole posting range of the term
+    const uint32_t* phi;
     uint32_t nt, n_ess;
     double tau_lo;                  // conservative threshold for the bound tests
     double delta;                   // 4 * nt * 2^-53
@@ -147,10 +171,10 @@ VB_HD bool vb_ms_score_posting(const VbMsCtx& c, uint32_t pe, uint32_t row, floa
     if (partial + c.suf[pe] < c.tau_lo) return false;          // cannot reach tau even with every later term at its maximum
     float lv;
     for (uint32_t i = 0; i < pe; ++i)                            // ownership: an earlier essential term in the row owns it
-        if (vb_ms_lookup(c.post_row, c.post_val, c.heavy_vals, c.heavy_stride, c.hidx[i], c.nlo[i], c.nhi[i], row, lv)) return false;
+        if (vb_ms_lookup(c.post_row, c.post_val, c.heavy_vals, c.heavy_stride, c.term_tab, c.hidx[i], c.tab[i], c.shift[i], c.plo[i], c.phi[i], row, lv)) return false;
     for (uint32_t i = pe + 1u; i < c.nt; ++i) {
         if (partial + c.suf[i - 1u] < c.tau_lo) return false;
-        if (vb_ms_lookup(c.post_row, c.post_val, c.heavy_vals, c.heavy_stride, c.hidx[i], c.nlo[i], c.nhi[i], row, lv))
+        if (vb_ms_lookup(c.post_row, c.post_val, c.heavy_vals, c.heavy_stride, c.term_tab, c.hidx[i], c.tab[i], c.shift[i], c.plo[i], c.phi[i], row, lv))
             partial = VB_DADD(partial, VB_DMUL(c.w[i], (double)lv));
     }
     if (partial < c.tau_lo) return false;
@@ -171,10 +195,19 @@ struct VbMsPlanShared {
 };
 
 // phase 1: segment range and upper bound of term j
-VB_HD void vb_ms_plan_load(VbMsPlanShared& s, uint32_t j, const uint32_t* post_row, uint32_t plo, uint32_t phi,
-                           uint32_t seg_row0, uint32_t seg_row1, double ub) {
-    const uint32_t lo = vb_ms_lower_bound(post_row, plo, phi, seg_row0);
-    const uint32_t hi = vb_ms_lower_bound(post_row, lo, phi, seg_row1);
+// first posting of a term with row >= target: the bucket table leaves a handful of search steps
+VB_HD uint32_t vb_ms_seg_bound(const uint32_t* post_row, const uint32_t* term_tab, uint32_t plo, uint32_t phi,
+                               uint32_t tab, uint32_t shift, uint32_t n_rows, uint32_t target) {
+    if (target >= n_rows) return phi;
+    uint32_t lo = plo, hi = phi;
+    if (tab != VB_MS_NO_TAB) vb_ms_bucket(term_tab, tab, shift, target, lo, hi);
+    return vb_ms_lower_bound(post_row, lo, hi, target);
+}
+
+VB_HD void vb_ms_plan_load(VbMsPlanShared& s, uint32_t j, const uint32_t* post_row, const uint32_t* term_tab, uint32_t plo, uint32_t phi,
+                           uint32_t tab, uint32_t shift, uint32_t n_rows, uint32_t seg_row0, uint32_t seg_row1, double ub) {
+    const uint32_t lo = vb_ms_seg_bound(post_row, term_tab, plo, phi, tab, shift, n_rows, seg_row0);
+    const uint32_t hi = vb_ms_seg_bound(post_row, term_tab, plo, phi, tab, shift, n_rows, seg_row1);
     s.slo[j] = lo; s.shi[j] = hi; s.len[j] = hi - lo; s.ub[j] = ub;
 }
 
@@ -217,22 +250,31 @@ VB_HD double vb_ms_tau_lo(double tau_d) { return tau_d > 0.0 ? tau_d * (1.0 - 1e
 #ifdef __CUDACC__
 #include "common.cuh"
 
-// ---- coarse slice table: offc[cb][t] = first posting of query-term t whose row >= cb << shift --------
+// ---- bucket tables (index build): tab[off_e + b] = first posting of term e whose row >= b << shift_e -------
+struct VbTabTerm { uint32_t start, end, off, shift; };     // posting range, first table entry, bucket shift
+
 __global__ void __launch_bounds__(256)
-vb_ms_coarse_kernel(const uint32_t* __restrict__ post_row, const uint32_t* __restrict__ q_plo, const uint32_t* __restrict__ q_phi,
-                    uint32_t n_qterms, uint32_t n_cb /* rows of the table */, uint32_t shift, uint32_t* __restrict__ offc)
+vb_ms_tab_fill_kernel(const uint32_t* __restrict__ post_row, const VbTabTerm* __restrict__ terms, uint32_t n_terms,
+                      uint64_t total, uint32_t* __restrict__ tab)
 {
-    const uint64_t total = (uint64_t)n_qterms * n_cb;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t cb = (uint32_t)(i / n_qterms), t = (uint32_t)(i % n_qterms);
-        const uint64_t target = (uint64_t)cb << shift;
-        const uint32_t lo = q_plo[t], hi = q_phi[t];
-        offc[i] = target > 0xffffffffull ? hi : vb_ms_lower_bound(post_row, lo, hi, (uint32_t)target);
+        uint32_t lo = 0, hi = n_terms;                       // last term whose table starts at or before entry i
+        while (hi - lo > 1u) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if ((uint64_t)terms[mid].off <= i) lo = mid; else hi = mid;
+        }
+        const VbTabTerm t = terms[lo];
+        const uint64_t target = (i - t.off) << t.shift;
+        tab[i] = target > 0xffffffffull ? t.end : vb_ms_lower_bound(post_row, t.start, t.end, (uint32_t)target);
     }
 }
 
 struct VbMsPlanArgs {
     const uint32_t* post_row;
+    const uint32_t* term_tab;    // bucket tables of the index
+    const uint32_t* q_tab;       // [n_qterms] table offset per query term (VB_MS_NO_TAB = none)
+    const uint8_t* q_shift;      // [n_qterms]
+    uint32_t n_rows;             // rows covered by the inverted index
     const int64_t* q_indptr;     // [B+1]
     const double* q_weight;      // [n_qterms] term order
     const double* q_ub;          // [n_qterms]
@@ -255,7 +297,6 @@ __global__ void __launch_bounds__(256)
 vb_ms_plan_kernel(const VbMsPlanArgs a)
 {
     __shared__ VbMsPlanShared s;
-    __shared__ uint32_t s_pos[VB_MS_MAX_TERMS];
     __shared__ uint32_t s_last;
     const uint32_t q = blockIdx.x, j = threadIdx.x;
     const uint32_t t_lo = (uint32_t)a.q_indptr[q];
@@ -263,14 +304,14 @@ vb_ms_plan_kernel(const VbMsPlanArgs a)
     const bool active = nt != 0u && a.q_ms[q] != 0;
     const double tau_d = (double)a.tau[a.n_queries + q];
     if (active) {
-        if (j < nt) vb_ms_plan_load(s, j, a.post_row, a.q_plo[t_lo + j], a.q_phi[t_lo + j], a.seg_row0, a.seg_row1, a.q_ub[t_lo + j]);
+        if (j < nt) vb_ms_plan_load(s, j, a.post_row, a.term_tab, a.q_plo[t_lo + j], a.q_phi[t_lo + j], a.q_tab[t_lo + j], a.q_shift[t_lo + j],
+                                    a.n_rows, a.seg_row0, a.seg_row1, a.q_ub[t_lo + j]);
         __syncthreads();
         if (j < nt) vb_ms_plan_partition(s, j, nt, tau_d, a.budget_pct);
         __syncthreads();
         uint32_t n_ess = 0, pos = 0;
         if (j < nt) {
             pos = vb_ms_plan_position(s, j, nt, n_ess);
-            s_pos[j] = pos;
             s.ub_pos[pos] = s.ub[j];
             if (j == 0) s.n_ess = n_ess;
         }
@@ -281,7 +322,8 @@ vb_ms_plan_kernel(const VbMsPlanArgs a)
             r.slo = s.slo[j]; r.shi = s.shi[j]; r.w = a.q_weight[t_lo + j];
             r.suf = vb_ms_plan_suffix(s, pos, nt);
             r.hidx = a.q_hidx ? a.q_hidx[t_lo + j] : -1;
-            r.j = j;
+            r.tab = a.q_tab[t_lo + j]; r.shift = a.q_shift[t_lo + j];
+            r.plo = a.q_plo[t_lo + j]; r.phi = a.q_phi[t_lo + j]; r.pad = 0u;
             a.rec[t_lo + pos] = r;
             a.unit_prefix[t_lo + pos] = s.ne[j] ? 0u : (s.len[j] + a.chunk - 1u) / a.chunk;   // counts; scanned below
         }
@@ -333,8 +375,7 @@ struct VbMsArgs {
     const VbMsQuery* qinfo;
     const uint32_t* unit_prefix; // [n_qterms + 1]
     uint32_t* counters;
-    const uint32_t* offc;        // coarse slice table [n_cb][n_qterms]
-    uint32_t cshift, n_cb;
+    const uint32_t* term_tab;    // bucket tables of the index
     const uint32_t* mask;        // [n_filters][mask_words] or nullptr
     const int32_t* mask_of;      // [B] or nullptr
     const float* tau;
@@ -345,7 +386,7 @@ struct VbMsArgs {
 #define VB_MS_THREADS 128
 #define VB_MS_U 4u               // postings per thread in flight
 
-static size_t vb_ms_smem_bytes(uint32_t nt_max) { return (size_t)nt_max * (8u + 8u + 4u + 4u + 4u) + 16u; }
+static size_t vb_ms_smem_bytes(uint32_t nt_max) { return (size_t)nt_max * (8u + 8u + 4u * 5u) + 16u; }
 
 __global__ void __launch_bounds__(VB_MS_THREADS)
 vb_ms_score_kernel(const VbMsArgs a)
@@ -354,12 +395,13 @@ vb_ms_score_kernel(const VbMsArgs a)
     double* s_w = reinterpret_cast<double*>(vb_ms_smem);                 // [nt_max]
     double* s_suf = s_w + a.nt_max;                                      // [nt_max]
     int32_t* s_hidx = reinterpret_cast<int32_t*>(s_suf + a.nt_max);      // [nt_max]
-    uint32_t* s_nlo = reinterpret_cast<uint32_t*>(s_hidx + a.nt_max);    // [nt_max]
-    uint32_t* s_nhi = s_nlo + a.nt_max;                                  // [nt_max]
+    uint32_t* s_tab = reinterpret_cast<uint32_t*>(s_hidx + a.nt_max);    // [nt_max]
+    uint32_t* s_shift = s_tab + a.nt_max;                                // [nt_max]
+    uint32_t* s_plo = s_shift + a.nt_max;                                // [nt_max]
+    uint32_t* s_phi = s_plo + a.nt_max;                                  // [nt_max]
     __shared__ uint32_t s_unit;
     const uint32_t tid = threadIdx.x;
     const uint32_t total = a.unit_prefix[a.n_qterms];
-    const uint32_t sub = blockIdx.x & a.lists.sub_mask;
     for (;;) {
         __syncthreads();                                                 // the previous unit's tables are no longer read
         if (tid == 0) s_unit = atomicAdd(&a.counters[1], 1u);
@@ -380,23 +422,16 @@ vb_ms_score_kernel(const VbMsArgs a)
         const VbMsRec e = a.rec[slot];
         const uint32_t p0 = e.slo + (u - __ldg(a.unit_prefix + slot)) * a.chunk;
         const uint32_t p1 = min(e.shi, p0 + a.chunk);
-        const uint32_t r_first = __ldg(a.post_row + p0), r_last = __ldg(a.post_row + p1 - 1u);
-        const uint32_t cb0 = r_first >> a.cshift, cb1 = min((r_last >> a.cshift) + 1u, a.n_cb - 1u);
         for (uint32_t i = tid; i < nt; i += VB_MS_THREADS) {
             const VbMsRec r = a.rec[t_lo + i];
             s_w[i] = r.w; s_suf[i] = r.suf; s_hidx[i] = r.hidx;
-            uint32_t nlo = r.slo, nhi = r.shi;
-            if (r.hidx < 0 && i != pe && nhi > nlo) {
-                nlo = max(nlo, __ldg(a.offc + (size_t)cb0 * a.n_qterms + t_lo + r.j));
-                nhi = min(nhi, __ldg(a.offc + (size_t)cb1 * a.n_qterms + t_lo + r.j));
-                if (nhi < nlo) nhi = nlo;
-            }
-            s_nlo[i] = nlo; s_nhi[i] = nhi;
+            s_tab[i] = r.tab; s_shift[i] = r.shift; s_plo[i] = r.plo; s_phi[i] = r.phi;
         }
         const VbMsQuery qi = a.qinfo[q];
         const uint32_t list = a.n_queries + q;
         VbMsCtx c;
         c.post_row = a.post_row; c.post_val = a.post_val; c.heavy_vals = a.heavy_vals; c.heavy_stride = a.heavy_stride;
+        c.term_tab = a.term_tab;
         c.sp_indptr = a.sp_indptr; c.sp_term = a.sp_term; c.sp_val = a.sp_val;
         c.q_term = a.q_term + t_lo; c.q_weight = a.q_weight + t_lo;
         c.mask = nullptr;
@@ -404,7 +439,7 @@ vb_ms_score_kernel(const VbMsArgs a)
             const int32_t f = __ldg(a.mask_of + q);
             if (f >= 0) c.mask = a.mask + (size_t)f * a.mask_words;
         }
-        c.w = s_w; c.suf = s_suf; c.hidx = s_hidx; c.nlo = s_nlo; c.nhi = s_nhi;
+        c.w = s_w; c.suf = s_suf; c.hidx = s_hidx; c.tab = s_tab; c.shift = s_shift; c.plo = s_plo; c.phi = s_phi;
         c.nt = nt; c.n_ess = qi.n_ess; c.tau_lo = qi.tau_lo;
         c.delta = (double)(4u * nt) * 1.1102230246251565e-16;
         c.tau = a.tau[list];
@@ -430,8 +465,10 @@ vb_ms_score_kernel(const VbMsArgs a)
             for (uint32_t k = 0; k < VB_MS_U; ++k) {
                 if (row[k] == 0xffffffffu || !((mw[k] >> (row[k] & 31u)) & 1u)) continue;
                 float score;
+                // the append counter is picked by a hash of the row: one query's candidates often come from one or
+                // two work units (= CTAs), and must still spread over all sub-ranges of its list
                 if (vb_ms_score_posting(c, pe, row[k], val[k], score))
-                    vb_push_sub(a.lists, list, sub, score, a.row_base + row[k]);
+                    vb_push_sub(a.lists, list, ((row[k] * 2654435761u) >> 20) & a.lists.sub_mask, score, a.row_base + row[k]);
             }
             c.mask = keep_mask;
         }

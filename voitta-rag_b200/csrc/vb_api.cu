@@ -10,6 +10,8 @@
 #include "sparse_ms.cuh"
 #include "topk.cuh"
 
+#include <unistd.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -76,6 +78,7 @@ struct Batch {
     bool any_ms = false, any_old = false;      // some sparse query goes to the MaxScore kernel / stays on K3
     uint32_t n_old = 0;                        // sparse queries that stay on K3 in every segment
     uint32_t n_rows = 0;                       // rows of the index when the batch was staged
+    uint64_t gen = 0;                          // write generation of the index when the batch was staged
     uint32_t seg_ratio = 32;                   // growth factor of the segment schedule for this batch
     std::vector<int32_t> mode, mask_of_host;
     // device pointers into h->args
@@ -93,6 +96,8 @@ struct Batch {
     const uint32_t* d_slotq = nullptr;         // query of every term slot
     const uint8_t* d_qms = nullptr;            // [B] 1 = scored by the MaxScore kernel outside the direct segment
     const uint32_t* d_oldq = nullptr;          // [n_old] the other sparse queries
+    const uint32_t* d_qtab = nullptr;          // [n_qterms] bucket table offset of the term (VB_MS_NO_TAB = none)
+    const uint8_t* d_qshift = nullptr;         // [n_qterms] bucket shift
     const int32_t* d_maskof = nullptr;
     const int32_t* d_mode = nullptr;
     const VbFilterDev* d_filters = nullptr;
@@ -117,7 +122,7 @@ struct vb_index {
     cudaEvent_t ev0s[2] = {nullptr, nullptr}, ev1s[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int cur = 0;                               // current slot: two batches can be in flight (pipelined callers)
-    std::mutex mu;
+    std::recursive_mutex mu;               // one-call entry points hold it for the whole call; staged calls re-enter
     int sm_count = 148;
     uint64_t device_bytes = 0;
 
@@ -129,19 +134,24 @@ struct vb_index {
 
     // inverted index (device) + host copy of the term directory
     bool sparse_dirty = true;
+    uint64_t write_gen = 0;                // bumped by every upsert / delete: a staged batch must not outlive it
     DevBuf post_row, post_val;
     uint64_t nnz_live = 0;
     std::vector<uint32_t> terms_sorted;
     std::vector<uint64_t> term_ptr;
     std::vector<float> term_maxval;        // largest posting value per term (MaxScore upper bounds)
     std::vector<int32_t> heavy_of_slot;    // term slot -> dense column, -1 = none
+    std::vector<uint32_t> tab_off_of_slot; // term slot -> first entry of its bucket table in term_tab (VB_MS_NO_TAB = none)
+    std::vector<uint8_t> tab_shift_of_slot;
+    DevBuf term_tab;                       // bucket tables: first posting with row >= b << shift, per term (K3M lookups)
+    uint64_t base_rows = 0;                // rows the inverted index was built over
     DevBuf heavy_vals;                     // [n_heavy][heavy_stride] fp32, NaN = term absent from the row
     uint32_t n_heavy = 0, heavy_stride = 0;
     bool sparse_nonneg = false;            // no negative posting value in the shard
 
     // per-search scratch
     DevBuf args, mask, cand, lists, offs, plan, out, q_hat, q_bf16, q_scale, tmp;
-    DevBuf ms_rec, ms_q, ms_units, ms_counters, ms_offc;   // K3M: plan output, work-unit prefix, counters, coarse slice table
+    DevBuf ms_rec, ms_q, ms_units, ms_counters;            // K3M: plan output, work-unit prefix, counters
     HostBuf h_args_s[2], h_out_s[2], h_stage;
     uint32_t cand_cap = 0;
 
@@ -150,6 +160,7 @@ struct vb_index {
     int64_t opt_sparse_ms = 1;             // 1: posting-driven MaxScore kernel (K3M) outside the direct segment; 0: K3 everywhere
     int64_t opt_ms_budget = 100;           // K3M: non-essential ub budget in % of tau (100 = full MaxScore partition)
     int64_t opt_ms_chunk = 0;              // K3M: postings per work unit (0 = auto)
+    int64_t opt_ms_max_terms = 16;         // K3M scores queries of at most this many terms; longer ones accumulate (K3)
 
     vb_stats stats{};
     Batch staged_s[2];
@@ -280,6 +291,7 @@ extern "C" int vb_create(int32_t dim, int32_t device, uint64_t capacity_hint, ui
     if (const char* env = getenv("VB200_SPARSE_MS")) h->opt_sparse_ms = atoi(env);
     if (const char* env = getenv("VB200_MS_BUDGET")) h->opt_ms_budget = atoi(env);
     if (const char* env = getenv("VB200_MS_CHUNK")) h->opt_ms_chunk = atoi(env);
+    if (const char* env = getenv("VB200_MS_MAX_TERMS")) h->opt_ms_max_terms = atoi(env);
     *out = h;
     return 0;
 }
@@ -291,7 +303,7 @@ extern "C" void vb_destroy(vb_index* h) {
     for (DevBuf* b : {&h->rows, &h->inv_norm, &h->scope_id, &h->created, &h->modified, &h->alive, &h->sp_indptr,
                       &h->sp_term, &h->sp_val, &h->post_row, &h->post_val, &h->heavy_vals, &h->args, &h->mask, &h->cand, &h->lists,
                       &h->offs, &h->plan, &h->out, &h->q_hat, &h->q_bf16, &h->q_scale, &h->tmp,
-                      &h->ms_rec, &h->ms_q, &h->ms_units, &h->ms_counters, &h->ms_offc})
+                      &h->ms_rec, &h->ms_q, &h->ms_units, &h->ms_counters, &h->term_tab})
         dev_free(h, *b);
     for (HostBuf* b : {&h->h_args_s[0], &h->h_args_s[1], &h->h_out_s[0], &h->h_out_s[1], &h->h_stage}) if (b->p) cudaFreeHost(b->p);
     for (auto ev : h->prof_events) cudaEventDestroy(ev);
@@ -305,7 +317,7 @@ extern "C" void vb_destroy(vb_index* h) {
 
 extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
     if (!h || !key) return vb_fail("vb_set_option: NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
     std::string k(key);
     if (k == "dense_path") h->opt_dense_path = value;
     else if (k == "seg_first") h->opt_seg_first = std::max<int64_t>(VB_ROWS_PER_BLOCK, (int64_t)align_up((size_t)value, VB_ROWS_PER_BLOCK));
@@ -318,6 +330,7 @@ extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
     else if (k == "sparse_ms") h->opt_sparse_ms = value;           // 0: K3 in every segment (no MaxScore kernel)
     else if (k == "ms_budget") h->opt_ms_budget = value;           // K3M non-essential budget in % of tau
     else if (k == "ms_chunk") h->opt_ms_chunk = value;             // K3M postings per work unit (0 auto)
+    else if (k == "ms_max_terms") h->opt_ms_max_terms = value;     // K3M only for queries of at most this many terms
     else if (k == "sparse_prune_force") h->opt_sparse_prune_force = value;   // 1: prune in every non-direct segment (tests)
     else if (k == "sparse_prune") h->opt_sparse_prune = value;     // MaxScore budget in % of tau (0: score every term's postings)
     else if (k == "k2_tiled") h->opt_k2_tiled = value;             // 0: never use the query-tiled kernel (multi-pass resident kernel instead)
@@ -331,7 +344,7 @@ extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
 
 extern "C" int vb_get_stats(vb_index* h, vb_stats* out) {
     if (!h || !out) return vb_fail("vb_get_stats: NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
     h->stats.n_rows = h->n_rows;
     h->stats.n_live = h->n_live;
     h->stats.nnz = h->nnz;
@@ -392,7 +405,7 @@ extern "C" int vb_upsert(vb_index* h, uint64_t n, const float* dense, const int6
     if (!h) return vb_fail("vb_upsert: NULL index");
     if (n == 0) { if (first_row) *first_row = h->row_base + h->n_rows; return 0; }
     if (!dense) return vb_fail("vb_upsert: dense is NULL");
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
     const uint64_t add_nnz = sp_indptr ? (uint64_t)(sp_indptr[n] - sp_indptr[0]) : 0;
     if (sp_indptr) {
@@ -447,6 +460,7 @@ extern "C" int vb_upsert(vb_index* h, uint64_t n, const float* dense, const int6
     h->n_live += n;
     h->nnz += add_nnz;
     h->sparse_dirty = true;
+    ++h->write_gen;
     if (first_row) *first_row = h->row_base + first;
     return 0;
 }
@@ -457,7 +471,7 @@ extern "C" int vb_upsert_dev(vb_index* h, uint64_t n, const void* rows_bf16, con
     if (!h) return vb_fail("vb_upsert_dev: NULL index");
     if (n == 0) { if (first_row) *first_row = h->row_base + h->n_rows; return 0; }
     if (!rows_bf16) return vb_fail("vb_upsert_dev: rows is NULL");
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
     uint64_t add_nnz = 0;
     int64_t ip0 = 0;
@@ -499,6 +513,7 @@ extern "C" int vb_upsert_dev(vb_index* h, uint64_t n, const void* rows_bf16, con
     h->n_live += n;
     h->nnz += add_nnz;
     h->sparse_dirty = true;
+    ++h->write_gen;
     if (first_row) *first_row = h->row_base + first;
     return 0;
 }
@@ -507,7 +522,7 @@ extern "C" int vb_delete_rows(vb_index* h, uint64_t n, const uint64_t* rows) {
     if (!h) return vb_fail("vb_delete_rows: NULL index");
     if (n == 0) return 0;
     if (!rows) return vb_fail("vb_delete_rows: rows is NULL");
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
     uint64_t killed = 0;
     std::vector<uint32_t> touched;
@@ -524,7 +539,7 @@ extern "C" int vb_delete_rows(vb_index* h, uint64_t n, const uint64_t* rows) {
         CK(cudaMemcpyAsync(h->alive.as<uint32_t>() + w, &h->alive_host[w], 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->n_live -= killed;
-    if (killed) h->sparse_dirty = true;
+    if (killed) { h->sparse_dirty = true; ++h->write_gen; }
     return 0;
 }
 
@@ -537,6 +552,8 @@ static int ensure_sparse_index(vb_index* h) {
     h->term_ptr.assign(1, 0);
     h->term_maxval.clear();
     h->heavy_of_slot.clear();
+    h->tab_off_of_slot.clear();
+    h->tab_shift_of_slot.clear();
     h->n_heavy = 0;
     h->sparse_nonneg = false;
     h->nnz_live = 0;
@@ -648,7 +665,45 @@ static int ensure_sparse_index(vb_index* h) {
             CKC2(cudaStreamSynchronize(h->stream));
         }
     }
+    // Bucket tables for K3M's term lookups: per term with >= 32 postings, tab[b] = first posting whose row >=
+    // b << shift, buckets sized for ~4 postings (frequent terms: 4096-row buckets, used only to find segment
+    // bounds — their lookups read the dense column).  ~1 byte per posting on top of the 8-byte postings.
+    h->tab_off_of_slot.assign(T, VB_MS_NO_TAB);
+    h->tab_shift_of_slot.assign(T, 0);
+    {
+        std::vector<VbTabTerm> tt;
+        uint64_t total = 0;
+        const uint64_t nr = h->n_rows;
+        for (uint32_t sl = 0; sl < T; ++sl) {
+            const uint64_t df = h->term_ptr[sl + 1] - h->term_ptr[sl];
+            if (df < 32) continue;
+            uint32_t shift = 0;
+            while (shift < 31u && (df << (shift + 1)) <= nr * 4) ++shift;       // 2^shift ~ 4 * rows / df
+            if (h->heavy_of_slot[sl] >= 0) shift = std::max(shift, 12u);
+            const uint64_t nb = (nr >> shift) + 2;
+            if (total + nb >= 0xffffffffull) break;                              // table offsets are 32-bit: the rest stay without
+            h->tab_off_of_slot[sl] = (uint32_t)total;
+            h->tab_shift_of_slot[sl] = (uint8_t)shift;
+            tt.push_back(VbTabTerm{(uint32_t)h->term_ptr[sl], (uint32_t)h->term_ptr[sl + 1], (uint32_t)total, shift});
+            total += nb;
+        }
+        if (!tt.empty()) {
+            DevBuf d_tt;
+            rc = dev_reserve(h, h->term_tab, total * 4, false); if (rc) { cleanup2(); return rc; }
+            rc = dev_reserve(h, d_tt, tt.size() * sizeof(VbTabTerm), false); if (rc) { cleanup2(); return rc; }
+            cudaError_t e = cudaMemcpyAsync(d_tt.p, tt.data(), tt.size() * sizeof(VbTabTerm), cudaMemcpyHostToDevice, h->stream);
+            if (e == cudaSuccess) {
+                vb_ms_tab_fill_kernel<<<grid_for(total, 256, 148u * 32u), 256, 0, h->stream>>>(
+                    h->post_row.as<uint32_t>(), d_tt.as<VbTabTerm>(), (uint32_t)tt.size(), total, h->term_tab.as<uint32_t>());
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            dev_free(h, d_tt);
+            if (e != cudaSuccess) { cleanup2(); return vb_fail("bucket table build failed: %s", cudaGetErrorString(e)); }
+        }
+    }
     cleanup2();
+    h->base_rows = h->n_rows;
     h->sparse_dirty = false;
     return 0;
 #undef TRYC
@@ -665,7 +720,7 @@ static int64_t term_slot(const vb_index* h, uint32_t term) {
 
 extern "C" int vb_term_stats(vb_index* h, uint32_t n_terms, const uint32_t* terms, uint64_t* df, uint64_t* n_live) {
     if (!h) return vb_fail("vb_term_stats: NULL index");
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
     TRY(ensure_sparse_index(h));
     for (uint32_t i = 0; i < n_terms; ++i) {
@@ -757,7 +812,8 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     std::vector<double> weight, qub;
     std::vector<uint32_t> qlo, qhi, qterm, qplo, qphi, slotq, oldq;
     std::vector<int32_t> qhidx;
-    std::vector<uint8_t> qrelaxed(b.B, 0), qms(b.B, 0);
+    std::vector<uint8_t> qrelaxed(b.B, 0), qms(b.B, 0), qshift;
+    std::vector<uint32_t> qtab;
     if (sparse_enabled) {
         if (need_corpus) TRY(ensure_sparse_index(h));
         std::vector<std::pair<uint32_t, double>> tw;
@@ -799,13 +855,17 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
                 qplo.push_back((uint32_t)plo);
                 qphi.push_back((uint32_t)phi);
                 slotq.push_back(i);
+                qtab.push_back((need_corpus && slot >= 0 && !h->tab_off_of_slot.empty()) ? h->tab_off_of_slot[slot] : VB_MS_NO_TAB);
+                qshift.push_back((need_corpus && slot >= 0 && !h->tab_shift_of_slot.empty()) ? h->tab_shift_of_slot[slot] : 0);
             }
             // terms routed to their dense column are not walked as postings (empty slice)
             // relaxed mode (order-free sums, dense columns) needs every product >= 0 for its error bound
             const bool relax = all_pos && need_corpus && h->sparse_nonneg && h->opt_sparse_dense;
             qrelaxed[i] = relax ? 1 : 0;
             // MaxScore kernel: bounds and the order-free sum need every product >= 0 as well
-            const bool ms = all_pos && need_corpus && h->sparse_nonneg && h->opt_sparse_ms && hi > lo;
+            // Long queries stay on K3: a row must rule out most of a long query's essential terms one lookup at a
+            // time before MaxScore can drop it, while K3 accumulates all of them without lookups.
+            const bool ms = all_pos && need_corpus && h->sparse_nonneg && h->opt_sparse_ms && hi > lo && hi - lo <= h->opt_ms_max_terms;
             qms[i] = ms ? 1 : 0;
             if (ms) b.any_ms = true;
             else if (hi > lo) { b.any_old = true; oldq.push_back(i); }
@@ -865,6 +925,8 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     const size_t o_sq = ar.take((size_t)b.n_qterms * 4 + 8);
     const size_t o_ms = ar.take((size_t)b.B + 8);
     const size_t o_oq = ar.take((size_t)oldq.size() * 4 + 8);
+    const size_t o_tab = ar.take((size_t)b.n_qterms * 4 + 8);
+    const size_t o_tsh = ar.take((size_t)b.n_qterms + 8);
     const size_t o_mo = ar.take((size_t)b.B * 4);
     const size_t o_md = ar.take((size_t)b.B * 4);
     const size_t o_fl = ar.take((size_t)std::max<uint32_t>(1, b.n_filters) * sizeof(VbFilterDev));
@@ -890,9 +952,12 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
         memcpy(hp + o_sq, slotq.data(), (size_t)b.n_qterms * 4);
         memcpy(hp + o_ms, qms.data(), (size_t)b.B);
         if (!oldq.empty()) memcpy(hp + o_oq, oldq.data(), oldq.size() * 4);
+        memcpy(hp + o_tab, qtab.data(), (size_t)b.n_qterms * 4);
+        memcpy(hp + o_tsh, qshift.data(), (size_t)b.n_qterms);
     }
     b.n_old = (uint32_t)oldq.size();
     b.n_rows = (uint32_t)h->n_rows;
+    b.gen = h->write_gen;
     memcpy(hp + o_mo, mask_of.data(), (size_t)b.B * 4);
     memcpy(hp + o_md, b.mode.data(), (size_t)b.B * 4);
     VbFilterDev* hf = reinterpret_cast<VbFilterDev*>(hp + o_fl);
@@ -921,6 +986,8 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     b.d_slotq = reinterpret_cast<const uint32_t*>(dp + o_sq);
     b.d_qms = reinterpret_cast<const uint8_t*>(dp + o_ms);
     b.d_oldq = reinterpret_cast<const uint32_t*>(dp + o_oq);
+    b.d_qtab = reinterpret_cast<const uint32_t*>(dp + o_tab);
+    b.d_qshift = reinterpret_cast<const uint8_t*>(dp + o_tsh);
     b.d_maskof = reinterpret_cast<const int32_t*>(dp + o_mo);
     b.d_mode = reinterpret_cast<const int32_t*>(dp + o_md);
     b.d_filters = reinterpret_cast<const VbFilterDev*>(dp + o_fl);
@@ -1100,17 +1167,15 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     // stay on K3 (block x query CTAs); everything else goes to K3M, the posting-driven MaxScore kernel.
     const bool ms_on = do_sparse && b.any_ms && h->opt_sparse_ms;
     const uint32_t ms_chunk = h->opt_ms_chunk > 0 ? (uint32_t)align_up((size_t)h->opt_ms_chunk, VB_MS_U * VB_MS_THREADS)
-                                                   : (b.B <= 4 ? 512u : 2048u);
-    uint32_t ms_shift = 15;                                     // coarse slice table: 2^shift rows per entry, <= 32 MB
-    while ((((uint64_t)(n - 1u) >> ms_shift) + 2u) * (uint64_t)b.n_qterms * 4u > (32ull << 20) && ms_shift < 31u) ++ms_shift;
-    const uint32_t ms_ncb = (uint32_t)(((uint64_t)(n - 1u) >> ms_shift) + 2u);
+                                                   : 512u;
     auto sparse_segment = [&](uint32_t r0, uint32_t r1, uint32_t direct, bool big) -> int {
         if (do_sparse) {
             const int pi = prof_begin(h, PH_SPARSE | (big ? PH_BIG : 0), ss);
             const bool use_ms = ms_on && !direct;
             if (use_ms) {
                 VbMsPlanArgs pa{};
-                pa.post_row = h->post_row.as<uint32_t>(); pa.q_indptr = b.d_qindptr; pa.q_weight = b.d_qweight; pa.q_ub = b.d_qub;
+                pa.post_row = h->post_row.as<uint32_t>(); pa.term_tab = h->term_tab.as<uint32_t>(); pa.q_tab = b.d_qtab; pa.q_shift = b.d_qshift;
+                pa.n_rows = (uint32_t)h->base_rows; pa.q_indptr = b.d_qindptr; pa.q_weight = b.d_qweight; pa.q_ub = b.d_qub;
                 pa.q_hidx = b.any_heavy ? b.d_qhidx : nullptr; pa.q_plo = b.d_qplo; pa.q_phi = b.d_qphi; pa.q_ms = b.d_qms; pa.tau = b.tau;
                 pa.rec = h->ms_rec.as<VbMsRec>(); pa.qinfo = h->ms_q.as<VbMsQuery>(); pa.unit_prefix = h->ms_units.as<uint32_t>();
                 pa.counters = h->ms_counters.as<uint32_t>(); pa.n_queries = b.B; pa.n_qterms = b.n_qterms;
@@ -1123,14 +1188,14 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
                 a.sp_indptr = h->sp_indptr.as<int64_t>(); a.sp_term = h->sp_term.as<uint32_t>(); a.sp_val = h->sp_val.as<float>();
                 a.q_indptr = b.d_qindptr; a.q_term = b.d_qterm; a.q_weight = b.d_qweight; a.slot_q = b.d_slotq;
                 a.rec = h->ms_rec.as<VbMsRec>(); a.qinfo = h->ms_q.as<VbMsQuery>(); a.unit_prefix = h->ms_units.as<uint32_t>();
-                a.counters = h->ms_counters.as<uint32_t>(); a.offc = h->ms_offc.as<uint32_t>(); a.cshift = ms_shift; a.n_cb = ms_ncb;
+                a.counters = h->ms_counters.as<uint32_t>(); a.term_tab = h->term_tab.as<uint32_t>();
                 a.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; a.mask_of = b.use_mask ? b.d_maskof : nullptr;
                 a.tau = b.tau; a.lists = L; a.mask_words = b.mask_words; a.n_qterms = b.n_qterms; a.n_queries = b.B;
                 a.row_base = (uint32_t)h->row_base; a.chunk = ms_chunk; a.nt_max = b.nt_max;
                 // persistent grid: enough CTAs to fill the machine, never more than the largest possible unit count
                 const uint64_t rows_seg = r1 - r0;
                 const uint64_t max_units = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)h->nnz_live / ms_chunk + b.n_qterms, (uint64_t)b.n_qterms * (rows_seg / ms_chunk + 1)));
-                const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)h->sm_count * 12u, max_units);
+                const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)h->sm_count * 16u, max_units);
                 vb_ms_score_kernel<<<grid, VB_MS_THREADS, vb_ms_smem_bytes(b.nt_max), ss>>>(a);
                 CKK("vb_ms_score_kernel");
                 h->stats.last_launches += 2;
@@ -1188,7 +1253,6 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
             TRY(dev_reserve(h, h->ms_q, (size_t)b.B * sizeof(VbMsQuery), false));
             TRY(dev_reserve(h, h->ms_units, ((size_t)b.n_qterms + 1) * 4, false));
             TRY(dev_reserve(h, h->ms_counters, 64, false));
-            TRY(dev_reserve(h, h->ms_offc, (size_t)ms_ncb * b.n_qterms * 4, false));
         }
     }
     if (do_sparse && phase != 2) {                              // sparse slice tables (sparse chain)
@@ -1199,13 +1263,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
             CKK("vb_slice_kernel");
             ++h->stats.last_launches;
         }
-        if (ms_on) {
-            CK(cudaMemsetAsync(h->ms_counters.p, 0, 64, ss));
-            vb_ms_coarse_kernel<<<grid_for((uint64_t)ms_ncb * b.n_qterms, 256), 256, 0, ss>>>(
-                h->post_row.as<uint32_t>(), b.d_qplo, b.d_qphi, b.n_qterms, ms_ncb, ms_shift, h->ms_offc.as<uint32_t>());
-            CKK("vb_ms_coarse_kernel");
-            ++h->stats.last_launches;
-        }
+        if (ms_on) CK(cudaMemsetAsync(h->ms_counters.p, 0, 64, ss));
         prof_end(h, pi, ss);
     }
     // enqueue the two chains interleaved so that neither stream starves on the host side
@@ -1326,7 +1384,7 @@ static bool wants_branches(const vb_result* out) {
 extern "C" int vb_stage(vb_index* h, const vb_query_batch* q, int32_t want_branches, int32_t need_corpus) {
     if (!h) return vb_fail("vb_stage: NULL index");
     TRY(validate_batch(h, q));
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
     h->staged_s[h->cur].valid = false;
     TRY(prepare_batch(h, q, h->staged_s[h->cur], need_corpus != 0));
@@ -1347,9 +1405,10 @@ __global__ void vb_tau_import_kernel(float* __restrict__ tau, const float* __res
 
 extern "C" int vb_run_local_begin(vb_index* h) {
     if (!h) return vb_fail("vb_run_local_begin: NULL index");
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
     Batch& b = h->staged_s[h->cur];
     if (!b.valid) return vb_fail("vb_run_local_begin: no staged batch");
+    if (b.need_corpus && b.n_rows != (uint32_t)h->n_rows) return vb_fail("vb_run_local_begin: the index changed since vb_stage; stage the batch again");
     CK(cudaSetDevice(h->device));
     h->stats.last_launches = 0;
     CK(cudaEventRecord(h->ev0s[h->cur], h->stream));
@@ -1361,7 +1420,7 @@ extern "C" int vb_run_local_begin(vb_index* h) {
 
 extern "C" int vb_tau_export(vb_index* h, float* tau_dev) {
     if (!h || !tau_dev) return vb_fail("vb_tau_export: NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
     const Batch& b = h->staged_s[h->cur];
     if (!b.valid || !b.begun) return vb_fail("vb_tau_export: call vb_run_local_begin first");
     CK(cudaSetDevice(h->device));
@@ -1371,7 +1430,7 @@ extern "C" int vb_tau_export(vb_index* h, float* tau_dev) {
 
 extern "C" int vb_tau_import(vb_index* h, const float* tau_dev) {
     if (!h || !tau_dev) return vb_fail("vb_tau_import: NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
     const Batch& b = h->staged_s[h->cur];
     if (!b.valid || !b.begun) return vb_fail("vb_tau_import: call vb_run_local_begin first");
     CK(cudaSetDevice(h->device));
@@ -1383,8 +1442,10 @@ extern "C" int vb_tau_import(vb_index* h, const float* tau_dev) {
 
 extern "C" int vb_run_local(vb_index* h, uint64_t* cand_dev) {
     if (!h) return vb_fail("vb_run_local: NULL index");
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
     if (!h->staged_s[h->cur].valid) return vb_fail("vb_run_local: no staged batch");
+    if (h->staged_s[h->cur].need_corpus && (h->staged_s[h->cur].n_rows != (uint32_t)h->n_rows || h->staged_s[h->cur].gen != h->write_gen))
+        return vb_fail("vb_run_local: the index changed since vb_stage; stage the batch again");
     CK(cudaSetDevice(h->device));
     if (h->staged_s[h->cur].begun) {                            // first segment done by vb_run_local_begin
         h->staged_s[h->cur].begun = false;
@@ -1408,7 +1469,7 @@ extern "C" int vb_run_local(vb_index* h, uint64_t* cand_dev) {
 
 extern "C" int vb_run_fuse(vb_index* h, uint32_t n_shards, const uint64_t* gathered_dev) {
     if (!h) return vb_fail("vb_run_fuse: NULL index");
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
     Batch& b = h->staged_s[h->cur];
     if (!b.valid) return vb_fail("vb_run_fuse: no staged batch");
     CK(cudaSetDevice(h->device));
@@ -1428,7 +1489,7 @@ extern "C" int vb_run_fuse(vb_index* h, uint32_t n_shards, const uint64_t* gathe
 
 extern "C" int vb_fetch(vb_index* h, vb_result* out, int32_t* overflowed) {
     if (!h) return vb_fail("vb_fetch: NULL index");
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
     if (!h->staged_s[h->cur].valid) return vb_fail("vb_fetch: no staged batch");
     CK(cudaSetDevice(h->device));
     int ovf = 0;
@@ -1442,6 +1503,7 @@ extern "C" int vb_fetch(vb_index* h, vb_result* out, int32_t* overflowed) {
 extern "C" int vb_search(vb_index* h, const vb_query_batch* q, vb_result* out) {
     if (!h || !out) return vb_fail("vb_search: NULL argument");
     TRY(validate_batch(h, q));
+    std::lock_guard<std::recursive_mutex> lk(h->mu);      // stage + run + fuse + fetch are one critical section
     if (h->n_rows == 0) { zero_result(q, out); return 0; }
     for (int attempt = 0; attempt < 2; ++attempt) {
         TRY(vb_stage(h, q, wants_branches(out), 1));
@@ -1463,6 +1525,7 @@ extern "C" int vb_search_local(vb_index* h, const vb_query_batch* q, uint64_t* c
     if (!h || !cand_dev) return vb_fail("vb_search_local: NULL argument");
     TRY(validate_batch(h, q));
     if (q->apply_idf) return vb_fail("vb_search_local: weights must carry the global IDF (apply_idf = 0)");
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
     for (int attempt = 0; attempt < 2; ++attempt) {
         TRY(vb_stage(h, q, 0, 1));
         h->staged_safe = attempt == 1;
@@ -1487,6 +1550,7 @@ extern "C" int vb_search_local(vb_index* h, const vb_query_batch* q, uint64_t* c
 extern "C" int vb_merge_fuse(vb_index* h, const vb_query_batch* q, uint32_t n_shards, const uint64_t* gathered_dev, vb_result* out) {
     if (!h || !gathered_dev || !out) return vb_fail("vb_merge_fuse: NULL argument");
     TRY(validate_batch(h, q));
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
     TRY(vb_stage(h, q, wants_branches(out), 0));
     CK(cudaEventRecord(h->ev0s[h->cur], h->stream));
     h->stats.last_launches = 0;
@@ -1518,21 +1582,27 @@ static int snap_write_dev(vb_index* h, FILE* f, const void* dev, size_t bytes) {
     }
     return 0;
 }
-static int snap_read_dev(vb_index* h, FILE* f, void* dev, size_t bytes) {
+template <class Check>
+static int snap_read_dev(vb_index* h, FILE* f, void* dev, size_t bytes, Check check) {
     const size_t chunk = 32u << 20;
     TRY(host_reserve(h->h_stage, std::min(bytes, chunk)));
     for (size_t o = 0; o < bytes; o += chunk) {
         const size_t m = std::min(chunk, bytes - o);
         if (fread(h->h_stage.p, 1, m, f) != m) return vb_fail("vb_load: snapshot truncated");
+        check(h->h_stage.p, m);
         CK(cudaMemcpyAsync(static_cast<char*>(dev) + o, h->h_stage.p, m, cudaMemcpyHostToDevice, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
     return 0;
 }
 
+static int snap_read_dev(vb_index* h, FILE* f, void* dev, size_t bytes) {
+    return snap_read_dev(h, f, dev, bytes, [](const void*, size_t) {});
+}
+
 extern "C" int vb_save(vb_index* h, const char* path) {
     if (!h || !path) return vb_fail("vb_save: NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     FILE* f = fopen(path, "wb");
@@ -1555,6 +1625,8 @@ extern "C" int vb_save(vb_index* h, const char* path) {
         if (!rc && h->nnz) rc = snap_write_dev(h, f, h->sp_term.p, h->nnz * 4);
         if (!rc && h->nnz) rc = snap_write_dev(h, f, h->sp_val.p, h->nnz * 4);
     }
+    // the caller renames the file into place afterwards: the data must be on disk first
+    if (!rc && (fflush(f) != 0 || fsync(fileno(f)) != 0)) rc = vb_fail("vb_save: flush/fsync failed");
     if (fclose(f) != 0 && !rc) rc = vb_fail("vb_save: close failed");
     return rc;
 }
@@ -1569,6 +1641,24 @@ extern "C" int vb_load(const char* path, int32_t device, vb_index** out) {
         fclose(f);
         return vb_fail("vb_load: '%s' is not a version-1 snapshot", path);
     }
+    // the header must describe exactly this file: nothing below trusts a count it has not checked
+    {
+        const uint64_t n = hd.n_rows, words = (n + 31) / 32;
+        if (hd.dim == 0 || hd.dim > 4096 || hd.d_pad != (hd.dim + 63) / 64 * 64 || hd.n_live > n || hd.nnz >= (1ull << 40) ||
+            n + hd.row_base > 0xffffffffull) {
+            fclose(f);
+            return vb_fail("vb_load: '%s' has an implausible header", path);
+        }
+        uint64_t want = sizeof hd;
+        if (n) want += n * hd.d_pad * 2 + n * 4 + n * 4 + n * 8 + n * 8 + words * 4 + (n + 1) * 8 + hd.nnz * 8;
+        if (fseek(f, 0, SEEK_END) != 0) { fclose(f); return vb_fail("vb_load: cannot seek in '%s'", path); }
+        const long long have = ftell(f);
+        if (have < 0 || (uint64_t)have != want) {
+            fclose(f);
+            return vb_fail("vb_load: '%s' is %lld bytes, its header describes %llu", path, have, (unsigned long long)want);
+        }
+        if (fseek(f, (long)sizeof hd, SEEK_SET) != 0) { fclose(f); return vb_fail("vb_load: cannot seek in '%s'", path); }
+    }
     vb_index* h = nullptr;
     int rc = vb_create((int32_t)hd.dim, device, hd.n_rows, hd.row_base, &h);
     if (rc) { fclose(f); return rc; }
@@ -1576,7 +1666,7 @@ extern "C" int vb_load(const char* path, int32_t device, vb_index** out) {
         if ((uint32_t)h->d_pad != hd.d_pad) return vb_fail("vb_load: snapshot row pitch %u != %d", hd.d_pad, h->d_pad);
         const uint64_t n = hd.n_rows, words = (n + 31) / 32;
         if (n == 0) return 0;
-        std::lock_guard<std::mutex> lk(h->mu);
+        std::lock_guard<std::recursive_mutex> lk(h->mu);
         TRY(reserve_rows(h, n, hd.nnz));
         TRY(snap_read_dev(h, f, h->rows.p, n * h->d_pad * 2));
         TRY(snap_read_dev(h, f, h->inv_norm.p, n * 4));
@@ -1584,8 +1674,25 @@ extern "C" int vb_load(const char* path, int32_t device, vb_index** out) {
         TRY(snap_read_dev(h, f, h->created.p, n * 8));
         TRY(snap_read_dev(h, f, h->modified.p, n * 8));
         if (fread(h->alive_host.data(), 4, words, f) != words) return vb_fail("vb_load: snapshot truncated");
+        // bits past n_rows never count; n_live is recomputed from the bitmap, not taken from the header
+        if (n & 31u) h->alive_host[words - 1] &= (1u << (n & 31u)) - 1u;
+        uint64_t live = 0;
+        for (uint64_t w = 0; w < words; ++w) live += (uint64_t)__builtin_popcount(h->alive_host[w]);
+        if (live != hd.n_live) return vb_fail("vb_load: header says %llu live rows, the bitmap holds %llu", (unsigned long long)hd.n_live, (unsigned long long)live);
         CK(cudaMemcpyAsync(h->alive.p, h->alive_host.data(), words * 4, cudaMemcpyHostToDevice, h->stream));
-        TRY(snap_read_dev(h, f, h->sp_indptr.p, (n + 1) * 8));
+        {   // forward index offsets: monotone, starting at 0, ending at nnz (checked on their way through the staging buffer)
+            int64_t prev = 0;
+            bool first = true, ok = true;
+            TRY(snap_read_dev(h, f, h->sp_indptr.p, (n + 1) * 8, [&](const void* p, size_t bytes) {
+                const int64_t* v = static_cast<const int64_t*>(p);
+                for (size_t i = 0; i < bytes / 8; ++i) {
+                    if (first) { ok = ok && v[i] == 0; first = false; }
+                    ok = ok && v[i] >= prev;
+                    prev = v[i];
+                }
+            }));
+            if (!ok || prev != (int64_t)hd.nnz) return vb_fail("vb_load: corrupt sparse offsets (not monotone from 0 to nnz)");
+        }
         if (hd.nnz) { TRY(snap_read_dev(h, f, h->sp_term.p, hd.nnz * 4)); TRY(snap_read_dev(h, f, h->sp_val.p, hd.nnz * 4)); }
         CK(cudaStreamSynchronize(h->stream));
         h->n_rows = n; h->n_live = hd.n_live; h->nnz = hd.nnz;

@@ -19,11 +19,13 @@ Additive API (not in the reference): ``search_batch`` and the ``fusion`` switch
 """
 from __future__ import annotations
 
+import atexit
+import json
 import logging
 import os
-import pickle
 from pathlib import Path
 import threading
+import time
 import uuid
 from dataclasses import dataclass
 
@@ -81,6 +83,10 @@ class _Settings:
         self.fusion = os.getenv("VOITTA_FUSION", "weighted")
         # directory of a snapshot to restore on first use (stands in for Qdrant's storage volume)
         self.snapshot_dir = os.getenv("VOITTA_B200_SNAPSHOT_DIR") or None
+        # seconds between automatic snapshots after writes (unset = only save_snapshot() and the exit hook; the
+        # reference persists every write through Qdrant, here a restart restores the last snapshot)
+        a = os.getenv("VOITTA_B200_AUTOSAVE_SECS")
+        self.autosave_secs = float(a) if a not in (None, "") else None
 
 
 def get_settings() -> _Settings:
@@ -131,6 +137,8 @@ class _Collection:
         self.by_url: dict[str, set[int]] = {}
         self.scopes: dict[tuple[str, str], int] = {}   # (folder_path, index_folder) -> scope id
         self.scope_list: list[tuple[str, str]] = []
+        self.dirty = False                     # written since the last snapshot
+        self.last_save = time.monotonic()
 
     @property
     def index(self):
@@ -154,7 +162,9 @@ class _Collection:
             m.setdefault(key, set()).add(row)
 
     def add_rows(self, first_row: int, ids: list[str], payloads: list[dict]):
-        assert first_row == len(self.ids)
+        if first_row != len(self.ids):
+            raise RuntimeError(f"collection '{self.name}': device index has {first_row} rows, host maps {len(self.ids)} "
+                               "(an earlier write failed half-way); reload the collection from its snapshot")
         for i, (pid, p) in enumerate(zip(ids, payloads)):
             r = first_row + i
             self.ids.append(pid)
@@ -182,43 +192,103 @@ class _Collection:
     def live_rows(self):
         return (r for r, p in enumerate(self.payload) if p is not None)
 
-    # ---- snapshot: <dir>/<name>.vb200 (device data, vb_save) + <dir>/<name>.host.pkl (ids, payloads) ----
-    def snapshot_paths(self, directory):
+    # ---- snapshot ---------------------------------------------------------------------------------
+    # <dir>/<name>.<generation>.vb200   device data (vb_save)
+    # <dir>/<name>.host.json            ids, payloads, scope dictionary + the generation it belongs to
+    # The JSON file is the commit record: it is written last, to a temporary name, fsynced and renamed, and it
+    # names the device file of the same generation — a crash at any point leaves the previous pair intact.
+    # JSON, not pickle: the directory comes from the environment and must not be able to run code on load.
+    def snapshot_paths(self, directory, generation: str | None = None):
         d = Path(directory)
-        return d / f"{self.name}.vb200", d / f"{self.name}.host.pkl"
+        host = d / f"{self.name}.host.json"
+        if generation is None and host.exists():
+            try:
+                with open(host, "r", encoding="utf-8") as f:
+                    head = f.read(4096)
+                generation = json.loads(head[:head.index(', "ids"')] + "}").get("generation")
+            except Exception:
+                generation = None
+        return d / f"{self.name}.{generation or 'none'}.vb200", host
 
     def save(self, directory) -> dict:
-        dev_path, host_path = self.snapshot_paths(directory)
-        Path(directory).mkdir(parents=True, exist_ok=True)
+        d = Path(directory)
+        d.mkdir(parents=True, exist_ok=True)
+        generation = uuid.uuid4().hex
+        dev_path, host_path = self.snapshot_paths(d, generation)
+        dev_tmp, host_tmp = dev_path.with_suffix(".vb200.tmp"), host_path.with_suffix(".json.tmp")
         with self.lock:
-            self.index.save(dev_path)
-            with open(host_path, "wb") as f:
-                pickle.dump({"version": 1, "name": self.name, "dim": self.dim, "ids": self.ids,
-                             "payload": self.payload, "scope_list": self.scope_list}, f, protocol=pickle.HIGHEST_PROTOCOL)
-        return {"rows": len(self.ids), "live": self.n_live, "device_file": str(dev_path), "host_file": str(host_path)}
+            self.index.save(dev_tmp)                       # vb_save flushes and fsyncs before it returns
+            os.replace(dev_tmp, dev_path)
+            head = {"version": 2, "name": self.name, "dim": self.dim, "generation": generation,
+                    "device_file": dev_path.name, "n_rows": len(self.ids), "n_live": self.n_live}
+            with open(host_tmp, "w", encoding="utf-8") as f:
+                # the small header keys come first so that snapshot_paths can read them without parsing the payloads
+                f.write(json.dumps(head)[:-1] + ', "ids": ')
+                json.dump(self.ids, f)
+                f.write(', "scope_list": ')
+                json.dump([list(k) for k in self.scope_list], f)
+                f.write(', "payload": ')
+                json.dump(self.payload, f)
+                f.write("}")
+                f.flush()
+                os.fsync(f.fileno())
+            os.replace(host_tmp, host_path)
+            try:
+                dfd = os.open(d, os.O_RDONLY)
+                try:
+                    os.fsync(dfd)
+                finally:
+                    os.close(dfd)
+            except OSError:
+                pass
+            for old in d.glob(f"{self.name}.*.vb200"):     # device files of earlier generations
+                if old != dev_path:
+                    try:
+                        old.unlink()
+                    except OSError:
+                        pass
+            self.last_save = time.monotonic()
+            self.dirty = False
+        return {"rows": len(self.ids), "live": self.n_live, "device_file": str(dev_path), "host_file": str(host_path),
+                "generation": generation}
 
     def load(self, directory, index_loader=None) -> int:
         """Replace this collection's contents with a snapshot.  Returns the number of live points."""
-        dev_path, host_path = self.snapshot_paths(directory)
-        with open(host_path, "rb") as f:
-            st = pickle.load(f)
-        if st.get("version") != 1 or st["dim"] != self.dim:
+        d = Path(directory)
+        _, host_path = self.snapshot_paths(d, "x")
+        with open(host_path, "r", encoding="utf-8") as f:
+            st = json.load(f)
+        if st.get("version") != 2 or st.get("dim") != self.dim or st.get("name") != self.name:
             raise ValueError(f"snapshot {host_path} does not match collection '{self.name}' (dim {self.dim})")
+        ids, payload = st["ids"], st["payload"]
+        n_live = sum(1 for p in payload if p is not None)
+        if len(ids) != len(payload) or len(ids) != st["n_rows"] or n_live != st["n_live"]:
+            raise ValueError(f"snapshot {host_path} is inconsistent (ids {len(ids)}, payloads {len(payload)}, "
+                             f"header rows {st['n_rows']} live {st['n_live']} / counted {n_live})")
+        dev_path = d / st["device_file"]
+        if Path(st["device_file"]).name != st["device_file"] or not dev_path.exists():
+            raise ValueError(f"snapshot {host_path}: device file {st['device_file']} of generation {st.get('generation')} is missing")
         loader = index_loader or (lambda path: engine.Index.load(path, device=self.device))
         with self.lock:
             new_index = loader(dev_path)
+            try:
+                ist = new_index.stats()
+                if int(ist["n_rows"]) != len(ids) or int(ist["n_live"]) != n_live or int(ist.get("dim", self.dim)) != self.dim:
+                    raise ValueError(f"snapshot {host_path}: device file holds {ist['n_rows']} rows / {ist['n_live']} live "
+                                     f"(dim {ist.get('dim')}), host file {len(ids)} / {n_live} (dim {self.dim})")
+            except Exception:
+                new_index.close()
+                raise
             if self._index is not None:
                 self._index.close()
             self._index = new_index
-            self.ids, self.payload = [], []
+            self.ids = [str(x) for x in ids]
+            self.payload = [None] * len(self.ids)
             self.n_live = 0
             self.by_file, self.by_folder, self.by_index_folder, self.by_url = {}, {}, {}, {}
             self.scope_list = [tuple(k) for k in st["scope_list"]]
             self.scopes = {k: i for i, k in enumerate(self.scope_list)}
-            live = [(r, p) for r, p in enumerate(st["payload"])]
-            self.ids = list(st["ids"])
-            self.payload = [None] * len(self.ids)
-            for r, pl in live:
+            for r, pl in enumerate(payload):
                 if pl is None:
                     continue
                 self.payload[r] = pl
@@ -227,7 +297,16 @@ class _Collection:
                 self._map_add(self.by_index_folder, pl["index_folder"], r)
                 self._map_add(self.by_url, pl.get("source_url"), r)
                 self.n_live += 1
+            self.dirty = False
+            self.last_save = time.monotonic()
             return self.n_live
+
+    def wrote(self):
+        """Called after every write (under the lock): autosave if VOITTA_B200_AUTOSAVE_SECS has elapsed."""
+        self.dirty = True
+        st = get_settings()
+        if st.snapshot_dir and st.autosave_secs is not None and time.monotonic() - self.last_save >= st.autosave_secs:
+            self.save(st.snapshot_dir)
 
 
 _collections: dict[str, _Collection] = {}
@@ -243,10 +322,37 @@ def _get_collection(name: str, dim: int, device: int, index_factory=None) -> _Co
             if snap and index_factory is None and all(p.exists() for p in c.snapshot_paths(snap)):
                 logger.info(f"Restoring collection '{name}' from {snap}")
                 c.load(snap)
+            if snap and index_factory is None:
+                _register_exit_save()
             _collections[name] = c
         elif c.dim != dim:
             raise ValueError(f"collection '{name}' exists with dimension {c.dim}, requested {dim}")
         return c
+
+
+_exit_hook = False
+
+
+def _register_exit_save() -> None:
+    """Save every collection written since its last snapshot when the process exits (the reference's
+    Qdrant volume survives restarts; SQLite would otherwise claim files are indexed that are gone)."""
+    global _exit_hook
+    if _exit_hook:
+        return
+    _exit_hook = True
+
+    def _save_all():
+        snap = get_settings().snapshot_dir
+        if not snap:
+            return
+        for c in list(_collections.values()):
+            if c.dirty and c._index is not None:
+                try:
+                    c.save(snap)
+                except Exception as e:       # pragma: no cover - best effort at exit
+                    logger.error(f"exit snapshot of '{c.name}' failed: {e}")
+
+    atexit.register(_save_all)
 
 
 def _drop_collection(name: str) -> None:
@@ -310,8 +416,11 @@ class VectorStoreService:
         """Update allowed_users on all chunks for a specific file (reference :216)."""
         coll = self._coll
         with coll.lock:
-            for r in self._rows_where(coll, coll.by_file, file_path):
+            rows = self._rows_where(coll, coll.by_file, file_path)
+            for r in rows:
                 coll.payload[r]["allowed_users"] = allowed_users
+            if rows:
+                coll.wrote()
 
     def store_chunks(
         self,
@@ -380,15 +489,18 @@ class VectorStoreService:
             tcat = np.concatenate(terms) if terms else np.zeros(0, np.uint32)
             vcat = np.concatenate(vals) if vals else np.zeros(0, np.float32)
             index = self.client
-            first = None
-            for i in range(0, n, max(1, batch_size)):       # reference upserts in batches (:311-313)
-                j = min(n, i + max(1, batch_size))
-                lo, hi = indptr[i], indptr[j]
-                f = index.upsert(dense[i:j], (indptr[i:j + 1] - lo, tcat[lo:hi], vcat[lo:hi]),
-                                 scope[i:j], created[i:j], modified[i:j])
-                if first is None:
-                    first = f
-            coll.add_rows(first - getattr(index, "row_base", 0), ids, payloads)
+            # One device upsert for the whole call (the C side chunks the H2D copies): either every row of
+            # the call exists on both sides afterwards or none does.  The reference's batch_size (:311-313)
+            # only sized its HTTP requests.
+            first = index.upsert(dense, (indptr, tcat, vcat), scope, created, modified)
+            try:
+                coll.add_rows(first - getattr(index, "row_base", 0), ids, payloads)
+            except Exception:
+                # host bookkeeping failed after the device accepted the rows: tombstone them so that the two
+                # sides keep the same live set, then surface the error
+                index.delete_rows(np.arange(first, first + n, dtype=np.uint64))
+                raise
+            coll.wrote()
         logger.info(f"Stored {n} chunks in B200 index")
         return ids
 
@@ -402,6 +514,7 @@ class VectorStoreService:
                 base = getattr(index, "row_base", 0)
                 index.delete_rows(np.asarray(rows, dtype=np.uint64) + np.uint64(base))
                 coll.remove_rows(rows)
+                coll.wrote()
                 logger.info(f"Deleted {count} chunks for {what}: {key}")
         return count
 
