@@ -17,7 +17,10 @@
  *   - rows are numbered in insertion order, starting at `row_base` (vb_create); a row id is
  *     the only handle the library returns — payloads and point ids stay in the host layer;
  *   - a missing timestamp is VB_TS_MISSING (a `must` range on a missing field fails);
- *   - thread-safety: calls on one index are serialised by an internal mutex.
+ *   - thread-safety: every entry point takes the index's (recursive) mutex for its whole duration, so the
+ *     one-call functions (vb_search, vb_upsert, vb_delete_rows, ...) may be called from any number of
+ *     threads.  The staged form (vb_stage ... vb_fetch) is a multi-call protocol over per-index slots and must
+ *     be driven by one thread at a time per index; a batch staged before a write is refused by vb_run_local.
  *   - no CPU fallback: every compute entry point fails if no sm_100 device is present.
  */
 #ifndef VOITTA_B200_H
@@ -30,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VB_ABI_VERSION 1
+#define VB_ABI_VERSION 2
 #define VB_TS_MISSING INT64_MIN
 #define VB_MAX_KPRIME 1024          /* limit*3 <= 1024 */
 #define VB_MAX_QUERY_TERMS 256      /* non-zeros per sparse query */
@@ -103,6 +106,8 @@ typedef struct vb_stats {
     uint64_t last_big_rows;                    /* rows of the largest (last) segment of the last search */
     double   last_dense_big_ms, last_sparse_big_ms;  /* profile: dense / sparse kernel time of that segment */
     uint64_t dim, row_base;                    /* geometry of the index (what vb_load restored)            */
+    uint64_t index_builds;                     /* full builds of the inverted index so far (sort of every posting) */
+    uint64_t delta_rows;                       /* rows appended since the last build (scored from the forward index) */
 } vb_stats;
 
 int         vb_abi_version(void);
@@ -133,6 +138,14 @@ int vb_upsert_dev(vb_index* h, uint64_t n, const void* rows_bf16,
  * resolves the payload predicate to rows; the library tombstones them (and they stop
  * counting towards N and df of the IDF, as in qdrant). */
 int vb_delete_rows(vb_index* h, uint64_t n, const uint64_t* rows);
+
+/* Index maintenance.  The reference interleaves store_chunks batches of 100 (indexing.py:434,560) and
+ * deletes (indexing.py:284, watcher.py:149-171) with searches, so writes do not invalidate the sorted
+ * inverted index: appended rows form a delta that is scored from the forward index, deletes only clear
+ * alive bits, and N / df follow both exactly.  vb_upsert merges the delta once it passes a threshold
+ * (max(16384, indexed rows / 32); option "delta_max"); a bulk load that jumps far past it is merged by the
+ * next search or by vb_optimize, which forces the merge now (bulk loaders call it when they are done). */
+int vb_optimize(vb_index* h);
 
 /* N (live points) and the document frequency of each term over live rows: the two inputs of
  * qdrant's IDF modifier.  Used by the multi-GPU host layer to sum df across shards. */

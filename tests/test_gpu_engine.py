@@ -721,3 +721,104 @@ def test_k3m_equals_k3_and_oracle(world):
     finally:
         for k, v in {"sparse_ms": 1, "ms_chunk": 0, "ms_budget": 100, "seg_ratio": 0, "seg_first": 2048, "safe_mode": 0, "sparse_dense": 1}.items():
             ix.set_option(k, v)
+
+
+def _csr_slice(csr, lo, hi):
+    ip, tm, vl = csr
+    return (ip[lo:hi + 1] - ip[lo], tm[ip[lo]:ip[hi]], vl[ip[lo]:ip[hi]])
+
+
+def test_incremental_upserts_and_deletes_interleaved(world):
+    """The reference interleaves store_chunks batches of 100 and per-file deletes with searches
+    (indexing.py:434,560,284).  Writes must not rebuild the inverted index: appended rows are scored as a delta
+    from the forward index, deletes only clear alive bits, N and df follow both.  After EVERY write the hybrid
+    results (every filter shape, both kernels' paths) are compared with the oracle on the same live set."""
+    from voitta_rag_b200 import engine
+    coded, dim, n = world["coded"], world["dim"], world["n"]
+    qs = world["queries"][:6]
+    Q = np.stack([q for q, _ in qs]); SP = [s for _, s in qs]
+    B = len(qs)
+    n0 = 12000
+    ix = engine.Index(dim)
+    ix.upsert(coded["dense"][:n0], _csr_slice(coded["csr"], 0, n0), coded["scope"][:n0], coded["created"][:n0], coded["modified"][:n0])
+    alive = np.ones(n, np.uint8)
+    rng = np.random.RandomState(7)
+    flts = filters_for(coded)
+
+    def compare(rows_now, what):
+        cc = oracle_c.CorpusC(coded["dense"][:rows_now], _csr_slice(coded["csr"], 0, rows_now), coded["scope"][:rows_now],
+                              coded["created"][:rows_now], coded["modified"][:rows_now], alive[:rows_now])
+        for t in SP[0][0]:
+            df, n_live = ix.term_stats(np.array([t], np.uint32))
+            assert int(df[0]) == cc.df(t) and n_live == int(alive[:rows_now].sum()), (what, t)
+        for fi in (0, 1, 3):
+            flt = flts[fi]
+            gf = None if flt is None else [engine.Filter(*flt)]
+            fo = None if flt is None else np.zeros(B, np.int32)
+            for path in (1, 2):
+                ix.set_option("dense_path", path)
+                got = ix.search_batch(Q, SP, gf, fo, limit=10, fusion="weighted", branches=True)
+                want = cc.search_batch(Q, SP, None if flt is None else [flt], fo, limit=10, kprime=30, fusion=1)
+                check(got, want, B, 1e-5 if path == 1 else 2e-5, f"{what} f{fi} path{path}")
+        ix.set_option("dense_path", 0)
+
+    compare(n0, "initial")
+    assert ix.stats()["index_builds"] == 1
+    rows_now = n0
+    for step in range(8):
+        if step % 2 == 0:                                   # a store_chunks batch
+            add = 100
+            ix.upsert(coded["dense"][rows_now:rows_now + add], _csr_slice(coded["csr"], rows_now, rows_now + add),
+                      coded["scope"][rows_now:rows_now + add], coded["created"][rows_now:rows_now + add], coded["modified"][rows_now:rows_now + add])
+            rows_now += add
+        else:                                               # delete a few "files" (3 consecutive chunks), old and new rows
+            starts = rng.randint(0, rows_now - 3, size=5)
+            dead = np.unique(np.concatenate([np.arange(s0, s0 + 3) for s0 in starts]))
+            ix.delete_rows(dead.astype(np.uint64))
+            alive[dead] = 0
+        compare(rows_now, f"step{step}")
+        st = ix.stats()
+        assert st["index_builds"] == 1 and st["delta_rows"] == rows_now - n0, st
+    # a query term that exists only in the delta rows: df comes from the adjustment table alone
+    new_term = int(coded["csr"][1].max()) + 17
+    extra = np.zeros((2, dim), np.float32); extra[:, 0] = 1.0
+    ix.upsert(extra, (np.array([0, 1, 2], np.int64), np.array([new_term, new_term], np.uint32), np.array([1.5, 0.5], np.float32)),
+              np.zeros(2, np.uint32), None, None)
+    got = ix.search_batch(Q[:1], [([new_term], [1.0])], limit=5, fusion="rrf", branches=True)
+    assert got.branch(0, "sparse")[0][0] == rows_now and got.sparse_counts[0] == 2
+    idf = math.log((int(alive[:rows_now].sum()) + 2 - 2 + 0.5) / (2 + 0.5) + 1.0)
+    assert got.branch(0, "sparse")[0][1] == float(np.float32(idf * 1.5))
+    ix.delete_rows(np.array([rows_now, rows_now + 1], np.uint64))
+    # crossing the threshold merges the delta inside vb_upsert (off the search path); results unchanged
+    ix.set_option("delta_max", 400)
+    alive2 = np.concatenate([alive[:rows_now], np.zeros(2, np.uint8)])
+    add = 200
+    ix.upsert(coded["dense"][rows_now:rows_now + add], _csr_slice(coded["csr"], rows_now, rows_now + add),
+              coded["scope"][rows_now:rows_now + add], coded["created"][rows_now:rows_now + add], coded["modified"][rows_now:rows_now + add])
+    st = ix.stats()
+    assert st["index_builds"] == 2 and st["delta_rows"] == 0, st
+    # rows rows_now, rows_now+1 are the two deleted extras: the oracle corpus skips them via its alive mask
+    dense2 = np.concatenate([coded["dense"][:rows_now], extra, coded["dense"][rows_now:rows_now + add]])
+    def cat_csr(a, b):
+        return (np.concatenate([a[0], a[0][-1] + b[0][1:]]), np.concatenate([a[1], b[1]]), np.concatenate([a[2], b[2]]))
+    csr2 = cat_csr(cat_csr(_csr_slice(coded["csr"], 0, rows_now), (np.array([0, 1, 2], np.int64), np.array([new_term, new_term], np.uint32), np.array([1.5, 0.5], np.float32))),
+                   _csr_slice(coded["csr"], rows_now, rows_now + add))
+    sc2 = np.concatenate([coded["scope"][:rows_now], np.zeros(2, np.uint32), coded["scope"][rows_now:rows_now + add]])
+    cr2 = np.concatenate([coded["created"][:rows_now], np.full(2, _coded.TS_MISSING, np.int64), coded["created"][rows_now:rows_now + add]])
+    mo2 = np.concatenate([coded["modified"][:rows_now], np.full(2, _coded.TS_MISSING, np.int64), coded["modified"][rows_now:rows_now + add]])
+    al2 = np.concatenate([alive2, np.ones(add, np.uint8)])
+    cc = oracle_c.CorpusC(dense2, csr2, sc2, cr2, mo2, al2)
+    got = ix.search_batch(Q, SP, limit=10, fusion="weighted", branches=True)
+    want = cc.search_batch(Q, SP, None, None, limit=10, kprime=30, fusion=1)
+    check(got, want, B, 2e-5, "after merge")
+    # vb_optimize with nothing to merge is a no-op; after a delete it rebuilds and drops the dead postings
+    ix.optimize()
+    assert ix.stats()["index_builds"] == 2
+    ix.delete_rows(np.array([5, 6], np.uint64)); al2[[5, 6]] = 0
+    ix.optimize()
+    assert ix.stats()["index_builds"] == 3
+    cc = oracle_c.CorpusC(dense2, csr2, sc2, cr2, mo2, al2)
+    got = ix.search_batch(Q, SP, limit=10, fusion="weighted", branches=True)
+    want = cc.search_batch(Q, SP, None, None, limit=10, kprime=30, fusion=1)
+    check(got, want, B, 2e-5, "after optimize")
+    ix.close()

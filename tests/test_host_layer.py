@@ -47,9 +47,11 @@ def test_golden_replay_through_host_layer(store):
 def test_surface_matches_reference_signatures():
     """Names, positional order and defaults of SURVEY.md §8(b)."""
     sig = inspect.signature(VS.VectorStoreService.search)
+    # the reference's parameters, in order; the one additive parameter comes after them and defaults to None
     assert list(sig.parameters) == ["self", "query_embedding", "limit", "folder_filter", "include_folders",
                                     "exclude_folders", "exclude_index_folders", "sparse_query", "sparse_weight",
-                                    "date_start", "date_end", "date_field"]
+                                    "date_start", "date_end", "date_field", "scope_key"]
+    assert sig.parameters["scope_key"].default is None
     assert sig.parameters["limit"].default == 10 and sig.parameters["sparse_weight"].default == 0.1
     sig = inspect.signature(VS.VectorStoreService.store_chunks)
     assert list(sig.parameters) == ["self", "chunks", "sparse_vectors", "batch_size"]
@@ -164,3 +166,61 @@ def test_concurrent_readers_and_writer(store):
     assert not errors, errors
     # 3 writers x 12 files x 4 chunks, every third file deleted again
     assert store.get_collection_info()["points_count"] == 3 * (12 - 4) * 4
+
+
+def test_concurrent_single_queries_are_coalesced_and_identical_to_serial(store):
+    """voitta issues B = 1 from several threads (mcp_server.py:474-485).  The submit queue turns callers that overlap
+    into one device batch, each with its OWN filter; every caller must get exactly what a serial call returns."""
+    import threading
+    corpus, queries = G.build_inputs()
+    G.replay(store, GOLD["ops"][:2], corpus, queries, VS.ChunkMetadata, {})
+    folders = sorted({m["folder_path"] for m in corpus["metas"]})
+    calls = []
+    for i, (q, sq) in enumerate(queries):
+        kw = {}
+        if i % 3 == 1:
+            kw = {"include_folders": folders[: 1 + i % 4]}
+        elif i % 3 == 2:
+            kw = {"exclude_folders": folders[:2], "date_start": 1500000000}
+        calls.append((list(map(float, q)), (list(sq[0]), list(sq[1])) if i % 4 else None, 5 + (i % 2) * 5, kw))
+    serial = [[(c.id, c.score) for c in store.search(q, limit=lim, sparse_query=sq, **kw)] for q, sq, lim, kw in calls]
+    assert any(serial)
+    before = store.coalescing_stats()
+    got = [None] * len(calls)
+    errors = []
+    gate = threading.Barrier(len(calls))
+
+    def run(i):
+        try:
+            q, sq, lim, kw = calls[i]
+            gate.wait()
+            for _ in range(5):
+                got[i] = [(c.id, c.score) for c in store.search(q, limit=lim, sparse_query=sq, **kw)]
+        except Exception as e:          # pragma: no cover
+            errors.append(e)
+
+    th = [threading.Thread(target=run, args=(i,)) for i in range(len(calls))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors
+    assert got == serial
+    after = store.coalescing_stats()
+    assert after["requests"] - before["requests"] == 5 * len(calls)
+    assert after["batches"] - before["batches"] <= 5 * len(calls)
+
+
+def test_scope_key_caches_the_folded_bitset_until_a_new_scope_appears(store):
+    corpus, queries = G.build_inputs()
+    G.replay(store, GOLD["ops"][:1], corpus, queries, VS.ChunkMetadata, {})
+    folders = sorted({m["folder_path"] for m in corpus["metas"]})
+    f1 = store._build_filter(include_folders=folders[:3], scope_key=("u", "p", 1))
+    f2 = store._build_filter(include_folders=["ignored: the key says the settings did not change"], scope_key=("u", "p", 1))
+    assert f2.scope_bits is f1.scope_bits
+    f3 = store._build_filter(include_folders=folders[:3], scope_key=("u", "p", 2))      # settings version bumped by the caller
+    assert f3.scope_bits is not f1.scope_bits and (f3.scope_bits == f1.scope_bits).all()
+    m = VS.ChunkMetadata("brand/new/file.txt", "brand/new", "brand", "file.txt", 0, 1, 0, 1, "t")
+    store.store_chunks([("t", [1.0] * GOLD["dim"], m)], [([3], [1.0])])                 # a new scope id: cached bitsets die
+    f4 = store._build_filter(include_folders=folders[:3] + ["brand/new"], scope_key=("u", "p", 2))
+    assert f4.scope_bits is not f3.scope_bits
+    hits = store.search([1.0] * GOLD["dim"], limit=50, include_folders=folders[:3] + ["brand/new"], scope_key=("u", "p", 2))
+    assert any(c.metadata.folder_path == "brand/new" for c in hits)

@@ -8,6 +8,7 @@
 #include "dense_gemm.cuh"
 #include "sparse.cuh"
 #include "sparse_ms.cuh"
+#include "sparse_delta.cuh"
 #include "topk.cuh"
 
 #include <unistd.h>
@@ -20,6 +21,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 // ------------------------------------------------------------------------------------------------
@@ -98,6 +100,13 @@ struct Batch {
     const uint32_t* d_oldq = nullptr;          // [n_old] the other sparse queries
     const uint32_t* d_qtab = nullptr;          // [n_qterms] bucket table offset of the term (VB_MS_NO_TAB = none)
     const uint8_t* d_qshift = nullptr;         // [n_qterms] bucket shift
+    // the query batch inverted by term, for the delta rows (K3D)
+    const uint32_t* d_ut = nullptr;            // [n_uterms] distinct terms, ascending
+    const uint32_t* d_up = nullptr;            // [n_uterms + 1]
+    const uint32_t* d_uq = nullptr;            // [n_qterms] query
+    const double* d_uw = nullptr;              // [n_qterms] weight
+    uint32_t n_uterms = 0;
+    uint32_t base_rows = 0;                    // rows covered by the inverted index when the batch was staged
     const int32_t* d_maskof = nullptr;
     const int32_t* d_mode = nullptr;
     const VbFilterDev* d_filters = nullptr;
@@ -144,7 +153,9 @@ struct vb_index {
     std::vector<uint32_t> tab_off_of_slot; // term slot -> first entry of its bucket table in term_tab (VB_MS_NO_TAB = none)
     std::vector<uint8_t> tab_shift_of_slot;
     DevBuf term_tab;                       // bucket tables: first posting with row >= b << shift, per term (K3M lookups)
-    uint64_t base_rows = 0;                // rows the inverted index was built over
+    uint64_t base_rows = 0;                // rows the inverted index was built over; rows past it are the DELTA (K3D)
+    std::unordered_map<uint32_t, int64_t> df_adj;   // term -> change of its live df since the build (delta rows +, deletes -)
+    uint64_t dead_since_build = 0;         // rows tombstoned since the build (their postings are still in the index)
     DevBuf heavy_vals;                     // [n_heavy][heavy_stride] fp32, NaN = term absent from the row
     uint32_t n_heavy = 0, heavy_stride = 0;
     bool sparse_nonneg = false;            // no negative posting value in the shard
@@ -160,6 +171,7 @@ struct vb_index {
     int64_t opt_sparse_ms = 1;             // 1: posting-driven MaxScore kernel (K3M) outside the direct segment; 0: K3 everywhere
     int64_t opt_ms_budget = 100;           // K3M: non-essential ub budget in % of tau (100 = full MaxScore partition)
     int64_t opt_ms_chunk = 0;              // K3M: postings per work unit (0 = auto)
+    int64_t opt_delta_max = 0;             // rows the delta may hold before vb_upsert merges it into the index (0 = auto)
     int64_t opt_ms_max_terms = 16;         // K3M scores queries of at most this many terms; longer ones accumulate (K3)
 
     vb_stats stats{};
@@ -234,6 +246,8 @@ __global__ void vb_find_tail_kernel(const uint64_t* keys, uint64_t n, uint64_t* 
     *out = lo;
 }
 
+static int g_delta_smem_max = 48 * 1024;
+
 static unsigned grid_for(uint64_t n, unsigned block, unsigned max_blocks = 148u * 16u) {
     uint64_t g = (n + block - 1) / block;
     if (g < 1) g = 1;
@@ -280,6 +294,10 @@ extern "C" int vb_create(int32_t dim, int32_t device, uint64_t capacity_hint, ui
     }
     h->stream = h->own_stream;
     if (vb_gemm_configure() != 0) { delete h; return vb_fail("vb_create: tensor-core kernel configuration failed: %s", vb_gemm_last_error()); }
+    {
+        const int want = std::min<int>((int)prop.sharedMemPerBlockOptin, 200 * 1024);
+        if (cudaFuncSetAttribute(vb_sparse_delta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want) == cudaSuccess) g_delta_smem_max = want;
+    }
     (void)capacity_hint;
     if (const char* env = getenv("VB200_DENSE_PATH")) h->opt_dense_path = atoi(env);   // 0 auto, 1 K1, 2 K2
     if (const char* env = getenv("VB200_SEG_FIRST")) h->opt_seg_first = std::max<int64_t>(VB_ROWS_PER_BLOCK, (int64_t)align_up((size_t)atoll(env), VB_ROWS_PER_BLOCK));
@@ -330,6 +348,7 @@ extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
     else if (k == "sparse_ms") h->opt_sparse_ms = value;           // 0: K3 in every segment (no MaxScore kernel)
     else if (k == "ms_budget") h->opt_ms_budget = value;           // K3M non-essential budget in % of tau
     else if (k == "ms_chunk") h->opt_ms_chunk = value;             // K3M postings per work unit (0 auto)
+    else if (k == "delta_max") h->opt_delta_max = value;           // delta rows that trigger a merge (0 = max(16384, base/32))
     else if (k == "ms_max_terms") h->opt_ms_max_terms = value;     // K3M only for queries of at most this many terms
     else if (k == "sparse_prune_force") h->opt_sparse_prune_force = value;   // 1: prune in every non-direct segment (tests)
     else if (k == "sparse_prune") h->opt_sparse_prune = value;     // MaxScore budget in % of tau (0: score every term's postings)
@@ -352,6 +371,7 @@ extern "C" int vb_get_stats(vb_index* h, vb_stats* out) {
     h->stats.device_bytes = h->device_bytes;
     h->stats.dim = (uint64_t)h->dim;
     h->stats.row_base = h->row_base;
+    h->stats.delta_rows = h->sparse_dirty ? h->n_rows : h->n_rows - h->base_rows;
     *out = h->stats;
     return 0;
 }
@@ -360,6 +380,50 @@ extern "C" int vb_sync(vb_index* h) {
     if (!h) return vb_fail("vb_sync: NULL index");
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// incremental index maintenance.  The sorted inverted index ("base") is immutable between
+// builds.  Upserts append to the forward CSR and become the DELTA, scored by K3D (sparse_delta.cuh); deletes
+// clear alive bits.  Both adjust df_adj so that the IDF keeps using the exact live document frequencies
+// (qdrant updates its df table on every upsert/delete).  The delta is merged (full rebuild) by vb_upsert once
+// it passes delta_max rows — off the search path — or lazily by the next search after a bulk load.
+// ------------------------------------------------------------------------------------------------
+static uint64_t delta_max(const vb_index* h) {
+    if (h->opt_delta_max > 0) return (uint64_t)h->opt_delta_max;
+    return std::max<uint64_t>(16384, h->base_rows / 32);
+}
+
+static uint64_t live_df(const vb_index* h, uint32_t term, int64_t slot) {
+    int64_t d = slot >= 0 ? (int64_t)(h->term_ptr[slot + 1] - h->term_ptr[slot]) : 0;
+    if (!h->df_adj.empty()) {
+        auto it = h->df_adj.find(term);
+        if (it != h->df_adj.end()) d += it->second;
+    }
+    return d < 0 ? 0 : (uint64_t)d;
+}
+
+__global__ void vb_row_ranges_kernel(const int64_t* __restrict__ indptr, const uint32_t* __restrict__ rows, uint32_t n, int64_t* __restrict__ se) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { se[2 * i] = indptr[rows[i]]; se[2 * i + 1] = indptr[rows[i] + 1]; }
+}
+__global__ void vb_gather_terms_kernel(const uint32_t* __restrict__ sp_term, const int64_t* __restrict__ se, const int64_t* __restrict__ dst0,
+                                       uint32_t n, uint32_t* __restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps)
+        for (int64_t p = se[2 * i] + lane; p < se[2 * i + 1]; p += 32) out[dst0[i] + (p - se[2 * i])] = sp_term[p];
+}
+
+static int ensure_sparse_index(vb_index* h);
+
+// after an append of rows [first, first + n): keep the index incremental if the delta stays small
+static int after_append(vb_index* h, const uint32_t* host_terms, uint64_t n_terms) {
+    const uint64_t delta = h->n_rows - h->base_rows;
+    if (h->sparse_dirty || delta > 2 * delta_max(h)) { h->sparse_dirty = true; return 0; }   // bulk load: rebuild lazily
+    for (uint64_t p = 0; p < n_terms; ++p) ++h->df_adj[host_terms[p]];
+    if (delta >= delta_max(h)) { h->sparse_dirty = true; TRY(ensure_sparse_index(h)); }       // merge, off the search path
     return 0;
 }
 
@@ -459,9 +523,9 @@ extern "C" int vb_upsert(vb_index* h, uint64_t n, const float* dense, const int6
     h->n_rows += n;
     h->n_live += n;
     h->nnz += add_nnz;
-    h->sparse_dirty = true;
     ++h->write_gen;
     if (first_row) *first_row = h->row_base + first;
+    TRY(after_append(h, sp_indptr ? sp_term + sp_indptr[0] : nullptr, add_nnz));
     return 0;
 }
 
@@ -512,9 +576,15 @@ extern "C" int vb_upsert_dev(vb_index* h, uint64_t n, const void* rows_bf16, con
     h->n_rows += n;
     h->n_live += n;
     h->nnz += add_nnz;
-    h->sparse_dirty = true;
     ++h->write_gen;
     if (first_row) *first_row = h->row_base + first;
+    if (!h->sparse_dirty && h->n_rows - h->base_rows <= 2 * delta_max(h)) {
+        std::vector<uint32_t> terms(add_nnz);                   // small append: its terms feed the df table
+        if (add_nnz) CK(cudaMemcpy(terms.data(), h->sp_term.as<uint32_t>() + (h->nnz - add_nnz), add_nnz * 4, cudaMemcpyDeviceToHost));
+        TRY(after_append(h, terms.data(), add_nnz));
+    } else {
+        h->sparse_dirty = true;
+    }
     return 0;
 }
 
@@ -525,21 +595,65 @@ extern "C" int vb_delete_rows(vb_index* h, uint64_t n, const uint64_t* rows) {
     std::lock_guard<std::recursive_mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
     uint64_t killed = 0;
-    std::vector<uint32_t> touched;
+    std::vector<uint32_t> touched, dead;
     for (uint64_t i = 0; i < n; ++i) {
         if (rows[i] < h->row_base || rows[i] - h->row_base >= h->n_rows)
             return vb_fail("vb_delete_rows: row %llu out of range", (unsigned long long)rows[i]);
         const uint64_t r = rows[i] - h->row_base;
         uint32_t& w = h->alive_host[r >> 5];
-        if (w & (1u << (r & 31u))) { w &= ~(1u << (r & 31u)); ++killed; touched.push_back((uint32_t)(r >> 5)); }
+        if (w & (1u << (r & 31u))) { w &= ~(1u << (r & 31u)); ++killed; touched.push_back((uint32_t)(r >> 5)); dead.push_back((uint32_t)r); }
     }
-    std::sort(touched.begin(), touched.end());
-    touched.erase(std::unique(touched.begin(), touched.end()), touched.end());
-    for (uint32_t w : touched)
-        CK(cudaMemcpyAsync(h->alive.as<uint32_t>() + w, &h->alive_host[w], 4, cudaMemcpyHostToDevice, h->stream));
+    if (!killed) return 0;
+    // one ranged upload of the touched bitmap words (a folder delete touches tens of thousands of them)
+    const uint32_t w_lo = *std::min_element(touched.begin(), touched.end()), w_hi = *std::max_element(touched.begin(), touched.end());
+    CK(cudaMemcpyAsync(h->alive.as<uint32_t>() + w_lo, &h->alive_host[w_lo], (size_t)(w_hi - w_lo + 1) * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->n_live -= killed;
-    if (killed) { h->sparse_dirty = true; ++h->write_gen; }
+    ++h->write_gen;
+    if (h->sparse_dirty) return 0;
+    // Incremental path: the postings of the dead rows stay in the index (the alive bits mask them); only the live
+    // document frequencies change.  Large deletes, or too many dead postings, fall back to a rebuild.
+    h->dead_since_build += killed;
+    if (killed > std::max<uint64_t>(4096, h->n_live / 16) || h->dead_since_build * 4 > std::max<uint64_t>(h->base_rows, 1)) {
+        h->sparse_dirty = true;
+        return 0;
+    }
+    if (h->nnz == 0) return 0;
+    {
+        const uint32_t m = (uint32_t)dead.size();
+        DevBuf d_rows, d_se, d_dst, d_out;
+        auto cleanup = [&]() { dev_free(h, d_rows); dev_free(h, d_se); dev_free(h, d_dst); dev_free(h, d_out); };
+        int rc = dev_reserve(h, d_rows, (size_t)m * 4, false);
+        if (!rc) rc = dev_reserve(h, d_se, (size_t)m * 16, false);
+        if (!rc) rc = dev_reserve(h, d_dst, (size_t)m * 8, false);
+        if (rc) { cleanup(); return rc; }
+        std::vector<int64_t> se(2 * (size_t)m), dst(m);
+        cudaError_t e = cudaMemcpyAsync(d_rows.p, dead.data(), (size_t)m * 4, cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) {
+            vb_row_ranges_kernel<<<(m + 255) / 256, 256, 0, h->stream>>>(h->sp_indptr.as<int64_t>(), d_rows.as<uint32_t>(), m, d_se.as<int64_t>());
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(se.data(), d_se.p, (size_t)m * 16, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        int64_t total = 0;
+        for (uint32_t i = 0; i < m; ++i) { dst[i] = total; total += se[2 * i + 1] - se[2 * i]; }
+        std::vector<uint32_t> terms((size_t)total);
+        if (e == cudaSuccess && total > 0) {
+            rc = dev_reserve(h, d_out, (size_t)total * 4, false);
+            if (rc) { cleanup(); return rc; }
+            e = cudaMemcpyAsync(d_dst.p, dst.data(), (size_t)m * 8, cudaMemcpyHostToDevice, h->stream);
+            if (e == cudaSuccess) {
+                vb_gather_terms_kernel<<<grid_for((uint64_t)m * 32, 256), 256, 0, h->stream>>>(
+                    h->sp_term.as<uint32_t>(), d_se.as<int64_t>(), d_dst.as<int64_t>(), m, d_out.as<uint32_t>());
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaMemcpyAsync(terms.data(), d_out.p, (size_t)total * 4, cudaMemcpyDeviceToHost, h->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        }
+        cleanup();
+        if (e != cudaSuccess) { h->sparse_dirty = true; return vb_fail("vb_delete_rows: df update failed: %s", cudaGetErrorString(e)); }
+        for (uint32_t t : terms) --h->df_adj[t];
+    }
     return 0;
 }
 
@@ -557,7 +671,9 @@ static int ensure_sparse_index(vb_index* h) {
     h->n_heavy = 0;
     h->sparse_nonneg = false;
     h->nnz_live = 0;
-    if (h->nnz == 0) { h->sparse_dirty = false; return 0; }
+    h->df_adj.clear();
+    h->dead_since_build = 0;
+    if (h->nnz == 0) { h->base_rows = h->n_rows; h->sparse_dirty = false; return 0; }
     const uint64_t nnz = h->nnz;
     if (nnz >= (1ull << 31)) return vb_fail("sparse index: %llu postings exceed the 2^31 limit of one shard", (unsigned long long)nnz);
     DevBuf keys_in, keys_out, vals_out, cub_tmp, misc;
@@ -584,7 +700,7 @@ static int ensure_sparse_index(vb_index* h) {
     CKC(cudaMemcpyAsync(&live, misc.p, 8, cudaMemcpyDeviceToHost, h->stream));
     CKC(cudaStreamSynchronize(h->stream));
     h->nnz_live = live;
-    if (live == 0) { cleanup(); h->sparse_dirty = false; return 0; }
+    if (live == 0) { cleanup(); h->base_rows = h->n_rows; h->sparse_dirty = false; return 0; }
     TRYC(dev_reserve(h, h->post_row, live * 4, false));
     TRYC(dev_reserve(h, h->post_val, live * 4, false));
     // keys_in is free now: reuse it for post_term (u32), unique terms (u32), run lengths (u32)
@@ -704,6 +820,7 @@ static int ensure_sparse_index(vb_index* h) {
     }
     cleanup2();
     h->base_rows = h->n_rows;
+    ++h->stats.index_builds;
     h->sparse_dirty = false;
     return 0;
 #undef TRYC
@@ -718,14 +835,21 @@ static int64_t term_slot(const vb_index* h, uint32_t term) {
     return it - h->terms_sorted.begin();
 }
 
+extern "C" int vb_optimize(vb_index* h) {
+    if (!h) return vb_fail("vb_optimize: NULL index");
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    if (h->n_rows != h->base_rows || h->dead_since_build) h->sparse_dirty = true;
+    return ensure_sparse_index(h);
+}
+
 extern "C" int vb_term_stats(vb_index* h, uint32_t n_terms, const uint32_t* terms, uint64_t* df, uint64_t* n_live) {
     if (!h) return vb_fail("vb_term_stats: NULL index");
     std::lock_guard<std::recursive_mutex> lk(h->mu);
     CK(cudaSetDevice(h->device));
     TRY(ensure_sparse_index(h));
     for (uint32_t i = 0; i < n_terms; ++i) {
-        const int64_t s = term_slot(h, terms[i]);
-        df[i] = s < 0 ? 0 : h->term_ptr[s + 1] - h->term_ptr[s];
+        df[i] = live_df(h, terms[i], term_slot(h, terms[i]));
     }
     if (n_live) *n_live = h->n_live;
     return 0;
@@ -837,7 +961,7 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
                 }
                 double w = pr.second;
                 if (q->apply_idf) {
-                    const double df = (double)(phi - plo);
+                    const double df = (double)(need_corpus ? live_df(h, pr.first, slot) : 0);
                     // local_collection.py _compute_idf: log((N - df + 0.5) / (df + 0.5) + 1)
                     w = w * std::log(((double)h->n_live - df + 0.5) / (df + 0.5) + 1.0);
                 }
@@ -907,7 +1031,7 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     b.mask_of_host = mask_of;
     b.n_filters = b.use_mask ? (uint32_t)flt.size() : 0;
     b.mask_words = (uint32_t)((h->n_rows + 31) / 32);
-    b.n_blocks = (uint32_t)((h->n_rows + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK);
+    b.n_blocks = (uint32_t)((h->base_rows + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK);   // row blocks of the inverted index
 
     // ---- pack everything into one pinned block, one H2D copy ----
     Arena ar;
@@ -927,6 +1051,25 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     const size_t o_oq = ar.take((size_t)oldq.size() * 4 + 8);
     const size_t o_tab = ar.take((size_t)b.n_qterms * 4 + 8);
     const size_t o_tsh = ar.take((size_t)b.n_qterms + 8);
+    // delta rows present: the batch inverted by term (term -> queries, weights) for K3D
+    std::vector<uint32_t> ut, up, uq;
+    std::vector<double> uw;
+    if (need_corpus && b.any_sparse && h->n_rows > h->base_rows) {
+        std::vector<uint32_t> order(b.n_qterms);
+        for (uint32_t t = 0; t < b.n_qterms; ++t) order[t] = t;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return qterm[x] < qterm[y]; });   // (term, query)
+        for (uint32_t t : order) {
+            if (ut.empty() || ut.back() != qterm[t]) { ut.push_back(qterm[t]); up.push_back((uint32_t)uq.size()); }
+            uq.push_back(slotq[t]);
+            uw.push_back(weight[t]);
+        }
+        up.push_back((uint32_t)uq.size());
+        b.n_uterms = (uint32_t)ut.size();
+    }
+    const size_t o_ut = ar.take(ut.size() * 4 + 8);
+    const size_t o_up = ar.take(up.size() * 4 + 8);
+    const size_t o_uq = ar.take(uq.size() * 4 + 8);
+    const size_t o_uw = ar.take(uw.size() * 8 + 8);
     const size_t o_mo = ar.take((size_t)b.B * 4);
     const size_t o_md = ar.take((size_t)b.B * 4);
     const size_t o_fl = ar.take((size_t)std::max<uint32_t>(1, b.n_filters) * sizeof(VbFilterDev));
@@ -955,8 +1098,15 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
         memcpy(hp + o_tab, qtab.data(), (size_t)b.n_qterms * 4);
         memcpy(hp + o_tsh, qshift.data(), (size_t)b.n_qterms);
     }
+    if (b.n_uterms) {
+        memcpy(hp + o_ut, ut.data(), ut.size() * 4);
+        memcpy(hp + o_up, up.data(), up.size() * 4);
+        memcpy(hp + o_uq, uq.data(), uq.size() * 4);
+        memcpy(hp + o_uw, uw.data(), uw.size() * 8);
+    }
     b.n_old = (uint32_t)oldq.size();
     b.n_rows = (uint32_t)h->n_rows;
+    b.base_rows = (uint32_t)h->base_rows;
     b.gen = h->write_gen;
     memcpy(hp + o_mo, mask_of.data(), (size_t)b.B * 4);
     memcpy(hp + o_md, b.mode.data(), (size_t)b.B * 4);
@@ -988,6 +1138,10 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     b.d_oldq = reinterpret_cast<const uint32_t*>(dp + o_oq);
     b.d_qtab = reinterpret_cast<const uint32_t*>(dp + o_tab);
     b.d_qshift = reinterpret_cast<const uint8_t*>(dp + o_tsh);
+    b.d_ut = reinterpret_cast<const uint32_t*>(dp + o_ut);
+    b.d_up = reinterpret_cast<const uint32_t*>(dp + o_up);
+    b.d_uq = reinterpret_cast<const uint32_t*>(dp + o_uq);
+    b.d_uw = reinterpret_cast<const double*>(dp + o_uw);
     b.d_maskof = reinterpret_cast<const int32_t*>(dp + o_mo);
     b.d_mode = reinterpret_cast<const int32_t*>(dp + o_md);
     b.d_filters = reinterpret_cast<const VbFilterDev*>(dp + o_fl);
@@ -1131,8 +1285,11 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     // select of the sparse lists) are independent until the fusion, so they run on two streams:
     // the small kernels of one chain (selects, first segments, slice table) hide behind the big
     // kernels of the other.
-    const bool do_sparse = b.any_sparse && h->nnz_live > 0 && b.n_qterms > 0;
-    const bool two_streams = do_sparse && h->opt_overlap;
+    // sparse work: the inverted index covers rows [0, nb); rows appended since (the delta) are scored by K3D
+    const uint32_t nb = (uint32_t)std::min<uint64_t>(h->base_rows, n);
+    const bool do_sparse = b.any_sparse && h->nnz_live > 0 && b.n_qterms > 0 && nb > 0;
+    const bool do_delta = b.any_sparse && b.n_uterms > 0 && nb < n;
+    const bool two_streams = (do_sparse || do_delta) && h->opt_overlap;
     cudaStream_t sd = h->stream, ss = two_streams ? h->aux_stream : h->stream;
     if (two_streams) {
         CK(cudaEventRecord(h->ev_fork, sd));
@@ -1168,8 +1325,10 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     const bool ms_on = do_sparse && b.any_ms && h->opt_sparse_ms;
     const uint32_t ms_chunk = h->opt_ms_chunk > 0 ? (uint32_t)align_up((size_t)h->opt_ms_chunk, VB_MS_U * VB_MS_THREADS)
                                                    : 512u;
-    auto sparse_segment = [&](uint32_t r0, uint32_t r1, uint32_t direct, bool big) -> int {
-        if (do_sparse) {
+    auto sparse_segment = [&](uint32_t r0, uint32_t r1_all, uint32_t direct, bool big) -> int {
+        const uint32_t r1 = std::min(r1_all, nb);               // the index stops at nb
+        if (!direct && !(do_sparse && r0 < r1)) return 0;       // nothing scored, nothing to compact
+        if (do_sparse && r0 < r1) {
             const int pi = prof_begin(h, PH_SPARSE | (big ? PH_BIG : 0), ss);
             const bool use_ms = ms_on && !direct;
             if (use_ms) {
@@ -1220,7 +1379,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
                 a.q_hidx = b.any_heavy ? b.d_qhidx : nullptr; a.q_relaxed = b.d_qrelaxed; a.heavy_vals = h->heavy_vals.as<float>(); a.heavy_stride = h->heavy_stride;
                 a.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; a.mask_of = b.use_mask ? b.d_maskof : nullptr;
                 a.tau = b.tau; a.lists = L; a.mask_words = b.mask_words;
-                a.n_qterms = b.n_qterms; a.nt_max = b.nt_max; a.blk_begin = r0 / VB_ROWS_PER_BLOCK; a.n_queries = b.B; a.n_rows = n;
+                a.n_qterms = b.n_qterms; a.nt_max = b.nt_max; a.blk_begin = r0 / VB_ROWS_PER_BLOCK; a.n_queries = b.B; a.n_rows = nb;
                 a.row_base = (uint32_t)h->row_base; a.direct = direct;
                 uint32_t n_q = b.B;
                 if (use_ms) { a.q_sel = b.d_oldq; a.n_sel = b.n_old; n_q = b.n_old; }   // the MaxScore kernel has the rest
@@ -1274,7 +1433,36 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         const bool big = s + 1 == n_seg;
         if (big) h->stats.last_big_rows = bounds[s + 1] - bounds[s];
         TRY(dense_segment(bounds[s], bounds[s + 1], direct, big));
-        if (do_sparse || s == 0) TRY(sparse_segment(bounds[s], bounds[s + 1], direct, big));
+        TRY(sparse_segment(bounds[s], bounds[s + 1], direct, big));
+    }
+    if (do_delta && phase != 1) {
+        // K3D: the rows appended since the index was built, straight from the forward CSR.  One launch (a few
+        // thousand rows against thresholds the indexed rows have already established); the safe mode cuts it into
+        // pieces a list cannot overflow on.
+        const uint32_t piece = safe_mode ? (uint32_t)std::max<size_t>(VB_ROWS_PER_BLOCK, h->cand_cap - b.k) : n - nb;
+        for (uint32_t r0 = nb; r0 < n; r0 += piece) {
+            const uint32_t r1 = (uint32_t)std::min<uint64_t>(n, (uint64_t)r0 + piece);
+            const int pi = prof_begin(h, PH_SPARSE, ss);
+            VbDeltaArgs a{};
+            a.sp_indptr = h->sp_indptr.as<int64_t>(); a.sp_term = h->sp_term.as<uint32_t>(); a.sp_val = h->sp_val.as<float>();
+            a.qt_term = b.d_ut; a.qt_ptr = b.d_up; a.qt_query = b.d_uq; a.qt_weight = b.d_uw;
+            a.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; a.mask_of = b.use_mask ? b.d_maskof : nullptr;
+            a.tau = b.tau; a.lists = L; a.mask_words = b.mask_words; a.n_uterms = b.n_uterms; a.n_queries = b.B;
+            a.row_begin = r0; a.row_end = r1; a.row_base = (uint32_t)h->row_base;
+            const uint32_t warps = vb_delta_warps(b.B);
+            const size_t smem = (size_t)warps * b.B * 8;
+            if (smem > (size_t)g_delta_smem_max) return vb_fail("batch of %u queries is too large for the delta rows (%zu bytes of shared memory)", b.B, smem);
+            const uint32_t grid = std::min<uint32_t>((r1 - r0 + warps - 1) / warps, (uint32_t)h->sm_count * 8u);
+            vb_sparse_delta_kernel<<<grid, warps * 32, smem, ss>>>(a);
+            CKK("vb_sparse_delta_kernel");
+            ++h->stats.last_launches;
+            prof_end(h, pi, ss);
+            const int ps = prof_begin(h, PH_SELECT, ss);
+            vb_compact_kernel<<<b.B, VB_COMPACT_THREADS, 0, ss>>>(L, b.tau, b.overflow, b.k, b.B, L.sub_cap);
+            CKK("vb_compact_kernel");
+            ++h->stats.last_launches;
+            prof_end(h, ps, ss);
+        }
     }
     if (two_streams) {
         CK(cudaEventRecord(h->ev_join, ss));

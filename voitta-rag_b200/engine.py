@@ -60,12 +60,12 @@ class _Stats(C.Structure):
                 ("last_dense_path", C.c_uint32), ("last_launches", C.c_uint32), ("device_bytes", C.c_uint64),
                 ("last_h2d_bytes", C.c_uint64), ("last_d2h_bytes", C.c_uint64), ("last_dense_passes", C.c_uint64),
                 ("last_big_rows", C.c_uint64), ("last_dense_big_ms", C.c_double), ("last_sparse_big_ms", C.c_double),
-                ("dim", C.c_uint64), ("row_base", C.c_uint64)]
+                ("dim", C.c_uint64), ("row_base", C.c_uint64), ("index_builds", C.c_uint64), ("delta_rows", C.c_uint64)]
 
 
 # every symbol include/voitta_b200.h declares
 EXPORTS = ["vb_abi_version", "vb_last_error", "vb_create", "vb_destroy", "vb_upsert", "vb_upsert_dev",
-           "vb_delete_rows", "vb_term_stats", "vb_search", "vb_search_local", "vb_merge_fuse",
+           "vb_delete_rows", "vb_optimize", "vb_term_stats", "vb_search", "vb_search_local", "vb_merge_fuse",
            "vb_stage", "vb_run_local", "vb_run_fuse", "vb_fetch",
            "vb_run_local_begin", "vb_tau_export", "vb_tau_import",
            "vb_set_option", "vb_get_stats", "vb_sync", "vb_save", "vb_load"]
@@ -91,6 +91,7 @@ def load_library():
     lib.vb_upsert.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, vp, vp, vp, u64p]
     lib.vb_upsert_dev.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, vp, vp, vp, u64p]
     lib.vb_delete_rows.argtypes = [vp, C.c_uint64, vp]
+    lib.vb_optimize.argtypes = [vp]
     lib.vb_term_stats.argtypes = [vp, C.c_uint32, vp, vp, u64p]
     lib.vb_search.argtypes = [vp, C.POINTER(_QueryBatch), C.POINTER(_Result)]
     lib.vb_search_local.argtypes = [vp, C.POINTER(_QueryBatch), vp]
@@ -311,6 +312,10 @@ class Index:
     def delete_rows(self, rows) -> None:
         r = np.ascontiguousarray(rows, dtype=np.uint64)
         self._check(self._lib.vb_delete_rows(self._h, r.size, _vp(r)))
+
+    def optimize(self) -> None:
+        """Merge the rows appended since the last index build into the inverted index now."""
+        self._check(self._lib.vb_optimize(self._h))
 
     def term_stats(self, terms):
         t = np.ascontiguousarray(terms, dtype=np.uint32)

@@ -118,6 +118,97 @@ def _payload_to_chunk(pid: str, payload: dict, score) -> StoredChunk:
     )
 
 
+class _Request:
+    __slots__ = ("q", "sparse", "flt", "limit", "fusion", "sparse_weight", "done", "result", "error")
+
+    def __init__(self, q, sparse, flt, limit, fusion, sparse_weight):
+        self.q, self.sparse, self.flt, self.limit, self.fusion, self.sparse_weight = q, sparse, flt, limit, fusion, sparse_weight
+        self.done, self.result, self.error = False, None, None
+
+
+class _Coalescer:
+    """Combines concurrent single-query searches into one device batch.
+
+    voitta only ever issues B = 1 (mcp_server.py:474-485), but from several threads at once (FastMCP tool
+    workers).  Holding the collection lock for one device search per caller would serialise
+    them at ~1 search latency each; instead the first caller to find the device free becomes the LEADER,
+    takes every request queued so far — each with its own filter, the C ABI takes one filter per query —
+    runs them as ONE vb_search, and hands the results back.  Callers that arrive while a batch is running
+    queue up and form the next batch, so the batch size adapts to the load and a lone caller pays no wait."""
+
+    def __init__(self, coll):
+        self.coll = coll
+        self.cv = threading.Condition()
+        self.pending: list[_Request] = []
+        self.busy = False
+        self.batches = 0
+        self.requests = 0
+
+    def submit(self, req: _Request):
+        with self.cv:
+            self.pending.append(req)
+            while not req.done and self.busy:
+                self.cv.wait()
+            if req.done:
+                batch = None
+            else:                                   # device free and nobody served us yet: lead the next batch
+                batch, self.pending = self.pending, []
+                self.busy = True
+        if batch is not None:
+            try:
+                self._run(batch)
+            finally:
+                with self.cv:
+                    self.busy = False
+                    self.batches += 1
+                    self.requests += len(batch)
+                    self.cv.notify_all()
+        if req.error is not None:
+            raise req.error
+        return req.result
+
+    def _run(self, batch: list[_Request]):
+        coll = self.coll
+        groups: dict = {}
+        for r in batch:                             # one device call per (limit, fusion, weight): the C ABI's per-batch knobs
+            groups.setdefault((r.limit, r.fusion, r.sparse_weight), []).append(r)
+        for (limit, fusion, weight), reqs in groups.items():
+            try:
+                with coll.lock:
+                    if coll.n_live == 0:
+                        for r in reqs:
+                            r.result = []
+                        continue
+                    index = coll.index
+                    flts, fo = [], []
+                    for r in reqs:
+                        if r.flt is None:
+                            fo.append(-1)
+                            continue
+                        for i, f in enumerate(flts):
+                            if f is r.flt:
+                                fo.append(i)
+                                break
+                        else:
+                            fo.append(len(flts))
+                            flts.append(r.flt)
+                    any_sparse = any(r.sparse is not None for r in reqs)
+                    res = index.search_batch(
+                        np.stack([r.q for r in reqs]), [r.sparse for r in reqs] if any_sparse else None,
+                        filters=flts or None, filter_of=np.asarray(fo, np.int32) if flts else None,
+                        limit=limit, kprime=limit * 3 if any_sparse else limit,
+                        fusion=fusion if any_sparse else "dense", sparse_weight=weight)
+                    base = getattr(index, "row_base", 0)
+                    for i, r in enumerate(reqs):
+                        r.result = [_payload_to_chunk(coll.ids[row - base], coll.payload[row - base], score) for row, score in res.hits(i)]
+            except Exception as e:                  # every caller of the failed device call sees the error (reference: propagate)
+                for r in reqs:
+                    r.error = e
+            finally:
+                for r in reqs:
+                    r.done = True
+
+
 class _Collection:
     """Host half of one collection: ids, payloads and exact-match maps; owns the device index."""
 
@@ -137,6 +228,9 @@ class _Collection:
         self.by_url: dict[str, set[int]] = {}
         self.scopes: dict[tuple[str, str], int] = {}   # (folder_path, index_folder) -> scope id
         self.scope_list: list[tuple[str, str]] = []
+        self.scope_version = 0                 # bumped whenever a scope id is added: cached scope bitsets die with it
+        self.bits_cache: dict = {}             # caller's scope_key -> (scope_version, args, bits)
+        self.coalescer = _Coalescer(self)
         self.dirty = False                     # written since the last snapshot
         self.last_save = time.monotonic()
 
@@ -155,6 +249,7 @@ class _Collection:
             sid = len(self.scope_list)
             self.scopes[key] = sid
             self.scope_list.append(key)
+            self.scope_version += 1
         return sid
 
     def _map_add(self, m: dict, key, row: int):
@@ -288,6 +383,8 @@ class _Collection:
             self.by_file, self.by_folder, self.by_index_folder, self.by_url = {}, {}, {}, {}
             self.scope_list = [tuple(k) for k in st["scope_list"]]
             self.scopes = {k: i for i, k in enumerate(self.scope_list)}
+            self.scope_version += 1
+            self.bits_cache.clear()
             for r, pl in enumerate(payload):
                 if pl is None:
                     continue
@@ -546,6 +643,7 @@ class VectorStoreService:
         date_start: int | None = None,
         date_end: int | None = None,
         date_field: str | None = None,
+        scope_key=None,
     ) -> engine.Filter | None:
         """Evaluate the folder clauses over the scope dictionary and return the device filter.
 
@@ -555,7 +653,17 @@ class VectorStoreService:
         Returns None when no clause applies (reference :525-530)."""
         coll = self._coll
         bits = None
-        if folder_filter or include_folders or exclude_folders or exclude_index_folders:
+        cached = None
+        if scope_key is not None:
+            # The caller (mcp_server.py:420-462) re-derives the same folder lists from SQLite for every query of a
+            # (user, project); with a key that changes whenever those settings change, the folded bitset is reused
+            # until a new scope (folder) appears in the collection.
+            cached = coll.bits_cache.get(scope_key)
+            if cached is not None and cached[0] != coll.scope_version:
+                cached = None
+        if cached is not None:
+            bits = cached[1]
+        elif folder_filter or include_folders or exclude_folders or exclude_index_folders:
             inc = set(include_folders) if include_folders else None
             exc = set(exclude_folders) if exclude_folders else ()
             dis = set(exclude_index_folders) if exclude_index_folders else ()
@@ -567,6 +675,10 @@ class VectorStoreService:
                           and fp not in exc and ifp not in dis)
                     if ok:
                         bits[sid >> 5] |= np.uint32(1 << (sid & 31))
+                if scope_key is not None:
+                    if len(coll.bits_cache) >= 256:
+                        coll.bits_cache.pop(next(iter(coll.bits_cache)))
+                    coll.bits_cache[scope_key] = (coll.scope_version, bits)
         ts_field, lo, hi = engine.TS_NONE, engine.TS_MIN, engine.TS_MAX
         if date_start is not None or date_end is not None:
             field_map = {"created": engine.TS_CREATED, "modified": engine.TS_MODIFIED}
@@ -600,15 +712,47 @@ class VectorStoreService:
         date_start: int | None = None,
         date_end: int | None = None,
         date_field: str | None = None,
+        scope_key=None,
     ) -> list[StoredChunk]:
         """Dense or hybrid (dense + sparse) retrieval (reference :560-697).
 
         Hybrid iff ``sparse_query`` has indices and the collection has the sparse vector: both
         branches fetch limit*3 candidates under the same filter and are fused (min-max weighted
-        sum by default).  Otherwise dense-only with ``limit``."""
-        return self.search_batch(
-            [query_embedding], limit, folder_filter, include_folders, exclude_folders, exclude_index_folders,
-            [sparse_query], sparse_weight, date_start, date_end, date_field)[0]
+        sum by default).  Otherwise dense-only with ``limit``.
+
+        Additive: ``scope_key`` (any hashable, e.g. ``(user_id, project_id, settings_version)``) lets the
+        folded folder bitset be cached across calls.  Concurrent callers are coalesced into one device
+        batch (``_Coalescer``)."""
+        self.client
+        coll = self._coll
+        search_filter = self._build_filter(
+            folder_filter, include_folders, exclude_folders, exclude_index_folders,
+            date_start=date_start, date_end=date_end, date_field=date_field, scope_key=scope_key)
+        q = np.asarray(query_embedding, dtype=np.float32)
+        if q.ndim != 1 or q.shape[0] != self.dimension:
+            raise ValueError(f"Vector dimension error: expected {self.dimension}, got {q.shape[-1] if q.ndim else 0}")
+        if not np.isfinite(q).all():
+            raise ValueError("Query vector must not contain NaN or inf")
+        sparse = None
+        if sparse_query and self._has_sparse:                  # reference :599-601
+            indices, values = sparse_query
+            if len(indices):
+                sparse = (indices, values)
+        return coll.coalescer.submit(_Request(q, sparse, search_filter, limit, self.fusion, sparse_weight))
+
+    def _hybrid_search(self, query_embedding, sparse_query, limit=10, search_filter=None, sparse_weight=0.1):
+        """Reference :621-697 (private there, no external callers): hybrid search with a prepared filter."""
+        return self._coll.coalescer.submit(_Request(np.asarray(query_embedding, dtype=np.float32), sparse_query, search_filter,
+                                                   limit, self.fusion, sparse_weight))
+
+    def _result_to_chunk(self, result) -> StoredChunk:
+        """Reference :532-558: anything with .id / .payload / .score (a qdrant ScoredPoint there)."""
+        return _payload_to_chunk(result.id, result.payload, getattr(result, "score", None))
+
+    def coalescing_stats(self) -> dict:
+        """Device batches formed out of concurrent single-query searches so far."""
+        c = self._coll.coalescer
+        return {"batches": c.batches, "requests": c.requests, "mean_batch": (c.requests / c.batches) if c.batches else None}
 
     def search_batch(
         self,
