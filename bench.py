@@ -566,10 +566,11 @@ def main():
     dom_name = names[dom]
     # the roofline is quoted on ONE launch: the dominant kernel's launch over the largest segment
     frac_rows = big_rows / max(1, rows_local)
-    if dom_name in ("dense", "sparse") and big[0 if dom_name == "dense" else 1] > 0:
-        launch_ms = float(big[0 if dom_name == "dense" else 1] / n_prof)
-        launch_bytes = (alg["dense"] / passes if dom_name == "dense" else alg["sparse"]) * frac_rows
-    else:
+    if dom_name == "dense" and big[0] > 0:
+        launch_ms = float(big[0] / n_prof)
+        launch_bytes = alg["dense"] / passes * frac_rows
+    else:                                               # (the sparse chain runs in posting stages over the whole index:
+        # its figure is the whole chain of a batch against the whole algorithmic byte count)
         launch_ms, launch_bytes = float(per_batch[dom]), alg[dom_name]
     achieved = launch_bytes / (launch_ms / 1e3) / 1e9 if launch_ms > 0 else 0.0
     tensor_bound = dense_path == 2 and B / passes > 250      # past the ridge (252 flop/B): the query-tiled kernel runs
@@ -585,8 +586,8 @@ def main():
     tf_launch = (dense_flops * frac_rows / (big[0] / n_prof / 1e3) / 1e12) if big[0] > 0 else None
     tensor_bound = tensor_bound and dom_name == "dense"
     roofline = {"kernel": kname[dom_name],
-                "launch": "largest segment: %d of %d rows%s" % (
-                    big_rows, rows_local, "" if dom_name != "dense" else ", one of %d pass(es)" % passes),
+                "launch": ("largest segment: %d of %d rows, one of %d pass(es)" % (big_rows, rows_local, passes)) if dom_name == "dense"
+                          else "all launches of the phase in one batch",
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind}, burst copy)", "traffic": traffic, "traffic_capture": traffic_src,
                 "algorithmic_bytes_per_launch": launch_bytes, "kernel_ms_per_launch": launch_ms,

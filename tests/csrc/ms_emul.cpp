@@ -13,7 +13,7 @@ extern "C" int ms_emul_segment(
     const int64_t* sp_indptr, const uint32_t* sp_term, const float* sp_val,
     uint32_t nt, const uint32_t* q_term, const double* q_weight, const double* q_ub, const int32_t* q_hidx,
     const uint32_t* q_plo, const uint32_t* q_phi, const uint32_t* mask, float tau,
-    uint32_t seg_row0, uint32_t seg_row1, uint32_t n_rows, uint32_t chunk, uint32_t budget_pct,
+    uint32_t seg_row0, uint32_t seg_row1, uint32_t n_rows, uint32_t chunk, uint32_t budget_pct, uint64_t stage_lo, uint64_t stage_hi,
     uint32_t* out_rows, float* out_scores, uint32_t max_out, uint64_t* stats /* [4]: essential postings, units, n_ess, lookups-unused */)
 {
     if (nt == 0 || nt > VB_MS_MAX_TERMS) return -1;
@@ -27,23 +27,24 @@ extern "C" int ms_emul_segment(
         const uint32_t hi = seg_row1 >= n_rows ? q_phi[j] : vb_ms_lower_bound(post_row, q_plo[j], q_phi[j], seg_row1);
         if (s.slo[j] != lo || s.shi[j] != hi) return -4;
     }
-    for (uint32_t j = 0; j < nt; ++j) vb_ms_plan_partition(s, j, nt, (double)tau, budget_pct);
-    std::vector<uint32_t> pos(nt);
-    uint32_t n_ess = 0;
-    for (uint32_t j = 0; j < nt; ++j) { pos[j] = vb_ms_plan_position(s, j, nt, n_ess); s.ub_pos[pos[j]] = s.ub[j]; }
+    for (uint32_t j = 0; j < nt; ++j) vb_ms_plan_position(s, j, nt);
+    { std::vector<uint32_t> p(s.term_at, s.term_at + nt); std::sort(p.begin(), p.end()); for (uint32_t i = 0; i < nt; ++i) if (p[i] != i) return -2; }
     std::vector<VbMsRec> rec(nt);
     std::vector<uint32_t> units(nt + 1, 0);
-    for (uint32_t j = 0; j < nt; ++j) {
+    uint32_t n_ess = 0;
+    bool seen_ne = false;
+    for (uint32_t i = 0; i < nt; ++i) {
+        const VbMsPos ps = vb_ms_plan_pos(s, i, nt, (double)tau, budget_pct, stage_lo, stage_hi);
+        if (ps.essential) { if (seen_ne) return -5; ++n_ess; } else seen_ne = true;      // NE must be a suffix
+        const uint32_t t = s.term_at[i];
         VbMsRec r;
-        r.slo = s.slo[j]; r.shi = s.shi[j]; r.w = q_weight[j]; r.suf = vb_ms_plan_suffix(s, pos[j], nt);
-        r.hidx = q_hidx ? q_hidx[j] : -1; r.tab = q_tab[j]; r.shift = q_shift[j]; r.plo = q_plo[j]; r.phi = q_phi[j]; r.pad = 0;
-        rec[pos[j]] = r;
-        units[pos[j]] = s.ne[j] ? 0u : (s.len[j] + chunk - 1u) / chunk;
+        r.slo = s.slo[t] + ps.w0; r.shi = s.slo[t] + ps.w1; r.w = q_weight[t]; r.suf = ps.suf;
+        r.hidx = q_hidx ? q_hidx[t] : -1; r.tab = q_tab[t]; r.shift = q_shift[t]; r.plo = q_plo[t]; r.phi = q_phi[t]; r.pad = 0;
+        rec[i] = r;
+        units[i] = (ps.w1 - ps.w0 + chunk - 1u) / chunk;
     }
     { uint32_t run = 0; for (uint32_t i = 0; i <= nt; ++i) { const uint32_t c = i < nt ? units[i] : 0u; units[i] = run; run += c; } }
     const uint32_t total = units[nt];
-    // sanity: positions are a permutation
-    { std::vector<uint32_t> p(pos); std::sort(p.begin(), p.end()); for (uint32_t i = 0; i < nt; ++i) if (p[i] != i) return -2; }
     // ---- score (vb_ms_score_kernel) ----
     std::vector<double> w(nt), suf(nt);
     std::vector<int32_t> hidx(nt);

@@ -822,3 +822,64 @@ def test_incremental_upserts_and_deletes_interleaved(world):
     want = cc.search_batch(Q, SP, None, None, limit=10, kprime=30, fusion=1)
     check(got, want, B, 2e-5, "after optimize")
     ix.close()
+
+
+@pytest.mark.parametrize("dim", [768, 1024])
+def test_query_tiled_gemm_at_model_dimensions_against_oracle(dim):
+    """K2T (the query-tiled tcgen05 kernel) at the dimensions the north_star names (768 = e5-base-v2, 1024), B = 1024,
+    limit 100 (k' = 300), all four epilogue mask modes, hybrid on a corpus >> k'.  The oracle scores a 96-query
+    subset per mode (the dense oracle is O(B x n x d) on the CPU); the other queries are held to the size-independent
+    properties (sorted, unique rows, pass their filter)."""
+    from voitta_rag_b200 import engine
+    rng = np.random.RandomState(dim)
+    n, B, limit = 150_000, 1024, 100
+    cents = rng.randn(256, dim).astype(np.float32)
+    dense = _data.bf16_round(cents[rng.randint(0, 256, size=n)] + 0.7 * rng.randn(n, dim).astype(np.float32))
+    vocab = np.unique(rng.randint(1, 2**31 - 1, size=8000).astype(np.int64))[:4000]
+    p = 1.0 / np.arange(1, len(vocab) + 1) ** 1.07; p /= p.sum()
+    L = 10
+    picks = np.sort(rng.choice(len(vocab), size=(n, L), p=p), axis=1)
+    rows_terms = [np.unique(vocab[picks[r]]) for r in range(n)]
+    indptr = np.zeros(n + 1, np.int64); np.cumsum([len(t) for t in rows_terms], out=indptr[1:])
+    terms = np.concatenate(rows_terms).astype(np.uint32)
+    vals = (0.5 + 1.5 * rng.rand(len(terms))).astype(np.float32)
+    scope = rng.randint(0, 64, size=n).astype(np.uint32)
+    modified = rng.randint(1420070400, 1767225600, size=n).astype(np.int64)
+    ix = engine.Index(dim)
+    ix.upsert(dense, (indptr, terms, vals), scope, None, modified)
+    cc = oracle_c.CorpusC(dense, (indptr, terms, vals), scope, None, modified)
+    qrows = rng.randint(0, n, size=B)
+    Q = _data.bf16_round(dense[qrows] + 0.4 * rng.randn(B, dim).astype(np.float32))
+    SP = [(list(dict.fromkeys(rows_terms[r][:5].tolist() + [int(vocab[rng.randint(0, len(vocab))])])), None) for r in qrows]
+    SP = [(t, [1.0] * len(t)) for t, _ in SP]
+
+    def flt(k):
+        bits = np.zeros(2, np.uint32); bits[0] = np.uint32((0x9E3779B1 * (k + 1)) & 0xFFFFFFFF); bits[1] = np.uint32((0x85EBCA77 * (k + 3)) & 0xFFFFFFFF)
+        return (bits, 2, 1420070400 + k * 1_000_000, 1767225600)
+    modes = {"none": (None, None), "uniform": ([flt(0)], np.zeros(B, np.int32)),
+             "few": ([flt(k) for k in range(8)], (np.arange(B) % 8).astype(np.int32)),
+             "many": ([flt(k) for k in range(40)], (np.arange(B) % 40).astype(np.int32))}
+    sub = np.sort(rng.choice(B, size=96, replace=False))
+    coded = {"scope": scope, "created": None, "modified": modified}
+    for name, (fl, fo) in modes.items():
+        gf = None if fl is None else [engine.Filter(*f) for f in fl]
+        got = ix.search_batch(Q, SP, gf, fo, limit=limit, fusion="rrf", branches=True)
+        st = ix.stats()
+        assert st["last_dense_path"] == 2 and st["last_dense_passes"] == 1, st          # one corpus pass for 1024 queries = K2T
+        assert got.dense_rows.shape[1] == 300
+        want = cc.search_batch(Q[sub], [SP[i] for i in sub], fl, None if fo is None else fo[sub], limit=limit, kprime=300, fusion=2)
+        for j, i in enumerate(sub):
+            wd = [(int(want["dense_rows"][j, t]), float(want["dense_scores"][j, t])) for t in range(want["dense_counts"][j])]
+            assert_same_ranking(got.branch(i, "dense"), wd, rel_tol=1e-3, abs_tol=1e-3, what=f"K2T d{dim} {name} dense q{i}")
+            ws = [(int(want["sparse_rows"][j, t]), float(want["sparse_scores"][j, t])) for t in range(want["sparse_counts"][j])]
+            assert_same_ranking(got.branch(i, "sparse"), ws, rel_tol=0.0, what=f"K2T d{dim} {name} sparse q{i}")
+            fusion_bit_exact(got, i, limit, "rrf", 0.1)
+        for i in range(0, B, 37):                     # properties for queries the oracle did not score
+            rows = [r for r, _ in got.branch(i, "dense")]
+            sc = [s_ for _, s_ in got.branch(i, "dense")]
+            assert len(set(rows)) == len(rows) and all(sc[t] >= sc[t + 1] for t in range(len(sc) - 1))
+            if fl is not None:
+                f = fl[int(fo[i])]
+                ok = ((f[0][scope[rows] >> 5] >> (scope[rows] & 31)) & 1).astype(bool) & (modified[rows] >= f[2]) & (modified[rows] <= f[3])
+                assert ok.all(), f"K2T d{dim} {name} q{i}: a returned row fails its filter"
+    ix.close()

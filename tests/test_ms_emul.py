@@ -29,7 +29,7 @@ def emul(tmp_path_factory):
     vp = C.c_void_p
     lib.ms_emul_segment.restype = C.c_int
     lib.ms_emul_segment.argtypes = ([vp, vp, vp, C.c_uint32, vp, vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, C.c_float]
-                                    + [C.c_uint32] * 5 + [vp, vp, C.c_uint32, vp])
+                                    + [C.c_uint32] * 5 + [C.c_uint64, C.c_uint64, vp, vp, C.c_uint32, vp])
     return lib
 
 
@@ -86,7 +86,7 @@ def _reference(ix, q_idx, q_w, r0, r1, mask_bits, tau):
     return out
 
 
-def _run(emul, ix, q_idx, q_w, r0, r1, mask_bits, tau, chunk, budget, use_tabs=True, use_heavy=True):
+def _run(emul, ix, q_idx, q_w, r0, r1, mask_bits, tau, chunk, budget, use_tabs=True, use_heavy=True, stage=(0, 2 ** 63)):
     nt = len(q_idx)
     qt = np.asarray(q_idx, np.uint32)
     qw = np.asarray(q_w, np.float64)
@@ -106,7 +106,7 @@ def _run(emul, ix, q_idx, q_w, r0, r1, mask_bits, tau, chunk, budget, use_tabs=T
     rc = emul.ms_emul_segment(p(ix["post_row"]), p(ix["post_val"]), p(ix["hv"]), ix["stride"], p(ix["term_tab"]), p(qtab), p(qshift),
                               p(ix["indptr"]), p(ix["terms"]),
                               p(ix["vals"]), nt, p(qt), p(qw), p(ub), p(hidx), p(plo), p(phi), p(mask_bits), C.c_float(tau),
-                              r0, r1, ix["n"], chunk, budget, p(out_rows), p(out_scores), cap, p(stats))
+                              r0, r1, ix["n"], chunk, budget, stage[0], stage[1], p(out_rows), p(out_scores), cap, p(stats))
     assert rc >= 0, f"emulation failed rc={rc}"
     got = {}
     for r, s in zip(out_rows[:rc], out_scores[:rc]):
@@ -197,3 +197,39 @@ def test_stress_values(emul, index):
             got, _ = _run(emul, ix, q_idx, w, 0, n, None, np.float32(tau), 512, 100)
             assert got.keys() == want.keys()
             assert all(got[r].tobytes() == want[r].tobytes() for r in want)
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_stages_score_every_row_once_and_reach_the_exact_top_k(emul, index, seed):
+    """The staged flow of a search: stage 0 scores the first postings (position order) with no threshold, each later
+    stage 32x more under the threshold the earlier stages produced.  No row may be reported twice across stages and
+    the top-k of everything reported must be the oracle's top-k, scores bit for bit."""
+    ix = index
+    n = ix["n"]
+    q_idx, w = _query(ix, 700 + seed, (3, 12) if seed % 2 else (12, 40))
+    rng = np.random.RandomState(seed)
+    mask_bits = rng.randint(0, 2 ** 32, size=(n + 31) // 32, dtype=np.uint64).astype(np.uint32) if seed % 2 else None
+    full = _reference(ix, q_idx, w, 0, n, mask_bits, -np.inf)
+    for k in (5, 30):
+        best = {}
+        tau = np.float32(-np.inf)
+        lo, hi = 0, 16 * k
+        dfm = {int(t): int(d) for t, d in zip(ix["uniq"], ix["df"])}
+        total = sum(dfm.get(t, 0) for t in q_idx)
+        n_stage = 0
+        while lo < total:
+            got, _ = _run(emul, ix, q_idx, w, 0, n, mask_bits, tau, 512, 100, stage=(lo, hi))
+            for r, s_ in got.items():
+                assert r not in best, f"row {r} scored in two stages"
+                assert s_ > tau
+                best[r] = s_
+            ranked = sorted(best.values(), reverse=True)
+            if len(ranked) >= k:
+                tau = np.float32(max(tau, ranked[k - 1]))
+            lo, hi = hi, hi * 32
+            n_stage += 1
+        assert n_stage >= 2
+        want = sorted(((s_, -r) for r, s_ in full.items()), reverse=True)[:k]
+        have = sorted(((s_, -r) for r, s_ in best.items()), reverse=True)[:k]
+        assert [(float(a), b) for a, b in have] == [(float(a), b) for a, b in want]
+        assert all(best[-b].tobytes() == full[-b].tobytes() for _, b in want)

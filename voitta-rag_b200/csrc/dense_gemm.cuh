@@ -337,28 +337,27 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                             }
                         }
                     }
-                } else if (__any_sync(0xffffffffu, m != 0u)) {
-                    // rare path: exact comparison on the scaled score, then reserve slots for all
-                    // survivors of the chunk first (predicated atomics issued back to back, so their L2
-                    // round trips overlap), then store the keys
-                    if (!split) {
+                } else {
+                    // rare path, entered per COLUMN: mm has a bit for every column in which some row of the warp
+                    // survived the pre-threshold.  Early segments (weak thresholds) hit this for most chunks, and
+                    // running all 16 columns' atomics for one survivor made those segments epilogue-bound; the
+                    // warp-uniform test skips the columns without survivors.  Slots of a column's survivors are
+                    // reserved (predicated atomic), then the key is stored.
+                    const uint32_t mm = __reduce_or_sync(0xffffffffu, m);
+                    if (mm != 0u) {
+                        const uint32_t sub = blockIdx.x & a.lists.sub_mask;
 #pragma unroll
-                        for (uint32_t j = 0; j < 16u; ++j)
-                            if (((m >> j) & 1u) && !(final_score(j) > tex_s[c0 + j])) m &= ~(1u << j);
-                    }
-                    uint32_t slot[16];
-                    const uint32_t sub = blockIdx.x & a.lists.sub_mask;
-#pragma unroll
-                    for (uint32_t j = 0; j < 16u; ++j) {
-                        asm volatile(
-                            "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p atom.global.add.u32 %0, [%1], 1;\n\t}"
-                            : "=r"(slot[j]) : "l"(a.lists.cnt + (size_t)(a.q_begin + c0 + j) * VB_SUB + sub), "r"((m >> j) & 1u) : "memory");
-                    }
-#pragma unroll
-                    for (uint32_t j = 0; j < 16u; ++j) {
-                        if (((m >> j) & 1u) && slot[j] < a.lists.sub_cap)
-                            a.lists.cand[(size_t)(a.q_begin + c0 + j) * a.lists.cap + (size_t)sub * a.lists.sub_cap + slot[j]] =
-                                vb_pack_key(final_score(j), a.row_base + row);
+                        for (uint32_t j = 0; j < 16u; ++j) {
+                            if (!((mm >> j) & 1u)) continue;                     // warp-uniform
+                            const float fs = final_score(j);
+                            const bool keep = ((m >> j) & 1u) && (split || fs > tex_s[c0 + j]);   // exact comparison on the scaled score
+                            if (keep) {
+                                const uint32_t slot = atomicAdd(a.lists.cnt + (size_t)(a.q_begin + c0 + j) * VB_SUB + sub, 1u);
+                                if (slot < a.lists.sub_cap)
+                                    a.lists.cand[(size_t)(a.q_begin + c0 + j) * a.lists.cap + (size_t)sub * a.lists.sub_cap + slot] =
+                                        vb_pack_key(fs, a.row_base + row);
+                            }
+                        }
                     }
                 }
             };
@@ -595,24 +594,22 @@ vb_dense_gemm_tiled_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
                                 }
                             }
                         }
-                    } else if (__any_sync(0xffffffffu, m != 0u)) {
-                        // rare path: exact comparison on the scaled score, reserve slots for all survivors
-                        // of the chunk, then store the keys
+                    } else {
+                        // rare path per COLUMN (see the resident kernel): only columns with a survivor somewhere in the
+                        // warp run the exact comparison, the slot reservation and the store
+                        const uint32_t mm = __reduce_or_sync(0xffffffffu, m);
+                        if (mm != 0u) {
 #pragma unroll
-                        for (uint32_t jj = 0; jj < 16u; ++jj)
-                            if (((m >> jj) & 1u) && !(__uint_as_float(v[jj]) * invn * qs_s[qoff + c0 + jj] > tex_s[qoff + c0 + jj])) m &= ~(1u << jj);
-                        uint32_t slot[16];
-#pragma unroll
-                        for (uint32_t jj = 0; jj < 16u; ++jj) {
-                            asm volatile(
-                                "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p atom.global.add.u32 %0, [%1], 1;\n\t}"
-                                : "=r"(slot[jj]) : "l"(a.lists.cnt + (size_t)(a.q_begin + qoff + c0 + jj) * VB_SUB + sub), "r"((m >> jj) & 1u) : "memory");
-                        }
-#pragma unroll
-                        for (uint32_t jj = 0; jj < 16u; ++jj) {
-                            if (((m >> jj) & 1u) && slot[jj] < a.lists.sub_cap)
-                                a.lists.cand[(size_t)(a.q_begin + qoff + c0 + jj) * a.lists.cap + (size_t)sub * a.lists.sub_cap + slot[jj]] =
-                                    vb_pack_key(__uint_as_float(v[jj]) * invn * qs_s[qoff + c0 + jj], a.row_base + row);
+                            for (uint32_t jj = 0; jj < 16u; ++jj) {
+                                if (!((mm >> jj) & 1u)) continue;                 // warp-uniform
+                                const float fs = __uint_as_float(v[jj]) * invn * qs_s[qoff + c0 + jj];
+                                if (((m >> jj) & 1u) && fs > tex_s[qoff + c0 + jj]) {
+                                    const uint32_t slot = atomicAdd(a.lists.cnt + (size_t)(a.q_begin + qoff + c0 + jj) * VB_SUB + sub, 1u);
+                                    if (slot < a.lists.sub_cap)
+                                        a.lists.cand[(size_t)(a.q_begin + qoff + c0 + jj) * a.lists.cap + (size_t)sub * a.lists.sub_cap + slot] =
+                                            vb_pack_key(fs, a.row_base + row);
+                                }
+                            }
                         }
                     }
                 };

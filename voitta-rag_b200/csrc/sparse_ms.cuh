@@ -11,17 +11,22 @@
 // only terms whose ub sum stays below tau cannot enter the list (MaxScore).  Measured on the
 // benchmark corpora (tools/proto_maxscore.py) the ESSENTIAL postings are 2-4 % of the posting mass.
 //
-// Per segment, per query (vb_ms_plan_kernel, one CTA per query):
-//   * terms sorted by ub; the longest prefix with sum(ub) < tau is NON-essential (NE);
-//   * essential terms ordered by ascending posting count (rarest first) = "ownership" order, then
-//     the NE terms by descending ub; suf[i] = sum of ub over positions > i;
-//   * every essential term's postings of the segment are cut into work units of `chunk` postings.
+// Per launch, per query (vb_ms_plan_kernel, one CTA per query):
+//   * terms ordered by DESCENDING ub = "position" order (independent of tau); suf[i] = sum of ub over the
+//     positions after i; the lowest-ub suffix whose ub sum stays below tau is NON-essential (NE);
+//   * the query's postings are numbered in position order, and a search runs in STAGES over the whole index:
+//     stage 0 scores the first ~16 k' of them (the highest-ub terms' postings: the rows most likely to be the
+//     best) with no threshold at all, every later stage 32x more under the threshold the stages before it
+//     established (vb_compact_kernel between stages).  A row is scored exactly once, by the posting of its
+//     earliest position ("owner"), in the stage that posting falls in.  (The safe mode runs the same kernels
+//     per row segment instead.)
+//   * every essential term's postings of the stage are cut into work units of `chunk` postings.
 // vb_ms_score_kernel (persistent, dynamic unit counter): one thread per essential posting (e, row):
 //   1. filter bit of the row;
 //   2. w_e*v + suf[e] < tau  =>  drop (even with every later term present at its maximum the row
 //      cannot reach tau; a frequent essential term's postings almost all end here: 8 bytes, one
 //      fma, one compare);
-//   3. ownership: if an EARLIER essential term also occurs in the row, that posting owns the row;
+//   3. ownership: if a term at an EARLIER position also occurs in the row, that term's posting owns the row;
 //   4. the remaining terms are looked up in position order, stopping as soon as partial + suf[i] < tau.
 //      A lookup is one load from the term's dense column (frequent terms) or one 8-byte load from the
 //      term's BUCKET TABLE — built with the index: tab[b] = first posting with row >= b << shift, buckets
@@ -63,10 +68,10 @@
 
 #define VB_MS_MAX_TERMS 256u
 
-// One query term in POSITION order (essential terms by ascending posting count, then NE by descending ub).
+// One query term in POSITION order (descending ub; the non-essential terms are a suffix).
 #define VB_MS_NO_TAB 0xffffffffu
 struct VbMsRec {
-    uint32_t slo, shi;      // the term's postings inside the segment: [slo, shi) of post_row / post_val
+    uint32_t slo, shi;      // the term's postings this launch scores: [slo, shi) of post_row / post_val (empty for NE terms)
     double w;               // idf-scaled query weight
     double suf;             // sum of ub over the positions after this one
     int32_t hidx;           // dense column of a frequent term, -1 = none
@@ -183,18 +188,22 @@ VB_HD bool vb_ms_score_posting(const VbMsCtx& c, uint32_t pe, uint32_t row, floa
     return score > c.tau;
 }
 
-// ---- plan: one query, `nt` terms; thread j owns term j.  Phases are separated by barriers on the device
-// and by loops in the CPU emulation. --------------------------------------------------------------------
+// ---- plan: one query, `nt` terms.  Thread j owns term j in phases 1-2 and POSITION j in phase 3; phases are
+// separated by barriers on the device and by loops in the CPU emulation. ---------------------------------
+// Position order = descending ub (ties: term index).  It does not depend on tau, so it is the same in every
+// stage of a search, and the non-essential terms (the lowest-ub terms whose ub sum stays below tau) are always
+// a SUFFIX of it.  That makes row ownership stable: the posting of the earliest position that contains a row
+// owns it in every stage, whatever the thresholds were when the other stages ran.
 struct VbMsPlanShared {
     double ub[VB_MS_MAX_TERMS];         // term order
     double ub_pos[VB_MS_MAX_TERMS];     // position order
-    uint32_t len[VB_MS_MAX_TERMS];      // postings inside the segment, term order
-    uint32_t slo[VB_MS_MAX_TERMS], shi[VB_MS_MAX_TERMS];
-    uint8_t ne[VB_MS_MAX_TERMS];
+    uint32_t len[VB_MS_MAX_TERMS];      // postings inside the row range, term order
+    uint32_t len_pos[VB_MS_MAX_TERMS];  // position order
+    uint32_t slo[VB_MS_MAX_TERMS], shi[VB_MS_MAX_TERMS];    // term order
+    uint32_t term_at[VB_MS_MAX_TERMS];  // position -> term
     uint32_t n_ess;
 };
 
-// phase 1: segment range and upper bound of term j
 // first posting of a term with row >= target: the bucket table leaves a handful of search steps
 VB_HD uint32_t vb_ms_seg_bound(const uint32_t* post_row, const uint32_t* term_tab, uint32_t plo, uint32_t phi,
                                uint32_t tab, uint32_t shift, uint32_t n_rows, uint32_t target) {
@@ -204,6 +213,7 @@ VB_HD uint32_t vb_ms_seg_bound(const uint32_t* post_row, const uint32_t* term_ta
     return vb_ms_lower_bound(post_row, lo, hi, target);
 }
 
+// phase 1: row-range slice and upper bound of term j
 VB_HD void vb_ms_plan_load(VbMsPlanShared& s, uint32_t j, const uint32_t* post_row, const uint32_t* term_tab, uint32_t plo, uint32_t phi,
                            uint32_t tab, uint32_t shift, uint32_t n_rows, uint32_t seg_row0, uint32_t seg_row1, double ub) {
     const uint32_t lo = vb_ms_seg_bound(post_row, term_tab, plo, phi, tab, shift, n_rows, seg_row0);
@@ -211,38 +221,36 @@ VB_HD void vb_ms_plan_load(VbMsPlanShared& s, uint32_t j, const uint32_t* post_r
     s.slo[j] = lo; s.shi[j] = hi; s.len[j] = hi - lo; s.ub[j] = ub;
 }
 
-// phase 2: MaxScore partition.  Sorting by ub, the longest prefix whose ub sum stays below
-// budget_pct % of tau is non-essential.  The 2e-9 margin dwarfs the rounding of the sums (<= 256 terms).
-VB_HD void vb_ms_plan_partition(VbMsPlanShared& s, uint32_t j, uint32_t nt, double tau_d, uint32_t budget_pct) {
-    const double ub = s.ub[j];
-    double cum = 0.0;
-    for (uint32_t i = 0; i < nt; ++i) {
-        const double u = s.ub[i];
-        if (u < ub || (u == ub && i <= j)) cum += u;
-    }
-    const bool ok = budget_pct != 0u && tau_d > 0.0 && tau_d < INFINITY;
-    const uint32_t pct = budget_pct < 100u ? budget_pct : 100u;
-    s.ne[j] = (ok && ub < INFINITY && cum < tau_d * (0.01 * (double)pct) * (1.0 - 2e-9)) ? 1 : 0;
+// phase 2: position of term j in descending-ub order
+VB_HD void vb_ms_plan_position(VbMsPlanShared& s, uint32_t j, uint32_t nt) {
+    uint32_t before = 0;
+    for (uint32_t i = 0; i < nt; ++i) before += (s.ub[i] > s.ub[j] || (s.ub[i] == s.ub[j] && i < j)) ? 1u : 0u;
+    s.ub_pos[before] = s.ub[j];
+    s.len_pos[before] = s.len[j];
+    s.term_at[before] = j;
 }
 
-// phase 3: position of term j — essential terms by (posting count, index) ascending, then NE by ub descending
-VB_HD uint32_t vb_ms_plan_position(const VbMsPlanShared& s, uint32_t j, uint32_t nt, uint32_t& n_ess_out) {
-    uint32_t n_ess = 0, before = 0;
-    for (uint32_t i = 0; i < nt; ++i) {
-        if (!s.ne[i]) ++n_ess;
-        if (s.ne[i] != s.ne[j] || i == j) continue;
-        if (!s.ne[j]) before += (s.len[i] < s.len[j] || (s.len[i] == s.len[j] && i < j)) ? 1u : 0u;
-        else before += (s.ub[i] > s.ub[j] || (s.ub[i] == s.ub[j] && i < j)) ? 1u : 0u;
-    }
-    n_ess_out = n_ess;
-    return s.ne[j] ? n_ess + before : before;
-}
-
-// phase 5: suffix sum of ub after position i (summed from the tail: small values first)
-VB_HD double vb_ms_plan_suffix(const VbMsPlanShared& s, uint32_t i, uint32_t nt) {
+// phase 3, position i: the ub sum after it (summed from the tail: small values first), whether it is essential
+// under tau (the 2e-9 margin dwarfs the rounding of sums of <= 256 terms), and the part of its postings this
+// STAGE scores: the query's postings are numbered in position order, a stage takes numbers [stage_lo, stage_hi).
+struct VbMsPos { double suf; uint32_t w0, w1; bool essential; };
+VB_HD VbMsPos vb_ms_plan_pos(const VbMsPlanShared& s, uint32_t i, uint32_t nt, double tau_d, uint32_t budget_pct,
+                             uint64_t stage_lo, uint64_t stage_hi) {
+    VbMsPos r;
     double acc = 0.0;
     for (uint32_t k = nt; k-- > i + 1u;) acc += s.ub_pos[k];
-    return acc;
+    r.suf = acc;
+    const bool ok = budget_pct != 0u && tau_d > 0.0 && tau_d < INFINITY;
+    const uint32_t pct = budget_pct < 100u ? budget_pct : 100u;
+    r.essential = !(ok && acc + s.ub_pos[i] < tau_d * (0.01 * (double)pct) * (1.0 - 2e-9));
+    uint64_t cum = 0;
+    for (uint32_t k = 0; k < i; ++k) cum += s.len_pos[k];
+    const uint64_t len = s.len_pos[i];
+    const uint64_t lo = stage_lo > cum ? (stage_lo - cum < len ? stage_lo - cum : len) : 0;
+    const uint64_t hi = stage_hi > cum ? (stage_hi - cum < len ? stage_hi - cum : len) : 0;
+    r.w0 = (uint32_t)lo;
+    r.w1 = r.essential ? (uint32_t)hi : (uint32_t)lo;
+    return r;
 }
 
 VB_HD double vb_ms_tau_lo(double tau_d) { return tau_d > 0.0 ? tau_d * (1.0 - 1e-9) : tau_d * (1.0 + 1e-9); }
@@ -288,7 +296,8 @@ struct VbMsPlanArgs {
     uint32_t* unit_prefix;       // [n_qterms + 1] out: exclusive prefix of the work units per (query, position)
     uint32_t* counters;          // [0] blocks done (self-resetting), [1] next work unit (reset here), [2] total units
     uint32_t n_queries, n_qterms;
-    uint32_t seg_row0, seg_row1;
+    uint32_t seg_row0, seg_row1; // rows this launch covers
+    uint64_t stage_lo, stage_hi; // the query's postings (numbered in position order) this launch scores
     uint32_t chunk;              // postings per work unit
     uint32_t budget_pct;         // MaxScore budget in % of tau (100 = the full MaxScore partition)
 };
@@ -306,27 +315,24 @@ vb_ms_plan_kernel(const VbMsPlanArgs a)
     if (active) {
         if (j < nt) vb_ms_plan_load(s, j, a.post_row, a.term_tab, a.q_plo[t_lo + j], a.q_phi[t_lo + j], a.q_tab[t_lo + j], a.q_shift[t_lo + j],
                                     a.n_rows, a.seg_row0, a.seg_row1, a.q_ub[t_lo + j]);
+        if (j == 0) s.n_ess = 0u;
         __syncthreads();
-        if (j < nt) vb_ms_plan_partition(s, j, nt, tau_d, a.budget_pct);
+        if (j < nt) vb_ms_plan_position(s, j, nt);
         __syncthreads();
-        uint32_t n_ess = 0, pos = 0;
-        if (j < nt) {
-            pos = vb_ms_plan_position(s, j, nt, n_ess);
-            s.ub_pos[pos] = s.ub[j];
-            if (j == 0) s.n_ess = n_ess;
-        }
-        __syncthreads();
-        if (j < nt) {
-            // thread j now finishes POSITION pos (it knows term j's data); the suffix needs every ub_pos
+        if (j < nt) {                                          // thread j now finishes POSITION j
+            const VbMsPos ps = vb_ms_plan_pos(s, j, nt, tau_d, a.budget_pct, a.stage_lo, a.stage_hi);
+            const uint32_t t = s.term_at[j];
             VbMsRec r;
-            r.slo = s.slo[j]; r.shi = s.shi[j]; r.w = a.q_weight[t_lo + j];
-            r.suf = vb_ms_plan_suffix(s, pos, nt);
-            r.hidx = a.q_hidx ? a.q_hidx[t_lo + j] : -1;
-            r.tab = a.q_tab[t_lo + j]; r.shift = a.q_shift[t_lo + j];
-            r.plo = a.q_plo[t_lo + j]; r.phi = a.q_phi[t_lo + j]; r.pad = 0u;
-            a.rec[t_lo + pos] = r;
-            a.unit_prefix[t_lo + pos] = s.ne[j] ? 0u : (s.len[j] + a.chunk - 1u) / a.chunk;   // counts; scanned below
+            r.slo = s.slo[t] + ps.w0; r.shi = s.slo[t] + ps.w1; r.w = a.q_weight[t_lo + t];
+            r.suf = ps.suf;
+            r.hidx = a.q_hidx ? a.q_hidx[t_lo + t] : -1;
+            r.tab = a.q_tab[t_lo + t]; r.shift = a.q_shift[t_lo + t];
+            r.plo = a.q_plo[t_lo + t]; r.phi = a.q_phi[t_lo + t]; r.pad = 0u;
+            a.rec[t_lo + j] = r;
+            a.unit_prefix[t_lo + j] = (ps.w1 - ps.w0 + a.chunk - 1u) / a.chunk;   // counts; scanned below
+            if (ps.essential) atomicAdd(&s.n_ess, 1u);
         }
+        __syncthreads();
         if (j == 0) { VbMsQuery qi; qi.tau_lo = vb_ms_tau_lo(tau_d); qi.n_ess = s.n_ess; qi.active = 1u; a.qinfo[q] = qi; }
     } else {
         for (uint32_t i = j; i < nt; i += blockDim.x) a.unit_prefix[t_lo + i] = 0u;

@@ -107,6 +107,7 @@ struct Batch {
     const double* d_uw = nullptr;              // [n_qterms] weight
     uint32_t n_uterms = 0;
     uint32_t base_rows = 0;                    // rows covered by the inverted index when the batch was staged
+    uint64_t ms_max_post = 0;                  // most postings any K3M query's terms hold (how many stages a search needs)
     const int32_t* d_maskof = nullptr;
     const int32_t* d_mode = nullptr;
     const VbFilterDev* d_filters = nullptr;
@@ -171,6 +172,8 @@ struct vb_index {
     int64_t opt_sparse_ms = 1;             // 1: posting-driven MaxScore kernel (K3M) outside the direct segment; 0: K3 everywhere
     int64_t opt_ms_budget = 100;           // K3M: non-essential ub budget in % of tau (100 = full MaxScore partition)
     int64_t opt_ms_chunk = 0;              // K3M: postings per work unit (0 = auto)
+    int64_t opt_ms_staged = 1;             // K3M: 1 = posting stages over the whole index, 0 = once per row segment
+    int64_t opt_ms_stage_ratio = 32;       // K3M: growth of the posting stages
     int64_t opt_delta_max = 0;             // rows the delta may hold before vb_upsert merges it into the index (0 = auto)
     int64_t opt_ms_max_terms = 16;         // K3M scores queries of at most this many terms; longer ones accumulate (K3)
 
@@ -218,11 +221,15 @@ static void dev_free(vb_index* h, DevBuf& b) {
 // ------------------------------------------------------------------------------------------------
 // tiny utility kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void vb_init_lists_kernel(float* tau, uint32_t* cnt, uint32_t* overflow, uint32_t n, uint32_t cnt0) {
+// cnt0: slots of the first (direct) segment at the front of every list.  `no_direct` (optional, one flag per
+// query): the sparse list of such a query is never written by a direct segment (K3M scores it in stages).
+__global__ void vb_init_lists_kernel(float* tau, uint32_t* cnt, uint32_t* overflow, uint32_t n, uint32_t cnt0,
+                                     const uint8_t* no_direct, uint32_t n_queries) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         tau[i] = -INFINITY; overflow[i] = 0u;
-        for (uint32_t s = 0; s < VB_SUB; ++s) cnt[i * VB_SUB + s] = s == 0 ? cnt0 : 0u;
+        const uint32_t c0 = (no_direct != nullptr && i >= n_queries && no_direct[i - n_queries]) ? 0u : cnt0;
+        for (uint32_t s = 0; s < VB_SUB; ++s) cnt[i * VB_SUB + s] = s == 0 ? c0 : 0u;
     }
 }
 __global__ void vb_fill_i64_kernel(int64_t* p, uint64_t n, int64_t v) {
@@ -309,6 +316,8 @@ extern "C" int vb_create(int32_t dim, int32_t device, uint64_t capacity_hint, ui
     if (const char* env = getenv("VB200_SPARSE_MS")) h->opt_sparse_ms = atoi(env);
     if (const char* env = getenv("VB200_MS_BUDGET")) h->opt_ms_budget = atoi(env);
     if (const char* env = getenv("VB200_MS_CHUNK")) h->opt_ms_chunk = atoi(env);
+    if (const char* env = getenv("VB200_MS_STAGED")) h->opt_ms_staged = atoi(env);
+    if (const char* env = getenv("VB200_MS_STAGE_RATIO")) h->opt_ms_stage_ratio = atoi(env);
     if (const char* env = getenv("VB200_MS_MAX_TERMS")) h->opt_ms_max_terms = atoi(env);
     *out = h;
     return 0;
@@ -348,6 +357,8 @@ extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
     else if (k == "sparse_ms") h->opt_sparse_ms = value;           // 0: K3 in every segment (no MaxScore kernel)
     else if (k == "ms_budget") h->opt_ms_budget = value;           // K3M non-essential budget in % of tau
     else if (k == "ms_chunk") h->opt_ms_chunk = value;             // K3M postings per work unit (0 auto)
+    else if (k == "ms_staged") h->opt_ms_staged = value;           // K3M: posting stages (1) or row segments (0)
+    else if (k == "ms_stage_ratio") h->opt_ms_stage_ratio = value; // K3M: growth of the posting stages
     else if (k == "delta_max") h->opt_delta_max = value;           // delta rows that trigger a merge (0 = max(16384, base/32))
     else if (k == "ms_max_terms") h->opt_ms_max_terms = value;     // K3M only for queries of at most this many terms
     else if (k == "sparse_prune_force") h->opt_sparse_prune_force = value;   // 1: prune in every non-direct segment (tests)
@@ -991,7 +1002,12 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
             // time before MaxScore can drop it, while K3 accumulates all of them without lookups.
             const bool ms = all_pos && need_corpus && h->sparse_nonneg && h->opt_sparse_ms && hi > lo && hi - lo <= h->opt_ms_max_terms;
             qms[i] = ms ? 1 : 0;
-            if (ms) b.any_ms = true;
+            if (ms) {
+                b.any_ms = true;
+                uint64_t tot = 0;
+                for (size_t t = q_first; t < weight.size(); ++t) tot += qphi[t] - qplo[t];
+                b.ms_max_post = std::max(b.ms_max_post, tot);
+            }
             else if (hi > lo) { b.any_old = true; oldq.push_back(i); }
             for (size_t t = q_first; t < weight.size(); ++t) {
                 if (!relax) qhidx[t] = -1;
@@ -1177,8 +1193,9 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
 
 // direct_rows > 0: the first segment stores its keys at fixed slots [0, direct_rows) of every
 // list (no atomics); slots nobody writes (masked rows, rows without postings) must read as empty.
-static int init_lists(vb_index* h, const Batch& b, uint32_t direct_rows) {
-    vb_init_lists_kernel<<<(b.n_lists + 255) / 256, 256, 0, h->stream>>>(b.tau, b.cnt, b.overflow, b.n_lists, direct_rows);
+static int init_lists(vb_index* h, const Batch& b, uint32_t direct_rows, bool ms_staged = false) {
+    vb_init_lists_kernel<<<(b.n_lists + 255) / 256, 256, 0, h->stream>>>(b.tau, b.cnt, b.overflow, b.n_lists, direct_rows,
+                                                                          ms_staged ? b.d_qms : nullptr, b.B);
     CKK("vb_init_lists_kernel");
     ++h->stats.last_launches;
     if (direct_rows)
@@ -1248,7 +1265,10 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     const VbLists L = make_lists(h, b, safe_mode);
     // the first segment writes its keys to fixed slots at the front of the list (no atomics)
     const uint32_t direct_rows = bounds[1] <= h->cand_cap ? bounds[1] : 0u;
-    if (phase != 2) TRY(init_lists(h, b, direct_rows));
+    // (sparse lists of queries K3M scores in stages get no direct slots: same condition as ms_staged below)
+    const bool ms_staged_lists = b.any_sparse && h->nnz_live > 0 && b.n_qterms > 0 && h->base_rows > 0 && b.any_ms && h->opt_sparse_ms &&
+                                 !safe_mode && h->opt_ms_staged;
+    if (phase != 2) TRY(init_lists(h, b, direct_rows, ms_staged_lists));
     // dense path choice
     int path = (int)h->opt_dense_path;
     if (path == 0) path = vb_gemm_supported(h->d_pad, b.B) && b.B >= 2 ? 2 : 1;
@@ -1320,46 +1340,67 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         prof_end(h, ps, sd);
         return 0;
     };
-    // Which sparse kernel scores which query: the direct segment and the queries whose products may be negative
-    // stay on K3 (block x query CTAs); everything else goes to K3M, the posting-driven MaxScore kernel.
+    // Which sparse kernel scores which query.  Queries whose products are all >= 0 and that are not too long go to
+    // K3M, the posting-driven MaxScore kernel; the others (and everything when K3M is off) stay on K3 (block x query
+    // CTAs over the row segments, first segment direct).
+    //   normal mode: K3M runs in STAGES over the whole index (sparse_ms.cuh): stage 0 scores the first ms_p0
+    //                postings of every query in descending-ub order with no threshold, each later stage 32x more;
+    //   safe mode:   K3M runs once per (small) row segment, like K3, so that no list can overflow.
     const bool ms_on = do_sparse && b.any_ms && h->opt_sparse_ms;
+    const bool ms_staged = ms_on && !safe_mode && h->opt_ms_staged;
     const uint32_t ms_chunk = h->opt_ms_chunk > 0 ? (uint32_t)align_up((size_t)h->opt_ms_chunk, VB_MS_U * VB_MS_THREADS)
                                                    : 512u;
+    auto ms_launch = [&](uint32_t r0, uint32_t r1, uint64_t stage_lo, uint64_t stage_hi) -> int {
+        VbMsPlanArgs pa{};
+        pa.post_row = h->post_row.as<uint32_t>(); pa.term_tab = h->term_tab.as<uint32_t>(); pa.q_tab = b.d_qtab; pa.q_shift = b.d_qshift;
+        pa.n_rows = (uint32_t)h->base_rows; pa.q_indptr = b.d_qindptr; pa.q_weight = b.d_qweight; pa.q_ub = b.d_qub;
+        pa.q_hidx = b.any_heavy ? b.d_qhidx : nullptr; pa.q_plo = b.d_qplo; pa.q_phi = b.d_qphi; pa.q_ms = b.d_qms; pa.tau = b.tau;
+        pa.rec = h->ms_rec.as<VbMsRec>(); pa.qinfo = h->ms_q.as<VbMsQuery>(); pa.unit_prefix = h->ms_units.as<uint32_t>();
+        pa.counters = h->ms_counters.as<uint32_t>(); pa.n_queries = b.B; pa.n_qterms = b.n_qterms;
+        pa.seg_row0 = r0; pa.seg_row1 = r1; pa.stage_lo = stage_lo; pa.stage_hi = stage_hi;
+        pa.chunk = ms_chunk; pa.budget_pct = (uint32_t)std::max<int64_t>(0, h->opt_ms_budget);
+        vb_ms_plan_kernel<<<b.B, 256, 0, ss>>>(pa);
+        CKK("vb_ms_plan_kernel");
+        VbMsArgs a{};
+        a.post_row = h->post_row.as<uint32_t>(); a.post_val = h->post_val.as<float>();
+        a.heavy_vals = h->heavy_vals.as<float>(); a.heavy_stride = h->heavy_stride;
+        a.sp_indptr = h->sp_indptr.as<int64_t>(); a.sp_term = h->sp_term.as<uint32_t>(); a.sp_val = h->sp_val.as<float>();
+        a.q_indptr = b.d_qindptr; a.q_term = b.d_qterm; a.q_weight = b.d_qweight; a.slot_q = b.d_slotq;
+        a.rec = h->ms_rec.as<VbMsRec>(); a.qinfo = h->ms_q.as<VbMsQuery>(); a.unit_prefix = h->ms_units.as<uint32_t>();
+        a.counters = h->ms_counters.as<uint32_t>(); a.term_tab = h->term_tab.as<uint32_t>();
+        a.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; a.mask_of = b.use_mask ? b.d_maskof : nullptr;
+        a.tau = b.tau; a.lists = L; a.mask_words = b.mask_words; a.n_qterms = b.n_qterms; a.n_queries = b.B;
+        a.row_base = (uint32_t)h->row_base; a.chunk = ms_chunk; a.nt_max = b.nt_max;
+        // persistent grid: enough CTAs to fill the machine, never more than the largest possible unit count
+        const uint64_t span = std::min<uint64_t>(r1 - r0, stage_hi - stage_lo);
+        const uint64_t max_units = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)h->nnz_live / ms_chunk + b.n_qterms, (uint64_t)b.n_qterms * (span / ms_chunk + 1)));
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)h->sm_count * 16u, max_units);
+        vb_ms_score_kernel<<<grid, VB_MS_THREADS, vb_ms_smem_bytes(b.nt_max), ss>>>(a);
+        CKK("vb_ms_score_kernel");
+        h->stats.last_launches += 2;
+        return 0;
+    };
+    auto sparse_compact = [&](uint32_t lim0) -> int {
+        const int ps = prof_begin(h, PH_SELECT, ss);
+        vb_compact_kernel<<<b.B, VB_COMPACT_THREADS, 0, ss>>>(L, b.tau, b.overflow, b.k, b.B, lim0);
+        CKK("vb_compact_kernel");
+        ++h->stats.last_launches;
+        prof_end(h, ps, ss);
+        return 0;
+    };
+    // K3 scores: every sparse query if K3M is off; else the queries K3M does not take (b.d_oldq) — plus, in the
+    // segment flow, everybody in the direct segment
     auto sparse_segment = [&](uint32_t r0, uint32_t r1_all, uint32_t direct, bool big) -> int {
         const uint32_t r1 = std::min(r1_all, nb);               // the index stops at nb
-        if (!direct && !(do_sparse && r0 < r1)) return 0;       // nothing scored, nothing to compact
-        if (do_sparse && r0 < r1) {
+        const bool rows_here = do_sparse && r0 < r1;
+        const bool ms_here = rows_here && ms_on && !ms_staged && !direct;
+        const bool k3_sel = ms_on && (ms_staged || !direct);    // K3 restricted to the queries K3M does not take
+        const bool k3_here = rows_here && (!k3_sel || b.any_old);
+        if (!direct && !ms_here && !k3_here) return 0;          // nothing scored, nothing to compact
+        if (ms_here || k3_here) {
             const int pi = prof_begin(h, PH_SPARSE | (big ? PH_BIG : 0), ss);
-            const bool use_ms = ms_on && !direct;
-            if (use_ms) {
-                VbMsPlanArgs pa{};
-                pa.post_row = h->post_row.as<uint32_t>(); pa.term_tab = h->term_tab.as<uint32_t>(); pa.q_tab = b.d_qtab; pa.q_shift = b.d_qshift;
-                pa.n_rows = (uint32_t)h->base_rows; pa.q_indptr = b.d_qindptr; pa.q_weight = b.d_qweight; pa.q_ub = b.d_qub;
-                pa.q_hidx = b.any_heavy ? b.d_qhidx : nullptr; pa.q_plo = b.d_qplo; pa.q_phi = b.d_qphi; pa.q_ms = b.d_qms; pa.tau = b.tau;
-                pa.rec = h->ms_rec.as<VbMsRec>(); pa.qinfo = h->ms_q.as<VbMsQuery>(); pa.unit_prefix = h->ms_units.as<uint32_t>();
-                pa.counters = h->ms_counters.as<uint32_t>(); pa.n_queries = b.B; pa.n_qterms = b.n_qterms;
-                pa.seg_row0 = r0; pa.seg_row1 = r1; pa.chunk = ms_chunk; pa.budget_pct = (uint32_t)std::max<int64_t>(0, h->opt_ms_budget);
-                vb_ms_plan_kernel<<<b.B, 256, 0, ss>>>(pa);
-                CKK("vb_ms_plan_kernel");
-                VbMsArgs a{};
-                a.post_row = h->post_row.as<uint32_t>(); a.post_val = h->post_val.as<float>();
-                a.heavy_vals = h->heavy_vals.as<float>(); a.heavy_stride = h->heavy_stride;
-                a.sp_indptr = h->sp_indptr.as<int64_t>(); a.sp_term = h->sp_term.as<uint32_t>(); a.sp_val = h->sp_val.as<float>();
-                a.q_indptr = b.d_qindptr; a.q_term = b.d_qterm; a.q_weight = b.d_qweight; a.slot_q = b.d_slotq;
-                a.rec = h->ms_rec.as<VbMsRec>(); a.qinfo = h->ms_q.as<VbMsQuery>(); a.unit_prefix = h->ms_units.as<uint32_t>();
-                a.counters = h->ms_counters.as<uint32_t>(); a.term_tab = h->term_tab.as<uint32_t>();
-                a.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; a.mask_of = b.use_mask ? b.d_maskof : nullptr;
-                a.tau = b.tau; a.lists = L; a.mask_words = b.mask_words; a.n_qterms = b.n_qterms; a.n_queries = b.B;
-                a.row_base = (uint32_t)h->row_base; a.chunk = ms_chunk; a.nt_max = b.nt_max;
-                // persistent grid: enough CTAs to fill the machine, never more than the largest possible unit count
-                const uint64_t rows_seg = r1 - r0;
-                const uint64_t max_units = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)h->nnz_live / ms_chunk + b.n_qterms, (uint64_t)b.n_qterms * (rows_seg / ms_chunk + 1)));
-                const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)h->sm_count * 16u, max_units);
-                vb_ms_score_kernel<<<grid, VB_MS_THREADS, vb_ms_smem_bytes(b.nt_max), ss>>>(a);
-                CKK("vb_ms_score_kernel");
-                h->stats.last_launches += 2;
-            }
-            if (!use_ms || b.any_old) {
+            if (ms_here) TRY(ms_launch(r0, r1, 0ull, ~0ull));
+            if (k3_here) {
                 // which terms are essential under the thresholds this segment starts with
                 double* d_ubne = h->plan.as<double>();
                 uint8_t* d_ess = reinterpret_cast<uint8_t*>(d_ubne + b.B);
@@ -1382,7 +1423,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
                 a.n_qterms = b.n_qterms; a.nt_max = b.nt_max; a.blk_begin = r0 / VB_ROWS_PER_BLOCK; a.n_queries = b.B; a.n_rows = nb;
                 a.row_base = (uint32_t)h->row_base; a.direct = direct;
                 uint32_t n_q = b.B;
-                if (use_ms) { a.q_sel = b.d_oldq; a.n_sel = b.n_old; n_q = b.n_old; }   // the MaxScore kernel has the rest
+                if (k3_sel) { a.q_sel = b.d_oldq; a.n_sel = b.n_old; n_q = b.n_old; }   // the MaxScore kernel has the rest
                 { static const char* dbg = getenv("VB200_SPARSE_DEBUG"); a.debug = dbg ? (uint32_t)atoi(dbg) : 0u; }
                 const uint32_t nblk = (r1 - r0 + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK;
                 vb_sparse_kernel<<<nblk * n_q, VB_SPARSE_THREADS, vb_sparse_smem_bytes(b.nt_max), ss>>>(a);
@@ -1392,17 +1433,12 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
             prof_end(h, pi, ss);
         }
         // the sparse lists are compacted even without postings (first-segment slots -> empty lists)
-        const int ps = prof_begin(h, PH_SELECT, ss);
-        vb_compact_kernel<<<b.B, VB_COMPACT_THREADS, 0, ss>>>(L, b.tau, b.overflow, b.k, b.B, direct ? std::max(direct_rows, L.sub_cap) : L.sub_cap);
-        CKK("vb_compact_kernel");
-        ++h->stats.last_launches;
-        prof_end(h, ps, ss);
-        return 0;
+        return sparse_compact(direct ? std::max(direct_rows, L.sub_cap) : L.sub_cap);
     };
-    // fine (2048-row) slice table rows K3 will read: the direct segment only when K3M takes every other segment
-    const bool old_everywhere = do_sparse && (!ms_on || b.any_old);
-    const uint32_t fine_blocks = old_everywhere ? b.n_blocks
-                                                : std::min<uint32_t>(b.n_blocks, (direct_rows + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK);
+    // fine (2048-row) slice table rows K3 will read
+    const bool k3_all_segments = do_sparse && (!ms_on || b.any_old);
+    const uint32_t fine_blocks = k3_all_segments ? b.n_blocks
+                                 : (do_sparse && !ms_staged ? std::min<uint32_t>(b.n_blocks, (direct_rows + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK) : 0u);
     if (do_sparse) {
         const uint64_t total = (uint64_t)b.n_qterms * (fine_blocks + 1);
         TRY(dev_reserve(h, h->offs, std::max<uint64_t>(total, 1) * 4, false));
@@ -1425,9 +1461,27 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         if (ms_on) CK(cudaMemsetAsync(h->ms_counters.p, 0, 64, ss));
         prof_end(h, pi, ss);
     }
+    // K3M stages (normal mode): stage 0 in phases 0 and 1, the rest in phases 0 and 2
+    auto ms_stages = [&](bool first, bool rest) -> int {
+        const uint64_t p0 = std::max<uint64_t>(ms_chunk, std::min<uint64_t>(std::max<uint64_t>(16ull * b.k, 2048ull), h->cand_cap / 4));
+        uint64_t lo = 0, hi = p0;
+        for (uint32_t st = 0; lo < b.ms_max_post; ++st) {
+            const bool last = hi >= b.ms_max_post;
+            if (st == 0 ? first : rest) {
+                const int pi = prof_begin(h, PH_SPARSE | (last ? PH_BIG : 0), ss);
+                TRY(ms_launch(0u, nb, lo, last ? ~0ull : hi));
+                prof_end(h, pi, ss);
+                TRY(sparse_compact(L.sub_cap));
+            }
+            lo = hi;
+            hi = hi * (uint64_t)std::max<int64_t>(2, h->opt_ms_stage_ratio);
+        }
+        return 0;
+    };
     // enqueue the two chains interleaved so that neither stream starves on the host side
     const size_t n_seg = bounds.size() - 1;
     const size_t s_begin = phase == 2 ? 1 : 0, s_end = phase == 1 ? 1 : n_seg;
+    if (ms_staged) TRY(ms_stages(phase != 2, phase != 1));
     for (size_t s = s_begin; s < s_end; ++s) {
         const uint32_t direct = (s == 0 && direct_rows) ? 1u : 0u;
         const bool big = s + 1 == n_seg;
