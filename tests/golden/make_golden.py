@@ -129,10 +129,40 @@ def _install_stub(dim_holder):
                         "qdrant_client.http.models": models, "qdrant_client.http.exceptions": exc})
 
 
-def load_reference_vector_store(dim: int):
+def real_qdrant_available() -> bool:
+    """True if the REAL qdrant-client can be imported (from the environment or from baseline/_ref, where a
+    driver-provided reference install would land).  It is not part of this image; the probe runs every round."""
+    ref_dir = ROOT / "baseline" / "_ref"
+    if ref_dir.is_dir() and str(ref_dir) not in sys.path:
+        sys.path.insert(0, str(ref_dir))
+    mod = sys.modules.get("qdrant_client")
+    if mod is not None and getattr(mod, "__file__", None) is None:
+        return False                                   # our own stub is installed in this process
+    try:
+        return importlib.util.find_spec("qdrant_client") is not None
+    except Exception:
+        return False
+
+
+def _install_real():
+    """Route the reference's QdrantClient(host, port) to qdrant-client's local in-memory mode."""
+    import qdrant_client
+    real = qdrant_client.QdrantClient
+
+    def local_client(host=None, port=None, **kw):
+        return real(":memory:")
+
+    qdrant_client.QdrantClient = local_client
+
+
+def load_reference_vector_store(dim: int, real: bool = False):
     """Import /root/reference/src/voitta/services/vector_store.py without running the
-    package __init__ files (they import sqlalchemy/fastmcp/... which are absent)."""
-    _install_stub(dim)
+    package __init__ files (they import sqlalchemy/fastmcp/... which are absent).  ``real``: over the real
+    qdrant-client (local mode) instead of the stub that delegates to the oracle."""
+    if real:
+        _install_real()
+    else:
+        _install_stub(dim)
     voitta = types.ModuleType("voitta"); voitta.__path__ = [str(REF)]
     services = types.ModuleType("voitta.services"); services.__path__ = [str(REF / "services")]
     config = types.ModuleType("voitta.config")
@@ -312,7 +342,32 @@ def replay(store, ops, corpus, queries, meta_cls, row_of: dict):
     return outs
 
 
+def check_against_real_qdrant():
+    """Replay the scenario through the reference over the REAL qdrant-client and compare with the committed
+    golden file (generated over the oracle).  Any difference means the oracle's restatement of qdrant-client
+    is wrong: fail loudly.  Returns the number of operations compared."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    from _parity import assert_same_ranking
+    corpus, queries = build_inputs()
+    gold = json.loads((Path(__file__).resolve().parent / "voitta_cases.json").read_text())
+    ref = load_reference_vector_store(DIM, real=True)
+    store = ref.VectorStoreService()
+    outs = replay(store, gold["ops"], corpus, queries, ref.ChunkMetadata, {})
+    assert len(outs) == len(gold["outs"])
+    for i, (op, got, want) in enumerate(zip(gold["ops"], outs, gold["outs"])):
+        what = f"real qdrant-client vs oracle golden, op {i} {op}"
+        if op["op"] == "search":
+            assert_same_ranking(got, want, rel_tol=1e-5, abs_tol=2e-6, what=what)
+        else:
+            assert json.loads(json.dumps(got)) == want, what
+    return len(outs)
+
+
 def main():
+    if real_qdrant_available():
+        n = check_against_real_qdrant()
+        print(f"qdrant-client is installed: {n} golden operations re-checked against it — the oracle is PINNED")
+        return
     corpus, queries = build_inputs()
     ops = scenario(corpus, queries)
     ref = load_reference_vector_store(DIM)

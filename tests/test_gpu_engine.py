@@ -883,3 +883,34 @@ def test_query_tiled_gemm_at_model_dimensions_against_oracle(dim):
                 ok = ((f[0][scope[rows] >> 5] >> (scope[rows] & 31)) & 1).astype(bool) & (modified[rows] >= f[2]) & (modified[rows] <= f[3])
                 assert ok.all(), f"K2T d{dim} {name} q{i}: a returned row fails its filter"
     ix.close()
+
+
+def test_k1f_single_pass_equals_segmented_scan_and_oracle(world):
+    """K1F (one pass, per-CTA candidate buffers, thresholds shared through one global word) against K1 in row segments:
+    identical lists for B = 1..8, every filter, limits up to 100 (k' = 300), exact ties included; and against the oracle."""
+    ix, coded, eng = world["ix"], world["coded"], world["engine"]
+    qs = world["queries"]
+    ix.set_option("dense_path", 1)
+    try:
+        for B in (1, 3, 8):
+            Q = np.stack([q for q, _ in qs[:B]]); SP = [s for _, s in qs[:B]]
+            for fi, flt in enumerate(filters_for(coded)):
+                gf = None if flt is None else [eng.Filter(*flt)]
+                fo = None if flt is None else np.zeros(B, np.int32)
+                for limit in (10, 100):
+                    ix.set_option("k1f", 0)
+                    base = ix.search_batch(Q, SP, gf, fo, limit=limit, fusion="weighted", branches=True)
+                    ix.set_option("k1f", 1)
+                    fast = ix.search_batch(Q, SP, gf, fo, limit=limit, fusion="weighted", branches=True)
+                    for name in ("rows", "scores", "counts", "dense_rows", "dense_scores", "dense_counts", "sparse_rows", "sparse_scores", "sparse_counts"):
+                        assert np.array_equal(getattr(fast, name), getattr(base, name)), (B, fi, limit, name)
+            got, want = run_both(world, qs[:B], filters_for(coded)[1], 10, "rrf")
+            check(got, want, B, 1e-5, f"k1f B{B}")
+        # dense-only, duplicate rows (exact tie between rows 99 and 100) around the cut-off
+        q = world["corpus"]["dense"][99][None, :]
+        for k1f in (0, 1):
+            ix.set_option("k1f", k1f)
+            r = ix.search_batch(q, None, limit=2, fusion="dense", branches=True)
+            assert [int(x) for x in r.rows[0, :2]] == [99, 100], (k1f, r.rows)
+    finally:
+        ix.set_option("k1f", 1); ix.set_option("dense_path", 0)

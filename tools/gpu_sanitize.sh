@@ -1,0 +1,9 @@
+#!/bin/bash
+# compute-sanitizer over the small all-kernel workload; summaries land in gpurun_out/ (copy to profiles/).
+R=${1:-r02}
+mkdir -p gpurun_out
+timeout 600 python tools/sanitize_workload.py > gpurun_out/${R}_sanitize_plain.log 2>&1; echo "plain rc=$?"; tail -3 gpurun_out/${R}_sanitize_plain.log
+for TOOL in memcheck racecheck synccheck; do
+  timeout 1500 compute-sanitizer --tool $TOOL --print-limit 20 --error-exitcode 7 python tools/sanitize_workload.py > gpurun_out/${R}_sanitize_$TOOL.log 2>&1
+  echo "$TOOL rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|^ok |done|Error|hazard" gpurun_out/${R}_sanitize_$TOOL.log | tail -14
+done

@@ -171,3 +171,160 @@ vb_dense_scan_generic_kernel(const VbScanArgs a)
         }
     }
 }
+
+// ---- K1F — single-pass form of K1 for the batch sizes voitta actually issues (B = 1, mcp_server.py:474) -----
+// K1 above walks the rows in segments (2048, x128, ...) with a select kernel after each one, so that a global
+// threshold exists before the bulk of the rows is scanned: 2-3 scan launches + 2-3 selects + list set-up per
+// search, ~100 us of launch latency around ~15 us of HBM time at 100k rows.  K1F makes ONE pass: every CTA
+// keeps its own candidate buffer in shared memory and its own threshold (the score of its current k'-th best),
+// re-selecting whenever the buffer could overflow; CTAs publish their thresholds through one global word per
+// list (atomicMax on the order-preserving score encoding) — any CTA's k'-th best is a lower bound of the
+// global k'-th best — so late CTAs prune with the best threshold known anywhere.  At the end each CTA writes
+// its exact local top-k' to cand[list][cta * k' ...]; vb_compact_kernel merges G*k' -> k' (the same kernel
+// that merges per-shard lists).  Rows are dealt to CTAs in an interleaved order, so every CTA sees a
+// uniform sample of the corpus and its threshold converges after a few hundred rows.
+// Exactness: pruning keeps every row with score >= threshold (ties stay, rows arrive out of row order); the
+// final order (score desc, row asc) comes from the keys, which are unique.  Same arithmetic as K1.
+#define VB_K1F_THREADS 256
+#define VB_K1F_CAP 4096u           // candidate slots per CTA (32 KB of shared memory)
+#define VB_K1F_CHECK 8u            // iterations between buffer checks: 8 warps x 32 rows x 8 = 2048 appends at most
+
+struct VbScan1Args {
+    const uint4* rows;
+    const float* inv_norm;
+    const uint32_t* mask;
+    const int32_t* mask_of;
+    const float* q_hat;
+    uint32_t* gtau;             // [n_lists] shared threshold: vb_f32_ordered(score), 0 = none yet
+    uint64_t* cand;
+    uint32_t* cnt;
+    uint32_t cap, k, mask_words, chunks, n_rows, row_base;
+};
+
+// descending bitonic sort of P keys (power of two <= VB_K1F_CAP) by all threads of the CTA
+__device__ __forceinline__ void vb_k1f_sort(uint64_t* s, uint32_t P) {
+    for (uint32_t size = 2; size <= P; size <<= 1)
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (uint32_t t = threadIdx.x; t < (P >> 1); t += VB_K1F_THREADS) {
+                const uint32_t i = 2u * t - (t & (stride - 1u)), j = i + stride;
+                const bool up = (i & size) == 0u;
+                const uint64_t x = s[i], y = s[j];
+                if ((x < y) == up) { s[i] = y; s[j] = x; }
+            }
+        }
+    __syncthreads();
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(VB_K1F_THREADS)
+vb_dense_scan1_kernel(const VbScan1Args a)
+{
+    constexpr int ROWS = 4;
+    __shared__ uint64_t s_keys[VB_K1F_CAP];
+    __shared__ uint32_t s_cnt;
+    __shared__ float s_tau;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t q_idx = blockIdx.y, list = q_idx;
+    const uint32_t* mask = nullptr;
+    if (a.mask != nullptr && a.mask_of != nullptr) {
+        const int32_t f = a.mask_of[q_idx];
+        if (f >= 0) mask = a.mask + (size_t)f * a.mask_words;
+    }
+    float q[NCH][8];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const uint32_t ch = lane + 32u * c;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            q[c][e] = ch < a.chunks ? a.q_hat[(size_t)q_idx * a.chunks * 8u + ch * 8u + e] : 0.0f;
+    }
+    if (threadIdx.x == 0) { s_cnt = 0u; s_tau = -INFINITY; }
+    __syncthreads();
+    float tau = -INFINITY;
+    const uint32_t n_groups = (a.n_rows + 31u) >> 5;
+    const uint32_t stride = gridDim.x * (VB_K1F_THREADS / 32u);
+    const uint32_t n_iter = (n_groups + stride - 1u) / stride;          // the same for every warp of the grid: barriers are uniform
+    for (uint32_t it = 0; it < n_iter; ++it) {
+        const uint32_t g = it * stride + blockIdx.x * (VB_K1F_THREADS / 32u) + warp;
+        if (g < n_groups) {
+            uint32_t bits = mask ? mask[g] : 0xffffffffu;
+            const uint32_t row0 = g << 5;
+            if (row0 + 32u > a.n_rows) bits &= (1u << (a.n_rows - row0)) - 1u;
+            const float invn = (bits != 0u && row0 + lane < a.n_rows) ? a.inv_norm[row0 + lane] : 0.0f;
+            while (bits) {
+                int r[ROWS];
+#pragma unroll
+                for (int k = 0; k < ROWS; ++k) { r[k] = bits ? (__ffs(bits) - 1) : -1; bits &= bits - 1u; }
+                uint4 v[ROWS][NCH];
+#pragma unroll
+                for (int k = 0; k < ROWS; ++k)
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const uint32_t ch = lane + 32u * c;
+                        v[k][c] = (r[k] >= 0 && ch < a.chunks) ? vb_ldg_stream(a.rows + (size_t)(row0 + r[k]) * a.chunks + ch)
+                                                                : make_uint4(0u, 0u, 0u, 0u);
+                    }
+#pragma unroll
+                for (int k = 0; k < ROWS; ++k)
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) vb_keep_loaded(v[k][c]);
+                float acc[ROWS];
+#pragma unroll
+                for (int k = 0; k < ROWS; ++k) {
+                    acc[k] = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) acc[k] = vb_dot8(v[k][c], q[c], acc[k]);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int k = 0; k < ROWS; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+                float mine = acc[0];
+                int myr = r[0];
+#pragma unroll
+                for (int k = 1; k < ROWS; ++k)
+                    if (lane == (uint32_t)k) { mine = acc[k]; myr = r[k]; }
+                const float inv_r = __shfl_sync(0xffffffffu, invn, myr < 0 ? 0 : myr);
+                if (lane < (uint32_t)ROWS && myr >= 0) {
+                    const float s = mine * inv_r;
+                    if (s >= tau) {                                     // ties stay: rows do not arrive in row order
+                        const uint32_t slot = atomicAdd(&s_cnt, 1u);
+                        if (slot < VB_K1F_CAP) s_keys[slot] = vb_pack_key(s, a.row_base + row0 + (uint32_t)myr);
+                    }
+                }
+            }
+        }
+        // every VB_K1F_CHECK iterations (and after the last one): re-select if the next stretch could overflow
+        const bool last = it + 1u == n_iter;
+        if (last || (it + 1u) % VB_K1F_CHECK == 0u) {
+            __syncthreads();
+            const uint32_t c = s_cnt;                                   // <= CAP: a stretch appends at most CAP/2, selection leaves <= k <= CAP/2... see host check
+            if (last || c > VB_K1F_CAP - VB_K1F_CHECK * VB_K1F_THREADS) {
+                uint32_t P = 2;
+                while (P < c) P <<= 1;
+                for (uint32_t i = c + threadIdx.x; i < P; i += VB_K1F_THREADS) s_keys[i] = 0ull;
+                vb_k1f_sort(s_keys, P);
+                const uint32_t keep = c < a.k ? c : a.k;
+                if (threadIdx.x == 0) {
+                    s_cnt = keep;
+                    if (keep >= a.k) {
+                        const uint32_t o = (uint32_t)(s_keys[a.k - 1u] >> 32);      // ordered encoding of the k'-th score
+                        atomicMax(a.gtau + list, o);
+                    }
+                }
+            }
+            if (threadIdx.x == 0) {                                     // best threshold known anywhere
+                const uint32_t o = *reinterpret_cast<volatile uint32_t*>(a.gtau + list);
+                s_tau = o ? __uint_as_float(vb_ordered_f32(o)) : -INFINITY;
+            }
+            __syncthreads();
+            tau = s_tau;
+        }
+    }
+    // local top-k' -> this CTA's slice of the list (0 = empty slot)
+    const uint32_t keep = s_cnt;
+    uint64_t* out = a.cand + (size_t)list * a.cap + (size_t)blockIdx.x * a.k;
+    for (uint32_t i = threadIdx.x; i < a.k; i += VB_K1F_THREADS) out[i] = i < keep ? s_keys[i] : 0ull;
+    if (blockIdx.x == 0 && threadIdx.x < VB_SUB) a.cnt[list * VB_SUB + threadIdx.x] = threadIdx.x == 0 ? gridDim.x * a.k : 0u;
+}

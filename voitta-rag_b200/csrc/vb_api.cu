@@ -116,6 +116,7 @@ struct Batch {
     float* tau = nullptr;
     uint32_t* cnt = nullptr;
     uint32_t* overflow = nullptr;
+    uint32_t* gtau = nullptr;                  // [n_lists] K1F: threshold shared by the CTAs of one pass (ordered score, 0 = none)
     // fusion / output
     double w_sparse = 0.0;
     bool want_branches = false, valid = false, need_corpus = true;
@@ -172,6 +173,7 @@ struct vb_index {
     int64_t opt_sparse_ms = 1;             // 1: posting-driven MaxScore kernel (K3M) outside the direct segment; 0: K3 everywhere
     int64_t opt_ms_budget = 100;           // K3M: non-essential ub budget in % of tau (100 = full MaxScore partition)
     int64_t opt_ms_chunk = 0;              // K3M: postings per work unit (0 = auto)
+    int64_t opt_k1f = 1;                   // single-pass dense scan (K1F) for batches of at most VB_K1F_MAX_B queries
     int64_t opt_ms_staged = 1;             // K3M: 1 = posting stages over the whole index, 0 = once per row segment
     int64_t opt_ms_stage_ratio = 32;       // K3M: growth of the posting stages
     int64_t opt_delta_max = 0;             // rows the delta may hold before vb_upsert merges it into the index (0 = auto)
@@ -223,11 +225,11 @@ static void dev_free(vb_index* h, DevBuf& b) {
 // ------------------------------------------------------------------------------------------------
 // cnt0: slots of the first (direct) segment at the front of every list.  `no_direct` (optional, one flag per
 // query): the sparse list of such a query is never written by a direct segment (K3M scores it in stages).
-__global__ void vb_init_lists_kernel(float* tau, uint32_t* cnt, uint32_t* overflow, uint32_t n, uint32_t cnt0,
+__global__ void vb_init_lists_kernel(float* tau, uint32_t* cnt, uint32_t* overflow, uint32_t* gtau, uint32_t n, uint32_t cnt0,
                                      const uint8_t* no_direct, uint32_t n_queries) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
-        tau[i] = -INFINITY; overflow[i] = 0u;
+        tau[i] = -INFINITY; overflow[i] = 0u; gtau[i] = 0u;
         const uint32_t c0 = (no_direct != nullptr && i >= n_queries && no_direct[i - n_queries]) ? 0u : cnt0;
         for (uint32_t s = 0; s < VB_SUB; ++s) cnt[i * VB_SUB + s] = s == 0 ? c0 : 0u;
     }
@@ -254,6 +256,9 @@ __global__ void vb_find_tail_kernel(const uint64_t* keys, uint64_t n, uint64_t* 
 }
 
 static int g_delta_smem_max = 48 * 1024;
+
+#define VB_K1F_MAX_B 8u
+static uint32_t vb_k1f_grid(int sm_count) { return (uint32_t)sm_count * 2u; }
 
 static unsigned grid_for(uint64_t n, unsigned block, unsigned max_blocks = 148u * 16u) {
     uint64_t g = (n + block - 1) / block;
@@ -317,6 +322,7 @@ extern "C" int vb_create(int32_t dim, int32_t device, uint64_t capacity_hint, ui
     if (const char* env = getenv("VB200_MS_BUDGET")) h->opt_ms_budget = atoi(env);
     if (const char* env = getenv("VB200_MS_CHUNK")) h->opt_ms_chunk = atoi(env);
     if (const char* env = getenv("VB200_MS_STAGED")) h->opt_ms_staged = atoi(env);
+    if (const char* env = getenv("VB200_K1F")) h->opt_k1f = atoi(env);
     if (const char* env = getenv("VB200_MS_STAGE_RATIO")) h->opt_ms_stage_ratio = atoi(env);
     if (const char* env = getenv("VB200_MS_MAX_TERMS")) h->opt_ms_max_terms = atoi(env);
     *out = h;
@@ -357,6 +363,7 @@ extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
     else if (k == "sparse_ms") h->opt_sparse_ms = value;           // 0: K3 in every segment (no MaxScore kernel)
     else if (k == "ms_budget") h->opt_ms_budget = value;           // K3M non-essential budget in % of tau
     else if (k == "ms_chunk") h->opt_ms_chunk = value;             // K3M postings per work unit (0 auto)
+    else if (k == "k1f") h->opt_k1f = value;                       // 0: K1 in row segments even for single queries
     else if (k == "ms_staged") h->opt_ms_staged = value;           // K3M: posting stages (1) or row segments (0)
     else if (k == "ms_stage_ratio") h->opt_ms_stage_ratio = value; // K3M: growth of the posting stages
     else if (k == "delta_max") h->opt_delta_max = value;           // delta rows that trigger a merge (0 = max(16384, base/32))
@@ -1167,13 +1174,16 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     // keep 32 (list memory and compaction time scale with B); single queries are launch-latency bound and take
     // 128 (one segment fewer on 100k..10M rows; measured +7..25 % q/s at B = 1).
     b.seg_ratio = h->opt_seg_ratio > 0 ? (uint32_t)h->opt_seg_ratio : (b.B <= 4 ? 128u : 32u);
-    const uint32_t need_cap = std::max<uint32_t>(16384u, (uint32_t)align_up((size_t)2 * (size_t)b.seg_ratio * b.k, 4096));
+    uint32_t need_cap = std::max<uint32_t>(16384u, (uint32_t)align_up((size_t)2 * (size_t)b.seg_ratio * b.k, 4096));
+    // K1F (single-pass scan for tiny batches) leaves one local top-k' per CTA in the list before the merge
+    if (b.B <= VB_K1F_MAX_B) need_cap = std::max<uint32_t>(need_cap, (uint32_t)align_up((size_t)vb_k1f_grid(h->sm_count) * b.k, 4096));
     h->cand_cap = need_cap;
     TRY(dev_reserve(h, h->cand, (size_t)b.n_lists * need_cap * 8, false));
-    TRY(dev_reserve(h, h->lists, (size_t)b.n_lists * (8 + 4 * VB_SUB), false));
+    TRY(dev_reserve(h, h->lists, (size_t)b.n_lists * (12 + 4 * VB_SUB), false));
     b.tau = h->lists.as<float>();
     b.overflow = h->lists.as<uint32_t>() + b.n_lists;
     b.cnt = h->lists.as<uint32_t>() + 2 * (size_t)b.n_lists;      // [n_lists][VB_SUB]
+    b.gtau = h->lists.as<uint32_t>() + (2 + (size_t)VB_SUB) * b.n_lists;
     b.h2d_bytes = ar.off;
     h->stats.last_h2d_bytes = ar.off;
     // output block layout
@@ -1194,7 +1204,7 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
 // direct_rows > 0: the first segment stores its keys at fixed slots [0, direct_rows) of every
 // list (no atomics); slots nobody writes (masked rows, rows without postings) must read as empty.
 static int init_lists(vb_index* h, const Batch& b, uint32_t direct_rows, bool ms_staged = false) {
-    vb_init_lists_kernel<<<(b.n_lists + 255) / 256, 256, 0, h->stream>>>(b.tau, b.cnt, b.overflow, b.n_lists, direct_rows,
+    vb_init_lists_kernel<<<(b.n_lists + 255) / 256, 256, 0, h->stream>>>(b.tau, b.cnt, b.overflow, b.gtau, b.n_lists, direct_rows,
                                                                           ms_staged ? b.d_qms : nullptr, b.B);
     CKK("vb_init_lists_kernel");
     ++h->stats.last_launches;
@@ -1263,12 +1273,6 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     bounds.push_back(n);
     const bool safe_mode = safe || h->opt_safe_mode;
     const VbLists L = make_lists(h, b, safe_mode);
-    // the first segment writes its keys to fixed slots at the front of the list (no atomics)
-    const uint32_t direct_rows = bounds[1] <= h->cand_cap ? bounds[1] : 0u;
-    // (sparse lists of queries K3M scores in stages get no direct slots: same condition as ms_staged below)
-    const bool ms_staged_lists = b.any_sparse && h->nnz_live > 0 && b.n_qterms > 0 && h->base_rows > 0 && b.any_ms && h->opt_sparse_ms &&
-                                 !safe_mode && h->opt_ms_staged;
-    if (phase != 2) TRY(init_lists(h, b, direct_rows, ms_staged_lists));
     // dense path choice
     int path = (int)h->opt_dense_path;
     if (path == 0) path = vb_gemm_supported(h->d_pad, b.B) && b.B >= 2 ? 2 : 1;
@@ -1280,6 +1284,26 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     // (one corpus pass per 1024 queries)
     const bool tiled = path == 2 && b.B > plan.sub && !plan.split && h->opt_k2_tiled && vb_gemm_tiled_supported(h->d_pad);
     h->stats.last_dense_passes = path == 2 ? (tiled ? (b.B + VB_TILED_MAX_Q - 1) / VB_TILED_MAX_Q : (b.B + plan.sub - 1) / plan.sub) : b.B;
+    // sparse work: the inverted index covers rows [0, nb); rows appended since (the delta) are scored by K3D
+    const uint32_t nb = (uint32_t)std::min<uint64_t>(h->base_rows, n);
+    const bool do_sparse = b.any_sparse && h->nnz_live > 0 && b.n_qterms > 0 && nb > 0;
+    const bool do_delta = b.any_sparse && b.n_uterms > 0 && nb < n;
+    // Which sparse kernel scores which query.  Queries whose products are all >= 0 and that are not too long go to
+    // K3M, the posting-driven MaxScore kernel; the others (and everything when K3M is off) stay on K3 (block x query
+    // CTAs over the row segments, first segment direct).
+    //   normal mode: K3M runs in STAGES over the whole index (sparse_ms.cuh): stage 0 scores the first ms_p0
+    //                postings of every query in descending-ub order with no threshold, each later stage 32x more;
+    //   safe mode:   K3M runs once per (small) row segment, like K3, so that no list can overflow.
+    const bool ms_on = do_sparse && b.any_ms && h->opt_sparse_ms;
+    const bool ms_staged = ms_on && !safe_mode && h->opt_ms_staged;
+    // K1F: one pass over all rows for tiny batches (no segments, no direct slots)
+    const bool k1f = path == 1 && !safe_mode && h->opt_k1f && b.B <= VB_K1F_MAX_B && (h->d_pad / 8 + 31) / 32 <= 4 &&
+                     b.k <= 2048u && (uint64_t)vb_k1f_grid(h->sm_count) * b.k <= h->cand_cap;
+    // the first segment writes its keys to fixed slots at the front of the list (no atomics) — unless nobody runs
+    // a first segment: K1F scans in one pass, K3M in posting stages
+    const bool k3_direct = do_sparse && (!ms_staged || b.any_old);
+    const uint32_t direct_rows = (bounds[1] <= h->cand_cap && (!k1f || k3_direct)) ? bounds[1] : 0u;
+    if (phase != 2) TRY(init_lists(h, b, direct_rows, ms_staged));
     // query prep (fp32 unit queries for K1, packed bf16 operand for K2)
     TRY(dev_reserve(h, h->q_hat, (size_t)b.B * h->d_pad * 4, false));
     TRY(dev_reserve(h, h->q_bf16, (size_t)(2 * ((size_t)b.B + 256)) * h->d_pad * 2, false));
@@ -1305,17 +1329,40 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     // select of the sparse lists) are independent until the fusion, so they run on two streams:
     // the small kernels of one chain (selects, first segments, slice table) hide behind the big
     // kernels of the other.
-    // sparse work: the inverted index covers rows [0, nb); rows appended since (the delta) are scored by K3D
-    const uint32_t nb = (uint32_t)std::min<uint64_t>(h->base_rows, n);
-    const bool do_sparse = b.any_sparse && h->nnz_live > 0 && b.n_qterms > 0 && nb > 0;
-    const bool do_delta = b.any_sparse && b.n_uterms > 0 && nb < n;
     const bool two_streams = (do_sparse || do_delta) && h->opt_overlap;
     cudaStream_t sd = h->stream, ss = two_streams ? h->aux_stream : h->stream;
     if (two_streams) {
         CK(cudaEventRecord(h->ev_fork, sd));
         CK(cudaStreamWaitEvent(ss, h->ev_fork, 0));
     }
+    auto dense_single_pass = [&]() -> int {
+        const int pi = prof_begin(h, PH_DENSE | PH_BIG, sd);
+        VbScan1Args a{};
+        a.rows = h->rows.as<uint4>(); a.inv_norm = h->inv_norm.as<float>();
+        a.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; a.mask_of = b.use_mask ? b.d_maskof : nullptr;
+        a.q_hat = h->q_hat.as<float>(); a.gtau = b.gtau; a.cand = h->cand.as<uint64_t>(); a.cnt = b.cnt;
+        a.cap = h->cand_cap; a.k = b.k; a.mask_words = b.mask_words; a.chunks = (uint32_t)h->d_pad / 8; a.n_rows = n;
+        a.row_base = (uint32_t)h->row_base;
+        const dim3 grid(vb_k1f_grid(h->sm_count), b.B);
+        switch ((a.chunks + 31) / 32) {
+            case 1: vb_dense_scan1_kernel<1><<<grid, VB_K1F_THREADS, 0, sd>>>(a); break;
+            case 2: vb_dense_scan1_kernel<2><<<grid, VB_K1F_THREADS, 0, sd>>>(a); break;
+            case 3: vb_dense_scan1_kernel<3><<<grid, VB_K1F_THREADS, 0, sd>>>(a); break;
+            default: vb_dense_scan1_kernel<4><<<grid, VB_K1F_THREADS, 0, sd>>>(a); break;
+        }
+        CKK("vb_dense_scan1_kernel");
+        ++h->stats.last_launches;
+        prof_end(h, pi, sd);
+        const int ps = prof_begin(h, PH_SELECT, sd);
+        vb_compact_kernel<<<b.B, VB_COMPACT_THREADS, 0, sd>>>(make_lists(h, b, true), b.tau, b.overflow, b.k, 0u, h->cand_cap);
+        CKK("vb_compact_kernel");
+        ++h->stats.last_launches;
+        prof_end(h, ps, sd);
+        h->stats.last_big_rows = n;
+        return 0;
+    };
     auto dense_segment = [&](uint32_t r0, uint32_t r1, uint32_t direct, bool big) -> int {
+        if (k1f) return 0;                                      // the single pass covers every segment
         const int pi = prof_begin(h, PH_DENSE | (big ? PH_BIG : 0), sd);
         if (path == 2) {
             VbGemmLaunch g{};
@@ -1340,14 +1387,6 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         prof_end(h, ps, sd);
         return 0;
     };
-    // Which sparse kernel scores which query.  Queries whose products are all >= 0 and that are not too long go to
-    // K3M, the posting-driven MaxScore kernel; the others (and everything when K3M is off) stay on K3 (block x query
-    // CTAs over the row segments, first segment direct).
-    //   normal mode: K3M runs in STAGES over the whole index (sparse_ms.cuh): stage 0 scores the first ms_p0
-    //                postings of every query in descending-ub order with no threshold, each later stage 32x more;
-    //   safe mode:   K3M runs once per (small) row segment, like K3, so that no list can overflow.
-    const bool ms_on = do_sparse && b.any_ms && h->opt_sparse_ms;
-    const bool ms_staged = ms_on && !safe_mode && h->opt_ms_staged;
     const uint32_t ms_chunk = h->opt_ms_chunk > 0 ? (uint32_t)align_up((size_t)h->opt_ms_chunk, VB_MS_U * VB_MS_THREADS)
                                                    : 512u;
     auto ms_launch = [&](uint32_t r0, uint32_t r1, uint64_t stage_lo, uint64_t stage_hi) -> int {
@@ -1482,10 +1521,11 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     const size_t n_seg = bounds.size() - 1;
     const size_t s_begin = phase == 2 ? 1 : 0, s_end = phase == 1 ? 1 : n_seg;
     if (ms_staged) TRY(ms_stages(phase != 2, phase != 1));
+    if (k1f && phase != 1) TRY(dense_single_pass());
     for (size_t s = s_begin; s < s_end; ++s) {
         const uint32_t direct = (s == 0 && direct_rows) ? 1u : 0u;
         const bool big = s + 1 == n_seg;
-        if (big) h->stats.last_big_rows = bounds[s + 1] - bounds[s];
+        if (big && !k1f) h->stats.last_big_rows = bounds[s + 1] - bounds[s];
         TRY(dense_segment(bounds[s], bounds[s + 1], direct, big));
         TRY(sparse_segment(bounds[s], bounds[s + 1], direct, big));
     }
