@@ -542,8 +542,22 @@ def main():
         phase += [s_["last_mask_ms"], s_["last_dense_ms"], s_["last_sparse_ms"], s_["last_select_ms"], s_["last_fuse_ms"]]
         big += [s_["last_dense_big_ms"], s_["last_sparse_big_ms"]]
     big_rows = int(ix.stats()["last_big_rows"])
-    ix.set_option("profile", 0)
+    # one more batch with the two chains on their two streams and the events still on: the timeline shows how
+    # much of the sparse chain runs under the dense one
     ix.set_option("overlap", 1)
+    device_batch(stage(0))
+    tl = ix.timeline()
+    def _busy(name):
+        iv = sorted((a_, b_) for n_, _, a_, b_ in tl if n_ in name)
+        tot, end = 0.0, -1.0
+        for a_, b_ in iv:
+            tot += max(0.0, b_ - max(a_, end)); end = max(end, b_)
+        return tot
+    timeline = {"span_ms": max((b_ for *_, b_ in tl), default=0.0), "dense_chain_busy_ms": _busy(("dense", "mask")),
+                "sparse_chain_busy_ms": _busy(("sparse",)), "regions": len(tl),
+                "note": "CUDA-event start/end of every timed region on its own stream, two-stream schedule; "
+                        "span < dense + sparse busy time means the chains overlap"}
+    ix.set_option("profile", 0)
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------
     hbm_peak, tf_peak, peak_kind = peaks()
@@ -659,7 +673,7 @@ def main():
             "config": config_block(args, cfg, world, rows_local, B, qps, kprime),
             "dense_path": {1: "K1 GEMV scan", 2: "K2 tcgen05 GEMM"}.get(dense_path),
             "e2e": e2e, "e2e_api": api, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "parity_spot_check": parity, "ingest": ingest,
+            "cpu_baseline": cpu, "parity_spot_check": parity, "ingest": ingest, "timeline": timeline,
         }
         print(json.dumps(line))
     if world > 1:

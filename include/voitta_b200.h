@@ -198,6 +198,11 @@ int vb_fetch(vb_index* h, vb_result* out, int32_t* overflowed);
 int vb_set_option(vb_index* h, const char* key, int64_t value);
 
 int vb_get_stats(vb_index* h, vb_stats* out);
+/* With option "profile" = 1: the timed regions of the last fetched search as (phase | 8 if largest launch, start ms,
+ * end ms) triples relative to the start of the search, in launch order — phases 0 mask, 1 dense, 2 sparse, 3 select,
+ * 4 fuse.  Start / end come from CUDA events on the stream each region ran on, so the overlap of the dense and the
+ * sparse chain (two streams) can be read off.  *n = regions available; at most `cap` are written. */
+int vb_get_timeline(vb_index* h, double* out, uint32_t cap, uint32_t* n);
 int vb_sync(vb_index* h);
 
 /* Snapshot of everything the shard holds on the device: bf16 rows, inverse norms, filter columns,

@@ -914,3 +914,38 @@ def test_k1f_single_pass_equals_segmented_scan_and_oracle(world):
             assert [int(x) for x in r.rows[0, :2]] == [99, 100], (k1f, r.rows)
     finally:
         ix.set_option("k1f", 1); ix.set_option("dense_path", 0)
+
+
+def test_k3h_long_queries_equal_k3_and_oracle(world):
+    """Long queries (more than ms_max_terms terms) go to K3H, the hash-accumulate MaxScore kernel: the sparse lists must be
+    bit-identical to K3's (sparse_mh = 0) and to the oracle's, in a batch that also holds short (K3M) and mixed-sign (K3)
+    queries, under every filter, in safe mode and with a tiny ms_max_terms (every query long)."""
+    ix, coded, eng = world["ix"], world["coded"], world["engine"]
+    long_qs = _data.make_queries(seed=77, corpus=world["corpus"], nq=10, nnz=(17, 24))
+    assert max(len(s[0]) for _, s in long_qs) > 16
+    qs = long_qs + world["queries"][:4]
+    Q = np.stack([q for q, _ in qs]); SP = [s for _, s in qs]
+    SP[-1] = (SP[-1][0], [-1.0] + [1.0] * (len(SP[-1][0]) - 1))           # a query K3 must keep (negative weight)
+    B = len(qs)
+    try:
+        for fi, flt in enumerate(filters_for(coded)):
+            gf = None if flt is None else [eng.Filter(*flt)]
+            fo = None if flt is None else np.zeros(B, np.int32)
+            ix.set_option("sparse_mh", 0)
+            base = ix.search_batch(Q, SP, gf, fo, limit=20, fusion="rrf", branches=True)
+            ix.set_option("sparse_mh", 1)
+            for opts in ({}, {"ms_max_terms": 2}, {"safe_mode": 1}, {"seg_ratio": 2}, {"ms_staged": 0}, {"sparse_dense": 0}):
+                for k, v in opts.items():
+                    ix.set_option(k, v)
+                r = ix.search_batch(Q, SP, gf, fo, limit=20, fusion="rrf", branches=True)
+                for name in ("rows", "scores", "counts", "sparse_rows", "sparse_scores", "sparse_counts"):
+                    assert np.array_equal(getattr(r, name), getattr(base, name)), (fi, opts, name)
+                for k in opts:
+                    ix.set_option(k, {"ms_max_terms": 16, "safe_mode": 0, "seg_ratio": 0, "ms_staged": 1, "sparse_dense": 1}[k])
+            want = world["cc"].search_batch(Q, SP, None if flt is None else [flt], fo, limit=20, kprime=60, fusion=2)
+            for i in range(B):
+                ws = [(int(want["sparse_rows"][i, j]), float(want["sparse_scores"][i, j])) for j in range(want["sparse_counts"][i])]
+                assert_same_ranking(base.branch(i, "sparse"), ws, rel_tol=0.0, what=f"k3h f{fi} q{i}")
+    finally:
+        for k, v in {"sparse_mh": 1, "ms_max_terms": 16, "safe_mode": 0, "seg_ratio": 0, "ms_staged": 1, "sparse_dense": 1}.items():
+            ix.set_option(k, v)

@@ -30,6 +30,9 @@ def emul(tmp_path_factory):
     lib.ms_emul_segment.restype = C.c_int
     lib.ms_emul_segment.argtypes = ([vp, vp, vp, C.c_uint32, vp, vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, C.c_float]
                                     + [C.c_uint32] * 5 + [C.c_uint64, C.c_uint64, vp, vp, C.c_uint32, vp])
+    lib.mh_emul_segment.restype = C.c_int
+    lib.mh_emul_segment.argtypes = ([vp, vp, vp, C.c_uint32, vp, vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, C.c_float]
+                                    + [C.c_uint32] * 5 + [vp, vp, C.c_uint32, vp])
     return lib
 
 
@@ -86,7 +89,7 @@ def _reference(ix, q_idx, q_w, r0, r1, mask_bits, tau):
     return out
 
 
-def _run(emul, ix, q_idx, q_w, r0, r1, mask_bits, tau, chunk, budget, use_tabs=True, use_heavy=True, stage=(0, 2 ** 63)):
+def _run(emul, ix, q_idx, q_w, r0, r1, mask_bits, tau, chunk, budget, use_tabs=True, use_heavy=True, stage=(0, 2 ** 63), mh_max_post=None):
     nt = len(q_idx)
     qt = np.asarray(q_idx, np.uint32)
     qw = np.asarray(q_w, np.float64)
@@ -103,10 +106,16 @@ def _run(emul, ix, q_idx, q_w, r0, r1, mask_bits, tau, chunk, budget, use_tabs=T
     out_scores = np.zeros(cap, np.float32)
     stats = np.zeros(4, np.uint64)
     p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
-    rc = emul.ms_emul_segment(p(ix["post_row"]), p(ix["post_val"]), p(ix["hv"]), ix["stride"], p(ix["term_tab"]), p(qtab), p(qshift),
-                              p(ix["indptr"]), p(ix["terms"]),
-                              p(ix["vals"]), nt, p(qt), p(qw), p(ub), p(hidx), p(plo), p(phi), p(mask_bits), C.c_float(tau),
-                              r0, r1, ix["n"], chunk, budget, stage[0], stage[1], p(out_rows), p(out_scores), cap, p(stats))
+    if mh_max_post is not None:             # K3H: hash-accumulate per row range
+        rc = emul.mh_emul_segment(p(ix["post_row"]), p(ix["post_val"]), p(ix["hv"]), ix["stride"], p(ix["term_tab"]), p(qtab), p(qshift),
+                                  p(ix["indptr"]), p(ix["terms"]),
+                                  p(ix["vals"]), nt, p(qt), p(qw), p(ub), p(hidx), p(plo), p(phi), p(mask_bits), C.c_float(tau),
+                                  r0, r1, ix["n"], budget, mh_max_post, p(out_rows), p(out_scores), cap, p(stats))
+    else:
+        rc = emul.ms_emul_segment(p(ix["post_row"]), p(ix["post_val"]), p(ix["hv"]), ix["stride"], p(ix["term_tab"]), p(qtab), p(qshift),
+                                  p(ix["indptr"]), p(ix["terms"]),
+                                  p(ix["vals"]), nt, p(qt), p(qw), p(ub), p(hidx), p(plo), p(phi), p(mask_bits), C.c_float(tau),
+                                  r0, r1, ix["n"], chunk, budget, stage[0], stage[1], p(out_rows), p(out_scores), cap, p(stats))
     assert rc >= 0, f"emulation failed rc={rc}"
     got = {}
     for r, s in zip(out_rows[:rc], out_scores[:rc]):
@@ -233,3 +242,30 @@ def test_stages_score_every_row_once_and_reach_the_exact_top_k(emul, index, seed
         have = sorted(((s_, -r) for r, s_ in best.items()), reverse=True)[:k]
         assert [(float(a), b) for a, b in have] == [(float(a), b) for a, b in want]
         assert all(best[-b].tobytes() == full[-b].tobytes() for _, b in want)
+
+
+@pytest.mark.parametrize("seed", range(5))
+@pytest.mark.parametrize("masked", [False, True])
+def test_k3h_hash_accumulate_matches_oracle(emul, index, seed, masked):
+    """K3H (long queries): essential postings summed per row over row ranges, NE terms looked up best-first.  Candidates
+    and score bits equal the oracle's for every threshold, segment and table capacity (a tiny capacity forces the
+    range-halving path)."""
+    ix = index
+    n = ix["n"]
+    q_idx, w = _query(ix, 900 + seed, (17, 64))
+    rng = np.random.RandomState(seed)
+    mask_bits = rng.randint(0, 2 ** 32, size=(n + 31) // 32, dtype=np.uint64).astype(np.uint32) if masked else None
+    full = _reference(ix, q_idx, w, 0, n, mask_bits, -np.inf)
+    ranked = sorted(full.values(), reverse=True)
+    taus = [-np.inf, 0.0, float(ranked[min(len(ranked) - 1, 60)]), float(ranked[min(len(ranked) - 1, 5)]), float(ranked[0])]
+    halved = 0
+    for tau in taus:
+        for (r0, r1) in ((0, n), (2048, n), (2048, 6144)):
+            want = {r: s_ for r, s_ in full.items() if r0 <= r < r1 and s_ > np.float32(tau)}
+            for max_post, budget, tabs, heavy in ((3072, 100, True, True), (40, 100, True, True), (3072, 20, False, False)):
+                got, stats = _run(emul, ix, q_idx, w, r0, r1, mask_bits, np.float32(tau), 512, budget, tabs, heavy, mh_max_post=max_post)
+                halved += int(stats[3])
+                assert got.keys() == want.keys(), (tau, r0, r1, max_post, sorted(set(got) ^ set(want))[:10])
+                bad = [r for r in want if got[r].tobytes() != want[r].tobytes()]
+                assert not bad, f"score bits differ for rows {bad[:5]}"
+    assert halved > 0

@@ -84,7 +84,9 @@ struct VbMsRec {
 struct VbMsQuery {          // per query, written by the plan kernel
     double tau_lo;          // tau lowered by 1e-9 relative (raised towards 0 for tau <= 0)
     uint32_t n_ess;         // essential terms (positions [0, n_ess))
-    uint32_t active;        // 1 = scored by the MaxScore kernel in this segment
+    uint32_t active;        // 0 = not planned, 1 = K3M (posting units), 2 = K3H (row-range units)
+    uint32_t shift;         // K3H: rows per work unit = 1 << shift
+    uint32_t pad;
 };
 
 // ---- term presence lookups -------------------------------------------------------------------------
@@ -168,6 +170,22 @@ struct VbMsCtx {
     float tau;                      // the list's threshold (exact compare)
 };
 
+// `partial` = the row's contributions from the positions before `first` (every one of them accounted for, present
+// or known absent).  Looks up the remaining positions while the row can still reach tau, then turns the order-free
+// fp64 sum into the reference's fp32 score (verified, or re-scored from the forward index).
+VB_HD bool vb_ms_finish_row(const VbMsCtx& c, uint32_t first, uint32_t row, double partial, float& score) {
+    float lv;
+    for (uint32_t i = first; i < c.nt; ++i) {
+        if (partial + (i ? c.suf[i - 1u] : INFINITY) < c.tau_lo) return false;
+        if (vb_ms_lookup(c.post_row, c.post_val, c.heavy_vals, c.heavy_stride, c.term_tab, c.hidx[i], c.tab[i], c.shift[i], c.plo[i], c.phi[i], row, lv))
+            partial = VB_DADD(partial, VB_DMUL(c.w[i], (double)lv));
+    }
+    if (partial < c.tau_lo) return false;
+    const float f_lo = VB_D2F(partial * (1.0 - c.delta)), f_hi = VB_D2F(partial * (1.0 + c.delta));
+    score = f_lo == f_hi ? f_lo : vb_ms_rescore(c.sp_indptr, c.sp_term, c.sp_val, row, c.q_term, c.q_weight, c.nt);
+    return score > c.tau;
+}
+
 // Score the posting (position pe, row, v).  Returns true and sets `score` iff the row is a candidate
 // owned by this posting (its fp32 score, identical to the reference's, beats tau).
 VB_HD bool vb_ms_score_posting(const VbMsCtx& c, uint32_t pe, uint32_t row, float v, float& score) {
@@ -177,15 +195,7 @@ VB_HD bool vb_ms_score_posting(const VbMsCtx& c, uint32_t pe, uint32_t row, floa
     float lv;
     for (uint32_t i = 0; i < pe; ++i)                            // ownership: an earlier essential term in the row owns it
         if (vb_ms_lookup(c.post_row, c.post_val, c.heavy_vals, c.heavy_stride, c.term_tab, c.hidx[i], c.tab[i], c.shift[i], c.plo[i], c.phi[i], row, lv)) return false;
-    for (uint32_t i = pe + 1u; i < c.nt; ++i) {
-        if (partial + c.suf[i - 1u] < c.tau_lo) return false;
-        if (vb_ms_lookup(c.post_row, c.post_val, c.heavy_vals, c.heavy_stride, c.term_tab, c.hidx[i], c.tab[i], c.shift[i], c.plo[i], c.phi[i], row, lv))
-            partial = VB_DADD(partial, VB_DMUL(c.w[i], (double)lv));
-    }
-    if (partial < c.tau_lo) return false;
-    const float f_lo = VB_D2F(partial * (1.0 - c.delta)), f_hi = VB_D2F(partial * (1.0 + c.delta));
-    score = f_lo == f_hi ? f_lo : vb_ms_rescore(c.sp_indptr, c.sp_term, c.sp_val, row, c.q_term, c.q_weight, c.nt);
-    return score > c.tau;
+    return vb_ms_finish_row(c, pe + 1u, row, partial, score);
 }
 
 // ---- plan: one query, `nt` terms.  Thread j owns term j in phases 1-2 and POSITION j in phase 3; phases are
@@ -253,6 +263,15 @@ VB_HD VbMsPos vb_ms_plan_pos(const VbMsPlanShared& s, uint32_t i, uint32_t nt, d
     return r;
 }
 
+// K3H (sparse_mh.cuh): width (as a shift) of a long query's row ranges — the largest power of two with
+// essential postings * W / rows <= VB_MH_TARGET
+#define VB_MH_TARGET 1024u
+VB_HD uint32_t vb_mh_shift(uint64_t essential_postings, uint32_t seg_rows) {
+    uint32_t shift = 31;
+    while (shift > 6u && (essential_postings << shift) > (uint64_t)VB_MH_TARGET * (seg_rows ? seg_rows : 1u)) --shift;
+    return shift;
+}
+
 VB_HD double vb_ms_tau_lo(double tau_d) { return tau_d > 0.0 ? tau_d * (1.0 - 1e-9) : tau_d * (1.0 + 1e-9); }
 
 #ifdef __CUDACC__
@@ -289,7 +308,9 @@ struct VbMsPlanArgs {
     const int32_t* q_hidx;       // [n_qterms] or nullptr
     const uint32_t* q_plo;       // [n_qterms] full posting range of the term (frequent terms included)
     const uint32_t* q_phi;
-    const uint8_t* q_ms;         // [B] 1 = query eligible for the MaxScore kernel
+    const uint8_t* q_ms;         // [B] 0 = not ours, 1 = K3M (short queries), 2 = K3H (long queries, sparse_mh.cuh)
+    uint32_t classes;            // bit 0: plan the K3M queries, bit 1: plan the K3H queries
+    uint32_t* hunit_prefix;      // [B + 1] out: exclusive prefix of the K3H work units per query
     const float* tau;            // [n_lists]
     VbMsRec* rec;                // [n_qterms] out, position order
     VbMsQuery* qinfo;            // [B] out
@@ -310,7 +331,10 @@ vb_ms_plan_kernel(const VbMsPlanArgs a)
     const uint32_t q = blockIdx.x, j = threadIdx.x;
     const uint32_t t_lo = (uint32_t)a.q_indptr[q];
     const uint32_t nt = (uint32_t)a.q_indptr[q + 1] - t_lo;
-    const bool active = nt != 0u && a.q_ms[q] != 0;
+    const uint32_t cls = nt != 0u ? a.q_ms[q] : 0u;
+    const bool active = cls != 0u && ((a.classes >> (cls - 1u)) & 1u);
+    __shared__ unsigned long long s_ess_post;
+    if (j == 0) s_ess_post = 0ull;
     const double tau_d = (double)a.tau[a.n_queries + q];
     if (active) {
         if (j < nt) vb_ms_plan_load(s, j, a.post_row, a.term_tab, a.q_plo[t_lo + j], a.q_phi[t_lo + j], a.q_tab[t_lo + j], a.q_shift[t_lo + j],
@@ -329,14 +353,26 @@ vb_ms_plan_kernel(const VbMsPlanArgs a)
             r.tab = a.q_tab[t_lo + t]; r.shift = a.q_shift[t_lo + t];
             r.plo = a.q_plo[t_lo + t]; r.phi = a.q_phi[t_lo + t]; r.pad = 0u;
             a.rec[t_lo + j] = r;
-            a.unit_prefix[t_lo + j] = (ps.w1 - ps.w0 + a.chunk - 1u) / a.chunk;   // counts; scanned below
+            a.unit_prefix[t_lo + j] = cls == 1u ? (ps.w1 - ps.w0 + a.chunk - 1u) / a.chunk : 0u;   // counts; scanned below
             if (ps.essential) atomicAdd(&s.n_ess, 1u);
+            if (cls == 2u && ps.w1 > ps.w0) atomicAdd(&s_ess_post, (unsigned long long)(ps.w1 - ps.w0));
         }
         __syncthreads();
-        if (j == 0) { VbMsQuery qi; qi.tau_lo = vb_ms_tau_lo(tau_d); qi.n_ess = s.n_ess; qi.active = 1u; a.qinfo[q] = qi; }
+        if (j == 0) {
+            VbMsQuery qi;
+            qi.tau_lo = vb_ms_tau_lo(tau_d); qi.n_ess = s.n_ess; qi.active = cls; qi.shift = 0u; qi.pad = 0u;
+            uint32_t hunits = 0u;
+            if (cls == 2u && s_ess_post != 0ull) {               // K3H: row ranges of ~VB_MH_TARGET essential postings
+                const uint32_t seg_rows = a.seg_row1 - a.seg_row0;
+                qi.shift = vb_mh_shift((uint64_t)s_ess_post, seg_rows);
+                hunits = (uint32_t)(((uint64_t)seg_rows + (1ull << qi.shift) - 1ull) >> qi.shift);
+            }
+            a.qinfo[q] = qi;
+            a.hunit_prefix[q] = hunits;
+        }
     } else {
         for (uint32_t i = j; i < nt; i += blockDim.x) a.unit_prefix[t_lo + i] = 0u;
-        if (j == 0) { VbMsQuery qi; qi.tau_lo = 0.0; qi.n_ess = 0u; qi.active = 0u; a.qinfo[q] = qi; }
+        if (j == 0) { VbMsQuery qi; qi.tau_lo = 0.0; qi.n_ess = 0u; qi.active = 0u; qi.shift = 0u; qi.pad = 0u; a.qinfo[q] = qi; a.hunit_prefix[q] = 0u; }
     }
     // the last CTA to finish turns the per-position unit counts into an exclusive prefix sum
     __threadfence();
@@ -363,6 +399,27 @@ vb_ms_plan_kernel(const VbMsPlanArgs a)
     uint32_t run = j ? s_scan[j - 1u] : 0u;
     for (uint32_t i = b0; i < b1; ++i) { const uint32_t c = up[i]; up[i] = run; run += c; }
     if (j == 255u) { up[n] = s_scan[255]; a.counters[2] = s_scan[255]; a.counters[1] = 0u; a.counters[0] = 0u; }
+    // same for the K3H units per query
+    __syncthreads();
+    {
+        const uint32_t nq = a.n_queries;
+        const uint32_t perq = (nq + 255u) / 256u;
+        const uint32_t c0 = j * perq, c1 = min(nq, c0 + perq);
+        volatile uint32_t* hp = a.hunit_prefix;
+        uint32_t hs = 0;
+        for (uint32_t i = c0; i < c1; ++i) hs += hp[i];
+        s_scan[j] = hs;
+        __syncthreads();
+        for (uint32_t o = 1; o < 256u; o <<= 1) {
+            const uint32_t v = j >= o ? s_scan[j - o] : 0u;
+            __syncthreads();
+            s_scan[j] += v;
+            __syncthreads();
+        }
+        uint32_t hrun = j ? s_scan[j - 1u] : 0u;
+        for (uint32_t i = c0; i < c1; ++i) { const uint32_t c = hp[i]; hp[i] = hrun; hrun += c; }
+        if (j == 255u) { hp[nq] = s_scan[255]; a.counters[3] = 0u; }
+    }
 }
 
 struct VbMsArgs {

@@ -8,6 +8,7 @@
 #include "dense_gemm.cuh"
 #include "sparse.cuh"
 #include "sparse_ms.cuh"
+#include "sparse_mh.cuh"
 #include "sparse_delta.cuh"
 #include "topk.cuh"
 
@@ -77,8 +78,9 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct Batch {
     uint32_t B = 0, k = 0, limit = 0, n_lists = 0, n_qterms = 0, nt_max = 1, n_filters = 0, mask_words = 0, n_blocks = 0;
     bool any_sparse = false, use_mask = false, any_heavy = false, begun = false;
-    bool any_ms = false, any_old = false;      // some sparse query goes to the MaxScore kernel / stays on K3
+    bool any_ms = false, any_old = false, any_mh = false;   // some sparse query goes to K3M / stays on K3 / goes to K3H
     uint32_t n_old = 0;                        // sparse queries that stay on K3 in every segment
+    uint32_t n_dir = 0;                        // sparse queries K3 scores in the direct segment when K3M runs in stages (K3 + K3H ones)
     uint32_t n_rows = 0;                       // rows of the index when the batch was staged
     uint64_t gen = 0;                          // write generation of the index when the batch was staged
     uint32_t seg_ratio = 32;                   // growth factor of the segment schedule for this batch
@@ -97,7 +99,8 @@ struct Batch {
     const uint32_t* d_qphi = nullptr;
     const uint32_t* d_slotq = nullptr;         // query of every term slot
     const uint8_t* d_qms = nullptr;            // [B] 1 = scored by the MaxScore kernel outside the direct segment
-    const uint32_t* d_oldq = nullptr;          // [n_old] the other sparse queries
+    const uint32_t* d_oldq = nullptr;          // [n_old] the sparse queries neither K3M nor K3H takes
+    const uint32_t* d_dirq = nullptr;          // [n_dir] those plus the K3H queries (first, direct segment)
     const uint32_t* d_qtab = nullptr;          // [n_qterms] bucket table offset of the term (VB_MS_NO_TAB = none)
     const uint8_t* d_qshift = nullptr;         // [n_qterms] bucket shift
     // the query batch inverted by term, for the delta rows (K3D)
@@ -164,7 +167,7 @@ struct vb_index {
 
     // per-search scratch
     DevBuf args, mask, cand, lists, offs, plan, out, q_hat, q_bf16, q_scale, tmp;
-    DevBuf ms_rec, ms_q, ms_units, ms_counters;            // K3M: plan output, work-unit prefix, counters
+    DevBuf ms_rec, ms_q, ms_units, ms_counters, mh_units;  // K3M / K3H: plan output, work-unit prefixes, counters
     HostBuf h_args_s[2], h_out_s[2], h_stage;
     uint32_t cand_cap = 0;
 
@@ -173,9 +176,10 @@ struct vb_index {
     int64_t opt_sparse_ms = 1;             // 1: posting-driven MaxScore kernel (K3M) outside the direct segment; 0: K3 everywhere
     int64_t opt_ms_budget = 100;           // K3M: non-essential ub budget in % of tau (100 = full MaxScore partition)
     int64_t opt_ms_chunk = 0;              // K3M: postings per work unit (0 = auto)
+    int64_t opt_sparse_mh = 1;             // 1: long queries go to K3H (hash-accumulate MaxScore); 0: they stay on K3
     int64_t opt_k1f = 1;                   // single-pass dense scan (K1F) for batches of at most VB_K1F_MAX_B queries
     int64_t opt_ms_staged = 1;             // K3M: 1 = posting stages over the whole index, 0 = once per row segment
-    int64_t opt_ms_stage_ratio = 32;       // K3M: growth of the posting stages
+    int64_t opt_ms_stage_ratio = 0;        // K3M: growth of the posting stages (0 = auto: 32, up to 1024 for tiny batches)
     int64_t opt_delta_max = 0;             // rows the delta may hold before vb_upsert merges it into the index (0 = auto)
     int64_t opt_ms_max_terms = 16;         // K3M scores queries of at most this many terms; longer ones accumulate (K3)
 
@@ -184,6 +188,7 @@ struct vb_index {
     bool staged_safe = false;
     std::vector<cudaEvent_t> prof_events;
     std::vector<int> prof_phase;
+    std::vector<double> timeline;          // profile: (phase, start ms, end ms) of every timed region of the last search
 };
 
 static int dev_reserve(vb_index* h, DevBuf& b, size_t bytes, bool keep, size_t used_bytes = 0) {
@@ -230,7 +235,7 @@ __global__ void vb_init_lists_kernel(float* tau, uint32_t* cnt, uint32_t* overfl
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         tau[i] = -INFINITY; overflow[i] = 0u; gtau[i] = 0u;
-        const uint32_t c0 = (no_direct != nullptr && i >= n_queries && no_direct[i - n_queries]) ? 0u : cnt0;
+        const uint32_t c0 = (no_direct != nullptr && i >= n_queries && no_direct[i - n_queries] == 1) ? 0u : cnt0;
         for (uint32_t s = 0; s < VB_SUB; ++s) cnt[i * VB_SUB + s] = s == 0 ? c0 : 0u;
     }
 }
@@ -306,6 +311,21 @@ extern "C" int vb_create(int32_t dim, int32_t device, uint64_t capacity_hint, ui
     }
     h->stream = h->own_stream;
     if (vb_gemm_configure() != 0) { delete h; return vb_fail("vb_create: tensor-core kernel configuration failed: %s", vb_gemm_last_error()); }
+    if (const char* env = getenv("VB200_SPARSE_CARVEOUT")) {
+        // Experiment: the persistent GEMM CTAs configure their SM for the maximum shared-memory carveout; give the
+        // sparse chain's kernels the same preference so that they can be co-resident without an SM reconfiguration.
+        const int pct = atoi(env);
+        if (pct >= 0) {
+            cudaFuncSetAttribute(vb_ms_score_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(vb_ms_plan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(vb_compact_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(vb_sparse_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        }
+    }
+    if (cudaFuncSetAttribute(vb_mh_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vb_mh_smem_bytes(VB_MS_MAX_TERMS)) != cudaSuccess) {
+        delete h;
+        return vb_fail("vb_create: cannot reserve shared memory for the long-query sparse kernel");
+    }
     {
         const int want = std::min<int>((int)prop.sharedMemPerBlockOptin, 200 * 1024);
         if (cudaFuncSetAttribute(vb_sparse_delta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want) == cudaSuccess) g_delta_smem_max = want;
@@ -323,6 +343,7 @@ extern "C" int vb_create(int32_t dim, int32_t device, uint64_t capacity_hint, ui
     if (const char* env = getenv("VB200_MS_CHUNK")) h->opt_ms_chunk = atoi(env);
     if (const char* env = getenv("VB200_MS_STAGED")) h->opt_ms_staged = atoi(env);
     if (const char* env = getenv("VB200_K1F")) h->opt_k1f = atoi(env);
+    if (const char* env = getenv("VB200_SPARSE_MH")) h->opt_sparse_mh = atoi(env);
     if (const char* env = getenv("VB200_MS_STAGE_RATIO")) h->opt_ms_stage_ratio = atoi(env);
     if (const char* env = getenv("VB200_MS_MAX_TERMS")) h->opt_ms_max_terms = atoi(env);
     *out = h;
@@ -336,7 +357,7 @@ extern "C" void vb_destroy(vb_index* h) {
     for (DevBuf* b : {&h->rows, &h->inv_norm, &h->scope_id, &h->created, &h->modified, &h->alive, &h->sp_indptr,
                       &h->sp_term, &h->sp_val, &h->post_row, &h->post_val, &h->heavy_vals, &h->args, &h->mask, &h->cand, &h->lists,
                       &h->offs, &h->plan, &h->out, &h->q_hat, &h->q_bf16, &h->q_scale, &h->tmp,
-                      &h->ms_rec, &h->ms_q, &h->ms_units, &h->ms_counters, &h->term_tab})
+                      &h->ms_rec, &h->ms_q, &h->ms_units, &h->ms_counters, &h->mh_units, &h->term_tab})
         dev_free(h, *b);
     for (HostBuf* b : {&h->h_args_s[0], &h->h_args_s[1], &h->h_out_s[0], &h->h_out_s[1], &h->h_stage}) if (b->p) cudaFreeHost(b->p);
     for (auto ev : h->prof_events) cudaEventDestroy(ev);
@@ -363,6 +384,7 @@ extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
     else if (k == "sparse_ms") h->opt_sparse_ms = value;           // 0: K3 in every segment (no MaxScore kernel)
     else if (k == "ms_budget") h->opt_ms_budget = value;           // K3M non-essential budget in % of tau
     else if (k == "ms_chunk") h->opt_ms_chunk = value;             // K3M postings per work unit (0 auto)
+    else if (k == "sparse_mh") h->opt_sparse_mh = value;           // 0: long queries stay on K3
     else if (k == "k1f") h->opt_k1f = value;                       // 0: K1 in row segments even for single queries
     else if (k == "ms_staged") h->opt_ms_staged = value;           // K3M: posting stages (1) or row segments (0)
     else if (k == "ms_stage_ratio") h->opt_ms_stage_ratio = value; // K3M: growth of the posting stages
@@ -391,6 +413,16 @@ extern "C" int vb_get_stats(vb_index* h, vb_stats* out) {
     h->stats.row_base = h->row_base;
     h->stats.delta_rows = h->sparse_dirty ? h->n_rows : h->n_rows - h->base_rows;
     *out = h->stats;
+    return 0;
+}
+
+extern "C" int vb_get_timeline(vb_index* h, double* out, uint32_t cap, uint32_t* n) {
+    if (!h || !n) return vb_fail("vb_get_timeline: NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
+    const uint32_t have = (uint32_t)(h->timeline.size() / 3);
+    *n = have;
+    for (uint32_t i = 0; i < std::min(have, cap) && out; ++i)
+        for (int j = 0; j < 3; ++j) out[3 * i + j] = h->timeline[3 * (size_t)i + j];
     return 0;
 }
 
@@ -906,9 +938,15 @@ static void prof_end(vb_index* h, int idx = -2, cudaStream_t st = nullptr) {
 static void prof_collect(vb_index* h) {
     double acc[PH_N] = {0, 0, 0, 0, 0};
     h->stats.last_dense_big_ms = h->stats.last_sparse_big_ms = 0.0;
+    h->timeline.clear();
     for (size_t i = 0; i < h->prof_phase.size(); ++i) {
-        float ms = 0.f;
+        float ms = 0.f, t0 = 0.f;
         cudaEventElapsedTime(&ms, h->prof_events[2 * i], h->prof_events[2 * i + 1]);
+        if (cudaEventElapsedTime(&t0, h->ev0s[h->cur], h->prof_events[2 * i]) == cudaSuccess) {
+            h->timeline.push_back((double)h->prof_phase[i]);
+            h->timeline.push_back((double)t0);
+            h->timeline.push_back((double)t0 + ms);
+        }
         const int ph = h->prof_phase[i] & 7;
         acc[ph] += ms;
         if (h->prof_phase[i] & PH_BIG) (ph == PH_DENSE ? h->stats.last_dense_big_ms : h->stats.last_sparse_big_ms) = ms;
@@ -952,7 +990,7 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     // ---- sparse queries: sort by term id, resolve posting ranges, apply IDF ----
     std::vector<int64_t> indptr(b.B + 1, 0);
     std::vector<double> weight, qub;
-    std::vector<uint32_t> qlo, qhi, qterm, qplo, qphi, slotq, oldq;
+    std::vector<uint32_t> qlo, qhi, qterm, qplo, qphi, slotq, oldq, dirq;
     std::vector<int32_t> qhidx;
     std::vector<uint8_t> qrelaxed(b.B, 0), qms(b.B, 0), qshift;
     std::vector<uint32_t> qtab;
@@ -1007,15 +1045,21 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
             // MaxScore kernel: bounds and the order-free sum need every product >= 0 as well
             // Long queries stay on K3: a row must rule out most of a long query's essential terms one lookup at a
             // time before MaxScore can drop it, while K3 accumulates all of them without lookups.
-            const bool ms = all_pos && need_corpus && h->sparse_nonneg && h->opt_sparse_ms && hi > lo && hi - lo <= h->opt_ms_max_terms;
-            qms[i] = ms ? 1 : 0;
+            const bool bounded = all_pos && need_corpus && h->sparse_nonneg && h->opt_sparse_ms && hi > lo;
+            const bool ms = bounded && hi - lo <= h->opt_ms_max_terms;
+            const bool mh = bounded && !ms && h->opt_sparse_mh;         // long query: hash-accumulate MaxScore (K3H)
+            qms[i] = ms ? 1 : (mh ? 2 : 0);
             if (ms) {
                 b.any_ms = true;
                 uint64_t tot = 0;
                 for (size_t t = q_first; t < weight.size(); ++t) tot += qphi[t] - qplo[t];
                 b.ms_max_post = std::max(b.ms_max_post, tot);
             }
-            else if (hi > lo) { b.any_old = true; oldq.push_back(i); }
+            else if (hi > lo) {
+                dirq.push_back(i);
+                if (mh) b.any_mh = true;
+                else { b.any_old = true; oldq.push_back(i); }
+            }
             for (size_t t = q_first; t < weight.size(); ++t) {
                 if (!relax) qhidx[t] = -1;
                 if (qhidx[t] >= 0) { qlo[t] = qhi[t] = 0; b.any_heavy = true; }
@@ -1072,6 +1116,7 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     const size_t o_sq = ar.take((size_t)b.n_qterms * 4 + 8);
     const size_t o_ms = ar.take((size_t)b.B + 8);
     const size_t o_oq = ar.take((size_t)oldq.size() * 4 + 8);
+    const size_t o_dq = ar.take((size_t)dirq.size() * 4 + 8);
     const size_t o_tab = ar.take((size_t)b.n_qterms * 4 + 8);
     const size_t o_tsh = ar.take((size_t)b.n_qterms + 8);
     // delta rows present: the batch inverted by term (term -> queries, weights) for K3D
@@ -1118,6 +1163,7 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
         memcpy(hp + o_sq, slotq.data(), (size_t)b.n_qterms * 4);
         memcpy(hp + o_ms, qms.data(), (size_t)b.B);
         if (!oldq.empty()) memcpy(hp + o_oq, oldq.data(), oldq.size() * 4);
+        if (!dirq.empty()) memcpy(hp + o_dq, dirq.data(), dirq.size() * 4);
         memcpy(hp + o_tab, qtab.data(), (size_t)b.n_qterms * 4);
         memcpy(hp + o_tsh, qshift.data(), (size_t)b.n_qterms);
     }
@@ -1128,6 +1174,7 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
         memcpy(hp + o_uw, uw.data(), uw.size() * 8);
     }
     b.n_old = (uint32_t)oldq.size();
+    b.n_dir = (uint32_t)dirq.size();
     b.n_rows = (uint32_t)h->n_rows;
     b.base_rows = (uint32_t)h->base_rows;
     b.gen = h->write_gen;
@@ -1159,6 +1206,7 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     b.d_slotq = reinterpret_cast<const uint32_t*>(dp + o_sq);
     b.d_qms = reinterpret_cast<const uint8_t*>(dp + o_ms);
     b.d_oldq = reinterpret_cast<const uint32_t*>(dp + o_oq);
+    b.d_dirq = reinterpret_cast<const uint32_t*>(dp + o_dq);
     b.d_qtab = reinterpret_cast<const uint32_t*>(dp + o_tab);
     b.d_qshift = reinterpret_cast<const uint8_t*>(dp + o_tsh);
     b.d_ut = reinterpret_cast<const uint32_t*>(dp + o_ut);
@@ -1177,6 +1225,8 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     uint32_t need_cap = std::max<uint32_t>(16384u, (uint32_t)align_up((size_t)2 * (size_t)b.seg_ratio * b.k, 4096));
     // K1F (single-pass scan for tiny batches) leaves one local top-k' per CTA in the list before the merge
     if (b.B <= VB_K1F_MAX_B) need_cap = std::max<uint32_t>(need_cap, (uint32_t)align_up((size_t)vb_k1f_grid(h->sm_count) * b.k, 4096));
+    // tiny batches are launch-latency bound: roomy lists (a few MB) let K3M take 1024x larger posting stages
+    if (b.B <= VB_K1F_MAX_B) need_cap = std::max<uint32_t>(need_cap, 262144u);
     h->cand_cap = need_cap;
     TRY(dev_reserve(h, h->cand, (size_t)b.n_lists * need_cap * 8, false));
     TRY(dev_reserve(h, h->lists, (size_t)b.n_lists * (12 + 4 * VB_SUB), false));
@@ -1296,12 +1346,13 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     //   safe mode:   K3M runs once per (small) row segment, like K3, so that no list can overflow.
     const bool ms_on = do_sparse && b.any_ms && h->opt_sparse_ms;
     const bool ms_staged = ms_on && !safe_mode && h->opt_ms_staged;
+    const bool mh_on = do_sparse && b.any_mh;                   // long queries: K3 direct segment, then K3H per segment
     // K1F: one pass over all rows for tiny batches (no segments, no direct slots)
     const bool k1f = path == 1 && !safe_mode && h->opt_k1f && b.B <= VB_K1F_MAX_B && (h->d_pad / 8 + 31) / 32 <= 4 &&
                      b.k <= 2048u && (uint64_t)vb_k1f_grid(h->sm_count) * b.k <= h->cand_cap;
     // the first segment writes its keys to fixed slots at the front of the list (no atomics) — unless nobody runs
     // a first segment: K1F scans in one pass, K3M in posting stages
-    const bool k3_direct = do_sparse && (!ms_staged || b.any_old);
+    const bool k3_direct = do_sparse && (!ms_staged || b.n_dir > 0);
     const uint32_t direct_rows = (bounds[1] <= h->cand_cap && (!k1f || k3_direct)) ? bounds[1] : 0u;
     if (phase != 2) TRY(init_lists(h, b, direct_rows, ms_staged));
     // query prep (fp32 unit queries for K1, packed bf16 operand for K2)
@@ -1389,8 +1440,10 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     };
     const uint32_t ms_chunk = h->opt_ms_chunk > 0 ? (uint32_t)align_up((size_t)h->opt_ms_chunk, VB_MS_U * VB_MS_THREADS)
                                                    : 512u;
-    auto ms_launch = [&](uint32_t r0, uint32_t r1, uint64_t stage_lo, uint64_t stage_hi) -> int {
+    // classes: bit 0 = plan + score the K3M queries, bit 1 = the K3H (long) queries
+    auto ms_launch = [&](uint32_t r0, uint32_t r1, uint64_t stage_lo, uint64_t stage_hi, uint32_t classes) -> int {
         VbMsPlanArgs pa{};
+        pa.classes = classes; pa.hunit_prefix = h->mh_units.as<uint32_t>();
         pa.post_row = h->post_row.as<uint32_t>(); pa.term_tab = h->term_tab.as<uint32_t>(); pa.q_tab = b.d_qtab; pa.q_shift = b.d_qshift;
         pa.n_rows = (uint32_t)h->base_rows; pa.q_indptr = b.d_qindptr; pa.q_weight = b.d_qweight; pa.q_ub = b.d_qub;
         pa.q_hidx = b.any_heavy ? b.d_qhidx : nullptr; pa.q_plo = b.d_qplo; pa.q_phi = b.d_qphi; pa.q_ms = b.d_qms; pa.tau = b.tau;
@@ -1400,6 +1453,25 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         pa.chunk = ms_chunk; pa.budget_pct = (uint32_t)std::max<int64_t>(0, h->opt_ms_budget);
         vb_ms_plan_kernel<<<b.B, 256, 0, ss>>>(pa);
         CKK("vb_ms_plan_kernel");
+        ++h->stats.last_launches;
+        if (classes & 2u) {
+            VbMhArgs m{};
+            m.post_row = h->post_row.as<uint32_t>(); m.post_val = h->post_val.as<float>();
+            m.heavy_vals = h->heavy_vals.as<float>(); m.heavy_stride = h->heavy_stride; m.term_tab = h->term_tab.as<uint32_t>();
+            m.sp_indptr = h->sp_indptr.as<int64_t>(); m.sp_term = h->sp_term.as<uint32_t>(); m.sp_val = h->sp_val.as<float>();
+            m.q_indptr = b.d_qindptr; m.q_term = b.d_qterm; m.q_weight = b.d_qweight;
+            m.rec = h->ms_rec.as<VbMsRec>(); m.qinfo = h->ms_q.as<VbMsQuery>(); m.hunit_prefix = h->mh_units.as<uint32_t>();
+            m.counters = h->ms_counters.as<uint32_t>();
+            m.mask = b.use_mask ? h->mask.as<uint32_t>() : nullptr; m.mask_of = b.use_mask ? b.d_maskof : nullptr;
+            m.tau = b.tau; m.lists = L; m.mask_words = b.mask_words; m.n_queries = b.B; m.n_rows = (uint32_t)h->base_rows;
+            m.row_base = (uint32_t)h->row_base; m.nt_max = b.nt_max; m.seg_row0 = r0; m.seg_row1 = r1;
+            const uint64_t max_units = std::max<uint64_t>(1, (uint64_t)h->nnz_live / 256 + b.B);
+            const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)h->sm_count * 4u, max_units);
+            vb_mh_score_kernel<<<grid, VB_MH_THREADS, vb_mh_smem_bytes(b.nt_max), ss>>>(m);
+            CKK("vb_mh_score_kernel");
+            ++h->stats.last_launches;
+        }
+        if (!(classes & 1u)) return 0;
         VbMsArgs a{};
         a.post_row = h->post_row.as<uint32_t>(); a.post_val = h->post_val.as<float>();
         a.heavy_vals = h->heavy_vals.as<float>(); a.heavy_stride = h->heavy_stride;
@@ -1416,7 +1488,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)h->sm_count * 16u, max_units);
         vb_ms_score_kernel<<<grid, VB_MS_THREADS, vb_ms_smem_bytes(b.nt_max), ss>>>(a);
         CKK("vb_ms_score_kernel");
-        h->stats.last_launches += 2;
+        ++h->stats.last_launches;
         return 0;
     };
     auto sparse_compact = [&](uint32_t lim0) -> int {
@@ -1432,13 +1504,21 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     auto sparse_segment = [&](uint32_t r0, uint32_t r1_all, uint32_t direct, bool big) -> int {
         const uint32_t r1 = std::min(r1_all, nb);               // the index stops at nb
         const bool rows_here = do_sparse && r0 < r1;
-        const bool ms_here = rows_here && ms_on && !ms_staged && !direct;
-        const bool k3_sel = ms_on && (ms_staged || !direct);    // K3 restricted to the queries K3M does not take
-        const bool k3_here = rows_here && (!k3_sel || b.any_old);
-        if (!direct && !ms_here && !k3_here) return 0;          // nothing scored, nothing to compact
-        if (ms_here || k3_here) {
+        const bool ms_here = rows_here && ms_on && !ms_staged && !direct;      // K3M once per segment (safe mode / ms_staged = 0)
+        const bool mh_here = rows_here && mh_on && !direct;                    // K3H for the long queries
+        // K3's queries here: everybody (no K3M / K3H at all, or the direct segment of the per-segment flow); in the
+        // direct segment of the staged flow the K3 + K3H queries; otherwise only the ones nobody else takes
+        const uint32_t* k3_list = nullptr;
+        uint32_t k3_n = b.B;
+        if (ms_on || mh_on) {
+            if (!direct) { k3_list = b.d_oldq; k3_n = b.n_old; }
+            else if (ms_staged) { k3_list = b.d_dirq; k3_n = b.n_dir; }
+        }
+        const bool k3_here = rows_here && k3_n > 0;
+        if (!direct && !ms_here && !mh_here && !k3_here) return 0;             // nothing scored, nothing to compact
+        if (ms_here || mh_here || k3_here) {
             const int pi = prof_begin(h, PH_SPARSE | (big ? PH_BIG : 0), ss);
-            if (ms_here) TRY(ms_launch(r0, r1, 0ull, ~0ull));
+            if (ms_here || mh_here) TRY(ms_launch(r0, r1, 0ull, ~0ull, (ms_here ? 1u : 0u) | (mh_here ? 2u : 0u)));
             if (k3_here) {
                 // which terms are essential under the thresholds this segment starts with
                 double* d_ubne = h->plan.as<double>();
@@ -1461,8 +1541,8 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
                 a.tau = b.tau; a.lists = L; a.mask_words = b.mask_words;
                 a.n_qterms = b.n_qterms; a.nt_max = b.nt_max; a.blk_begin = r0 / VB_ROWS_PER_BLOCK; a.n_queries = b.B; a.n_rows = nb;
                 a.row_base = (uint32_t)h->row_base; a.direct = direct;
-                uint32_t n_q = b.B;
-                if (k3_sel) { a.q_sel = b.d_oldq; a.n_sel = b.n_old; n_q = b.n_old; }   // the MaxScore kernel has the rest
+                const uint32_t n_q = k3_n;
+                if (k3_list != nullptr) { a.q_sel = k3_list; a.n_sel = k3_n; }          // K3M / K3H have the rest
                 { static const char* dbg = getenv("VB200_SPARSE_DEBUG"); a.debug = dbg ? (uint32_t)atoi(dbg) : 0u; }
                 const uint32_t nblk = (r1 - r0 + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK;
                 vb_sparse_kernel<<<nblk * n_q, VB_SPARSE_THREADS, vb_sparse_smem_bytes(b.nt_max), ss>>>(a);
@@ -1475,14 +1555,15 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         return sparse_compact(direct ? std::max(direct_rows, L.sub_cap) : L.sub_cap);
     };
     // fine (2048-row) slice table rows K3 will read
-    const bool k3_all_segments = do_sparse && (!ms_on || b.any_old);
+    const bool k3_all_segments = do_sparse && ((!ms_on && !mh_on) || b.any_old);
     const uint32_t fine_blocks = k3_all_segments ? b.n_blocks
-                                 : (do_sparse && !ms_staged ? std::min<uint32_t>(b.n_blocks, (direct_rows + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK) : 0u);
+                                 : (k3_direct ? std::min<uint32_t>(b.n_blocks, (direct_rows + VB_ROWS_PER_BLOCK - 1) / VB_ROWS_PER_BLOCK) : 0u);
     if (do_sparse) {
         const uint64_t total = (uint64_t)b.n_qterms * (fine_blocks + 1);
         TRY(dev_reserve(h, h->offs, std::max<uint64_t>(total, 1) * 4, false));
         TRY(dev_reserve(h, h->plan, (size_t)b.B * 8 + b.n_qterms + 64, false));
-        if (ms_on) {
+        if (ms_on || mh_on) {
+            TRY(dev_reserve(h, h->mh_units, ((size_t)b.B + 1) * 4, false));
             TRY(dev_reserve(h, h->ms_rec, (size_t)b.n_qterms * sizeof(VbMsRec), false));
             TRY(dev_reserve(h, h->ms_q, (size_t)b.B * sizeof(VbMsQuery), false));
             TRY(dev_reserve(h, h->ms_units, ((size_t)b.n_qterms + 1) * 4, false));
@@ -1497,7 +1578,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
             CKK("vb_slice_kernel");
             ++h->stats.last_launches;
         }
-        if (ms_on) CK(cudaMemsetAsync(h->ms_counters.p, 0, 64, ss));
+        if (ms_on || mh_on) CK(cudaMemsetAsync(h->ms_counters.p, 0, 64, ss));
         prof_end(h, pi, ss);
     }
     // K3M stages (normal mode): stage 0 in phases 0 and 1, the rest in phases 0 and 2
@@ -1508,12 +1589,15 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
             const bool last = hi >= b.ms_max_post;
             if (st == 0 ? first : rest) {
                 const int pi = prof_begin(h, PH_SPARSE | (last ? PH_BIG : 0), ss);
-                TRY(ms_launch(0u, nb, lo, last ? ~0ull : hi));
+                TRY(ms_launch(0u, nb, lo, last ? ~0ull : hi, 1u));
                 prof_end(h, pi, ss);
                 TRY(sparse_compact(L.sub_cap));
             }
             lo = hi;
-            hi = hi * (uint64_t)std::max<int64_t>(2, h->opt_ms_stage_ratio);
+            // a stage appends ~ratio * k' candidates per list at worst (rows are visited best-first, usually far fewer)
+            const uint64_t ratio = h->opt_ms_stage_ratio > 0 ? (uint64_t)std::max<int64_t>(2, h->opt_ms_stage_ratio)
+                                   : (b.B <= VB_K1F_MAX_B ? std::min<uint64_t>(1024, std::max<uint64_t>(32, h->cand_cap / (8ull * b.k))) : 32ull);
+            hi = hi * ratio;
         }
         return 0;
     };

@@ -68,7 +68,7 @@ EXPORTS = ["vb_abi_version", "vb_last_error", "vb_create", "vb_destroy", "vb_ups
            "vb_delete_rows", "vb_optimize", "vb_term_stats", "vb_search", "vb_search_local", "vb_merge_fuse",
            "vb_stage", "vb_run_local", "vb_run_fuse", "vb_fetch",
            "vb_run_local_begin", "vb_tau_export", "vb_tau_import",
-           "vb_set_option", "vb_get_stats", "vb_sync", "vb_save", "vb_load"]
+           "vb_set_option", "vb_get_stats", "vb_get_timeline", "vb_sync", "vb_save", "vb_load"]
 
 _lib = None
 
@@ -103,6 +103,7 @@ def load_library():
     lib.vb_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.vb_get_stats.argtypes = [vp, C.POINTER(_Stats)]
     lib.vb_sync.argtypes = [vp]
+    lib.vb_get_timeline.argtypes = [vp, vp, C.c_uint32, C.POINTER(C.c_uint32)]
     lib.vb_run_local_begin.argtypes = [vp]
     lib.vb_tau_export.argtypes = [vp, vp]
     lib.vb_tau_import.argtypes = [vp, vp]
@@ -479,6 +480,15 @@ class Index:
         s = _Stats()
         self._check(self._lib.vb_get_stats(self._h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in _Stats._fields_}
+
+    def timeline(self):
+        """[(phase name, largest-launch flag, start ms, end ms)] of the last fetched search (option profile = 1)."""
+        n = C.c_uint32()
+        buf = np.zeros(3 * 4096, np.float64)
+        self._check(self._lib.vb_get_timeline(self._h, _vp(buf), 4096, C.byref(n)))
+        names = ["mask", "dense", "sparse", "select", "fuse"]
+        return [(names[int(buf[3 * i]) & 7], bool(int(buf[3 * i]) & 8), float(buf[3 * i + 1]), float(buf[3 * i + 2]))
+                for i in range(min(int(n.value), 4096))]
 
     def sync(self) -> None:
         self._check(self._lib.vb_sync(self._h))
