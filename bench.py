@@ -455,7 +455,9 @@ def main():
             ev1.record(sh.stream)
         res = ix.fetch(staged, allow_overflow=True)
         if res is None:
-            raise SystemExit("bench.py: candidate overflow in the timed region (unexpected for this workload)")
+            s_ = ix.stats()
+            raise SystemExit("bench.py: candidate overflow in the timed region (unexpected for this workload): %d list(s), first %d of %d"
+                             % (s_["last_overflow_lists"], s_["last_overflow_first"], 2 * B))
         return ev0.elapsed_time(ev1), res
 
     def barrier():

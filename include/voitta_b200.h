@@ -108,6 +108,8 @@ typedef struct vb_stats {
     uint64_t dim, row_base;                    /* geometry of the index (what vb_load restored)            */
     uint64_t index_builds;                     /* full builds of the inverted index so far (sort of every posting) */
     uint64_t delta_rows;                       /* rows appended since the last build (scored from the forward index) */
+    uint32_t last_overflow_lists;              /* candidate lists that overflowed in the last fetched search (0 = none)  */
+    uint32_t last_overflow_first;              /* the first of them: list q = dense list of query q, B + q = its sparse list */
 } vb_stats;
 
 int         vb_abi_version(void);

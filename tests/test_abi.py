@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(engine._Filter) == 32
     assert ctypes.sizeof(engine._QueryBatch) == 88
     assert ctypes.sizeof(engine._Result) == 72
-    assert ctypes.sizeof(engine._Stats) == 200
+    assert ctypes.sizeof(engine._Stats) == 208
 
 
 def test_no_cpu_fallback():

@@ -243,11 +243,22 @@ def test_overflow_falls_back_to_safe_mode_and_stays_exact():
     ix = engine.Index(dim)
     ix.upsert(dense)
     q = np.zeros(dim, np.float32); q[0] = 1.0
-    r = ix.search_batch(q[None, :], limit=10)
-    assert ix.stats()["overflow_reruns"] == 1
     v = dense.astype(np.float64)
     scores = (v[:, 0] / np.linalg.norm(v, axis=1)).astype(np.float32)
+    # the single-pass scan (K1F) keeps its candidates in per-CTA buffers that it re-selects as often as needed: no overflow
+    r = ix.search_batch(q[None, :], limit=10)
+    assert ix.stats()["overflow_reruns"] == 0
+    assert_topk_valid(r.hits(0), scores, np.ones(n, bool), 10, rel_tol=1e-6, abs_tol=1e-6, what="ascending corpus, K1F")
+    # the segmented kernels (here K1 with k1f = 0; batches use the same lists) overflow, notice, and re-run in safe mode
+    ix.set_option("k1f", 0)
+    r = ix.search_batch(q[None, :], limit=10)
+    assert ix.stats()["overflow_reruns"] == 1
     assert_topk_valid(r.hits(0), scores, np.ones(n, bool), 10, rel_tol=1e-6, abs_tol=1e-6, what="ascending corpus")
+    # and a batch on the tensor-core path
+    r = ix.search_batch(np.stack([q, q, q]), limit=10)
+    assert ix.stats()["overflow_reruns"] == 2
+    for i in range(3):
+        assert_topk_valid(r.hits(i), scores, np.ones(n, bool), 10, rel_tol=1e-3, abs_tol=1e-3, what="ascending corpus, K2")
     ix.close()
 
 

@@ -186,8 +186,9 @@ vb_dense_scan_generic_kernel(const VbScanArgs a)
 // Exactness: pruning keeps every row with score >= threshold (ties stay, rows arrive out of row order); the
 // final order (score desc, row asc) comes from the keys, which are unique.  Same arithmetic as K1.
 #define VB_K1F_THREADS 256
-#define VB_K1F_CAP 4096u           // candidate slots per CTA (32 KB of shared memory)
-#define VB_K1F_CHECK 8u            // iterations between buffer checks: 8 warps x 32 rows x 8 = 2048 appends at most
+#define VB_K1F_CAP 2048u           // candidate slots per CTA (16 KB of shared memory: 8 CTAs per SM, full occupancy —
+                                   // the first version had 32 KB buffers, 2 CTAs per SM, and ran at half of K1's bandwidth)
+#define VB_K1F_CHECK 4u            // iterations between buffer checks: 8 warps x 32 rows x 4 = 1024 appends at most
 
 struct VbScan1Args {
     const uint4* rows;

@@ -263,7 +263,12 @@ __global__ void vb_find_tail_kernel(const uint64_t* keys, uint64_t n, uint64_t* 
 static int g_delta_smem_max = 48 * 1024;
 
 #define VB_K1F_MAX_B 8u
-static uint32_t vb_k1f_grid(int sm_count) { return (uint32_t)sm_count * 2u; }
+// CTAs per query of the single-pass scan: full occupancy (8 x 256 threads per SM) for the usual small k'; fewer for
+// large k' so that the merge of G * k' keys stays short
+static uint32_t vb_k1f_grid(int sm_count, uint32_t k, uint32_t B) {
+    const uint32_t per_sm = k <= 64u ? 8u : (k <= 256u ? 4u : 2u);
+    return std::max<uint32_t>(1u, (uint32_t)sm_count * per_sm / std::min<uint32_t>(B, 4u));
+}
 
 static unsigned grid_for(uint64_t n, unsigned block, unsigned max_blocks = 148u * 16u) {
     uint64_t g = (n + block - 1) / block;
@@ -1221,10 +1226,14 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     // segment growth: each segment appends ~ratio * k' candidates per list before the next compaction.  Batches
     // keep 32 (list memory and compaction time scale with B); single queries are launch-latency bound and take
     // 128 (one segment fewer on 100k..10M rows; measured +7..25 % q/s at B = 1).
-    b.seg_ratio = h->opt_seg_ratio > 0 ? (uint32_t)h->opt_seg_ratio : (b.B <= 4 ? 128u : 32u);
-    uint32_t need_cap = std::max<uint32_t>(16384u, (uint32_t)align_up((size_t)2 * (size_t)b.seg_ratio * b.k, 4096));
+    // (round 2: 8 instead of 32 for batches — the appends of a segment cost more than the extra launch + compaction:
+    //  cfg4 dense 18.0 -> 15.8 ms)
+    b.seg_ratio = h->opt_seg_ratio > 0 ? (uint32_t)h->opt_seg_ratio : (b.B <= 4 ? 128u : 8u);
+    uint32_t need_cap = std::max<uint32_t>(16384u, (uint32_t)align_up((size_t)2 * (size_t)std::max<uint32_t>(b.seg_ratio, 32u) * b.k, 4096));
+    // roomier lists (up to 256 MB in all) let K3M take larger posting stages: fewer launches on small corpora
+    need_cap = std::max<uint32_t>(need_cap, (uint32_t)std::min<uint64_t>(align_up((size_t)16 * 128 * b.k, 4096), (256ull << 20) / ((uint64_t)b.n_lists * 8u) / 4096u * 4096u));
     // K1F (single-pass scan for tiny batches) leaves one local top-k' per CTA in the list before the merge
-    if (b.B <= VB_K1F_MAX_B) need_cap = std::max<uint32_t>(need_cap, (uint32_t)align_up((size_t)vb_k1f_grid(h->sm_count) * b.k, 4096));
+    if (b.B <= VB_K1F_MAX_B) need_cap = std::max<uint32_t>(need_cap, (uint32_t)align_up((size_t)vb_k1f_grid(h->sm_count, b.k, b.B) * b.k, 4096));
     // tiny batches are launch-latency bound: roomy lists (a few MB) let K3M take 1024x larger posting stages
     if (b.B <= VB_K1F_MAX_B) need_cap = std::max<uint32_t>(need_cap, 262144u);
     h->cand_cap = need_cap;
@@ -1349,7 +1358,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     const bool mh_on = do_sparse && b.any_mh;                   // long queries: K3 direct segment, then K3H per segment
     // K1F: one pass over all rows for tiny batches (no segments, no direct slots)
     const bool k1f = path == 1 && !safe_mode && h->opt_k1f && b.B <= VB_K1F_MAX_B && (h->d_pad / 8 + 31) / 32 <= 4 &&
-                     b.k <= 2048u && (uint64_t)vb_k1f_grid(h->sm_count) * b.k <= h->cand_cap;
+                     b.k <= VB_K1F_CAP / 2u && (uint64_t)vb_k1f_grid(h->sm_count, b.k, b.B) * b.k <= h->cand_cap;
     // the first segment writes its keys to fixed slots at the front of the list (no atomics) — unless nobody runs
     // a first segment: K1F scans in one pass, K3M in posting stages
     const bool k3_direct = do_sparse && (!ms_staged || b.n_dir > 0);
@@ -1394,7 +1403,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         a.q_hat = h->q_hat.as<float>(); a.gtau = b.gtau; a.cand = h->cand.as<uint64_t>(); a.cnt = b.cnt;
         a.cap = h->cand_cap; a.k = b.k; a.mask_words = b.mask_words; a.chunks = (uint32_t)h->d_pad / 8; a.n_rows = n;
         a.row_base = (uint32_t)h->row_base;
-        const dim3 grid(vb_k1f_grid(h->sm_count), b.B);
+        const dim3 grid(vb_k1f_grid(h->sm_count, b.k, b.B), b.B);
         switch ((a.chunks + 31) / 32) {
             case 1: vb_dense_scan1_kernel<1><<<grid, VB_K1F_THREADS, 0, sd>>>(a); break;
             case 2: vb_dense_scan1_kernel<2><<<grid, VB_K1F_THREADS, 0, sd>>>(a); break;
@@ -1596,7 +1605,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
             lo = hi;
             // a stage appends ~ratio * k' candidates per list at worst (rows are visited best-first, usually far fewer)
             const uint64_t ratio = h->opt_ms_stage_ratio > 0 ? (uint64_t)std::max<int64_t>(2, h->opt_ms_stage_ratio)
-                                   : (b.B <= VB_K1F_MAX_B ? std::min<uint64_t>(1024, std::max<uint64_t>(32, h->cand_cap / (8ull * b.k))) : 32ull);
+                                   : std::min<uint64_t>(1024, std::max<uint64_t>(32, h->cand_cap / (16ull * b.k)));
             hi = hi * ratio;
         }
         return 0;
@@ -1686,7 +1695,13 @@ static int fetch_stage(vb_index* h, const Batch& b, vb_result* out, int* overflo
     CK(cudaEventSynchronize(h->ev_done[h->cur]));
     const uint32_t* ovf = reinterpret_cast<const uint32_t*>(hp + b.o_ovf);
     *overflowed = 0;
-    for (uint32_t i = 0; i < b.n_lists; ++i) if (ovf[i]) *overflowed = 1;
+    h->stats.last_overflow_lists = 0;
+    h->stats.last_overflow_first = 0xffffffffu;
+    for (uint32_t i = 0; i < b.n_lists; ++i)
+        if (ovf[i]) {
+            *overflowed = 1;
+            if (h->stats.last_overflow_lists++ == 0) h->stats.last_overflow_first = i;
+        }
     if (*overflowed || !out) return 0;
     const uint32_t* rows = reinterpret_cast<const uint32_t*>(hp + b.o_rows);
     const double* sc = reinterpret_cast<const double*>(hp + b.o_sc);
