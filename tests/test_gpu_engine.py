@@ -235,7 +235,7 @@ def test_overflow_falls_back_to_safe_mode_and_stays_exact():
     """Adversarial order (scores strictly increasing with the row id) floods the candidate lists;
     the library must notice, re-run in safe mode and still return the exact answer."""
     from voitta_rag_b200 import engine
-    n, dim = 300000, 64
+    n, dim = 700000, 64          # (tiny batches get 262144-slot lists: the corpus must outgrow them)
     theta = np.linspace(1.5, 0.05, n).astype(np.float64)
     dense = np.zeros((n, dim), np.float32)
     dense[:, 0] = np.cos(theta); dense[:, 1] = np.sin(theta)
@@ -246,6 +246,7 @@ def test_overflow_falls_back_to_safe_mode_and_stays_exact():
     v = dense.astype(np.float64)
     scores = (v[:, 0] / np.linalg.norm(v, axis=1)).astype(np.float32)
     # the single-pass scan (K1F) keeps its candidates in per-CTA buffers that it re-selects as often as needed: no overflow
+    ix.set_option("k1f", 2)        # (2 = also on corpora larger than the 2M rows K1F is used for by default)
     r = ix.search_batch(q[None, :], limit=10)
     assert ix.stats()["overflow_reruns"] == 0
     assert_topk_valid(r.hits(0), scores, np.ones(n, bool), 10, rel_tol=1e-6, abs_tol=1e-6, what="ascending corpus, K1F")

@@ -179,9 +179,9 @@ vb_dense_scan_generic_kernel(const VbScanArgs a)
 // keeps its own candidate buffer in shared memory and its own threshold (the score of its current k'-th best),
 // re-selecting whenever the buffer could overflow; CTAs publish their thresholds through one global word per
 // list (atomicMax on the order-preserving score encoding) — any CTA's k'-th best is a lower bound of the
-// global k'-th best — so late CTAs prune with the best threshold known anywhere.  At the end each CTA writes
-// its exact local top-k' to cand[list][cta * k' ...]; vb_compact_kernel merges G*k' -> k' (the same kernel
-// that merges per-shard lists).  Rows are dealt to CTAs in an interleaved order, so every CTA sees a
+// global k'-th best — so late CTAs prune with the best threshold known anywhere.  At the end each CTA appends
+// the part of its exact local top-k' that still reaches that threshold to the list (one atomic per CTA);
+// vb_compact_kernel merges the few hundred keys (the same kernel that merges per-shard lists).  Rows are dealt to CTAs in an interleaved order, so every CTA sees a
 // uniform sample of the corpus and its threshold converges after a few hundred rows.
 // Exactness: pruning keeps every row with score >= threshold (ties stay, rows arrive out of row order); the
 // final order (score desc, row asc) comes from the keys, which are unique.  Same arithmetic as K1.
@@ -323,9 +323,23 @@ vb_dense_scan1_kernel(const VbScan1Args a)
             tau = s_tau;
         }
     }
-    // local top-k' -> this CTA's slice of the list (0 = empty slot)
+    // local top-k' -> the list.  Only entries at or above the best threshold known anywhere can be in the global
+    // top-k' (the local list is sorted: they are a prefix); the CTA reserves that many slots with ONE atomic on the
+    // list's counter (pre-set to 0 by the list set-up; at most G * k' <= cap in total) and the merge sees a few hundred
+    // keys instead of G * k'.
     const uint32_t keep = s_cnt;
-    uint64_t* out = a.cand + (size_t)list * a.cap + (size_t)blockIdx.x * a.k;
-    for (uint32_t i = threadIdx.x; i < a.k; i += VB_K1F_THREADS) out[i] = i < keep ? s_keys[i] : 0ull;
-    if (blockIdx.x == 0 && threadIdx.x < VB_SUB) a.cnt[list * VB_SUB + threadIdx.x] = threadIdx.x == 0 ? gridDim.x * a.k : 0u;
+    __shared__ uint32_t s_take, s_base;
+    if (threadIdx.x == 0) {
+        const uint32_t o = *reinterpret_cast<volatile uint32_t*>(a.gtau + list);
+        uint32_t lo = 0, hi = keep;                              // first index whose ordered score is below the threshold
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if ((uint32_t)(s_keys[mid] >> 32) >= o) lo = mid + 1u; else hi = mid;
+        }
+        s_take = lo;
+        s_base = lo ? atomicAdd(a.cnt + (size_t)list * VB_SUB, lo) : 0u;
+    }
+    __syncthreads();
+    uint64_t* out = a.cand + (size_t)list * a.cap + s_base;
+    for (uint32_t i = threadIdx.x; i < s_take; i += VB_K1F_THREADS) out[i] = s_keys[i];
 }

@@ -218,6 +218,7 @@ struct VbMsPlanShared {
 VB_HD uint32_t vb_ms_seg_bound(const uint32_t* post_row, const uint32_t* term_tab, uint32_t plo, uint32_t phi,
                                uint32_t tab, uint32_t shift, uint32_t n_rows, uint32_t target) {
     if (target >= n_rows) return phi;
+    if (target == 0u) return plo;                              // (the staged flow plans the whole index: no loads at all)
     uint32_t lo = plo, hi = phi;
     if (tab != VB_MS_NO_TAB) vb_ms_bucket(term_tab, tab, shift, target, lo, hi);
     return vb_ms_lower_bound(post_row, lo, hi, target);
@@ -321,6 +322,7 @@ struct VbMsPlanArgs {
     uint64_t stage_lo, stage_hi; // the query's postings (numbered in position order) this launch scores
     uint32_t chunk;              // postings per work unit
     uint32_t budget_pct;         // MaxScore budget in % of tau (100 = the full MaxScore partition)
+    uint32_t budget_pct_long;    // the same for the K3H (long) queries
 };
 
 __global__ void __launch_bounds__(256)
@@ -344,7 +346,7 @@ vb_ms_plan_kernel(const VbMsPlanArgs a)
         if (j < nt) vb_ms_plan_position(s, j, nt);
         __syncthreads();
         if (j < nt) {                                          // thread j now finishes POSITION j
-            const VbMsPos ps = vb_ms_plan_pos(s, j, nt, tau_d, a.budget_pct, a.stage_lo, a.stage_hi);
+            const VbMsPos ps = vb_ms_plan_pos(s, j, nt, tau_d, cls == 2u ? a.budget_pct_long : a.budget_pct, a.stage_lo, a.stage_hi);
             const uint32_t t = s.term_at[j];
             VbMsRec r;
             r.slo = s.slo[t] + ps.w0; r.shi = s.slo[t] + ps.w1; r.w = a.q_weight[t_lo + t];

@@ -176,6 +176,7 @@ struct vb_index {
     int64_t opt_sparse_ms = 1;             // 1: posting-driven MaxScore kernel (K3M) outside the direct segment; 0: K3 everywhere
     int64_t opt_ms_budget = 100;           // K3M: non-essential ub budget in % of tau (100 = full MaxScore partition)
     int64_t opt_ms_chunk = 0;              // K3M: postings per work unit (0 = auto)
+    int64_t opt_mh_budget = 50;            // K3H: non-essential ub budget in % of tau (see sparse_mh.cuh: 100 % leaves every touched row to be finished by lookups)
     int64_t opt_sparse_mh = 1;             // 1: long queries go to K3H (hash-accumulate MaxScore); 0: they stay on K3
     int64_t opt_k1f = 1;                   // single-pass dense scan (K1F) for batches of at most VB_K1F_MAX_B queries
     int64_t opt_ms_staged = 1;             // K3M: 1 = posting stages over the whole index, 0 = once per row segment
@@ -231,11 +232,12 @@ static void dev_free(vb_index* h, DevBuf& b) {
 // cnt0: slots of the first (direct) segment at the front of every list.  `no_direct` (optional, one flag per
 // query): the sparse list of such a query is never written by a direct segment (K3M scores it in stages).
 __global__ void vb_init_lists_kernel(float* tau, uint32_t* cnt, uint32_t* overflow, uint32_t* gtau, uint32_t n, uint32_t cnt0,
-                                     const uint8_t* no_direct, uint32_t n_queries) {
+                                     const uint8_t* no_direct, uint32_t n_queries, uint32_t dense_direct) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         tau[i] = -INFINITY; overflow[i] = 0u; gtau[i] = 0u;
-        const uint32_t c0 = (no_direct != nullptr && i >= n_queries && no_direct[i - n_queries] == 1) ? 0u : cnt0;
+        uint32_t c0 = (no_direct != nullptr && i >= n_queries && no_direct[i - n_queries] == 1) ? 0u : cnt0;
+        if (i < n_queries && !dense_direct) c0 = 0u;             // K1F appends to an empty list
         for (uint32_t s = 0; s < VB_SUB; ++s) cnt[i * VB_SUB + s] = s == 0 ? c0 : 0u;
     }
 }
@@ -349,6 +351,7 @@ extern "C" int vb_create(int32_t dim, int32_t device, uint64_t capacity_hint, ui
     if (const char* env = getenv("VB200_MS_STAGED")) h->opt_ms_staged = atoi(env);
     if (const char* env = getenv("VB200_K1F")) h->opt_k1f = atoi(env);
     if (const char* env = getenv("VB200_SPARSE_MH")) h->opt_sparse_mh = atoi(env);
+    if (const char* env = getenv("VB200_MH_BUDGET")) h->opt_mh_budget = atoi(env);
     if (const char* env = getenv("VB200_MS_STAGE_RATIO")) h->opt_ms_stage_ratio = atoi(env);
     if (const char* env = getenv("VB200_MS_MAX_TERMS")) h->opt_ms_max_terms = atoi(env);
     *out = h;
@@ -389,6 +392,7 @@ extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
     else if (k == "sparse_ms") h->opt_sparse_ms = value;           // 0: K3 in every segment (no MaxScore kernel)
     else if (k == "ms_budget") h->opt_ms_budget = value;           // K3M non-essential budget in % of tau
     else if (k == "ms_chunk") h->opt_ms_chunk = value;             // K3M postings per work unit (0 auto)
+    else if (k == "mh_budget") h->opt_mh_budget = value;           // K3H non-essential budget in % of tau
     else if (k == "sparse_mh") h->opt_sparse_mh = value;           // 0: long queries stay on K3
     else if (k == "k1f") h->opt_k1f = value;                       // 0: K1 in row segments even for single queries
     else if (k == "ms_staged") h->opt_ms_staged = value;           // K3M: posting stages (1) or row segments (0)
@@ -1262,9 +1266,9 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
 
 // direct_rows > 0: the first segment stores its keys at fixed slots [0, direct_rows) of every
 // list (no atomics); slots nobody writes (masked rows, rows without postings) must read as empty.
-static int init_lists(vb_index* h, const Batch& b, uint32_t direct_rows, bool ms_staged = false) {
+static int init_lists(vb_index* h, const Batch& b, uint32_t direct_rows, bool ms_staged = false, bool dense_direct = true) {
     vb_init_lists_kernel<<<(b.n_lists + 255) / 256, 256, 0, h->stream>>>(b.tau, b.cnt, b.overflow, b.gtau, b.n_lists, direct_rows,
-                                                                          ms_staged ? b.d_qms : nullptr, b.B);
+                                                                          ms_staged ? b.d_qms : nullptr, b.B, dense_direct ? 1u : 0u);
     CKK("vb_init_lists_kernel");
     ++h->stats.last_launches;
     if (direct_rows)
@@ -1357,13 +1361,15 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     const bool ms_staged = ms_on && !safe_mode && h->opt_ms_staged;
     const bool mh_on = do_sparse && b.any_mh;                   // long queries: K3 direct segment, then K3H per segment
     // K1F: one pass over all rows for tiny batches (no segments, no direct slots)
-    const bool k1f = path == 1 && !safe_mode && h->opt_k1f && b.B <= VB_K1F_MAX_B && (h->d_pad / 8 + 31) / 32 <= 4 &&
+    // (on large corpora the segmented K1 streams faster — no per-stretch barriers — and its launches are noise there:
+    //  cfg3 10M rows, B = 1: K1 1.65 ms, K1F 1.83 ms; cfg1 100k rows: K1 59 us + 3 selects, K1F 48 us + 1 merge)
+    const bool k1f = path == 1 && !safe_mode && h->opt_k1f && (h->opt_k1f > 1 || n <= (2u << 20)) && b.B <= VB_K1F_MAX_B && (h->d_pad / 8 + 31) / 32 <= 4 &&
                      b.k <= VB_K1F_CAP / 2u && (uint64_t)vb_k1f_grid(h->sm_count, b.k, b.B) * b.k <= h->cand_cap;
     // the first segment writes its keys to fixed slots at the front of the list (no atomics) — unless nobody runs
     // a first segment: K1F scans in one pass, K3M in posting stages
     const bool k3_direct = do_sparse && (!ms_staged || b.n_dir > 0);
     const uint32_t direct_rows = (bounds[1] <= h->cand_cap && (!k1f || k3_direct)) ? bounds[1] : 0u;
-    if (phase != 2) TRY(init_lists(h, b, direct_rows, ms_staged));
+    if (phase != 2) TRY(init_lists(h, b, direct_rows, ms_staged, !k1f));
     // query prep (fp32 unit queries for K1, packed bf16 operand for K2)
     TRY(dev_reserve(h, h->q_hat, (size_t)b.B * h->d_pad * 4, false));
     TRY(dev_reserve(h, h->q_bf16, (size_t)(2 * ((size_t)b.B + 256)) * h->d_pad * 2, false));
@@ -1460,6 +1466,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         pa.counters = h->ms_counters.as<uint32_t>(); pa.n_queries = b.B; pa.n_qterms = b.n_qterms;
         pa.seg_row0 = r0; pa.seg_row1 = r1; pa.stage_lo = stage_lo; pa.stage_hi = stage_hi;
         pa.chunk = ms_chunk; pa.budget_pct = (uint32_t)std::max<int64_t>(0, h->opt_ms_budget);
+        pa.budget_pct_long = (uint32_t)std::max<int64_t>(0, h->opt_mh_budget);
         vb_ms_plan_kernel<<<b.B, 256, 0, ss>>>(pa);
         CKK("vb_ms_plan_kernel");
         ++h->stats.last_launches;
@@ -1592,7 +1599,9 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     }
     // K3M stages (normal mode): stage 0 in phases 0 and 1, the rest in phases 0 and 2
     auto ms_stages = [&](bool first, bool rest) -> int {
-        const uint64_t p0 = std::max<uint64_t>(ms_chunk, std::min<uint64_t>(std::max<uint64_t>(16ull * b.k, 2048ull), h->cand_cap / 4));
+        // stage 0 scores its postings with no threshold (every lookup of every posting): just enough of them to fill a
+        // list twice over after filters and ownership
+        const uint64_t p0 = std::max<uint64_t>(ms_chunk, std::min<uint64_t>(align_up((size_t)8 * b.k, ms_chunk), h->cand_cap / 4));
         uint64_t lo = 0, hi = p0;
         for (uint32_t st = 0; lo < b.ms_max_post; ++st) {
             const bool last = hi >= b.ms_max_post;
@@ -1613,7 +1622,9 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     // enqueue the two chains interleaved so that neither stream starves on the host side
     const size_t n_seg = bounds.size() - 1;
     const size_t s_begin = phase == 2 ? 1 : 0, s_end = phase == 1 ? 1 : n_seg;
-    if (ms_staged) TRY(ms_stages(phase != 2, phase != 1));
+    // Order on the sparse stream: K3's direct first segment (fixed slots, counted by the list set-up) and its
+    // compaction come BEFORE the K3M stages — a stage's compaction runs over every sparse list and would turn a
+    // still-unwritten direct block into an empty list.
     if (k1f && phase != 1) TRY(dense_single_pass());
     for (size_t s = s_begin; s < s_end; ++s) {
         const uint32_t direct = (s == 0 && direct_rows) ? 1u : 0u;
@@ -1621,7 +1632,9 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         if (big && !k1f) h->stats.last_big_rows = bounds[s + 1] - bounds[s];
         TRY(dense_segment(bounds[s], bounds[s + 1], direct, big));
         TRY(sparse_segment(bounds[s], bounds[s + 1], direct, big));
+        if (s == 0 && ms_staged) TRY(ms_stages(true, phase != 1));
     }
+    if (phase == 2 && ms_staged) TRY(ms_stages(false, true));
     if (do_delta && phase != 1) {
         // K3D: the rows appended since the index was built, straight from the forward CSR.  One launch (a few
         // thousand rows against thresholds the indexed rows have already established); the safe mode cuts it into
