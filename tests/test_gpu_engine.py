@@ -959,5 +959,5 @@ def test_k3h_long_queries_equal_k3_and_oracle(world):
                 ws = [(int(want["sparse_rows"][i, j]), float(want["sparse_scores"][i, j])) for j in range(want["sparse_counts"][i])]
                 assert_same_ranking(base.branch(i, "sparse"), ws, rel_tol=0.0, what=f"k3h f{fi} q{i}")
     finally:
-        for k, v in {"sparse_mh": 1, "ms_max_terms": 16, "safe_mode": 0, "seg_ratio": 0, "ms_staged": 1, "sparse_dense": 1}.items():
+        for k, v in {"sparse_mh": 0, "ms_max_terms": 16, "safe_mode": 0, "seg_ratio": 0, "ms_staged": 1, "sparse_dense": 1}.items():
             ix.set_option(k, v)

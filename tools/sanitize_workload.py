@@ -54,8 +54,11 @@ check(3, n0, "B=3 K2 resident", dense_path=2)
 check(3, n0, "B=3 K3 only", sparse_ms=0)
 check(3, n0, "B=3 safe mode", safe_mode=1)
 check(300, n0, "B=300 K2T")
-ix.set_option("ms_max_terms", 4)                      # queries of more than 4 terms become "long": K3H
-check(6, n0, "B=6 long queries (K3H)")
+ix.set_option("ms_max_terms", 4)                      # queries of more than 4 terms become "long"
+check(6, n0, "B=6 long queries on K3")
+ix.set_option("sparse_mh", 1)                         # ... and on K3H (off by default)
+check(6, n0, "B=6 long queries on K3H")
+ix.set_option("sparse_mh", 0)
 ix.set_option("ms_max_terms", 16)
 ix.upsert(coded["dense"][n0:n], sl(n0, n), coded["scope"][n0:n], coded["created"][n0:n], coded["modified"][n0:n])
 dead = np.arange(100, 400, 7)

@@ -200,6 +200,7 @@ struct VbScan1Args {
     uint64_t* cand;
     uint32_t* cnt;
     uint32_t cap, k, mask_words, chunks, n_rows, row_base;
+    uint32_t split_shift;       // a warp takes 32 >> split_shift rows of a group (tiny corpora: more warps than groups)
 };
 
 // descending bitonic sort of P keys (power of two <= VB_K1F_CAP) by all threads of the CTA
@@ -244,14 +245,18 @@ vb_dense_scan1_kernel(const VbScan1Args a)
     __syncthreads();
     float tau = -INFINITY;
     const uint32_t n_groups = (a.n_rows + 31u) >> 5;
+    const uint32_t n_slots = n_groups << a.split_shift;                  // (group, part of the group) pairs
+    const uint32_t part_rows = 32u >> a.split_shift;
     const uint32_t stride = gridDim.x * (VB_K1F_THREADS / 32u);
-    const uint32_t n_iter = (n_groups + stride - 1u) / stride;          // the same for every warp of the grid: barriers are uniform
+    const uint32_t n_iter = (n_slots + stride - 1u) / stride;           // the same for every warp of the grid: barriers are uniform
     for (uint32_t it = 0; it < n_iter; ++it) {
-        const uint32_t g = it * stride + blockIdx.x * (VB_K1F_THREADS / 32u) + warp;
-        if (g < n_groups) {
+        const uint32_t slot_id = it * stride + blockIdx.x * (VB_K1F_THREADS / 32u) + warp;
+        if (slot_id < n_slots) {
+            const uint32_t g = slot_id >> a.split_shift, part = slot_id & ((1u << a.split_shift) - 1u);
             uint32_t bits = mask ? mask[g] : 0xffffffffu;
             const uint32_t row0 = g << 5;
             if (row0 + 32u > a.n_rows) bits &= (1u << (a.n_rows - row0)) - 1u;
+            if (a.split_shift) bits &= ((part_rows == 32u ? 0xffffffffu : ((1u << part_rows) - 1u)) << (part * part_rows));
             const float invn = (bits != 0u && row0 + lane < a.n_rows) ? a.inv_norm[row0 + lane] : 0.0f;
             while (bits) {
                 int r[ROWS];

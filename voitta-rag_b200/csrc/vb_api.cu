@@ -177,7 +177,8 @@ struct vb_index {
     int64_t opt_ms_budget = 100;           // K3M: non-essential ub budget in % of tau (100 = full MaxScore partition)
     int64_t opt_ms_chunk = 0;              // K3M: postings per work unit (0 = auto)
     int64_t opt_mh_budget = 50;            // K3H: non-essential ub budget in % of tau (see sparse_mh.cuh: 100 % leaves every touched row to be finished by lookups)
-    int64_t opt_sparse_mh = 1;             // 1: long queries go to K3H (hash-accumulate MaxScore); 0: they stay on K3
+    int64_t opt_sparse_mh = 0;             // 1: long queries go to K3H (hash-accumulate MaxScore); 0 (default): they stay on K3 —
+                                           // measured on the cfg5 shard: K3 190 ms, K3H 346-715 ms depending on the budget (sparse_mh.cuh)
     int64_t opt_k1f = 1;                   // single-pass dense scan (K1F) for batches of at most VB_K1F_MAX_B queries
     int64_t opt_ms_staged = 1;             // K3M: 1 = posting stages over the whole index, 0 = once per row segment
     int64_t opt_ms_stage_ratio = 0;        // K3M: growth of the posting stages (0 = auto: 32, up to 1024 for tiny batches)
@@ -1410,6 +1411,10 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         a.cap = h->cand_cap; a.k = b.k; a.mask_words = b.mask_words; a.chunks = (uint32_t)h->d_pad / 8; a.n_rows = n;
         a.row_base = (uint32_t)h->row_base;
         const dim3 grid(vb_k1f_grid(h->sm_count, b.k, b.B), b.B);
+        // small corpora: fewer 32-row groups than warps — give each warp a half / quarter / eighth of a group
+        const uint32_t n_groups = (n + 31u) / 32u, n_warps = grid.x * (VB_K1F_THREADS / 32u);
+        a.split_shift = 0;
+        while (a.split_shift < 3u && (n_groups << (a.split_shift + 1u)) <= n_warps) ++a.split_shift;
         switch ((a.chunks + 31) / 32) {
             case 1: vb_dense_scan1_kernel<1><<<grid, VB_K1F_THREADS, 0, sd>>>(a); break;
             case 2: vb_dense_scan1_kernel<2><<<grid, VB_K1F_THREADS, 0, sd>>>(a); break;
