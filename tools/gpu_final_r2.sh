@@ -20,18 +20,23 @@ for W in cfg4 cfg2 cfg3-b1-s1 cfg5-shard; do
     python bench.py --workload $W --steps 1 --warmup 3 --no-cpu-baseline --no-api > gpurun_out/ncu_l_$W.log 2>&1
   echo "launch list $W rc=$?"
 done
-# full captures: name  workload  kernel-regex  launches-to-skip
+# full captures: name  workload  kernel-regex  launches-to-skip.  Only the raw-metric CSV travels back (gpurun_out is
+# capped at 64 MiB and a --set full report is 5-15 MB); the two dominant kernels keep their .ncu-rep as well.
 cap() {
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$3 -s $4 -c 1 -f -o gpurun_out/${R}_prof_$1 \
+  timeout 900 ncu --set full --clock-control none -k regex:$3 -s $4 -c 1 -f -o gpurun_out/${R}_prof_$1 \
     python bench.py --workload $2 --steps 1 --warmup 3 --no-cpu-baseline --no-api > gpurun_out/ncu_$1.log 2>&1
   echo "capture $1 ($2 $3 skip $4) rc=$?"
+  ncu -i gpurun_out/${R}_prof_$1.ncu-rep --page raw --csv > gpurun_out/${R}_prof_$1.csv 2>/dev/null
+  [ "$5" = "keep" ] || rm -f gpurun_out/${R}_prof_$1.ncu-rep
+  tail -c 2000 gpurun_out/ncu_$1.log > gpurun_out/ncu_$1.tail; rm -f gpurun_out/ncu_$1.log
 }
-cap k2t cfg4 vb_dense_gemm_tiled_kernel 10
-cap k3m cfg4 vb_ms_score_kernel 9
+cap k2t cfg4 vb_dense_gemm_tiled_kernel 10 keep
+cap k3m cfg4 vb_ms_score_kernel 9 keep
 cap mask cfg4 vb_mask_kernel 3
 cap compact cfg4 vb_compact_kernel 40
 cap k1 cfg3-b1-s50 vb_dense_scan_kernel 8
 cap k1f cfg1 vb_dense_scan1_kernel 5
 cap k3 cfg5-shard vb_sparse_kernel 6
 cap k2 cfg2 vb_dense_gemm_kernel 8
-bash tools/gpu_sanitize.sh ${R}
+rm -f gpurun_out/ncu_l_*.log
+du -sh gpurun_out

@@ -30,7 +30,11 @@ CAPS = {"k2t": ("cfg4", "vb_dense_gemm_tiled_kernel", 12_500_000, 1024), "k3m": 
 
 
 def raw(rep):
-    txt = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    c = rep.with_suffix(".csv")
+    if c.exists() and c.stat().st_size:
+        txt = c.read_text()
+    else:
+        txt = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     return rows[0], rows[1], rows[2:]
 
@@ -45,7 +49,7 @@ def main():
     lines, traffic = [], []
     for name, (wl, kern, rows_gpu, qpb) in CAPS.items():
         rep = OUT / f"{R}_prof_{name}.ncu-rep"
-        if not rep.exists():
+        if not rep.exists() and not rep.with_suffix(".csv").exists():
             continue
         hdr, units, data = raw(rep)
         if not data:

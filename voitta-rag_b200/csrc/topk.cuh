@@ -308,6 +308,10 @@ struct VbFuseArgs {
     uint32_t* out_rows;       // [B][limit]
     double* out_scores;       // [B][limit]
     int32_t* out_cnt;         // [B]
+    // list bookkeeping for the host, written here instead of by two more copies after the kernel
+    const uint32_t* overflow; // [2B]
+    uint32_t* out_lcnt;       // [2B] entries of every list
+    uint32_t* out_ovf;        // [2B] overflow flags
 };
 
 __global__ void __launch_bounds__(128)
@@ -320,6 +324,11 @@ vb_fuse_kernel(const VbFuseArgs a)
     uint8_t* valid = reinterpret_cast<uint8_t*>(row + 2 * k);   // [2k]
 
     const uint32_t q = blockIdx.x, B = a.n_queries;
+    if (threadIdx.x < 2u && a.out_lcnt != nullptr) {
+        const uint32_t l = threadIdx.x * B + q;
+        a.out_lcnt[l] = a.cnt[l * VB_SUB];
+        a.out_ovf[l] = a.overflow[l];
+    }
     const uint64_t* dk = a.cand + (size_t)q * a.cap;
     const uint64_t* sk = a.cand + (size_t)(B + q) * a.cap;
     const uint32_t nd = a.cnt[q * VB_SUB] < k ? a.cnt[q * VB_SUB] : k;

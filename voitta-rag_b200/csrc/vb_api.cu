@@ -1685,6 +1685,7 @@ static int fuse_stage(vb_index* h, const Batch& b) {
     f.k = b.k; f.limit = b.limit; f.w_sparse = b.w_sparse; f.w_dense = 1.0 - b.w_sparse;
     f.out_rows = reinterpret_cast<uint32_t*>(dp + b.o_rows); f.out_scores = reinterpret_cast<double*>(dp + b.o_sc);
     f.out_cnt = reinterpret_cast<int32_t*>(dp + b.o_cnt);
+    f.overflow = b.overflow; f.out_lcnt = reinterpret_cast<uint32_t*>(dp + b.o_lcnt); f.out_ovf = reinterpret_cast<uint32_t*>(dp + b.o_ovf);
     vb_fuse_kernel<<<b.B, 128, (size_t)2 * b.k * 13 + 16, h->stream>>>(f);
     CKK("vb_fuse_kernel");
     ++h->stats.last_launches;
@@ -1694,8 +1695,6 @@ static int fuse_stage(vb_index* h, const Batch& b) {
         ++h->stats.last_launches;
     }
     prof_end(h);
-    CK(cudaMemcpy2DAsync(dp + b.o_lcnt, 4, b.cnt, VB_SUB * 4, 4, b.n_lists, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(dp + b.o_ovf, b.overflow, (size_t)b.n_lists * 4, cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaEventRecord(h->ev1s[h->cur], h->stream));
     // results go to this slot's pinned buffer right away, so a pipelined caller's fetch does not
     // queue behind the next batch's kernels
