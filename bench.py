@@ -565,10 +565,11 @@ def main():
     hbm_peak, tf_peak, peak_kind = peaks()
     names = ["mask", "dense", "sparse", "select", "fuse"]
     per_batch = phase / n_prof
-    dom = int(np.argmax(per_batch))
+    dom = int(np.argmax(per_batch[:3]))                  # the dominant byte / flop moving kernel (mask, dense, sparse); select and
+    #                                                      fuse are many small launches with no roofline of their own
     passes = max(1, int(ix.stats()["last_dense_passes"]))     # corpus passes of the dense kernel per batch
     sel = cfg["sel"] if cfg["sel"] is not None else 1.0
-    dense_bytes = passes * rows_local * ((d_pad * 2 + 4) * (sel if dense_path == 1 else 1.0)) + (rows_local / 8 if flt else 0)
+    dense_bytes = passes * rows_local * ((d_pad * 2 + 4) * (sel if dense_path in (1, 3) else 1.0)) + (rows_local / 8 if flt else 0)
     dense_flops = 2.0 * B * rows_local * d_pad
     sparse_bytes = 0.0
     if hybrid:
@@ -590,7 +591,8 @@ def main():
         launch_ms, launch_bytes = float(per_batch[dom]), alg[dom_name]
     achieved = launch_bytes / (launch_ms / 1e3) / 1e9 if launch_ms > 0 else 0.0
     tensor_bound = dense_path == 2 and B / passes > 250      # past the ridge (252 flop/B): the query-tiled kernel runs
-    kname = {"dense": ("vb_dense_gemm_tiled_kernel" if tensor_bound else "vb_dense_gemm_kernel") if dense_path == 2 else "vb_dense_scan_kernel",
+    kname = {"dense": ("vb_dense_gemm_tiled_kernel" if tensor_bound else "vb_dense_gemm_kernel") if dense_path == 2
+                      else ("vb_dense_scan1_kernel" if dense_path == 3 else "vb_dense_scan_kernel"),
              "sparse": "vb_ms_score_kernel", "mask": "vb_mask_kernel", "select": "vb_compact_kernel", "fuse": "vb_fuse_kernel"}
     traffic, traffic_src = None, None
     tfile = ROOT / "profiles" / "traffic.json"          # dram bytes per launch from a committed ncu --set full capture
@@ -673,7 +675,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": config_block(args, cfg, world, rows_local, B, qps, kprime),
-            "dense_path": {1: "K1 GEMV scan", 2: "K2 tcgen05 GEMM"}.get(dense_path),
+            "dense_path": {1: "K1 GEMV scan", 2: "K2 tcgen05 GEMM", 3: "K1F single-pass GEMV scan"}.get(dense_path),
             "e2e": e2e, "e2e_api": api, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "parity_spot_check": parity, "ingest": ingest, "timeline": timeline,
         }

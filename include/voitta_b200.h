@@ -98,7 +98,7 @@ typedef struct vb_stats {
     uint64_t searches, queries, overflow_reruns;
     double   last_search_ms;      /* device time of the last vb_search (CUDA events)          */
     double   last_dense_ms, last_sparse_ms, last_select_ms, last_mask_ms, last_fuse_ms;
-    uint32_t last_dense_path;     /* 1 = GEMV scan (K1), 2 = tcgen05 GEMM (K2)                */
+    uint32_t last_dense_path;     /* 1 = GEMV scan (K1), 2 = tcgen05 GEMM (K2 / K2T), 3 = single-pass GEMV scan (K1F) */
     uint32_t last_launches;       /* kernels launched by the last vb_search                   */
     uint64_t device_bytes;
     uint64_t last_h2d_bytes, last_d2h_bytes;   /* host<->device copies of the last staged search */

@@ -28,6 +28,19 @@ def needs_build() -> bool:
     return any(s.stat().st_mtime > t for s in srcs)
 
 
+LIB_DEBUG = HERE / "libvoitta_b200_dbg.so"
+
+
+def build_debug() -> Path:
+    """The same library with -DVB_DEBUG_BOUNDS: every VB_CHECK becomes a device-side assert (tools/gpu_sanitize.sh;
+    select it with VB200_LIB=<path>).  compute-sanitizer is closed on the GPU pool; these are our own bounds checks."""
+    cmd = [nvcc_path(), *FLAGS, "-DVB_DEBUG_BOUNDS", "-o", str(LIB_DEBUG), str(SRC)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{r.stdout}\n{r.stderr}")
+    return LIB_DEBUG
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB

@@ -7,6 +7,16 @@
 
 #define VB_ROWS_PER_BLOCK 2048u   // sparse row block (smem accumulators) and segment alignment
 
+// Bounds checks of our own (compute-sanitizer is closed on the GPU pool): a debug build (-DVB_DEBUG_BOUNDS,
+// libvoitta_b200_dbg.so, tools/gpu_sanitize.sh) turns every VB_CHECK into a device-side assert — a failing check traps
+// the kernel and the next CUDA call fails loudly.  The release build compiles them away.
+#ifdef VB_DEBUG_BOUNDS
+#include <assert.h>
+#define VB_CHECK(cond) assert(cond)
+#else
+#define VB_CHECK(cond) ((void)0)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // Candidate key: one u64 orders candidates by (score desc, row asc).  0 is never a valid key
 // (it would need a NaN score), so 0 marks an empty slot.
@@ -36,6 +46,7 @@ __device__ __forceinline__ float vb_key_score(uint64_t key) {
 struct VbLists {
     uint64_t* cand;       // [n_lists][cap]
     uint32_t* cnt;        // [n_lists][VB_SUB]
+    uint32_t n_lists;     // (bounds checks)
     uint32_t cap;         // slots per list
     uint32_t sub_cap;     // slots per sub-range = cap / nsub
     uint32_t sub_mask;    // nsub - 1 (nsub is a power of two <= VB_SUB; 1 in safe mode)
@@ -50,6 +61,7 @@ __device__ __forceinline__ void vb_push(const VbLists& L, uint32_t list, float s
 }
 
 __device__ __forceinline__ void vb_push_sub(const VbLists& L, uint32_t list, uint32_t sub, float score, uint32_t row) {
+    VB_CHECK(list < L.n_lists && sub <= L.sub_mask && (size_t)(sub + 1u) * L.sub_cap <= L.cap);
     const uint32_t slot = atomicAdd(&L.cnt[list * VB_SUB + sub], 1u);
     if (slot < L.sub_cap) L.cand[(size_t)list * L.cap + (size_t)sub * L.sub_cap + slot] = vb_pack_key(score, row);
 }

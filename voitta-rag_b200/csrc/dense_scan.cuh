@@ -333,6 +333,7 @@ vb_dense_scan1_kernel(const VbScan1Args a)
     // list's counter (pre-set to 0 by the list set-up; at most G * k' <= cap in total) and the merge sees a few hundred
     // keys instead of G * k'.
     const uint32_t keep = s_cnt;
+    VB_CHECK(keep <= a.k && keep <= VB_K1F_CAP);
     __shared__ uint32_t s_take, s_base;
     if (threadIdx.x == 0) {
         const uint32_t o = *reinterpret_cast<volatile uint32_t*>(a.gtau + list);
@@ -346,5 +347,6 @@ vb_dense_scan1_kernel(const VbScan1Args a)
     }
     __syncthreads();
     uint64_t* out = a.cand + (size_t)list * a.cap + s_base;
+    VB_CHECK(s_base + s_take <= a.cap);
     for (uint32_t i = threadIdx.x; i < s_take; i += VB_K1F_THREADS) out[i] = s_keys[i];
 }

@@ -211,6 +211,7 @@ vb_sparse_kernel(const VbSparseArgs a)
     const uint32_t blk = a.blk_begin + blk_rel;
     const uint32_t t_lo = (uint32_t)__ldg(a.q_indptr + q);
     const uint32_t nt = (uint32_t)__ldg(a.q_indptr + q + 1) - t_lo;
+    VB_CHECK(q < a.n_queries && nt <= a.nt_max && (size_t)(blk + 1u) * VB_ROWS_PER_BLOCK <= (size_t)a.n_rows + VB_ROWS_PER_BLOCK);
     if (nt == 0) return;                                        // dense-only query
 
     // Term table: every warp builds it by itself (lane = term, 32 terms per step) and all warps store the

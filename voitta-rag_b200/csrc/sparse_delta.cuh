@@ -76,6 +76,7 @@ vb_sparse_delta_kernel(const VbDeltaArgs a)
             const uint32_t k1 = __ldg(a.qt_ptr + lo + 1u);
             for (uint32_t k = __ldg(a.qt_ptr + lo) + lane; k < k1; k += 32u) {     // a query holds a term once: no conflicts
                 const uint32_t q = __ldg(a.qt_query + k);
+                VB_CHECK(q < a.n_queries);
                 acc[q] = __dadd_rn(acc[q], __dadd_rn(__dmul_rn(__ldg(a.qt_weight + k), v), 0.0));
             }
             __syncwarp();

@@ -94,6 +94,7 @@ vb_mh_score_kernel(const VbMhArgs a)
         const uint32_t nt = (uint32_t)__ldg(a.q_indptr + q + 1) - t_lo;
         const VbMsQuery qi = a.qinfo[q];
         const uint32_t n_ess = qi.n_ess;
+        VB_CHECK(q < a.n_queries && nt <= a.nt_max && n_ess <= nt && qi.active == 2u);
         for (uint32_t i = tid; i < nt; i += VB_MH_THREADS) {
             const VbMsRec r = a.rec[t_lo + i];
             s_w[i] = r.w; s_suf[i] = r.suf; s_hidx[i] = r.hidx; s_tab[i] = r.tab; s_shift[i] = r.shift;
@@ -152,6 +153,7 @@ vb_mh_score_kernel(const VbMhArgs a)
                     if (prev == VB_MH_EMPTY || prev == row) break;
                     slot = (slot + 1u) & (VB_MH_SLOTS - 1u);
                 }
+                VB_CHECK(slot < VB_MH_SLOTS && pp < s_shi[k] && row >= pos && row < r1);
                 atomicAdd(&s_acc[slot], prod);
             }
             __syncthreads();

@@ -104,6 +104,9 @@ VB_HD void vb_ms_bucket(const uint32_t* term_tab, uint32_t tab, uint32_t shift, 
     const uint32_t* t = term_tab + (size_t)tab + (row >> shift);
     lo = VB_LD(t);
     hi = VB_LD(t + 1);
+#if defined(__CUDA_ARCH__) && defined(VB_DEBUG_BOUNDS)
+    assert(lo <= hi);
+#endif
 }
 
 // value of a term in `row`: dense column (NaN = absent), bucket table + short search, or (short lists) a
@@ -487,6 +490,7 @@ vb_ms_score_kernel(const VbMsArgs a)
         const VbMsRec e = a.rec[slot];
         const uint32_t p0 = e.slo + (u - __ldg(a.unit_prefix + slot)) * a.chunk;
         const uint32_t p1 = min(e.shi, p0 + a.chunk);
+        VB_CHECK(slot < a.n_qterms && q < a.n_queries && pe < nt && nt <= a.nt_max && p0 < p1 && e.plo <= e.slo && e.shi <= e.phi);
         for (uint32_t i = tid; i < nt; i += VB_MS_THREADS) {
             const VbMsRec r = a.rec[t_lo + i];
             s_w[i] = r.w; s_suf[i] = r.suf; s_hidx[i] = r.hidx;

@@ -210,37 +210,43 @@ vb_compact_kernel(VbLists L, float* __restrict__ tau, uint32_t* __restrict__ ove
         E[sub] = raw < lim ? raw : lim;
     }
     if (over && threadIdx.x == 0) overflow[list] = 1u;
+    VB_CHECK(list < L.n_lists && lim0 <= L.cap);
     __syncthreads();                                   // everyone has read the counters before they are rewritten
     // Small lists (the common case once thresholds exist, and every list of a single-query search): no selection
-    // needed — gather the used prefixes into shared memory, sort, write back.  The general path below costs ~9 us
-    // even for a handful of keys (min/max reductions, a 2048-bin histogram, a scan), and a search runs a compaction
-    // after every segment / stage of both branches.
+    // needed — gather the non-empty keys of the used prefixes into shared memory, sort them, write back.  The general
+    // path below costs ~9 us even for a handful of keys (min/max reductions, a 2048-bin histogram, a scan) and a
+    // search runs a compaction after every segment / stage of both branches.  Empty slots (a direct first segment
+    // under a selective filter is mostly empty) are dropped before the sort.
     {
         uint32_t total = 0;
 #pragma unroll
         for (uint32_t sub = 0; sub < VB_SUB; ++sub) total += E[sub];
-        if (total <= VB_SORT_MAX) {
-            uint32_t base = 0;
+        if (total <= 4u * VB_SORT_MAX) {
+            if (threadIdx.x == 0) s_misc[0] = 0u;
+            __syncthreads();
 #pragma unroll
-            for (uint32_t sub = 0; sub < VB_SUB; ++sub) {
-                for (uint32_t i = threadIdx.x; i < E[sub]; i += VB_COMPACT_THREADS) s_sel[base + i] = gkeys[(size_t)sub * L.sub_cap + i];
-                base += E[sub];
+            for (uint32_t sub = 0; sub < VB_SUB; ++sub)
+                for (uint32_t i = threadIdx.x; i < E[sub]; i += VB_COMPACT_THREADS) {
+                    const uint64_t key = gkeys[(size_t)sub * L.sub_cap + i];
+                    if (key != 0ull) {
+                        const uint32_t slot = atomicAdd(&s_misc[0], 1u);
+                        if (slot < VB_SORT_MAX) s_sel[slot] = key;
+                    }
+                }
+            __syncthreads();
+            const uint32_t valid = s_misc[0];
+            if (valid <= VB_SORT_MAX) {
+                uint32_t P = 2;
+                while (P < valid) P <<= 1;
+                for (uint32_t i = valid + threadIdx.x; i < P; i += VB_COMPACT_THREADS) s_sel[i] = 0ull;
+                vb_bitonic_desc(s_sel, P);              // (every stage starts with a barrier; ends with one)
+                const uint32_t keep = valid < k ? valid : k;
+                for (uint32_t i = threadIdx.x; i < keep; i += VB_COMPACT_THREADS) gkeys[i] = s_sel[i];
+                if (threadIdx.x < VB_SUB) L.cnt[(size_t)list * VB_SUB + threadIdx.x] = threadIdx.x == 0 ? keep : 0u;
+                if (threadIdx.x == 0) tau[list] = fmaxf(tau[list], (keep >= k) ? vb_key_score(s_sel[k - 1]) : -INFINITY);
+                return;
             }
-            uint32_t P = 2;
-            while (P < total) P <<= 1;
-            for (uint32_t i = total + threadIdx.x; i < P; i += VB_COMPACT_THREADS) s_sel[i] = 0ull;
-            vb_bitonic_desc(s_sel, P);                  // (starts and ends with a barrier) zeros — empty slots — sort last
-            uint32_t valid = 0;                         // number of non-zero keys = first zero position (binary search)
-            {
-                uint32_t lo = 0, hi = total;
-                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (s_sel[mid] != 0ull) lo = mid + 1u; else hi = mid; }
-                valid = lo;
-            }
-            const uint32_t keep = valid < k ? valid : k;
-            for (uint32_t i = threadIdx.x; i < keep; i += VB_COMPACT_THREADS) gkeys[i] = s_sel[i];
-            if (threadIdx.x < VB_SUB) L.cnt[(size_t)list * VB_SUB + threadIdx.x] = threadIdx.x == 0 ? keep : 0u;
-            if (threadIdx.x == 0) tau[list] = fmaxf(tau[list], (keep >= k) ? vb_key_score(s_sel[k - 1]) : -INFINITY);
-            return;
+            __syncthreads();                            // too many live keys: the general path (it re-initialises its scratch)
         }
     }
     bool fits = E[0] <= VB_REG0 * VB_COMPACT_THREADS;

@@ -1281,6 +1281,7 @@ static VbLists make_lists(const vb_index* h, const Batch& b, bool safe) {
     VbLists L;
     L.cand = h->cand.as<uint64_t>();
     L.cnt = b.cnt;
+    L.n_lists = b.n_lists;
     L.cap = h->cand_cap;
     const uint32_t nsub = safe ? 1u : VB_SUB;          // safe mode: one range, segments that cannot overflow it
     L.sub_cap = h->cand_cap / nsub;
@@ -1430,6 +1431,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         ++h->stats.last_launches;
         prof_end(h, ps, sd);
         h->stats.last_big_rows = n;
+        h->stats.last_dense_path = 3u;                          // K1F
         return 0;
     };
     auto dense_segment = [&](uint32_t r0, uint32_t r1, uint32_t direct, bool big) -> int {
@@ -1627,13 +1629,15 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     // enqueue the two chains interleaved so that neither stream starves on the host side
     const size_t n_seg = bounds.size() - 1;
     const size_t s_begin = phase == 2 ? 1 : 0, s_end = phase == 1 ? 1 : n_seg;
+    size_t big_seg = 0;
+    for (size_t s = 1; s < n_seg; ++s) if (bounds[s + 1] - bounds[s] > bounds[big_seg + 1] - bounds[big_seg]) big_seg = s;
     // Order on the sparse stream: K3's direct first segment (fixed slots, counted by the list set-up) and its
     // compaction come BEFORE the K3M stages — a stage's compaction runs over every sparse list and would turn a
     // still-unwritten direct block into an empty list.
     if (k1f && phase != 1) TRY(dense_single_pass());
     for (size_t s = s_begin; s < s_end; ++s) {
         const uint32_t direct = (s == 0 && direct_rows) ? 1u : 0u;
-        const bool big = s + 1 == n_seg;
+        const bool big = s == big_seg;                          // the segment with the most rows: the roofline's launch
         if (big && !k1f) h->stats.last_big_rows = bounds[s + 1] - bounds[s];
         TRY(dense_segment(bounds[s], bounds[s + 1], direct, big));
         TRY(sparse_segment(bounds[s], bounds[s + 1], direct, big));

@@ -13,8 +13,10 @@ from pathlib import Path
 
 import numpy as np
 
+import os
+
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libvoitta_b200.so"
+LIB_PATH = Path(os.environ["VB200_LIB"]) if os.environ.get("VB200_LIB") else HERE / "libvoitta_b200.so"   # (debug build: bounds checks)
 
 TS_MISSING = -(2 ** 63)
 TS_MIN = -(2 ** 63) + 1
