@@ -1,0 +1,84 @@
+#!/usr/bin/env python3
+"""profiles/rNN_results.md from the bench lines under profiles/ (written by tools/summarize_profiles_r2.py).
+Usage: python tools/make_results_md.py [r02]"""
+import json
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+PROF = ROOT / "profiles"
+R = sys.argv[1] if len(sys.argv) > 1 else "r02"
+ORDER = ["cfg4", "cfg1", "cfg2", "cfg3-b1-s1", "cfg3-b1-s50", "cfg3-b256-s50", "cfg5-shard"]
+R1 = {"cfg1": (9.1e3, 0.110), "cfg2": (155e3, 0.441), "cfg3-b1-s1": (3.7e3, 0.272), "cfg3-b1-s50": (559, 1.79),
+      "cfg3-b256-s50": (25.0e3, 10.2), "cfg4": (16.3e3, 62.8), "cfg5-shard": (18.8e3, 218.0)}
+CEIL = {"cfg2": 0.12, "cfg3-b1-s1": 0.06, "cfg3-b1-s50": 1.2, "cfg3-b256-s50": 1.2, "cfg4": 11.9}
+
+
+def load(name):
+    f = PROF / f"{R}_bench_{name}.json"
+    if not f.exists():
+        return None
+    try:
+        return json.loads(f.read_text().strip().splitlines()[-1])
+    except Exception:
+        return None
+
+
+def main():
+    out = [f"# Round 2 — measured on B200 ({R})", "",
+           "Everything here comes from `tools/gpu_final_r2.sh` on one fresh B200 (bench lines `profiles/%s_bench_*.json`, launch lists "
+           "`profiles/%s_launches_*.txt`, ncu `--set full` summaries `profiles/%s_ncu_summary.txt`, SASS mnemonics "
+           "`profiles/%s_sass_summary.txt`).  CUDA events on the launching stream; `value` = batch resident in HBM, `e2e` = pack + "
+           "H2D + kernels + D2H through the public API.  Round-1 numbers from VERDICT.md / DESIGN.md r1 for comparison." % (R, R, R, R), "",
+           "| workload | value q/s | e2e q/s | ms per batch | r1 q/s | r1 ms | speed-up | BASELINE.md ceiling ms | mask | dense | sparse | select | fuse |",
+           "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
+    lines = {}
+    for name in ORDER:
+        d = load(name)
+        if d is None:
+            continue
+        lines[name] = d
+        c, r = d["config"], d["roofline"]
+        msb = d["ms_per_step"] / c["batches_per_step"]
+        p = r["phase_ms_per_batch"]
+        r1 = R1.get(name)
+        out.append(f"| {name} (B={c['queries_per_batch']}, {c['rows_per_gpu']:,} x {c['dim']}) | {d['value']:,.0f} | {d['e2e']['value']:,.0f} | {msb:.3f} | "
+                   f"{r1[0]:,.0f} | {r1[1]} | {d['value'] / r1[0]:.2f}x | {CEIL.get(name, '—')} | {p['mask']:.3f} | {p['dense']:.3f} | {p['sparse']:.3f} | {p['select']:.3f} | {p['fuse']:.3f} |")
+    out += ["", "## Headline configuration (bench.py default: cfg4 weak form, N = 1)", ""]
+    d = lines.get("cfg4")
+    ref = load("reference")
+    if d:
+        r = d["roofline"]
+        out += [f"* value **{d['value']:,.0f} q/s** ({d['ms_per_step']:.2f} ms per 1024-query batch), e2e **{d['e2e']['value']:,.0f} q/s**, "
+                f"{d['gpu_launches']} launches in {d['steps']} steps; clocks {d['clocks']['sm_mhz']} MHz, reasons {d['clocks']['reasons']}, {d['clocks']['samples']} samples over {d['clocks'].get('timed_region_s', 0):.2f} s.",
+                f"* dominant kernel `{r['kernel']}` ({r['launch']}): **{r['achieved']:.0f} {r['unit']} = {100 * r['frac']:.1f} % of the measured {r['bound']} peak** ({r['peak']} {r['unit']}); "
+                f"whole step: {r['step_tflops']:.0f} TFLOP/s = {100 * r['step_tflops'] / 1648.7:.1f} % of the bf16 burst peak, {100 * r['step_tflops'] / 1390.6:.1f} % of the sustained one (north_star asks >= 60 % at batch 1024).",
+                f"* ingest: {d['ingest']['rows']:,} rows in {d['ingest']['upsert_s']:.2f} s + index build {d['ingest']['index_build_s']:.2f} s = {d['ingest']['rows_per_s']:,.0f} rows/s (device-resident blocks).",
+                f"* timeline (two streams): span {d['timeline']['span_ms']:.2f} ms, dense chain busy {d['timeline']['dense_chain_busy_ms']:.2f} ms, sparse chain busy {d['timeline']['sparse_chain_busy_ms']:.2f} ms — "
+                "the chains run side by side but the step is not shorter than their serial sum: the tensor kernel sits at the 1 kW power cap (`sw_power_cap`), and work added next to it lowers its clock."]
+        if d.get("cpu_baseline"):
+            out.append(f"* cpu_baseline (in-run): {d['cpu_baseline']['value']:.3f} q/s on {d['cpu_baseline']['cores']} cores — {d['cpu_baseline']['sample']}")
+        if ref:
+            out.append(f"* reference arm (`--impl reference`): {ref['value']:.3f} q/s on {ref['cpu_baseline']['cores']} cores; value / reference = {d['value'] / ref['value']:,.0f}x, e2e / reference = {d['e2e']['value'] / ref['value']:,.0f}x (the driver computes the official ratio).")
+        if d.get("e2e_api"):
+            a = d["e2e_api"]
+            out.append("* `VectorStoreService.search` (Python lists in, StoredChunk out, limit 20, weighted fusion, folder list + date range): " +
+                       "; ".join(f"{k.replace('threads_', '')} thread(s): {v['queries_per_s']:.0f} q/s, p50 {v['p50_ms']:.2f} ms, p99 {v['p99_ms']:.2f} ms, mean coalesced batch {v['mean_coalesced_batch']:.1f}"
+                                 for k, v in a.items() if k.startswith("threads_")))
+    out += ["", "## e2e through the Python class, per workload (1 thread / 16 threads)", "",
+            "| workload | q/s (1) | p50 ms | p99 ms | q/s (16) | p50 ms | p99 ms | mean batch |", "|---|---|---|---|---|---|---|---|"]
+    for name, d in lines.items():
+        a = d.get("e2e_api")
+        if not a or "threads_1" not in a:
+            continue
+        one, many = a["threads_1"], a.get("threads_16", {})
+        out.append(f"| {name} | {one['queries_per_s']:.0f} | {one['p50_ms']:.2f} | {one['p99_ms']:.2f} | {many.get('queries_per_s', 0):.0f} | {many.get('p50_ms', 0):.2f} | {many.get('p99_ms', 0):.2f} | {many.get('mean_coalesced_batch') or 0:.1f} |")
+    c2 = lines.get("cfg2")
+    if c2 and c2.get("parity_spot_check"):
+        out += ["", f"cfg2 parity spot check against the C oracle inside the bench run: {c2['parity_spot_check']}; cpu_baseline {c2['cpu_baseline']['value']:.1f} q/s on {c2['cpu_baseline']['cores']} cores."]
+    (PROF / f"{R}_results.md").write_text("\n".join(out) + "\n")
+    print("\n".join(out))
+
+
+if __name__ == "__main__":
+    main()
