@@ -1,0 +1,7 @@
+#!/bin/bash
+# Round 2: N-GPU lines exactly as the driver launches them (torchrun): default workload (cfg4 weak form) + reference arm.
+N=${1:-2}
+mkdir -p gpurun_out
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
+timeout 900 $TR bench.py --gpus $N --steps 10 --warmup 5 > gpurun_out/r02_scale_cfg4_g$N.json 2> gpurun_out/r02_scale_cfg4_g$N.err; echo "cfg4 x$N rc=$?"; cut -c1-900 gpurun_out/r02_scale_cfg4_g$N.json; tail -3 gpurun_out/r02_scale_cfg4_g$N.err
+timeout 600 $TR bench.py --gpus $N --impl reference --steps 3 --warmup 1 > gpurun_out/r02_scale_reference_g$N.json 2> gpurun_out/r02_scale_reference_g$N.err; echo "reference x$N rc=$?"; cut -c1-300 gpurun_out/r02_scale_reference_g$N.json

@@ -34,6 +34,7 @@ class ShardedIndex:
         self.df_g: np.ndarray | None = None
         self.n_live_g = 0
         self._bufs: dict = {}
+        self._idf_cache: dict = {}
         # optional all-reduce(MAX) of the list thresholds after the first row segment (see _enqueue).  Off by
         # default: on B200 + NVLink the extra collective (~45 us) costs more than the skipped candidates save at
         # cfg2's shard sizes (measured at 2 and 8 GPUs); VB200_SHARE_TAU=1 enables it (skewed shards).
@@ -80,6 +81,7 @@ class ShardedIndex:
         if self.world > 1:
             dist.all_reduce(n, group=self.group)
         self.n_live_g = int(n.item())
+        self._idf_cache = {}
 
     def finalize_from_queries(self, sparse_batches) -> None:
         """Cheaper variant for static benchmark corpora: only the terms that occur in the given
@@ -94,21 +96,28 @@ class ShardedIndex:
         if sparse is None:
             return None
         out = []
-        N = self.n_live_g
+        cache = self._idf_cache          # term -> ln((N - df + 0.5) / (df + 0.5) + 1), emptied by finalize()
         for s in sparse:
             if s is None or len(s[0]) == 0:
                 out.append(None)
                 continue
-            idx = np.asarray(s[0], dtype=np.uint32)
-            pos = np.searchsorted(self.terms_g, idx)
-            pos_c = np.minimum(pos, max(len(self.terms_g) - 1, 0))
-            hit = (pos < len(self.terms_g)) & (self.terms_g[pos_c] == idx) if len(self.terms_g) else np.zeros(len(idx), bool)
+            terms = s[0].tolist() if isinstance(s[0], np.ndarray) else list(s[0])
             w = []
-            for j, v in enumerate(s[1]):
-                d = float(self.df_g[pos_c[j]]) if hit[j] else 0.0
-                w.append(float(v) * math.log((N - d + 0.5) / (d + 0.5) + 1.0))
-            out.append((list(s[0]), w))
+            for t, v in zip(terms, s[1]):
+                f = cache.get(t)
+                if f is None:
+                    f = cache[t] = self._idf_factor(t)
+                w.append(float(v) * f)
+            out.append((terms, w))
         return out
+
+    def _idf_factor(self, term: int) -> float:
+        N, d = self.n_live_g, 0.0
+        if len(self.terms_g):
+            pos = int(np.searchsorted(self.terms_g, np.uint32(term)))
+            if pos < len(self.terms_g) and int(self.terms_g[pos]) == int(term):
+                d = float(self.df_g[pos])
+        return math.log((N - d + 0.5) / (d + 0.5) + 1.0)
 
     # ---- query --------------------------------------------------------------------------------
     def _buf(self, name, numel):
