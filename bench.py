@@ -377,6 +377,7 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dense-path", type=int, default=0, help="0 auto, 1 GEMV scan, 2 tcgen05 GEMM")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="vb_set_option on the index (A/B runs), repeatable")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-api", action="store_true", help="skip the e2e_api (VectorStoreService.search) section")
     ap.add_argument("--api-threads", type=int, default=16)
@@ -411,6 +412,9 @@ def main():
     ix, keep, (lo, hi), ingest = build_shard(cfg, rank, world, device, torch, synth, engine)
     if args.dense_path:
         ix.set_option("dense_path", args.dense_path)
+    for kv in args.opt:
+        k_, v_ = kv.split("=", 1)
+        ix.set_option(k_, int(v_))
     sh = ShardedIndex(ix, rank, world, device=device)
     obj = [None]
     if rank == 0:

@@ -66,6 +66,24 @@ __device__ __forceinline__ void vb_push_sub(const VbLists& L, uint32_t list, uin
     if (slot < L.sub_cap) L.cand[(size_t)list * L.cap + (size_t)sub * L.sub_cap + slot] = vb_pack_key(score, row);
 }
 
+// List set-up of one search, done by the first n threads of the query-prep launch (it was a launch of its own).
+// cnt0: slots of the first (direct) segment at the front of every list.  `no_direct` (optional, one flag per query): the
+// sparse list of such a query is never written by a direct segment (K3M scores it in stages).  gtau[n..2n) are the
+// single-pass scan's ticket counters.
+struct VbListInit {
+    float* tau; uint32_t* cnt; uint32_t* overflow; uint32_t* gtau;
+    uint32_t n, cnt0;
+    const uint8_t* no_direct;
+    uint32_t n_queries, dense_direct;
+};
+__device__ __forceinline__ void vb_init_list(const VbListInit& a, uint32_t i) {
+    if (i >= a.n) return;
+    a.tau[i] = -INFINITY; a.overflow[i] = 0u; a.gtau[i] = 0u; a.gtau[a.n + i] = 0u;
+    uint32_t c0 = (a.no_direct != nullptr && i >= a.n_queries && a.no_direct[i - a.n_queries] == 1) ? 0u : a.cnt0;
+    if (i < a.n_queries && !a.dense_direct) c0 = 0u;                 // the single-pass scan appends to an empty list
+    for (uint32_t s = 0; s < VB_SUB; ++s) a.cnt[i * VB_SUB + s] = s == 0 ? c0 : 0u;
+}
+
 __device__ __forceinline__ uint4 vb_ldg_stream(const uint4* p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"

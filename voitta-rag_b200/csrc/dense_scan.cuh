@@ -63,9 +63,13 @@ vb_dense_scan_kernel(const VbScanArgs a)
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
         const uint32_t ch = lane + 32u * c;
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-            q[c][e] = ch < a.chunks ? a.q_hat[(size_t)q_idx * a.chunks * 8u + ch * 8u + e] : 0.0f;
+        float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+        if (ch < a.chunks) {
+            const float4* qp = reinterpret_cast<const float4*>(a.q_hat + (size_t)q_idx * a.chunks * 8u + ch * 8u);
+            lo = __ldg(qp); hi = __ldg(qp + 1);
+        }
+        q[c][0] = lo.x; q[c][1] = lo.y; q[c][2] = lo.z; q[c][3] = lo.w;
+        q[c][4] = hi.x; q[c][5] = hi.y; q[c][6] = hi.z; q[c][7] = hi.w;
     }
 
     const uint32_t warps = gridDim.x * (blockDim.x >> 5);
@@ -188,7 +192,7 @@ vb_dense_scan_generic_kernel(const VbScanArgs a)
 #define VB_K1F_THREADS 256
 #define VB_K1F_CAP 2048u           // candidate slots per CTA (16 KB of shared memory: 8 CTAs per SM, full occupancy —
                                    // the first version had 32 KB buffers, 2 CTAs per SM, and ran at half of K1's bandwidth)
-#define VB_K1F_CHECK 4u            // iterations between buffer checks: 8 warps x 32 rows x 4 = 1024 appends at most
+#define VB_K1F_CHECK 4u            // iterations between buffer checks: 8 warps x (8 batches x 4 rows) x 4 = 1024 appends at most
 
 struct VbScan1Args {
     const uint4* rows;
@@ -201,10 +205,14 @@ struct VbScan1Args {
     uint32_t* cnt;
     uint32_t cap, k, mask_words, chunks, n_rows, row_base;
     uint32_t split_shift;       // a warp takes 32 >> split_shift rows of a group (tiny corpora: more warps than groups)
+    uint32_t unit_shift;        // otherwise a warp's unit is 2^unit_shift consecutive groups (0..5)
+    uint32_t* done;             // [n_lists] CTAs of the list that have appended their part (0 before the launch, 0 again after)
+    float* tau;                 // [n_lists] list threshold, raised by the in-kernel merge like vb_compact_kernel does
 };
 
-// descending bitonic sort of P keys (power of two <= VB_K1F_CAP) by all threads of the CTA
-__device__ __forceinline__ void vb_k1f_sort(uint64_t* s, uint32_t P) {
+// descending bitonic sort of P keys (power of two <= VB_K1F_CAP) by all threads of the CTA.  One out-of-line copy
+// serves the scan loop and the final merge: a single-CTA tail is bound by instruction fetch, not by arithmetic.
+__device__ __noinline__ void vb_k1f_sort(uint64_t* s, uint32_t P) {
     for (uint32_t size = 2; size <= P; size <<= 1)
         for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
             __syncthreads();
@@ -237,75 +245,121 @@ vb_dense_scan1_kernel(const VbScan1Args a)
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
         const uint32_t ch = lane + 32u * c;
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-            q[c][e] = ch < a.chunks ? a.q_hat[(size_t)q_idx * a.chunks * 8u + ch * 8u + e] : 0.0f;
+        float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+        if (ch < a.chunks) {
+            const float4* qp = reinterpret_cast<const float4*>(a.q_hat + (size_t)q_idx * a.chunks * 8u + ch * 8u);
+            lo = __ldg(qp); hi = __ldg(qp + 1);
+        }
+        q[c][0] = lo.x; q[c][1] = lo.y; q[c][2] = lo.z; q[c][3] = lo.w;
+        q[c][4] = hi.x; q[c][5] = hi.y; q[c][6] = hi.z; q[c][7] = hi.w;
     }
     if (threadIdx.x == 0) { s_cnt = 0u; s_tau = -INFINITY; }
     __syncthreads();
     float tau = -INFINITY;
+    // Work units.  A warp takes UNITS of 2^unit_shift consecutive 32-row groups (lane l holds the filter word of group
+    // g0 + l: one coalesced load per unit, and the NEXT unit's words are already in flight while this one is scored), or,
+    // on tiny corpora (split_shift > 0), a half / quarter / eighth of one group.  Rows are scored four at a time, and a
+    // batch of four is filled ACROSS the groups of a unit (and across units): under a selective filter (1 % of the rows:
+    // one passing row in three groups) every warp still keeps four rows of loads in flight.  (The first version
+    // walked one group at a time: a dependent filter-word load, then 0..1 rows, per iteration.)
     const uint32_t n_groups = (a.n_rows + 31u) >> 5;
-    const uint32_t n_slots = n_groups << a.split_shift;                  // (group, part of the group) pairs
+    const uint32_t U = 1u << a.unit_shift;
+    const uint32_t n_units = a.split_shift ? (n_groups << a.split_shift) : ((n_groups + U - 1u) >> a.unit_shift);
     const uint32_t part_rows = 32u >> a.split_shift;
     const uint32_t stride = gridDim.x * (VB_K1F_THREADS / 32u);
-    const uint32_t n_iter = (n_slots + stride - 1u) / stride;           // the same for every warp of the grid: barriers are uniform
-    for (uint32_t it = 0; it < n_iter; ++it) {
-        const uint32_t slot_id = it * stride + blockIdx.x * (VB_K1F_THREADS / 32u) + warp;
-        if (slot_id < n_slots) {
-            const uint32_t g = slot_id >> a.split_shift, part = slot_id & ((1u << a.split_shift) - 1u);
-            uint32_t bits = mask ? mask[g] : 0xffffffffu;
-            const uint32_t row0 = g << 5;
-            if (row0 + 32u > a.n_rows) bits &= (1u << (a.n_rows - row0)) - 1u;
-            if (a.split_shift) bits &= ((part_rows == 32u ? 0xffffffffu : ((1u << part_rows) - 1u)) << (part * part_rows));
-            const float invn = (bits != 0u && row0 + lane < a.n_rows) ? a.inv_norm[row0 + lane] : 0.0f;
-            while (bits) {
-                int r[ROWS];
+    constexpr uint32_t NONE = 0xffffffffu;
+    auto load_unit = [&](uint32_t u) -> uint32_t {                      // this lane's filter word of unit u (0 past the end)
+        if (u >= n_units) return 0u;
+        uint32_t g, bits;
+        if (a.split_shift) {
+            if (lane != 0u) return 0u;
+            g = u >> a.split_shift;
+            bits = mask ? mask[g] : 0xffffffffu;
+            const uint32_t part = u & ((1u << a.split_shift) - 1u);
+            bits &= ((1u << part_rows) - 1u) << (part * part_rows);
+        } else {
+            g = (u << a.unit_shift) + lane;
+            if (lane >= U || g >= n_groups) return 0u;
+            bits = mask ? mask[g] : 0xffffffffu;
+        }
+        if ((g << 5) + 32u > a.n_rows) bits &= (1u << (a.n_rows - (g << 5))) - 1u;
+        return bits;
+    };
+    auto unit_g0 = [&](uint32_t u) -> uint32_t { return a.split_shift ? (u >> a.split_shift) : (u << a.unit_shift); };
+    uint32_t u_cur = blockIdx.x * (VB_K1F_THREADS / 32u) + warp;
+    uint32_t bits = load_unit(u_cur), g0 = unit_g0(u_cur);
+    uint32_t u_nxt = u_cur + stride;
+    uint32_t bits_nxt = load_unit(u_nxt);
+    uint32_t nz = __ballot_sync(0xffffffffu, bits != 0u);               // lanes (groups) of the current unit with rows left
+    bool more = true;                                                   // CTA-uniform: some warp still has rows
+    for (uint32_t it = 0; more; ++it) {
+        // up to 8 batches of 4 rows per warp and iteration: at most 8 x 32 = 256 appends per CTA and iteration
+        for (uint32_t bt = 0; bt < 8u; ++bt) {
+            uint32_t r[ROWS];
 #pragma unroll
-                for (int k = 0; k < ROWS; ++k) { r[k] = bits ? (__ffs(bits) - 1) : -1; bits &= bits - 1u; }
-                uint4 v[ROWS][NCH];
+            for (int k = 0; k < ROWS; ++k) {
+                while (nz == 0u && u_cur < n_units) {                   // unit exhausted: the prefetched one becomes current
+                    u_cur = u_nxt; bits = bits_nxt; g0 = unit_g0(u_cur);
+                    u_nxt += stride; bits_nxt = load_unit(u_nxt);
+                    nz = __ballot_sync(0xffffffffu, bits != 0u);
+                }
+                if (nz) {
+                    const uint32_t j = __ffs(nz) - 1u;
+                    uint32_t bj = __shfl_sync(0xffffffffu, bits, j);
+                    r[k] = ((g0 + j) << 5) + (__ffs(bj) - 1u);
+                    bj &= bj - 1u;
+                    if (lane == j) bits = bj;
+                    if (bj == 0u) nz &= nz - 1u;
+                } else r[k] = NONE;
+            }
+            if (r[0] == NONE) break;                                    // warp-uniform: nothing left for this warp
+            uint32_t myr = r[0];
 #pragma unroll
-                for (int k = 0; k < ROWS; ++k)
+            for (int k = 1; k < ROWS; ++k)
+                if (lane == (uint32_t)k) myr = r[k];
+            const float inv_r = (lane < (uint32_t)ROWS && myr != NONE) ? a.inv_norm[myr] : 0.0f;
+            uint4 v[ROWS][NCH];
 #pragma unroll
-                    for (int c = 0; c < NCH; ++c) {
-                        const uint32_t ch = lane + 32u * c;
-                        v[k][c] = (r[k] >= 0 && ch < a.chunks) ? vb_ldg_stream(a.rows + (size_t)(row0 + r[k]) * a.chunks + ch)
-                                                                : make_uint4(0u, 0u, 0u, 0u);
-                    }
+            for (int k = 0; k < ROWS; ++k)
 #pragma unroll
-                for (int k = 0; k < ROWS; ++k)
-#pragma unroll
-                    for (int c = 0; c < NCH; ++c) vb_keep_loaded(v[k][c]);
-                float acc[ROWS];
-#pragma unroll
-                for (int k = 0; k < ROWS; ++k) {
-                    acc[k] = 0.0f;
-#pragma unroll
-                    for (int c = 0; c < NCH; ++c) acc[k] = vb_dot8(v[k][c], q[c], acc[k]);
+                for (int c = 0; c < NCH; ++c) {
+                    const uint32_t ch = lane + 32u * c;
+                    v[k][c] = (r[k] != NONE && ch < a.chunks) ? vb_ldg_stream(a.rows + (size_t)r[k] * a.chunks + ch)
+                                                              : make_uint4(0u, 0u, 0u, 0u);
                 }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
+            for (int k = 0; k < ROWS; ++k)
 #pragma unroll
-                    for (int k = 0; k < ROWS; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-                float mine = acc[0];
-                int myr = r[0];
+                for (int c = 0; c < NCH; ++c) vb_keep_loaded(v[k][c]);
+            float acc[ROWS];
 #pragma unroll
-                for (int k = 1; k < ROWS; ++k)
-                    if (lane == (uint32_t)k) { mine = acc[k]; myr = r[k]; }
-                const float inv_r = __shfl_sync(0xffffffffu, invn, myr < 0 ? 0 : myr);
-                if (lane < (uint32_t)ROWS && myr >= 0) {
-                    const float s = mine * inv_r;
-                    if (s >= tau) {                                     // ties stay: rows do not arrive in row order
-                        const uint32_t slot = atomicAdd(&s_cnt, 1u);
-                        if (slot < VB_K1F_CAP) s_keys[slot] = vb_pack_key(s, a.row_base + row0 + (uint32_t)myr);
-                    }
+            for (int k = 0; k < ROWS; ++k) {
+                acc[k] = 0.0f;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) acc[k] = vb_dot8(v[k][c], q[c], acc[k]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int k = 0; k < ROWS; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+            float mine = acc[0];
+#pragma unroll
+            for (int k = 1; k < ROWS; ++k)
+                if (lane == (uint32_t)k) mine = acc[k];
+            if (lane < (uint32_t)ROWS && myr != NONE) {
+                const float s = mine * inv_r;
+                if (s >= tau) {                                         // ties stay: rows do not arrive in row order
+                    const uint32_t slot = atomicAdd(&s_cnt, 1u);
+                    if (slot < VB_K1F_CAP) s_keys[slot] = vb_pack_key(s, a.row_base + myr);
                 }
             }
         }
-        // every VB_K1F_CHECK iterations (and after the last one): re-select if the next stretch could overflow
-        const bool last = it + 1u == n_iter;
-        if (last || (it + 1u) % VB_K1F_CHECK == 0u) {
-            __syncthreads();
-            const uint32_t c = s_cnt;                                   // <= CAP: a stretch appends at most CAP/2, selection leaves <= k <= CAP/2... see host check
+        // every VB_K1F_CHECK iterations: is anybody still working?  re-select if the next stretch could overflow
+        if ((it + 1u) % VB_K1F_CHECK == 0u) {
+            more = __syncthreads_or((nz != 0u || u_cur < n_units) ? 1 : 0) != 0;
+            const bool last = !more;
+            const uint32_t c = s_cnt;                                   // <= CAP: a stretch appends at most CAP/2, a selection leaves <= k <= CAP/2
+            VB_CHECK(c <= VB_K1F_CAP);
             if (last || c > VB_K1F_CAP - VB_K1F_CHECK * VB_K1F_THREADS) {
                 uint32_t P = 2;
                 while (P < c) P <<= 1;
@@ -320,14 +374,17 @@ vb_dense_scan1_kernel(const VbScan1Args a)
                     }
                 }
             }
-            if (threadIdx.x == 0) {                                     // best threshold known anywhere
-                const uint32_t o = *reinterpret_cast<volatile uint32_t*>(a.gtau + list);
-                s_tau = o ? __uint_as_float(vb_ordered_f32(o)) : -INFINITY;
+            if (!last) {
+                if (threadIdx.x == 0) {                                 // best threshold known anywhere
+                    const uint32_t o = *reinterpret_cast<volatile uint32_t*>(a.gtau + list);
+                    s_tau = o ? __uint_as_float(vb_ordered_f32(o)) : -INFINITY;
+                }
+                __syncthreads();
+                tau = s_tau;
             }
-            __syncthreads();
-            tau = s_tau;
         }
     }
+    __syncthreads();
     // local top-k' -> the list.  Only entries at or above the best threshold known anywhere can be in the global
     // top-k' (the local list is sorted: they are a prefix); the CTA reserves that many slots with ONE atomic on the
     // list's counter (pre-set to 0 by the list set-up; at most G * k' <= cap in total) and the merge sees a few hundred
@@ -349,4 +406,34 @@ vb_dense_scan1_kernel(const VbScan1Args a)
     uint64_t* out = a.cand + (size_t)list * a.cap + s_base;
     VB_CHECK(s_base + s_take <= a.cap);
     for (uint32_t i = threadIdx.x; i < s_take; i += VB_K1F_THREADS) out[i] = s_keys[i];
+    // ---- merge, by the last CTA of the list to get here (what a vb_compact_kernel launch did before: ~25 us of
+    // launch + cold instruction fetch for a few hundred keys).  Every CTA publishes its keys (fence), then takes a
+    // ticket; the CTA with the last ticket sees every other CTA's keys.
+    __shared__ uint32_t s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(a.done + list, 1u) == gridDim.x - 1u ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    uint64_t* in = a.cand + (size_t)list * a.cap;
+    const uint32_t total = min(*reinterpret_cast<volatile uint32_t*>(a.cnt + (size_t)list * VB_SUB), a.cap);
+    uint32_t kept = 0;
+    for (uint32_t pos = 0; pos < total;) {                            // 2048 slots: (kept so far) + the next stretch of keys
+        const uint32_t take = min(VB_K1F_CAP - kept, total - pos);
+        for (uint32_t i = threadIdx.x; i < take; i += VB_K1F_THREADS) s_keys[kept + i] = __ldcg(in + pos + i);
+        pos += take;
+        const uint32_t c = kept + take;
+        uint32_t P = 2;
+        while (P < c) P <<= 1;
+        for (uint32_t i = c + threadIdx.x; i < P; i += VB_K1F_THREADS) s_keys[i] = 0ull;
+        vb_k1f_sort(s_keys, P);
+        kept = c < a.k ? c : a.k;
+    }
+    for (uint32_t i = threadIdx.x; i < kept; i += VB_K1F_THREADS) in[i] = s_keys[i];
+    if (threadIdx.x == 0) {
+        a.cnt[(size_t)list * VB_SUB] = kept;                          // sub-ranges 1.. were never used by this pass
+        a.tau[list] = fmaxf(a.tau[list], kept >= a.k ? vb_key_score(s_keys[a.k - 1u]) : -INFINITY);
+        a.done[list] = 0u;
+    }
 }

@@ -110,10 +110,11 @@ vb_ingest_bf16_kernel(const __nv_bfloat16* __restrict__ src, uint32_t n, uint32_
 __global__ void __launch_bounds__(128)
 vb_prep_query_kernel(const float* __restrict__ q, uint32_t dim, uint32_t d_pad, uint32_t n_queries,
                      uint32_t sub, uint32_t split, float* __restrict__ q_hat, __nv_bfloat16* __restrict__ q_bf16,
-                     float* __restrict__ q_scale)
+                     float* __restrict__ q_scale, const VbListInit li)
 {
     __shared__ double red[4];
     const uint32_t b = blockIdx.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < li.n; i += gridDim.x * blockDim.x) vb_init_list(li, i);
     double ss = 0.0;
     for (uint32_t c = threadIdx.x; c < dim; c += blockDim.x) {
         const double v = (double)q[(size_t)b * dim + c];

@@ -120,6 +120,7 @@ struct Batch {
     uint32_t* cnt = nullptr;
     uint32_t* overflow = nullptr;
     uint32_t* gtau = nullptr;                  // [n_lists] K1F: threshold shared by the CTAs of one pass (ordered score, 0 = none)
+    uint32_t* done = nullptr;                  // [n_lists] K1F: CTAs that have appended their part (the last one merges)
     // fusion / output
     double w_sparse = 0.0;
     bool want_branches = false, valid = false, need_corpus = true;
@@ -230,18 +231,6 @@ static void dev_free(vb_index* h, DevBuf& b) {
 // ------------------------------------------------------------------------------------------------
 // tiny utility kernels
 // ------------------------------------------------------------------------------------------------
-// cnt0: slots of the first (direct) segment at the front of every list.  `no_direct` (optional, one flag per
-// query): the sparse list of such a query is never written by a direct segment (K3M scores it in stages).
-__global__ void vb_init_lists_kernel(float* tau, uint32_t* cnt, uint32_t* overflow, uint32_t* gtau, uint32_t n, uint32_t cnt0,
-                                     const uint8_t* no_direct, uint32_t n_queries, uint32_t dense_direct) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        tau[i] = -INFINITY; overflow[i] = 0u; gtau[i] = 0u;
-        uint32_t c0 = (no_direct != nullptr && i >= n_queries && no_direct[i - n_queries] == 1) ? 0u : cnt0;
-        if (i < n_queries && !dense_direct) c0 = 0u;             // K1F appends to an empty list
-        for (uint32_t s = 0; s < VB_SUB; ++s) cnt[i * VB_SUB + s] = s == 0 ? c0 : 0u;
-    }
-}
 __global__ void vb_fill_i64_kernel(int64_t* p, uint64_t n, int64_t v) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -266,11 +255,28 @@ __global__ void vb_find_tail_kernel(const uint64_t* keys, uint64_t n, uint64_t* 
 static int g_delta_smem_max = 48 * 1024;
 
 #define VB_K1F_MAX_B 8u
-// CTAs per query of the single-pass scan: full occupancy (8 x 256 threads per SM) for the usual small k'; fewer for
+// CTAs per query of the single-pass scan: ONE wave of resident CTAs (the register file holds 5 x 256 threads per SM;
+// round 2 launched 8 per SM = 1.6 waves, so the kernel lasted two CTA lifetimes: 52 us for 77 MB at cfg1); fewer for
 // large k' so that the merge of G * k' keys stays short
-static uint32_t vb_k1f_grid(int sm_count, uint32_t k, uint32_t B) {
-    const uint32_t per_sm = k <= 64u ? 8u : (k <= 256u ? 4u : 2u);
-    return std::max<uint32_t>(1u, (uint32_t)sm_count * per_sm / std::min<uint32_t>(B, 4u));
+static uint32_t vb_k1f_resident(int d_pad) {
+    static int resident[5] = {0, 0, 0, 0, 0};
+    const int nch = std::min(4, std::max(1, (d_pad / 8 + 31) / 32));
+    if (!resident[nch]) {
+        int v = 0;
+        cudaError_t e = cudaErrorUnknown;
+        switch (nch) {
+            case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, vb_dense_scan1_kernel<1>, VB_K1F_THREADS, 0); break;
+            case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, vb_dense_scan1_kernel<2>, VB_K1F_THREADS, 0); break;
+            case 3: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, vb_dense_scan1_kernel<3>, VB_K1F_THREADS, 0); break;
+            default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, vb_dense_scan1_kernel<4>, VB_K1F_THREADS, 0); break;
+        }
+        resident[nch] = (e == cudaSuccess && v > 0) ? std::min(v, 8) : 2;
+    }
+    return (uint32_t)resident[nch];
+}
+static uint32_t vb_k1f_grid(int sm_count, uint32_t k, uint32_t B, int d_pad) {
+    const uint32_t per_sm = std::min<uint32_t>(vb_k1f_resident(d_pad), k <= 64u ? 8u : (k <= 256u ? 4u : 2u));
+    return std::max<uint32_t>(1u, (uint32_t)sm_count * per_sm / std::max<uint32_t>(B, 1u));
 }
 
 static unsigned grid_for(uint64_t n, unsigned block, unsigned max_blocks = 148u * 16u) {
@@ -1238,16 +1244,17 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     // roomier lists (up to 256 MB in all) let K3M take larger posting stages: fewer launches on small corpora
     need_cap = std::max<uint32_t>(need_cap, (uint32_t)std::min<uint64_t>(align_up((size_t)16 * 128 * b.k, 4096), (256ull << 20) / ((uint64_t)b.n_lists * 8u) / 4096u * 4096u));
     // K1F (single-pass scan for tiny batches) leaves one local top-k' per CTA in the list before the merge
-    if (b.B <= VB_K1F_MAX_B) need_cap = std::max<uint32_t>(need_cap, (uint32_t)align_up((size_t)vb_k1f_grid(h->sm_count, b.k, b.B) * b.k, 4096));
+    if (b.B <= VB_K1F_MAX_B) need_cap = std::max<uint32_t>(need_cap, (uint32_t)align_up((size_t)vb_k1f_grid(h->sm_count, b.k, b.B, h->d_pad) * b.k, 4096));
     // tiny batches are launch-latency bound: roomy lists (a few MB) let K3M take 1024x larger posting stages
     if (b.B <= VB_K1F_MAX_B) need_cap = std::max<uint32_t>(need_cap, 262144u);
     h->cand_cap = need_cap;
     TRY(dev_reserve(h, h->cand, (size_t)b.n_lists * need_cap * 8, false));
-    TRY(dev_reserve(h, h->lists, (size_t)b.n_lists * (12 + 4 * VB_SUB), false));
+    TRY(dev_reserve(h, h->lists, (size_t)b.n_lists * (16 + 4 * VB_SUB), false));
     b.tau = h->lists.as<float>();
     b.overflow = h->lists.as<uint32_t>() + b.n_lists;
     b.cnt = h->lists.as<uint32_t>() + 2 * (size_t)b.n_lists;      // [n_lists][VB_SUB]
     b.gtau = h->lists.as<uint32_t>() + (2 + (size_t)VB_SUB) * b.n_lists;
+    b.done = h->lists.as<uint32_t>() + (3 + (size_t)VB_SUB) * b.n_lists;
     b.h2d_bytes = ar.off;
     h->stats.last_h2d_bytes = ar.off;
     // output block layout
@@ -1267,13 +1274,22 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
 
 // direct_rows > 0: the first segment stores its keys at fixed slots [0, direct_rows) of every
 // list (no atomics); slots nobody writes (masked rows, rows without postings) must read as empty.
-static int init_lists(vb_index* h, const Batch& b, uint32_t direct_rows, bool ms_staged = false, bool dense_direct = true) {
-    vb_init_lists_kernel<<<(b.n_lists + 255) / 256, 256, 0, h->stream>>>(b.tau, b.cnt, b.overflow, b.gtau, b.n_lists, direct_rows,
-                                                                          ms_staged ? b.d_qms : nullptr, b.B, dense_direct ? 1u : 0u);
-    CKK("vb_init_lists_kernel");
-    ++h->stats.last_launches;
+static int init_lists(vb_index* h, const Batch& b, uint32_t direct_rows) {
     if (direct_rows)
         CK(cudaMemset2DAsync(h->cand.p, (size_t)h->cand_cap * 8, 0, (size_t)direct_rows * 8, b.n_lists, h->stream));
+    return 0;
+}
+// empty lists for the paths that score nothing (empty index, merge of gathered shard lists)
+__global__ void vb_init_lists_kernel(const VbListInit li) {
+    vb_init_list(li, blockIdx.x * blockDim.x + threadIdx.x);
+}
+static int empty_lists(vb_index* h, const Batch& b) {
+    VbListInit li{};
+    li.tau = b.tau; li.cnt = b.cnt; li.overflow = b.overflow; li.gtau = b.gtau; li.n = b.n_lists; li.cnt0 = 0;
+    li.no_direct = nullptr; li.n_queries = b.B; li.dense_direct = 1u;
+    vb_init_lists_kernel<<<(b.n_lists + 255) / 256, 256, 0, h->stream>>>(li);
+    CKK("vb_init_lists_kernel");
+    ++h->stats.last_launches;
     return 0;
 }
 
@@ -1366,19 +1382,22 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     // (on large corpora the segmented K1 streams faster — no per-stretch barriers — and its launches are noise there:
     //  cfg3 10M rows, B = 1: K1 1.65 ms, K1F 1.83 ms; cfg1 100k rows: K1 59 us + 3 selects, K1F 48 us + 1 merge)
     const bool k1f = path == 1 && !safe_mode && h->opt_k1f && (h->opt_k1f > 1 || n <= (2u << 20)) && b.B <= VB_K1F_MAX_B && (h->d_pad / 8 + 31) / 32 <= 4 &&
-                     b.k <= VB_K1F_CAP / 2u && (uint64_t)vb_k1f_grid(h->sm_count, b.k, b.B) * b.k <= h->cand_cap;
+                     b.k <= VB_K1F_CAP / 2u && (uint64_t)vb_k1f_grid(h->sm_count, b.k, b.B, h->d_pad) * b.k <= h->cand_cap;
     // the first segment writes its keys to fixed slots at the front of the list (no atomics) — unless nobody runs
     // a first segment: K1F scans in one pass, K3M in posting stages
     const bool k3_direct = do_sparse && (!ms_staged || b.n_dir > 0);
     const uint32_t direct_rows = (bounds[1] <= h->cand_cap && (!k1f || k3_direct)) ? bounds[1] : 0u;
-    if (phase != 2) TRY(init_lists(h, b, direct_rows, ms_staged, !k1f));
-    // query prep (fp32 unit queries for K1, packed bf16 operand for K2)
+    if (phase != 2) TRY(init_lists(h, b, direct_rows));
+    // list set-up + query prep (fp32 unit queries for K1, packed bf16 operand for K2) in ONE launch
     TRY(dev_reserve(h, h->q_hat, (size_t)b.B * h->d_pad * 4, false));
     TRY(dev_reserve(h, h->q_bf16, (size_t)(2 * ((size_t)b.B + 256)) * h->d_pad * 2, false));
     TRY(dev_reserve(h, h->q_scale, (size_t)b.B * 4, false));
     if (phase != 2) {
+        VbListInit li{};
+        li.tau = b.tau; li.cnt = b.cnt; li.overflow = b.overflow; li.gtau = b.gtau; li.n = b.n_lists; li.cnt0 = direct_rows;
+        li.no_direct = ms_staged ? b.d_qms : nullptr; li.n_queries = b.B; li.dense_direct = k1f ? 0u : 1u;
         vb_prep_query_kernel<<<b.B, 128, 0, h->stream>>>(b.d_q, (uint32_t)h->dim, (uint32_t)h->d_pad, b.B, plan.sub, plan.split,
-                                                         h->q_hat.as<float>(), h->q_bf16.as<__nv_bfloat16>(), h->q_scale.as<float>());
+                                                         h->q_hat.as<float>(), h->q_bf16.as<__nv_bfloat16>(), h->q_scale.as<float>(), li);
         CKK("vb_prep_query_kernel");
         ++h->stats.last_launches;
     }
@@ -1411,11 +1430,17 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         a.q_hat = h->q_hat.as<float>(); a.gtau = b.gtau; a.cand = h->cand.as<uint64_t>(); a.cnt = b.cnt;
         a.cap = h->cand_cap; a.k = b.k; a.mask_words = b.mask_words; a.chunks = (uint32_t)h->d_pad / 8; a.n_rows = n;
         a.row_base = (uint32_t)h->row_base;
-        const dim3 grid(vb_k1f_grid(h->sm_count, b.k, b.B), b.B);
+        a.done = b.done; a.tau = b.tau;
+        const dim3 grid(vb_k1f_grid(h->sm_count, b.k, b.B, h->d_pad), b.B);
         // small corpora: fewer 32-row groups than warps — give each warp a half / quarter / eighth of a group
         const uint32_t n_groups = (n + 31u) / 32u, n_warps = grid.x * (VB_K1F_THREADS / 32u);
         a.split_shift = 0;
         while (a.split_shift < 3u && (n_groups << (a.split_shift + 1u)) <= n_warps) ++a.split_shift;
+        // large corpora: units of 2..32 groups (one coalesced filter-word load per unit, row batches filled across its
+        // groups), as long as every warp still gets >= 4 units (static interleaved assignment: +-1 unit of imbalance)
+        a.unit_shift = 0;
+        if (!a.split_shift)
+            while (a.unit_shift < 5u && (n_groups >> (a.unit_shift + 1u)) >= 4u * n_warps) ++a.unit_shift;
         switch ((a.chunks + 31) / 32) {
             case 1: vb_dense_scan1_kernel<1><<<grid, VB_K1F_THREADS, 0, sd>>>(a); break;
             case 2: vb_dense_scan1_kernel<2><<<grid, VB_K1F_THREADS, 0, sd>>>(a); break;
@@ -1424,12 +1449,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         }
         CKK("vb_dense_scan1_kernel");
         ++h->stats.last_launches;
-        prof_end(h, pi, sd);
-        const int ps = prof_begin(h, PH_SELECT, sd);
-        vb_compact_kernel<<<b.B, VB_COMPACT_THREADS, 0, sd>>>(make_lists(h, b, true), b.tau, b.overflow, b.k, 0u, h->cand_cap);
-        CKK("vb_compact_kernel");
-        ++h->stats.last_launches;
-        prof_end(h, ps, sd);
+        prof_end(h, pi, sd);                                    // (the merge of the per-CTA lists happens inside: last CTA)
         h->stats.last_big_rows = n;
         h->stats.last_dense_path = 3u;                          // K1F
         return 0;
@@ -1814,7 +1834,7 @@ extern "C" int vb_run_local_begin(vb_index* h) {
     CK(cudaSetDevice(h->device));
     h->stats.last_launches = 0;
     CK(cudaEventRecord(h->ev0s[h->cur], h->stream));
-    if (h->n_rows == 0) TRY(init_lists(h, b, 0));
+    if (h->n_rows == 0) TRY(empty_lists(h, b));
     else TRY(run_branches(h, b, h->staged_safe, 1));
     b.begun = true;
     return 0;
@@ -1856,7 +1876,7 @@ extern "C" int vb_run_local(vb_index* h, uint64_t* cand_dev) {
         h->stats.last_launches = 0;
         CK(cudaEventRecord(h->ev0s[h->cur], h->stream));
         if (h->n_rows == 0) {
-            TRY(init_lists(h, h->staged_s[h->cur], 0));
+            TRY(empty_lists(h, h->staged_s[h->cur]));
         } else {
             TRY(run_branches(h, h->staged_s[h->cur], h->staged_safe));
         }
@@ -1956,7 +1976,7 @@ extern "C" int vb_merge_fuse(vb_index* h, const vb_query_batch* q, uint32_t n_sh
     TRY(vb_stage(h, q, wants_branches(out), 0));
     CK(cudaEventRecord(h->ev0s[h->cur], h->stream));
     h->stats.last_launches = 0;
-    TRY(init_lists(h, h->staged_s[h->cur], 0));
+    TRY(empty_lists(h, h->staged_s[h->cur]));
     TRY(vb_run_fuse(h, n_shards, gathered_dev));
     int32_t overflowed = 0;
     TRY(vb_fetch(h, out, &overflowed));
