@@ -41,6 +41,15 @@ def build_debug() -> Path:
     return LIB_DEBUG
 
 
+def build_variant(name: str, *defines: str) -> Path:
+    """A/B builds (tools/gpu_r2_m.sh): the library with extra -D flags as libvoitta_b200_<name>.so; select with VB200_LIB."""
+    out = HERE / f"libvoitta_b200_{name}.so"
+    r = subprocess.run([nvcc_path(), *FLAGS, *[f"-D{d}" for d in defines], "-o", str(out), str(SRC)], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB

@@ -262,7 +262,7 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         // mask, ONE warp vote per 16-column chunk decides whether the (rare) append path runs.
         const uint32_t quad = warp & 3u;
         const uint32_t half = (warp - 2u) >> 2;            // 0: even chunks, 1: odd chunks
-        const uint32_t tau_addr = vb_smem_u32(tau_s), mof_addr = vb_smem_u32(mof_s);
+        const uint32_t tau_addr = vb_smem_u32(tau_s), mof_addr = vb_smem_u32(mof_s), qs_addr = vb_smem_u32(qs_s), tex_addr = vb_smem_u32(tex_s);
         const uint32_t mw_addr = vb_smem_u32(mw_s + (warp - 2u) * VB_GEMM_MAX_FILTERS);
         uint32_t* mw = mw_s + (warp - 2u) * VB_GEMM_MAX_FILTERS;   // private: the two warps of a quadrant may be one tile apart
         constexpr uint32_t mode = (uint32_t)MODE;
@@ -338,27 +338,16 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                         }
                     }
                 } else {
-                    // rare path, entered per COLUMN: mm has a bit for every column in which some row of the warp
-                    // survived the pre-threshold.  Early segments (weak thresholds) hit this for most chunks, and
-                    // running all 16 columns' atomics for one survivor made those segments epilogue-bound; the
-                    // warp-uniform test skips the columns without survivors.  Slots of a column's survivors are
-                    // reserved (predicated atomic), then the key is stored.
+                    // rare path: mm has a bit for every column in which some row of the warp survived the
+                    // pre-threshold (warp-uniform) — a COMPACT loop over those columns (vb_append_flagged)
                     const uint32_t mm = __reduce_or_sync(0xffffffffu, m);
-                    if (mm != 0u) {
-                        const uint32_t sub = blockIdx.x & a.lists.sub_mask;
-#pragma unroll
-                        for (uint32_t j = 0; j < 16u; ++j) {
-                            if (!((mm >> j) & 1u)) continue;                     // warp-uniform
-                            const float fs = final_score(j);
-                            const bool keep = ((m >> j) & 1u) && (split || fs > tex_s[c0 + j]);   // exact comparison on the scaled score
-                            if (keep) {
-                                const uint32_t slot = atomicAdd(a.lists.cnt + (size_t)(a.q_begin + c0 + j) * VB_SUB + sub, 1u);
-                                if (slot < a.lists.sub_cap)
-                                    a.lists.cand[(size_t)(a.q_begin + c0 + j) * a.lists.cap + (size_t)sub * a.lists.sub_cap + slot] =
-                                        vb_pack_key(fs, a.row_base + row);
-                            }
-                        }
-                    }
+                    if (mm != 0u)
+                        vb_append_flagged(a.lists, a.q_begin + c0, blockIdx.x & a.lists.sub_mask, mm, m, lane, (1u << lane) - 1u, a.row_base + row,
+                                          [&](uint32_t j) -> float {
+                                              if (split) return (__uint_as_float(vb_sel16(v, j)) + __uint_as_float(vb_sel16(w, j))) * invn;
+                                              return __uint_as_float(vb_sel16(v, j)) * invn * __uint_as_float(vb_lds_u32(qs_addr + (c0 + j) * 4u));
+                                          },
+                                          [&](uint32_t j, float fs) -> bool { return split || fs > __uint_as_float(vb_lds_u32(tex_addr + (c0 + j) * 4u)); });
                 }
             };
             uint32_t va[16], vb[16], wa[16], wb[16];
@@ -441,6 +430,8 @@ vb_dense_gemm_tiled_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
     float* tex_s = reinterpret_cast<float*>(mof_s + VB_TILED_MAX_Q);          // [VB_TILED_MAX_Q] exact thresholds
     float* qs_s = tex_s + VB_TILED_MAX_Q;                                     // [VB_TILED_MAX_Q] query scales
     uint32_t* mw_s = reinterpret_cast<uint32_t*>(qs_s + VB_TILED_MAX_Q);      // [8 epilogue warps][VB_GEMM_MAX_FILTERS]
+    uint64_t* pk_s = reinterpret_cast<uint64_t*>(mw_s + 8u * VB_GEMM_MAX_FILTERS);   // [8 epilogue warps][VB_PEND] parked keys
+    uint32_t* pl_s = reinterpret_cast<uint32_t*>(pk_s + 8u * VB_PEND);               // [8 epilogue warps][VB_PEND] their lists
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t S = a.stages;
@@ -524,12 +515,15 @@ vb_dense_gemm_tiled_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
         //       16-column chunks (even / odd); branch-free compare, one vote per chunk =====
         const uint32_t quad = warp & 3u;
         const uint32_t half = (warp - 2u) >> 2;
-        const uint32_t tau_addr = vb_smem_u32(tau_s), mof_addr = vb_smem_u32(mof_s);
+        const uint32_t tau_addr = vb_smem_u32(tau_s), mof_addr = vb_smem_u32(mof_s), qs_addr = vb_smem_u32(qs_s), tex_addr = vb_smem_u32(tex_s);
         const uint32_t mw_addr = vb_smem_u32(mw_s + (warp - 2u) * VB_GEMM_MAX_FILTERS);
         uint32_t* mw = mw_s + (warp - 2u) * VB_GEMM_MAX_FILTERS;   // private: the two warps of a quadrant may be one tile apart
         constexpr uint32_t mode = (uint32_t)MODE;
         const float qnan = __int_as_float(0x7fc00000);
         const uint32_t sub = blockIdx.x & a.lists.sub_mask;
+        const uint32_t lane_lt = (1u << lane) - 1u;
+        const uint32_t pk_addr = vb_smem_u32(pk_s + (warp - 2u) * VB_PEND), pl_addr = vb_smem_u32(pl_s + (warp - 2u) * VB_PEND);
+        uint32_t pn = 0u;                                     // parked candidates of this warp (warp-uniform)
         uint32_t it = 0;
         for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const uint32_t tile = a.tile_begin + t;
@@ -595,22 +589,16 @@ vb_dense_gemm_tiled_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
                             }
                         }
                     } else {
-                        // rare path per COLUMN (see the resident kernel): only columns with a survivor somewhere in the
-                        // warp run the exact comparison, the slot reservation and the store
+                        // rare path (see the resident kernel): a COMPACT loop over the flagged columns
                         const uint32_t mm = __reduce_or_sync(0xffffffffu, m);
-                        if (mm != 0u) {
-#pragma unroll
-                            for (uint32_t jj = 0; jj < 16u; ++jj) {
-                                if (!((mm >> jj) & 1u)) continue;                 // warp-uniform
-                                const float fs = __uint_as_float(v[jj]) * invn * qs_s[qoff + c0 + jj];
-                                if (((m >> jj) & 1u) && fs > tex_s[qoff + c0 + jj]) {
-                                    const uint32_t slot = atomicAdd(a.lists.cnt + (size_t)(a.q_begin + qoff + c0 + jj) * VB_SUB + sub, 1u);
-                                    if (slot < a.lists.sub_cap)
-                                        a.lists.cand[(size_t)(a.q_begin + qoff + c0 + jj) * a.lists.cap + (size_t)sub * a.lists.sub_cap + slot] =
-                                            vb_pack_key(fs, a.row_base + row);
-                                }
-                            }
-                        }
+                        if (mm != 0u)
+#ifdef VB_K2T_DIRECT_APPEND
+                            vb_append_flagged(a.lists, a.q_begin + qoff + c0, sub, mm, m, lane, lane_lt, a.row_base + row,
+#else
+                            pn = vb_park_flagged(a.lists, a.q_begin + qoff + c0, sub, mm, m, lane_lt, a.row_base + row, pk_addr, pl_addr, pn, lane,
+#endif
+                                              [&](uint32_t jj) -> float { return __uint_as_float(vb_sel16(v, jj)) * invn * __uint_as_float(vb_lds_u32(qs_addr + (qoff + c0 + jj) * 4u)); },
+                                              [&](uint32_t jj, float fs) -> bool { return fs > __uint_as_float(vb_lds_u32(tex_addr + (qoff + c0 + jj) * 4u)); });
                     }
                 };
                 uint32_t va[16], vb[16];
@@ -632,6 +620,7 @@ vb_dense_gemm_tiled_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
                 if (lane == 0) vb_mbar_arrive(bar_tempty + 8u * acc);
             }
         }
+        if (pn != 0u) vb_flush_pending(a.lists.cand, a.lists.cnt, a.lists.cap, a.lists.sub_cap, sub, pk_addr, pl_addr, pn, lane);
     }
     vb_tcgen05_fence_before();
     __syncthreads();
@@ -835,12 +824,13 @@ static int vb_gemm_launch(const VbGemmLaunch& g, int* launches) {
 }
 
 // ---- K2T launcher -------------------------------------------------------------------------------------
-static const uint32_t VB_TILED_TAIL_BYTES = 320u + VB_TILED_MAX_Q * 16u + 8u * VB_GEMM_MAX_FILTERS * 4u;
+static const uint32_t VB_TILED_TAIL_BYTES = 320u + VB_TILED_MAX_Q * 16u + 8u * VB_GEMM_MAX_FILTERS * 4u + 8u * VB_PEND * 12u;
 
+static int g_k2t_stages = 0;           // vb_set_option("k2t_stages"): 0 = VB200_K2T_STAGES or 4 (process-wide)
 static uint32_t vb_gemm_tiled_stages() {
     const uint32_t avail = (uint32_t)g_gemm_smem_max - 1024u - VB_TILED_TAIL_BYTES;
     uint32_t st = avail / VB_TILED_STAGE_BYTES;
-    const uint32_t cap = (uint32_t)vb_env_int("VB200_K2T_STAGES", 4);
+    const uint32_t cap = g_k2t_stages > 0 ? (uint32_t)g_k2t_stages : (uint32_t)vb_env_int("VB200_K2T_STAGES", 4);
     return st > cap ? cap : st;
 }
 static bool vb_gemm_tiled_supported(int d_pad) {

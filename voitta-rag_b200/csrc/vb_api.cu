@@ -184,6 +184,7 @@ struct vb_index {
     int64_t opt_ms_staged = 1;             // K3M: 1 = posting stages over the whole index, 0 = once per row segment
     int64_t opt_ms_stage_ratio = 0;        // K3M: growth of the posting stages (0 = auto: 32, up to 1024 for tiny batches)
     int64_t opt_delta_max = 0;             // rows the delta may hold before vb_upsert merges it into the index (0 = auto)
+    int64_t opt_ms_ctas = 0;               // K3M: resident CTAs per SM of the persistent score kernel (0 = auto, see ms_launch)
     int64_t opt_ms_max_terms = 16;         // K3M scores queries of at most this many terms; longer ones accumulate (K3)
 
     vb_stats stats{};
@@ -361,6 +362,7 @@ extern "C" int vb_create(int32_t dim, int32_t device, uint64_t capacity_hint, ui
     if (const char* env = getenv("VB200_MH_BUDGET")) h->opt_mh_budget = atoi(env);
     if (const char* env = getenv("VB200_MS_STAGE_RATIO")) h->opt_ms_stage_ratio = atoi(env);
     if (const char* env = getenv("VB200_MS_MAX_TERMS")) h->opt_ms_max_terms = atoi(env);
+    if (const char* env = getenv("VB200_MS_CTAS")) h->opt_ms_ctas = atoi(env);
     *out = h;
     return 0;
 }
@@ -405,6 +407,8 @@ extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
     else if (k == "ms_staged") h->opt_ms_staged = value;           // K3M: posting stages (1) or row segments (0)
     else if (k == "ms_stage_ratio") h->opt_ms_stage_ratio = value; // K3M: growth of the posting stages
     else if (k == "delta_max") h->opt_delta_max = value;           // delta rows that trigger a merge (0 = max(16384, base/32))
+    else if (k == "ms_ctas") h->opt_ms_ctas = value;               // K3M: CTAs per SM of the score kernel (0 = auto)
+    else if (k == "k2t_stages") g_k2t_stages = (int)value;         // K2T: TMA ring depth (0 = default 4); process-wide
     else if (k == "ms_max_terms") h->opt_ms_max_terms = value;     // K3M only for queries of at most this many terms
     else if (k == "sparse_prune_force") h->opt_sparse_prune_force = value;   // 1: prune in every non-direct segment (tests)
     else if (k == "sparse_prune") h->opt_sparse_prune = value;     // MaxScore budget in % of tau (0: score every term's postings)
@@ -1482,6 +1486,8 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     };
     const uint32_t ms_chunk = h->opt_ms_chunk > 0 ? (uint32_t)align_up((size_t)h->opt_ms_chunk, VB_MS_U * VB_MS_THREADS)
                                                    : 512u;
+    // Resident CTAs per SM of the persistent K3M score kernel.  16 (every register of the SM) when it runs alone.
+    const uint32_t ms_per_sm = h->opt_ms_ctas > 0 ? (uint32_t)std::min<int64_t>(16, h->opt_ms_ctas) : 16u;
     // classes: bit 0 = plan + score the K3M queries, bit 1 = the K3H (long) queries
     auto ms_launch = [&](uint32_t r0, uint32_t r1, uint64_t stage_lo, uint64_t stage_hi, uint32_t classes) -> int {
         VbMsPlanArgs pa{};
@@ -1528,7 +1534,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         // persistent grid: enough CTAs to fill the machine, never more than the largest possible unit count
         const uint64_t span = std::min<uint64_t>(r1 - r0, stage_hi - stage_lo);
         const uint64_t max_units = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)h->nnz_live / ms_chunk + b.n_qterms, (uint64_t)b.n_qterms * (span / ms_chunk + 1)));
-        const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)h->sm_count * 16u, max_units);
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)h->sm_count * ms_per_sm, max_units);
         vb_ms_score_kernel<<<grid, VB_MS_THREADS, vb_ms_smem_bytes(b.nt_max), ss>>>(a);
         CKK("vb_ms_score_kernel");
         ++h->stats.last_launches;
