@@ -65,41 +65,31 @@ __device__ __forceinline__ uint64_t vb_block_reduce_u64(uint64_t v, uint64_t* s_
     return r;
 }
 
-// IN_REGS: the whole list fits the per-thread register image (sub-range 0: <= 8 keys per thread,
-// sub-ranges 1..7: <= 1 key per thread each) and is read from memory exactly once.
-#define VB_REG0 8u
-template <bool IN_REGS>
-__device__ __forceinline__ void vb_compact_body(uint64_t* __restrict__ gkeys, const uint32_t (&E)[VB_SUB], uint32_t sub_cap,
-                                                uint32_t k, uint32_t* __restrict__ cnt_out, float* __restrict__ tau_out,
-                                                uint64_t* s_sel, uint32_t* s_hist, uint64_t* s_red,
-                                                uint32_t* s_scan, uint32_t* s_misc)
+// The general path: selection by histogram over the used prefixes of the sub-ranges (s_E[sub] keys each), which are
+// L2-resident and re-read in each pass.  Deliberately compact code (run-time loops, no register image of the list, one
+// instantiation): the first version unrolled every pass over the 8 sub-ranges and kept a second, register-resident
+// variant — 9.5 k instructions (150 KB) for a kernel that runs after every segment / stage of both branches, ~10 times
+// per search, with 8 CTAs per SM in different phases: instruction fetch, not the few thousand keys, set its duration.
+__device__ __noinline__ void vb_compact_select(uint64_t* __restrict__ gkeys, const uint32_t* s_E, uint32_t sub_cap,
+                                               uint32_t k, uint32_t* __restrict__ cnt_out, float* __restrict__ tau_out,
+                                               uint64_t* s_sel, uint32_t* s_hist, uint64_t* s_red,
+                                               uint32_t* s_scan, uint32_t* s_misc)
 {
-    uint64_t r[VB_REG0 + VB_SUB - 1];
-    if (IN_REGS) {
-#pragma unroll
-        for (uint32_t j = 0; j < VB_REG0; ++j) {
-            const uint32_t i = threadIdx.x + j * VB_COMPACT_THREADS;
-            r[j] = i < E[0] ? gkeys[i] : 0ull;
-        }
-#pragma unroll
-        for (uint32_t sub = 1; sub < VB_SUB; ++sub)
-            r[VB_REG0 + sub - 1] = threadIdx.x < E[sub] ? gkeys[(size_t)sub * sub_cap + threadIdx.x] : 0ull;
-    }
-    // visit every key of the list (register image, or the used prefix of each sub-range in L2)
+    // visit every key of the list
     auto for_each = [&](auto&& f) {
-        if (IN_REGS) {
-#pragma unroll
-            for (uint32_t j = 0; j < VB_REG0 + VB_SUB - 1; ++j) f(r[j]);
-        } else {
-#pragma unroll
-            for (uint32_t sub = 0; sub < VB_SUB; ++sub)
-                for (uint32_t i = threadIdx.x; i < E[sub]; i += VB_COMPACT_THREADS) f(gkeys[(size_t)sub * sub_cap + i]);
+#pragma unroll 1
+        for (uint32_t sub = 0; sub < VB_SUB; ++sub) {
+            const uint32_t e = s_E[sub];
+            const uint64_t* g = gkeys + (size_t)sub * sub_cap;
+#pragma unroll 1
+            for (uint32_t i = threadIdx.x; i < e; i += VB_COMPACT_THREADS) f(g[i]);
         }
     };
 
     uint32_t need = k;                                 // rank of the k-th largest among the active keys
     uint64_t pmask = 0ull, pval = 0ull;                // active: key != 0 && (key & pmask) == pval
     uint64_t bound = 1ull;                             // gather every key >= bound
+#pragma unroll 1
     for (;;) {
         uint64_t kmax = 0ull, kmin = ~0ull;
         uint32_t n_act = 0;
@@ -121,6 +111,7 @@ __device__ __forceinline__ void vb_compact_body(uint64_t* __restrict__ gkeys, co
         }
         const int top = 63 - __clzll((long long)(kmax ^ kmin));   // highest differing bit
         const int shift = top >= 10 ? top - 10 : 0;                // digit = bits [shift, shift+11)
+#pragma unroll 1
         for (uint32_t i = threadIdx.x; i < VB_BINS; i += VB_COMPACT_THREADS) s_hist[i] = 0u;
         __syncthreads();
         for_each([&](uint64_t key) {
@@ -131,7 +122,7 @@ __device__ __forceinline__ void vb_compact_body(uint64_t* __restrict__ gkeys, co
         constexpr uint32_t PER = VB_BINS / VB_COMPACT_THREADS;
         const uint32_t hi_bin = VB_BINS - 1u - threadIdx.x * PER;
         uint32_t mine = 0;
-#pragma unroll
+#pragma unroll 1
         for (uint32_t j = 0; j < PER; ++j) mine += s_hist[hi_bin - j];
         uint32_t incl = mine;
 #pragma unroll
@@ -142,11 +133,12 @@ __device__ __forceinline__ void vb_compact_body(uint64_t* __restrict__ gkeys, co
         if ((threadIdx.x & 31u) == 31u) s_scan[threadIdx.x >> 5] = incl;
         __syncthreads();
         uint32_t before = 0;
+#pragma unroll 1
         for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) before += s_scan[w];
         const uint32_t above_me = before + incl - mine;           // active keys in bins above mine
         if (above_me < need && above_me + mine >= need) {         // the pivot bin is one of mine
             uint32_t above = above_me;
-#pragma unroll
+#pragma unroll 1
             for (uint32_t j = 0; j < PER; ++j) {
                 const uint32_t c = s_hist[hi_bin - j];
                 if (above < need && above + c >= need) { s_misc[1] = hi_bin - j; s_misc[2] = above; }
@@ -174,19 +166,6 @@ __device__ __forceinline__ void vb_compact_body(uint64_t* __restrict__ gkeys, co
         }
     });
     __syncthreads();
-    const uint32_t nsel = s_misc[0] < VB_SORT_MAX ? s_misc[0] : VB_SORT_MAX;
-    uint32_t P = 2;
-    while (P < nsel) P <<= 1;
-    for (uint32_t i = nsel + threadIdx.x; i < P; i += VB_COMPACT_THREADS) s_sel[i] = 0ull;
-    vb_bitonic_desc(s_sel, P);
-    const uint32_t keep = nsel < k ? nsel : k;
-    for (uint32_t i = threadIdx.x; i < keep; i += VB_COMPACT_THREADS) gkeys[i] = s_sel[i];
-    if (threadIdx.x < VB_SUB) cnt_out[threadIdx.x] = threadIdx.x == 0 ? keep : 0u;   // the list now lives in sub-range 0
-    if (threadIdx.x == 0) {
-        // never below the threshold the segment ran with: another shard's k'-th best may have been imported
-        // (vb_tau_import), and then this list can legitimately hold fewer than k' entries
-        *tau_out = fmaxf(*tau_out, (keep >= k) ? vb_key_score(s_sel[k - 1]) : -INFINITY);
-    }
 }
 
 __global__ void __launch_bounds__(VB_COMPACT_THREADS)
@@ -198,64 +177,59 @@ vb_compact_kernel(VbLists L, float* __restrict__ tau, uint32_t* __restrict__ ove
     __shared__ uint64_t s_red[VB_COMPACT_THREADS / 32];
     __shared__ uint32_t s_scan[VB_COMPACT_THREADS / 32];
     __shared__ uint32_t s_misc[4];
+    __shared__ uint32_t s_E[VB_SUB];
     const uint32_t list = list_begin + blockIdx.x;
     uint64_t* gkeys = L.cand + (size_t)list * L.cap;
-    uint32_t E[VB_SUB];
-    bool over = false;
-#pragma unroll
-    for (uint32_t sub = 0; sub < VB_SUB; ++sub) {
+    VB_CHECK(list < L.n_lists && lim0 <= L.cap);
+    if (threadIdx.x < VB_SUB) {
+        const uint32_t sub = threadIdx.x;
         const uint32_t raw = L.cnt[list * VB_SUB + sub];
         const uint32_t lim = sub == 0 ? lim0 : L.sub_cap;
-        over = over || raw > lim || (sub > L.sub_mask && raw != 0u);
-        E[sub] = raw < lim ? raw : lim;
+        if (raw > lim || (sub > L.sub_mask && raw != 0u)) overflow[list] = 1u;
+        s_E[sub] = raw < lim ? raw : lim;
     }
-    if (over && threadIdx.x == 0) overflow[list] = 1u;
-    VB_CHECK(list < L.n_lists && lim0 <= L.cap);
-    __syncthreads();                                   // everyone has read the counters before they are rewritten
+    if (threadIdx.x == 0) s_misc[0] = 0u;
+    __syncthreads();                                   // everyone sees the counters before they are rewritten
     // Small lists (the common case once thresholds exist, and every list of a single-query search): no selection
-    // needed — gather the non-empty keys of the used prefixes into shared memory, sort them, write back.  The general
-    // path below costs ~9 us even for a handful of keys (min/max reductions, a 2048-bin histogram, a scan) and a
-    // search runs a compaction after every segment / stage of both branches.  Empty slots (a direct first segment
-    // under a selective filter is mostly empty) are dropped before the sort.
-    {
-        uint32_t total = 0;
-#pragma unroll
-        for (uint32_t sub = 0; sub < VB_SUB; ++sub) total += E[sub];
-        if (total <= 4u * VB_SORT_MAX) {
-            if (threadIdx.x == 0) s_misc[0] = 0u;
-            __syncthreads();
-#pragma unroll
-            for (uint32_t sub = 0; sub < VB_SUB; ++sub)
-                for (uint32_t i = threadIdx.x; i < E[sub]; i += VB_COMPACT_THREADS) {
-                    const uint64_t key = gkeys[(size_t)sub * L.sub_cap + i];
-                    if (key != 0ull) {
-                        const uint32_t slot = atomicAdd(&s_misc[0], 1u);
-                        if (slot < VB_SORT_MAX) s_sel[slot] = key;
-                    }
+    // needed — gather the non-empty keys of the used prefixes into shared memory, sort them, write back.  Empty slots
+    // (a direct first segment under a selective filter is mostly empty) are dropped before the sort.
+    uint32_t total = 0;
+#pragma unroll 1
+    for (uint32_t sub = 0; sub < VB_SUB; ++sub) total += s_E[sub];
+    bool selected = false;
+    if (total <= 4u * VB_SORT_MAX) {
+#pragma unroll 1
+        for (uint32_t sub = 0; sub < VB_SUB; ++sub) {
+            const uint32_t e = s_E[sub];
+            const uint64_t* g = gkeys + (size_t)sub * L.sub_cap;
+#pragma unroll 1
+            for (uint32_t i = threadIdx.x; i < e; i += VB_COMPACT_THREADS) {
+                const uint64_t key = g[i];
+                if (key != 0ull) {
+                    const uint32_t slot = atomicAdd(&s_misc[0], 1u);
+                    if (slot < VB_SORT_MAX) s_sel[slot] = key;
                 }
-            __syncthreads();
-            const uint32_t valid = s_misc[0];
-            if (valid <= VB_SORT_MAX) {
-                uint32_t P = 2;
-                while (P < valid) P <<= 1;
-                for (uint32_t i = valid + threadIdx.x; i < P; i += VB_COMPACT_THREADS) s_sel[i] = 0ull;
-                vb_bitonic_desc(s_sel, P);              // (every stage starts with a barrier; ends with one)
-                const uint32_t keep = valid < k ? valid : k;
-                for (uint32_t i = threadIdx.x; i < keep; i += VB_COMPACT_THREADS) gkeys[i] = s_sel[i];
-                if (threadIdx.x < VB_SUB) L.cnt[(size_t)list * VB_SUB + threadIdx.x] = threadIdx.x == 0 ? keep : 0u;
-                if (threadIdx.x == 0) tau[list] = fmaxf(tau[list], (keep >= k) ? vb_key_score(s_sel[k - 1]) : -INFINITY);
-                return;
             }
-            __syncthreads();                            // too many live keys: the general path (it re-initialises its scratch)
         }
+        __syncthreads();
+        selected = s_misc[0] <= VB_SORT_MAX;
+        __syncthreads();                                // (s_misc[0] is reset by the general path)
     }
-    bool fits = E[0] <= VB_REG0 * VB_COMPACT_THREADS;
-#pragma unroll
-    for (uint32_t sub = 1; sub < VB_SUB; ++sub) fits = fits && E[sub] <= VB_COMPACT_THREADS;
-    if (fits)
-        vb_compact_body<true>(gkeys, E, L.sub_cap, k, L.cnt + (size_t)list * VB_SUB, tau + list, s_sel, s_hist, s_red, s_scan, s_misc);
-    else
-        vb_compact_body<false>(gkeys, E, L.sub_cap, k, L.cnt + (size_t)list * VB_SUB, tau + list, s_sel, s_hist, s_red, s_scan, s_misc);
+    if (!selected)                                      // too many live keys: select those that can be in the top k' first
+        vb_compact_select(gkeys, s_E, L.sub_cap, k, L.cnt + (size_t)list * VB_SUB, tau + list, s_sel, s_hist, s_red, s_scan, s_misc);
+    const uint32_t nsel = s_misc[0] < VB_SORT_MAX ? s_misc[0] : VB_SORT_MAX;
+    uint32_t P = 2;
+    while (P < nsel) P <<= 1;
+    for (uint32_t i = nsel + threadIdx.x; i < P; i += VB_COMPACT_THREADS) s_sel[i] = 0ull;
+    vb_bitonic_desc(s_sel, P);                          // (every stage starts with a barrier; ends with one)
+    const uint32_t keep = nsel < k ? nsel : k;
+    for (uint32_t i = threadIdx.x; i < keep; i += VB_COMPACT_THREADS) gkeys[i] = s_sel[i];
+    if (threadIdx.x < VB_SUB) L.cnt[(size_t)list * VB_SUB + threadIdx.x] = threadIdx.x == 0 ? keep : 0u;   // the list now lives in sub-range 0
+    if (threadIdx.x == 0) {
+        // never below the threshold the segment ran with: another shard's k'-th best may have been imported
+        // (vb_tau_import), and then this list can legitimately hold fewer than k' entries
+        tau[list] = fmaxf(tau[list], (keep >= k) ? vb_key_score(s_sel[k - 1]) : -INFINITY);
+    }
 }
 
 // Pack the first k keys of every list into out[list][k] (0-padded): the all-gather payload.
@@ -320,14 +294,17 @@ struct VbFuseArgs {
     uint32_t* out_ovf;        // [2B] overflow flags
 };
 
-__global__ void __launch_bounds__(128)
+#define VB_FUSE_THREADS 256
+static size_t vb_fuse_smem_bytes(uint32_t k) { return (size_t)2 * k * (8 + 4 + 4 + 1) + 16; }
+__global__ void __launch_bounds__(VB_FUSE_THREADS)
 vb_fuse_kernel(const VbFuseArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t k = a.k;
     double* fin = reinterpret_cast<double*>(smem_raw);          // [2k] fused score
     uint32_t* row = reinterpret_cast<uint32_t*>(fin + 2 * k);   // [2k]
-    uint8_t* valid = reinterpret_cast<uint8_t*>(row + 2 * k);   // [2k]
+    uint32_t* lrow = row + 2 * k;                               // [2k] row ids of the two lists (dense [0,k), sparse [k,2k))
+    uint8_t* valid = reinterpret_cast<uint8_t*>(lrow + 2 * k);  // [2k]
 
     const uint32_t q = blockIdx.x, B = a.n_queries;
     if (threadIdx.x < 2u && a.out_lcnt != nullptr) {
@@ -356,13 +333,16 @@ vb_fuse_kernel(const VbFuseArgs a)
     if (ns) { smin = (double)vb_key_score(sk[ns - 1]); sspread = __dsub_rn((double)vb_key_score(sk[0]), smin); }
 
     for (uint32_t i = threadIdx.x; i < 2 * k; i += blockDim.x) valid[i] = 0;
+    // the membership tests below read every row id of the other list: from shared memory, not k' x k' global loads
+    for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) lrow[i] = vb_key_row(dk[i]);
+    for (uint32_t j = threadIdx.x; j < ns; j += blockDim.x) lrow[k + j] = vb_key_row(sk[j]);
     __syncthreads();
 
     // dense candidates: slot i
     for (uint32_t i = threadIdx.x; i < nd; i += blockDim.x) {
-        const uint32_t r = vb_key_row(dk[i]);
+        const uint32_t r = lrow[i];
         int j = -1;
-        for (uint32_t t = 0; t < ns; ++t) if (vb_key_row(sk[t]) == r) { j = (int)t; break; }
+        for (uint32_t t = 0; t < ns; ++t) if (lrow[k + t] == r) { j = (int)t; break; }
         double f;
         if (mode == 1) {
             const double dn = dspread > 0.0 ? __ddiv_rn(__dsub_rn((double)vb_key_score(dk[i]), dmin), dspread) : 1.0;
@@ -377,9 +357,9 @@ vb_fuse_kernel(const VbFuseArgs a)
     }
     // sparse-only candidates: slot k + j
     for (uint32_t j = threadIdx.x; j < ns; j += blockDim.x) {
-        const uint32_t r = vb_key_row(sk[j]);
+        const uint32_t r = lrow[k + j];
         bool in_dense = false;
-        for (uint32_t t = 0; t < nd; ++t) if (vb_key_row(dk[t]) == r) { in_dense = true; break; }
+        for (uint32_t t = 0; t < nd; ++t) if (lrow[t] == r) { in_dense = true; break; }
         if (in_dense) continue;
         double f;
         if (mode == 1) {

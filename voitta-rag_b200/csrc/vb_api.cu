@@ -1716,7 +1716,7 @@ static int fuse_stage(vb_index* h, const Batch& b) {
     f.out_rows = reinterpret_cast<uint32_t*>(dp + b.o_rows); f.out_scores = reinterpret_cast<double*>(dp + b.o_sc);
     f.out_cnt = reinterpret_cast<int32_t*>(dp + b.o_cnt);
     f.overflow = b.overflow; f.out_lcnt = reinterpret_cast<uint32_t*>(dp + b.o_lcnt); f.out_ovf = reinterpret_cast<uint32_t*>(dp + b.o_ovf);
-    vb_fuse_kernel<<<b.B, 128, (size_t)2 * b.k * 13 + 16, h->stream>>>(f);
+    vb_fuse_kernel<<<b.B, VB_FUSE_THREADS, vb_fuse_smem_bytes(b.k), h->stream>>>(f);
     CKK("vb_fuse_kernel");
     ++h->stats.last_launches;
     if (b.want_branches) {
