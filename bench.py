@@ -95,13 +95,13 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+    def __init__(self, gpu_index: int, period_ms: int = 50):
+        self.gpu, self.rows, self.proc, self.period_ms = gpu_index, [], None, int(period_ms)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", str(self.period_ms), "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
             time.sleep(0.3)                              # the sampler is running before the timed region starts
         except Exception:
@@ -379,6 +379,7 @@ def main():
     ap.add_argument("--dense-path", type=int, default=0, help="0 auto, 1 GEMV scan, 2 tcgen05 GEMM")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="vb_set_option on the index (A/B runs), repeatable")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-period-ms", type=int, default=50, help="nvidia-smi sampling period during the timed region")
     ap.add_argument("--no-api", action="store_true", help="skip the e2e_api (VectorStoreService.search) section")
     ap.add_argument("--api-threads", type=int, default=16)
     args = ap.parse_args()
@@ -484,7 +485,7 @@ def main():
     # ---- device-resident timing ("value") ----------------------------------------------------------
     for i in range(args.warmup):
         device_step(i)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.clock_period_ms)
     sampler.start()
     barrier()
     t_begin = time.perf_counter()
@@ -509,15 +510,21 @@ def main():
     # staged (H2D from pinned memory), run, and its results read back (D2H) and decoded
     packer = ix if world == 1 else sh
 
+    pack_ms = [0.0]
+
     def packed_stream(first, count):
         for i in range(first, first + count):
             q, sp = batches[i % len(batches)]
-            yield packer.pack(q, sp, filters, filter_of, limit=limit, kprime=kprime, fusion=cfg["fusion"], sparse_weight=0.1)
+            t_ = time.perf_counter()
+            p_ = packer.pack(q, sp, filters, filter_of, limit=limit, kprime=kprime, fusion=cfg["fusion"], sparse_weight=0.1)
+            pack_ms[0] += 1e3 * (time.perf_counter() - t_)
+            yield p_
 
     streamer = ix if world == 1 else sh
     for _ in streamer.search_stream(packed_stream(0, max(3, min(args.warmup, 5)) * bps)):
         pass
     barrier()
+    pack_ms[0] = 0.0
     t0 = time.perf_counter()
     n_done = 0
     for last in streamer.search_stream(packed_stream(args.warmup * bps, args.steps * bps)):
@@ -530,7 +537,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     st = ix.stats()
-    e2e = {"value": qps * args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(st["last_h2d_bytes"]) * bps,
+    host_ms = {"pack": round(pack_ms[0] / n_done, 3)}
+    if world > 1 and getattr(sh, "host_ms", None):
+        host_ms.update({k_: round(v_ / max(1, sh.host_ms["batches"]), 3) for k_, v_ in sh.host_ms.items() if k_ != "batches"})
+    e2e = {"value": qps * args.steps / e2e_s, "host_ms_per_batch": host_ms, "unit": "queries/s", "h2d_bytes_per_step": int(st["last_h2d_bytes"]) * bps,
            "d2h_bytes_per_step": int(st["last_d2h_bytes"]) * bps, "ms_per_step": 1e3 * e2e_s / args.steps,
            "note": "pack + stage + H2D + kernels + D2H + decode per batch, two batches in flight (pipelined): a throughput figure, "
                    "while `value` sums one-at-a-time device latencies — e2e may therefore exceed value"}
@@ -683,6 +693,13 @@ def main():
             "e2e": e2e, "e2e_api": api, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "parity_spot_check": parity, "ingest": ingest, "timeline": timeline,
         }
+        if cfg.get("fixed_batch"):
+            # the corpus grows with N (rows_per_gpu fixed) while the batch belongs to the whole job: each query visits N times
+            # the rows, so ideal weak scaling keeps queries/s FLAT; the rate that grows with N is row-query scores per second
+            line["scaling_detail"] = {
+                "kind": "weak in corpus rows: rows_total = N x rows_per_gpu, batch fixed for the whole job",
+                "row_queries_per_s": value * cfg["n"], "ideal": "value(N) == value(1); efficiency = value(N) / value(1) "
+                "(the usual v_N / (N v_1) applies to row_queries_per_s, not to queries/s over an N-times larger corpus)"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

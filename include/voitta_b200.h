@@ -194,6 +194,17 @@ int vb_run_local(vb_index* h, uint64_t* cand_dev);
 int vb_run_fuse(vb_index* h, uint32_t n_shards, const uint64_t* gathered_dev);
 int vb_fetch(vb_index* h, vb_result* out, int32_t* overflowed);
 
+/* Device-resident queries: the embedding forward (embedding.py:76-86 — `model.encode` then
+ * `.tolist()`) can leave its output on the GPU and skip the list[float] -> H2D hop.  Same as vb_stage / vb_search, but
+ * the dense rows are read from `dense_dev` (fp32 [B][dim] on this index's device; q->dense is ignored, may be NULL).
+ * `producer_stream` is the cudaStream_t the producer wrote them on (NULL = the legacy default stream): the library
+ * orders its device-to-device copy after that stream's work, without a host synchronisation.  The buffer may be
+ * reused when vb_search_dev returns / after the vb_fetch of the staged batch.  A NaN or inf in a query is found on
+ * the device and reported by vb_fetch / vb_search(_dev) as an error (qdrant-client local mode asserts on NaN). */
+int vb_stage_dev(vb_index* h, const vb_query_batch* q, const float* dense_dev, void* producer_stream,
+                 int32_t want_branches, int32_t need_corpus);
+int vb_search_dev(vb_index* h, const vb_query_batch* q, const float* dense_dev, void* producer_stream, vb_result* out);
+
 /* Tuning knobs (tests exercise every path with them): key = "dense_path" (0 auto, 1 K1, 2 K2),
  * "seg_first", "seg_ratio", "safe_mode", "profile" (per-phase CUDA-event times in vb_stats),
  * "stream" (a cudaStream_t to run on instead of the index's own stream; 0 restores it). */

@@ -110,7 +110,7 @@ vb_ingest_bf16_kernel(const __nv_bfloat16* __restrict__ src, uint32_t n, uint32_
 __global__ void __launch_bounds__(128)
 vb_prep_query_kernel(const float* __restrict__ q, uint32_t dim, uint32_t d_pad, uint32_t n_queries,
                      uint32_t sub, uint32_t split, float* __restrict__ q_hat, __nv_bfloat16* __restrict__ q_bf16,
-                     float* __restrict__ q_scale, const VbListInit li)
+                     float* __restrict__ q_scale, uint32_t* __restrict__ q_bad, const VbListInit li)
 {
     __shared__ double red[4];
     const uint32_t b = blockIdx.x;
@@ -125,6 +125,7 @@ vb_prep_query_kernel(const float* __restrict__ q, uint32_t dim, uint32_t d_pad, 
     __syncthreads();
     ss = red[0] + red[1] + red[2] + red[3];
     __syncthreads();
+    if (threadIdx.x == 0) q_bad[b] = ss <= 1.0e300 ? 0u : 1u;  // NaN or inf anywhere in the query (qdrant asserts; reported at vb_fetch)
     const float inv = ss > 0.0 ? (float)(1.0 / sqrt(ss)) : 0.0f;
     const uint32_t s_idx = b / sub, j = b % sub;
     const uint32_t n_q = min(sub, n_queries - s_idx * sub);

@@ -332,6 +332,9 @@ struct VbMsPlanArgs {
     uint32_t chunk;              // postings per work unit
     uint32_t budget_pct;         // MaxScore budget in % of tau (100 = the full MaxScore partition)
     uint32_t budget_pct_long;    // the same for the K3H (long) queries
+    uint32_t long_terms;         // K3M queries of more terms than this plan with budget_pct_mslong:
+    uint32_t budget_pct_mslong;  //   a long query's non-essential ub sum (the slack of the per-posting bound test) is better kept
+                                 //   well below tau — more essential postings, but far fewer of them reach the lookups
 };
 
 __global__ void __launch_bounds__(256)
@@ -355,7 +358,7 @@ vb_ms_plan_kernel(const VbMsPlanArgs a)
         if (j < nt) vb_ms_plan_position(s, j, nt);
         __syncthreads();
         if (j < nt) {                                          // thread j now finishes POSITION j
-            const VbMsPos ps = vb_ms_plan_pos(s, j, nt, tau_d, cls == 2u ? a.budget_pct_long : a.budget_pct, a.stage_lo, a.stage_hi);
+            const VbMsPos ps = vb_ms_plan_pos(s, j, nt, tau_d, cls == 2u ? a.budget_pct_long : (nt > a.long_terms ? a.budget_pct_mslong : a.budget_pct), a.stage_lo, a.stage_hi);
             const uint32_t t = s.term_at[j];
             VbMsRec r;
             r.slo = s.slo[t] + ps.w0; r.shi = s.slo[t] + ps.w1; r.w = a.q_weight[t_lo + t];

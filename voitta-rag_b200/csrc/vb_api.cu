@@ -124,7 +124,7 @@ struct Batch {
     // fusion / output
     double w_sparse = 0.0;
     bool want_branches = false, valid = false, need_corpus = true;
-    size_t o_rows = 0, o_sc = 0, o_cnt = 0, o_keys = 0, o_lcnt = 0, o_ovf = 0, out_bytes = 0;
+    size_t o_rows = 0, o_sc = 0, o_cnt = 0, o_keys = 0, o_lcnt = 0, o_ovf = 0, o_bad = 0, out_bytes = 0;
     size_t h2d_bytes = 0;
 };
 
@@ -185,7 +185,13 @@ struct vb_index {
     int64_t opt_ms_stage_ratio = 0;        // K3M: growth of the posting stages (0 = auto: 32, up to 1024 for tiny batches)
     int64_t opt_delta_max = 0;             // rows the delta may hold before vb_upsert merges it into the index (0 = auto)
     int64_t opt_ms_ctas = 0;               // K3M: resident CTAs per SM of the persistent score kernel (0 = auto, see ms_launch)
-    int64_t opt_ms_max_terms = 16;         // K3M scores queries of at most this many terms; longer ones accumulate (K3)
+    int64_t opt_ms_long_terms = 16, opt_ms_budget_long = 85;   // K3M: queries of more terms than the first plan with the second budget
+                                           // (cfg5 shard, 2..65-term queries: 561 ms per batch at 100 %, 154 at 92, 153-156 at 85, 160 at 70, 188 at 40)
+    int64_t opt_ms_max_terms = VB_MS_MAX_TERMS;         // K3M scores queries of at most this many terms; longer ones accumulate (K3)
+
+    const float* q_dev = nullptr;          // vb_stage_dev / vb_search_dev: dense queries of the batch being staged live on this device
+    cudaStream_t q_dev_stream = nullptr;   //   ... written on this stream
+    cudaEvent_t ev_q = nullptr;
 
     vb_stats stats{};
     Batch staged_s[2];
@@ -379,6 +385,7 @@ extern "C" void vb_destroy(vb_index* h) {
     for (HostBuf* b : {&h->h_args_s[0], &h->h_args_s[1], &h->h_out_s[0], &h->h_out_s[1], &h->h_stage}) if (b->p) cudaFreeHost(b->p);
     for (auto ev : h->prof_events) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev0s[i]); cudaEventDestroy(h->ev1s[i]); cudaEventDestroy(h->ev_done[i]); }
+    if (h->ev_q) cudaEventDestroy(h->ev_q);
     cudaEventDestroy(h->ev_fork);
     cudaEventDestroy(h->ev_join);
     cudaStreamDestroy(h->aux_stream);
@@ -409,6 +416,8 @@ extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
     else if (k == "delta_max") h->opt_delta_max = value;           // delta rows that trigger a merge (0 = max(16384, base/32))
     else if (k == "ms_ctas") h->opt_ms_ctas = value;               // K3M: CTAs per SM of the score kernel (0 = auto)
     else if (k == "k2t_stages") g_k2t_stages = (int)value;         // K2T: TMA ring depth (0 = default 4); process-wide
+    else if (k == "ms_long_terms") h->opt_ms_long_terms = value;   // K3M: queries above this many terms use ms_budget_long
+    else if (k == "ms_budget_long") h->opt_ms_budget_long = value; // K3M non-essential budget of those queries, % of tau
     else if (k == "ms_max_terms") h->opt_ms_max_terms = value;     // K3M only for queries of at most this many terms
     else if (k == "sparse_prune_force") h->opt_sparse_prune_force = value;   // 1: prune in every non-direct segment (tests)
     else if (k == "sparse_prune") h->opt_sparse_prune = value;     // MaxScore budget in % of tau (0: score every term's postings)
@@ -982,7 +991,7 @@ static void prof_collect(vb_index* h) {
 static int validate_batch(const vb_index* h, const vb_query_batch* q) {
     if (!q) return vb_fail("query batch is NULL");
     if (q->n_queries == 0) return vb_fail("empty query batch");
-    if (!q->dense) return vb_fail("dense queries are NULL");
+    if (!q->dense && !h->q_dev) return vb_fail("dense queries are NULL");
     if (q->limit == 0) return vb_fail("limit must be > 0");
     if (q->kprime < q->limit) return vb_fail("kprime (%u) < limit (%u)", q->kprime, q->limit);
     if (q->kprime > VB_MAX_KPRIME) return vb_fail("kprime %u exceeds VB_MAX_KPRIME (%d)", q->kprime, VB_MAX_KPRIME);
@@ -1063,8 +1072,10 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
             const bool relax = all_pos && need_corpus && h->sparse_nonneg && h->opt_sparse_dense;
             qrelaxed[i] = relax ? 1 : 0;
             // MaxScore kernel: bounds and the order-free sum need every product >= 0 as well
-            // Long queries stay on K3: a row must rule out most of a long query's essential terms one lookup at a
-            // time before MaxScore can drop it, while K3 accumulates all of them without lookups.
+            // Every query length comes this way (up to VB_MS_MAX_TERMS terms).  Until the kernel tested the score
+            // bound BEFORE the ownership lookups, a long query paid ~pe lookups per surviving posting and K3's
+            // accumulate-everything beat it (hence the ms_max_terms option, then 16); now K3M with an 85 % budget for
+            // long queries runs the 2..65-term MCP replay in 155 ms per 4096-query batch against 214 with K3.
             const bool bounded = all_pos && need_corpus && h->sparse_nonneg && h->opt_sparse_ms && hi > lo;
             const bool ms = bounded && hi - lo <= h->opt_ms_max_terms;
             const bool mh = bounded && !ms && h->opt_sparse_mh;         // long query: hash-accumulate MaxScore (K3H)
@@ -1168,7 +1179,10 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     TRY(dev_reserve(h, h->args, ar.off, false));
     unsigned char* hp = h->h_args_s[h->cur].as<unsigned char>();
     unsigned char* dp = h->args.as<unsigned char>();
-    memcpy(hp + o_q, q->dense, (size_t)b.B * h->dim * 4);
+    if (!h->q_dev) {
+        if (!q->dense) return vb_fail("dense queries are NULL");   // validate_batch ran before the lock
+        memcpy(hp + o_q, q->dense, (size_t)b.B * h->dim * 4);
+    }
     memcpy(hp + o_ip, indptr.data(), (b.B + 1) * 8);
     if (b.n_qterms) {
         memcpy(hp + o_w, weight.data(), (size_t)b.n_qterms * 8);
@@ -1211,7 +1225,16 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
         if (flt[f].ts_field == VB_TS_CREATED) b.need_created = 1;
         if (flt[f].ts_field == VB_TS_MODIFIED) b.need_modified = 1;
     }
-    CK(cudaMemcpyAsync(dp, hp, ar.off, cudaMemcpyHostToDevice, h->stream));
+    // device hand-off: the query rows never visit the host — the H2D copy starts after their slot and a
+    // D2D copy, ordered after the producer's stream, fills it
+    const size_t h2d_skip = h->q_dev ? o_ip : 0;
+    CK(cudaMemcpyAsync(dp + h2d_skip, hp + h2d_skip, ar.off - h2d_skip, cudaMemcpyHostToDevice, h->stream));
+    if (h->q_dev) {
+        if (!h->ev_q) CK(cudaEventCreateWithFlags(&h->ev_q, cudaEventDisableTiming));
+        CK(cudaEventRecord(h->ev_q, h->q_dev_stream));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_q, 0));
+        CK(cudaMemcpyAsync(dp + o_q, h->q_dev, (size_t)b.B * h->dim * 4, cudaMemcpyDeviceToDevice, h->stream));
+    }
     b.d_q = reinterpret_cast<const float*>(dp + o_q);
     b.d_qindptr = reinterpret_cast<const int64_t*>(dp + o_ip);
     b.d_qweight = reinterpret_cast<const double*>(dp + o_w);
@@ -1259,8 +1282,8 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     b.cnt = h->lists.as<uint32_t>() + 2 * (size_t)b.n_lists;      // [n_lists][VB_SUB]
     b.gtau = h->lists.as<uint32_t>() + (2 + (size_t)VB_SUB) * b.n_lists;
     b.done = h->lists.as<uint32_t>() + (3 + (size_t)VB_SUB) * b.n_lists;
-    b.h2d_bytes = ar.off;
-    h->stats.last_h2d_bytes = ar.off;
+    b.h2d_bytes = ar.off - h2d_skip;
+    h->stats.last_h2d_bytes = ar.off - h2d_skip;
     // output block layout
     Arena ao;
     b.o_rows = ao.take((size_t)b.B * b.limit * 4);
@@ -1268,6 +1291,7 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     b.o_cnt = ao.take((size_t)b.B * 4);
     b.o_lcnt = ao.take((size_t)b.n_lists * 4);
     b.o_ovf = ao.take((size_t)b.n_lists * 4);
+    b.o_bad = ao.take((size_t)b.B * 4);
     b.o_keys = ao.take((size_t)b.n_lists * b.k * 8);
     b.out_bytes = ao.off;
     TRY(dev_reserve(h, h->out, b.out_bytes, false));
@@ -1401,7 +1425,8 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         li.tau = b.tau; li.cnt = b.cnt; li.overflow = b.overflow; li.gtau = b.gtau; li.n = b.n_lists; li.cnt0 = direct_rows;
         li.no_direct = ms_staged ? b.d_qms : nullptr; li.n_queries = b.B; li.dense_direct = k1f ? 0u : 1u;
         vb_prep_query_kernel<<<b.B, 128, 0, h->stream>>>(b.d_q, (uint32_t)h->dim, (uint32_t)h->d_pad, b.B, plan.sub, plan.split,
-                                                         h->q_hat.as<float>(), h->q_bf16.as<__nv_bfloat16>(), h->q_scale.as<float>(), li);
+                                                         h->q_hat.as<float>(), h->q_bf16.as<__nv_bfloat16>(), h->q_scale.as<float>(),
+                                                         reinterpret_cast<uint32_t*>(h->out.as<unsigned char>() + b.o_bad), li);
         CKK("vb_prep_query_kernel");
         ++h->stats.last_launches;
     }
@@ -1500,6 +1525,8 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         pa.seg_row0 = r0; pa.seg_row1 = r1; pa.stage_lo = stage_lo; pa.stage_hi = stage_hi;
         pa.chunk = ms_chunk; pa.budget_pct = (uint32_t)std::max<int64_t>(0, h->opt_ms_budget);
         pa.budget_pct_long = (uint32_t)std::max<int64_t>(0, h->opt_mh_budget);
+        pa.long_terms = (uint32_t)std::max<int64_t>(0, h->opt_ms_long_terms);
+        pa.budget_pct_mslong = (uint32_t)std::max<int64_t>(0, h->opt_ms_budget_long);
         vb_ms_plan_kernel<<<b.B, 256, 0, ss>>>(pa);
         CKK("vb_ms_plan_kernel");
         ++h->stats.last_launches;
@@ -1749,6 +1776,11 @@ static int fetch_stage(vb_index* h, const Batch& b, vb_result* out, int* overflo
             *overflowed = 1;
             if (h->stats.last_overflow_lists++ == 0) h->stats.last_overflow_first = i;
         }
+    if (b.need_corpus) {                                       // flags of the query-prep kernel (a device-resident query is only seen there)
+        const uint32_t* bad = reinterpret_cast<const uint32_t*>(hp + b.o_bad);
+        for (uint32_t i = 0; i < b.B; ++i)
+            if (bad[i]) return vb_fail("Query vector must not contain NaN or inf (query %u of the batch)", i);
+    }
     if (*overflowed || !out) return 0;
     const uint32_t* rows = reinterpret_cast<const uint32_t*>(hp + b.o_rows);
     const double* sc = reinterpret_cast<const double*>(hp + b.o_sc);
@@ -1947,6 +1979,44 @@ extern "C" int vb_search(vb_index* h, const vb_query_batch* q, vb_result* out) {
         ++h->stats.overflow_reruns;
     }
     return 0;
+}
+
+// ---- device-resident queries ------------------------------------------------------------
+// The embedding model's output (embedding.py:76-86) stays on the GPU: same calls, but the dense rows come from
+// `dense_dev` (fp32 [B][dim] on this index's device; q->dense is ignored and may be NULL).  The library orders its
+// copy after the work queued on `producer_stream` (a cudaStream_t; NULL = the legacy default stream) — no host sync.
+struct QDevScope {
+    vb_index* h;
+    QDevScope(vb_index* h_, const float* p, void* s) : h(h_) { h->q_dev = p; h->q_dev_stream = (cudaStream_t)s; }
+    ~QDevScope() { h->q_dev = nullptr; h->q_dev_stream = nullptr; }
+};
+
+static int check_dev_queries(vb_index* h, const float* dense_dev) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, dense_dev) != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
+        cudaGetLastError();
+        return vb_fail("dense_dev is not a device pointer");
+    }
+    if (at.type == cudaMemoryTypeDevice && at.device != h->device) return vb_fail("dense_dev lives on device %d, the index on device %d", at.device, h->device);
+    return 0;
+}
+
+extern "C" int vb_stage_dev(vb_index* h, const vb_query_batch* q, const float* dense_dev, void* producer_stream, int32_t want_branches, int32_t need_corpus) {
+    if (!h || !dense_dev) return vb_fail("vb_stage_dev: NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    TRY(check_dev_queries(h, dense_dev));
+    QDevScope scope(h, dense_dev, producer_stream);
+    return vb_stage(h, q, want_branches, need_corpus);
+}
+
+extern "C" int vb_search_dev(vb_index* h, const vb_query_batch* q, const float* dense_dev, void* producer_stream, vb_result* out) {
+    if (!h || !dense_dev || !out) return vb_fail("vb_search_dev: NULL argument");
+    std::lock_guard<std::recursive_mutex> lk(h->mu);
+    CK(cudaSetDevice(h->device));
+    TRY(check_dev_queries(h, dense_dev));
+    QDevScope scope(h, dense_dev, producer_stream);
+    return vb_search(h, q, out);
 }
 
 extern "C" int vb_search_local(vb_index* h, const vb_query_batch* q, uint64_t* cand_dev) {

@@ -72,7 +72,7 @@ class _Stats(C.Structure):
 # every symbol include/voitta_b200.h declares
 EXPORTS = ["vb_abi_version", "vb_last_error", "vb_create", "vb_destroy", "vb_upsert", "vb_upsert_dev",
            "vb_delete_rows", "vb_optimize", "vb_term_stats", "vb_search", "vb_search_local", "vb_merge_fuse",
-           "vb_stage", "vb_run_local", "vb_run_fuse", "vb_fetch",
+           "vb_stage", "vb_run_local", "vb_run_fuse", "vb_fetch", "vb_stage_dev", "vb_search_dev",
            "vb_run_local_begin", "vb_tau_export", "vb_tau_import",
            "vb_set_option", "vb_get_stats", "vb_get_timeline", "vb_sync", "vb_save", "vb_load"]
 
@@ -103,6 +103,8 @@ def load_library():
     lib.vb_search_local.argtypes = [vp, C.POINTER(_QueryBatch), vp]
     lib.vb_merge_fuse.argtypes = [vp, C.POINTER(_QueryBatch), C.c_uint32, vp, C.POINTER(_Result)]
     lib.vb_stage.argtypes = [vp, C.POINTER(_QueryBatch), C.c_int32, C.c_int32]
+    lib.vb_stage_dev.argtypes = [vp, C.POINTER(_QueryBatch), vp, vp, C.c_int32, C.c_int32]
+    lib.vb_search_dev.argtypes = [vp, C.POINTER(_QueryBatch), vp, vp, C.POINTER(_Result)]
     lib.vb_run_local.argtypes = [vp, vp]
     lib.vb_run_fuse.argtypes = [vp, C.c_uint32, vp]
     lib.vb_fetch.argtypes = [vp, C.POINTER(_Result), C.POINTER(C.c_int32)]
@@ -186,14 +188,29 @@ class _Packed:
     """Keeps the numpy arrays behind a vb_query_batch alive."""
 
     def __init__(self, dim, queries, sparse, filters, filter_of, limit, kprime, fusion, sparse_weight, apply_idf):
-        q = np.ascontiguousarray(queries, dtype=np.float32)
-        if q.ndim == 1:
-            q = q[None, :]
-        if q.ndim != 2 or q.shape[1] != dim:
-            raise ValueError(f"queries must have shape [B, {dim}], got {q.shape}")
-        if not np.isfinite(q).all():
-            raise ValueError("Query vector must not contain NaN or inf")
-        B = q.shape[0]
+        self.q_dev = None
+        self.q_stream = None
+        if getattr(queries, "is_cuda", False) and hasattr(queries, "data_ptr"):
+            # tensor hand-off (SURVEY 8 f-4): the rows stay on the GPU; NaN / inf are found by the query-prep kernel
+            import torch
+            t = queries if queries.dim() == 2 else queries[None, :]
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.to(torch.float32).contiguous()
+            if t.dim() != 2 or t.shape[1] != dim:
+                raise ValueError(f"queries must have shape [B, {dim}], got {tuple(t.shape)}")
+            self.q_dev = t
+            self.q_stream = torch.cuda.current_stream(t.device).cuda_stream
+            q = None
+            B = int(t.shape[0])
+        else:
+            q = np.ascontiguousarray(queries, dtype=np.float32)
+            if q.ndim == 1:
+                q = q[None, :]
+            if q.ndim != 2 or q.shape[1] != dim:
+                raise ValueError(f"queries must have shape [B, {dim}], got {q.shape}")
+            if not np.isfinite(q).all():
+                raise ValueError("Query vector must not contain NaN or inf")
+            B = q.shape[0]
         self.q = q
         self.B = B
         self.indptr = self.terms = self.weights = None
@@ -363,8 +380,14 @@ class Index:
             kprime = limit * 3 if (sparse is not None and fz != FUSE_DENSE_ONLY) else limit
         p = _Packed(self.dim, queries, sparse, filters, filter_of, limit, kprime, fz, sparse_weight, apply_idf)
         res, cres = self._alloc_result(p.B, limit, kprime, branches)
-        self._check(self._lib.vb_search(self._h, C.byref(p.c), C.byref(cres)))
+        self._search(p, cres)
         return res
+
+    def _search(self, p, cres):
+        if p.q_dev is not None:
+            self._check(self._lib.vb_search_dev(self._h, C.byref(p.c), p.q_dev.data_ptr(), p.q_stream, C.byref(cres)))
+        else:
+            self._check(self._lib.vb_search(self._h, C.byref(p.c), C.byref(cres)))
 
     @staticmethod
     def cand_block_words(n_queries: int, kprime: int) -> int:
@@ -385,7 +408,7 @@ class Index:
     def search_packed(self, packed) -> SearchResult:
         """vb_search on prepared host buffers: staging, H2D, kernels, D2H and decode, nothing else."""
         res, cres = packed.result
-        self._check(self._lib.vb_search(self._h, C.byref(packed.c), C.byref(cres)))
+        self._search(packed, cres)
         return res
 
     def search_stream(self, packed_iter):
@@ -446,7 +469,10 @@ class Index:
         if kprime is None:
             kprime = limit * 3 if (sparse is not None and fz != FUSE_DENSE_ONLY) else limit
         p = _Packed(self.dim, queries, sparse, filters, filter_of, limit, kprime, fz, sparse_weight, apply_idf)
-        self._check(self._lib.vb_stage(self._h, C.byref(p.c), int(branches), int(need_corpus)))
+        if p.q_dev is not None:
+            self._check(self._lib.vb_stage_dev(self._h, C.byref(p.c), p.q_dev.data_ptr(), p.q_stream, int(branches), int(need_corpus)))
+        else:
+            self._check(self._lib.vb_stage(self._h, C.byref(p.c), int(branches), int(need_corpus)))
         res, cres = self._alloc_result(p.B, limit, kprime, branches)
         return res, cres
 
@@ -454,7 +480,10 @@ class Index:
         """vb_stage on host buffers built earlier by ``pack`` (branches as chosen there)."""
         res, cres = packed.result
         want = res.dense_rows is not None
-        self._check(self._lib.vb_stage(self._h, C.byref(packed.c), int(want), int(need_corpus)))
+        if packed.q_dev is not None:
+            self._check(self._lib.vb_stage_dev(self._h, C.byref(packed.c), packed.q_dev.data_ptr(), packed.q_stream, int(want), int(need_corpus)))
+        else:
+            self._check(self._lib.vb_stage(self._h, C.byref(packed.c), int(want), int(need_corpus)))
         return packed.result
 
     def run_local_begin(self) -> None:

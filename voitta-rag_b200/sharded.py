@@ -192,14 +192,21 @@ class ShardedIndex:
         staging + H2D of batch i+1 overlap the kernels / all-gather of batch i.  Yields in order."""
         prev = None
         slot = 0
+        import time
+        t = self.host_ms = {"stage": 0.0, "enqueue": 0.0, "fetch": 0.0, "batches": 0}   # host wall time per call site (diagnostic)
         try:
             for packed in packed_iter:
                 self.index.set_option("slot", slot)
+                t0 = time.perf_counter()
                 staged = self.index.stage_packed(packed)
+                t1 = time.perf_counter()
                 self._enqueue(packed.B, packed.kprime)
+                t2 = time.perf_counter()
+                t["stage"] += 1e3 * (t1 - t0); t["enqueue"] += 1e3 * (t2 - t1); t["batches"] += 1
                 if prev is not None:
                     self.index.set_option("slot", slot ^ 1)
                     res = self.index.fetch(prev, allow_overflow=True)
+                    t["fetch"] += 1e3 * (time.perf_counter() - t2)
                     if res is None:
                         raise RuntimeError("candidate overflow in a pipelined search; use search_packed")
                     yield res

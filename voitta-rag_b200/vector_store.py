@@ -97,6 +97,11 @@ _OPTIONAL = ("start_page", "end_page", "source_page_count", "source_created_at",
              "source_modified_at", "allowed_users", "source_url")
 
 
+def _is_device_tensor(x) -> bool:
+    """A torch CUDA tensor (duck-typed: this module does not import torch)."""
+    return bool(getattr(x, "is_cuda", False)) and hasattr(x, "data_ptr")
+
+
 def _payload_to_chunk(pid: str, payload: dict, score) -> StoredChunk:
     """reference :532-558 (_result_to_chunk) and the identical blocks at :186-210, :943-965.
     Positional construction in dataclass field order: this runs 20 times per search on the caller's thread."""
@@ -740,6 +745,14 @@ class VectorStoreService:
         search_filter = self._build_filter(
             folder_filter, include_folders, exclude_folders, exclude_index_folders,
             date_start=date_start, date_end=date_end, date_field=date_field, scope_key=scope_key)
+        if _is_device_tensor(query_embedding):
+            # additive: a CUDA tensor from the embedding model goes to the device search as it is (no .tolist() hop)
+            if query_embedding.dim() != 1 or query_embedding.shape[0] != self.dimension:
+                raise ValueError(f"Vector dimension error: expected {self.dimension}, got {query_embedding.shape[-1] if query_embedding.dim() else 0}")
+            return self.search_batch(query_embedding[None, :], limit=limit, folder_filter=folder_filter, include_folders=include_folders,
+                                     exclude_folders=exclude_folders, exclude_index_folders=exclude_index_folders,
+                                     sparse_queries=[sparse_query], sparse_weight=sparse_weight, date_start=date_start,
+                                     date_end=date_end, date_field=date_field)[0]
         q = np.asarray(query_embedding, dtype=np.float32)
         if q.ndim != 1 or q.shape[0] != self.dimension:
             raise ValueError(f"Vector dimension error: expected {self.dimension}, got {q.shape[-1] if q.ndim else 0}")
@@ -788,9 +801,15 @@ class VectorStoreService:
             folder_filter, include_folders, exclude_folders, exclude_index_folders,
             date_start=date_start, date_end=date_end, date_field=date_field)
         B = len(query_embeddings)
-        q = np.asarray(query_embeddings, dtype=np.float32)
-        if q.ndim != 2 or q.shape[1] != self.dimension:
-            raise ValueError(f"Vector dimension error: expected {self.dimension}, got {q.shape[-1] if q.ndim else 0}")
+        if _is_device_tensor(query_embeddings):
+            # tensor hand-off: the embedding model's output (embedding.py:76-86) stays on the GPU
+            q = query_embeddings
+            if q.dim() != 2 or q.shape[1] != self.dimension:
+                raise ValueError(f"Vector dimension error: expected {self.dimension}, got {q.shape[-1] if q.dim() else 0}")
+        else:
+            q = np.asarray(query_embeddings, dtype=np.float32)
+            if q.ndim != 2 or q.shape[1] != self.dimension:
+                raise ValueError(f"Vector dimension error: expected {self.dimension}, got {q.shape[-1] if q.ndim else 0}")
         sparse = [None] * B
         any_sparse = False
         if sparse_queries is not None and self._has_sparse:
