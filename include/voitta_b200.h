@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VB_ABI_VERSION 2
+#define VB_ABI_VERSION 3
 #define VB_TS_MISSING INT64_MIN
 #define VB_MAX_KPRIME 1024          /* limit*3 <= 1024 */
 #define VB_MAX_QUERY_TERMS 256      /* non-zeros per sparse query */
@@ -110,6 +110,8 @@ typedef struct vb_stats {
     uint64_t delta_rows;                       /* rows appended since the last build (scored from the forward index) */
     uint32_t last_overflow_lists;              /* candidate lists that overflowed in the last fetched search (0 = none)  */
     uint32_t last_overflow_first;              /* the first of them: list q = dense list of query q, B + q = its sparse list */
+    uint32_t last_sel_rows;                    /* K2T row selection: rows of the largest segment that pass the batch-wide filter (0 = not run) */
+    uint32_t last_sel_used;                    /* 1 = the tensor-core kernel walked the compacted copy of those rows        */
 } vb_stats;
 
 int         vb_abi_version(void);

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/voitta_b200.h but not exported"
     assert sorted(engine.EXPORTS) == syms
-    assert lib.vb_abi_version() == 2
+    assert lib.vb_abi_version() == 3
 
 
 def test_struct_layouts_match_header():
@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(engine._Filter) == 32
     assert ctypes.sizeof(engine._QueryBatch) == 88
     assert ctypes.sizeof(engine._Result) == 72
-    assert ctypes.sizeof(engine._Stats) == 208
+    assert ctypes.sizeof(engine._Stats) == 216
 
 
 def test_no_cpu_fallback():

@@ -961,3 +961,62 @@ def test_k3h_long_queries_equal_k3_and_oracle(world):
     finally:
         for k, v in {"sparse_mh": 0, "ms_max_terms": 16, "safe_mode": 0, "seg_ratio": 0, "ms_staged": 1, "sparse_dense": 1}.items():
             ix.set_option(k, v)
+
+
+def test_k2t_row_selection_equals_in_place_scoring_and_oracle():
+    """K2T over the compacted copy of the rows that pass a batch-wide filter (dense_compact.cuh) must return exactly
+    what K2T returns with the filter bit tested in its epilogue (same operands, same accumulation: identical keys),
+    and both must match the oracle.  Selectivities from nothing to everything, tombstones, rows appended after the
+    index build, a row count that is not a multiple of the tile."""
+    from voitta_rag_b200 import engine
+    rng = np.random.RandomState(77)
+    n, dim, B, limit = 61_003, 128, 320, 10
+    cents = rng.randn(64, dim).astype(np.float32)
+    dense = _data.bf16_round(cents[rng.randint(0, 64, size=n)] + 0.6 * rng.randn(n, dim).astype(np.float32))
+    scope = rng.randint(0, 100, size=n).astype(np.uint32)
+    modified = rng.randint(1420070400, 1767225600, size=n).astype(np.int64)
+    ix = engine.Index(dim)
+    n0 = 50_000                                            # the rest arrives later: delta rows (dense covers them all)
+    ix.upsert(dense[:n0], None, scope[:n0], None, modified[:n0])
+    Q = _data.bf16_round(dense[rng.randint(0, n, size=B)] + 0.3 * rng.randn(B, dim).astype(np.float32))
+    ix.search_batch(Q[:4], None, limit=3, fusion="dense")  # builds the index state before the append
+    ix.upsert(dense[n0:], None, scope[n0:], None, modified[n0:])
+    dead = rng.choice(n, size=900, replace=False)
+    ix.delete_rows(dead)
+    alive = np.ones(n, bool); alive[dead] = False
+    cc = oracle_c.CorpusC(dense, None, scope, None, modified, alive=alive.astype(np.uint8))
+
+    def scope_filter(ids, lo=1420070400, hi=1767225600):
+        bits = np.zeros(4, np.uint32)
+        for s in ids:
+            bits[s >> 5] |= np.uint32(1 << (s & 31))
+        return (bits, 2, lo, hi)
+    cases = {"1 scope of 100": scope_filter([7]), "half": scope_filter(range(0, 100, 2)), "all": scope_filter(range(100)),
+             "none": scope_filter([]), "60 % and a date range": scope_filter(range(60), 1500000000, 1700000000)}
+    fo = np.zeros(B, np.int32)
+    sub = np.sort(rng.choice(B, size=48, replace=False))
+    for name, f in cases.items():
+        passing = ((f[0][scope >> 5] >> (scope & 31)) & 1).astype(bool) & (modified >= f[2]) & (modified <= f[3]) & alive
+        res = {}
+        for sel in (0, 70):
+            ix.set_option("dense_compact", sel)
+            ix.set_option("dense_compact_min_rows", 1024)
+            res[sel] = ix.search_batch(Q, None, [engine.Filter(*f)], fo, limit=limit, fusion="dense", branches=True)
+            st = ix.stats()
+            assert st["last_dense_path"] == 2 and st["last_dense_passes"] == 1, st
+            if sel:
+                assert st["last_sel_rows"] > 0 or passing.sum() == 0 or name == "none", (name, st)
+                big_share = st["last_sel_rows"] / max(1, st["last_big_rows"])
+                assert st["last_sel_used"] == (1 if big_share <= 0.70 else 0), (name, st)
+            else:
+                assert st["last_sel_used"] == 0
+        for i in range(B):
+            assert res[70].branch(i, "dense") == res[0].branch(i, "dense"), f"row selection changed the answer: {name} q{i}"
+            rows = [r for r, _ in res[70].branch(i, "dense")]
+            assert passing[rows].all(), f"{name} q{i}: a returned row fails the filter or is deleted"
+            assert len(rows) == min(limit, int(passing.sum()))
+        want = cc.search_batch(Q[sub], None, [f], fo[sub], limit=limit, kprime=limit, fusion=0)
+        for j, i in enumerate(sub):
+            wd = [(int(want["dense_rows"][j, t]), float(want["dense_scores"][j, t])) for t in range(want["dense_counts"][j])]
+            assert_same_ranking(res[70].branch(i, "dense"), wd, rel_tol=1e-3, abs_tol=1e-3, what=f"row selection {name} q{i}")
+    ix.close()

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Small end-to-end workload for compute-sanitizer (memcheck / racecheck / synccheck): every kernel of the path on a
-6000-row corpus — K0 mask, K1 + K1F scans, K2 tcgen05 GEMM (resident) and K2T (query-tiled), K3 (block x query), K3M
+6000-row corpus — K0 mask, K1 + K1F scans, K2 tcgen05 GEMM (resident) and K2T (query-tiled, in place and over the row selection's copy), K3 (block x query), K3M
 (MaxScore stages and per-segment), K3D (delta rows), select, K4 fusion, ingest, index build, deletes — checked against
 the oracle so that a sanitizer-clean run is also a correct one.  Run by tools/gpu_sanitize.sh."""
 import sys
@@ -54,6 +54,11 @@ check(3, n0, "B=3 K2 resident", dense_path=2)
 check(3, n0, "B=3 K3 only", sparse_ms=0)
 check(3, n0, "B=3 safe mode", safe_mode=1)
 check(300, n0, "B=300 K2T")
+ix.set_option("dense_compact_min_rows", 1024)         # the row selection normally needs 262144-row segments
+check(300, n0, "B=300 K2T over the compacted copy of the passing rows (row selection)")
+st = ix.stats()
+assert st["last_sel_rows"] > 0 and st["last_sel_used"] == 1, st
+ix.set_option("dense_compact_min_rows", 1 << 18)
 ix.set_option("ms_max_terms", 4)                      # queries of more than 4 terms become "long"
 check(6, n0, "B=6 long queries on K3")
 ix.set_option("sparse_mh", 1)                         # ... and on K3H (off by default)

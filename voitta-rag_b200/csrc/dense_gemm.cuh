@@ -413,12 +413,16 @@ struct VbGemmTiledArgs {
     uint32_t stages;
     uint32_t mask_mode;              // 0 none, 1 one filter for all queries, 2 <= 31 filters, 3 general
     int32_t  uniform_filter;
+    // SEL (dense_compact.cuh): sel[1] != 0 -> walk the compacted copy of the rows that pass the shared filter instead
+    const uint32_t* sel;             // [0] rows of the copy, [1] decision (taken on the device)
+    const uint32_t* sel_ids;         // [rows of the copy] shard row id of each copied row
+    const float* sel_inv_norm;       // [rows of the copy]
 };
 
-template <int MODE, bool DIRECT>
+template <int MODE, bool DIRECT, bool SEL>
 __global__ void __launch_bounds__(VB_GEMM_THREADS, 1)
 vb_dense_gemm_tiled_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_q,
-                           const VbGemmTiledArgs a)
+                           const __grid_constant__ CUtensorMap tmap_c, const VbGemmTiledArgs a)
 {
     extern __shared__ unsigned char vb_gemm_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)vb_gemm_smem_raw + 1023u) & ~(uintptr_t)1023u);
@@ -462,21 +466,26 @@ vb_dense_gemm_tiled_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
     vb_tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    const uint32_t n_tiles = a.tile_end - a.tile_begin;
+    // SEL: the row-selection kernels decided (on the device) whether this launch walks the compacted copy
+    const bool cmp = SEL && a.sel[1] != 0u;
+    const uint32_t tile_begin = cmp ? 0u : a.tile_begin;
+    const uint32_t row_end = cmp ? a.sel[0] : a.row_end;
+    const uint32_t n_tiles = cmp ? (a.sel[0] + VB_TILE_M - 1u) / VB_TILE_M : a.tile_end - a.tile_begin;
     const uint32_t n_ntiles = (a.n_q + VB_TILE_N - 1u) / VB_TILE_N;
 
     if (warp == 0) {
         // ===== TMA producer: per (corpus tile, query tile, K block) one corpus box + one query box =====
         if (lane == 0) {
+            const CUtensorMap* tmap_rows = cmp ? &tmap_c : &tmap_a;
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int32_t row0 = (int32_t)((a.tile_begin + t) * VB_TILE_M);
+                const int32_t row0 = (int32_t)((tile_begin + t) * VB_TILE_M);
                 for (uint32_t j = 0; j < n_ntiles; ++j) {
                     for (uint32_t kb = 0; kb < a.k_blocks; ++kb) {
                         vb_mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
                         vb_mbar_expect_tx(bar_full + 8u * stage, VB_TILED_STAGE_BYTES);
                         const uint32_t dst = vb_smem_u32(smem + stage * VB_TILED_STAGE_BYTES);
-                        vb_tma_load_2d(dst, &tmap_a, (int32_t)(kb * VB_BLOCK_K), row0, bar_full + 8u * stage);
+                        vb_tma_load_2d(dst, tmap_rows, (int32_t)(kb * VB_BLOCK_K), row0, bar_full + 8u * stage);
                         vb_tma_load_2d(dst + VB_STAGE_BYTES, &tmap_q, (int32_t)(kb * VB_BLOCK_K), (int32_t)(j * VB_TILE_N), bar_full + 8u * stage);
                         if (++stage == S) { stage = 0; phase ^= 1u; }
                     }
@@ -526,14 +535,17 @@ vb_dense_gemm_tiled_kernel(const __grid_constant__ CUtensorMap tmap_a, const __g
         uint32_t pn = 0u;                                     // parked candidates of this warp (warp-uniform)
         uint32_t it = 0;
         for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const uint32_t tile = a.tile_begin + t;
-            const uint32_t row = tile * VB_TILE_M + quad * 32u + lane;
-            const bool row_ok = row < a.row_end;
+            const uint32_t tile = tile_begin + t;
+            const uint32_t pos = tile * VB_TILE_M + quad * 32u + lane;       // row of the matrix this launch walks
+            const bool row_ok = pos < row_end;
+            // the shard row behind it: itself, or (compacted copy) the id the selection recorded
+            const uint32_t row = cmp ? (row_ok ? a.sel_ids[pos] : 0u) : pos;
+            VB_CHECK(row < a.row_end || !row_ok);
             // a row that is out of range or (modes 0/1) masked gets a NaN scale: every compare fails
-            float invn = row_ok ? a.inv_norm[row] : qnan;
+            float invn = row_ok ? (cmp ? a.sel_inv_norm[pos] : a.inv_norm[pos]) : qnan;
             const uint32_t word = tile * 4u + quad;
             uint32_t fbits = 0x80000000u;                 // mode 2: bit f = row passes filter f; bit 31 = unfiltered
-            if (MODE == 0 && a.mask_mode == 1u) {
+            if (MODE == 0 && a.mask_mode == 1u && !cmp) { // (every row of the compacted copy passes the shared filter)
                 const uint32_t w = word < a.mask_words ? a.mask[(size_t)a.uniform_filter * a.mask_words + word] : 0u;
                 if (!((w >> lane) & 1u)) invn = qnan;
             } else if (mode == 2u) {
@@ -667,12 +679,13 @@ static int vb_gemm_configure() {
         e = cudaFuncSetAttribute(vb_gemm_variant(i), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { g_gemm_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
     }
-    e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(vb_dense_gemm_tiled_kernel<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { g_gemm_err = std::string("cudaFuncSetAttribute(tiled): ") + cudaGetErrorString(e); return 1; }
     g_gemm_smem_max = smem;
     g_encode_tiled = reinterpret_cast<VbEncodeTiledFn>(fn);
@@ -744,6 +757,12 @@ struct VbGemmLaunch {
     uint32_t direct;
     VbGemmPlan plan;
     const int32_t* mask_of_host;   // host copy of mask_of (to pick the epilogue's mask mode)
+    // K2T over the compacted copy of the rows passing the batch's shared filter (dense_compact.cuh); sel == nullptr: off
+    const uint32_t* sel = nullptr;
+    const uint32_t* sel_ids = nullptr;
+    const float* sel_inv_norm = nullptr;
+    const void* sel_rows = nullptr;    // [sel_cap_rows][d_pad] bf16
+    uint32_t sel_cap_rows = 0;
 };
 
 static int vb_encode_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
@@ -844,6 +863,8 @@ static int vb_gemm_tiled_launch(const VbGemmLaunch& g, int* launches) {
     if (g.plan.split) { g_gemm_err = "tiled kernel needs the unsplit query layout"; return 1; }
     CUtensorMap tmap_a;
     if (vb_encode_2d(&tmap_a, g.rows, g.n_rows_total, g.d_pad, VB_TILE_M)) return 1;
+    CUtensorMap tmap_c = tmap_a;
+    if (g.sel && vb_encode_2d(&tmap_c, g.sel_rows, g.sel_cap_rows, g.d_pad, VB_TILE_M)) return 1;
     const uint32_t stages = vb_gemm_tiled_stages();
     for (uint32_t q0 = 0; q0 < g.n_queries; q0 += VB_TILED_MAX_Q) {
         const uint32_t n_q = std::min(VB_TILED_MAX_Q, g.n_queries - q0);
@@ -864,17 +885,21 @@ static int vb_gemm_tiled_launch(const VbGemmLaunch& g, int* launches) {
             else if (uniform) { a.mask_mode = 1; a.uniform_filter = g.mask_of_host[q0]; }
             else a.mask_mode = g.n_filters <= 31u ? 2 : 3;
         }
+        const bool use_sel = g.sel != nullptr && a.mask_mode == 1u && !g.direct;
         const size_t smem = 1024u + (size_t)stages * VB_TILED_STAGE_BYTES + VB_TILED_TAIL_BYTES;
         const uint32_t tiles = a.tile_end - a.tile_begin;
         const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)g.sm_count);
         if (g.direct) {
-            if (a.mask_mode == 2u) vb_dense_gemm_tiled_kernel<2, true><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
-            else if (a.mask_mode == 3u) vb_dense_gemm_tiled_kernel<3, true><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
-            else vb_dense_gemm_tiled_kernel<0, true><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
+            if (a.mask_mode == 2u) vb_dense_gemm_tiled_kernel<2, true, false><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, tmap_a, a);
+            else if (a.mask_mode == 3u) vb_dense_gemm_tiled_kernel<3, true, false><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, tmap_a, a);
+            else vb_dense_gemm_tiled_kernel<0, true, false><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, tmap_a, a);
         } else {
-            if (a.mask_mode == 2u) vb_dense_gemm_tiled_kernel<2, false><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
-            else if (a.mask_mode == 3u) vb_dense_gemm_tiled_kernel<3, false><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
-            else vb_dense_gemm_tiled_kernel<0, false><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
+            if (a.mask_mode == 2u) vb_dense_gemm_tiled_kernel<2, false, false><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, tmap_a, a);
+            else if (a.mask_mode == 3u) vb_dense_gemm_tiled_kernel<3, false, false><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, tmap_a, a);
+            else if (use_sel) {
+                a.sel = g.sel; a.sel_ids = g.sel_ids; a.sel_inv_norm = g.sel_inv_norm;
+                vb_dense_gemm_tiled_kernel<0, false, true><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, tmap_c, a);
+            } else vb_dense_gemm_tiled_kernel<0, false, false><<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, tmap_a, a);
         }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { g_gemm_err = std::string("tiled launch failed: ") + cudaGetErrorString(e); return 1; }

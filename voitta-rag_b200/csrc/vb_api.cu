@@ -6,6 +6,7 @@
 #include "mask.cuh"
 #include "dense_scan.cuh"
 #include "dense_gemm.cuh"
+#include "dense_compact.cuh"
 #include "sparse.cuh"
 #include "sparse_ms.cuh"
 #include "sparse_mh.cuh"
@@ -133,7 +134,8 @@ struct vb_index {
     uint64_t row_base = 0;
     uint64_t n_rows = 0, n_live = 0, cap_rows = 0;
     uint64_t nnz = 0, cap_nnz = 0;
-    cudaStream_t stream = nullptr, own_stream = nullptr, aux_stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr, aux_stream = nullptr, sel_stream = nullptr;
+    cudaEvent_t ev_sel_fork = nullptr, ev_sel[8] = {};
     cudaEvent_t ev0s[2] = {nullptr, nullptr}, ev1s[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int cur = 0;                               // current slot: two batches can be in flight (pipelined callers)
@@ -168,8 +170,11 @@ struct vb_index {
 
     // per-search scratch
     DevBuf args, mask, cand, lists, offs, plan, out, q_hat, q_bf16, q_scale, tmp;
+    DevBuf sel_rows, sel_inv, sel_ids, sel_meta;   // K2T row selection (dense_compact.cuh): compacted copy, its inverse norms / row ids, {count, decision, block sums}
+    bool sel_no_memory = false;               // the scratch matrix did not fit once: do not try again
     DevBuf ms_rec, ms_q, ms_units, ms_counters, mh_units;  // K3M / K3H: plan output, work-unit prefixes, counters
-    HostBuf h_args_s[2], h_out_s[2], h_stage;
+    HostBuf h_args_s[2], h_out_s[2], h_stage, h_sel[2];
+    bool sel_ran[2] = {false, false};         // the row selection ran for the batch staged in this slot
     uint32_t cand_cap = 0;
 
     // options
@@ -184,6 +189,8 @@ struct vb_index {
     int64_t opt_ms_staged = 1;             // K3M: 1 = posting stages over the whole index, 0 = once per row segment
     int64_t opt_ms_stage_ratio = 0;        // K3M: growth of the posting stages (0 = auto: 32, up to 1024 for tiny batches)
     int64_t opt_delta_max = 0;             // rows the delta may hold before vb_upsert merges it into the index (0 = auto)
+    int64_t opt_dense_compact_min_rows = 1 << 18;   // ... on segments of at least this many rows (tests lower it)
+    int64_t opt_dense_compact = 70;        // K2T: walk a compacted copy of the passing rows when a batch-wide filter passes at most this % (0 = never)
     int64_t opt_ms_ctas = 0;               // K3M: resident CTAs per SM of the persistent score kernel (0 = auto, see ms_launch)
     int64_t opt_ms_long_terms = 16, opt_ms_budget_long = 85;   // K3M: queries of more terms than the first plan with the second budget
                                            // (cfg5 shard, 2..65-term queries: 561 ms per batch at 100 %, 154 at 92, 153-156 at 85, 160 at 70, 188 at 40)
@@ -380,15 +387,17 @@ extern "C" void vb_destroy(vb_index* h) {
     for (DevBuf* b : {&h->rows, &h->inv_norm, &h->scope_id, &h->created, &h->modified, &h->alive, &h->sp_indptr,
                       &h->sp_term, &h->sp_val, &h->post_row, &h->post_val, &h->heavy_vals, &h->args, &h->mask, &h->cand, &h->lists,
                       &h->offs, &h->plan, &h->out, &h->q_hat, &h->q_bf16, &h->q_scale, &h->tmp,
-                      &h->ms_rec, &h->ms_q, &h->ms_units, &h->ms_counters, &h->mh_units, &h->term_tab})
+                      &h->ms_rec, &h->ms_q, &h->ms_units, &h->ms_counters, &h->mh_units, &h->term_tab,
+                      &h->sel_rows, &h->sel_inv, &h->sel_ids, &h->sel_meta})
         dev_free(h, *b);
-    for (HostBuf* b : {&h->h_args_s[0], &h->h_args_s[1], &h->h_out_s[0], &h->h_out_s[1], &h->h_stage}) if (b->p) cudaFreeHost(b->p);
+    for (HostBuf* b : {&h->h_args_s[0], &h->h_args_s[1], &h->h_out_s[0], &h->h_out_s[1], &h->h_stage, &h->h_sel[0], &h->h_sel[1]}) if (b->p) cudaFreeHost(b->p);
     for (auto ev : h->prof_events) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(h->ev0s[i]); cudaEventDestroy(h->ev1s[i]); cudaEventDestroy(h->ev_done[i]); }
     if (h->ev_q) cudaEventDestroy(h->ev_q);
     cudaEventDestroy(h->ev_fork);
     cudaEventDestroy(h->ev_join);
     cudaStreamDestroy(h->aux_stream);
+    if (h->sel_stream) { cudaStreamDestroy(h->sel_stream); cudaEventDestroy(h->ev_sel_fork); for (auto e : h->ev_sel) cudaEventDestroy(e); }
     cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -414,6 +423,8 @@ extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
     else if (k == "ms_staged") h->opt_ms_staged = value;           // K3M: posting stages (1) or row segments (0)
     else if (k == "ms_stage_ratio") h->opt_ms_stage_ratio = value; // K3M: growth of the posting stages
     else if (k == "delta_max") h->opt_delta_max = value;           // delta rows that trigger a merge (0 = max(16384, base/32))
+    else if (k == "dense_compact_min_rows") h->opt_dense_compact_min_rows = value;
+    else if (k == "dense_compact") h->opt_dense_compact = value;   // K2T row selection threshold in % of the segment's rows (0 = off)
     else if (k == "ms_ctas") h->opt_ms_ctas = value;               // K3M: CTAs per SM of the score kernel (0 = auto)
     else if (k == "k2t_stages") g_k2t_stages = (int)value;         // K2T: TMA ring depth (0 = default 4); process-wide
     else if (k == "ms_long_terms") h->opt_ms_long_terms = value;   // K3M: queries above this many terms use ms_budget_long
@@ -1296,6 +1307,7 @@ static int prepare_batch(vb_index* h, const vb_query_batch* q, Batch& b, bool ne
     b.out_bytes = ao.off;
     TRY(dev_reserve(h, h->out, b.out_bytes, false));
     TRY(host_reserve(h->h_out_s[h->cur], b.out_bytes));
+    h->sel_ran[h->cur] = false;
     b.valid = true;
     return 0;
 }
@@ -1451,6 +1463,77 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         CK(cudaEventRecord(h->ev_fork, sd));
         CK(cudaStreamWaitEvent(ss, h->ev_fork, 0));
     }
+    // ---- K2T row selection plan (dense_compact.cuh): the tensor-bound kernel, ONE filter for the whole batch, every
+    // segment of at least dense_compact_min_rows rows.  Count, list and copy run on a side stream right after the mask
+    // kernel: the copy of segment s + 1 (HBM-bound) hides behind the GEMM of segment s (tensor-bound).  With the chains
+    // serialised (overlap = 0: per-phase timing) they run inline on the dense stream and are charged to the dense phase.
+    struct SelSeg { bool on = false; uint32_t cap_rows = 0, n_blocks = 0, ev = 0; size_t row_off = 0, meta_off = 0; };
+    std::vector<SelSeg> selseg(bounds.size() - 1);
+    bool sel_any = false;
+    const bool sel_side = h->opt_overlap != 0;
+    if (tiled && b.use_mask && h->opt_dense_compact > 0 && !h->sel_no_memory && h->d_pad <= 1024 && phase != 1) {
+        bool uniform = b.mask_of_host[0] >= 0;
+        for (uint32_t i = 1; uniform && i < b.B; ++i) uniform = b.mask_of_host[i] == b.mask_of_host[0];
+        size_t rows_total = 0, meta_total = 0;
+        uint32_t n_on = 0;
+        for (size_t si = (direct_rows ? 1 : 0); uniform && si + 1 < bounds.size() && n_on < 8u; ++si) {
+            const uint32_t r0 = bounds[si], r1 = bounds[si + 1];
+            if ((r0 % 128u) != 0u || (int64_t)(r1 - r0) < h->opt_dense_compact_min_rows) continue;
+            SelSeg& z = selseg[si];
+            z.on = true; z.cap_rows = (uint32_t)align_up(r1 - r0, 128); z.n_blocks = ((r1 - r0 + 31u) / 32u + VB_SEL_WORDS - 1u) / VB_SEL_WORDS;
+            z.row_off = rows_total; z.meta_off = meta_total; z.ev = n_on++;
+            rows_total += z.cap_rows; meta_total += align_up((size_t)4 + z.n_blocks, 4);
+        }
+        const size_t scratch = rows_total * h->d_pad * 2;
+        if (n_on && scratch > h->sel_rows.cap) {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b + h->sel_rows.cap < scratch + (4ull << 30)) {
+                cudaGetLastError();
+                h->sel_no_memory = true;                         // the scratch matrix does not fit beside the shard: stay in place
+                n_on = 0;
+            }
+        }
+        if (n_on) {
+            TRY(dev_reserve(h, h->sel_rows, scratch, false));
+            TRY(dev_reserve(h, h->sel_inv, rows_total * 4, false));
+            TRY(dev_reserve(h, h->sel_ids, rows_total * 4, false));
+            TRY(dev_reserve(h, h->sel_meta, meta_total * 4, false));
+            sel_any = true;
+        } else for (auto& z : selseg) z.on = false;
+    }
+    auto sel_launch = [&](size_t si, cudaStream_t st) -> int {
+        const SelSeg& z = selseg[si];
+        const uint32_t r0 = bounds[si], r1 = bounds[si + 1];
+        VbRowSelArgs sa{};
+        sa.mask = h->mask.as<uint32_t>() + (size_t)b.mask_of_host[0] * b.mask_words;
+        sa.word_begin = r0 / 32u; sa.word_end = (r1 + 31u) / 32u; sa.row_end = r1;
+        sa.sel = h->sel_meta.as<uint32_t>() + z.meta_off; sa.block_sums = sa.sel + 4; sa.ids = h->sel_ids.as<uint32_t>() + z.row_off;
+        sa.pct = (uint32_t)std::min<int64_t>(100, h->opt_dense_compact); sa.pad_row = r0; sa.cap_rows = z.cap_rows;
+        vb_rowsel_count_kernel<<<z.n_blocks, VB_SEL_THREADS, 0, st>>>(sa);
+        CKK("vb_rowsel_count_kernel");
+        vb_rowsel_scatter_kernel<<<z.n_blocks, VB_SEL_THREADS, 0, st>>>(sa);
+        CKK("vb_rowsel_scatter_kernel");
+        vb_rowsel_gather_kernel<<<h->sm_count * 8, 256, 0, st>>>(h->rows.as<uint4>(), h->inv_norm.as<float>(), sa.ids, sa.sel,
+                                                                h->sel_rows.as<uint4>() + z.row_off * (h->d_pad / 8), h->sel_inv.as<float>() + z.row_off,
+                                                                (uint32_t)h->d_pad / 8u);
+        CKK("vb_rowsel_gather_kernel");
+        h->stats.last_launches += 3;
+        return 0;
+    };
+    if (sel_any && sel_side) {
+        if (!h->sel_stream) {
+            CK(cudaStreamCreateWithFlags(&h->sel_stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&h->ev_sel_fork, cudaEventDisableTiming));
+            for (auto& e : h->ev_sel) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        CK(cudaEventRecord(h->ev_sel_fork, sd));                 // after the mask kernel (and after the previous batch's dense chain)
+        CK(cudaStreamWaitEvent(h->sel_stream, h->ev_sel_fork, 0));
+        for (size_t si = 0; si < selseg.size(); ++si)
+            if (selseg[si].on) {
+                TRY(sel_launch(si, h->sel_stream));
+                CK(cudaEventRecord(h->ev_sel[selseg[si].ev], h->sel_stream));
+            }
+    }
     auto dense_single_pass = [&]() -> int {
         const int pi = prof_begin(h, PH_DENSE | PH_BIG, sd);
         VbScan1Args a{};
@@ -1494,6 +1577,22 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
             g.n_rows_total = n; g.row_begin = r0; g.row_end = r1; g.row_base = (uint32_t)h->row_base;
             g.d_pad = (uint32_t)h->d_pad; g.n_queries = b.B; g.sm_count = h->sm_count; g.stream = sd;
             g.direct = direct; g.plan = plan; g.mask_of_host = b.mask_of_host.data();
+            // Row selection (planned before the segment loop): wait for / run this segment's selection and hand the
+            // compacted copy to the kernel, which reads the device-side decision
+            for (size_t si = 0; si + 1 < bounds.size(); ++si)
+                if (bounds[si] == r0 && selseg[si].on) {
+                    SelSeg& z = selseg[si];
+                    if (sel_side) CK(cudaStreamWaitEvent(sd, h->ev_sel[z.ev], 0));
+                    else TRY(sel_launch(si, sd));
+                    g.sel = h->sel_meta.as<uint32_t>() + z.meta_off; g.sel_ids = h->sel_ids.as<uint32_t>() + z.row_off;
+                    g.sel_inv_norm = h->sel_inv.as<float>() + z.row_off;
+                    g.sel_rows = h->sel_rows.as<unsigned char>() + z.row_off * h->d_pad * 2; g.sel_cap_rows = z.cap_rows;
+                    if (big) {                                   // {rows, decision} of the roofline's segment for vb_stats
+                        TRY(host_reserve(h->h_sel[h->cur], 16));
+                        CK(cudaMemcpyAsync(h->h_sel[h->cur].p, g.sel, 8, cudaMemcpyDeviceToHost, sd));
+                        h->sel_ran[h->cur] = true;
+                    }
+                }
             int launches = 0;
             if ((tiled ? vb_gemm_tiled_launch(g, &launches) : vb_gemm_launch(g, &launches)) != 0)
                 return vb_fail("tensor-core dense kernel: %s", vb_gemm_last_error());
@@ -1823,6 +1922,8 @@ static void finish_stats(vb_index* h, const Batch& b) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev0s[h->cur], h->ev1s[h->cur]);
     h->stats.last_search_ms = ms;
+    h->stats.last_sel_rows = h->sel_ran[h->cur] ? h->h_sel[h->cur].as<uint32_t>()[0] : 0u;
+    h->stats.last_sel_used = h->sel_ran[h->cur] ? h->h_sel[h->cur].as<uint32_t>()[1] : 0u;
     h->stats.searches += 1;
     h->stats.queries += b.B;
     if (h->opt_profile) prof_collect(h);

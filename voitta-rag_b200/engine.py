@@ -66,10 +66,13 @@ class _Stats(C.Structure):
                 ("last_h2d_bytes", C.c_uint64), ("last_d2h_bytes", C.c_uint64), ("last_dense_passes", C.c_uint64),
                 ("last_big_rows", C.c_uint64), ("last_dense_big_ms", C.c_double), ("last_sparse_big_ms", C.c_double),
                 ("dim", C.c_uint64), ("row_base", C.c_uint64), ("index_builds", C.c_uint64), ("delta_rows", C.c_uint64),
-                ("last_overflow_lists", C.c_uint32), ("last_overflow_first", C.c_uint32)]
+                ("last_overflow_lists", C.c_uint32), ("last_overflow_first", C.c_uint32),
+                ("last_sel_rows", C.c_uint32), ("last_sel_used", C.c_uint32)]
 
 
 # every symbol include/voitta_b200.h declares
+ABI_VERSION = 3          # include/voitta_b200.h VB_ABI_VERSION
+
 EXPORTS = ["vb_abi_version", "vb_last_error", "vb_create", "vb_destroy", "vb_upsert", "vb_upsert_dev",
            "vb_delete_rows", "vb_optimize", "vb_term_stats", "vb_search", "vb_search_local", "vb_merge_fuse",
            "vb_stage", "vb_run_local", "vb_run_fuse", "vb_fetch", "vb_stage_dev", "vb_search_dev",
@@ -90,6 +93,8 @@ def load_library():
     lib = C.CDLL(str(LIB_PATH))
     vp, u64p, u32p = C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
     lib.vb_abi_version.restype = C.c_int
+    if lib.vb_abi_version() != ABI_VERSION:
+        raise B200Error(f"{LIB_PATH} has ABI version {lib.vb_abi_version()}, this module binds version {ABI_VERSION}: rebuild it")
     lib.vb_last_error.restype = C.c_char_p
     lib.vb_create.argtypes = [C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.POINTER(vp)]
     lib.vb_destroy.argtypes = [vp]
