@@ -60,6 +60,8 @@ WORKLOADS = {
                        desc="10M x 768-d hybrid, scope+time filter 1%, batch 1"),
     "cfg3-b256-s50": dict(n=10_000_000, dim=768, batch=256, limit=10, fusion="rrf", sel=0.5, dist="C", bps=4, ref_rows=1_000_000, ref_q=8,
                           desc="10M x 768-d hybrid, scope+time filter 50%, batch 256"),
+    "cfg3-b256-s1": dict(n=10_000_000, dim=768, batch=256, limit=10, fusion="rrf", sel=0.01, dist="C", bps=16, ref_rows=1_000_000, ref_q=8,
+                         desc="10M x 768-d hybrid, scope+time filter 1%, batch 256"),
     # one of the 8 row shards of configs[3] (same as cfg4 at --gpus 1; kept for the round-1 profile names)
     "cfg4-shard": dict(n=12_500_000, dim=768, batch=1024, limit=100, fusion="rrf", sel=0.5, dist="C", bps=1, ref_rows=1_000_000, ref_q=8,
                        desc="one 12.5M-row shard of 100M x 768-d hybrid, filter 50%, batch 1024, top-100"),
@@ -558,6 +560,9 @@ def main():
         phase += [s_["last_mask_ms"], s_["last_dense_ms"], s_["last_sparse_ms"], s_["last_select_ms"], s_["last_fuse_ms"]]
         big += [s_["last_dense_big_ms"], s_["last_sparse_big_ms"]]
     big_rows = int(ix.stats()["last_big_rows"])
+    # K2T row selection (dense_compact.cuh): the tensor-core kernel scored only the rows passing the batch-wide filter
+    sel_used, sel_rows = int(ix.stats()["last_sel_used"]), int(ix.stats()["last_sel_rows"])
+    scored_share = (sel_rows / max(1, big_rows)) if sel_used else 1.0
     # one more batch with the two chains on their two streams and the events still on: the timeline shows how
     # much of the sparse chain runs under the dense one
     ix.set_option("overlap", 1)
@@ -596,7 +601,7 @@ def main():
            "select": 0.0, "fuse": 0.0}
     dom_name = names[dom]
     # the roofline is quoted on ONE launch: the dominant kernel's launch over the largest segment
-    frac_rows = big_rows / max(1, rows_local)
+    frac_rows = big_rows * scored_share / max(1, rows_local)      # rows the dominant launch scored / rows of the shard
     if dom_name == "dense" and big[0] > 0:
         launch_ms = float(big[0] / n_prof)
         launch_bytes = alg["dense"] / passes * frac_rows
@@ -618,14 +623,20 @@ def main():
     tf_launch = (dense_flops * frac_rows / (big[0] / n_prof / 1e3) / 1e12) if big[0] > 0 else None
     tensor_bound = tensor_bound and dom_name == "dense"
     roofline = {"kernel": kname[dom_name],
-                "launch": ("largest segment: %d of %d rows, one of %d pass(es)" % (big_rows, rows_local, passes)) if dom_name == "dense"
+                "launch": (("largest segment: %d of %d rows, one of %d pass(es)" % (big_rows, rows_local, passes))
+                           + ((": the kernel walked the compacted copy of the %d rows (%.1f %%) that pass the batch-wide filter"
+                               % (sel_rows, 100.0 * scored_share)) if sel_used else "")) if dom_name == "dense"
                           else "all launches of the phase in one batch",
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind}, burst copy)", "traffic": traffic, "traffic_capture": traffic_src,
                 "algorithmic_bytes_per_launch": launch_bytes, "kernel_ms_per_launch": launch_ms,
                 "how": "CUDA events around each kernel on its launching stream, chains serialised on one stream, %d batches after the timed region" % n_prof,
-                "dense_tflops_per_batch": dense_flops / (per_batch[1] / 1e3) / 1e12 if per_batch[1] > 0 else None,
-                "step_tflops": dense_flops * bps * args.steps / (total_ms / 1e3) / 1e12,
+                "dense_tflops_per_batch": dense_flops * scored_share / (per_batch[1] / 1e3) / 1e12 if per_batch[1] > 0 else None,
+                "step_tflops": dense_flops * scored_share * bps * args.steps / (total_ms / 1e3) / 1e12,
+                "step_tflops_nominal": dense_flops * bps * args.steps / (total_ms / 1e3) / 1e12,
+                "step_tflops_note": "step_tflops counts the flops EXECUTED (rows the filter drops are not multiplied when the row "
+                                    "selection is on: scored share %.3f); step_tflops_nominal is 2*B*rows*d_pad over the same time, "
+                                    "i.e. the rate an all-rows GEMM would need for this step time" % scored_share,
                 "phase_ms_per_batch": {n_: float(v) for n_, v in zip(names, per_batch)},
                 "phase_gbs_per_batch": {n_: (alg[n_] / (per_batch[j] / 1e3) / 1e9 if per_batch[j] > 0 else None) for j, n_ in enumerate(names)},
                 "sparse_note": "sparse bytes are SURVEY §8(d)'s sum(df)*8 (every posting of every query term); the MaxScore kernel "

@@ -147,15 +147,19 @@ struct VbGemmArgs {
     uint32_t split;                  // 1: columns [0,bn/2) hold q_hi, [bn/2,bn) hold q_lo (bf16x2 query precision)
     uint32_t kbox;                   // K-blocks (of 64) per TMA box / pipeline stage
     uint32_t debug;                  // perf triage only (VB200_K2_DEBUG): 1 skip epilogue math, 2 skip MMA, 4 skip TMA
+    // SEL (dense_compact.cuh): sel[1] != 0 -> walk the compacted copy of the rows that pass the shared filter instead
+    const uint32_t* sel;             // [0] rows of the copy, [1] decision (taken on the device)
+    const uint32_t* sel_ids;         // [rows of the copy] shard row id of each copied row
+    const float* sel_inv_norm;       // [rows of the copy]
 };
 
 // MODE: per-column mask handling (0 = none / one filter folded into the row scale, 2 = <= 31
 // filters via a per-row bit set, 3 = general); SPLIT: bf16x2 query; DIRECT: first-segment stores.
 // They are template parameters so that the per-column epilogue code is branch-free.
-template <int MODE, bool SPLIT, bool DIRECT>
+template <int MODE, bool SPLIT, bool DIRECT, bool SEL>
 __global__ void __launch_bounds__(VB_GEMM_THREADS, 1)
 vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_q,
-                     const VbGemmArgs a)
+                     const __grid_constant__ CUtensorMap tmap_c, const VbGemmArgs a)
 {
     extern __shared__ unsigned char vb_gemm_smem_raw[];
     // 1024-byte alignment for the 128B-swizzle atoms
@@ -203,24 +207,29 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     vb_tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    const uint32_t n_tiles = a.tile_end - a.tile_begin;
+    // SEL: the row-selection kernels decided (on the device) whether this launch walks the compacted copy
+    const bool cmp = SEL && a.sel[1] != 0u;
+    const uint32_t tile_begin = cmp ? 0u : a.tile_begin;
+    const uint32_t row_end = cmp ? a.sel[0] : a.row_end;
+    const uint32_t n_tiles = cmp ? (a.sel[0] + VB_TILE_M - 1u) / VB_TILE_M : a.tile_end - a.tile_begin;
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
+            const CUtensorMap* tmap_rows = cmp ? &tmap_c : &tmap_a;
             vb_mbar_expect_tx(bar_q, q_bytes);
             for (uint32_t kb = 0; kb < a.k_blocks; ++kb)
                 vb_tma_load_2d(vb_smem_u32(smem_q + kb * a.bn * 128u), &tmap_q, (int32_t)(kb * VB_BLOCK_K), 0, bar_q);
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int32_t row0 = (int32_t)((a.tile_begin + t) * VB_TILE_M);
+                const int32_t row0 = (int32_t)((tile_begin + t) * VB_TILE_M);
                 for (uint32_t kb = 0; kb < a.k_blocks; kb += a.kbox) {
                     vb_mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
                     if (a.debug & 4u) { vb_mbar_arrive(bar_full + 8u * stage); }
                     else {
                     vb_mbar_expect_tx(bar_full + 8u * stage, stage_bytes);
                     // one box = 128 rows x kbox K-blocks: [kb][row][64] in smem, i.e. kbox UMMA slabs
-                    vb_tma_load_3d(vb_smem_u32(smem_a + stage * stage_bytes), &tmap_a, 0, row0, (int32_t)kb, bar_full + 8u * stage);
+                    vb_tma_load_3d(vb_smem_u32(smem_a + stage * stage_bytes), tmap_rows, 0, row0, (int32_t)kb, bar_full + 8u * stage);
                     }
                     if (++stage == S) { stage = 0; phase ^= 1u; }
                 }
@@ -272,15 +281,18 @@ vb_dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         uint32_t it = 0;
         for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const uint32_t acc = it & 1u;
-            const uint32_t tile = a.tile_begin + t;
-            const uint32_t row = tile * VB_TILE_M + quad * 32u + lane;
-            const bool row_ok = row < a.row_end;
+            const uint32_t tile = tile_begin + t;
+            const uint32_t pos = tile * VB_TILE_M + quad * 32u + lane;       // row of the matrix this launch walks
+            const bool row_ok = pos < row_end;
+            // the shard row behind it: itself, or (compacted copy) the id the selection recorded
+            const uint32_t row = cmp ? (row_ok ? a.sel_ids[pos] : 0u) : pos;
+            VB_CHECK(row < a.row_end || !row_ok);
             // global loads are issued before blocking on the accumulator.
             // A row that is out of range or (modes 0/1) masked gets a NaN scale: every compare fails.
-            float invn = row_ok ? a.inv_norm[row] : qnan;
+            float invn = row_ok ? (cmp ? a.sel_inv_norm[pos] : a.inv_norm[pos]) : qnan;
             const uint32_t word = tile * 4u + quad;
             uint32_t fbits = 0x80000000u;                 // mode 2: bit f = row passes filter f; bit 31 = unfiltered
-            if (MODE == 0 && a.mask_mode == 1u) {
+            if (MODE == 0 && a.mask_mode == 1u && !cmp) { // (every row of the compacted copy passes the shared filter)
                 const uint32_t w = word < a.mask_words ? a.mask[(size_t)a.uniform_filter * a.mask_words + word] : 0u;
                 if (!((w >> lane) & 1u)) invn = qnan;
             } else if (mode == 2u) {
@@ -649,16 +661,17 @@ typedef CUresult (*VbEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 static VbEncodeTiledFn g_encode_tiled = nullptr;
 static int g_gemm_smem_max = 0;
 
-typedef void (*VbGemmKernel)(const CUtensorMap, const CUtensorMap, const VbGemmArgs);
-// variant index = modeIdx*4 + split*2 + direct, modeIdx: 0 -> MODE 0, 1 -> MODE 2, 2 -> MODE 3
+typedef void (*VbGemmKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const VbGemmArgs);
+// variant index = modeIdx*4 + split*2 + direct, modeIdx: 0 -> MODE 0, 1 -> MODE 2, 2 -> MODE 3; 12 / 13: row selection (MODE 0, not direct), split 0 / 1
 static VbGemmKernel vb_gemm_variant(int i) {
-    static const VbGemmKernel table[12] = {
-        vb_dense_gemm_kernel<0, false, false>, vb_dense_gemm_kernel<0, false, true>,
-        vb_dense_gemm_kernel<0, true, false>,  vb_dense_gemm_kernel<0, true, true>,
-        vb_dense_gemm_kernel<2, false, false>, vb_dense_gemm_kernel<2, false, true>,
-        vb_dense_gemm_kernel<2, true, false>,  vb_dense_gemm_kernel<2, true, true>,
-        vb_dense_gemm_kernel<3, false, false>, vb_dense_gemm_kernel<3, false, true>,
-        vb_dense_gemm_kernel<3, true, false>,  vb_dense_gemm_kernel<3, true, true>,
+    static const VbGemmKernel table[14] = {
+        vb_dense_gemm_kernel<0, false, false, false>, vb_dense_gemm_kernel<0, false, true, false>,
+        vb_dense_gemm_kernel<0, true, false, false>,  vb_dense_gemm_kernel<0, true, true, false>,
+        vb_dense_gemm_kernel<2, false, false, false>, vb_dense_gemm_kernel<2, false, true, false>,
+        vb_dense_gemm_kernel<2, true, false, false>,  vb_dense_gemm_kernel<2, true, true, false>,
+        vb_dense_gemm_kernel<3, false, false, false>, vb_dense_gemm_kernel<3, false, true, false>,
+        vb_dense_gemm_kernel<3, true, false, false>,  vb_dense_gemm_kernel<3, true, true, false>,
+        vb_dense_gemm_kernel<0, false, false, true>, vb_dense_gemm_kernel<0, true, false, true>,
     };
     return table[i];
 }
@@ -675,7 +688,7 @@ static int vb_gemm_configure() {
     int dev = 0, smem = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    for (int i = 0; i < 12; ++i) {
+    for (int i = 0; i < 14; ++i) {
         e = cudaFuncSetAttribute(vb_gemm_variant(i), cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { g_gemm_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return 1; }
     }
@@ -801,6 +814,8 @@ static int vb_gemm_launch(const VbGemmLaunch& g, int* launches) {
     (void)k_blocks;
     CUtensorMap tmap_a;
     if (vb_encode_a3d(&tmap_a, g.rows, g.n_rows_total, g.d_pad, kbox, vb_env_int("VB200_K2_L2PROMO", 1))) return 1;
+    CUtensorMap tmap_c = tmap_a;
+    if (g.sel && vb_encode_a3d(&tmap_c, g.sel_rows, g.sel_cap_rows, g.d_pad, kbox, vb_env_int("VB200_K2_L2PROMO", 1))) return 1;
     for (uint32_t q0 = 0; q0 < g.n_queries; q0 += sub) {
         const uint32_t n_q = std::min(sub, g.n_queries - q0);
         const uint32_t bn = (n_q + 15u) / 16u * 16u * mult;
@@ -833,8 +848,12 @@ static int vb_gemm_launch(const VbGemmLaunch& g, int* launches) {
         const size_t smem = 1024u + q_bytes + a.stages * kbox * VB_STAGE_BYTES + VB_GEMM_TAIL_BYTES;
         const uint32_t tiles = a.tile_end - a.tile_begin;
         const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)g.sm_count);
-        const int variant = (a.mask_mode >= 2u ? (int)a.mask_mode - 1 : 0) * 4 + (a.split ? 2 : 0) + (a.direct ? 1 : 0);
-        vb_gemm_variant(variant)<<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, a);
+        int variant = (a.mask_mode >= 2u ? (int)a.mask_mode - 1 : 0) * 4 + (a.split ? 2 : 0) + (a.direct ? 1 : 0);
+        if (g.sel != nullptr && a.mask_mode == 1u && !a.direct) {
+            a.sel = g.sel; a.sel_ids = g.sel_ids; a.sel_inv_norm = g.sel_inv_norm;
+            variant = 12 + (a.split ? 1 : 0);
+        }
+        vb_gemm_variant(variant)<<<grid, VB_GEMM_THREADS, smem, g.stream>>>(tmap_a, tmap_q, tmap_c, a);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { g_gemm_err = std::string("launch failed: ") + cudaGetErrorString(e); return 1; }
         ++*launches;

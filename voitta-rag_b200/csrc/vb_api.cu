@@ -190,7 +190,8 @@ struct vb_index {
     int64_t opt_ms_stage_ratio = 0;        // K3M: growth of the posting stages (0 = auto: 32, up to 1024 for tiny batches)
     int64_t opt_delta_max = 0;             // rows the delta may hold before vb_upsert merges it into the index (0 = auto)
     int64_t opt_dense_compact_min_rows = 1 << 18;   // ... on segments of at least this many rows (tests lower it)
-    int64_t opt_dense_compact = 70;        // K2T: walk a compacted copy of the passing rows when a batch-wide filter passes at most this % (0 = never)
+    int64_t opt_dense_compact = -1;        // K2 / K2T: walk a compacted copy of the passing rows when a batch-wide filter passes at most this % of a
+                                           // segment (0 = never, -1 = auto: where the copy costs less than the passes over the dropped rows)
     int64_t opt_ms_ctas = 0;               // K3M: resident CTAs per SM of the persistent score kernel (0 = auto, see ms_launch)
     int64_t opt_ms_long_terms = 16, opt_ms_budget_long = 85;   // K3M: queries of more terms than the first plan with the second budget
                                            // (cfg5 shard, 2..65-term queries: 561 ms per batch at 100 %, 154 at 92, 153-156 at 85, 160 at 70, 188 at 40)
@@ -424,7 +425,7 @@ extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
     else if (k == "ms_stage_ratio") h->opt_ms_stage_ratio = value; // K3M: growth of the posting stages
     else if (k == "delta_max") h->opt_delta_max = value;           // delta rows that trigger a merge (0 = max(16384, base/32))
     else if (k == "dense_compact_min_rows") h->opt_dense_compact_min_rows = value;
-    else if (k == "dense_compact") h->opt_dense_compact = value;   // K2T row selection threshold in % of the segment's rows (0 = off)
+    else if (k == "dense_compact") h->opt_dense_compact = value;   // row selection threshold in % of the segment's rows (0 = off, -1 = auto)
     else if (k == "ms_ctas") h->opt_ms_ctas = value;               // K3M: CTAs per SM of the score kernel (0 = auto)
     else if (k == "k2t_stages") g_k2t_stages = (int)value;         // K2T: TMA ring depth (0 = default 4); process-wide
     else if (k == "ms_long_terms") h->opt_ms_long_terms = value;   // K3M: queries above this many terms use ms_budget_long
@@ -1471,7 +1472,17 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     std::vector<SelSeg> selseg(bounds.size() - 1);
     bool sel_any = false;
     const bool sel_side = h->opt_overlap != 0;
-    if (tiled && b.use_mask && h->opt_dense_compact > 0 && !h->sel_no_memory && h->d_pad <= 1024 && phase != 1) {
+    // auto threshold: the copy costs ~0.49 ns per passing row (read + write of 2 * d_pad bytes at HBM speed, d_pad = 768);
+    // one pass of the tensor-core kernel over a row costs max(0.245 ns (HBM), 1.08 ns * queries / 1024 (tensor pipe)) — both
+    // scale with d_pad alike.  Copying pays when (1 - p) * passes' time > p * copy time.
+    uint32_t sel_pct = (uint32_t)std::max<int64_t>(0, std::min<int64_t>(100, h->opt_dense_compact));
+    if (h->opt_dense_compact < 0 && path == 2) {
+        double T = 0.0;
+        if (tiled) for (uint32_t q0 = 0; q0 < b.B; q0 += VB_TILED_MAX_Q) T += std::max(0.245, 1.08 * std::min(VB_TILED_MAX_Q, b.B - q0) / 1024.0);
+        else T = 0.245 * ((b.B + plan.sub - 1) / plan.sub);
+        sel_pct = (uint32_t)(95.0 * T / (T + 0.49));
+    }
+    if (path == 2 && !k1f && b.use_mask && sel_pct > 0 && !h->sel_no_memory && h->d_pad <= 1024 && phase != 1) {
         bool uniform = b.mask_of_host[0] >= 0;
         for (uint32_t i = 1; uniform && i < b.B; ++i) uniform = b.mask_of_host[i] == b.mask_of_host[0];
         size_t rows_total = 0, meta_total = 0;
@@ -1508,7 +1519,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         sa.mask = h->mask.as<uint32_t>() + (size_t)b.mask_of_host[0] * b.mask_words;
         sa.word_begin = r0 / 32u; sa.word_end = (r1 + 31u) / 32u; sa.row_end = r1;
         sa.sel = h->sel_meta.as<uint32_t>() + z.meta_off; sa.block_sums = sa.sel + 4; sa.ids = h->sel_ids.as<uint32_t>() + z.row_off;
-        sa.pct = (uint32_t)std::min<int64_t>(100, h->opt_dense_compact); sa.pad_row = r0; sa.cap_rows = z.cap_rows;
+        sa.pct = sel_pct; sa.pad_row = r0; sa.cap_rows = z.cap_rows;
         vb_rowsel_count_kernel<<<z.n_blocks, VB_SEL_THREADS, 0, st>>>(sa);
         CKK("vb_rowsel_count_kernel");
         vb_rowsel_scatter_kernel<<<z.n_blocks, VB_SEL_THREADS, 0, st>>>(sa);
@@ -1568,6 +1579,26 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
     };
     auto dense_segment = [&](uint32_t r0, uint32_t r1, uint32_t direct, bool big) -> int {
         if (k1f) return 0;                                      // the single pass covers every segment
+        // Row selection (planned before the segment loop): wait for this segment's copy (side stream), or run the
+        // selection here (chains serialised: its own timed region of the dense phase, so that the PH_BIG region
+        // stays the tensor-core kernel alone)
+        const SelSeg* zsel = nullptr;
+        if (path == 2)
+            for (size_t si = 0; si + 1 < bounds.size(); ++si)
+                if (bounds[si] == r0 && selseg[si].on) {
+                    zsel = &selseg[si];
+                    if (sel_side) CK(cudaStreamWaitEvent(sd, h->ev_sel[zsel->ev], 0));
+                    else {
+                        const int pz = prof_begin(h, PH_DENSE, sd);
+                        TRY(sel_launch(si, sd));
+                        prof_end(h, pz, sd);
+                    }
+                    if (big) {                                   // {rows, decision} of the roofline's segment for vb_stats
+                        TRY(host_reserve(h->h_sel[h->cur], 16));
+                        CK(cudaMemcpyAsync(h->h_sel[h->cur].p, h->sel_meta.as<uint32_t>() + zsel->meta_off, 8, cudaMemcpyDeviceToHost, sd));
+                        h->sel_ran[h->cur] = true;
+                    }
+                }
         const int pi = prof_begin(h, PH_DENSE | (big ? PH_BIG : 0), sd);
         if (path == 2) {
             VbGemmLaunch g{};
@@ -1577,22 +1608,11 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
             g.n_rows_total = n; g.row_begin = r0; g.row_end = r1; g.row_base = (uint32_t)h->row_base;
             g.d_pad = (uint32_t)h->d_pad; g.n_queries = b.B; g.sm_count = h->sm_count; g.stream = sd;
             g.direct = direct; g.plan = plan; g.mask_of_host = b.mask_of_host.data();
-            // Row selection (planned before the segment loop): wait for / run this segment's selection and hand the
-            // compacted copy to the kernel, which reads the device-side decision
-            for (size_t si = 0; si + 1 < bounds.size(); ++si)
-                if (bounds[si] == r0 && selseg[si].on) {
-                    SelSeg& z = selseg[si];
-                    if (sel_side) CK(cudaStreamWaitEvent(sd, h->ev_sel[z.ev], 0));
-                    else TRY(sel_launch(si, sd));
-                    g.sel = h->sel_meta.as<uint32_t>() + z.meta_off; g.sel_ids = h->sel_ids.as<uint32_t>() + z.row_off;
-                    g.sel_inv_norm = h->sel_inv.as<float>() + z.row_off;
-                    g.sel_rows = h->sel_rows.as<unsigned char>() + z.row_off * h->d_pad * 2; g.sel_cap_rows = z.cap_rows;
-                    if (big) {                                   // {rows, decision} of the roofline's segment for vb_stats
-                        TRY(host_reserve(h->h_sel[h->cur], 16));
-                        CK(cudaMemcpyAsync(h->h_sel[h->cur].p, g.sel, 8, cudaMemcpyDeviceToHost, sd));
-                        h->sel_ran[h->cur] = true;
-                    }
-                }
+            if (zsel) {                                          // K2T walks the compacted copy when the device-side decision says so
+                g.sel = h->sel_meta.as<uint32_t>() + zsel->meta_off; g.sel_ids = h->sel_ids.as<uint32_t>() + zsel->row_off;
+                g.sel_inv_norm = h->sel_inv.as<float>() + zsel->row_off;
+                g.sel_rows = h->sel_rows.as<unsigned char>() + zsel->row_off * h->d_pad * 2; g.sel_cap_rows = zsel->cap_rows;
+            }
             int launches = 0;
             if ((tiled ? vb_gemm_tiled_launch(g, &launches) : vb_gemm_launch(g, &launches)) != 0)
                 return vb_fail("tensor-core dense kernel: %s", vb_gemm_last_error());
