@@ -4,13 +4,13 @@
 # tools/summarize_profiles_r2.py (run in the dev container afterwards) turns it into the tracked files under profiles/.
 R=r02
 mkdir -p gpurun_out
-SEARCH='regex:vb_(ms_|mh_|dense|compact|fuse|mask|sparse_kernel|sparse_plan|sparse_delta|slice|prep|init_lists)'
+SEARCH='regex:vb_(ms_|mh_|dense|compact|fuse|mask|sparse_kernel|sparse_plan|sparse_delta|slice|prep|init_lists|rowsel)'
 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${R}_pytest_gpu.log 2>&1; echo "gpu tests rc=$?"; tail -3 gpurun_out/${R}_pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${R}_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/${R}_smoke.log
 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/${R}_bench_cfg4.json 2> gpurun_out/${R}_bench_cfg4.err; echo "default bench rc=$?"; cut -c1-300 gpurun_out/${R}_bench_cfg4.json
 timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${R}_bench_reference.json 2> gpurun_out/${R}_bench_reference.err; echo "reference rc=$?"; cut -c1-200 gpurun_out/${R}_bench_reference.json
 timeout 900 python bench.py --workload cfg2 --steps 20 --warmup 5 > gpurun_out/${R}_bench_cfg2.json 2> gpurun_out/${R}_bench_cfg2.err; echo "cfg2 rc=$?"
-for W in cfg1 cfg3-b1-s1 cfg3-b1-s50 cfg3-b256-s50 cfg5-shard; do
+for W in cfg1 cfg3-b1-s1 cfg3-b1-s50 cfg3-b256-s1 cfg3-b256-s50 cfg5-shard; do
   timeout 900 python bench.py --workload $W --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${R}_bench_$W.json 2> gpurun_out/${R}_bench_$W.err; echo "$W rc=$?"
 done
 # per-launch device times (bounded: a step is a stream of batches)
@@ -32,6 +32,7 @@ cap() {
 }
 cap k2t cfg4 vb_dense_gemm_tiled_kernel 10 keep
 cap k3m cfg4 vb_ms_score_kernel 9 keep
+cap sel cfg4 vb_rowsel_gather_kernel 4
 cap mask cfg4 vb_mask_kernel 3
 cap compact cfg4 vb_compact_kernel 40
 cap k1 cfg3-b1-s50 vb_dense_scan_kernel 8
@@ -39,4 +40,6 @@ cap k1f cfg1 vb_dense_scan1_kernel 5
 cap k3 cfg5-shard vb_sparse_kernel 6
 cap k2 cfg2 vb_dense_gemm_kernel 8
 rm -f gpurun_out/ncu_l_*.log
+# bounds-checked build (compute-sanitizer is closed on the pool): all-kernel workload + GPU suite with every VB_CHECK armed
+bash tools/gpu_sanitize.sh ${R}
 du -sh gpurun_out

@@ -8,7 +8,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
 PROF = ROOT / "profiles"
 R = sys.argv[1] if len(sys.argv) > 1 else "r02"
-ORDER = ["cfg4", "cfg1", "cfg2", "cfg3-b1-s1", "cfg3-b1-s50", "cfg3-b256-s50", "cfg5-shard"]
+ORDER = ["cfg4", "cfg1", "cfg2", "cfg3-b1-s1", "cfg3-b1-s50", "cfg3-b256-s1", "cfg3-b256-s50", "cfg5-shard"]
 R1 = {"cfg1": (9.1e3, 0.110), "cfg2": (155e3, 0.441), "cfg3-b1-s1": (3.7e3, 0.272), "cfg3-b1-s50": (559, 1.79),
       "cfg3-b256-s50": (25.0e3, 10.2), "cfg4": (16.3e3, 62.8), "cfg5-shard": (18.8e3, 218.0)}
 CEIL = {"cfg2": 0.12, "cfg3-b1-s1": 0.06, "cfg3-b1-s50": 1.2, "cfg3-b256-s50": 1.2, "cfg4": 11.9}
@@ -42,8 +42,9 @@ def main():
         msb = d["ms_per_step"] / c["batches_per_step"]
         p = r["phase_ms_per_batch"]
         r1 = R1.get(name)
+        r1s = (f"{r1[0]:,.0f} | {r1[1]} | {d['value'] / r1[0]:.2f}x") if r1 else "— | — | —"
         out.append(f"| {name} (B={c['queries_per_batch']}, {c['rows_per_gpu']:,} x {c['dim']}) | {d['value']:,.0f} | {d['e2e']['value']:,.0f} | {msb:.3f} | "
-                   f"{r1[0]:,.0f} | {r1[1]} | {d['value'] / r1[0]:.2f}x | {CEIL.get(name, '—')} | {p['mask']:.3f} | {p['dense']:.3f} | {p['sparse']:.3f} | {p['select']:.3f} | {p['fuse']:.3f} |")
+                   f"{r1s} | {CEIL.get(name, '—')} | {p['mask']:.3f} | {p['dense']:.3f} | {p['sparse']:.3f} | {p['select']:.3f} | {p['fuse']:.3f} |")
     out += ["", "## Headline configuration (bench.py default: cfg4 weak form, N = 1)", ""]
     d = lines.get("cfg4")
     ref = load("reference")
@@ -52,10 +53,15 @@ def main():
         out += [f"* value **{d['value']:,.0f} q/s** ({d['ms_per_step']:.2f} ms per 1024-query batch), e2e **{d['e2e']['value']:,.0f} q/s**, "
                 f"{d['gpu_launches']} launches in {d['steps']} steps; clocks {d['clocks']['sm_mhz']} MHz, reasons {d['clocks']['reasons']}, {d['clocks']['samples']} samples over {d['clocks'].get('timed_region_s', 0):.2f} s.",
                 f"* dominant kernel `{r['kernel']}` ({r['launch']}): **{r['achieved']:.0f} {r['unit']} = {100 * r['frac']:.1f} % of the measured {r['bound']} peak** ({r['peak']} {r['unit']}); "
-                f"whole step: {r['step_tflops']:.0f} TFLOP/s = {100 * r['step_tflops'] / 1648.7:.1f} % of the bf16 burst peak, {100 * r['step_tflops'] / 1390.6:.1f} % of the sustained one (north_star asks >= 60 % at batch 1024).",
+                f"whole step: {r['step_tflops']:.0f} TFLOP/s executed = {100 * r['step_tflops'] / 1648.7:.1f} % of the bf16 burst peak; counted as an all-rows GEMM "
+                f"(2*B*rows*d_pad over the same time, rows the filter drops included) {r.get('step_tflops_nominal', r['step_tflops']):.0f} TFLOP/s = "
+                f"{100 * r.get('step_tflops_nominal', r['step_tflops']) / 1648.7:.1f} % of the burst peak, {100 * r.get('step_tflops_nominal', r['step_tflops']) / 1390.6:.1f} % of the sustained one "
+                "(north_star asks >= 60 % at batch 1024).",
                 f"* ingest: {d['ingest']['rows']:,} rows in {d['ingest']['upsert_s']:.2f} s + index build {d['ingest']['index_build_s']:.2f} s = {d['ingest']['rows_per_s']:,.0f} rows/s (device-resident blocks).",
                 f"* timeline (two streams): span {d['timeline']['span_ms']:.2f} ms, dense chain busy {d['timeline']['dense_chain_busy_ms']:.2f} ms, sparse chain busy {d['timeline']['sparse_chain_busy_ms']:.2f} ms — "
-                "the chains run side by side but the step is not shorter than their serial sum: the tensor kernel sits at the 1 kW power cap (`sw_power_cap`), and work added next to it lowers its clock."]
+                "the chains run side by side but the step is barely shorter than their serial sum: K3M, the row-selection copy and the tensor kernel each fill the SMs "
+                "(thread slots / registers / shared memory) and the board sits at its 1 kW power cap (`sw_power_cap`); `profiles/%s_timeline_cfg4.txt` lists every region, "
+                "and neither a different order (large GEMMs after the sparse stages) nor fewer CTAs per SM for K3M / the copy changed the 15 ms (`profiles/%s_ab_schedule.txt`)." % (R, R)]
         if d.get("cpu_baseline"):
             out.append(f"* cpu_baseline (in-run): {d['cpu_baseline']['value']:.3f} q/s on {d['cpu_baseline']['cores']} cores — {d['cpu_baseline']['sample']}")
         if ref:
@@ -73,6 +79,21 @@ def main():
             continue
         one, many = a["threads_1"], a.get("threads_16", {})
         out.append(f"| {name} | {one['queries_per_s']:.0f} | {one['p50_ms']:.2f} | {one['p99_ms']:.2f} | {many.get('queries_per_s', 0):.0f} | {many.get('p50_ms', 0):.2f} | {many.get('p99_ms', 0):.2f} | {many.get('mean_coalesced_batch') or 0:.1f} |")
+    scale = []
+    for f in sorted(PROF.glob(f"{R}_scale_*.json")):
+        try:
+            dd = json.loads([l for l in f.read_text().splitlines() if l.startswith("{")][-1])
+        except Exception:
+            continue
+        scale.append((f.name, dd))
+    if scale:
+        out += ["", "## Row-sharded runs (torchrun, one process per GPU, NCCL all-gather of the candidates)", "",
+                "| file | workload | GPUs | rows total | value q/s | ms per step | e2e q/s | clocks |", "|---|---|---|---|---|---|---|---|"]
+        for name, dd in scale:
+            out.append(f"| {name} | {dd['config']['workload'].split(':')[0]} | {dd['n_gpus']} | {dd['config']['rows_total']:,} | {dd['value']:,.0f} | {dd['ms_per_step']:.2f} | "
+                       f"{dd['e2e']['value']:,.0f} | {dd['clocks'].get('sm_mhz')} MHz {dd['clocks'].get('reasons')} |")
+        out += ["", "The corpus grows with the GPU count (12.5M / 6.25M rows per GPU) while the batch belongs to the whole job: flat queries/s is ideal weak scaling "
+                "(`scaling_detail` in the line); the lines were measured before the row selection went in unless their name says otherwise."]
     c2 = lines.get("cfg2")
     if c2 and c2.get("parity_spot_check"):
         out += ["", f"cfg2 parity spot check against the C oracle inside the bench run: {c2['parity_spot_check']}; cpu_baseline {c2['cpu_baseline']['value']:.1f} q/s on {c2['cpu_baseline']['cores']} cores."]

@@ -26,7 +26,8 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
 CAPS = {"k2t": ("cfg4", "vb_dense_gemm_tiled_kernel", 12_500_000, 1024), "k3m": ("cfg4", "vb_ms_score_kernel", 12_500_000, 1024),
         "mask": ("cfg4", "vb_mask_kernel", 12_500_000, 1024), "compact": ("cfg4", "vb_compact_kernel", 12_500_000, 1024),
         "k1": ("cfg3-b1-s50", "vb_dense_scan_kernel", 10_000_000, 1), "k1f": ("cfg1", "vb_dense_scan1_kernel", 100_000, 1),
-        "k3": ("cfg5-shard", "vb_sparse_kernel", 6_250_000, 4096), "k2": ("cfg2", "vb_dense_gemm_kernel", 1_000_000, 64)}
+        "k3": ("cfg5-shard", "vb_sparse_kernel", 6_250_000, 4096), "k2": ("cfg2", "vb_dense_gemm_kernel", 1_000_000, 64),
+        "sel": ("cfg4", "vb_rowsel_gather_kernel", 12_500_000, 1024)}
 
 
 def raw(rep):
@@ -97,6 +98,8 @@ def main():
             out.append(f"  {k[:50]:50s} {len(v):8d} {sum(v):10.1f} {sum(v) / len(v):9.2f} {100 * sum(v) / total:6.1f}%")
         seq = [(r["Kernel Name"].split("(")[0][:48], float(r["Metric Value"]) / 1e3, r.get("Grid Size", "")) for r in rows]
         starts = [i for i, x in enumerate(seq) if x[0].startswith("vb_init_lists")]
+        if len(starts) < 2:                                 # (the list set-up is folded into the query prep on most paths)
+            starts = [i for i, x in enumerate(seq) if x[0].startswith("vb_prep_query")]
         if len(starts) >= 2:
             out.append("# one batch, launch by launch (us, grid):")
             out += [f"  {n:48s} {t:10.2f} {g}" for n, t, g in seq[starts[-2]:starts[-1]]]
@@ -104,7 +107,13 @@ def main():
     for f in sorted(OUT.glob(f"{R}_bench_*.json")) + [OUT / f"{R}_pytest_gpu.log", OUT / f"{R}_smoke.log"]:
         if f.exists() and f.stat().st_size:
             shutil.copy(f, PROF / f.name)
-    for tool in ("plain", "memcheck", "racecheck", "synccheck"):
+    f = OUT / f"{R}_pytest_bounds.log"
+    if f.exists():
+        (PROF / f"{R}_pytest_bounds.txt").write_text("GPU suite on the bounds-checked build (libvoitta_b200_dbg.so, every VB_CHECK a device-side assert):\n" + "\n".join(f.read_text().splitlines()[-3:]) + "\n")
+    f = OUT / f"{R}_sanitize_version.log"
+    if f.exists():
+        (PROF / f"{R}_sanitize_version.txt").write_text(f.read_text()[:2000])
+    for tool in ("plain", "bounds", "memcheck", "racecheck", "synccheck"):
         f = OUT / f"{R}_sanitize_{tool}.log"
         if f.exists():
             keep = [l for l in f.read_text().splitlines() if any(k in l for k in ("SUMMARY", "ok ", "done", "Error", "hazard", "ERROR", "COMPUTE-SANITIZER"))]

@@ -137,7 +137,7 @@ struct vb_index {
     cudaStream_t stream = nullptr, own_stream = nullptr, aux_stream = nullptr, sel_stream = nullptr;
     cudaEvent_t ev_sel_fork = nullptr, ev_sel[8] = {};
     cudaEvent_t ev0s[2] = {nullptr, nullptr}, ev1s[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_sp_done = nullptr;
     int cur = 0;                               // current slot: two batches can be in flight (pipelined callers)
     std::recursive_mutex mu;               // one-call entry points hold it for the whole call; staged calls re-enter
     int sm_count = 148;
@@ -190,6 +190,8 @@ struct vb_index {
     int64_t opt_ms_stage_ratio = 0;        // K3M: growth of the posting stages (0 = auto: 32, up to 1024 for tiny batches)
     int64_t opt_delta_max = 0;             // rows the delta may hold before vb_upsert merges it into the index (0 = auto)
     int64_t opt_dense_compact_min_rows = 1 << 18;   // ... on segments of at least this many rows (tests lower it)
+    int64_t opt_sel_ctas = 4;              // row selection: CTAs per SM of the copy kernel (1..8 measured at cfg4: 15.1-15.4 ms per batch, no trend)
+    int64_t opt_dense_wait_sparse = 0;     // 1: the large tensor-core segments start after the K3M stages (no co-running with the sparse chain)
     int64_t opt_dense_compact = -1;        // K2 / K2T: walk a compacted copy of the passing rows when a batch-wide filter passes at most this % of a
                                            // segment (0 = never, -1 = auto: where the copy costs less than the passes over the dropped rows)
     int64_t opt_ms_ctas = 0;               // K3M: resident CTAs per SM of the persistent score kernel (0 = auto, see ms_launch)
@@ -397,6 +399,7 @@ extern "C" void vb_destroy(vb_index* h) {
     if (h->ev_q) cudaEventDestroy(h->ev_q);
     cudaEventDestroy(h->ev_fork);
     cudaEventDestroy(h->ev_join);
+    if (h->ev_sp_done) cudaEventDestroy(h->ev_sp_done);
     cudaStreamDestroy(h->aux_stream);
     if (h->sel_stream) { cudaStreamDestroy(h->sel_stream); cudaEventDestroy(h->ev_sel_fork); for (auto e : h->ev_sel) cudaEventDestroy(e); }
     cudaStreamDestroy(h->own_stream);
@@ -425,6 +428,8 @@ extern "C" int vb_set_option(vb_index* h, const char* key, int64_t value) {
     else if (k == "ms_stage_ratio") h->opt_ms_stage_ratio = value; // K3M: growth of the posting stages
     else if (k == "delta_max") h->opt_delta_max = value;           // delta rows that trigger a merge (0 = max(16384, base/32))
     else if (k == "dense_compact_min_rows") h->opt_dense_compact_min_rows = value;
+    else if (k == "sel_ctas") h->opt_sel_ctas = value;
+    else if (k == "dense_wait_sparse") h->opt_dense_wait_sparse = value;
     else if (k == "dense_compact") h->opt_dense_compact = value;   // row selection threshold in % of the segment's rows (0 = off, -1 = auto)
     else if (k == "ms_ctas") h->opt_ms_ctas = value;               // K3M: CTAs per SM of the score kernel (0 = auto)
     else if (k == "k2t_stages") g_k2t_stages = (int)value;         // K2T: TMA ring depth (0 = default 4); process-wide
@@ -1524,7 +1529,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         CKK("vb_rowsel_count_kernel");
         vb_rowsel_scatter_kernel<<<z.n_blocks, VB_SEL_THREADS, 0, st>>>(sa);
         CKK("vb_rowsel_scatter_kernel");
-        vb_rowsel_gather_kernel<<<h->sm_count * 8, 256, 0, st>>>(h->rows.as<uint4>(), h->inv_norm.as<float>(), sa.ids, sa.sel,
+        vb_rowsel_gather_kernel<<<h->sm_count * (int)std::max<int64_t>(1, std::min<int64_t>(8, h->opt_sel_ctas)), 256, 0, st>>>(h->rows.as<uint4>(), h->inv_norm.as<float>(), sa.ids, sa.sel,
                                                                 h->sel_rows.as<uint4>() + z.row_off * (h->d_pad / 8), h->sel_inv.as<float>() + z.row_off,
                                                                 (uint32_t)h->d_pad / 8u);
         CKK("vb_rowsel_gather_kernel");
@@ -1545,6 +1550,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
                 CK(cudaEventRecord(h->ev_sel[selseg[si].ev], h->sel_stream));
             }
     }
+    bool sp_done_recorded = false;                                // dense_wait_sparse: an event after the K3M stages exists
     auto dense_single_pass = [&]() -> int {
         const int pi = prof_begin(h, PH_DENSE | PH_BIG, sd);
         VbScan1Args a{};
@@ -1599,6 +1605,7 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
                         h->sel_ran[h->cur] = true;
                     }
                 }
+        if (sp_done_recorded && path == 2 && r1 - r0 >= (1u << 20)) CK(cudaStreamWaitEvent(sd, h->ev_sp_done, 0));
         const int pi = prof_begin(h, PH_DENSE | (big ? PH_BIG : 0), sd);
         if (path == 2) {
             VbGemmLaunch g{};
@@ -1813,7 +1820,14 @@ static int run_branches(vb_index* h, const Batch& b, bool safe, int phase = 0) {
         if (big && !k1f) h->stats.last_big_rows = bounds[s + 1] - bounds[s];
         TRY(dense_segment(bounds[s], bounds[s + 1], direct, big));
         TRY(sparse_segment(bounds[s], bounds[s + 1], direct, big));
-        if (s == 0 && ms_staged) TRY(ms_stages(true, phase != 1));
+        if (s == 0 && ms_staged) {
+            TRY(ms_stages(true, phase != 1));
+            if (two_streams && h->opt_dense_wait_sparse && phase != 1) {
+                if (!h->ev_sp_done) CK(cudaEventCreateWithFlags(&h->ev_sp_done, cudaEventDisableTiming));
+                CK(cudaEventRecord(h->ev_sp_done, ss));
+                sp_done_recorded = true;
+            }
+        }
     }
     if (phase == 2 && ms_staged) TRY(ms_stages(false, true));
     if (do_delta && phase != 1) {
