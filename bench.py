@@ -353,6 +353,12 @@ def run_api(ix, cfg, batches, flt, n_threads, n_calls, device, torch):
         svc.search(qe, limit=20, sparse_query=sq, sparse_weight=0.1, **kw)
     res = {}
     for nt in sorted({1, n_threads}):
+        if nt > 1:                                            # untimed round first: the coalesced batch shapes (B = 2..nt) set up their
+            th = [threading.Thread(target=worker, args=(k,)) for k in range(nt)]   # buffers / tensor maps / kernel variants once
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
         lat.clear()
         th = [threading.Thread(target=worker, args=(k,)) for k in range(nt)]
         t0 = time.perf_counter()

@@ -54,11 +54,13 @@ check(3, n0, "B=3 K2 resident", dense_path=2)
 check(3, n0, "B=3 K3 only", sparse_ms=0)
 check(3, n0, "B=3 safe mode", safe_mode=1)
 check(300, n0, "B=300 K2T")
-ix.set_option("dense_compact_min_rows", 1024)         # the row selection normally needs 262144-row segments
+ix.set_option("dense_compact_min_rows", 1024)         # the row selection normally needs 262144-row segments ...
+ix.set_option("dense_compact", 100)                   # ... and a filter selective enough to pay for the copy (here: always)
 check(300, n0, "B=300 K2T over the compacted copy of the passing rows (row selection)")
 st = ix.stats()
 assert st["last_sel_rows"] > 0 and st["last_sel_used"] == 1, st
 ix.set_option("dense_compact_min_rows", 1 << 18)
+ix.set_option("dense_compact", -1)
 ix.set_option("ms_max_terms", 4)                      # queries of more than 4 terms become "long"
 check(6, n0, "B=6 long queries on K3")
 ix.set_option("sparse_mh", 1)                         # ... and on K3H (off by default)

@@ -20,10 +20,11 @@ def nvcc_path() -> str:
     return p
 
 
-def needs_build() -> bool:
-    if not LIB.exists():
+def needs_build(lib: Path | None = None) -> bool:
+    lib = lib or LIB
+    if not lib.exists():
         return True
-    t = LIB.stat().st_mtime
+    t = lib.stat().st_mtime
     srcs = list((HERE / "csrc").glob("*")) + [HERE.parent / "include" / "voitta_b200.h"]
     return any(s.stat().st_mtime > t for s in srcs)
 
@@ -50,18 +51,25 @@ def build_variant(name: str, *defines: str) -> Path:
     return out
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not needs_build():
-        return LIB
-    cmd = [nvcc_path(), *FLAGS, "-o", str(LIB), str(SRC)]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{r.stdout}\n{r.stderr}")
-    if verbose:
-        print(r.stderr)
+def build(force: bool = False, verbose: bool = False, debug: bool = True) -> Path:
+    """Release library and (debug=True) the bounds-checked one, each only when older than its sources; the two nvcc
+    runs go side by side.  A stale debug library once made tools/gpu_sanitize.sh test yesterday's kernels."""
+    jobs = []
+    if force or needs_build(LIB):
+        cmd = [nvcc_path(), *FLAGS, "-o", str(LIB), str(SRC)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd))
+        jobs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    if debug and (force or needs_build(LIB_DEBUG)):
+        jobs.append(subprocess.Popen([nvcc_path(), *FLAGS, "-DVB_DEBUG_BOUNDS", "-o", str(LIB_DEBUG), str(SRC)],
+                                     stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    for j in jobs:
+        out, err = j.communicate()
+        if j.returncode != 0:
+            raise RuntimeError(f"nvcc failed:\n{out}\n{err}")
+        if verbose:
+            print(err)
     return LIB
 
 
