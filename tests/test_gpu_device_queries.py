@@ -120,3 +120,34 @@ def test_wrong_device_pointer_is_refused(world):
     t.device = torch.device("cuda:0")
     with pytest.raises(eng.B200Error, match="not a device pointer"):
         ix.search_batch(t, None, limit=5, fusion="dense")
+
+
+def test_vector_store_service_accepts_cuda_tensors(monkeypatch):
+    """The drop-in class: `search(tensor)` and `search_batch(tensor)` return what the list[float] calls return
+    (the reference's embed_query ends in .tolist(), embedding.py:76-86; the tensor form skips that hop)."""
+    import torch
+    from golden import make_golden as G
+    from voitta_rag_b200 import vector_store as VS
+    name = "gpu_device_queries"
+    corpus, queries = G.build_inputs()
+    monkeypatch.setenv("QDRANT_COLLECTION", name)
+    monkeypatch.setenv("EMBEDDING_DIMENSION", str(corpus["dense"].shape[1]))
+    VS._drop_collection(name)
+    store = VS.VectorStoreService()
+    n = len(corpus["texts"])
+    chunks = [(corpus["texts"][r], corpus["dense"][r].astype(float).tolist(), VS.ChunkMetadata(**corpus["metas"][r])) for r in range(n)]
+    store.store_chunks(chunks, [corpus["sparse"][r] for r in range(n)])
+    folders = sorted({m["folder_path"] for m in corpus["metas"]})
+    for qv, sq in queries[:6]:
+        for kw in ({}, {"include_folders": folders[:3]}, {"exclude_folders": folders[:1], "date_start": 1500000000, "date_field": "modified"}):
+            want = store.search(qv.astype(float).tolist(), limit=7, sparse_query=sq, **kw)
+            got = store.search(torch.from_numpy(qv.astype(np.float32)).cuda(), limit=7, sparse_query=sq, **kw)
+            assert [(c.id, c.score) for c in got] == [(c.id, c.score) for c in want]
+    Q = np.stack([q for q, _ in queries[:6]]).astype(np.float32)
+    SQ = [s for _, s in queries[:6]]
+    want = store.search_batch(Q, limit=5, sparse_queries=SQ, include_folders=folders[:4])
+    got = store.search_batch(torch.from_numpy(Q).cuda(), limit=5, sparse_queries=SQ, include_folders=folders[:4])
+    assert [[(c.id, c.score) for c in r] for r in got] == [[(c.id, c.score) for c in r] for r in want]
+    with pytest.raises(ValueError, match="dimension"):
+        store.search(torch.zeros(3, device="cuda"), limit=3)
+    VS._drop_collection(name)
