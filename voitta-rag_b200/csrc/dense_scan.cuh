@@ -419,6 +419,38 @@ vb_dense_scan1_kernel(const VbScan1Args a)
     uint64_t* in = a.cand + (size_t)list * a.cap;
     const uint32_t total = min(*reinterpret_cast<volatile uint32_t*>(a.cnt + (size_t)list * VB_SUB), a.cap);
     uint32_t kept = 0;
+    // Every CTA has published by now: gtau is the best k'-th score any CTA holds, and that CTA's k' keys at or above it
+    // were all appended (a CTA appends what reaches the threshold it sees, which is never above the final one).  Keys
+    // below it cannot be in the global top-k': keep only the others — a few dozen instead of a few hundred to sort.
+    {
+        const uint32_t o_fin = *reinterpret_cast<volatile uint32_t*>(a.gtau + list);
+        if (threadIdx.x == 0) s_cnt = 0u;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < total; i += VB_K1F_THREADS) {
+            const uint64_t key = __ldcg(in + i);
+            if ((uint32_t)(key >> 32) >= o_fin) {
+                const uint32_t slot = atomicAdd(&s_cnt, 1u);
+                if (slot < VB_K1F_CAP) s_keys[slot] = key;
+            }
+        }
+        __syncthreads();
+        const uint32_t c = s_cnt;
+        if (c <= VB_K1F_CAP) {
+            uint32_t P = 2;
+            while (P < c) P <<= 1;
+            for (uint32_t i = c + threadIdx.x; i < P; i += VB_K1F_THREADS) s_keys[i] = 0ull;
+            vb_k1f_sort(s_keys, P);
+            kept = c < a.k ? c : a.k;
+            for (uint32_t i = threadIdx.x; i < kept; i += VB_K1F_THREADS) in[i] = s_keys[i];
+            if (threadIdx.x == 0) {
+                a.cnt[(size_t)list * VB_SUB] = kept;
+                a.tau[list] = fmaxf(a.tau[list], kept >= a.k ? vb_key_score(s_keys[a.k - 1u]) : -INFINITY);
+                a.done[list] = 0u;
+            }
+            return;
+        }
+        __syncthreads();                                              // more survivors than slots (no threshold yet): the chunked merge below
+    }
     for (uint32_t pos = 0; pos < total;) {                            // 2048 slots: (kept so far) + the next stretch of keys
         const uint32_t take = min(VB_K1F_CAP - kept, total - pos);
         for (uint32_t i = threadIdx.x; i < take; i += VB_K1F_THREADS) s_keys[kept + i] = __ldcg(in + pos + i);
