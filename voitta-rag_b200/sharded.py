@@ -141,8 +141,8 @@ class ShardedIndex:
     def search_batch(self, queries, sparse=None, filters=None, filter_of=None, limit=10, kprime=None,
                      fusion="weighted", sparse_weight=0.1, branches=False):
         """Same call shape and result as engine.Index.search_batch; identical on every rank."""
-        q = np.ascontiguousarray(queries, dtype=np.float32)
-        B = q.shape[0]
+        q = queries if getattr(queries, "is_cuda", False) else np.ascontiguousarray(queries, dtype=np.float32)
+        B = int(q.shape[0])
         any_sparse = sparse is not None and any(s is not None and len(s[0]) for s in sparse)
         if kprime is None:
             kprime = limit * 3 if (any_sparse and fusion != "dense") else limit
@@ -163,7 +163,8 @@ class ShardedIndex:
     def pack(self, queries, sparse=None, filters=None, filter_of=None, limit=10, kprime=None,
              fusion="weighted", sparse_weight=0.1, branches=False):
         """Host buffers of one batch with the GLOBAL idf already applied (reusable across calls)."""
-        q = np.ascontiguousarray(queries, dtype=np.float32)
+        # (a torch CUDA tensor on this rank's device goes through as it is: vb_stage_dev, no H2D copy of the vectors)
+        q = queries if getattr(queries, "is_cuda", False) else np.ascontiguousarray(queries, dtype=np.float32)
         any_sparse = sparse is not None and any(s is not None and len(s[0]) for s in sparse)
         if kprime is None:
             kprime = limit * 3 if (any_sparse and fusion != "dense") else limit
