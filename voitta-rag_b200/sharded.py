@@ -92,24 +92,27 @@ class ShardedIndex:
         self.finalize(t, np.asarray(df, dtype=np.int64), n_live)
 
     def idf_weights(self, sparse):
-        """qdrant's IDF modifier with GLOBAL statistics (local_collection.py _rescore_idf)."""
+        """qdrant's IDF modifier with GLOBAL statistics (local_collection.py _rescore_idf).  One flattening pass, one
+        factor per DISTINCT term of the batch (cached; math.log as in the single-shard path, so the products are the
+        same doubles), one vectorised multiply.  Returns engine.FlatSparse."""
         if sparse is None:
             return None
-        out = []
+        from . import engine as _engine
+        flat = _engine.flatten_sparse(sparse, len(sparse))
+        nnz = int(flat.indptr[-1])
+        if nnz == 0:
+            return flat
         cache = self._idf_cache          # term -> ln((N - df + 0.5) / (df + 0.5) + 1), emptied by finalize()
-        for s in sparse:
-            if s is None or len(s[0]) == 0:
-                out.append(None)
-                continue
-            terms = s[0].tolist() if isinstance(s[0], np.ndarray) else list(s[0])
-            w = []
-            for t, v in zip(terms, s[1]):
-                f = cache.get(t)
-                if f is None:
-                    f = cache[t] = self._idf_factor(t)
-                w.append(float(v) * f)
-            out.append((terms, w))
-        return out
+        uniq, inv = np.unique(flat.terms[:nnz], return_inverse=True)
+        f = np.empty(len(uniq), np.float64)
+        for j, t in enumerate(uniq.tolist()):
+            v = cache.get(t)
+            if v is None:
+                v = cache[t] = self._idf_factor(t)
+            f[j] = v
+        w = np.zeros_like(flat.weights)
+        w[:nnz] = flat.weights[:nnz] * f[inv]
+        return _engine.FlatSparse(flat.indptr, flat.terms, w)
 
     def _idf_factor(self, term: int) -> float:
         N, d = self.n_live_g, 0.0
