@@ -93,7 +93,7 @@ def main():
             out.append(f"| {name} | {dd['config']['workload'].split(':')[0]} | {dd['n_gpus']} | {dd['config']['rows_total']:,} | {dd['value']:,.0f} | {dd['ms_per_step']:.2f} | "
                        f"{dd['e2e']['value']:,.0f} | {dd['clocks'].get('sm_mhz')} MHz {dd['clocks'].get('reasons')} |")
         out += ["", "The corpus grows with the GPU count (12.5M / 6.25M rows per GPU) while the batch belongs to the whole job: flat queries/s is ideal weak scaling "
-                "(`scaling_detail` in the line); the lines were measured before the row selection went in unless their name says otherwise."]
+                "(`scaling_detail` in the line); files named `*_head.json` were measured with the row selection in (the 8-GPU `_head` lines still with the per-term Python IDF loop in the sharded pack: their e2e was host-bound; the 2-GPU `_head` line has the vectorised pack)."]
     c2 = lines.get("cfg2")
     if c2 and c2.get("parity_spot_check"):
         out += ["", f"cfg2 parity spot check against the C oracle inside the bench run: {c2['parity_spot_check']}; cpu_baseline {c2['cpu_baseline']['value']:.1f} q/s on {c2['cpu_baseline']['cores']} cores."]
