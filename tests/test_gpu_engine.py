@@ -1021,6 +1021,15 @@ def test_k2t_row_selection_equals_in_place_scoring_and_oracle(B):
         for j, i in enumerate(sub):
             wd = [(int(want["dense_rows"][j, t]), float(want["dense_scores"][j, t])) for t in range(want["dense_counts"][j])]
             assert_same_ranking(res[70].branch(i, "dense"), wd, rel_tol=tol, abs_tol=tol, what=f"row selection B={B} {name} q{i}")
+    # every query on the SECOND filter of the batch: its words start at mask + 1 * mask_words, and 61003 rows are 1907
+    # words — not 16-byte aligned (the selection kernels must not assume it)
+    ix.set_option("dense_compact", 70)
+    two = ix.search_batch(Q, None, [engine.Filter(*cases["all"]), engine.Filter(*cases["half"])], np.ones(B, np.int32), limit=limit,
+                          fusion="dense", branches=True)
+    assert ix.stats()["last_sel_used"] == 1
+    one = ix.search_batch(Q, None, [engine.Filter(*cases["half"])], fo, limit=limit, fusion="dense", branches=True)
+    for i in range(B):
+        assert two.branch(i, "dense") == one.branch(i, "dense"), f"second filter of two, q{i}"
     ix.close()
 
 

@@ -32,11 +32,13 @@ struct VbRowSelArgs {
 __device__ __forceinline__ uint4 vb_rowsel_words(const VbRowSelArgs& a, uint32_t w0) {
     uint4 w = make_uint4(0u, 0u, 0u, 0u);
     if (w0 < a.word_end) {
-        if (w0 + 4u <= a.word_end) w = __ldg(reinterpret_cast<const uint4*>(a.mask + w0));
+        // (the filter's words start at mask + f * mask_words: 16-byte aligned only for f = 0 or a word count divisible by 4)
+        if (w0 + 4u <= a.word_end && (reinterpret_cast<uintptr_t>(a.mask + w0) & 15u) == 0u) w = __ldg(reinterpret_cast<const uint4*>(a.mask + w0));
         else {
             w.x = a.mask[w0];
             if (w0 + 1u < a.word_end) w.y = a.mask[w0 + 1u];
             if (w0 + 2u < a.word_end) w.z = a.mask[w0 + 2u];
+            if (w0 + 3u < a.word_end) w.w = a.mask[w0 + 3u];
         }
         uint32_t* p = &w.x;
 #pragma unroll
