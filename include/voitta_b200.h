@@ -209,7 +209,10 @@ int vb_search_dev(vb_index* h, const vb_query_batch* q, const float* dense_dev, 
 
 /* Tuning knobs (tests exercise every path with them): key = "dense_path" (0 auto, 1 K1, 2 K2),
  * "seg_first", "seg_ratio", "safe_mode", "profile" (per-phase CUDA-event times in vb_stats),
- * "stream" (a cudaStream_t to run on instead of the index's own stream; 0 restores it). */
+ * "stream" (a cudaStream_t to run on instead of the index's own stream; 0 restores it),
+ * "dense_compact" (row selection for the tensor-core kernels under a batch-wide filter: -1 auto, 0 off,
+ * 1..100 = walk the compacted copy when at most that % of a segment passes), "dense_compact_min_rows".
+ * The full list with defaults is vb_set_option in csrc/vb_api.cu; unknown keys are an error. */
 int vb_set_option(vb_index* h, const char* key, int64_t value);
 
 int vb_get_stats(vb_index* h, vb_stats* out);

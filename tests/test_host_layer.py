@@ -224,3 +224,56 @@ def test_scope_key_caches_the_folded_bitset_until_a_new_scope_appears(store):
     assert f4.scope_bits is not f3.scope_bits
     hits = store.search([1.0] * GOLD["dim"], limit=50, include_folders=folders[:3] + ["brand/new"], scope_key=("u", "p", 2))
     assert any(c.metadata.folder_path == "brand/new" for c in hits)
+
+
+def test_flat_sparse_batches_and_global_idf_weights_are_bit_equal_to_the_per_term_form():
+    """engine.flatten_sparse / FlatSparse (one pass over a batch of the reference's (indices, values) pairs) and the
+    sharded layer's vectorised IDF weighting: same CSR, same doubles as the per-term formula
+    ln((N - df + 0.5) / (df + 0.5) + 1) * value (qdrant local mode's IDF modifier, global statistics)."""
+    import math
+    import numpy as np
+    from voitta_rag_b200 import engine
+    from voitta_rag_b200.sharded import ShardedIndex
+    rng = np.random.RandomState(3)
+    vocab = np.unique(rng.randint(1, 2**32 - 1, size=500, dtype=np.int64))
+    sparse = []
+    for i in range(97):
+        k = int(rng.randint(0, 9))
+        if i % 11 == 0:
+            sparse.append(None)
+        elif i % 5 == 0:                                      # numpy inputs and Python lists mix freely
+            sparse.append((rng.choice(vocab, size=k, replace=False), rng.rand(k)))
+        else:
+            sparse.append(([int(t) for t in rng.choice(vocab, size=k, replace=False)], [float(v) for v in rng.rand(k)]))
+    flat = engine.flatten_sparse(sparse, len(sparse))
+    assert len(flat) == len(sparse) and flat.indptr[0] == 0
+    for i, s in enumerate(sparse):
+        t, w = flat[i]
+        assert list(t) == ([] if s is None else [int(x) for x in s[0]])
+        assert list(w) == ([] if s is None else [float(x) for x in s[1]])
+    assert engine.flatten_sparse(flat, len(sparse)) is flat
+    with pytest.raises(ValueError):
+        engine.flatten_sparse(sparse, len(sparse) + 1)
+    with pytest.raises(ValueError):
+        engine.flatten_sparse([([1, 2], [1.0])], 1)
+    with pytest.raises(ValueError):
+        engine.flatten_sparse([([-1], [1.0])], 1)
+    sh = ShardedIndex.__new__(ShardedIndex)                   # only the IDF state: no process group, no device
+    sh.terms_g = vocab[::2].astype(np.uint32)                 # half of the vocabulary is known to the shards
+    sh.df_g = rng.randint(1, 5000, size=len(sh.terms_g)).astype(np.int64)
+    sh.n_live_g = 123_457
+    sh._idf_cache = {}
+    got = sh.idf_weights(sparse)
+    df_of = dict(zip(sh.terms_g.tolist(), sh.df_g.tolist()))
+    for i, s in enumerate(sparse):
+        t, w = got[i]
+        if s is None:
+            assert len(t) == 0
+            continue
+        want = [float(v) * math.log((sh.n_live_g - df_of.get(int(x), 0) + 0.5) / (df_of.get(int(x), 0) + 0.5) + 1.0) for x, v in zip(s[0], s[1])]
+        assert list(w) == want, f"query {i}"
+    # the packed batch built from the flat form equals the one built from the pairs
+    q = rng.randn(len(sparse), 8).astype(np.float32)
+    a = engine._Packed(8, q, sparse, None, None, 5, 15, 1, 0.1, True)
+    b = engine._Packed(8, q, flat, None, None, 5, 15, 1, 0.1, True)
+    assert (a.indptr == b.indptr).all() and (a.terms == b.terms).all() and (a.weights == b.weights).all()
