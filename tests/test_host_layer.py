@@ -277,3 +277,38 @@ def test_flat_sparse_batches_and_global_idf_weights_are_bit_equal_to_the_per_ter
     a = engine._Packed(8, q, sparse, None, None, 5, 15, 1, 0.1, True)
     b = engine._Packed(8, q, flat, None, None, 5, 15, 1, 0.1, True)
     assert (a.indptr == b.indptr).all() and (a.terms == b.terms).all() and (a.weights == b.weights).all()
+
+
+def test_qdrant_scroll_facade_serves_the_admin_scan(store):
+    """scripts/sync_qdrant_stats.py:29-81 scrolls every point (limit 1000, four payload keys, no vectors) and counts
+    chunks per file.  The same loop over ``store.qdrant_facade()`` must see every live chunk exactly once, with the
+    payload keys it asks for, across page boundaries and deletions."""
+    corpus, queries = G.build_inputs()
+    n = len(corpus["texts"])
+    chunks = [(corpus["texts"][r], corpus["dense"][r].astype(float).tolist(), VS.ChunkMetadata(**corpus["metas"][r])) for r in range(n)]
+    ids = store.store_chunks(chunks, [corpus["sparse"][r] for r in range(n)])
+    gone = corpus["metas"][3]["file_path"]
+    store.delete_by_file(gone)
+    client = store.qdrant_facade()
+    total = client.get_collection(store.collection_name).points_count
+    assert total == sum(store.get_file_chunk_counts().values()) and 0 < total < n
+    for page in (7, 1000):
+        seen, stats, offset, pages = [], {}, None, 0
+        while True:
+            results, offset = client.scroll(collection_name=store.collection_name, limit=page, offset=offset,
+                                            with_payload=["file_path", "folder_path", "index_folder", "indexed_at"], with_vectors=False)
+            pages += 1
+            for pt in results:
+                assert set(pt.payload) <= {"file_path", "folder_path", "index_folder", "indexed_at"} and "file_path" in pt.payload
+                seen.append(pt.id)
+                st = stats.setdefault(pt.payload["file_path"], {"chunk_count": 0, "folder_path": pt.payload.get("folder_path", "")})
+                st["chunk_count"] += 1
+            if offset is None:
+                break
+        assert len(seen) == len(set(seen)) == total
+        assert gone not in stats
+        assert {fp: s_["chunk_count"] for fp, s_ in stats.items()} == store.get_file_chunk_counts()
+        assert set(seen) <= set(ids)
+        assert pages >= (total + page - 1) // page
+    with pytest.raises(ValueError):
+        client.scroll(collection_name="another_collection", limit=5)

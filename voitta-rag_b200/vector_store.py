@@ -774,6 +774,11 @@ class VectorStoreService:
         """Reference :532-558: anything with .id / .payload / .score (a qdrant ScoredPoint there)."""
         return _payload_to_chunk(result.id, result.payload, getattr(result, "score", None))
 
+    def qdrant_facade(self) -> "QdrantScrollFacade":
+        """Additive: a QdrantClient-shaped object for scripts/sync_qdrant_stats.py (get_collection + scroll)."""
+        self.client
+        return QdrantScrollFacade(self)
+
     def coalescing_stats(self) -> dict:
         """Device batches formed out of concurrent single-query searches so far."""
         c = self._coll.coalescer
@@ -961,6 +966,67 @@ class VectorStoreService:
         except Exception as e:
             logger.error(f"Error getting file chunk counts: {e}")
             return {}
+
+
+class _ScrollRecord:
+    """What QdrantClient.scroll returns per point, as far as the reference's scripts read it: .id and .payload."""
+    __slots__ = ("id", "payload")
+
+    def __init__(self, pid, payload):
+        self.id, self.payload = pid, payload
+
+
+class _CollectionInfo:
+    __slots__ = ("points_count",)
+
+    def __init__(self, n):
+        self.points_count = n
+
+
+class QdrantScrollFacade:
+    """The two QdrantClient calls of scripts/sync_qdrant_stats.py:29-81 (the admin script that rebuilds SQLite's
+    indexed_files table from the vector store) over this backend's host-side payload store:
+    ``get_collection(name).points_count`` and ``scroll(collection_name, limit, offset, with_payload, with_vectors)``
+    -> ``(records, next_offset)``.  The script's only change is its client line:
+    ``client = get_vector_store().qdrant_facade()`` instead of ``QdrantClient(host=..., port=...)``.
+    Offsets are opaque to the caller (there: a point id; here: the next row), ``None`` ends the scan; deleted rows
+    are skipped; ``with_payload`` may be True or a list of keys."""
+
+    def __init__(self, store: "VectorStoreService"):
+        self._store = store
+
+    def _coll_for(self, collection_name):
+        if collection_name not in (None, self._store.collection_name):
+            raise ValueError(f"Collection {collection_name} not found")
+        return self._store._coll
+
+    def get_collection(self, collection_name=None):
+        coll = self._coll_for(collection_name)
+        with coll.lock:
+            return _CollectionInfo(coll.n_live)
+
+    def scroll(self, collection_name=None, scroll_filter=None, limit: int = 10, offset=None, with_payload=True, with_vectors=False):
+        if scroll_filter is not None or with_vectors:
+            raise NotImplementedError("the facade serves the unfiltered payload scan of sync_qdrant_stats.py")
+        coll = self._coll_for(collection_name)
+        out = []
+        with coll.lock:
+            r = int(offset or 0)
+            n = len(coll.ids)
+            while r < n and len(out) < limit:
+                pl = coll.payload[r]
+                if pl is not None:
+                    if with_payload is True:
+                        view = dict(pl)
+                    elif with_payload:
+                        view = {k: pl[k] for k in with_payload if k in pl}
+                    else:
+                        view = None
+                    out.append(_ScrollRecord(coll.ids[r], view))
+                r += 1
+            while r < n and coll.payload[r] is None:           # do not hand out an offset that only leads to deleted rows
+                r += 1
+            return out, (r if r < n else None)
 
 
 # Global singleton instance (reference :1019-1028)
