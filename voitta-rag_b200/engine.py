@@ -223,6 +223,18 @@ def flatten_sparse(sparse, B: int) -> FlatSparse:
         return sparse
     if len(sparse) != B:
         raise ValueError("one sparse query (or None) per dense query expected")
+    if B == 1:                                               # the reference's own call shape (mcp_server.py:474): no batch machinery
+        s0 = sparse[0]
+        n0 = 0 if s0 is None else len(s0[0])
+        if n0 != (0 if s0 is None else len(s0[1])):
+            raise ValueError("sparse indices/values length mismatch")
+        indptr = np.array([0, n0], dtype=np.int64)
+        if n0 == 0:
+            return FlatSparse(indptr, np.zeros(1, np.uint32), np.zeros(1, np.float64))
+        idx = np.asarray(s0[0], dtype=np.int64)
+        if idx.min() < 0 or idx.max() > 0xFFFFFFFF:
+            raise ValueError("sparse index out of uint32 range")
+        return FlatSparse(indptr, idx.astype(np.uint32), np.asarray(s0[1], dtype=np.float64))
     lens = np.fromiter((0 if s is None else len(s[0]) for s in sparse), np.int64, B)
     lens_v = np.fromiter((0 if s is None else len(s[1]) for s in sparse), np.int64, B)
     if (lens != lens_v).any():
