@@ -1127,3 +1127,47 @@ def test_full_size_cfg4_shard_properties():
             assert_same_ranking(got.branch(i, "dense"), one.branch(0, "dense"), rel_tol=1e-3, abs_tol=1e-3, what=f"K2T vs K1 q{i}")
     finally:
         ix.close()
+
+
+def test_row_selection_in_the_sharded_flow():
+    """Two row shards (row_base 0 / n/2) under one batch-wide filter, tensor-core path over each shard's compacted copy,
+    candidates merged as the multi-GPU layer does (vb_search_local x 2 -> vb_merge_fuse): the dense lists must equal
+    the single-index answer — a candidate's id is row_base + the shard row the selection recorded."""
+    import torch
+    from voitta_rag_b200 import engine
+    rng = np.random.RandomState(91)
+    n, dim, B, limit = 40_000, 128, 320, 10
+    dense = _data.bf16_round(rng.randn(n, dim).astype(np.float32))
+    scope = rng.randint(0, 64, size=n).astype(np.uint32)
+    modified = rng.randint(1420070400, 1767225600, size=n).astype(np.int64)
+    Q = _data.bf16_round(dense[rng.randint(0, n, size=B)] + 0.3 * rng.randn(B, dim).astype(np.float32))
+    bits = np.zeros(2, np.uint32); bits[0] = np.uint32(0x0F0F3C5A); bits[1] = np.uint32(0x00FF0011)
+    flt = engine.Filter(bits, 2, 1450000000, 1767225600)
+    fo = np.zeros(B, np.int32)
+    one = engine.Index(dim)
+    one.upsert(dense, None, scope, None, modified)
+    halves = [engine.Index(dim, row_base=0), engine.Index(dim, row_base=n // 2)]
+    halves[0].upsert(dense[:n // 2], None, scope[:n // 2], None, modified[:n // 2])
+    halves[1].upsert(dense[n // 2:], None, scope[n // 2:], None, modified[n // 2:])
+    try:
+        for ix in [one] + halves:
+            ix.set_option("dense_compact", 100)
+            ix.set_option("dense_compact_min_rows", 1024)
+        want = one.search_batch(Q, None, [flt], fo, limit=limit, fusion="dense", branches=True)
+        assert one.stats()["last_sel_used"] == 1
+        words = engine.Index.cand_block_words(B, limit)
+        dev = torch.device("cuda", 0)
+        gathered = torch.zeros(2 * words, dtype=torch.int64, device=dev)
+        for r, hx in enumerate(halves):
+            hx.search_local(gathered[r * words:].data_ptr(), Q, None, [flt], fo, limit=limit, kprime=limit, fusion="dense")
+            assert hx.stats()["last_sel_used"] == 1
+        torch.cuda.synchronize()
+        merged = halves[0].merge_fuse(gathered.data_ptr(), 2, Q, None, limit=limit, kprime=limit, fusion="dense", branches=True)
+        for i in range(B):
+            assert merged.branch(i, "dense") == want.branch(i, "dense"), f"sharded row selection q{i}"
+            assert merged.hits(i) == want.hits(i)
+        assert any(r >= n // 2 for i in range(B) for r, _ in merged.branch(i, "dense"))
+    finally:
+        one.close()
+        for hx in halves:
+            hx.close()
