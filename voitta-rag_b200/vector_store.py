@@ -742,9 +742,6 @@ class VectorStoreService:
         batch (``_Coalescer``)."""
         self.client
         coll = self._coll
-        search_filter = self._build_filter(
-            folder_filter, include_folders, exclude_folders, exclude_index_folders,
-            date_start=date_start, date_end=date_end, date_field=date_field, scope_key=scope_key)
         if _is_device_tensor(query_embedding):
             # additive: a CUDA tensor from the embedding model goes to the device search as it is (no .tolist() hop)
             if query_embedding.dim() != 1 or query_embedding.shape[0] != self.dimension:
@@ -753,6 +750,9 @@ class VectorStoreService:
                                      exclude_folders=exclude_folders, exclude_index_folders=exclude_index_folders,
                                      sparse_queries=[sparse_query], sparse_weight=sparse_weight, date_start=date_start,
                                      date_end=date_end, date_field=date_field)[0]
+        search_filter = self._build_filter(
+            folder_filter, include_folders, exclude_folders, exclude_index_folders,
+            date_start=date_start, date_end=date_end, date_field=date_field, scope_key=scope_key)
         q = np.asarray(query_embedding, dtype=np.float32)
         if q.ndim != 1 or q.shape[0] != self.dimension:
             raise ValueError(f"Vector dimension error: expected {self.dimension}, got {q.shape[-1] if q.ndim else 0}")
