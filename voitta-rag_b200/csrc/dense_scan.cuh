@@ -226,8 +226,11 @@ __device__ __noinline__ void vb_k1f_sort(uint64_t* s, uint32_t P) {
     __syncthreads();
 }
 
+#ifndef VB_K1F_MINBLOCKS
+#define VB_K1F_MINBLOCKS 1         // resident CTAs per SM asked of the compiler (A/B builds: -DVB_K1F_MINBLOCKS=6 / 8 cap the registers)
+#endif
 template <int NCH>
-__global__ void __launch_bounds__(VB_K1F_THREADS)
+__global__ void __launch_bounds__(VB_K1F_THREADS, VB_K1F_MINBLOCKS)
 vb_dense_scan1_kernel(const VbScan1Args a)
 {
     constexpr int ROWS = 4;
